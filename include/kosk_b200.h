@@ -1,0 +1,82 @@
+/* kosk_b200.h -- C ABI of the B200-native KOSK prover/verifier core (libkosk_b200.so).
+ *
+ * Drop-in boundary for the reference's KOSK API (reference kosk.hpp:13-24):
+ *   void kyber_verifiable_keygen(kyber_keypair *keypair, uint8_t *pi)   kosk.cpp:72-86
+ *   bool kyber_kosk_verify(const uint8_t *pi, const uint8_t *pk)        kosk.cpp:88-117
+ * The proof is the raw byte image of struct mpcith_proof (mlwe_prover.hpp:57-75, encode_mpcith_proof
+ * mlwe_prover.cpp:540-543); pk/sk are the Kyber byte strings of kyber_keygen (kosk.cpp:57-69).
+ * The reference is one process / one K per binary and pulls randomness from a global randombytes()
+ * (kyber/randombytes.c:43-57).  This ABI adds what a device library needs and the reference lacks:
+ * a context (device, tables, scratch), KYBER_K as a run-time argument, batch entry points, and an
+ * explicit 32-byte seed per proof in place of the global RNG:
+ *
+ *   KOSK counter-mode DRBG: the c-th randombytes(out, len) call made by kyber_verifiable_keygen
+ *   (c = 0, 1, ... in the reference's call order) returns
+ *   SHAKE256(seed[32] || LE32(c))[0:len].
+ *
+ * With that definition of randombytes linked into the reference, pk, sk and proof bytes are
+ * bit-identical to the reference's.  All functions return 0 on success, a negative KOSK_E_* code on
+ * error (kosk_b200_last_error() gives the message); there is no CPU fallback: without a CUDA device
+ * kosk_b200_create fails with KOSK_E_CUDA.
+ */
+#ifndef KOSK_B200_H
+#define KOSK_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct kosk_b200_ctx kosk_b200_ctx;
+
+enum { KOSK_OK = 0, KOSK_E_ARG = -1, KOSK_E_CUDA = -2, KOSK_E_NOMEM = -3, KOSK_E_UNSUPPORTED = -4 };
+
+/* sizes: KYBER_PUBLICKEYBYTES / KYBER_SECRETKEYBYTES (kyber/params.h:50-53), MPCITH_PROOF_SIZE (mlwe_prover.hpp:30) */
+size_t kosk_b200_pk_bytes(int kyber_k);
+size_t kosk_b200_sk_bytes(int kyber_k);
+size_t kosk_b200_proof_bytes(int kyber_k);
+const char *kosk_b200_last_error(void);
+const char *kosk_b200_version(void);
+
+/* Context: one per (device, KYBER_K).  max_chunk = proofs processed per kernel wave (scratch is sized for
+ * it; 0 = default).  Replaces the reference's compile-time -DKYBER_K (params.hpp:8-10). */
+int kosk_b200_create(kosk_b200_ctx **ctx, int kyber_k, int device, int max_chunk);
+void kosk_b200_destroy(kosk_b200_ctx *ctx);
+
+/* kyber_verifiable_keygen (kosk.hpp:19-20) with the RNG seed made explicit.  Host buffers. */
+int kosk_b200_verifiable_keygen(kosk_b200_ctx *ctx, const uint8_t seed[32], uint8_t *pk, uint8_t *sk, uint8_t *pi);
+/* kyber_kosk_verify (kosk.hpp:22-23): returns 1 = accept, 0 = reject, <0 = error.  Host buffers. */
+int kosk_b200_kosk_verify(kosk_b200_ctx *ctx, const uint8_t *pi, const uint8_t *pk);
+
+/* Batch mode, host buffers, densely packed: seeds[n][32], pk[n][pk_bytes], sk[n][sk_bytes], pi[n][proof_bytes].
+ * Host<->device copies happen inside (pinned buffers are used asynchronously). */
+int kosk_b200_prove_batch(kosk_b200_ctx *ctx, size_t n, const uint8_t *seeds, uint8_t *pk, uint8_t *sk, uint8_t *pi);
+int kosk_b200_verify_batch(kosk_b200_ctx *ctx, size_t n, const uint8_t *pi, const uint8_t *pk, uint8_t *ok);
+
+/* Batch mode, device-resident buffers (same packing), enqueued on `stream` (a cudaStream_t, NULL = default).
+ * Asynchronous: the caller synchronises the stream. */
+int kosk_b200_prove_batch_device(kosk_b200_ctx *ctx, size_t n, const uint8_t *d_seeds, uint8_t *d_pk, uint8_t *d_sk,
+                                 uint8_t *d_pi, void *stream);
+int kosk_b200_verify_batch_device(kosk_b200_ctx *ctx, size_t n, const uint8_t *d_pi, const uint8_t *d_pk,
+                                  uint8_t *d_ok, void *stream);
+
+/* Components (BASELINE config 5 microbenches, kernel-level parity tests).
+ * share_eval: recompute_share_secrets_ddeg (ss.cpp:76-99) on n rows: y[n][407] -> shares[n][1454]. Host buffers.
+ * sha3_256_rows: n independent SHA3-256 over rows of `len` bytes (len even): in[n][len] -> out[n][32].
+ * ntt_rows: poly_ntt (kyber/poly.c:261-265) on canonical residues, in place: a[n][256]. */
+int kosk_b200_share_eval(kosk_b200_ctx *ctx, size_t n, const uint16_t *y, uint16_t *shares);
+int kosk_b200_sha3_256_rows(kosk_b200_ctx *ctx, size_t n, size_t len, const uint8_t *in, uint8_t *out);
+int kosk_b200_ntt_rows(kosk_b200_ctx *ctx, size_t n, uint16_t *a);
+/* device-resident share_eval for benchmarking: d_y[n][416] (zero padded rows), d_planes[n][1456] */
+int kosk_b200_share_eval_device(kosk_b200_ctx *ctx, size_t n, const uint16_t *d_y, uint16_t *d_planes, void *stream);
+
+/* Introspection for tests/bench: number of kernels launched by this context so far; copy of an internal
+ * buffer of the last prove chunk ("alpha_pow", "I", "tcomm", "views", "Y", "planes") to host memory. */
+uint64_t kosk_b200_kernel_launches(const kosk_b200_ctx *ctx);
+int kosk_b200_debug_fetch(kosk_b200_ctx *ctx, const char *what, void *out, size_t bytes);
+int kosk_b200_sync(kosk_b200_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

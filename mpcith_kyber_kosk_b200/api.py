@@ -1,0 +1,213 @@
+"""Host-side mirror of the reference's KOSK interface (reference kosk.hpp:13-24) over the C ABI of
+libkosk_b200.so (include/kosk_b200.h).  Python is only the binding used by tests and bench.py; all
+field/hash arithmetic runs in the CUDA kernels.  There is no CPU fallback: loading fails loudly if the
+library is missing, and context creation fails if there is no CUDA device.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libkosk_b200.so")
+
+EXPORTS = [
+    "kosk_b200_pk_bytes", "kosk_b200_sk_bytes", "kosk_b200_proof_bytes", "kosk_b200_last_error", "kosk_b200_version",
+    "kosk_b200_create", "kosk_b200_destroy", "kosk_b200_verifiable_keygen", "kosk_b200_kosk_verify",
+    "kosk_b200_prove_batch", "kosk_b200_verify_batch", "kosk_b200_prove_batch_device", "kosk_b200_verify_batch_device",
+    "kosk_b200_share_eval", "kosk_b200_sha3_256_rows", "kosk_b200_ntt_rows", "kosk_b200_share_eval_device",
+    "kosk_b200_kernel_launches", "kosk_b200_debug_fetch", "kosk_b200_sync",
+]
+
+_lib = None
+
+
+class KoskError(RuntimeError):
+    pass
+
+
+def load_library(path=None):
+    """dlopen libkosk_b200.so and declare the prototypes of include/kosk_b200.h."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise KoskError(f"{path} not found: build it with `python -m mpcith_kyber_kosk_b200.build` (no CPU fallback exists)")
+    lib = ctypes.CDLL(path)
+    vp, sz, i32, u8p = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p
+    for n in ("kosk_b200_pk_bytes", "kosk_b200_sk_bytes", "kosk_b200_proof_bytes"):
+        getattr(lib, n).restype = sz
+        getattr(lib, n).argtypes = [i32]
+    lib.kosk_b200_last_error.restype = ctypes.c_char_p
+    lib.kosk_b200_version.restype = ctypes.c_char_p
+    lib.kosk_b200_create.argtypes = [ctypes.POINTER(vp), i32, i32, i32]
+    lib.kosk_b200_destroy.argtypes = [vp]
+    lib.kosk_b200_destroy.restype = None
+    lib.kosk_b200_verifiable_keygen.argtypes = [vp, u8p, u8p, u8p, u8p]
+    lib.kosk_b200_kosk_verify.argtypes = [vp, u8p, u8p]
+    lib.kosk_b200_prove_batch.argtypes = [vp, sz, u8p, u8p, u8p, u8p]
+    lib.kosk_b200_verify_batch.argtypes = [vp, sz, u8p, u8p, u8p]
+    lib.kosk_b200_prove_batch_device.argtypes = [vp, sz, u8p, u8p, u8p, u8p, vp]
+    lib.kosk_b200_verify_batch_device.argtypes = [vp, sz, u8p, u8p, u8p, vp]
+    lib.kosk_b200_share_eval.argtypes = [vp, sz, u8p, u8p]
+    lib.kosk_b200_sha3_256_rows.argtypes = [vp, sz, sz, u8p, u8p]
+    lib.kosk_b200_ntt_rows.argtypes = [vp, sz, u8p]
+    lib.kosk_b200_share_eval_device.argtypes = [vp, sz, u8p, u8p, vp]
+    lib.kosk_b200_kernel_launches.argtypes = [vp]
+    lib.kosk_b200_kernel_launches.restype = ctypes.c_uint64
+    lib.kosk_b200_debug_fetch.argtypes = [vp, ctypes.c_char_p, u8p, sz]
+    lib.kosk_b200_sync.argtypes = [vp]
+    if path == LIB_PATH:
+        _lib = lib
+    return lib
+
+
+def pk_bytes(k):
+    return load_library().kosk_b200_pk_bytes(k)
+
+
+def sk_bytes(k):
+    return load_library().kosk_b200_sk_bytes(k)
+
+
+def proof_bytes(k):
+    return load_library().kosk_b200_proof_bytes(k)
+
+
+def _ptr(a):
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+class KoskContext:
+    """One (device, KYBER_K) instance of the B200 KOSK core."""
+
+    def __init__(self, kyber_k=2, device=0, max_chunk=0):
+        self.lib = load_library()
+        self.k = kyber_k
+        self._h = ctypes.c_void_p()
+        rc = self.lib.kosk_b200_create(ctypes.byref(self._h), kyber_k, device, max_chunk)
+        if rc != 0:
+            raise KoskError(f"kosk_b200_create failed ({rc}): {self.lib.kosk_b200_last_error().decode()}")
+        self.pk_bytes, self.sk_bytes, self.proof_bytes = pk_bytes(kyber_k), sk_bytes(kyber_k), proof_bytes(kyber_k)
+
+    def close(self):
+        if self._h:
+            self.lib.kosk_b200_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc < 0:
+            raise KoskError(f"{what} failed ({rc}): {self.lib.kosk_b200_last_error().decode()}")
+        return rc
+
+    # ---- reference-shaped single calls (kosk.hpp:19-23) ----
+    def verifiable_keygen(self, seed):
+        pk, sk, pi = self.prove_batch(np.frombuffer(bytes(seed), dtype=np.uint8).reshape(1, 32))
+        return bytes(pk[0]), bytes(sk[0]), bytes(pi[0])
+
+    def kosk_verify(self, pi, pk):
+        a = np.frombuffer(bytes(pi), dtype=np.uint8)
+        b = np.frombuffer(bytes(pk), dtype=np.uint8)
+        if a.size != self.proof_bytes or b.size != self.pk_bytes:
+            raise KoskError("bad proof or pk length")
+        return self._check(self.lib.kosk_b200_kosk_verify(self._h, _ptr(a), _ptr(b)), "kosk_verify") == 1
+
+    # ---- batch, host buffers ----
+    def prove_batch(self, seeds, out=None):
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint8).reshape(-1, 32)
+        n = seeds.shape[0]
+        if out is None:
+            out = (np.empty((n, self.pk_bytes), np.uint8), np.empty((n, self.sk_bytes), np.uint8), np.empty((n, self.proof_bytes), np.uint8))
+        pk, sk, pi = out
+        self._check(self.lib.kosk_b200_prove_batch(self._h, n, _ptr(seeds), _ptr(pk), _ptr(sk), _ptr(pi)), "prove_batch")
+        return pk, sk, pi
+
+    def verify_batch(self, pi, pk):
+        pi = np.ascontiguousarray(pi, dtype=np.uint8).reshape(-1, self.proof_bytes)
+        pk = np.ascontiguousarray(pk, dtype=np.uint8).reshape(-1, self.pk_bytes)
+        n = pi.shape[0]
+        if pk.shape[0] != n:
+            raise KoskError("pi / pk batch mismatch")
+        ok = np.zeros(n, np.uint8)
+        self._check(self.lib.kosk_b200_verify_batch(self._h, n, _ptr(pi), _ptr(pk), _ptr(ok)), "verify_batch")
+        return ok.astype(bool)
+
+    # ---- batch, device pointers (integers), asynchronous on `stream` ----
+    def prove_batch_device(self, n, d_seeds, d_pk, d_sk, d_pi, stream=0):
+        vp = ctypes.c_void_p
+        self._check(self.lib.kosk_b200_prove_batch_device(self._h, n, vp(d_seeds), vp(d_pk), vp(d_sk), vp(d_pi), vp(stream)), "prove_batch_device")
+
+    def verify_batch_device(self, n, d_pi, d_pk, d_ok, stream=0):
+        vp = ctypes.c_void_p
+        self._check(self.lib.kosk_b200_verify_batch_device(self._h, n, vp(d_pi), vp(d_pk), vp(d_ok), vp(stream)), "verify_batch_device")
+
+    def share_eval_device(self, n, d_y, d_planes, stream=0):
+        vp = ctypes.c_void_p
+        self._check(self.lib.kosk_b200_share_eval_device(self._h, n, vp(d_y), vp(d_planes), vp(stream)), "share_eval_device")
+
+    # ---- components ----
+    def share_eval(self, y):
+        y = np.ascontiguousarray(y, dtype=np.uint16).reshape(-1, 407)
+        out = np.empty((y.shape[0], 1454), np.uint16)
+        self._check(self.lib.kosk_b200_share_eval(self._h, y.shape[0], _ptr(y), _ptr(out)), "share_eval")
+        return out
+
+    def sha3_256_rows(self, rows):
+        rows = np.ascontiguousarray(rows, dtype=np.uint8)
+        n, ln = rows.shape
+        out = np.empty((n, 32), np.uint8)
+        self._check(self.lib.kosk_b200_sha3_256_rows(self._h, n, ln, _ptr(rows), _ptr(out)), "sha3_256_rows")
+        return out
+
+    def ntt_rows(self, a):
+        a = np.array(a, dtype=np.uint16).reshape(-1, 256)
+        self._check(self.lib.kosk_b200_ntt_rows(self._h, a.shape[0], _ptr(a)), "ntt_rows")
+        return a
+
+    def kernel_launches(self):
+        return int(self.lib.kosk_b200_kernel_launches(self._h))
+
+    def debug_fetch(self, what, nbytes, dtype=np.uint8):
+        out = np.zeros(nbytes, np.uint8)
+        self._check(self.lib.kosk_b200_debug_fetch(self._h, what.encode(), _ptr(out), nbytes), "debug_fetch")
+        return out.view(dtype)
+
+    def sync(self):
+        self._check(self.lib.kosk_b200_sync(self._h), "sync")
+
+
+class kyber_keypair:
+    """Mirror of the reference's `kyber_keypair` (kosk.hpp:13-16)."""
+
+    def __init__(self, pk=b"", sk=b""):
+        self.pk, self.sk = pk, sk
+
+
+_default_ctx = {}
+
+
+def _ctx(k):
+    if k not in _default_ctx:
+        _default_ctx[k] = KoskContext(k)
+    return _default_ctx[k]
+
+
+def kyber_verifiable_keygen(kyber_k=2, seed=None):
+    """kyber_verifiable_keygen (kosk.cpp:72-86): returns (kyber_keypair, pi).  `seed` replaces the global
+    randombytes() stream (KOSK counter-mode DRBG); if None, 32 bytes from the OS RNG are used, as the
+    reference's randombytes does (kyber/randombytes.c:43-57)."""
+    seed = os.urandom(32) if seed is None else bytes(seed)
+    pk, sk, pi = _ctx(kyber_k).verifiable_keygen(seed)
+    return kyber_keypair(pk, sk), pi
+
+
+def kyber_kosk_verify(pi, pk, kyber_k=2):
+    """kyber_kosk_verify (kosk.cpp:88-117)."""
+    return _ctx(kyber_k).kosk_verify(pi, pk)

@@ -1,0 +1,418 @@
+// kosk_b200.cu -- context, host orchestration and the C ABI (include/kosk_b200.h) of the B200 KOSK core.
+// Host side is C++ because the reference's host side is C++ (kosk.cpp); nothing here runs field or hash
+// arithmetic on the CPU except the one-time construction of the Lagrange tables at context creation.
+#include "../../include/kosk_b200.h"
+#include "prove_kernels.cuh"
+#include "verify_kernels.cuh"
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+using namespace kosk;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) return fail(KOSK_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+// ---- one-time host table construction (the reference's missing utils/precomputed_kyber.c) ----
+static uint32_t h_pow(uint32_t b, uint32_t e) { uint32_t r = 1; b %= Q; while (e) { if (e & 1) r = r * b % Q; b = b * b % Q; e >>= 1; } return r; }
+// out[t*n + j] = l_j^{nodes}(targets[t]) mod q (barycentric form); nodes distinct mod q, no target equals a node
+static void h_lagrange(std::vector<uint16_t> &out, const std::vector<int> &nodes, const std::vector<int> &targets)
+{
+    const int n = (int)nodes.size(), nt = (int)targets.size();
+    std::vector<uint32_t> w(n);
+    for (int k = 0; k < n; k++) {
+        uint32_t d = 1;
+        for (int m = 0; m < n; m++) if (m != k) d = d * ((uint32_t)(nodes[k] - nodes[m] + 2 * Q) % Q) % Q;
+        w[k] = h_pow(d, Q - 2);
+    }
+    out.assign((size_t)n * nt, 0);
+    for (int t = 0; t < nt; t++) {
+        uint32_t full = 1;
+        for (int m = 0; m < n; m++) full = full * ((uint32_t)(targets[t] - nodes[m] + 2 * Q) % Q) % Q;
+        for (int k = 0; k < n; k++)
+            out[(size_t)t * n + k] = (uint16_t)(full * w[k] % Q * h_pow((uint32_t)(targets[t] - nodes[k] + 2 * Q) % Q, Q - 2) % Q);
+    }
+}
+
+struct kosk_b200_ctx {
+    int k = 0, device = 0, chunk = 0;
+    Slots sl; Layout L;
+    cudaStream_t stream = nullptr;         // internal stream of the host-buffer API
+    uint64_t launches = 0;
+    int lastB = 0;
+    // constant tables
+    int16_t *d_St = nullptr;               // [GE_NPAD][YLD] centered share table S (zero padded)
+    int16_t *d_R1 = nullptr, *d_R2 = nullptr; // verifier: centered recon tables [256][YLD], [256][VR2LD]
+    u16 *d_inv = nullptr;                  // [3329] inverses
+    int16_t *d_tab_commit = nullptr, *d_tab_view = nullptr;
+    // per-chunk scratch
+    ProveBufs pb{};
+    u8 *d_seeds = nullptr, *d_pk = nullptr, *d_sk = nullptr, *d_pi = nullptr, *d_ok = nullptr; // staging of the host API
+    VerifyBufs vb{};
+    void *h_pin = nullptr; size_t h_pin_bytes = 0;
+};
+
+static void ctx_free(kosk_b200_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    void *ptrs[] = {c->d_St, c->d_R1, c->d_R2, c->d_inv, c->d_tab_commit, c->d_tab_view, c->pb.Y, c->pb.SH, c->pb.BG, c->pb.TCR, c->pb.VWR,
+                    c->pb.PW, c->pb.AH, c->pb.SHAT, c->pb.I, c->pb.REST, c->d_seeds, c->d_pk, c->d_sk, c->d_pi, c->d_ok};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    verify_free(c->vb);
+    if (c->h_pin) cudaFreeHost(c->h_pin);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" {
+
+size_t kosk_b200_pk_bytes(int k) { return (k >= 2 && k <= 4) ? make_layout(k).pk_bytes : 0; }
+size_t kosk_b200_sk_bytes(int k) { return (k >= 2 && k <= 4) ? make_layout(k).sk_bytes : 0; }
+size_t kosk_b200_proof_bytes(int k) { return (k >= 2 && k <= 4) ? make_layout(k).proof_bytes : 0; }
+const char *kosk_b200_last_error(void) { return g_err.c_str(); }
+const char *kosk_b200_version(void) { return "kosk_b200 0.1 (sm_100a)"; }
+
+int kosk_b200_create(kosk_b200_ctx **out, int k, int device, int max_chunk)
+{
+    if (!out || k < 2 || k > 4) return fail(KOSK_E_ARG, "kyber_k must be 2, 3 or 4");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(KOSK_E_CUDA, "no CUDA device: the KOSK core has no CPU path");
+    if (device < 0 || device >= ndev) return fail(KOSK_E_ARG, "bad device index");
+    CU(cudaSetDevice(device));
+    kosk_b200_ctx *c = new kosk_b200_ctx;
+    c->k = k; c->device = device; c->sl = make_slots(k); c->L = make_layout(k);
+    c->chunk = max_chunk > 0 ? max_chunk : 1024;
+    if (c->chunk > 16384) c->chunk = 16384;
+    const Slots &sl = c->sl; const Layout &L = c->L;
+    const size_t B = (size_t)c->chunk;
+#define ALLOC(ptr, bytes) do { if (cudaMalloc((void **)&(ptr), (bytes)) != cudaSuccess) { ctx_free(c); return fail(KOSK_E_NOMEM, "cudaMalloc failed for " #ptr); } } while (0)
+    // ---- tables ----
+    {
+        uint16_t hz[128];
+        for (int i = 0; i < 128; i++) { int br = 0; for (int b = 0; b < 7; b++) br |= ((i >> b) & 1) << (6 - b); hz[i] = (uint16_t)h_pow(17, br); }
+        CU(cudaMemcpyToSymbol(c_zeta, hz, sizeof hz));
+        std::vector<int> nodes(D1), targets(NX);
+        for (int j = 0; j < D1; j++) nodes[j] = j;
+        for (int x = 0; x < NX; x++) targets[x] = x + D1;
+        std::vector<uint16_t> S; h_lagrange(S, nodes, targets);
+        std::vector<int16_t> St((size_t)GE_NPAD * YLD, 0);
+        for (int x = 0; x < NX; x++) for (int j = 0; j < D1; j++) St[(size_t)x * YLD + j] = (int16_t)gf_center(S[(size_t)x * D1 + j]);
+        ALLOC(c->d_St, St.size() * 2); CU(cudaMemcpy(c->d_St, St.data(), St.size() * 2, cudaMemcpyHostToDevice));
+        // verifier recon tables R1 (256 x 407 over nodes 256..662) and R2 (256 x 813 over nodes 256..1068)
+        std::vector<int> n1(D1), n2(D2), tg(NL);
+        for (int j = 0; j < D1; j++) n1[j] = 256 + j;
+        for (int j = 0; j < D2; j++) n2[j] = 256 + j;
+        for (int i = 0; i < NL; i++) tg[i] = i;
+        std::vector<uint16_t> R1, R2; h_lagrange(R1, n1, tg); h_lagrange(R2, n2, tg);
+        std::vector<int16_t> R1p((size_t)NL * YLD, 0), R2p((size_t)NL * VR2LD, 0);
+        for (int i = 0; i < NL; i++) { for (int j = 0; j < D1; j++) R1p[(size_t)i * YLD + j] = (int16_t)gf_center(R1[(size_t)i * D1 + j]);
+                                       for (int j = 0; j < D2; j++) R2p[(size_t)i * VR2LD + j] = (int16_t)gf_center(R2[(size_t)i * D2 + j]); }
+        ALLOC(c->d_R1, R1p.size() * 2); CU(cudaMemcpy(c->d_R1, R1p.data(), R1p.size() * 2, cudaMemcpyHostToDevice));
+        ALLOC(c->d_R2, R2p.size() * 2); CU(cudaMemcpy(c->d_R2, R2p.data(), R2p.size() * 2, cudaMemcpyHostToDevice));
+        std::vector<uint16_t> inv(Q, 0); for (int a = 1; a < Q; a++) inv[a] = (uint16_t)h_pow(a, Q - 2);
+        ALLOC(c->d_inv, Q * 2); CU(cudaMemcpy(c->d_inv, inv.data(), Q * 2, cudaMemcpyHostToDevice));
+        // hashed-record slot tables: commitment (mlwe_prover.cpp:117-126) and view (:398-443)
+        std::vector<int16_t> tc, tv;
+        for (int j = 0; j < k; j++) tc.push_back((int16_t)(sl.s0 + j));
+        for (int j = 0; j < k; j++) tc.push_back((int16_t)(sl.e0 + j));
+        for (int j = 0; j < sl.F; j++) tc.push_back((int16_t)(sl.f0 + j));
+        for (int j = 0; j < sl.F; j++) tc.push_back((int16_t)(sl.Tf0 + j));
+        for (int j = 0; j < 16; j++) tv.push_back((int16_t)(sl.TC0 + j));
+        tv.insert(tv.end(), tc.begin(), tc.end());
+        for (int j = 0; j < k; j++) tv.push_back((int16_t)(sl.B0 + j));
+        for (int j = 0; j < k; j++) tv.push_back((int16_t)(sl.G0 + j));
+        for (int j = 0; j < k; j++) tv.push_back((int16_t)(sl.SR0 + j));
+        for (int j = 0; j < k; j++) tv.push_back((int16_t)(sl.ER0 + j));
+        for (int j = 0; j < k; j++) {
+            for (int m = 0; m < sl.M; m++) tv.push_back((int16_t)(sl.zs0 + j * sl.M + m));
+            for (int m = 0; m < sl.M; m++) tv.push_back((int16_t)(sl.ze0 + j * sl.M + m));
+            for (int m = 0; m < sl.M; m++) tv.push_back((int16_t)(sl.US0 + j * sl.M + m));
+            for (int m = 0; m < sl.M; m++) tv.push_back((int16_t)(sl.UE0 + j * sl.M + m));
+        }
+        ALLOC(c->d_tab_commit, tc.size() * 2); CU(cudaMemcpy(c->d_tab_commit, tc.data(), tc.size() * 2, cudaMemcpyHostToDevice));
+        ALLOC(c->d_tab_view, tv.size() * 2); CU(cudaMemcpy(c->d_tab_view, tv.data(), tv.size() * 2, cudaMemcpyHostToDevice));
+    }
+    // ---- scratch ----
+    ALLOC(c->pb.Y, B * sl.n2 * YLD * 2);       CU(cudaMemset(c->pb.Y, 0, B * sl.n2 * YLD * 2));
+    ALLOC(c->pb.SH, B * sl.nslot * SLD * 2);   CU(cudaMemset(c->pb.SH, 0, B * sl.nslot * SLD * 2));
+    ALLOC(c->pb.BG, B * NP * 2 * MK * 2);
+    ALLOC(c->pb.TCR, B * TREE_BYTES); ALLOC(c->pb.VWR, B * TREE_BYTES);
+    ALLOC(c->pb.PW, B * (MK + 2 * k) * sl.F * 2);
+    ALLOC(c->pb.AH, B * k * k * 256 * 2); ALLOC(c->pb.SHAT, B * k * 256 * 2);
+    ALLOC(c->pb.I, B * NT * 2); ALLOC(c->pb.REST, B * NR * 2);
+    ALLOC(c->d_seeds, B * 32); ALLOC(c->d_pk, B * L.pk_bytes); ALLOC(c->d_sk, B * L.sk_bytes); ALLOC(c->d_pi, B * L.proof_bytes); ALLOC(c->d_ok, B);
+    if (verify_alloc(c->vb, k, c->chunk) != 0) { ctx_free(c); return fail(KOSK_E_NOMEM, "cudaMalloc failed for verifier scratch"); }
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU(cudaDeviceSynchronize());
+    *out = c;
+    return KOSK_OK;
+}
+
+void kosk_b200_destroy(kosk_b200_ctx *c) { ctx_free(c); }
+uint64_t kosk_b200_kernel_launches(const kosk_b200_ctx *c) { return c ? c->launches : 0; }
+int kosk_b200_sync(kosk_b200_ctx *c) { if (!c) return KOSK_E_ARG; CU(cudaSetDevice(c->device)); CU(cudaStreamSynchronize(c->stream)); return KOSK_OK; }
+
+}  // extern "C"
+
+// ---- launch sequence for one chunk of B proofs; everything stays on `st` ----
+static void launch_share_eval(kosk_b200_ctx *c, const u16 *Y, u16 *SH, int slot_lo, int rows, int y_slots, int sh_slots, int B, cudaStream_t st)
+{
+    GemmArgs g{};
+    g.A = Y; g.Bt = c->d_St; g.C = SH; g.lda = YLD; g.ldb = YLD; g.ldc = SLD;
+    g.mtotal = B * rows; g.ksteps = YLD / GE_BK; g.nvalid = NX; g.c_off = SOFF + NT + 1;
+    g.rpp = rows; g.slot_lo = slot_lo; g.a_slots = y_slots; g.c_slots = sh_slots; g.tail = 1;
+    c->launches += gf_gemm_launch<8>(g, GE_NPAD, 1, st);
+}
+
+template <int K>
+static int prove_chunk(kosk_b200_ctx *c, int B, const u8 *d_seeds, u8 *d_pk, u8 *d_sk, u8 *d_pi, cudaStream_t st)
+{
+    const Slots &sl = c->sl;
+    ProveBufs pb = c->pb;
+    pb.seeds = d_seeds; pb.pk = d_pk; pb.sk = d_sk; pb.pi = d_pi; pb.B = B;
+    constexpr int NCOMMIT = 2 * (K + MK + 2 * K + 1), ETA = (K == 2) ? 3 : 2;
+    constexpr int NVIEW = 16 + NCOMMIT + 4 * K + 8 * ETA * K;
+    const int ptiles = (NP + 127) / 128;
+    k_keygen<K><<<B, 128, 0, st>>>(pb);
+    k_expand_f<K><<<(B * sl.F + 63) / 64, 64, 0, st>>>(pb);
+    k_ntt_f<K><<<dim3(sl.F, B), 128, 0, st>>>(pb);
+    k_tails<K><<<(B * (sl.n1 + K) + 63) / 64, 64, 0, st>>>(pb);
+    launch_share_eval(c, pb.Y, pb.SH, 0, sl.n1, sl.n2, sl.nslot, B, st);
+    HashSrc hc{pb.SH, (long long)sl.nslot * SLD, 1, SLD, SOFF, c->d_tab_commit, nullptr, 0};
+    k_hash_records<NCOMMIT><<<dim3(ptiles, B), 128, 0, st>>>(hc, pb.TCR, pb.SH, sl.nslot, sl.TC0);
+    k_fs1<K><<<(B + 31) / 32, 32, 0, st>>>(pb.TCR, pb.PW, B);
+    k_eval<K><<<dim3(ptiles, B), 256, 0, st>>>(pb);
+    k_open<K><<<B, 128, 0, st>>>(pb);
+    launch_share_eval(c, pb.Y, pb.SH, sl.n1, 4 * K, sl.n2, sl.nslot, B, st);
+    k_derive<K><<<dim3(ptiles, B), 128, 0, st>>>(pb);
+    HashSrc hv{pb.SH, (long long)sl.nslot * SLD, 1, SLD, SOFF, c->d_tab_view, nullptr, 0};
+    k_hash_records<NVIEW><<<dim3(ptiles, B), 128, 0, st>>>(hv, pb.VWR, nullptr, 0, 0);
+    k_fs2<<<(B + 31) / 32, 32, 0, st>>>(pb.VWR, pb.I, pb.REST, B);
+    k_assemble<K><<<dim3((NT + 31) / 32 + (NR + 31) / 32, B), 128, 0, st>>>(pb);
+    c->launches += 12;
+    c->lastB = B;
+    CU(cudaGetLastError());
+    return KOSK_OK;
+}
+
+static int prove_chunk_k(kosk_b200_ctx *c, int B, const u8 *s, u8 *pk, u8 *sk, u8 *pi, cudaStream_t st)
+{
+    switch (c->k) {
+    case 2: return prove_chunk<2>(c, B, s, pk, sk, pi, st);
+    case 3: return prove_chunk<3>(c, B, s, pk, sk, pi, st);
+    default: return prove_chunk<4>(c, B, s, pk, sk, pi, st);
+    }
+}
+
+// ---- generic component kernels ----
+__global__ void __launch_bounds__(128) k_ntt_rows(u16 *a)
+{
+    __shared__ u16 p[256];
+    u16 *row = a + (size_t)blockIdx.x * 256;
+    const int tid = threadIdx.x;
+    p[tid] = row[tid]; p[tid + 128] = row[tid + 128];
+    __syncthreads();
+    ntt256_block(p, tid);
+    row[tid] = p[tid]; row[tid + 128] = p[tid + 128];
+}
+
+__global__ void __launch_bounds__(64) k_sha3_rows(const u8 *in, u8 *out, size_t n, size_t len)
+{
+    const size_t r = (size_t)blockIdx.x * 64 + threadIdx.x;
+    if (r >= n) return;
+    const u8 *src = in + r * len;
+    uint64_t a[25]; keccak_zero(a);
+    size_t off = 0;
+    while (len - off >= 136) {
+#pragma unroll
+        for (int l = 0; l < 17; l++) { uint64_t w = 0; for (int i = 0; i < 8; i++) w |= (uint64_t)src[off + 8 * l + i] << (8 * i); a[l] ^= w; }
+        keccak_f1600(a);
+        off += 136;
+    }
+    uint64_t last[17];
+    for (int l = 0; l < 17; l++) last[l] = 0;
+    const int rem = (int)(len - off);
+    for (int i = 0; i < rem; i++) last[i >> 3] |= (uint64_t)src[off + i] << (8 * (i & 7));
+    last[rem >> 3] |= 0x06ULL << (8 * (rem & 7));
+    last[16] |= 0x8000000000000000ULL;
+#pragma unroll
+    for (int l = 0; l < 17; l++) a[l] ^= last[l];
+    keccak_f1600(a);
+    uint64_t *o = reinterpret_cast<uint64_t *>(out + r * 32);
+    o[0] = a[0]; o[1] = a[1]; o[2] = a[2]; o[3] = a[3];
+}
+
+extern "C" {
+
+int kosk_b200_prove_batch_device(kosk_b200_ctx *c, size_t n, const uint8_t *d_seeds, uint8_t *d_pk, uint8_t *d_sk, uint8_t *d_pi, void *stream)
+{
+    if (!c || !d_seeds || !d_pk || !d_sk || !d_pi) return fail(KOSK_E_ARG, "null argument");
+    CU(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const Layout &L = c->L;
+    for (size_t o = 0; o < n; o += c->chunk) {
+        const int B = (int)std::min<size_t>(c->chunk, n - o);
+        int rc = prove_chunk_k(c, B, d_seeds + 32 * o, d_pk + L.pk_bytes * o, d_sk + L.sk_bytes * o, d_pi + L.proof_bytes * o, st);
+        if (rc) return rc;
+    }
+    return KOSK_OK;
+}
+
+int kosk_b200_prove_batch(kosk_b200_ctx *c, size_t n, const uint8_t *seeds, uint8_t *pk, uint8_t *sk, uint8_t *pi)
+{
+    if (!c || !seeds || !pk || !sk || !pi) return fail(KOSK_E_ARG, "null argument");
+    CU(cudaSetDevice(c->device));
+    const Layout &L = c->L;
+    cudaStream_t st = c->stream;
+    for (size_t o = 0; o < n; o += c->chunk) {
+        const int B = (int)std::min<size_t>(c->chunk, n - o);
+        CU(cudaMemcpyAsync(c->d_seeds, seeds + 32 * o, 32 * (size_t)B, cudaMemcpyHostToDevice, st));
+        int rc = prove_chunk_k(c, B, c->d_seeds, c->d_pk, c->d_sk, c->d_pi, st);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(pk + L.pk_bytes * o, c->d_pk, L.pk_bytes * (size_t)B, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(sk + L.sk_bytes * o, c->d_sk, L.sk_bytes * (size_t)B, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(pi + L.proof_bytes * o, c->d_pi, L.proof_bytes * (size_t)B, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return KOSK_OK;
+}
+
+int kosk_b200_verifiable_keygen(kosk_b200_ctx *c, const uint8_t seed[32], uint8_t *pk, uint8_t *sk, uint8_t *pi)
+{
+    return kosk_b200_prove_batch(c, 1, seed, pk, sk, pi);
+}
+
+int kosk_b200_verify_batch_device(kosk_b200_ctx *c, size_t n, const uint8_t *d_pi, const uint8_t *d_pk, uint8_t *d_ok, void *stream)
+{
+    if (!c || !d_pi || !d_pk || !d_ok) return fail(KOSK_E_ARG, "null argument");
+    CU(cudaSetDevice(c->device));
+    const Layout &L = c->L;
+    for (size_t o = 0; o < n; o += c->chunk) {
+        const int B = (int)std::min<size_t>(c->chunk, n - o);
+        VerifyTables vt{c->d_St, c->d_R1, c->d_R2, c->d_inv};
+        int nl = verify_chunk(c->k, c->vb, vt, B, d_pi + L.proof_bytes * o, d_pk + L.pk_bytes * o, d_ok + o, (cudaStream_t)stream);
+        if (nl < 0) return fail(KOSK_E_CUDA, "verify launch failed");
+        c->launches += nl;
+        CU(cudaGetLastError());
+    }
+    return KOSK_OK;
+}
+
+int kosk_b200_verify_batch(kosk_b200_ctx *c, size_t n, const uint8_t *pi, const uint8_t *pk, uint8_t *ok)
+{
+    if (!c || !pi || !pk || !ok) return fail(KOSK_E_ARG, "null argument");
+    CU(cudaSetDevice(c->device));
+    const Layout &L = c->L;
+    cudaStream_t st = c->stream;
+    for (size_t o = 0; o < n; o += c->chunk) {
+        const int B = (int)std::min<size_t>(c->chunk, n - o);
+        CU(cudaMemcpyAsync(c->d_pi, pi + L.proof_bytes * o, L.proof_bytes * (size_t)B, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(c->d_pk, pk + L.pk_bytes * o, L.pk_bytes * (size_t)B, cudaMemcpyHostToDevice, st));
+        int rc = kosk_b200_verify_batch_device(c, (size_t)B, c->d_pi, c->d_pk, c->d_ok, st);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(ok + o, c->d_ok, (size_t)B, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return KOSK_OK;
+}
+
+int kosk_b200_kosk_verify(kosk_b200_ctx *c, const uint8_t *pi, const uint8_t *pk)
+{
+    uint8_t ok = 0;
+    int rc = kosk_b200_verify_batch(c, 1, pi, pk, &ok);
+    return rc ? rc : (int)ok;
+}
+
+int kosk_b200_share_eval_device(kosk_b200_ctx *c, size_t n, const uint16_t *d_y, uint16_t *d_planes, void *stream)
+{
+    if (!c || !d_y || !d_planes) return fail(KOSK_E_ARG, "null argument");
+    CU(cudaSetDevice(c->device));
+    for (size_t o = 0; o < n; o += (1u << 22)) {
+        const int m = (int)std::min<size_t>(1u << 22, n - o);
+        launch_share_eval(c, d_y + o * YLD, d_planes + o * SLD, 0, m, m, m, 1, (cudaStream_t)stream);
+    }
+    CU(cudaGetLastError());
+    return KOSK_OK;
+}
+
+int kosk_b200_share_eval(kosk_b200_ctx *c, size_t n, const uint16_t *y, uint16_t *shares)
+{
+    if (!c || !y || !shares) return fail(KOSK_E_ARG, "null argument");
+    CU(cudaSetDevice(c->device));
+    u16 *dy = nullptr, *dp = nullptr;
+    std::vector<u16> hy(n * YLD, 0), hp(n * SLD);
+    for (size_t r = 0; r < n; r++) memcpy(&hy[r * YLD], y + r * D1, D1 * 2);
+    CU(cudaMalloc(&dy, hy.size() * 2 + 16)); CU(cudaMalloc(&dp, hp.size() * 2 + 16));
+    CU(cudaMemcpy(dy, hy.data(), hy.size() * 2, cudaMemcpyHostToDevice));
+    int rc = kosk_b200_share_eval_device(c, n, dy, dp, c->stream);
+    if (!rc) { cudaError_t e = cudaStreamSynchronize(c->stream); if (e != cudaSuccess) rc = fail(KOSK_E_CUDA, cudaGetErrorString(e)); }
+    if (!rc) { cudaError_t e = cudaMemcpy(hp.data(), dp, hp.size() * 2, cudaMemcpyDeviceToHost); if (e != cudaSuccess) rc = fail(KOSK_E_CUDA, cudaGetErrorString(e)); }
+    cudaFree(dy); cudaFree(dp);
+    if (rc) return rc;
+    for (size_t r = 0; r < n; r++) memcpy(shares + r * NP, &hp[r * SLD + SOFF], NP * 2);
+    return KOSK_OK;
+}
+
+int kosk_b200_sha3_256_rows(kosk_b200_ctx *c, size_t n, size_t len, const uint8_t *in, uint8_t *out)
+{
+    if (!c || !in || !out || n == 0) return fail(KOSK_E_ARG, "bad argument");
+    CU(cudaSetDevice(c->device));
+    u8 *di = nullptr, *dout = nullptr;
+    CU(cudaMalloc(&di, n * len + 16)); CU(cudaMalloc(&dout, n * 32));
+    CU(cudaMemcpy(di, in, n * len, cudaMemcpyHostToDevice));
+    k_sha3_rows<<<(unsigned)((n + 63) / 64), 64, 0, c->stream>>>(di, dout, n, len); c->launches++;
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e == cudaSuccess) e = cudaMemcpy(out, dout, n * 32, cudaMemcpyDeviceToHost);
+    cudaFree(di); cudaFree(dout);
+    if (e != cudaSuccess) return fail(KOSK_E_CUDA, cudaGetErrorString(e));
+    return KOSK_OK;
+}
+
+int kosk_b200_ntt_rows(kosk_b200_ctx *c, size_t n, uint16_t *a)
+{
+    if (!c || !a || n == 0) return fail(KOSK_E_ARG, "bad argument");
+    CU(cudaSetDevice(c->device));
+    u16 *d = nullptr;
+    CU(cudaMalloc(&d, n * 512));
+    CU(cudaMemcpy(d, a, n * 512, cudaMemcpyHostToDevice));
+    k_ntt_rows<<<(unsigned)n, 128, 0, c->stream>>>(d); c->launches++;
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e == cudaSuccess) e = cudaMemcpy(a, d, n * 512, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(KOSK_E_CUDA, cudaGetErrorString(e));
+    return KOSK_OK;
+}
+
+int kosk_b200_debug_fetch(kosk_b200_ctx *c, const char *what, void *out, size_t bytes)
+{
+    if (!c || !what || !out) return fail(KOSK_E_ARG, "null argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaDeviceSynchronize());
+    const Slots &sl = c->sl;
+    const size_t B = (size_t)c->chunk;
+    const void *src = nullptr; size_t avail = 0;
+    std::string w(what);
+    if (w == "alpha_pow") { src = c->pb.PW; avail = B * (MK + 2 * c->k) * sl.F * 2; }
+    else if (w == "I") { src = c->pb.I; avail = B * NT * 2; }
+    else if (w == "rest") { src = c->pb.REST; avail = B * NR * 2; }
+    else if (w == "tcomm") { src = c->pb.TCR; avail = B * TREE_BYTES; }
+    else if (w == "views") { src = c->pb.VWR; avail = B * TREE_BYTES; }
+    else if (w == "Y") { src = c->pb.Y; avail = B * sl.n2 * YLD * 2; }
+    else if (w == "planes") { src = c->pb.SH; avail = B * sl.nslot * SLD * 2; }
+    else if (w == "bg") { src = c->pb.BG; avail = B * NP * 2 * MK * 2; }
+    else if (w == "vflags") { src = c->vb.flags; avail = B * 4; }
+    else return fail(KOSK_E_ARG, "unknown buffer name");
+    CU(cudaMemcpy(out, src, std::min(bytes, avail), cudaMemcpyDeviceToHost));
+    return KOSK_OK;
+}
+
+}  // extern "C"

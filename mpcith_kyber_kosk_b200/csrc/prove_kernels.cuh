@@ -1,0 +1,609 @@
+// prove_kernels.cuh -- sm_100a kernels of the KOSK prover (kyber_verifiable_keygen, reference kosk.cpp:72-86).
+// One launch processes a whole chunk of B independent proofs; per-proof state lives in HBM as
+//   Y   [B][n2][YLD]      u16  sharing inputs: 256 packed secrets | 151 tail randoms   (ss.cpp:13-20)
+//   SH  [B][nslot][SLD]   u16  planes: one row of 1454 party shares per slot           (share_vec.share_y)
+//   BG  [B][NP][140]      u16  beta[70] | gamma[70] per party                          (mpcith_vp_state)
+//   TCR [B][NP][32]       u8   party commitments, VWR the same for view hashes
+// Parties are the contiguous (coalesced) axis of every per-party kernel.
+#pragma once
+#include "keccak.cuh"
+#include "gf_gemm.cuh"
+
+namespace kosk {
+
+__constant__ u16 c_zeta[128];   // 17^brv7(i) mod q: plain-residue form of kyber/ntt.c:39-56
+
+struct ProveBufs {
+    const u8 *seeds;   // [B][32]
+    u16 *Y, *SH, *BG;
+    u8 *TCR, *VWR;
+    u16 *PW;           // [B][NA][F] powers of the FS-1 challenges alpha (mlwe_prover.cpp:144-153)
+    u16 *AH;           // [B][k*k][256] matrix A-hat (NTT domain), row-major A[i][j]
+    u16 *SHAT;         // [B][k][256]   s-hat
+    u16 *I, *REST;     // [B][150], [B][1304]
+    u8 *pk, *sk, *pi;  // outputs
+    int B;
+};
+
+__device__ __forceinline__ u16 *yrow(const ProveBufs &pb, const Slots &sl, int b, int slot) { return pb.Y + ((size_t)b * sl.n2 + slot) * YLD; }
+__device__ __forceinline__ u16 *plane(const ProveBufs &pb, const Slots &sl, int b, int slot) { return pb.SH + ((size_t)b * sl.nslot + slot) * SLD + SOFF; }
+
+// ---------------------------------------------------------------------------------------------
+// 256-point Kyber NTT on canonical residues, 128 threads, data in shared memory.
+// Reference: kyber/ntt.c:80-95 + poly_reduce (poly.c:261-265).
+__device__ __forceinline__ void ntt256_block(u16 *p, int tid)
+{
+    for (int len = 128; len >= 2; len >>= 1) {
+        int grp = tid / len, j = grp * 2 * len + (tid % len);
+        uint32_t z = c_zeta[128 / len + grp];
+        uint32_t t = gf_mul(z, p[j + len]), u = p[j];
+        p[j + len] = (u16)gf_sub(u, t);
+        p[j] = (u16)gf_add(u, t);
+        __syncthreads();
+    }
+}
+// pairwise product in Z_q[X]/(X^2 - zeta): kyber/ntt.c:139-146 with the signs of poly.c:290-297; plain residues
+__device__ __forceinline__ void basemul_pair(uint32_t &r0, uint32_t &r1, uint32_t a0, uint32_t a1, uint32_t b0, uint32_t b1, int pair)
+{
+    uint32_t z = c_zeta[64 + (pair >> 1)];
+    if (pair & 1) z = gf_sub(0, z);
+    r0 = gf_add(gf_mul(gf_mul(a1, b1), z), gf_mul(a0, b0));
+    r1 = gf_add(gf_mul(a0, b1), gf_mul(a1, b0));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Keygen: kosk.cpp:4-70 (gen_matrix indcpa.c:168-193, poly_getnoise_eta1 poly.c:225-230, cbd.c:58-107,
+// polyvec_ntt, basemul_acc + tomont, tobytes poly.c:124-139).  One CTA of 128 threads per proof.
+// Also emits the secrets of the s/e sharings and of the range-proof products z_j (mlwe_prover.cpp:338-372:
+// recon_secrets_2ddeg of a product sharing is the pointwise product of the secrets).
+template <int K>
+__global__ void __launch_bounds__(128) k_keygen(ProveBufs pb)
+{
+    constexpr int ETA = (K == 2) ? 3 : 2, M = 2 * ETA;
+    const Slots sl = make_slots(K);
+    const Layout L = make_layout(K);
+    const int b = blockIdx.x, tid = threadIdx.x;
+    __shared__ u16 sA[K * K][256];
+    __shared__ u16 sS[K][256], sE[K][256], sSh[K][256], sEh[K][256], sT[K][256];
+    __shared__ uint64_t sSeed[8];
+    __shared__ u8 sPk[384 * K + 32];
+
+    if (tid == 0) {
+        uint64_t sd[4], a[25];
+        const uint64_t *gs = reinterpret_cast<const uint64_t *>(pb.seeds + 32 * (size_t)b);
+        for (int i = 0; i < 4; i++) sd[i] = gs[i];
+        drbg_begin(a, sd, 0);                       // randombytes(buf, 64): only bytes 0..31 are used (kosk.cpp:12-14)
+        uint64_t c0 = a[0], c1 = a[1], c2 = a[2], c3 = a[3];
+        keccak_zero(a);                             // sha3_512(coins || K): rate 72
+        a[0] = c0; a[1] = c1; a[2] = c2; a[3] = c3; a[4] = (uint64_t)K | (0x06ULL << 8); a[8] = 0x8000000000000000ULL;
+        keccak_f1600(a);
+        for (int i = 0; i < 8; i++) sSeed[i] = a[i];
+    }
+    __syncthreads();
+    if (tid < K * K) {                              // A[i][j] <- SHAKE128(publicseed || j || i), 12-bit rejection
+        const int i = tid / K, j = tid % K;
+        ByteSponge sp; sp.init(168);
+        sp.absorb(reinterpret_cast<const u8 *>(sSeed), 32);
+        u8 ji[2] = {(u8)j, (u8)i}; sp.absorb(ji, 2); sp.finalize(0x1F);
+        int ctr = 0;
+        while (ctr < 256) {
+            uint32_t b0 = sp.next(), b1 = sp.next(), b2 = sp.next();
+            uint32_t v0 = (b0 | (b1 << 8)) & 0xFFF, v1 = ((b1 >> 4) | (b2 << 4)) & 0xFFF;
+            if (v0 < (uint32_t)Q) sA[tid][ctr++] = (u16)v0;
+            if (ctr < 256 && v1 < (uint32_t)Q) sA[tid][ctr++] = (u16)v1;
+        }
+    } else if (tid < K * K + 2 * K) {               // noise: PRF(noiseseed, nonce) -> CBD_eta
+        const int idx = tid - K * K;
+        u16 *dst = idx < K ? sS[idx] : sE[idx - K];
+        ByteSponge sp; sp.init(136);
+        sp.absorb(reinterpret_cast<const u8 *>(sSeed + 4), 32);
+        u8 nonce = (u8)idx; sp.absorb(&nonce, 1); sp.finalize(0x1F);
+        if (ETA == 2) {
+            for (int i = 0; i < 32; i++) {
+                uint32_t t = sp.next(); t |= (uint32_t)sp.next() << 8; t |= (uint32_t)sp.next() << 16; t |= (uint32_t)sp.next() << 24;
+                uint32_t d = (t & 0x55555555u) + ((t >> 1) & 0x55555555u);
+                for (int j = 0; j < 8; j++) { int x = (int)((d >> (4 * j)) & 3) - (int)((d >> (4 * j + 2)) & 3); dst[8 * i + j] = (u16)(x < 0 ? x + Q : x); }
+            }
+        } else {
+            for (int i = 0; i < 64; i++) {
+                uint32_t t = sp.next(); t |= (uint32_t)sp.next() << 8; t |= (uint32_t)sp.next() << 16;
+                uint32_t d = (t & 0x249249u) + ((t >> 1) & 0x249249u) + ((t >> 2) & 0x249249u);
+                for (int j = 0; j < 4; j++) { int x = (int)((d >> (6 * j)) & 7) - (int)((d >> (6 * j + 3)) & 7); dst[4 * i + j] = (u16)(x < 0 ? x + Q : x); }
+            }
+        }
+    }
+    __syncthreads();
+    // secrets of [s_i], [e_i] and of the 2*eta range-proof products z_j = prod_{m<=j+1} (x - eta_m)
+    for (int c = tid; c < 256; c += 128)
+        for (int i = 0; i < K; i++)
+            for (int w = 0; w < 2; w++) {
+                uint32_t x = w ? sE[i][c] : sS[i][c];
+                yrow(pb, sl, b, (w ? sl.e0 : sl.s0) + i)[c] = (u16)x;
+                uint32_t z = gf_sub(x, gf_sub(0, ETA));             // x - (-eta)
+                for (int j = 0; j < M; j++) {
+                    uint32_t eta_m = (j + 1 >= ETA) ? (uint32_t)(j + 1 - ETA) : (uint32_t)(Q + j + 1 - ETA);
+                    z = gf_mul(z, gf_sub(x, eta_m));
+                    yrow(pb, sl, b, (w ? sl.ze0 : sl.zs0) + i * M + j)[c] = (u16)z;
+                }
+            }
+    for (int c = tid; c < 256; c += 128)
+        for (int i = 0; i < K; i++) { sSh[i][c] = sS[i][c]; sEh[i][c] = sE[i][c]; }
+    __syncthreads();
+    for (int i = 0; i < K; i++) { ntt256_block(sSh[i], tid); ntt256_block(sEh[i], tid); }
+    // t-hat = A-hat o s-hat + e-hat
+    for (int i = 0; i < K; i++) {
+        uint32_t a0 = 0, a1 = 0;
+        for (int j = 0; j < K; j++) {
+            uint32_t r0, r1;
+            basemul_pair(r0, r1, sA[i * K + j][2 * tid], sA[i * K + j][2 * tid + 1], sSh[j][2 * tid], sSh[j][2 * tid + 1], tid);
+            a0 = gf_add(a0, r0); a1 = gf_add(a1, r1);
+        }
+        sT[i][2 * tid] = (u16)gf_add(a0, sEh[i][2 * tid]); sT[i][2 * tid + 1] = (u16)gf_add(a1, sEh[i][2 * tid + 1]);
+    }
+    __syncthreads();
+    // pack pk = tobytes(t-hat) || publicseed ; sk = tobytes(s-hat) || pk || SHA3-256(pk) || noiseseed (kosk.cpp:57-69)
+    u8 *pk = pb.pk + L.pk_bytes * (size_t)b, *sk = pb.sk + L.sk_bytes * (size_t)b;
+    for (int i = 0; i < K; i++) {
+        uint32_t t0 = sT[i][2 * tid], t1 = sT[i][2 * tid + 1];
+        u8 *d = sPk + 384 * i + 3 * tid;
+        d[0] = (u8)t0; d[1] = (u8)((t0 >> 8) | (t1 << 4)); d[2] = (u8)(t1 >> 4);
+        t0 = sSh[i][2 * tid]; t1 = sSh[i][2 * tid + 1];
+        u8 *e = sk + 384 * i + 3 * tid;
+        e[0] = (u8)t0; e[1] = (u8)((t0 >> 8) | (t1 << 4)); e[2] = (u8)(t1 >> 4);
+    }
+    if (tid < 32) sPk[384 * K + tid] = reinterpret_cast<const u8 *>(sSeed)[tid];
+    __syncthreads();
+    for (int i = tid; i < 384 * K + 32; i += 128) { pk[i] = sPk[i]; sk[384 * K + i] = sPk[i]; }
+    if (tid < 32) sk[L.sk_bytes - 32 + tid] = reinterpret_cast<const u8 *>(sSeed + 4)[tid];
+    if (tid == 0) {
+        ByteSponge sp; sp.init(136); sp.absorb(sPk, 384 * K + 32); sp.finalize(0x06);
+        for (int i = 0; i < 32; i++) sk[L.sk_bytes - 64 + i] = sp.next();
+    }
+    // keep A-hat and s-hat for the online phase
+    for (int i = tid; i < K * K * 256; i += 128) pb.AH[(size_t)b * K * K * 256 + i] = (&sA[0][0])[i];
+    for (int i = tid; i < K * 256; i += 128) pb.SHAT[(size_t)b * K * 256 + i] = (&sSh[0][0])[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// prepare_randomness, PRF part (mlwe_prover.cpp:8-14): seed_i = randombytes(32); f_i = BE16(SHAKE256(seed_i||i)[0:512]) mod q.
+// One thread per (proof, i); five permutations each.
+template <int K>
+__global__ void __launch_bounds__(64) k_expand_f(ProveBufs pb)
+{
+    const Slots sl = make_slots(K);
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= pb.B * sl.F) return;
+    const int b = gid / sl.F, i = gid % sl.F;
+    uint64_t sd[4], a[25];
+    const uint64_t *gs = reinterpret_cast<const uint64_t *>(pb.seeds + 32 * (size_t)b);
+#pragma unroll
+    for (int w = 0; w < 4; w++) sd[w] = gs[w];
+    drbg_begin(a, sd, sl.c_seed0 + i);
+    uint64_t key[4] = {a[0], a[1], a[2], a[3]};
+    prf_begin(a, key, (u8)i);
+    u16 *dst = yrow(pb, sl, b, sl.f0 + i);
+#pragma unroll 1
+    for (int blk = 0; blk < 4; blk++) {             // 512 bytes = 3 x 136 + 104
+#pragma unroll
+        for (int v = 0; v < 68; v++) {
+            if (blk * 68 + v < 256) dst[blk * 68 + v] = (u16)(lane_be16(a[v >> 2], v & 3) % (uint32_t)Q);
+        }
+        if (blk < 3) keccak_f1600(a);
+    }
+}
+
+// NTT_f_i = NTT(f_i) (mlwe_prover.cpp:17-26): one CTA per (proof, i)
+template <int K>
+__global__ void __launch_bounds__(128) k_ntt_f(ProveBufs pb)
+{
+    const Slots sl = make_slots(K);
+    const int b = blockIdx.y, i = blockIdx.x, tid = threadIdx.x;
+    __shared__ u16 p[256];
+    const u16 *src = yrow(pb, sl, b, sl.f0 + i);
+    p[tid] = src[tid]; p[tid + 128] = src[tid + 128];
+    __syncthreads();
+    ntt256_block(p, tid);
+    u16 *dst = yrow(pb, sl, b, sl.Tf0 + i);
+    dst[tid] = p[tid]; dst[tid + 128] = p[tid + 128];
+}
+
+// The 151 tail randoms of every fresh sharing: randombytes(302) -> BE16 mod q (ss.cpp:4-11), in the reference's
+// call order.  One thread per (proof, sharing); also writes the constant secrets of the
+// eta sharings (mlwe_prover.cpp:42-48) and zero-fills the row padding.
+template <int K>
+__global__ void __launch_bounds__(64) k_tails(ProveBufs pb)
+{
+    const Slots sl = make_slots(K);
+    const int nfresh = sl.n1 + K;                   // all challenge-independent sharings + [A s]
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= pb.B * nfresh) return;
+    const int b = gid / nfresh, idx = gid % nfresh;
+    int slot, call;
+    if (idx < sl.n1) {
+        slot = idx;
+        if (slot < sl.Tf0) call = sl.c_f0 + 2 * (slot - sl.f0);
+        else if (slot < sl.seta0) call = sl.c_f0 + 2 * (slot - sl.Tf0) + 1;
+        else if (slot < sl.eeta0) call = sl.c_eta0 + 2 * (slot - sl.seta0);
+        else if (slot < sl.s0) call = sl.c_eta0 + 2 * (slot - sl.eeta0) + 1;
+        else if (slot < sl.e0) call = sl.c_se0 + 2 * (slot - sl.s0);
+        else if (slot < sl.zs0) call = sl.c_se0 + 2 * (slot - sl.e0) + 1;
+        else if (slot < sl.ze0) call = sl.c_z0 + 2 * (slot - sl.zs0);
+        else call = sl.c_z0 + 2 * (slot - sl.ze0) + 1;
+    } else { slot = sl.As0 + (idx - sl.n1); call = sl.c_As0 + (idx - sl.n1); }
+    uint64_t sd[4], a[25];
+    const uint64_t *gs = reinterpret_cast<const uint64_t *>(pb.seeds + 32 * (size_t)b);
+#pragma unroll
+    for (int w = 0; w < 4; w++) sd[w] = gs[w];
+    drbg_begin(a, sd, call);
+    u16 *dst = yrow(pb, sl, b, slot);
+#pragma unroll 1
+    for (int blk = 0; blk < 3; blk++) {             // 302 bytes = 136 + 136 + 30
+#pragma unroll
+        for (int v = 0; v < 68; v++) {
+            if (blk * 68 + v <= NT) dst[256 + blk * 68 + v] = (u16)(lane_be16(a[v >> 2], v & 3) % (uint32_t)Q);
+        }
+        if (blk < 2) keccak_f1600(a);
+    }
+    for (int c = D1; c < YLD; c++) dst[c] = 0;
+    if (slot >= sl.seta0 && slot < sl.s0) {
+        int j = (slot - sl.seta0) % sl.E;           // same constant for the s and e copies
+        u16 ev = (u16)((j - sl.eta + Q) % Q);
+        for (int c = 0; c < 256; c++) dst[c] = ev;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// SHA3-256 of a per-party record: commit hash (mlwe_prover.cpp:116-127, mlwe_verifier.cpp:23-35) and view
+// hash (mlwe_prover.cpp:395-444, mlwe_verifier.cpp:584-632).  One thread per (proof, party).
+//   prover  : record element v = plane[tab[v]][party]  -> every absorb load is coalesced across the CTA's parties
+//   verifier: record element v = rec[opened index][v]   (row-major records of the 150 opened parties)
+// NVALS u16 values = 2*NVALS bytes.
+struct HashSrc {
+    const u16 *src; long long proof_stride, item_stride, elem_stride; int off0;
+    const int16_t *tab;      // nullptr = identity
+    const u16 *plist; int nlist;   // nullptr: items are parties 0..NP-1; else item idx -> output party plist[b][idx]
+};
+template <int NVALS>
+__global__ void __launch_bounds__(128)
+k_hash_records(const HashSrc hs, u8 *__restrict__ out_rows, u16 *__restrict__ out_planes, int nslot, int out_plane_slot)
+{
+    __shared__ int16_t stab[NVALS];
+    for (int i = threadIdx.x; i < NVALS; i += 128) stab[i] = hs.tab ? hs.tab[i] : (int16_t)i;
+    __syncthreads();
+    const int b = blockIdx.y, idx = blockIdx.x * 128 + threadIdx.x;
+    int p = idx;
+    if (hs.plist) { if (idx >= hs.nlist) return; p = hs.plist[(size_t)b * hs.nlist + idx]; if (p >= NP) return; }
+    else if (idx >= NP) return;
+    const u16 *base = hs.src + (size_t)b * hs.proof_stride + (size_t)idx * hs.item_stride + hs.off0;
+    const size_t es = (size_t)hs.elem_stride;
+    uint64_t a[25];
+    keccak_zero(a);
+    constexpr int NFULL = (2 * NVALS) / 136, REMV = NVALS - NFULL * 68;   // u16 values left for the last block
+#pragma unroll 1
+    for (int blk = 0; blk < NFULL; blk++) {
+#pragma unroll
+        for (int l = 0; l < 17; l++) {
+            uint64_t w = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) w |= (uint64_t)base[(size_t)stab[blk * 68 + 4 * l + i] * es] << (16 * i);
+            a[l] ^= w;
+        }
+        keccak_f1600(a);
+    }
+#pragma unroll
+    for (int l = 0; l < 17; l++) {
+        uint64_t w = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            if (4 * l + i < REMV) w |= (uint64_t)base[(size_t)stab[NFULL * 68 + 4 * l + i] * es] << (16 * i);
+        if (l == REMV / 4) w |= 0x06ULL << (16 * (REMV % 4));
+        if (l == 16) w |= 0x8000000000000000ULL;
+        a[l] ^= w;
+    }
+    keccak_f1600(a);
+    if (out_rows) {
+        uint64_t *o = reinterpret_cast<uint64_t *>(out_rows + ((size_t)b * NP + p) * 32);
+        o[0] = a[0]; o[1] = a[1]; o[2] = a[2]; o[3] = a[3];
+    }
+    if (out_planes) {
+        u16 *o = out_planes + ((size_t)b * nslot + out_plane_slot) * SLD + SOFF + p;
+#pragma unroll
+        for (int i = 0; i < 16; i++) o[(size_t)i * SLD] = (u16)(a[i >> 2] >> (16 * (i & 3)));
+    }
+}
+
+// SHA3-256 over the 1454 x 32-byte digests of one proof (FS tree hash): 342 full rate blocks + 16 bytes.
+// Strictly sequential sponge: one thread per proof (mlwe_prover.cpp:131-135, :445-449).
+__device__ __forceinline__ void tree_hash(uint64_t (&a)[25], const u8 *rows)
+{
+    const uint64_t *src = reinterpret_cast<const uint64_t *>(rows);
+    keccak_zero(a);
+    constexpr int NFULL = TREE_BYTES / 136;            // 342
+#pragma unroll 1
+    for (int blk = 0; blk < NFULL; blk++) {
+#pragma unroll
+        for (int l = 0; l < 17; l++) a[l] ^= src[blk * 17 + l];
+        keccak_f1600(a);
+    }
+    a[0] ^= src[NFULL * 17]; a[1] ^= src[NFULL * 17 + 1];   // 46528 - 342*136 = 16 bytes
+    a[2] ^= 0x06ULL; a[16] ^= 0x8000000000000000ULL;
+    keccak_f1600(a);
+}
+
+// FS-1: alpha = BE16(SHAKE256(SHA3-256(Tcomm_0 || ... ) || 0x01)) mod q and the power table (mlwe_prover.cpp:130-153)
+template <int K>
+__global__ void __launch_bounds__(32) k_fs1(const u8 *__restrict__ TCR, u16 *__restrict__ PW, int B)
+{
+    constexpr int F = MK + 2 * K + 1, NA = MK + 2 * K;
+    const int b = blockIdx.x * 32 + threadIdx.x;
+    if (b >= B) return;
+    uint64_t a[25];
+    tree_hash(a, TCR + (size_t)b * TREE_BYTES);
+    uint64_t dg[4] = {a[0], a[1], a[2], a[3]};
+    prf_begin(a, dg, 1);
+    u16 *pw = PW + (size_t)b * NA * F;
+#pragma unroll 1
+    for (int blk = 0; blk < 2; blk++) {
+#pragma unroll
+        for (int v = 0; v < 68; v++) {
+            const int j = blk * 68 + v;
+            if (j < NA) {
+                uint32_t al = lane_be16(a[v >> 2], v & 3) % (uint32_t)Q, x = 1;
+                for (int kk = 0; kk < F; kk++) { pw[j * F + kk] = (u16)x; x = gf_mul(x, al); }
+            }
+        }
+        if (blk == 0) keccak_f1600(a);
+    }
+}
+
+// FS-2: opened set I from the view hashes, with the reference's linear-probe de-duplication
+// (mlwe_prover.cpp:445-474) and the ascending rest list (:480-490).
+__global__ void __launch_bounds__(32) k_fs2(const u8 *__restrict__ VWR, u16 *__restrict__ Iout, u16 *__restrict__ REST, int B)
+{
+    const int b = blockIdx.x * 32 + threadIdx.x;
+    if (b >= B) return;
+    uint64_t a[25];
+    tree_hash(a, VWR + (size_t)b * TREE_BYTES);
+    uint64_t dg[4] = {a[0], a[1], a[2], a[3]};
+    prf_begin(a, dg, 1);
+    u16 *I = Iout + (size_t)b * NT;
+#pragma unroll 1
+    for (int blk = 0; blk < 3; blk++) {               // 300 bytes = 136 + 136 + 28
+#pragma unroll
+        for (int v = 0; v < 68; v++)
+            if (blk * 68 + v < NT) I[blk * 68 + v] = (u16)(lane_be16(a[v >> 2], v & 3) % (uint32_t)NP);
+        if (blk < 2) keccak_f1600(a);
+    }
+    for (int i = 1; i < NT; i++) {
+        uint32_t cur = I[i]; uint32_t inc = 0; bool dup;
+        do {
+            dup = false;
+            for (int j = 0; j < i; j++)
+                if ((cur + inc) % NP == I[j]) { dup = true; inc = (inc + 1) & 0xFFFF; break; }
+        } while (dup);
+        I[i] = (u16)((cur + inc) % NP);
+    }
+    // rest list: parties not in I, ascending.  O(N*T) scan is negligible next to the tree hash.
+    u16 *rest = REST + (size_t)b * NR;
+    int n = 0;
+    for (int p = 0; p < NP; p++) {
+        bool in = false;
+        for (int j = 0; j < NT; j++) in |= (I[j] == p);
+        if (!in && n < NR) rest[n++] = (u16)p;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// beta/gamma and r/NTT_r evaluation (mlwe_prover.cpp:159-214): per party p
+//   beta[p][j]  = f[p][0]  + sum_{k>=1} alpha_j^k f[p][k]        j < 70
+//   r[p][j']    = f[p][71] + sum_{k>=1} alpha_{70+j'}^k f[p][k]  j' < 2K      (c0 index quirk)
+// and the same over NTT_f.  CTA = 128 parties x {f, NTT_f}; the power table sits in shared memory.
+template <int K>
+__global__ void __launch_bounds__(256) k_eval(ProveBufs pb)
+{
+    constexpr int F = MK + 2 * K + 1, NA = MK + 2 * K, NAP = 80;
+    const Slots sl = make_slots(K);
+    __shared__ __align__(16) int32_t spw[F][NAP];
+    const int b = blockIdx.y, tid = threadIdx.x;
+    const u16 *pw = pb.PW + (size_t)b * NA * F;
+    for (int i = tid; i < F * NAP; i += 256) {
+        int kk = i / NAP, j = i % NAP;
+        int32_t v = 0;
+        if (j < NA) { v = gf_center(pw[j * F + kk]); if (kk == 0 && j >= MK) v = 0; }
+        spw[kk][j] = v;
+    }
+    __syncthreads();
+    const int half = tid >> 7, p = blockIdx.x * 128 + (tid & 127);
+    if (p >= NP) return;
+    const u16 *src = plane(pb, sl, b, half ? sl.Tf0 : sl.f0) + p;
+    int32_t acc[NAP];
+#pragma unroll
+    for (int j = 0; j < NAP; j++) acc[j] = 0;
+    int32_t c71 = 0;
+#pragma unroll 1
+    for (int kk = 0; kk < F; kk++) {
+        const int32_t v = gf_center(src[(size_t)kk * SLD]);
+        if (kk == MK + 1) c71 = v;
+#pragma unroll
+        for (int j4 = 0; j4 < NAP / 4; j4++) {
+            const int4 w = *reinterpret_cast<const int4 *>(&spw[kk][4 * j4]);
+            acc[4 * j4] += v * w.x; acc[4 * j4 + 1] += v * w.y; acc[4 * j4 + 2] += v * w.z; acc[4 * j4 + 3] += v * w.w;
+        }
+    }
+    u16 *bg = pb.BG + ((size_t)b * NP + p) * (2 * MK) + half * MK;
+#pragma unroll
+    for (int j = 0; j < MK; j++) bg[j] = (u16)gf_canon(acc[j]);
+#pragma unroll
+    for (int j = 0; j < K; j++) plane(pb, sl, b, (half ? sl.G0 : sl.B0) + j)[p] = (u16)gf_canon(acc[j]);
+#pragma unroll
+    for (int j = 0; j < 2 * K; j++) plane(pb, sl, b, (half ? sl.TR0 : sl.R0) + j)[p] = (u16)gf_canon(acc[MK + j] + c71);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Online opening, in the clear (mlwe_prover.cpp:222-318).  By linearity of the sharing the opened
+// masked secrets are s + r with r = f_71 + sum_k alpha^k f_k over the clear f vectors, so no
+// reconstruction mat-vec is needed.  Emits the Y rows of [NTT(s+r)], [NTT(e+r)], [A(s+r)] (all
+// re-using the tail of [s+r]/[e+r]) and the secrets of [A s].  One CTA per proof.
+template <int K>
+__global__ void __launch_bounds__(128) k_open(ProveBufs pb)
+{
+    constexpr int F = MK + 2 * K + 1, NA = MK + 2 * K;
+    const Slots sl = make_slots(K);
+    const int b = blockIdx.x, tid = threadIdx.x;
+    __shared__ u16 sSR[K][256], sER[K][256];
+    __shared__ u16 spw[2 * K][F];
+    for (int i = tid; i < 2 * K * F; i += 128) spw[i / F][i % F] = pb.PW[(size_t)b * NA * F + (MK + i / F) * F + (i % F)];
+    __syncthreads();
+    for (int c = tid; c < 256; c += 128) {
+        uint32_t acc[2 * K];
+        const uint32_t f71 = yrow(pb, sl, b, sl.f0 + MK + 1)[c];
+#pragma unroll
+        for (int j = 0; j < 2 * K; j++) acc[j] = f71;
+        for (int kk = 1; kk < F; kk++) {
+            const uint32_t v = yrow(pb, sl, b, sl.f0 + kk)[c];
+#pragma unroll
+            for (int j = 0; j < 2 * K; j++) acc[j] = gf_add(acc[j], gf_mul(spw[j][kk], v));
+        }
+#pragma unroll
+        for (int i = 0; i < K; i++) {
+            sSR[i][c] = (u16)gf_add(yrow(pb, sl, b, sl.s0 + i)[c], acc[i]);
+            sER[i][c] = (u16)gf_add(yrow(pb, sl, b, sl.e0 + i)[c], acc[K + i]);
+        }
+    }
+    __syncthreads();
+    for (int i = 0; i < K; i++) { ntt256_block(sSR[i], tid); ntt256_block(sER[i], tid); }
+    const u16 *AH = pb.AH + (size_t)b * K * K * 256, *SHAT = pb.SHAT + (size_t)b * K * 256;
+    for (int i = 0; i < K; i++) {
+        uint32_t s0 = 0, s1 = 0, q0 = 0, q1 = 0;
+        for (int j = 0; j < K; j++) {
+            const uint32_t a0 = AH[(i * K + j) * 256 + 2 * tid], a1 = AH[(i * K + j) * 256 + 2 * tid + 1];
+            uint32_t r0, r1;
+            basemul_pair(r0, r1, a0, a1, SHAT[j * 256 + 2 * tid], SHAT[j * 256 + 2 * tid + 1], tid);
+            s0 = gf_add(s0, r0); s1 = gf_add(s1, r1);
+            basemul_pair(r0, r1, a0, a1, sSR[j][2 * tid], sSR[j][2 * tid + 1], tid);
+            q0 = gf_add(q0, r0); q1 = gf_add(q1, r1);
+        }
+        u16 *yAs = yrow(pb, sl, b, sl.As0 + i), *yAsr = yrow(pb, sl, b, sl.Asr0 + i);
+        yAs[2 * tid] = (u16)s0; yAs[2 * tid + 1] = (u16)s1;
+        yAsr[2 * tid] = (u16)q0; yAsr[2 * tid + 1] = (u16)q1;
+        u16 *yTsr = yrow(pb, sl, b, sl.Tsr0 + i), *yTer = yrow(pb, sl, b, sl.Ter0 + i);
+        yTsr[tid] = sSR[i][tid]; yTsr[tid + 128] = sSR[i][tid + 128];
+        yTer[tid] = sER[i][tid]; yTer[tid + 128] = sER[i][tid + 128];
+        // tails: shares of [s+r] / [e+r] held by parties 0..150
+        for (int q = tid; q <= NT; q += 128) {
+            const u16 srq = (u16)gf_add(plane(pb, sl, b, sl.s0 + i)[q], plane(pb, sl, b, sl.R0 + i)[q]);
+            const u16 erq = (u16)gf_add(plane(pb, sl, b, sl.e0 + i)[q], plane(pb, sl, b, sl.R0 + K + i)[q]);
+            yTsr[256 + q] = srq; yAsr[256 + q] = srq; yTer[256 + q] = erq;
+        }
+        for (int c = D1 + tid; c < YLD; c += 128) { yTsr[c] = 0; yTer[c] = 0; yAsr[c] = 0; }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per-party derived planes hashed into the view: [s+r], [e+r] (mlwe_prover.cpp:227-245) and the
+// range-proof zero sharings u_j = z_j^(2d) - z_j^(d) (:338-381).  One thread per (proof, party).
+template <int K>
+__global__ void __launch_bounds__(128) k_derive(ProveBufs pb)
+{
+    constexpr int ETA = (K == 2) ? 3 : 2, E = 2 * ETA + 1, M = 2 * ETA;
+    const Slots sl = make_slots(K);
+    const int b = blockIdx.y, p = blockIdx.x * 128 + threadIdx.x;
+    if (p >= NP) return;
+#pragma unroll
+    for (int i = 0; i < K; i++)
+#pragma unroll
+        for (int w = 0; w < 2; w++) {
+            const uint32_t x = plane(pb, sl, b, (w ? sl.e0 : sl.s0) + i)[p];
+            plane(pb, sl, b, (w ? sl.ER0 : sl.SR0) + i)[p] = (u16)gf_add(x, plane(pb, sl, b, sl.R0 + w * K + i)[p]);
+            uint32_t sub[E];
+#pragma unroll
+            for (int m = 0; m < E; m++) sub[m] = gf_sub(x, plane(pb, sl, b, (w ? sl.eeta0 : sl.seta0) + i * E + m)[p]);
+            uint32_t prev = sub[0];
+#pragma unroll
+            for (int j = 0; j < M; j++) {
+                const uint32_t z2 = gf_mul(prev, sub[j + 1]);
+                const uint32_t zd = plane(pb, sl, b, (w ? sl.ze0 : sl.zs0) + i * M + j)[p];
+                plane(pb, sl, b, (w ? sl.UE0 : sl.US0) + i * M + j)[p] = (u16)gf_sub(z2, zd);
+                prev = zd;
+            }
+        }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Proof assembly (mlwe_prover.cpp:480-537): gather the opened-set and rest-set fields into the packed
+// byte layout of struct mpcith_proof.  grid = (row tiles, B); tile 0..T_TILES-1 = opened rows.
+template <int K>
+__global__ void __launch_bounds__(128) k_assemble(ProveBufs pb)
+{
+    constexpr int ETA = (K == 2) ? 3 : 2, E = 2 * ETA + 1, M = 2 * ETA, F = MK + 2 * K + 1;
+    constexpr int ROWS = 32, T_TILES = (NT + ROWS - 1) / ROWS;
+    const Slots sl = make_slots(K);
+    const Layout L = make_layout(K);
+    const int b = blockIdx.y, tid = threadIdx.x;
+    u8 *pi = pb.pi + L.proof_bytes * (size_t)b;
+    const u16 *I = pb.I + (size_t)b * NT, *rest = pb.REST + (size_t)b * NR;
+    auto P = [&](int slot, int p) -> uint32_t { return plane(pb, sl, b, slot)[p]; };
+    auto out16 = [&](size_t off, size_t idx) -> u16 * { return reinterpret_cast<u16 *>(pi + off) + idx; };
+    __shared__ u16 sp[ROWS];
+    if ((int)blockIdx.x < T_TILES) {
+        const int r0 = blockIdx.x * ROWS, nr = min(ROWS, NT - r0);
+        if (tid < nr) { sp[tid] = I[r0 + tid]; *out16(L.o_I, r0 + tid) = sp[tid]; }
+        __syncthreads();
+        for (int idx = tid; idx < nr * F; idx += 128) {
+            const int r = idx / F, j = idx % F, p = sp[r];
+            *out16(L.o_f, (size_t)(r0 + r) * F + j) = (u16)P(sl.f0 + j, p);
+            *out16(L.o_Tf, (size_t)(r0 + r) * F + j) = (u16)P(sl.Tf0 + j, p);
+        }
+        for (int idx = tid; idx < nr * K; idx += 128) {
+            const int r = idx / K, j = idx % K, p = sp[r];
+            const size_t o = (size_t)(r0 + r) * K + j;
+            const uint32_t s = P(sl.s0 + j, p), e = P(sl.e0 + j, p), As = P(sl.As0 + j, p);
+            const uint32_t Te = gf_sub(P(sl.Ter0 + j, p), P(sl.TR0 + K + j, p));
+            *out16(L.o_s, o) = (u16)s; *out16(L.o_e, o) = (u16)e;
+            *out16(L.o_NTTs, o) = (u16)gf_sub(P(sl.Tsr0 + j, p), P(sl.TR0 + j, p));
+            *out16(L.o_NTTe, o) = (u16)Te;
+            *out16(L.o_NTTAr, o) = (u16)gf_sub(P(sl.Asr0 + j, p), As);
+            *out16(L.o_NTTAs, o) = (u16)As;
+            for (int m = 0; m < E; m++) {
+                *out16(L.o_ssub, o * E + m) = (u16)gf_sub(s, P(sl.seta0 + j * E + m, p));
+                *out16(L.o_esub, o * E + m) = (u16)gf_sub(e, P(sl.eeta0 + j * E + m, p));
+            }
+            for (int m = 0; m < M; m++) {
+                *out16(L.o_zs, o * M + m) = (u16)P(sl.zs0 + j * M + m, p);
+                *out16(L.o_ze, o * M + m) = (u16)P(sl.ze0 + j * M + m, p);
+            }
+        }
+    } else {
+        const int r0 = (blockIdx.x - T_TILES) * ROWS, nr = min(ROWS, NR - r0);
+        if (tid < nr) sp[tid] = rest[r0 + tid];
+        __syncthreads();
+        for (int idx = tid; idx < nr * MK; idx += 128) {
+            const int r = idx / MK, j = idx % MK, p = sp[r];
+            const u16 *bg = pb.BG + ((size_t)b * NP + p) * (2 * MK);
+            *out16(L.o_beta, (size_t)(r0 + r) * MK + j) = bg[j];
+            *out16(L.o_gamma, (size_t)(r0 + r) * MK + j) = bg[MK + j];
+        }
+        for (int idx = tid; idx < nr * 8; idx += 128) {         // 32-byte digests as 8 x u32 (proofs are only 4-byte aligned)
+            const int r = idx / 8, w = idx % 8, p = sp[r];
+            reinterpret_cast<uint32_t *>(pi + L.o_Tcomm)[(size_t)(r0 + r) * 8 + w] = reinterpret_cast<const uint32_t *>(pb.TCR + ((size_t)b * NP + p) * 32)[w];
+            reinterpret_cast<uint32_t *>(pi + L.o_comm)[(size_t)(r0 + r) * 8 + w] = reinterpret_cast<const uint32_t *>(pb.VWR + ((size_t)b * NP + p) * 32)[w];
+        }
+        for (int idx = tid; idx < nr * K; idx += 128) {
+            const int r = idx / K, j = idx % K, p = sp[r];
+            const size_t o = (size_t)(r0 + r) * K + j;
+            *out16(L.o_sr, o) = (u16)P(sl.SR0 + j, p);
+            *out16(L.o_er, o) = (u16)P(sl.ER0 + j, p);
+            *out16(L.o_t, o) = (u16)gf_add(P(sl.As0 + j, p), gf_sub(P(sl.Ter0 + j, p), P(sl.TR0 + K + j, p)));
+            for (int m = 0; m < E; m++) {
+                *out16(L.o_seta, o * E + m) = (u16)P(sl.seta0 + j * E + m, p);
+                *out16(L.o_eeta, o * E + m) = (u16)P(sl.eeta0 + j * E + m, p);
+            }
+            for (int m = 0; m < M; m++) {
+                *out16(L.o_us, o * M + m) = (u16)P(sl.US0 + j * M + m, p);
+                *out16(L.o_ue, o * M + m) = (u16)P(sl.UE0 + j * M + m, p);
+            }
+        }
+    }
+}
+
+}  // namespace kosk

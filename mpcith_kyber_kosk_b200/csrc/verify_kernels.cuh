@@ -1,0 +1,485 @@
+// verify_kernels.cuh -- sm_100a kernels of the KOSK verifier (kyber_kosk_verify, reference kosk.cpp:88-117 and
+// verify(), mlwe_verifier.cpp:4-686).  One launch handles a chunk of B independent proofs.  Every failed check
+// ORs a bit into flags[b]; the proof is accepted iff flags[b] == 0 (the reference returns false at the first
+// failing check, so only the conjunction matters).  The reference's NTL interpolate/eval over the rest-party
+// nodes (mlwe_verifier.cpp:188-224, :326-352, :397-443, :510-543) becomes one Lagrange matrix per proof,
+// applied with the same integer-pipe GEMM as the prover's share evaluation.
+#pragma once
+#include "prove_kernels.cuh"
+#include <cuda_runtime.h>
+
+namespace kosk {
+
+constexpr int VR2LD = 816;        // row stride of 813-term rows (16B-aligned rows, 51 k-steps)
+constexpr int LM1_ROWS = 512;     // 407 targets padded to the GEMM's 128-column tiles
+constexpr int OPLD = 160;         // opened-party values: beta[70] gamma[70] r[2k] NTT_r[2k]
+
+enum VFlag { VF_I = 1, VF_BG = 2, VF_SR = 4, VF_NTT = 8, VF_ASR = 16, VF_T = 32, VF_TREL = 64, VF_ETA = 128,
+             VF_SUBETA = 256, VF_UZ = 512, VF_U2D = 1024, VF_FS2 = 2048 };
+
+struct VerifyTables { const int16_t *St, *R1, *R2; const u16 *inv; };
+
+struct VerifyBufs {
+    int *flags = nullptr;
+    u16 *I = nullptr, *REST = nullptr, *I2 = nullptr, *REST2 = nullptr; int16_t *POS = nullptr;
+    u16 *AH = nullptr, *TPK = nullptr, *PW = nullptr;
+    u8 *TCR = nullptr, *VWR = nullptr;
+    u16 *CR = nullptr, *VR = nullptr, *OPV = nullptr, *UOP = nullptr;
+    u16 *ABG = nullptr, *BS = nullptr, *A1 = nullptr, *YV = nullptr, *A2 = nullptr, *UZ = nullptr, *VSH = nullptr, *U2 = nullptr, *UR = nullptr;
+    int16_t *LM1 = nullptr, *LM2 = nullptr;
+    int k = 0, chunk = 0;
+};
+
+struct VDims {
+    int k, eta, E, M, F, NA, nc, nv, crld, vrld, n1rows, nyrows, n2rows;
+};
+KOSK_HD VDims make_vdims(int k)
+{
+    VDims d; d.k = k; d.eta = (k == 2) ? 3 : 2; d.E = 2 * d.eta + 1; d.M = 2 * d.eta; d.F = MK + 2 * k + 1; d.NA = MK + 2 * k;
+    d.nc = 2 * (k + d.F); d.nv = 16 + d.nc + 4 * k + 4 * k * d.M;
+    d.crld = (d.nc + 3) & ~3; d.vrld = (d.nv + 3) & ~3;
+    d.n1rows = k * (3 + 2 * d.E); d.nyrows = d.n1rows + 3 * k; d.n2rows = 2 * k * d.M;
+    return d;
+}
+
+static inline void verify_free(VerifyBufs &v)
+{
+    void *p[] = {v.flags, v.I, v.REST, v.I2, v.REST2, v.POS, v.AH, v.TPK, v.PW, v.TCR, v.VWR, v.CR, v.VR, v.OPV, v.UOP,
+                 v.ABG, v.BS, v.A1, v.YV, v.A2, v.UZ, v.VSH, v.U2, v.UR, v.LM1, v.LM2};
+    for (void *q : p) if (q) cudaFree(q);
+    v = VerifyBufs{};
+}
+static inline int verify_alloc(VerifyBufs &v, int k, int chunk)
+{
+    const VDims d = make_vdims(k); const size_t B = (size_t)chunk;
+    v.k = k; v.chunk = chunk;
+#define VA(ptr, bytes, zero) do { if (cudaMalloc((void **)&(ptr), (bytes)) != cudaSuccess) return -1; if (zero) cudaMemset((ptr), 0, (bytes)); } while (0)
+    VA(v.flags, B * 4, 1); VA(v.I, B * NT * 2, 0); VA(v.REST, B * NR * 2, 0); VA(v.I2, B * NT * 2, 0); VA(v.REST2, B * NR * 2, 0); VA(v.POS, B * NP * 2, 0);
+    VA(v.AH, B * k * k * 256 * 2, 0); VA(v.TPK, B * k * 256 * 2, 0); VA(v.PW, B * d.NA * d.F * 2, 0);
+    VA(v.TCR, B * TREE_BYTES, 0); VA(v.VWR, B * TREE_BYTES, 0);
+    VA(v.CR, B * NT * d.crld * 2, 1); VA(v.VR, B * NT * d.vrld * 2, 1); VA(v.OPV, B * NT * OPLD * 2, 1); VA(v.UOP, B * NT * d.n2rows * 2, 1);
+    VA(v.ABG, B * 2 * MK * YLD * 2, 1); VA(v.BS, B * 2 * MK * 256 * 2, 0);
+    VA(v.A1, B * d.n1rows * YLD * 2, 1); VA(v.YV, B * d.nyrows * YLD * 2, 1);
+    VA(v.A2, B * d.n2rows * VR2LD * 2, 1); VA(v.UZ, B * d.n2rows * 256 * 2, 0);
+    VA(v.VSH, B * d.nyrows * SLD * 2, 1); VA(v.U2, B * d.n2rows * VR2LD * 2, 1); VA(v.UR, B * d.n2rows * 256 * 2, 0);
+    VA(v.LM1, B * LM1_ROWS * YLD * 2, 1); VA(v.LM2, B * 256 * VR2LD * 2, 1);
+#undef VA
+    return 0;
+}
+
+__device__ __forceinline__ u16 pi16(const u8 *pi, size_t off, size_t idx) { return reinterpret_cast<const u16 *>(pi + off)[idx]; }
+
+// V1 (mlwe_verifier.cpp:9-19) + kosk.cpp:94-112: opened/rest sets, A-hat from the pk seed, t from pk, and
+// the rest parties' commitment / view digests copied into the per-party digest rows (:36-38, :645-647).
+template <int K>
+__global__ void __launch_bounds__(128) kv_setup(VerifyBufs vb, const u8 *__restrict__ pis, const u8 *__restrict__ pks)
+{
+    const Layout L = make_layout(K);
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const u8 *pi = pis + L.proof_bytes * (size_t)b, *pk = pks + L.pk_bytes * (size_t)b;
+    __shared__ int cnt[NP];
+    __shared__ int bad, base[129];
+    __shared__ u16 sI[NT];
+    for (int p = tid; p < NP; p += 128) cnt[p] = 0;
+    if (tid == 0) bad = 0;
+    __syncthreads();
+    for (int i = tid; i < NT; i += 128) {
+        u16 v = pi16(pi, L.o_I, i); sI[i] = v;
+        if (v >= NP) atomicOr(&bad, 1); else if (atomicAdd(&cnt[v], 1) != 0) atomicOr(&bad, 1);
+    }
+    __syncthreads();
+    if (bad) {   // malformed I is UB in the reference (mlwe_verifier.cpp:12); rejected here, with a sane set for the remaining kernels
+        for (int p = tid; p < NP; p += 128) cnt[p] = p < NT ? 1 : 0;
+        for (int i = tid; i < NT; i += 128) sI[i] = (u16)i;
+        if (tid == 0) atomicOr(&vb.flags[b], VF_I);
+    }
+    __syncthreads();
+    for (int i = tid; i < NT; i += 128) { vb.I[(size_t)b * NT + i] = sI[i]; vb.POS[(size_t)b * NP + sI[i]] = (int16_t)(-1 - i); }
+    constexpr int PER = 12;   // 128 * 12 >= 1454
+    int mine = 0;
+    for (int p = tid * PER; p < min(NP, tid * PER + PER); p++) mine += cnt[p] == 0;
+    base[tid + 1] = mine;
+    if (tid == 0) base[0] = 0;
+    __syncthreads();
+    if (tid == 0) for (int i = 1; i <= 128; i++) base[i] += base[i - 1];
+    __syncthreads();
+    { int j = base[tid];
+      for (int p = tid * PER; p < min(NP, tid * PER + PER); p++) if (cnt[p] == 0) { vb.REST[(size_t)b * NR + j] = (u16)p; vb.POS[(size_t)b * NP + p] = (int16_t)j; j++; } }
+    // t from pk: polyvec_frombytes (kyber/poly.c:151-158), raw 12-bit values
+    for (int i = 0; i < K; i++) {
+        const u8 *a = pk + 384 * i + 3 * tid;
+        vb.TPK[((size_t)b * K + i) * 256 + 2 * tid] = (u16)((a[0] | ((u16)a[1] << 8)) & 0xFFF);
+        vb.TPK[((size_t)b * K + i) * 256 + 2 * tid + 1] = (u16)(((a[1] >> 4) | ((u16)a[2] << 4)) & 0xFFF);
+    }
+    if (tid < K * K) {      // gen_matrix (indcpa.c:168-193)
+        const int i = tid / K, j = tid % K;
+        ByteSponge sp; sp.init(168);
+        sp.absorb(pk + 384 * K, 32);
+        u8 ji[2] = {(u8)j, (u8)i}; sp.absorb(ji, 2); sp.finalize(0x1F);
+        u16 *dst = vb.AH + ((size_t)b * K * K + tid) * 256;
+        int ctr = 0;
+        while (ctr < 256) {
+            uint32_t b0 = sp.next(), b1 = sp.next(), b2 = sp.next();
+            uint32_t v0 = (b0 | (b1 << 8)) & 0xFFF, v1 = ((b1 >> 4) | (b2 << 4)) & 0xFFF;
+            if (v0 < (uint32_t)Q) dst[ctr++] = (u16)v0;
+            if (ctr < 256 && v1 < (uint32_t)Q) dst[ctr++] = (u16)v1;
+        }
+    }
+    __syncthreads();   // REST visible block-wide (written by this block)
+    for (int idx = tid; idx < NR * 8; idx += 128) {
+        const int j = idx / 8, w = idx % 8, p = vb.REST[(size_t)b * NR + j];
+        reinterpret_cast<uint32_t *>(vb.TCR + ((size_t)b * NP + p) * 32)[w] = reinterpret_cast<const uint32_t *>(pi + L.o_Tcomm)[(size_t)j * 8 + w];
+        reinterpret_cast<uint32_t *>(vb.VWR + ((size_t)b * NP + p) * 32)[w] = reinterpret_cast<const uint32_t *>(pi + L.o_comm)[(size_t)j * 8 + w];
+    }
+    // commit records of the opened parties (mlwe_verifier.cpp:23-33), row-major
+    const VDims d = make_vdims(K);
+    for (int idx = tid; idx < NT * d.nc; idx += 128) {
+        const int i = idx / d.nc, v = idx % d.nc;
+        u16 x;
+        if (v < K) x = pi16(pi, L.o_s, i * K + v);
+        else if (v < 2 * K) x = pi16(pi, L.o_e, i * K + v - K);
+        else if (v < 2 * K + d.F) x = pi16(pi, L.o_f, i * d.F + v - 2 * K);
+        else x = pi16(pi, L.o_Tf, i * d.F + v - 2 * K - d.F);
+        vb.CR[((size_t)b * NT + i) * d.crld + v] = x;
+    }
+}
+
+// V4 + V8 (mlwe_verifier.cpp:67-89, :148-170): beta/gamma/r/NTT_r of the opened parties.
+// Exact reference semantics: the sum starts from the raw (possibly non-canonical) share f[c0] and every step is
+// gf3329_add(acc, gf3329_mul(pow, f)); with a canonical first term this equals plain mod-q arithmetic.
+template <int K>
+__global__ void __launch_bounds__(320) kv_eval_opened(VerifyBufs vb)
+{
+    constexpr int F = MK + 2 * K + 1, NA = MK + 2 * K;
+    const VDims d = make_vdims(K);
+    const int b = blockIdx.x, tid = threadIdx.x;
+    __shared__ u16 spw[NA][F];
+    for (int i = tid; i < NA * F; i += 320) spw[i / F][i % F] = vb.PW[(size_t)b * NA * F + i];
+    __syncthreads();
+    if (tid >= 2 * NT) return;
+    const int i = tid >> 1, half = tid & 1;
+    const u16 *f = vb.CR + ((size_t)b * NT + i) * d.crld + 2 * K + half * F;
+    u16 *out = vb.OPV + ((size_t)b * NT + i) * OPLD;
+    for (int j = 0; j < NA; j++) {
+        const int c0 = j < MK ? 0 : MK + 1;
+        u16 acc = f[c0];
+        if (acc < Q) {
+            uint32_t s = 0;                                   // lazy: 78 * 3328^2 < 2^32
+            for (int kk = 1; kk < F; kk++) s += (uint32_t)spw[j][kk] * (f[kk] % (uint32_t)Q);
+            acc = (u16)((s + acc) % (uint32_t)Q);
+        } else {
+            for (int kk = 1; kk < F; kk++) acc = ref_add(acc, (u16)(((uint32_t)spw[j][kk] * f[kk]) % (uint32_t)Q));
+        }
+        if (j < MK) out[half * MK + j] = acc; else out[2 * MK + half * 2 * K + (j - MK)] = acc;
+    }
+}
+
+// Row gathers for the table / interpolation contractions (values reduced mod q exactly where the reference
+// reduces them: gf3329_mul in recon_* and the NTL ZZ_p assignment in the interpolation inputs).
+//   ABG[j*2+w][p]  p<407: beta/gamma share of party p      (mlwe_verifier.cpp:97-108)
+//   A1 [row][j]    j<407: sr, er, t, s_eta, e_eta shares of rest party j   (:178-186, :320-324, :390-395)
+//   A2 [row][j]    j<813: u_s, u_e shares of rest party j  (:503-508)
+template <int K>
+__global__ void __launch_bounds__(128) kv_gather(VerifyBufs vb, const u8 *__restrict__ pis)
+{
+    const Layout L = make_layout(K);
+    const VDims d = make_vdims(K);
+    const int b = blockIdx.y, row = blockIdx.x, tid = threadIdx.x;
+    const u8 *pi = pis + L.proof_bytes * (size_t)b;
+    if (row < 2 * MK) {
+        const int j = row >> 1, w = row & 1;
+        u16 *dst = vb.ABG + ((size_t)b * 2 * MK + row) * YLD;
+        for (int p = tid; p < D1; p += 128) {
+            const int pos = vb.POS[(size_t)b * NP + p];
+            const u16 v = pos >= 0 ? pi16(pi, w ? L.o_gamma : L.o_beta, (size_t)pos * MK + j) : vb.OPV[((size_t)b * NT + (-1 - pos)) * OPLD + w * MK + j];
+            dst[p] = (u16)(v % (uint32_t)Q);
+        }
+    } else if (row < 2 * MK + d.n1rows) {
+        const int r = row - 2 * MK;
+        size_t off; int mul, add;
+        if (r < K) { off = L.o_sr; mul = K; add = r; }
+        else if (r < 2 * K) { off = L.o_er; mul = K; add = r - K; }
+        else if (r < 3 * K) { off = L.o_t; mul = K; add = r - 2 * K; }
+        else if (r < 3 * K + K * d.E) { off = L.o_seta; mul = K * d.E; add = r - 3 * K; }
+        else { off = L.o_eeta; mul = K * d.E; add = r - 3 * K - K * d.E; }
+        u16 *dst = vb.A1 + ((size_t)b * d.n1rows + r) * YLD;
+        for (int j = tid; j < D1; j += 128) dst[j] = (u16)(pi16(pi, off, (size_t)j * mul + add) % (uint32_t)Q);
+    } else {
+        const int r = row - 2 * MK - d.n1rows;              // r = w*K*M + i*M + m
+        const int w = r / (K * d.M), im = r % (K * d.M);
+        u16 *dst = vb.A2 + ((size_t)b * d.n2rows + r) * VR2LD;
+        for (int j = tid; j < D2; j += 128) dst[j] = (u16)(pi16(pi, w ? L.o_ue : L.o_us, (size_t)j * K * d.M + im) % (uint32_t)Q);
+    }
+}
+
+// Per-proof Lagrange matrices over the rest-party nodes x_k = rest[k] + 256 (barycentric form):
+//   LM1[t][k] = l_k^{x_0..x_406}(t), t = 0..406 (a target that is itself a node gives a unit row);
+//   LM2[t][k] = l_k^{x_0..x_812}(t), t = 0..255.
+__global__ void __launch_bounds__(256) kv_lagrange(VerifyBufs vb, const u16 *__restrict__ inv_g)
+{
+    const int b = blockIdx.x, tid = threadIdx.x;
+    __shared__ u16 x[D2], w[D2], P[D1], inv[Q];
+    __shared__ int16_t hit[D1];
+    for (int i = tid; i < Q; i += 256) inv[i] = inv_g[i];
+    for (int i = tid; i < D2; i += 256) x[i] = (u16)(vb.REST[(size_t)b * NR + i] + 256);
+    __syncthreads();
+    for (int pass = 0; pass < 2; pass++) {
+        const int n = pass ? D2 : D1, nt = pass ? 256 : D1, ld = pass ? VR2LD : YLD;
+        int16_t *out = pass ? vb.LM2 + (size_t)b * 256 * VR2LD : vb.LM1 + (size_t)b * LM1_ROWS * YLD;
+        for (int k = tid; k < n; k += 256) {
+            uint32_t dprod = 1; const uint32_t xk = x[k];
+            for (int m = 0; m < n; m++) if (m != k) dprod = gf_mul(dprod, gf_sub(xk, x[m]));
+            w[k] = inv[dprod];
+        }
+        for (int t = tid; t < nt; t += 256) {
+            uint32_t full = 1; int h = -1;
+            for (int m = 0; m < n; m++) { const uint32_t dd = gf_sub((uint32_t)t, x[m]); if (dd == 0) h = m; else full = gf_mul(full, dd); }
+            P[t] = (u16)full; hit[t] = (int16_t)h;
+        }
+        __syncthreads();
+        for (int idx = tid; idx < nt * n; idx += 256) {
+            const int t = idx / n, k = idx % n;
+            int32_t v;
+            if (hit[t] >= 0) v = (k == hit[t]);
+            else v = gf_center(gf_mul(gf_mul(P[t], w[k]), inv[gf_sub((uint32_t)t, x[k])]));
+            out[(size_t)t * ld + k] = (int16_t)v;
+        }
+        __syncthreads();
+    }
+}
+
+// V5+V6 (mlwe_verifier.cpp:97-124): NTT(recon(beta_j)) == recon(gamma_j).  BS rows are j*2 + {beta,gamma}.
+__global__ void __launch_bounds__(128) kv_check_bg(VerifyBufs vb)
+{
+    const int b = blockIdx.y, j = blockIdx.x, tid = threadIdx.x;
+    __shared__ u16 p[256];
+    __shared__ int bad;
+    const u16 *bs = vb.BS + ((size_t)b * 2 * MK + 2 * j) * 256, *gs = bs + 256;
+    p[tid] = bs[tid]; p[tid + 128] = bs[tid + 128];
+    if (tid == 0) bad = 0;
+    __syncthreads();
+    ntt256_block(p, tid);
+    if (p[tid] != gs[tid] || p[tid + 128] != gs[tid + 128]) bad = 1;
+    __syncthreads();
+    if (tid == 0 && bad) atomicOr(&vb.flags[b], VF_BG);
+}
+
+// Checks on the interpolated secrets and the rows of the re-sharing GEMM (mlwe_verifier.cpp:257-270, :287-301,
+// :354-363, :415-441, :528-543).  YV rows: [0,K) s+r, [K,2K) e+r, [2K,3K) t, then s_eta[K][E], e_eta[K][E];
+// appended here: NTT(s+r), NTT(e+r), A o NTT(s+r), all with the tail of the row they derive from.
+template <int K>
+__global__ void __launch_bounds__(128) kv_open(VerifyBufs vb)
+{
+    const VDims d = make_vdims(K);
+    const int b = blockIdx.x, tid = threadIdx.x;
+    __shared__ u16 sSR[K][256], sER[K][256];
+    __shared__ int bad;
+    if (tid == 0) bad = 0;
+    __syncthreads();
+    u16 *yv = vb.YV + (size_t)b * d.nyrows * YLD;
+    int f = 0;
+    for (int c = tid; c < 256; c += 128) {
+        for (int i = 0; i < K; i++) {
+            sSR[i][c] = yv[(size_t)i * YLD + c]; sER[i][c] = yv[(size_t)(K + i) * YLD + c];
+            if (yv[(size_t)(2 * K + i) * YLD + c] != vb.TPK[((size_t)b * K + i) * 256 + c]) f |= VF_T;
+            for (int m = 0; m < d.E; m++) {
+                const u16 cur = (u16)(m >= d.eta ? m - d.eta : m + Q - d.eta);     // gf3329_sub(j, KYBER_ETA1), :418
+                if (yv[(size_t)(3 * K + i * d.E + m) * YLD + c] != cur) f |= VF_ETA;
+                if (yv[(size_t)(3 * K + K * d.E + i * d.E + m) * YLD + c] != cur) f |= VF_ETA;
+            }
+        }
+        for (int r = 0; r < d.n2rows; r++) if (vb.UZ[((size_t)b * d.n2rows + r) * 256 + c] != 0) f |= VF_UZ;
+    }
+    if (f) atomicOr(&bad, f);
+    __syncthreads();
+    for (int i = 0; i < K; i++) { ntt256_block(sSR[i], tid); ntt256_block(sER[i], tid); }
+    const u16 *AH = vb.AH + (size_t)b * K * K * 256;
+    for (int i = 0; i < K; i++) {
+        uint32_t q0 = 0, q1 = 0;
+        for (int j = 0; j < K; j++) {
+            uint32_t r0, r1;
+            basemul_pair(r0, r1, AH[(i * K + j) * 256 + 2 * tid], AH[(i * K + j) * 256 + 2 * tid + 1], sSR[j][2 * tid], sSR[j][2 * tid + 1], tid);
+            q0 = gf_add(q0, r0); q1 = gf_add(q1, r1);
+        }
+        u16 *yTsr = yv + (size_t)(d.n1rows + i) * YLD, *yTer = yv + (size_t)(d.n1rows + K + i) * YLD, *yAsr = yv + (size_t)(d.n1rows + 2 * K + i) * YLD;
+        yAsr[2 * tid] = (u16)q0; yAsr[2 * tid + 1] = (u16)q1;
+        yTsr[tid] = sSR[i][tid]; yTsr[tid + 128] = sSR[i][tid + 128];
+        yTer[tid] = sER[i][tid]; yTer[tid + 128] = sER[i][tid + 128];
+        for (int q = 256 + tid; q < D1; q += 128) {
+            const u16 srq = yv[(size_t)i * YLD + q], erq = yv[(size_t)(K + i) * YLD + q];
+            yTsr[q] = srq; yAsr[q] = srq; yTer[q] = erq;
+        }
+    }
+    if (tid == 0 && bad) atomicOr(&vb.flags[b], bad);
+}
+
+// Per-party checks against the regenerated sharings (planes VSH, same row order as YV) and construction of the
+// inputs of the last two steps: the u^(2d) rows for recon_secrets_2ddeg (mlwe_verifier.cpp:469-556) and the view
+// records of the opened parties (:584-630).  One thread per (proof, party).
+template <int K>
+__global__ void __launch_bounds__(128) kv_check_parties(VerifyBufs vb, const u8 *__restrict__ pis)
+{
+    const Layout L = make_layout(K);
+    const VDims d = make_vdims(K);
+    constexpr int ETA = (K == 2) ? 3 : 2, E = 2 * ETA + 1, M = 2 * ETA, F = MK + 2 * K + 1;
+    const int b = blockIdx.y, p = blockIdx.x * 128 + threadIdx.x;
+    if (p >= NP) return;
+    const u8 *pi = pis + L.proof_bytes * (size_t)b;
+    const u16 *vsh = vb.VSH + (size_t)b * d.nyrows * SLD + SOFF + p;
+    auto V = [&](int row) -> u16 { return vsh[(size_t)row * SLD]; };
+    const int pos = vb.POS[(size_t)b * NP + p];
+    int f = 0;
+    if (pos >= 0) {                                            // rest party, index pos in the proof's [R] arrays
+        for (int i = 0; i < K; i++) {
+            if (V(i) != pi16(pi, L.o_sr, (size_t)pos * K + i)) f |= VF_SR;              // :232-246
+            if (V(K + i) != pi16(pi, L.o_er, (size_t)pos * K + i)) f |= VF_SR;
+        }
+        if (p < D2)                                            // :547-552 rest shares of u^(2d), used raw in gf3329_mul
+            for (int r = 0; r < d.n2rows; r++) {
+                const int w = r / (K * M), im = r % (K * M);
+                vb.U2[((size_t)b * d.n2rows + r) * VR2LD + p] = (u16)(pi16(pi, w ? L.o_ue : L.o_us, (size_t)pos * K * M + im) % (uint32_t)Q);
+            }
+    } else {
+        const int o = -1 - pos;                                // opened party, index o in the proof's [T] arrays
+        const u16 *opv = vb.OPV + ((size_t)b * NT + o) * OPLD;
+        u16 *vr = vb.VR + ((size_t)b * NT + o) * d.vrld;
+        const u16 *tc = reinterpret_cast<const u16 *>(vb.TCR + ((size_t)b * NP + p) * 32);
+        int vo = 0;
+        for (int i = 0; i < 16; i++) vr[vo++] = tc[i];
+        const u16 *cr = vb.CR + ((size_t)b * NT + o) * d.crld;
+        for (int i = 0; i < d.nc; i++) vr[vo++] = cr[i];
+        for (int i = 0; i < K; i++) vr[vo++] = opv[i];                                   // beta[0..K)
+        for (int i = 0; i < K; i++) vr[vo++] = opv[MK + i];                              // gamma[0..K)
+        for (int i = 0; i < K; i++) vr[vo++] = V(i);                                     // regenerated [s+r] share (:249-255)
+        for (int i = 0; i < K; i++) vr[vo++] = V(K + i);
+        for (int i = 0; i < K; i++) {
+            const size_t oi = (size_t)o * K + i;
+            const u16 s = pi16(pi, L.o_s, oi), e = pi16(pi, L.o_e, oi);
+            const u16 As = pi16(pi, L.o_NTTAs, oi), Ar = pi16(pi, L.o_NTTAr, oi), Te = pi16(pi, L.o_NTTe, oi);
+            if (pi16(pi, L.o_NTTs, oi) != ref_sub(V(d.n1rows + i), opv[2 * MK + 2 * K + i])) f |= VF_NTT;          // :273-284
+            if (Te != ref_sub(V(d.n1rows + K + i), opv[2 * MK + 2 * K + K + i])) f |= VF_NTT;
+            if (V(d.n1rows + 2 * K + i) != ref_add(As, Ar)) f |= VF_ASR;                                           // :304-312
+            if (V(2 * K + i) != ref_add(As, Te)) f |= VF_TREL;                                                     // :365-376
+            for (int m = 0; m < E; m++) {                                                                         // :447-466
+                if (pi16(pi, L.o_ssub, oi * E + m) != ref_sub(s, V(3 * K + i * E + m))) f |= VF_SUBETA;
+                if (pi16(pi, L.o_esub, oi * E + m) != ref_sub(e, V(3 * K + K * E + i * E + m))) f |= VF_SUBETA;
+            }
+            u16 us[M], ue[M];
+            for (int m = 0; m < M; m++) {                                                                         // :471-493
+                const u16 as_ = m == 0 ? pi16(pi, L.o_ssub, oi * E) : pi16(pi, L.o_zs, oi * M + m - 1);
+                const u16 ae_ = m == 0 ? pi16(pi, L.o_esub, oi * E) : pi16(pi, L.o_ze, oi * M + m - 1);
+                const u16 z2s = (u16)(((uint32_t)as_ * pi16(pi, L.o_ssub, oi * E + m + 1)) % (uint32_t)Q);
+                const u16 z2e = (u16)(((uint32_t)ae_ * pi16(pi, L.o_esub, oi * E + m + 1)) % (uint32_t)Q);
+                us[m] = ref_sub(z2s, pi16(pi, L.o_zs, oi * M + m));
+                ue[m] = ref_sub(z2e, pi16(pi, L.o_ze, oi * M + m));
+                if (p < D2) {
+                    vb.U2[((size_t)b * d.n2rows + i * M + m) * VR2LD + p] = (u16)(us[m] % (uint32_t)Q);
+                    vb.U2[((size_t)b * d.n2rows + K * M + i * M + m) * VR2LD + p] = (u16)(ue[m] % (uint32_t)Q);
+                }
+            }
+            for (int m = 0; m < M; m++) vr[vo++] = pi16(pi, L.o_zs, oi * M + m);
+            for (int m = 0; m < M; m++) vr[vo++] = pi16(pi, L.o_ze, oi * M + m);
+            for (int m = 0; m < M; m++) vr[vo++] = us[m];
+            for (int m = 0; m < M; m++) vr[vo++] = ue[m];
+        }
+    }
+    if (f) atomicOr(&vb.flags[b], f);
+}
+
+// Final: recon_secrets_2ddeg outputs must vanish (:555-569), recomputed I must equal pi->I (:678-683).
+template <int K>
+__global__ void __launch_bounds__(128) kv_final(VerifyBufs vb, u8 *__restrict__ ok)
+{
+    const VDims d = make_vdims(K);
+    const int b = blockIdx.x, tid = threadIdx.x;
+    __shared__ int bad;
+    if (tid == 0) bad = 0;
+    __syncthreads();
+    int f = 0;
+    for (int idx = tid; idx < d.n2rows * 256; idx += 128) if (vb.UR[(size_t)b * d.n2rows * 256 + idx] != 0) f |= VF_U2D;
+    for (int i = tid; i < NT; i += 128) if (vb.I2[(size_t)b * NT + i] != vb.I[(size_t)b * NT + i]) f |= VF_FS2;
+    if (f) atomicOr(&bad, f);
+    __syncthreads();
+    if (tid == 0) {
+        const int fl = vb.flags[b] | bad;
+        vb.flags[b] = fl;
+        ok[b] = fl == 0 ? 1 : 0;
+    }
+}
+
+template <int K> __global__ void kv_clear(VerifyBufs vb, int B)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) vb.flags[b] = 0;
+}
+
+// launch sequence; returns the number of kernels launched or -1
+template <int K>
+static int verify_chunk_t(VerifyBufs &vb, const VerifyTables &vt, int B, const u8 *d_pi, const u8 *d_pk, u8 *d_ok, cudaStream_t st)
+{
+    const VDims d = make_vdims(K);
+    int nl = 0;
+    const int ptiles = (NP + 127) / 128;
+    kv_clear<K><<<(B + 127) / 128, 128, 0, st>>>(vb, B); nl++;
+    kv_setup<K><<<B, 128, 0, st>>>(vb, d_pi, d_pk); nl++;
+    {   // V2: commitments of the opened parties
+        constexpr int NC = 2 * (K + MK + 2 * K + 1);
+        HashSrc hs{vb.CR, (long long)NT * d.crld, d.crld, 1, 0, nullptr, vb.I, NT};
+        k_hash_records<NC><<<dim3(2, B), 128, 0, st>>>(hs, vb.TCR, nullptr, 0, 0); nl++;
+    }
+    k_fs1<K><<<(B + 31) / 32, 32, 0, st>>>(vb.TCR, vb.PW, B); nl++;
+    kv_eval_opened<K><<<B, 320, 0, st>>>(vb); nl++;
+    kv_gather<K><<<dim3(2 * MK + d.n1rows + d.n2rows, B), 128, 0, st>>>(vb, d_pi); nl++;
+    kv_lagrange<<<B, 256, 0, st>>>(vb, vt.inv); nl++;
+    GemmArgs g{};
+    // beta/gamma reconstruction: ABG x R1
+    g = GemmArgs{}; g.A = vb.ABG; g.Bt = vt.R1; g.C = vb.BS; g.lda = YLD; g.ldb = YLD; g.ldc = 256;
+    g.mtotal = B * 2 * MK; g.ksteps = YLD / GE_BK; g.nvalid = 256; g.rpp = g.mtotal; g.c_off = 0;
+    nl += gf_gemm_launch<8>(g, 256, 1, st);
+    kv_check_bg<<<dim3(MK, B), 128, 0, st>>>(vb); nl++;
+    // interpolation-apply, one Lagrange matrix per proof (batched over blockIdx.z)
+    g = GemmArgs{}; g.A = vb.A1; g.Bt = vb.LM1; g.C = vb.YV; g.lda = YLD; g.ldb = YLD; g.ldc = YLD;
+    g.a_batch = (long long)d.n1rows * YLD; g.b_batch = (long long)LM1_ROWS * YLD; g.c_batch = (long long)d.nyrows * YLD;
+    g.mtotal = d.n1rows; g.ksteps = YLD / GE_BK; g.nvalid = D1; g.rpp = g.mtotal;
+    for (int o = 0; o < B; o += 32768) {
+        GemmArgs h = g; const int nb = min(32768, B - o);
+        h.A += (size_t)o * g.a_batch; h.Bt += (size_t)o * g.b_batch; h.C += (size_t)o * g.c_batch;
+        nl += gf_gemm_launch<4>(h, LM1_ROWS, nb, st);
+    }
+    g = GemmArgs{}; g.A = vb.A2; g.Bt = vb.LM2; g.C = vb.UZ; g.lda = VR2LD; g.ldb = VR2LD; g.ldc = 256;
+    g.a_batch = (long long)d.n2rows * VR2LD; g.b_batch = (long long)256 * VR2LD; g.c_batch = (long long)d.n2rows * 256;
+    g.mtotal = d.n2rows; g.ksteps = VR2LD / GE_BK; g.nvalid = 256; g.rpp = g.mtotal;
+    for (int o = 0; o < B; o += 32768) {
+        GemmArgs h = g; const int nb = min(32768, B - o);
+        h.A += (size_t)o * g.a_batch; h.Bt += (size_t)o * g.b_batch; h.C += (size_t)o * g.c_batch;
+        nl += gf_gemm_launch<4>(h, 256, nb, st);
+    }
+    kv_open<K><<<B, 128, 0, st>>>(vb); nl++;
+    // regenerate every sharing at all 1454 parties: YV x S
+    g = GemmArgs{}; g.A = vb.YV; g.Bt = vt.St; g.C = vb.VSH; g.lda = YLD; g.ldb = YLD; g.ldc = SLD;
+    g.mtotal = B * d.nyrows; g.ksteps = YLD / GE_BK; g.nvalid = NX; g.c_off = SOFF + NT + 1; g.rpp = g.mtotal; g.tail = 1;
+    nl += gf_gemm_launch<8>(g, GE_NPAD, 1, st);
+    kv_check_parties<K><<<dim3(ptiles, B), 128, 0, st>>>(vb, d_pi); nl++;
+    g = GemmArgs{}; g.A = vb.U2; g.Bt = vt.R2; g.C = vb.UR; g.lda = VR2LD; g.ldb = VR2LD; g.ldc = 256;
+    g.mtotal = B * d.n2rows; g.ksteps = VR2LD / GE_BK; g.nvalid = 256; g.rpp = g.mtotal;
+    nl += gf_gemm_launch<8>(g, 256, 1, st);
+    {   // V16: view hashes of the opened parties, FS-2, compare
+        constexpr int ETA = (K == 2) ? 3 : 2, NV = 16 + 2 * (K + MK + 2 * K + 1) + 4 * K + 8 * ETA * K;
+        HashSrc hs{vb.VR, (long long)NT * d.vrld, d.vrld, 1, 0, nullptr, vb.I, NT};
+        k_hash_records<NV><<<dim3(2, B), 128, 0, st>>>(hs, vb.VWR, nullptr, 0, 0); nl++;
+    }
+    k_fs2<<<(B + 31) / 32, 32, 0, st>>>(vb.VWR, vb.I2, vb.REST2, B); nl++;
+    kv_final<K><<<B, 128, 0, st>>>(vb, d_ok); nl++;
+    return cudaGetLastError() == cudaSuccess ? nl : -1;
+}
+
+static inline int verify_chunk(int k, VerifyBufs &vb, const VerifyTables &vt, int B, const u8 *d_pi, const u8 *d_pk, u8 *d_ok, cudaStream_t st)
+{
+    switch (k) {
+    case 2: return verify_chunk_t<2>(vb, vt, B, d_pi, d_pk, d_ok, st);
+    case 3: return verify_chunk_t<3>(vb, vt, B, d_pi, d_pk, d_ok, st);
+    default: return verify_chunk_t<4>(vb, vt, B, d_pi, d_pk, d_ok, st);
+    }
+}
+
+}  // namespace kosk

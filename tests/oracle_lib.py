@@ -1,0 +1,142 @@
+"""ctypes bindings of the CPU oracles (TEST INFRASTRUCTURE): the plain-C restatement (oracle/kosk_oracle.c)
+and, when present, the unmodified reference compiled into oracle/_ref/."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+ORACLE_SO = os.path.join(ORACLE_DIR, "_build", "libkosk_oracle.so")
+
+
+class Layout(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int) for n in "k eta F E M".split()] + \
+               [(n, ctypes.c_size_t) for n in "pk_bytes sk_bytes proof_bytes".split()] + \
+               [(n, ctypes.c_size_t) for n in ("o_f o_Tf o_beta o_gamma o_Tcomm o_I o_s o_e o_t o_NTTs o_NTTe o_NTTAr o_NTTAs "
+                                               "o_sr o_er o_seta o_eeta o_ssub o_esub o_zs o_ze o_us o_ue o_comm").split()]
+
+
+class Trace(ctypes.Structure):
+    _fields_ = [("alpha", ctypes.c_uint16 * 78), ("fs1_digest", ctypes.c_uint8 * 32), ("fs2_digest", ctypes.c_uint8 * 32),
+                ("I", ctypes.c_uint16 * 150), ("first_share", ctypes.c_uint16 * 1454), ("first_secret", ctypes.c_uint16 * 256),
+                ("first_ntt", ctypes.c_uint16 * 256), ("tcomm0", ctypes.c_uint8 * 32), ("view0", ctypes.c_uint8 * 32)]
+
+
+FIELDS = [f[0] for f in Layout._fields_[8:]]
+
+
+def build_oracle():
+    if not os.path.exists(ORACLE_SO) or any(
+            os.path.getmtime(os.path.join(ORACLE_DIR, f)) > os.path.getmtime(ORACLE_SO)
+            for f in ("kosk_oracle.c", "kosk_oracle.h", "ok_keccak.h", "ok_rng.c", "ok_tables.c")):
+        subprocess.run(["make", "-C", ORACLE_DIR, "oracle"], check=True, capture_output=True)
+    return ORACLE_SO
+
+
+_oracle = None
+
+
+def oracle():
+    global _oracle
+    if _oracle is None:
+        lib = ctypes.CDLL(build_oracle())
+        vp = ctypes.c_void_p
+        lib.kosk_oracle_layout.argtypes = [ctypes.c_int, ctypes.POINTER(Layout)]
+        lib.kosk_oracle_verifiable_keygen.argtypes = [ctypes.c_int, vp, ctypes.c_int, vp, vp, vp]
+        lib.kosk_oracle_verifiable_keygen.restype = None
+        lib.kosk_oracle_verify.argtypes = [ctypes.c_int, vp, vp]
+        lib.kosk_oracle_last_trace.restype = ctypes.POINTER(Trace)
+        lib.ko_share_ddeg.argtypes = [vp, vp]
+        lib.ko_recon_ddeg.argtypes = [vp, vp]
+        lib.ko_recon_2ddeg.argtypes = [vp, vp]
+        lib.ko_ntt.argtypes = [vp]
+        lib.ko_sha3_256.argtypes = [vp, vp, ctypes.c_size_t]
+        lib.ko_shake256.argtypes = [vp, ctypes.c_size_t, vp, ctypes.c_size_t]
+        lib.ko_shake128.argtypes = [vp, ctypes.c_size_t, vp, ctypes.c_size_t]
+        lib.ko_sha3_512.argtypes = [vp, vp, ctypes.c_size_t]
+        lib.ko_keccak_f1600.argtypes = [vp]
+        lib.ko_randombytes_at.argtypes = [vp, ctypes.c_uint32, vp, ctypes.c_size_t]
+        lib.ko_gen_matrix.argtypes = [ctypes.c_int, vp, vp]
+        _oracle = lib
+    return _oracle
+
+
+def layout(k):
+    L = Layout()
+    assert oracle().kosk_oracle_layout(k, ctypes.byref(L)) == 0
+    return L
+
+
+def _p(a):
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+def oracle_prove(k, seed, rng_mode=0):
+    L = layout(k)
+    seed = np.frombuffer(bytes(seed), dtype=np.uint8).copy()
+    pk, sk, pi = np.zeros(L.pk_bytes, np.uint8), np.zeros(L.sk_bytes, np.uint8), np.zeros(L.proof_bytes, np.uint8)
+    oracle().kosk_oracle_verifiable_keygen(k, _p(seed), rng_mode, _p(pk), _p(sk), _p(pi))
+    return pk, sk, pi
+
+
+def oracle_trace():
+    return oracle().kosk_oracle_last_trace().contents
+
+
+def oracle_verify(k, pi, pk):
+    pi = np.ascontiguousarray(pi, dtype=np.uint8)
+    pk = np.ascontiguousarray(pk, dtype=np.uint8)
+    return oracle().kosk_oracle_verify(k, _p(pi), _p(pk)) == 1
+
+
+def oracle_share(y):
+    y = np.ascontiguousarray(y, dtype=np.uint16)
+    out = np.zeros(1454, np.uint16)
+    oracle().ko_share_ddeg(_p(out), _p(y))
+    return out
+
+
+def oracle_ntt(a):
+    a = np.array(a, dtype=np.uint16)
+    oracle().ko_ntt(_p(a))
+    return a
+
+
+_refs = {}
+
+
+def ref(k):
+    """The unmodified reference (oracle/_ref), or None when it has not been built (e.g. no /root/reference)."""
+    if k not in _refs:
+        path = os.path.join(ORACLE_DIR, "_ref", f"libkosk_ref_k{k}.so")
+        if not os.path.exists(path):
+            _refs[k] = None
+        else:
+            lib = ctypes.CDLL(path)
+            vp = ctypes.c_void_p
+            lib.ref_verifiable_keygen.argtypes = [vp, ctypes.c_int, vp, vp, vp]
+            lib.ref_verifiable_keygen.restype = None
+            lib.ref_kosk_verify.argtypes = [vp, vp]
+            _refs[k] = lib
+    return _refs[k]
+
+
+def ref_prove(k, seed, rng_mode=0):
+    L = layout(k)
+    seed = np.frombuffer(bytes(seed), dtype=np.uint8).copy()
+    pk, sk, pi = np.zeros(L.pk_bytes, np.uint8), np.zeros(L.sk_bytes, np.uint8), np.zeros(L.proof_bytes, np.uint8)
+    ref(k).ref_verifiable_keygen(_p(seed), rng_mode, _p(pk), _p(sk), _p(pi))
+    return pk, sk, pi
+
+
+def ref_verify(k, pi, pk):
+    pi = np.ascontiguousarray(pi, dtype=np.uint8)
+    pk = np.ascontiguousarray(pk, dtype=np.uint8)
+    return ref(k).ref_kosk_verify(_p(pi), _p(pk)) == 1
+
+
+def seed_of(i, tag=b"kosk-b200"):
+    import hashlib
+    return hashlib.sha256(tag + b":" + str(i).encode()).digest()
