@@ -1,0 +1,304 @@
+#!/usr/bin/env python
+"""bench.py -- KOSK proofs/s on B200 (BASELINE.json metric), one JSON line on rank 0.
+
+  python bench.py --gpus N --steps K --warmup W            the CUDA path (this repo)
+  python bench.py --impl reference --gpus N --steps K ...  the reference's CPU implementation (oracle/_ref, else the C port)
+
+A "step" is one pass of the hot path over one batch: kyber_verifiable_keygen for `--batch` independent proofs
+(default: BASELINE configs[1], Kyber512 x 1024) on every rank; ranks are independent (batch mode shards whole proofs,
+no data-path collective), so scaling is weak and `value` = all ranks' proofs / max-over-ranks device time.
+`value` is timed with inputs (seeds) and outputs resident in HBM; `e2e` goes through the host-buffer C-ABI call
+(kosk_b200_prove_batch) with pinned host buffers, so H2D of the seeds and D2H of pk/sk/proof are inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+# Algorithmic work per prove: field MACs and Keccak-f permutations
+MACS_PER_PROVE = {2: 135.14e6, 3: 142.69e6, 4: 160.41e6}
+KECCAK_PER_PROVE = {2: 11196, 3: 11220, 4: 11254}
+SHARE_MACS_PER_ROW = 1303 * 407          # ss.cpp:23-32: one sharing = 1303 x 407 MACs
+INT_OPS_PER_KECCAK = 7440                # 24 rounds x 155 64-bit logic ops x 2 (32-bit lanes)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--kyber-k", type=int, default=2)
+    ap.add_argument("--batch", type=int, default=1024, help="proofs per rank per step")
+    ap.add_argument("--chunk", type=int, default=0, help="proofs per kernel wave (0 = batch)")
+    ap.add_argument("--cpu-sample", type=int, default=8, help="proofs of the bounded single-core CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--verify", action="store_true", help="also time kyber_kosk_verify on the produced proofs")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_oracle():
+    """(kind, prove_fn(k, seed) -> (pk, sk, pi), verify_fn): the unmodified reference if oracle/_ref travelled, else the C port."""
+    import oracle_lib as O
+    if all(O.ref(k) is not None for k in (2, 3, 4)):
+        return "reference", O.ref_prove, O.ref_verify
+    return "port", O.oracle_prove, O.oracle_verify
+
+
+def cpu_baseline(k, nsample):
+    kind, prove, verify = cpu_oracle()
+    import oracle_lib as O
+    prove(k, O.seed_of(0))                                   # warm-up (table generation excluded)
+    t0 = time.perf_counter()
+    outs = [prove(k, O.seed_of(10 + i)) for i in range(nsample)]
+    t1 = time.perf_counter()
+    nv = min(nsample, 4)
+    for pk, sk, pi in outs[:nv]:
+        assert verify(k, pi, pk)
+    t2 = time.perf_counter()
+    return {"value": nsample / (t1 - t0), "unit": "proofs/s", "cores": 1, "kind": kind,
+            "sample": f"{nsample} sequential Kyber{256 * k} kyber_verifiable_keygen calls on one host core (of {os.cpu_count()})",
+            "verify_per_s": nv / (t2 - t1)}
+
+
+def run_reference(args):
+    """The reference's own CPU implementation with every host thread (ctypes releases the GIL)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from concurrent.futures import ThreadPoolExecutor
+    import oracle_lib as O
+    kind, prove, verify = cpu_oracle()
+    k, threads = args.kyber_k, os.cpu_count() or 1
+    per_step = threads                                      # bounded sample: one proof per host thread per step
+    prove(k, O.seed_of(0))
+    pool = ThreadPoolExecutor(threads)
+
+    def step(s):
+        list(pool.map(lambda i: prove(k, O.seed_of(1000 * s + i)), range(per_step)))
+    for w in range(min(args.warmup, 1)):
+        step(-1 - w)
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        step(s)
+    dt = time.perf_counter() - t0
+    val = per_step * args.steps / dt
+    sample = f"{per_step} proofs per step, one per host thread ({threads} threads), of the {args.batch}-proof batch"
+    print(json.dumps({
+        "impl": "reference", "metric": "KOSK proofs/sec (prove)", "value": val, "unit": "proofs/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u16", "data": "synthetic",
+        "config": {"workload": f"Kyber{256 * k} kyber_verifiable_keygen, batch {args.batch} (bounded CPU sample)", "kyber_k": k, "batch": args.batch},
+        "cpu_baseline": {"value": val, "unit": "proofs/s", "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": val, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from mpcith_kyber_kosk_b200 import KoskContext
+    from mpcith_kyber_kosk_b200.sharding import seeds_for_range
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the KOSK core has no CPU path; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    k, B = args.kyber_k, args.batch
+    ctx = KoskContext(k, local, args.chunk or B)
+    npk, nsk, npi = ctx.pk_bytes, ctx.sk_bytes, ctx.proof_bytes
+
+    # device-resident inputs/outputs; a different seed range every step and rank (placement-independent seeds)
+    total_steps = args.warmup + args.steps
+    d_seeds = [torch.from_numpy(seeds_for_range(1 << 32, (s * world + rank) * B, (s * world + rank + 1) * B)).to(dev) for s in range(total_steps)]
+    d_pk = torch.empty(B * npk, dtype=torch.uint8, device=dev)
+    d_sk = torch.empty(B * nsk, dtype=torch.uint8, device=dev)
+    d_pi = torch.empty(B * npi, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(s):
+        ctx.prove_batch_device(B, d_seeds[s].data_ptr(), d_pk.data_ptr(), d_sk.data_ptr(), d_pi.data_ptr(), stream)
+
+    peaks = ctx.int_peak() if rank == 0 else None
+    for s in range(args.warmup):
+        step(s)
+    barrier()
+    ctx.set_profiling(True)
+    ctx.phase_times(reset=True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(args.steps):
+        step(args.warmup + s)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.kernel_launches() - l0
+    phases = ctx.phase_times(reset=True)
+    ctx.set_profiling(False)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+
+    # ---- end to end through the host-buffer C-ABI call, pinned host memory, copies inside the timed region ----
+    h_seeds = [torch.from_numpy(seeds_for_range(1 << 33, (s * world + rank) * B, (s * world + rank + 1) * B)).pin_memory() for s in range(args.steps + 1)]
+    h_pk = torch.empty(B * npk, dtype=torch.uint8).pin_memory()
+    h_sk = torch.empty(B * nsk, dtype=torch.uint8).pin_memory()
+    h_pi = torch.empty(B * npi, dtype=torch.uint8).pin_memory()
+
+    def e2e_step(s):
+        rc = ctx.lib.kosk_b200_prove_batch(ctx._h, B, h_seeds[s].data_ptr(), h_pk.data_ptr(), h_sk.data_ptr(), h_pi.data_ptr())
+        assert rc == 0, ctx.lib.kosk_b200_last_error()
+    e2e_step(args.steps)
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        e2e_step(s)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_max = float(t.item())
+
+    # ---- sanity on the measured outputs: every proof of the last e2e step verifies on the device; rank 0 checks one against the oracle
+    pi_np = h_pi.numpy().reshape(B, npi)
+    pk_np = h_pk.numpy().reshape(B, npk)
+    nver = min(B, 64)
+    tv0 = time.perf_counter()
+    ok = ctx.verify_batch(pi_np[:nver], pk_np[:nver])
+    tv = time.perf_counter() - tv0
+    assert ok.all(), "a measured proof failed verification"
+    verify_stats = None
+    if args.verify:
+        d_ok = torch.empty(B, dtype=torch.uint8, device=dev)
+        d_pi.copy_(h_pi.to(dev)); d_pk.copy_(h_pk.to(dev))
+        ctx.verify_batch_device(B, d_pi.data_ptr(), d_pk.data_ptr(), d_ok.data_ptr(), stream)
+        torch.cuda.synchronize()
+        v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        v0.record()
+        for _ in range(max(1, args.steps // 2)):
+            ctx.verify_batch_device(B, d_pi.data_ptr(), d_pk.data_ptr(), d_ok.data_ptr(), stream)
+        v1.record(); torch.cuda.synchronize()
+        assert bool(d_ok.all())
+        verify_stats = {"verifies_per_s": B * max(1, args.steps // 2) / (v0.elapsed_time(v1) * 1e-3), "batch": B}
+
+    if rank == 0:
+        import oracle_lib as O
+        kind, prove, verify = cpu_oracle()
+        opk, osk, opi = prove(k, bytes(h_seeds[args.steps - 1][0].numpy()))
+        assert (opi == pi_np[0]).all() and (opk == pk_np[0]).all(), "measured proof differs from the CPU oracle"
+        peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        hbm_peak, hbm_src = (json.load(open(peaks_file))["hbm_gbs"], "measured") if os.path.exists(peaks_file) else (6650.0, "fallback")
+        sh_ms, sh_calls = phases["share1"]
+        rows = min(args.chunk or B, B) * ctx_rows(k)          # sharings per launch
+        ms_per_launch = sh_ms / max(sh_calls, 1)
+        macs_per_launch = rows * SHARE_MACS_PER_ROW
+        achieved_tmac = macs_per_launch / (ms_per_launch * 1e-3) / 1e12 if sh_calls else None
+        peak_tmac = peaks["imad"] / 1e12
+        # HBM view of the same kernel: algorithmic bytes = Y rows in (407 x 2 B) + planes out (1454 x 2 B) per sharing
+        bytes_per_launch = macs_per_launch / SHARE_MACS_PER_ROW * (407 + 1454) * 2
+        step_ms = ms_max / args.steps
+        out = {
+            "metric": "KOSK proofs/sec (prove)", "value": world * B * args.steps / (ms_max * 1e-3), "unit": "proofs/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u16", "data": "synthetic",
+            "config": {"workload": f"Kyber{256 * k} kyber_verifiable_keygen, batch of {B} independent proofs per GPU (BASELINE configs[1])",
+                       "kyber_k": k, "batch_per_gpu": B, "chunk": args.chunk or B, "parallelism": f"proof-sharded x{world}, no collective",
+                       "l2": f"per-step working set {B * (npi + 1_500_000) / 1e6:.0f} MB >> 126 MB L2, fresh seeds every step"},
+            "e2e": {"value": world * B * args.steps / e2e_max, "unit": "proofs/s", "h2d_bytes_per_step": B * 32, "d2h_bytes_per_step": B * (npk + nsk + npi)},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "int32-pipe", "kernel": "k_gf_gemm<8> (share evaluation, ss.cpp:23-32)", "achieved": achieved_tmac, "peak": peak_tmac,
+                         "unit": "TMAC/s", "frac": (achieved_tmac / peak_tmac) if achieved_tmac else None, "traffic": None,
+                         "peak_source": "IMAD issue-rate microbenchmark run in this process (MEASURED_PEAKS.json has no integer entry)",
+                         "ms_per_launch": ms_per_launch, "share_of_step": sh_ms / ms if ms else None},
+            "roofline_hbm": {"bound": "hbm", "achieved": bytes_per_launch / (ms_per_launch * 1e-3) / 1e9 if sh_calls else None, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": (bytes_per_launch / (ms_per_launch * 1e-3) / 1e9 / hbm_peak) if sh_calls else None, "peak_source": hbm_src},
+            "int_pipe": {"imad_tops": peaks["imad"] / 1e12, "lop3_tops": peaks["lop3"] / 1e12, "shf_tops": peaks["shf"] / 1e12,
+                         "algorithmic_int_ops_per_proof": 2 * MACS_PER_PROVE[k] + KECCAK_PER_PROVE[k] * INT_OPS_PER_KECCAK,
+                         "whole_job_frac_of_imad_plus_lop3": (world * B * args.steps / (ms_max * 1e-3)) * (2 * MACS_PER_PROVE[k] + KECCAK_PER_PROVE[k] * INT_OPS_PER_KECCAK)
+                         / (world * (peaks["imad"] + peaks["lop3"]))},
+            "phases_ms_per_step": {n: v[0] / args.steps for n, v in phases.items() if v[1]},
+            "verify_check": {"proofs": nver, "all_accept": True, "wall_s": tv},
+        }
+        if verify_stats:
+            out["verify"] = verify_stats
+        if not args.no_cpu_baseline and world == 1:
+            out["cpu_baseline"] = cpu_baseline(k, args.cpu_sample)
+        print(json.dumps(out))
+    ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def ctx_rows(k):
+    """sharings evaluated by the first (dominant) share-eval launch per proof: 2F + 2K(2eta+1) + 2K + 4 eta K."""
+    eta = 3 if k == 2 else 2
+    F = 70 + 2 * k + 1
+    return 2 * F + 2 * k * (2 * eta + 1) + 2 * k + 4 * eta * k
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

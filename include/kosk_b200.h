@@ -76,6 +76,16 @@ uint64_t kosk_b200_kernel_launches(const kosk_b200_ctx *ctx);
 int kosk_b200_debug_fetch(kosk_b200_ctx *ctx, const char *what, void *out, size_t bytes);
 int kosk_b200_sync(kosk_b200_ctx *ctx);
 
+/* Measurement support.  With profiling on, every prove chunk records CUDA events on its launching stream at the
+ * phase boundaries; kosk_b200_phase_times() synchronises and returns accumulated milliseconds and call counts for
+ * the KOSK_PH_* phases (order: keygen, expand, share1, commit, fs1, eval, open, share2, view, fs2, assemble, verify).
+ * kosk_b200_int_peak() runs issue-rate microbenchmarks and returns thread-level ops/s for IMAD, LOP3 and SHF
+ * (the SM integer-pipe roofline denominators). */
+#define KOSK_B200_NPHASE 12
+int kosk_b200_set_profiling(kosk_b200_ctx *ctx, int on);
+int kosk_b200_phase_times(kosk_b200_ctx *ctx, double *ms, uint64_t *calls, int n, int reset);
+int kosk_b200_int_peak(kosk_b200_ctx *ctx, double *ops_per_s);
+
 #ifdef __cplusplus
 }
 #endif

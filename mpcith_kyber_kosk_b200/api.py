@@ -17,6 +17,7 @@ EXPORTS = [
     "kosk_b200_prove_batch", "kosk_b200_verify_batch", "kosk_b200_prove_batch_device", "kosk_b200_verify_batch_device",
     "kosk_b200_share_eval", "kosk_b200_sha3_256_rows", "kosk_b200_ntt_rows", "kosk_b200_share_eval_device",
     "kosk_b200_kernel_launches", "kosk_b200_debug_fetch", "kosk_b200_sync",
+    "kosk_b200_set_profiling", "kosk_b200_phase_times", "kosk_b200_int_peak",
 ]
 
 _lib = None
@@ -58,6 +59,9 @@ def load_library(path=None):
     lib.kosk_b200_kernel_launches.restype = ctypes.c_uint64
     lib.kosk_b200_debug_fetch.argtypes = [vp, ctypes.c_char_p, u8p, sz]
     lib.kosk_b200_sync.argtypes = [vp]
+    lib.kosk_b200_set_profiling.argtypes = [vp, i32]
+    lib.kosk_b200_phase_times.argtypes = [vp, u8p, u8p, i32, i32]
+    lib.kosk_b200_int_peak.argtypes = [vp, u8p]
     if path == LIB_PATH:
         _lib = lib
     return lib
@@ -178,6 +182,22 @@ class KoskContext:
         out = np.zeros(nbytes, np.uint8)
         self._check(self.lib.kosk_b200_debug_fetch(self._h, what.encode(), _ptr(out), nbytes), "debug_fetch")
         return out.view(dtype)
+
+    PHASES = ["keygen", "expand", "share1", "commit", "fs1", "eval", "open", "share2", "view", "fs2", "assemble", "verify"]
+
+    def set_profiling(self, on=True):
+        self._check(self.lib.kosk_b200_set_profiling(self._h, 1 if on else 0), "set_profiling")
+
+    def phase_times(self, reset=True):
+        ms = np.zeros(len(self.PHASES), np.float64)
+        calls = np.zeros(len(self.PHASES), np.uint64)
+        self._check(self.lib.kosk_b200_phase_times(self._h, _ptr(ms), _ptr(calls), len(self.PHASES), 1 if reset else 0), "phase_times")
+        return {n: (float(m), int(c)) for n, m, c in zip(self.PHASES, ms, calls)}
+
+    def int_peak(self):
+        out = np.zeros(3, np.float64)
+        self._check(self.lib.kosk_b200_int_peak(self._h, _ptr(out)), "int_peak")
+        return {"imad": float(out[0]), "lop3": float(out[1]), "shf": float(out[2])}
 
     def sync(self):
         self._check(self.lib.kosk_b200_sync(self._h), "sync")

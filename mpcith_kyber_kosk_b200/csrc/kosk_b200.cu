@@ -10,6 +10,7 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <utility>
 
 using namespace kosk;
 
@@ -42,6 +43,9 @@ static void h_lagrange(std::vector<uint16_t> &out, const std::vector<int> &nodes
     }
 }
 
+enum { KOSK_PH_KEYGEN = 0, KOSK_PH_EXPAND, KOSK_PH_SHARE1, KOSK_PH_COMMIT, KOSK_PH_FS1, KOSK_PH_EVAL, KOSK_PH_OPEN, KOSK_PH_SHARE2,
+       KOSK_PH_VIEW, KOSK_PH_FS2, KOSK_PH_ASSEMBLE, KOSK_PH_VERIFY, KOSK_NPHASE };
+
 struct kosk_b200_ctx {
     int k = 0, device = 0, chunk = 0;
     Slots sl; Layout L;
@@ -58,7 +62,30 @@ struct kosk_b200_ctx {
     u8 *d_seeds = nullptr, *d_pk = nullptr, *d_sk = nullptr, *d_pi = nullptr, *d_ok = nullptr; // staging of the host API
     VerifyBufs vb{};
     void *h_pin = nullptr; size_t h_pin_bytes = 0;
+    // optional phase timing with CUDA events on the launching stream (bench.py roofline)
+    bool prof = false;
+    std::vector<cudaEvent_t> ev; int ev_used = 0;
+    std::vector<std::pair<int, int>> ev_phase;     // (phase id, event index of its start); end = next event
+    double phase_ms[KOSK_NPHASE] = {0}; uint64_t phase_calls[KOSK_NPHASE] = {0};
 };
+
+static void prof_mark(kosk_b200_ctx *c, int phase, cudaStream_t st)
+{
+    if (!c->prof) return;
+    if (c->ev_used >= (int)c->ev.size()) { cudaEvent_t e; cudaEventCreate(&e); c->ev.push_back(e); }
+    cudaEventRecord(c->ev[c->ev_used], st);
+    c->ev_phase.push_back({phase, c->ev_used});
+    c->ev_used++;
+}
+static void prof_collect(kosk_b200_ctx *c)
+{
+    for (size_t i = 0; i + 1 < c->ev_phase.size(); i++) {
+        const int ph = c->ev_phase[i].first;
+        if (ph < 0) continue;
+        float ms = 0; if (cudaEventElapsedTime(&ms, c->ev[c->ev_phase[i].second], c->ev[c->ev_phase[i + 1].second]) == cudaSuccess) { c->phase_ms[ph] += ms; c->phase_calls[ph]++; }
+    }
+    c->ev_phase.clear(); c->ev_used = 0;
+}
 
 static void ctx_free(kosk_b200_ctx *c)
 {
@@ -69,6 +96,7 @@ static void ctx_free(kosk_b200_ctx *c)
     for (void *p : ptrs) if (p) cudaFree(p);
     verify_free(c->vb);
     if (c->h_pin) cudaFreeHost(c->h_pin);
+    for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -182,22 +210,34 @@ static int prove_chunk(kosk_b200_ctx *c, int B, const u8 *d_seeds, u8 *d_pk, u8 
     constexpr int NCOMMIT = 2 * (K + MK + 2 * K + 1), ETA = (K == 2) ? 3 : 2;
     constexpr int NVIEW = 16 + NCOMMIT + 4 * K + 8 * ETA * K;
     const int ptiles = (NP + 127) / 128;
+    prof_mark(c, KOSK_PH_KEYGEN, st);
     k_keygen<K><<<B, 128, 0, st>>>(pb);
+    prof_mark(c, KOSK_PH_EXPAND, st);
     k_expand_f<K><<<(B * sl.F + 63) / 64, 64, 0, st>>>(pb);
     k_ntt_f<K><<<dim3(sl.F, B), 128, 0, st>>>(pb);
     k_tails<K><<<(B * (sl.n1 + K) + 63) / 64, 64, 0, st>>>(pb);
+    prof_mark(c, KOSK_PH_SHARE1, st);
     launch_share_eval(c, pb.Y, pb.SH, 0, sl.n1, sl.n2, sl.nslot, B, st);
+    prof_mark(c, KOSK_PH_COMMIT, st);
     HashSrc hc{pb.SH, (long long)sl.nslot * SLD, 1, SLD, SOFF, c->d_tab_commit, nullptr, 0};
     k_hash_records<NCOMMIT><<<dim3(ptiles, B), 128, 0, st>>>(hc, pb.TCR, pb.SH, sl.nslot, sl.TC0);
+    prof_mark(c, KOSK_PH_FS1, st);
     k_fs1<K><<<(B + 31) / 32, 32, 0, st>>>(pb.TCR, pb.PW, B);
+    prof_mark(c, KOSK_PH_EVAL, st);
     k_eval<K><<<dim3(ptiles, B), 256, 0, st>>>(pb);
+    prof_mark(c, KOSK_PH_OPEN, st);
     k_open<K><<<B, 128, 0, st>>>(pb);
+    prof_mark(c, KOSK_PH_SHARE2, st);
     launch_share_eval(c, pb.Y, pb.SH, sl.n1, 4 * K, sl.n2, sl.nslot, B, st);
+    prof_mark(c, KOSK_PH_VIEW, st);
     k_derive<K><<<dim3(ptiles, B), 128, 0, st>>>(pb);
     HashSrc hv{pb.SH, (long long)sl.nslot * SLD, 1, SLD, SOFF, c->d_tab_view, nullptr, 0};
     k_hash_records<NVIEW><<<dim3(ptiles, B), 128, 0, st>>>(hv, pb.VWR, nullptr, 0, 0);
+    prof_mark(c, KOSK_PH_FS2, st);
     k_fs2<<<(B + 31) / 32, 32, 0, st>>>(pb.VWR, pb.I, pb.REST, B);
+    prof_mark(c, KOSK_PH_ASSEMBLE, st);
     k_assemble<K><<<dim3((NT + 31) / 32 + (NR + 31) / 32, B), 128, 0, st>>>(pb);
+    prof_mark(c, -1, st);
     c->launches += 12;
     c->lastB = B;
     CU(cudaGetLastError());
@@ -299,7 +339,9 @@ int kosk_b200_verify_batch_device(kosk_b200_ctx *c, size_t n, const uint8_t *d_p
     for (size_t o = 0; o < n; o += c->chunk) {
         const int B = (int)std::min<size_t>(c->chunk, n - o);
         VerifyTables vt{c->d_St, c->d_R1, c->d_R2, c->d_inv};
+        prof_mark(c, KOSK_PH_VERIFY, (cudaStream_t)stream);
         int nl = verify_chunk(c->k, c->vb, vt, B, d_pi + L.proof_bytes * o, d_pk + L.pk_bytes * o, d_ok + o, (cudaStream_t)stream);
+        prof_mark(c, -1, (cudaStream_t)stream);
         if (nl < 0) return fail(KOSK_E_CUDA, "verify launch failed");
         c->launches += nl;
         CU(cudaGetLastError());
@@ -415,4 +457,73 @@ int kosk_b200_debug_fetch(kosk_b200_ctx *c, const char *what, void *out, size_t 
     return KOSK_OK;
 }
 
+
+int kosk_b200_set_profiling(kosk_b200_ctx *c, int on)
+{
+    if (!c) return fail(KOSK_E_ARG, "null argument");
+    c->prof = on != 0;
+    return KOSK_OK;
+}
+
+int kosk_b200_phase_times(kosk_b200_ctx *c, double *ms, uint64_t *calls, int n, int reset)
+{
+    if (!c || !ms || !calls) return fail(KOSK_E_ARG, "null argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaDeviceSynchronize());
+    prof_collect(c);
+    for (int i = 0; i < n && i < KOSK_NPHASE; i++) { ms[i] = c->phase_ms[i]; calls[i] = c->phase_calls[i]; }
+    if (reset) for (int i = 0; i < KOSK_NPHASE; i++) { c->phase_ms[i] = 0; c->phase_calls[i] = 0; }
+    return KOSK_OK;
+}
+
 }  // extern "C"
+
+// ---- integer-pipe issue-rate microbenchmarks (roofline denominators; MEASURED_PEAKS.json has no integer entry) ----
+template <int MODE>
+__global__ void __launch_bounds__(256) k_int_peak(uint32_t *out, int iters, uint32_t seed)
+{
+    uint32_t r[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) r[i] = seed * (threadIdx.x + 1) + i * 0x9E3779B9u;
+    const uint32_t m = seed | 1u, x = seed * 0x85EBCA6Bu + 3u;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                if (MODE == 0) r[i] = r[i] * m + x;                                   // IMAD (fma pipe)
+                else if (MODE == 1) r[i] = (r[i] & m) ^ (r[(i + 1) & 15] | x);          // LOP3 (alu pipe)
+                else r[i] = __funnelshift_l(r[i], r[(i + 5) & 15], 7);                 // SHF (alu pipe)
+            }
+    }
+    uint32_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) acc ^= r[i];
+    if (acc == 0x12345678u) out[blockIdx.x] = acc;      // keeps the chain live
+}
+
+extern "C" int kosk_b200_int_peak(kosk_b200_ctx *c, double *ops_per_s /* [3]: IMAD, LOP3, SHF thread-ops/s */)
+{
+    if (!c || !ops_per_s) return fail(KOSK_E_ARG, "null argument");
+    CU(cudaSetDevice(c->device));
+    cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, c->device));
+    const int blocks = prop.multiProcessorCount * 8, iters = 4096;
+    uint32_t *d = nullptr; CU(cudaMalloc(&d, blocks * 4));
+    cudaEvent_t e0, e1; CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    for (int mode = 0; mode < 3; mode++) {
+        float best = 1e30f;
+        for (int rep = 0; rep < 4; rep++) {
+            CU(cudaEventRecord(e0, c->stream));
+            if (mode == 0) k_int_peak<0><<<blocks, 256, 0, c->stream>>>(d, iters, 12345u + rep);
+            else if (mode == 1) k_int_peak<1><<<blocks, 256, 0, c->stream>>>(d, iters, 12345u + rep);
+            else k_int_peak<2><<<blocks, 256, 0, c->stream>>>(d, iters, 12345u + rep);
+            CU(cudaEventRecord(e1, c->stream));
+            CU(cudaEventSynchronize(e1));
+            float ms = 0; CU(cudaEventElapsedTime(&ms, e0, e1));
+            if (rep > 0 && ms < best) best = ms;
+        }
+        ops_per_s[mode] = (double)blocks * 256.0 * iters * 64.0 / (best * 1e-3);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    return KOSK_OK;
+}

@@ -1,0 +1,57 @@
+"""CPU suite: the C-ABI library builds for sm_100a, loads, exports every symbol include/kosk_b200.h declares,
+reports the reference's sizes, and fails loudly without a CUDA device (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+import mpcith_kyber_kosk_b200 as pkg
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "kosk_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(kosk_b200_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    lib = ctypes.CDLL(built_lib)
+    names = _declared()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/kosk_b200.h but not exported"
+    assert sorted(pkg.EXPORTS) == names
+
+
+def test_sizes_match_reference(built_lib):
+    assert [(pkg.pk_bytes(k), pkg.sk_bytes(k), pkg.proof_bytes(k)) for k in (2, 3, 4)] == \
+        [(800, 1632, 664340), (1184, 2400, 680980), (1568, 3168, 744148)]
+    assert pkg.proof_bytes(5) == 0
+
+
+def test_bad_arguments(built_lib):
+    lib = pkg.load_library()
+    h = ctypes.c_void_p()
+    assert lib.kosk_b200_create(ctypes.byref(h), 7, 0, 0) == -1
+    assert b"kyber_k" in lib.kosk_b200_last_error()
+
+
+def test_no_cpu_fallback(built_lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(pkg.KoskError, match="no CUDA device"):
+        pkg.KoskContext(2)
+
+
+def test_sass_is_sm100a(built_lib):
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([cuobjdump, "-lelf", built_lib], capture_output=True, text=True).stdout
+    assert "sm_100a" in out

@@ -1,0 +1,199 @@
+"""GPU suite (-m gpu): the CUDA path through the C ABI against the oracle and the reference-generated golden
+vectors: bit-exact pk / sk / proof bytes and verify result (integer work, so no tolerance)."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from mpcith_kyber_kosk_b200.sharding import seeds_for_range
+
+pytestmark = pytest.mark.gpu
+GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "kosk_golden.json")))
+
+
+def test_native_library_is_loaded(ctxs):
+    ctx = ctxs(2)
+    assert any("libkosk_b200.so" in l for l in open("/proc/self/maps"))
+    n0 = ctx.kernel_launches()
+    ctx.ntt_rows(np.zeros((1, 256), np.uint16))
+    assert ctx.kernel_launches() == n0 + 1
+
+
+# ---------------- components (BASELINE config 5) ----------------
+@pytest.mark.parametrize("rows", [1, 8, 214, 300])
+def test_share_eval_sweep(ctxs, rows):
+    rng = np.random.default_rng(rows)
+    y = rng.integers(0, 3329, size=(rows, 407), dtype=np.uint16)
+    y[0] = 3328                                    # worst-case magnitude for the lazy int32 accumulation
+    if rows > 1:
+        y[1] = 0
+    got = ctxs(2).share_eval(y)
+    for i in sorted(set([0, 1 % rows, rows - 1, rows // 2])):
+        assert (got[i] == O.oracle_share(y[i])).all()
+    assert (got[:, :151] == y[:, 256:]).all()
+
+
+def test_share_eval_linearity_full_size(ctxs):
+    """Size-independent property at a batch the oracle could not finish quickly: S is linear over GF(3329)."""
+    rng = np.random.default_rng(5)
+    n = 214 * 64
+    a = rng.integers(0, 3329, size=(n, 407), dtype=np.uint16)
+    b = rng.integers(0, 3329, size=(n, 407), dtype=np.uint16)
+    ctx = ctxs(2)
+    sa, sb = ctx.share_eval(a), ctx.share_eval(b)
+    sab = ctx.share_eval(((a.astype(np.uint32) + b) % 3329).astype(np.uint16))
+    assert (sab == (sa.astype(np.uint32) + sb) % 3329).all()
+    assert (sa[7] == O.oracle_share(a[7])).all() and (sa[n - 1] == O.oracle_share(a[n - 1])).all()
+
+
+@pytest.mark.parametrize("length", [0, 2, 134, 136, 138, 272, 308, 320, 332, 452, 472, 524])
+def test_sha3_rows(ctxs, length):
+    rng = np.random.default_rng(length)
+    rows = rng.integers(0, 256, size=(33, max(length, 1)), dtype=np.uint8)[:, :length]
+    got = ctxs(2).sha3_256_rows(np.ascontiguousarray(rows))
+    for h, r in zip(got, rows):
+        assert bytes(h) == hashlib.sha3_256(bytes(r)).digest()
+
+
+def test_ntt_rows(ctxs):
+    rng = np.random.default_rng(9)
+    a = rng.integers(0, 3329, size=(17, 256), dtype=np.uint16)
+    a[0] = 3328
+    got = ctxs(2).ntt_rows(a)
+    assert (got == np.stack([O.oracle_ntt(r) for r in a])).all()
+
+
+# ---------------- prove ----------------
+@pytest.mark.parametrize("case", GOLDEN["cases"], ids=lambda c: f"k{c['k']}s{c['seed_index']}")
+def test_prove_matches_reference_golden(ctxs, case):
+    ctx = ctxs(case["k"])
+    pk, sk, pi = ctx.verifiable_keygen(bytes.fromhex(case["seed"]))
+    assert hashlib.sha256(pk).hexdigest() == case["pk_sha256"]
+    assert hashlib.sha256(sk).hexdigest() == case["sk_sha256"]
+    assert hashlib.sha256(pi).hexdigest() == case["proof_sha256"]
+    assert ctx.kosk_verify(pi, pk) is True
+
+
+@pytest.mark.parametrize("k", [2, 3, 4])
+def test_prove_batch_matches_oracle(ctxs, k):
+    """A ragged batch (not a multiple of the chunk, spans two chunks) against the oracle, byte for byte."""
+    ctx = ctxs(k, 8)
+    n = 11
+    seeds = np.stack([np.frombuffer(O.seed_of(1000 + i), np.uint8) for i in range(n)])
+    pk, sk, pi = ctx.prove_batch(seeds)
+    for i in range(n):
+        opk, osk, opi = O.oracle_prove(k, seeds[i])
+        assert (pk[i] == opk).all() and (sk[i] == osk).all() and (pi[i] == opi).all(), i
+    # intermediates of the last chunk (proofs 8..10) against the oracle's trace of proof 10
+    tr = O.oracle_trace()
+    F, NA = 70 + 2 * k + 1, 70 + 2 * k
+    pw = ctx.debug_fetch("alpha_pow", 8 * NA * F * 2, np.uint16).reshape(8, NA, F)
+    assert (pw[2, :, 1] == np.array(tr.alpha[:NA])).all() and (pw[2, :, 0] == 1).all()
+    I = ctx.debug_fetch("I", 8 * 150 * 2, np.uint16).reshape(8, 150)
+    assert (I[2] == np.array(tr.I[:])).all() and len(set(I[2])) == 150
+
+
+def test_prove_empty_batch(ctxs):
+    pk, sk, pi = ctxs(2).prove_batch(np.zeros((0, 32), np.uint8))
+    assert pk.shape == (0, 800) and pi.shape == (0, 664340)
+
+
+def test_prove_is_placement_independent(ctxs):
+    """Same seeds through different chunkings / batch positions give the same bytes."""
+    seeds = seeds_for_range(5, 0, 6)
+    a = ctxs(2, 8).prove_batch(seeds)
+    b = ctxs(2, 64).prove_batch(seeds[::-1].copy())
+    for x, y in zip(a, b):
+        assert (x == y[::-1]).all()
+
+
+# ---------------- verify ----------------
+@pytest.mark.parametrize("k", [2, 3, 4])
+def test_verify_tamper_matrix_matches_reference(ctxs, k):
+    """Accept/reject parity with the reference (golden), incl. the 7 lax accepts."""
+    tam = GOLDEN["tamper"][str(k)]
+    ctx = ctxs(k)
+    L = O.layout(k)
+    opk, osk, opi = O.oracle_prove(k, O.seed_of(0))
+    names, cases = [], []
+    offs = [(n, getattr(L, n)) for n in O.FIELDS] + [("end", L.proof_bytes)]
+    for (n, o), (_, e) in zip(offs[:-1], offs[1:]):
+        step = 1 if n in ("o_Tcomm", "o_comm") else 2
+        for tag, off in (("first", o), ("last", e - step)):
+            t = opi.copy(); t[off] ^= 1
+            names.append(f"{n[2:]}:{tag}"); cases.append(t)
+    got = ctx.verify_batch(np.stack(cases), np.repeat(opk[None], len(cases), 0))
+    for nme, g in zip(names, got):
+        assert bool(g) == tam[nme], nme
+    assert int(got.sum()) == 7
+    for tag, off in (("pk:t", 5), ("pk:seed", -1)):
+        t = opk.copy(); t[off] ^= 1
+        assert ctx.kosk_verify(bytes(opi), bytes(t)) == tam[tag]
+
+
+@pytest.mark.parametrize("k", [2, 3])
+def test_verify_random_tampering_matches_oracle(ctxs, k):
+    """Random single-byte corruption anywhere in the proof (incl. non-canonical field elements >= q)."""
+    rng = np.random.default_rng(40 + k)
+    ctx = ctxs(k)
+    opk, osk, opi = O.oracle_prove(k, O.seed_of(2))
+    cases = []
+    for _ in range(24):
+        t = opi.copy(); off = int(rng.integers(0, t.size)); t[off] ^= int(rng.integers(1, 256)); cases.append(t)
+    got = ctx.verify_batch(np.stack(cases), np.repeat(opk[None], len(cases), 0))
+    exp = [O.oracle_verify(k, t, opk) for t in cases]
+    assert [bool(g) for g in got] == exp
+
+
+def test_verify_rejects_malformed_open_set(ctxs):
+    k = 2
+    L = O.layout(k)
+    ctx = ctxs(k)
+    opk, osk, opi = O.oracle_prove(k, O.seed_of(1))
+    t = opi.copy(); t[L.o_I:L.o_I + 2] = np.frombuffer((1454).to_bytes(2, "little"), np.uint8)
+    assert ctx.kosk_verify(bytes(t), bytes(opk)) is False
+    t = opi.copy(); t[L.o_I + 2:L.o_I + 4] = t[L.o_I:L.o_I + 2]
+    assert ctx.kosk_verify(bytes(t), bytes(opk)) is False
+    t = opi.copy(); t[L.o_I:L.o_I + 300] = 0xFF
+    assert ctx.kosk_verify(bytes(t), bytes(opk)) is False
+    assert ctx.kosk_verify(bytes(opi), bytes(opk)) is True            # context still healthy afterwards
+
+
+def test_verify_noncanonical_values_match_oracle(ctxs):
+    """Shares shifted by q in fields the reference reduces silently (t, eta, u) and in fields it compares raw."""
+    k = 2
+    L = O.layout(k)
+    ctx = ctxs(k)
+    opk, osk, opi = O.oracle_prove(k, O.seed_of(3))
+    cases = []
+    for off in (L.o_t, L.o_seta, L.o_us, L.o_sr, L.o_beta, L.o_f, L.o_s, L.o_zs, L.o_ssub, L.o_NTTAs):
+        t = opi.copy(); v = int(t[off:off + 2].view(np.uint16)[0]) + 3329
+        t[off:off + 2] = np.frombuffer(v.to_bytes(2, "little"), np.uint8); cases.append(t)
+    got = ctx.verify_batch(np.stack(cases), np.repeat(opk[None], len(cases), 0))
+    exp = [O.oracle_verify(k, t, opk) for t in cases]
+    assert [bool(g) for g in got] == exp
+    assert any(exp) and not all(exp)
+
+
+# ---------------- BASELINE config 2 at full size: properties + sampled bit-exactness ----------------
+def test_full_batch_1024_k2(ctxs):
+    ctx = ctxs(2, 1024)
+    n = 1024
+    seeds = seeds_for_range(20240, 0, n)
+    pk, sk, pi = ctx.prove_batch(seeds)
+    ok = ctx.verify_batch(pi, pk)
+    assert ok.all()                                              # prove -> verify round trip for every proof
+    L = O.layout(2)
+    I = pi[:, L.o_I:L.o_I + 300].copy().view(np.uint16)
+    assert (I < 1454).all() and all(len(set(r)) == 150 for r in I)
+    assert len({hashlib.sha256(p).digest() for p in pk}) == n    # all keys distinct
+    for i in (0, 1, 511, 1023):                                  # sampled bit-exactness against the oracle
+        opk, osk, opi = O.oracle_prove(2, seeds[i])
+        assert (pk[i] == opk).all() and (sk[i] == osk).all() and (pi[i] == opi).all()
+    # erase-and-check: swapping two proofs' keys must be rejected
+    swapped = pk.copy(); swapped[[0, 1]] = swapped[[1, 0]]
+    ok2 = ctx.verify_batch(pi[:4], swapped[:4])
+    assert list(ok2) == [False, False, True, True]

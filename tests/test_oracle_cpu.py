@@ -1,0 +1,139 @@
+"""CPU suite: pins the oracle (plain-C restatement, oracle/kosk_oracle.c) against
+ - FIPS-202 known answers (hashlib),
+ - the mathematical identities that force the regenerated Lagrange tables,
+ - golden vectors produced by the UNMODIFIED reference (tests/golden/kosk_golden.json, generator committed),
+ - the reference itself (oracle/_ref) when it is present in this checkout.
+No GPU needed."""
+import ctypes
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "kosk_golden.json")))
+SIZES = {2: (800, 1632, 664340), 3: (1184, 2400, 680980), 4: (1568, 3168, 744148)}
+
+
+def _p(a):
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+@pytest.mark.parametrize("n", [0, 1, 31, 32, 71, 72, 73, 135, 136, 137, 271, 272, 308, 452, 524, 1568, 46528])
+def test_fips202_known_answers(n):
+    msg = np.frombuffer(hashlib.shake_128(b"m%d" % n).digest(max(n, 1)), np.uint8)[:n].copy()
+    buf = msg if n else np.zeros(1, np.uint8)
+    h = np.zeros(32, np.uint8); O.oracle().ko_sha3_256(_p(h), _p(buf), n)
+    assert bytes(h) == hashlib.sha3_256(bytes(msg)).digest()
+    h = np.zeros(64, np.uint8); O.oracle().ko_sha3_512(_p(h), _p(buf), n)
+    assert bytes(h) == hashlib.sha3_512(bytes(msg)).digest()
+    out = np.zeros(600, np.uint8); O.oracle().ko_shake256(_p(out), 600, _p(buf), n)
+    assert bytes(out) == hashlib.shake_256(bytes(msg)).digest(600)
+    out = np.zeros(700, np.uint8); O.oracle().ko_shake128(_p(out), 700, _p(buf), n)
+    assert bytes(out) == hashlib.shake_128(bytes(msg)).digest(700)
+
+
+def test_drbg_definition():
+    seed = np.frombuffer(O.seed_of(3), np.uint8).copy()
+    for call, n in [(0, 64), (1, 32), (77, 302), (283, 302)]:
+        out = np.zeros(n, np.uint8)
+        O.oracle().ko_randombytes_at(_p(seed), call, _p(out), n)
+        assert bytes(out) == hashlib.shake_256(bytes(seed) + call.to_bytes(4, "little")).digest(n)
+
+
+def test_layout_sizes():
+    for k, (pk, sk, pi) in SIZES.items():
+        L = O.layout(k)
+        assert (L.pk_bytes, L.sk_bytes, L.proof_bytes) == (pk, sk, pi)
+    L = O.layout(2)   # spot offsets from SURVEY Appendix B
+    assert (L.o_beta, L.o_Tcomm, L.o_I, L.o_t, L.o_sr, L.o_seta, L.o_us, L.o_comm) == (45000, 410120, 451848, 453348, 460964, 471396, 560020, 622612)
+
+
+def test_share_table_identities():
+    """Row sums of a Lagrange basis are 1 (constant secrets share to constants); share -> recon is the identity."""
+    rng = np.random.default_rng(1)
+    c = np.full(407, 1234, np.uint16)
+    assert (O.oracle_share(c) == 1234).all()
+    y = rng.integers(0, 3329, 407, dtype=np.uint16)
+    sh = O.oracle_share(y)
+    assert (sh[:151] == y[256:]).all()
+    sec = np.zeros(256, np.uint16); first = sh[:407].copy(); O.oracle().ko_recon_ddeg(_p(sec), _p(first))
+    assert (sec == y[:256]).all()
+    # product of two d-sharings reconstructs (2d) to the pointwise product of the secrets
+    y2 = rng.integers(0, 3329, 407, dtype=np.uint16)
+    prod = ((sh.astype(np.uint32) * O.oracle_share(y2)) % 3329).astype(np.uint16)
+    sec2 = np.zeros(256, np.uint16); first2 = prod[:813].copy(); O.oracle().ko_recon_2ddeg(_p(sec2), _p(first2))
+    assert (sec2 == (y[:256].astype(np.uint32) * y2[:256] % 3329)).all()
+
+
+def test_ntt_matches_reference_zetas():
+    """kyber/ntt.c:39-40: zetas[0] = -1044 = 2^16 mod q (centered), zetas[1] = -758 = 17^64 * 2^16; the first
+    butterfly layer multiplies by zetas[1], i.e. by 17^64 in plain residues."""
+    assert (1 << 16) % 3329 == (-1044) % 3329
+    assert (pow(17, 64, 3329) * (1 << 16)) % 3329 == (-758) % 3329
+    a = np.zeros(256, np.uint16); a[128] = 1
+    out = O.oracle_ntt(a)
+    assert out[0] == pow(17, 64, 3329) and out[128] == (3329 - pow(17, 64, 3329))
+
+
+@pytest.mark.parametrize("case", GOLDEN["cases"], ids=lambda c: f"k{c['k']}s{c['seed_index']}")
+def test_oracle_matches_reference_golden(case):
+    k = case["k"]
+    seed = bytes.fromhex(case["seed"])
+    assert seed == O.seed_of(case["seed_index"])
+    pk, sk, pi = O.oracle_prove(k, seed)
+    assert hashlib.sha256(pk).hexdigest() == case["pk_sha256"]
+    assert hashlib.sha256(sk).hexdigest() == case["sk_sha256"]
+    assert hashlib.sha256(pi).hexdigest() == case["proof_sha256"]
+    L = O.layout(k)
+    assert [int(x) for x in pi[L.o_I:L.o_I + 300].view(np.uint16)] == case["I"]
+    if case["seed_index"] == 0:
+        assert O.oracle_verify(k, pi, pk) == case["verify"] is True
+
+
+@pytest.mark.parametrize("k", [2, 3, 4])
+def test_oracle_verify_tamper_matrix_matches_reference(k):
+    """Accept/reject of the reference under single-bit tampering, from the golden file."""
+    tam = GOLDEN["tamper"][str(k)]
+    L = O.layout(k)
+    pk, sk, pi = O.oracle_prove(k, O.seed_of(0))
+    offs = [(n, getattr(L, n)) for n in O.FIELDS] + [("end", L.proof_bytes)]
+    accepted = []
+    for (n, o), (_, e) in zip(offs[:-1], offs[1:]):
+        step = 1 if n in ("o_Tcomm", "o_comm") else 2
+        for tag, off in (("first", o), ("last", e - step)):
+            t = pi.copy(); t[off] ^= 1
+            got = O.oracle_verify(k, t, pk)
+            assert got == tam[f"{n[2:]}:{tag}"], (n, tag)
+            if got:
+                accepted.append(f"{n[2:]}:{tag}")
+    assert sorted(accepted) == sorted(x for x, v in tam.items() if v)
+    t = pk.copy(); t[5] ^= 1
+    assert O.oracle_verify(k, pi, t) == tam["pk:t"]
+    t = pk.copy(); t[-1] ^= 1
+    assert O.oracle_verify(k, pi, t) == tam["pk:seed"]
+
+
+def test_oracle_rejects_malformed_I():
+    k = 2
+    L = O.layout(k)
+    pk, sk, pi = O.oracle_prove(k, O.seed_of(1))
+    t = pi.copy(); t[L.o_I:L.o_I + 2] = np.frombuffer((1454).to_bytes(2, "little"), np.uint8)
+    assert not O.oracle_verify(k, t, pk)
+    t = pi.copy(); t[L.o_I + 2:L.o_I + 4] = t[L.o_I:L.o_I + 2]       # duplicate index
+    assert not O.oracle_verify(k, t, pk)
+
+
+@pytest.mark.parametrize("k", [2, 3, 4])
+def test_oracle_matches_reference_live(k):
+    """Only where oracle/_ref was built (needs /root/reference at build time)."""
+    if O.ref(k) is None:
+        pytest.skip("oracle/_ref not built in this checkout")
+    seed = O.seed_of(100 + k)
+    a = O.ref_prove(k, seed); b = O.oracle_prove(k, seed)
+    for x, y in zip(a, b):
+        assert (x == y).all()
+    assert O.ref_verify(k, a[2], a[0]) and O.oracle_verify(k, a[2], a[0])
