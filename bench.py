@@ -37,7 +37,8 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--kyber-k", type=int, default=2)
     ap.add_argument("--batch", type=int, default=1024, help="proofs per rank per step")
-    ap.add_argument("--chunk", type=int, default=0, help="proofs per kernel wave (0 = batch)")
+    ap.add_argument("--chunk", type=int, default=0, help="proofs per kernel wave (0 = batch / lanes)")
+    ap.add_argument("--lanes", type=int, default=2, help="pipeline lanes (CUDA streams with their own scratch)")
     ap.add_argument("--cpu-sample", type=int, default=8, help="proofs of the bounded single-core CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--verify", action="store_true", help="also time kyber_kosk_verify on the produced proofs")
@@ -151,7 +152,8 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     k, B = args.kyber_k, args.batch
-    ctx = KoskContext(k, local, args.chunk or B)
+    chunk = args.chunk or -(-B // args.lanes)
+    ctx = KoskContext(k, local, chunk, args.lanes)
     npk, nsk, npi = ctx.pk_bytes, ctx.sk_bytes, ctx.proof_bytes
 
     # device-resident inputs/outputs; a different seed range every step and rank (placement-independent seeds)
@@ -247,7 +249,7 @@ def run_b200(args):
         peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
         hbm_peak, hbm_src = (json.load(open(peaks_file))["hbm_gbs"], "measured") if os.path.exists(peaks_file) else (6650.0, "fallback")
         sh_ms, sh_calls = phases["share1"]
-        rows = min(args.chunk or B, B) * ctx_rows(k)          # sharings per launch
+        rows = min(chunk, B) * ctx_rows(k)                    # sharings per launch
         ms_per_launch = sh_ms / max(sh_calls, 1)
         macs_per_launch = rows * SHARE_MACS_PER_ROW
         achieved_tmac = macs_per_launch / (ms_per_launch * 1e-3) / 1e12 if sh_calls else None
@@ -260,7 +262,7 @@ def run_b200(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u16", "data": "synthetic",
             "config": {"workload": f"Kyber{256 * k} kyber_verifiable_keygen, batch of {B} independent proofs per GPU (BASELINE configs[1])",
-                       "kyber_k": k, "batch_per_gpu": B, "chunk": args.chunk or B, "parallelism": f"proof-sharded x{world}, no collective",
+                       "kyber_k": k, "batch_per_gpu": B, "chunk": chunk, "lanes": args.lanes, "parallelism": f"proof-sharded x{world}, no collective",
                        "l2": f"per-step working set {B * (npi + 1_500_000) / 1e6:.0f} MB >> 126 MB L2, fresh seeds every step"},
             "e2e": {"value": world * B * args.steps / e2e_max, "unit": "proofs/s", "h2d_bytes_per_step": B * 32, "d2h_bytes_per_step": B * (npk + nsk + npi)},
             "gpu_launches": launches,

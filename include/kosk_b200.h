@@ -41,6 +41,10 @@ const char *kosk_b200_version(void);
 /* Context: one per (device, KYBER_K).  max_chunk = proofs processed per kernel wave (scratch is sized for
  * it; 0 = default).  Replaces the reference's compile-time -DKYBER_K (params.hpp:8-10). */
 int kosk_b200_create(kosk_b200_ctx **ctx, int kyber_k, int device, int max_chunk);
+/* Same, with the number of pipeline lanes made explicit (0 = default 2).  A batch is split into sub-batches of at
+ * most max_chunk proofs that run on `lanes` CUDA streams, each with its own scratch, so that sub-batches overlap. */
+int kosk_b200_create_ex(kosk_b200_ctx **ctx, int kyber_k, int device, int max_chunk, int lanes);
+int kosk_b200_lanes(const kosk_b200_ctx *ctx);
 void kosk_b200_destroy(kosk_b200_ctx *ctx);
 
 /* kyber_verifiable_keygen (kosk.hpp:19-20) with the RNG seed made explicit.  Host buffers. */

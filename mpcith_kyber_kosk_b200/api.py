@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libkosk_b200.so")
 
 EXPORTS = [
     "kosk_b200_pk_bytes", "kosk_b200_sk_bytes", "kosk_b200_proof_bytes", "kosk_b200_last_error", "kosk_b200_version",
-    "kosk_b200_create", "kosk_b200_destroy", "kosk_b200_verifiable_keygen", "kosk_b200_kosk_verify",
+    "kosk_b200_create", "kosk_b200_create_ex", "kosk_b200_lanes", "kosk_b200_destroy", "kosk_b200_verifiable_keygen", "kosk_b200_kosk_verify",
     "kosk_b200_prove_batch", "kosk_b200_verify_batch", "kosk_b200_prove_batch_device", "kosk_b200_verify_batch_device",
     "kosk_b200_share_eval", "kosk_b200_sha3_256_rows", "kosk_b200_ntt_rows", "kosk_b200_share_eval_device",
     "kosk_b200_kernel_launches", "kosk_b200_debug_fetch", "kosk_b200_sync",
@@ -43,6 +43,8 @@ def load_library(path=None):
     lib.kosk_b200_last_error.restype = ctypes.c_char_p
     lib.kosk_b200_version.restype = ctypes.c_char_p
     lib.kosk_b200_create.argtypes = [ctypes.POINTER(vp), i32, i32, i32]
+    lib.kosk_b200_create_ex.argtypes = [ctypes.POINTER(vp), i32, i32, i32, i32]
+    lib.kosk_b200_lanes.argtypes = [vp]
     lib.kosk_b200_destroy.argtypes = [vp]
     lib.kosk_b200_destroy.restype = None
     lib.kosk_b200_verifiable_keygen.argtypes = [vp, u8p, u8p, u8p, u8p]
@@ -86,11 +88,11 @@ def _ptr(a):
 class KoskContext:
     """One (device, KYBER_K) instance of the B200 KOSK core."""
 
-    def __init__(self, kyber_k=2, device=0, max_chunk=0):
+    def __init__(self, kyber_k=2, device=0, max_chunk=0, lanes=0):
         self.lib = load_library()
         self.k = kyber_k
         self._h = ctypes.c_void_p()
-        rc = self.lib.kosk_b200_create(ctypes.byref(self._h), kyber_k, device, max_chunk)
+        rc = self.lib.kosk_b200_create_ex(ctypes.byref(self._h), kyber_k, device, max_chunk, lanes)
         if rc != 0:
             raise KoskError(f"kosk_b200_create failed ({rc}): {self.lib.kosk_b200_last_error().decode()}")
         self.pk_bytes, self.sk_bytes, self.proof_bytes = pk_bytes(kyber_k), sk_bytes(kyber_k), proof_bytes(kyber_k)

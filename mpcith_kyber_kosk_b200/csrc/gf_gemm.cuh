@@ -30,8 +30,8 @@ struct GemmArgs {
     int tail;            // 1: also copy A[row][256..406] to C[row][c_off-151 ..] (parties 0..150, ss.cpp:7-11,:77-80)
 };
 
-template <int TM>
-__global__ void __launch_bounds__(256, 2) k_gf_gemm(const GemmArgs g)
+template <int TM, int NREG>
+__global__ void __maxnreg__(NREG) k_gf_gemm(const GemmArgs g)
 {
     constexpr int BM = 16 * TM;
     __shared__ __align__(16) int32_t As[2][GE_BK][BM];
@@ -139,11 +139,11 @@ __global__ void __launch_bounds__(256, 2) k_gf_gemm(const GemmArgs g)
 }
 
 // host-side launcher; returns the number of kernels launched
-template <int TM>
+template <int TM, int NREG = 128>
 static inline int gf_gemm_launch(const GemmArgs &g, int npad, int nbatch, cudaStream_t st)
 {
     dim3 grid(npad / GE_BN, (g.mtotal + 16 * TM - 1) / (16 * TM), nbatch);
-    k_gf_gemm<TM><<<grid, 256, 0, st>>>(g);
+    k_gf_gemm<TM, NREG><<<grid, 256, 0, st>>>(g);
     return 1;
 }
 

@@ -6,6 +6,7 @@
 #include "verify_kernels.cuh"
 #include <cuda_runtime.h>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -46,58 +47,73 @@ static void h_lagrange(std::vector<uint16_t> &out, const std::vector<int> &nodes
 enum { KOSK_PH_KEYGEN = 0, KOSK_PH_EXPAND, KOSK_PH_SHARE1, KOSK_PH_COMMIT, KOSK_PH_FS1, KOSK_PH_EVAL, KOSK_PH_OPEN, KOSK_PH_SHARE2,
        KOSK_PH_VIEW, KOSK_PH_FS2, KOSK_PH_ASSEMBLE, KOSK_PH_VERIFY, KOSK_NPHASE };
 
+// One pipeline lane: a stream plus the per-chunk scratch of one sub-batch.  Independent sub-batches run on
+// different lanes so that latency-bound phases (the sequential Fiat-Shamir sponges), ALU-pipe phases (Keccak) and
+// FMA-pipe phases (share evaluation) of different sub-batches overlap on the SMs, and D2H copies overlap compute.
+struct Lane {
+    cudaStream_t st = nullptr;
+    cudaEvent_t done = nullptr;
+    ProveBufs pb{};
+    u8 *d_seeds = nullptr, *d_pk = nullptr, *d_sk = nullptr, *d_pi = nullptr, *d_ok = nullptr;   // staging of the host-buffer API
+    VerifyBufs vb{};
+    std::vector<cudaEvent_t> ev; int ev_used = 0;
+    std::vector<std::pair<int, int>> ev_phase;     // (phase id, event index of its start); end = next event
+};
+
 struct kosk_b200_ctx {
-    int k = 0, device = 0, chunk = 0;
+    int k = 0, device = 0, chunk = 0, gemm_regs = 128;
     Slots sl; Layout L;
-    cudaStream_t stream = nullptr;         // internal stream of the host-buffer API
     uint64_t launches = 0;
-    int lastB = 0;
     // constant tables
     int16_t *d_St = nullptr;               // [GE_NPAD][YLD] centered share table S (zero padded)
     int16_t *d_R1 = nullptr, *d_R2 = nullptr; // verifier: centered recon tables [256][YLD], [256][VR2LD]
     u16 *d_inv = nullptr;                  // [3329] inverses
     int16_t *d_tab_commit = nullptr, *d_tab_view = nullptr;
-    // per-chunk scratch
-    ProveBufs pb{};
-    u8 *d_seeds = nullptr, *d_pk = nullptr, *d_sk = nullptr, *d_pi = nullptr, *d_ok = nullptr; // staging of the host API
-    VerifyBufs vb{};
-    void *h_pin = nullptr; size_t h_pin_bytes = 0;
+    std::vector<Lane> lanes;
+    cudaEvent_t ev_start = nullptr;
     // optional phase timing with CUDA events on the launching stream (bench.py roofline)
     bool prof = false;
-    std::vector<cudaEvent_t> ev; int ev_used = 0;
-    std::vector<std::pair<int, int>> ev_phase;     // (phase id, event index of its start); end = next event
     double phase_ms[KOSK_NPHASE] = {0}; uint64_t phase_calls[KOSK_NPHASE] = {0};
 };
 
-static void prof_mark(kosk_b200_ctx *c, int phase, cudaStream_t st)
+static void prof_mark(kosk_b200_ctx *c, Lane &ln, int phase)
 {
     if (!c->prof) return;
-    if (c->ev_used >= (int)c->ev.size()) { cudaEvent_t e; cudaEventCreate(&e); c->ev.push_back(e); }
-    cudaEventRecord(c->ev[c->ev_used], st);
-    c->ev_phase.push_back({phase, c->ev_used});
-    c->ev_used++;
+    if (ln.ev_used >= (int)ln.ev.size()) { cudaEvent_t e; cudaEventCreate(&e); ln.ev.push_back(e); }
+    cudaEventRecord(ln.ev[ln.ev_used], ln.st);
+    ln.ev_phase.push_back({phase, ln.ev_used});
+    ln.ev_used++;
 }
 static void prof_collect(kosk_b200_ctx *c)
 {
-    for (size_t i = 0; i + 1 < c->ev_phase.size(); i++) {
-        const int ph = c->ev_phase[i].first;
-        if (ph < 0) continue;
-        float ms = 0; if (cudaEventElapsedTime(&ms, c->ev[c->ev_phase[i].second], c->ev[c->ev_phase[i + 1].second]) == cudaSuccess) { c->phase_ms[ph] += ms; c->phase_calls[ph]++; }
+    for (Lane &ln : c->lanes) {
+        for (size_t i = 0; i + 1 < ln.ev_phase.size(); i++) {
+            const int ph = ln.ev_phase[i].first;
+            if (ph < 0) continue;
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, ln.ev[ln.ev_phase[i].second], ln.ev[ln.ev_phase[i + 1].second]) == cudaSuccess) { c->phase_ms[ph] += ms; c->phase_calls[ph]++; }
+        }
+        ln.ev_phase.clear(); ln.ev_used = 0;
     }
-    c->ev_phase.clear(); c->ev_used = 0;
 }
 
 static void ctx_free(kosk_b200_ctx *c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
-    void *ptrs[] = {c->d_St, c->d_R1, c->d_R2, c->d_inv, c->d_tab_commit, c->d_tab_view, c->pb.Y, c->pb.SH, c->pb.BG, c->pb.TCR, c->pb.VWR,
-                    c->pb.PW, c->pb.AH, c->pb.SHAT, c->pb.I, c->pb.REST, c->d_seeds, c->d_pk, c->d_sk, c->d_pi, c->d_ok};
+    cudaDeviceSynchronize();
+    void *ptrs[] = {c->d_St, c->d_R1, c->d_R2, c->d_inv, c->d_tab_commit, c->d_tab_view};
     for (void *p : ptrs) if (p) cudaFree(p);
-    verify_free(c->vb);
-    if (c->h_pin) cudaFreeHost(c->h_pin);
-    for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
-    if (c->stream) cudaStreamDestroy(c->stream);
+    for (Lane &ln : c->lanes) {
+        void *lp[] = {ln.pb.Y, ln.pb.SH, ln.pb.BG, ln.pb.TCR, ln.pb.VWR, ln.pb.PW, ln.pb.AH, ln.pb.SHAT, ln.pb.I, ln.pb.REST,
+                      ln.d_seeds, ln.d_pk, ln.d_sk, ln.d_pi, ln.d_ok};
+        for (void *p : lp) if (p) cudaFree(p);
+        verify_free(ln.vb);
+        for (cudaEvent_t e : ln.ev) cudaEventDestroy(e);
+        if (ln.done) cudaEventDestroy(ln.done);
+        if (ln.st) cudaStreamDestroy(ln.st);
+    }
+    if (c->ev_start) cudaEventDestroy(c->ev_start);
     delete c;
 }
 
@@ -111,6 +127,12 @@ const char *kosk_b200_version(void) { return "kosk_b200 0.1 (sm_100a)"; }
 
 int kosk_b200_create(kosk_b200_ctx **out, int k, int device, int max_chunk)
 {
+    const char *e = getenv("KOSK_B200_LANES");
+    return kosk_b200_create_ex(out, k, device, max_chunk, e ? atoi(e) : 0);
+}
+
+int kosk_b200_create_ex(kosk_b200_ctx **out, int k, int device, int max_chunk, int nlanes)
+{
     if (!out || k < 2 || k > 4) return fail(KOSK_E_ARG, "kyber_k must be 2, 3 or 4");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(KOSK_E_CUDA, "no CUDA device: the KOSK core has no CPU path");
@@ -118,8 +140,11 @@ int kosk_b200_create(kosk_b200_ctx **out, int k, int device, int max_chunk)
     CU(cudaSetDevice(device));
     kosk_b200_ctx *c = new kosk_b200_ctx;
     c->k = k; c->device = device; c->sl = make_slots(k); c->L = make_layout(k);
-    c->chunk = max_chunk > 0 ? max_chunk : 1024;
+    c->chunk = max_chunk > 0 ? max_chunk : 512;
     if (c->chunk > 16384) c->chunk = 16384;
+    if (nlanes <= 0) nlanes = 2;
+    if (nlanes > 8) nlanes = 8;
+    { const char *e = getenv("KOSK_B200_GEMM_REGS"); if (e) c->gemm_regs = atoi(e) <= 96 ? 96 : 128; }
     const Slots &sl = c->sl; const Layout &L = c->L;
     const size_t B = (size_t)c->chunk;
 #define ALLOC(ptr, bytes) do { if (cudaMalloc((void **)&(ptr), (bytes)) != cudaSuccess) { ctx_free(c); return fail(KOSK_E_NOMEM, "cudaMalloc failed for " #ptr); } } while (0)
@@ -169,17 +194,22 @@ int kosk_b200_create(kosk_b200_ctx **out, int k, int device, int max_chunk)
         ALLOC(c->d_tab_commit, tc.size() * 2); CU(cudaMemcpy(c->d_tab_commit, tc.data(), tc.size() * 2, cudaMemcpyHostToDevice));
         ALLOC(c->d_tab_view, tv.size() * 2); CU(cudaMemcpy(c->d_tab_view, tv.data(), tv.size() * 2, cudaMemcpyHostToDevice));
     }
-    // ---- scratch ----
-    ALLOC(c->pb.Y, B * sl.n2 * YLD * 2);       CU(cudaMemset(c->pb.Y, 0, B * sl.n2 * YLD * 2));
-    ALLOC(c->pb.SH, B * sl.nslot * SLD * 2);   CU(cudaMemset(c->pb.SH, 0, B * sl.nslot * SLD * 2));
-    ALLOC(c->pb.BG, B * NP * 2 * MK * 2);
-    ALLOC(c->pb.TCR, B * TREE_BYTES); ALLOC(c->pb.VWR, B * TREE_BYTES);
-    ALLOC(c->pb.PW, B * (MK + 2 * k) * sl.F * 2);
-    ALLOC(c->pb.AH, B * k * k * 256 * 2); ALLOC(c->pb.SHAT, B * k * 256 * 2);
-    ALLOC(c->pb.I, B * NT * 2); ALLOC(c->pb.REST, B * NR * 2);
-    ALLOC(c->d_seeds, B * 32); ALLOC(c->d_pk, B * L.pk_bytes); ALLOC(c->d_sk, B * L.sk_bytes); ALLOC(c->d_pi, B * L.proof_bytes); ALLOC(c->d_ok, B);
-    if (verify_alloc(c->vb, k, c->chunk) != 0) { ctx_free(c); return fail(KOSK_E_NOMEM, "cudaMalloc failed for verifier scratch"); }
-    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    // ---- per-lane scratch ----
+    c->lanes.resize(nlanes);
+    for (Lane &ln : c->lanes) {
+        ALLOC(ln.pb.Y, B * sl.n2 * YLD * 2);       CU(cudaMemset(ln.pb.Y, 0, B * sl.n2 * YLD * 2));
+        ALLOC(ln.pb.SH, B * sl.nslot * SLD * 2);   CU(cudaMemset(ln.pb.SH, 0, B * sl.nslot * SLD * 2));
+        ALLOC(ln.pb.BG, B * NP * 2 * BGH * 2);
+        ALLOC(ln.pb.TCR, B * TREE_BYTES); ALLOC(ln.pb.VWR, B * TREE_BYTES);
+        ALLOC(ln.pb.PW, B * (MK + 2 * k) * sl.F * 2);
+        ALLOC(ln.pb.AH, B * k * k * 256 * 2); ALLOC(ln.pb.SHAT, B * k * 256 * 2);
+        ALLOC(ln.pb.I, B * NT * 2); ALLOC(ln.pb.REST, B * NR * 2);
+        ALLOC(ln.d_seeds, B * 32); ALLOC(ln.d_pk, B * L.pk_bytes); ALLOC(ln.d_sk, B * L.sk_bytes); ALLOC(ln.d_pi, B * L.proof_bytes); ALLOC(ln.d_ok, B);
+        if (verify_alloc(ln.vb, k, c->chunk) != 0) { ctx_free(c); return fail(KOSK_E_NOMEM, "cudaMalloc failed for verifier scratch"); }
+        CU(cudaStreamCreateWithFlags(&ln.st, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming));
+    }
+    CU(cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming));
     CU(cudaDeviceSynchronize());
     *out = c;
     return KOSK_OK;
@@ -187,70 +217,103 @@ int kosk_b200_create(kosk_b200_ctx **out, int k, int device, int max_chunk)
 
 void kosk_b200_destroy(kosk_b200_ctx *c) { ctx_free(c); }
 uint64_t kosk_b200_kernel_launches(const kosk_b200_ctx *c) { return c ? c->launches : 0; }
-int kosk_b200_sync(kosk_b200_ctx *c) { if (!c) return KOSK_E_ARG; CU(cudaSetDevice(c->device)); CU(cudaStreamSynchronize(c->stream)); return KOSK_OK; }
+int kosk_b200_sync(kosk_b200_ctx *c) { if (!c) return KOSK_E_ARG; CU(cudaSetDevice(c->device)); for (Lane &ln : c->lanes) CU(cudaStreamSynchronize(ln.st)); return KOSK_OK; }
+int kosk_b200_lanes(const kosk_b200_ctx *c) { return c ? (int)c->lanes.size() : 0; }
 
 }  // extern "C"
 
-// ---- launch sequence for one chunk of B proofs; everything stays on `st` ----
+// ---- launch sequence for one chunk of B proofs on one lane ----
 static void launch_share_eval(kosk_b200_ctx *c, const u16 *Y, u16 *SH, int slot_lo, int rows, int y_slots, int sh_slots, int B, cudaStream_t st)
 {
     GemmArgs g{};
     g.A = Y; g.Bt = c->d_St; g.C = SH; g.lda = YLD; g.ldb = YLD; g.ldc = SLD;
     g.mtotal = B * rows; g.ksteps = YLD / GE_BK; g.nvalid = NX; g.c_off = SOFF + NT + 1;
     g.rpp = rows; g.slot_lo = slot_lo; g.a_slots = y_slots; g.c_slots = sh_slots; g.tail = 1;
-    c->launches += gf_gemm_launch<8>(g, GE_NPAD, 1, st);
+    c->launches += (c->gemm_regs <= 96) ? gf_gemm_launch<8, 96>(g, GE_NPAD, 1, st) : gf_gemm_launch<8, 128>(g, GE_NPAD, 1, st);
 }
 
 template <int K>
-static int prove_chunk(kosk_b200_ctx *c, int B, const u8 *d_seeds, u8 *d_pk, u8 *d_sk, u8 *d_pi, cudaStream_t st)
+static int prove_chunk(kosk_b200_ctx *c, Lane &ln, int B, const u8 *d_seeds, u8 *d_pk, u8 *d_sk, u8 *d_pi)
 {
     const Slots &sl = c->sl;
-    ProveBufs pb = c->pb;
+    cudaStream_t st = ln.st;
+    ProveBufs pb = ln.pb;
     pb.seeds = d_seeds; pb.pk = d_pk; pb.sk = d_sk; pb.pi = d_pi; pb.B = B;
     constexpr int NCOMMIT = 2 * (K + MK + 2 * K + 1), ETA = (K == 2) ? 3 : 2;
     constexpr int NVIEW = 16 + NCOMMIT + 4 * K + 8 * ETA * K;
     const int ptiles = (NP + 127) / 128;
-    prof_mark(c, KOSK_PH_KEYGEN, st);
+    prof_mark(c, ln, KOSK_PH_KEYGEN);
     k_keygen<K><<<B, 128, 0, st>>>(pb);
-    prof_mark(c, KOSK_PH_EXPAND, st);
+    prof_mark(c, ln, KOSK_PH_EXPAND);
     k_expand_f<K><<<(B * sl.F + 63) / 64, 64, 0, st>>>(pb);
     k_ntt_f<K><<<dim3(sl.F, B), 128, 0, st>>>(pb);
     k_tails<K><<<(B * (sl.n1 + K) + 63) / 64, 64, 0, st>>>(pb);
-    prof_mark(c, KOSK_PH_SHARE1, st);
+    prof_mark(c, ln, KOSK_PH_SHARE1);
     launch_share_eval(c, pb.Y, pb.SH, 0, sl.n1, sl.n2, sl.nslot, B, st);
-    prof_mark(c, KOSK_PH_COMMIT, st);
+    prof_mark(c, ln, KOSK_PH_COMMIT);
     HashSrc hc{pb.SH, (long long)sl.nslot * SLD, 1, SLD, SOFF, c->d_tab_commit, nullptr, 0};
     k_hash_records<NCOMMIT><<<dim3(ptiles, B), 128, 0, st>>>(hc, pb.TCR, pb.SH, sl.nslot, sl.TC0);
-    prof_mark(c, KOSK_PH_FS1, st);
-    k_fs1<K><<<(B + 31) / 32, 32, 0, st>>>(pb.TCR, pb.PW, B);
-    prof_mark(c, KOSK_PH_EVAL, st);
+    prof_mark(c, ln, KOSK_PH_FS1);
+    k_fs1<K><<<(B + 3) / 4, 128, 0, st>>>(pb.TCR, pb.PW, B);
+    prof_mark(c, ln, KOSK_PH_EVAL);
     k_eval<K><<<dim3(ptiles, B), 256, 0, st>>>(pb);
-    prof_mark(c, KOSK_PH_OPEN, st);
+    prof_mark(c, ln, KOSK_PH_OPEN);
     k_open<K><<<B, 128, 0, st>>>(pb);
-    prof_mark(c, KOSK_PH_SHARE2, st);
+    prof_mark(c, ln, KOSK_PH_SHARE2);
     launch_share_eval(c, pb.Y, pb.SH, sl.n1, 4 * K, sl.n2, sl.nslot, B, st);
-    prof_mark(c, KOSK_PH_VIEW, st);
+    prof_mark(c, ln, KOSK_PH_VIEW);
     k_derive<K><<<dim3(ptiles, B), 128, 0, st>>>(pb);
     HashSrc hv{pb.SH, (long long)sl.nslot * SLD, 1, SLD, SOFF, c->d_tab_view, nullptr, 0};
     k_hash_records<NVIEW><<<dim3(ptiles, B), 128, 0, st>>>(hv, pb.VWR, nullptr, 0, 0);
-    prof_mark(c, KOSK_PH_FS2, st);
-    k_fs2<<<(B + 31) / 32, 32, 0, st>>>(pb.VWR, pb.I, pb.REST, B);
-    prof_mark(c, KOSK_PH_ASSEMBLE, st);
+    prof_mark(c, ln, KOSK_PH_FS2);
+    k_fs2<<<(B + 3) / 4, 128, 0, st>>>(pb.VWR, pb.I, pb.REST, B);
+    prof_mark(c, ln, KOSK_PH_ASSEMBLE);
     k_assemble<K><<<dim3((NT + 31) / 32 + (NR + 31) / 32, B), 128, 0, st>>>(pb);
-    prof_mark(c, -1, st);
+    prof_mark(c, ln, -1);
     c->launches += 12;
-    c->lastB = B;
     CU(cudaGetLastError());
     return KOSK_OK;
 }
 
-static int prove_chunk_k(kosk_b200_ctx *c, int B, const u8 *s, u8 *pk, u8 *sk, u8 *pi, cudaStream_t st)
+static int prove_chunk_k(kosk_b200_ctx *c, Lane &ln, int B, const u8 *s, u8 *pk, u8 *sk, u8 *pi)
 {
     switch (c->k) {
-    case 2: return prove_chunk<2>(c, B, s, pk, sk, pi, st);
-    case 3: return prove_chunk<3>(c, B, s, pk, sk, pi, st);
-    default: return prove_chunk<4>(c, B, s, pk, sk, pi, st);
+    case 2: return prove_chunk<2>(c, ln, B, s, pk, sk, pi);
+    case 3: return prove_chunk<3>(c, ln, B, s, pk, sk, pi);
+    default: return prove_chunk<4>(c, ln, B, s, pk, sk, pi);
     }
+}
+
+static int verify_chunk_lane(kosk_b200_ctx *c, Lane &ln, int B, const u8 *d_pi, const u8 *d_pk, u8 *d_ok)
+{
+    VerifyTables vt{c->d_St, c->d_R1, c->d_R2, c->d_inv};
+    prof_mark(c, ln, KOSK_PH_VERIFY);
+    int nl = verify_chunk(c->k, ln.vb, vt, B, d_pi, d_pk, d_ok, ln.st);
+    prof_mark(c, ln, -1);
+    if (nl < 0) return fail(KOSK_E_CUDA, "verify launch failed");
+    c->launches += nl;
+    CU(cudaGetLastError());
+    return KOSK_OK;
+}
+
+// sub-batch size: spread n proofs over the lanes, at most `chunk` per wave
+static size_t sub_batch(const kosk_b200_ctx *c, size_t n)
+{
+    const size_t L = c->lanes.size();
+    return std::max<size_t>(1, std::min<size_t>((size_t)c->chunk, (n + L - 1) / L));
+}
+// lanes start after everything already enqueued on the caller's stream ...
+static int lanes_fork(kosk_b200_ctx *c, cudaStream_t caller)
+{
+    CU(cudaEventRecord(c->ev_start, caller));
+    for (Lane &ln : c->lanes) CU(cudaStreamWaitEvent(ln.st, c->ev_start, 0));
+    return KOSK_OK;
+}
+// ... and the caller's stream continues after all lanes are done
+static int lanes_join(kosk_b200_ctx *c, cudaStream_t caller)
+{
+    for (Lane &ln : c->lanes) { CU(cudaEventRecord(ln.done, ln.st)); CU(cudaStreamWaitEvent(caller, ln.done, 0)); }
+    return KOSK_OK;
 }
 
 // ---- generic component kernels ----
@@ -297,14 +360,17 @@ int kosk_b200_prove_batch_device(kosk_b200_ctx *c, size_t n, const uint8_t *d_se
 {
     if (!c || !d_seeds || !d_pk || !d_sk || !d_pi) return fail(KOSK_E_ARG, "null argument");
     CU(cudaSetDevice(c->device));
-    cudaStream_t st = (cudaStream_t)stream;
+    if (n == 0) return KOSK_OK;
     const Layout &L = c->L;
-    for (size_t o = 0; o < n; o += c->chunk) {
-        const int B = (int)std::min<size_t>(c->chunk, n - o);
-        int rc = prove_chunk_k(c, B, d_seeds + 32 * o, d_pk + L.pk_bytes * o, d_sk + L.sk_bytes * o, d_pi + L.proof_bytes * o, st);
+    int rc = lanes_fork(c, (cudaStream_t)stream); if (rc) return rc;
+    const size_t sub = sub_batch(c, n);
+    size_t i = 0;
+    for (size_t o = 0; o < n; o += sub, i++) {
+        const int B = (int)std::min<size_t>(sub, n - o);
+        rc = prove_chunk_k(c, c->lanes[i % c->lanes.size()], B, d_seeds + 32 * o, d_pk + L.pk_bytes * o, d_sk + L.sk_bytes * o, d_pi + L.proof_bytes * o);
         if (rc) return rc;
     }
-    return KOSK_OK;
+    return lanes_join(c, (cudaStream_t)stream);
 }
 
 int kosk_b200_prove_batch(kosk_b200_ctx *c, size_t n, const uint8_t *seeds, uint8_t *pk, uint8_t *sk, uint8_t *pi)
@@ -312,17 +378,19 @@ int kosk_b200_prove_batch(kosk_b200_ctx *c, size_t n, const uint8_t *seeds, uint
     if (!c || !seeds || !pk || !sk || !pi) return fail(KOSK_E_ARG, "null argument");
     CU(cudaSetDevice(c->device));
     const Layout &L = c->L;
-    cudaStream_t st = c->stream;
-    for (size_t o = 0; o < n; o += c->chunk) {
-        const int B = (int)std::min<size_t>(c->chunk, n - o);
-        CU(cudaMemcpyAsync(c->d_seeds, seeds + 32 * o, 32 * (size_t)B, cudaMemcpyHostToDevice, st));
-        int rc = prove_chunk_k(c, B, c->d_seeds, c->d_pk, c->d_sk, c->d_pi, st);
+    const size_t sub = sub_batch(c, n);
+    size_t i = 0;
+    for (size_t o = 0; o < n; o += sub, i++) {
+        const int B = (int)std::min<size_t>(sub, n - o);
+        Lane &ln = c->lanes[i % c->lanes.size()];
+        CU(cudaMemcpyAsync(ln.d_seeds, seeds + 32 * o, 32 * (size_t)B, cudaMemcpyHostToDevice, ln.st));
+        int rc = prove_chunk_k(c, ln, B, ln.d_seeds, ln.d_pk, ln.d_sk, ln.d_pi);
         if (rc) return rc;
-        CU(cudaMemcpyAsync(pk + L.pk_bytes * o, c->d_pk, L.pk_bytes * (size_t)B, cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(sk + L.sk_bytes * o, c->d_sk, L.sk_bytes * (size_t)B, cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(pi + L.proof_bytes * o, c->d_pi, L.proof_bytes * (size_t)B, cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
+        CU(cudaMemcpyAsync(pk + L.pk_bytes * o, ln.d_pk, L.pk_bytes * (size_t)B, cudaMemcpyDeviceToHost, ln.st));
+        CU(cudaMemcpyAsync(sk + L.sk_bytes * o, ln.d_sk, L.sk_bytes * (size_t)B, cudaMemcpyDeviceToHost, ln.st));
+        CU(cudaMemcpyAsync(pi + L.proof_bytes * o, ln.d_pi, L.proof_bytes * (size_t)B, cudaMemcpyDeviceToHost, ln.st));
     }
+    for (Lane &ln : c->lanes) CU(cudaStreamSynchronize(ln.st));
     return KOSK_OK;
 }
 
@@ -335,18 +403,17 @@ int kosk_b200_verify_batch_device(kosk_b200_ctx *c, size_t n, const uint8_t *d_p
 {
     if (!c || !d_pi || !d_pk || !d_ok) return fail(KOSK_E_ARG, "null argument");
     CU(cudaSetDevice(c->device));
+    if (n == 0) return KOSK_OK;
     const Layout &L = c->L;
-    for (size_t o = 0; o < n; o += c->chunk) {
-        const int B = (int)std::min<size_t>(c->chunk, n - o);
-        VerifyTables vt{c->d_St, c->d_R1, c->d_R2, c->d_inv};
-        prof_mark(c, KOSK_PH_VERIFY, (cudaStream_t)stream);
-        int nl = verify_chunk(c->k, c->vb, vt, B, d_pi + L.proof_bytes * o, d_pk + L.pk_bytes * o, d_ok + o, (cudaStream_t)stream);
-        prof_mark(c, -1, (cudaStream_t)stream);
-        if (nl < 0) return fail(KOSK_E_CUDA, "verify launch failed");
-        c->launches += nl;
-        CU(cudaGetLastError());
+    int rc = lanes_fork(c, (cudaStream_t)stream); if (rc) return rc;
+    const size_t sub = sub_batch(c, n);
+    size_t i = 0;
+    for (size_t o = 0; o < n; o += sub, i++) {
+        const int B = (int)std::min<size_t>(sub, n - o);
+        rc = verify_chunk_lane(c, c->lanes[i % c->lanes.size()], B, d_pi + L.proof_bytes * o, d_pk + L.pk_bytes * o, d_ok + o);
+        if (rc) return rc;
     }
-    return KOSK_OK;
+    return lanes_join(c, (cudaStream_t)stream);
 }
 
 int kosk_b200_verify_batch(kosk_b200_ctx *c, size_t n, const uint8_t *pi, const uint8_t *pk, uint8_t *ok)
@@ -354,16 +421,18 @@ int kosk_b200_verify_batch(kosk_b200_ctx *c, size_t n, const uint8_t *pi, const 
     if (!c || !pi || !pk || !ok) return fail(KOSK_E_ARG, "null argument");
     CU(cudaSetDevice(c->device));
     const Layout &L = c->L;
-    cudaStream_t st = c->stream;
-    for (size_t o = 0; o < n; o += c->chunk) {
-        const int B = (int)std::min<size_t>(c->chunk, n - o);
-        CU(cudaMemcpyAsync(c->d_pi, pi + L.proof_bytes * o, L.proof_bytes * (size_t)B, cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(c->d_pk, pk + L.pk_bytes * o, L.pk_bytes * (size_t)B, cudaMemcpyHostToDevice, st));
-        int rc = kosk_b200_verify_batch_device(c, (size_t)B, c->d_pi, c->d_pk, c->d_ok, st);
+    const size_t sub = sub_batch(c, n);
+    size_t i = 0;
+    for (size_t o = 0; o < n; o += sub, i++) {
+        const int B = (int)std::min<size_t>(sub, n - o);
+        Lane &ln = c->lanes[i % c->lanes.size()];
+        CU(cudaMemcpyAsync(ln.d_pi, pi + L.proof_bytes * o, L.proof_bytes * (size_t)B, cudaMemcpyHostToDevice, ln.st));
+        CU(cudaMemcpyAsync(ln.d_pk, pk + L.pk_bytes * o, L.pk_bytes * (size_t)B, cudaMemcpyHostToDevice, ln.st));
+        int rc = verify_chunk_lane(c, ln, B, ln.d_pi, ln.d_pk, ln.d_ok);
         if (rc) return rc;
-        CU(cudaMemcpyAsync(ok + o, c->d_ok, (size_t)B, cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
+        CU(cudaMemcpyAsync(ok + o, ln.d_ok, (size_t)B, cudaMemcpyDeviceToHost, ln.st));
     }
+    for (Lane &ln : c->lanes) CU(cudaStreamSynchronize(ln.st));
     return KOSK_OK;
 }
 
@@ -395,8 +464,8 @@ int kosk_b200_share_eval(kosk_b200_ctx *c, size_t n, const uint16_t *y, uint16_t
     for (size_t r = 0; r < n; r++) memcpy(&hy[r * YLD], y + r * D1, D1 * 2);
     CU(cudaMalloc(&dy, hy.size() * 2 + 16)); CU(cudaMalloc(&dp, hp.size() * 2 + 16));
     CU(cudaMemcpy(dy, hy.data(), hy.size() * 2, cudaMemcpyHostToDevice));
-    int rc = kosk_b200_share_eval_device(c, n, dy, dp, c->stream);
-    if (!rc) { cudaError_t e = cudaStreamSynchronize(c->stream); if (e != cudaSuccess) rc = fail(KOSK_E_CUDA, cudaGetErrorString(e)); }
+    int rc = kosk_b200_share_eval_device(c, n, dy, dp, c->lanes[0].st);
+    if (!rc) { cudaError_t e = cudaStreamSynchronize(c->lanes[0].st); if (e != cudaSuccess) rc = fail(KOSK_E_CUDA, cudaGetErrorString(e)); }
     if (!rc) { cudaError_t e = cudaMemcpy(hp.data(), dp, hp.size() * 2, cudaMemcpyDeviceToHost); if (e != cudaSuccess) rc = fail(KOSK_E_CUDA, cudaGetErrorString(e)); }
     cudaFree(dy); cudaFree(dp);
     if (rc) return rc;
@@ -411,8 +480,8 @@ int kosk_b200_sha3_256_rows(kosk_b200_ctx *c, size_t n, size_t len, const uint8_
     u8 *di = nullptr, *dout = nullptr;
     CU(cudaMalloc(&di, n * len + 16)); CU(cudaMalloc(&dout, n * 32));
     CU(cudaMemcpy(di, in, n * len, cudaMemcpyHostToDevice));
-    k_sha3_rows<<<(unsigned)((n + 63) / 64), 64, 0, c->stream>>>(di, dout, n, len); c->launches++;
-    cudaError_t e = cudaStreamSynchronize(c->stream);
+    k_sha3_rows<<<(unsigned)((n + 63) / 64), 64, 0, c->lanes[0].st>>>(di, dout, n, len); c->launches++;
+    cudaError_t e = cudaStreamSynchronize(c->lanes[0].st);
     if (e == cudaSuccess) e = cudaMemcpy(out, dout, n * 32, cudaMemcpyDeviceToHost);
     cudaFree(di); cudaFree(dout);
     if (e != cudaSuccess) return fail(KOSK_E_CUDA, cudaGetErrorString(e));
@@ -426,8 +495,8 @@ int kosk_b200_ntt_rows(kosk_b200_ctx *c, size_t n, uint16_t *a)
     u16 *d = nullptr;
     CU(cudaMalloc(&d, n * 512));
     CU(cudaMemcpy(d, a, n * 512, cudaMemcpyHostToDevice));
-    k_ntt_rows<<<(unsigned)n, 128, 0, c->stream>>>(d); c->launches++;
-    cudaError_t e = cudaStreamSynchronize(c->stream);
+    k_ntt_rows<<<(unsigned)n, 128, 0, c->lanes[0].st>>>(d); c->launches++;
+    cudaError_t e = cudaStreamSynchronize(c->lanes[0].st);
     if (e == cudaSuccess) e = cudaMemcpy(a, d, n * 512, cudaMemcpyDeviceToHost);
     cudaFree(d);
     if (e != cudaSuccess) return fail(KOSK_E_CUDA, cudaGetErrorString(e));
@@ -443,15 +512,15 @@ int kosk_b200_debug_fetch(kosk_b200_ctx *c, const char *what, void *out, size_t 
     const size_t B = (size_t)c->chunk;
     const void *src = nullptr; size_t avail = 0;
     std::string w(what);
-    if (w == "alpha_pow") { src = c->pb.PW; avail = B * (MK + 2 * c->k) * sl.F * 2; }
-    else if (w == "I") { src = c->pb.I; avail = B * NT * 2; }
-    else if (w == "rest") { src = c->pb.REST; avail = B * NR * 2; }
-    else if (w == "tcomm") { src = c->pb.TCR; avail = B * TREE_BYTES; }
-    else if (w == "views") { src = c->pb.VWR; avail = B * TREE_BYTES; }
-    else if (w == "Y") { src = c->pb.Y; avail = B * sl.n2 * YLD * 2; }
-    else if (w == "planes") { src = c->pb.SH; avail = B * sl.nslot * SLD * 2; }
-    else if (w == "bg") { src = c->pb.BG; avail = B * NP * 2 * MK * 2; }
-    else if (w == "vflags") { src = c->vb.flags; avail = B * 4; }
+    if (w == "alpha_pow") { src = c->lanes[0].pb.PW; avail = B * (MK + 2 * c->k) * sl.F * 2; }
+    else if (w == "I") { src = c->lanes[0].pb.I; avail = B * NT * 2; }
+    else if (w == "rest") { src = c->lanes[0].pb.REST; avail = B * NR * 2; }
+    else if (w == "tcomm") { src = c->lanes[0].pb.TCR; avail = B * TREE_BYTES; }
+    else if (w == "views") { src = c->lanes[0].pb.VWR; avail = B * TREE_BYTES; }
+    else if (w == "Y") { src = c->lanes[0].pb.Y; avail = B * sl.n2 * YLD * 2; }
+    else if (w == "planes") { src = c->lanes[0].pb.SH; avail = B * sl.nslot * SLD * 2; }
+    else if (w == "bg") { src = c->lanes[0].pb.BG; avail = B * NP * 2 * BGH * 2; }
+    else if (w == "vflags") { src = c->lanes[0].vb.flags; avail = B * 4; }
     else return fail(KOSK_E_ARG, "unknown buffer name");
     CU(cudaMemcpy(out, src, std::min(bytes, avail), cudaMemcpyDeviceToHost));
     return KOSK_OK;
@@ -492,7 +561,7 @@ __global__ void __launch_bounds__(256) k_int_peak(uint32_t *out, int iters, uint
 #pragma unroll
             for (int i = 0; i < 16; i++) {
                 if (MODE == 0) r[i] = r[i] * m + x;                                   // IMAD (fma pipe)
-                else if (MODE == 1) r[i] = (r[i] & m) ^ (r[(i + 1) & 15] | x);          // LOP3 (alu pipe)
+                else if (MODE == 1) r[i] = r[i] ^ (~r[(i + 1) & 15] & m);                  // LOP3 (alu pipe)
                 else r[i] = __funnelshift_l(r[i], r[(i + 5) & 15], 7);                 // SHF (alu pipe)
             }
     }
@@ -513,11 +582,11 @@ extern "C" int kosk_b200_int_peak(kosk_b200_ctx *c, double *ops_per_s /* [3]: IM
     for (int mode = 0; mode < 3; mode++) {
         float best = 1e30f;
         for (int rep = 0; rep < 4; rep++) {
-            CU(cudaEventRecord(e0, c->stream));
-            if (mode == 0) k_int_peak<0><<<blocks, 256, 0, c->stream>>>(d, iters, 12345u + rep);
-            else if (mode == 1) k_int_peak<1><<<blocks, 256, 0, c->stream>>>(d, iters, 12345u + rep);
-            else k_int_peak<2><<<blocks, 256, 0, c->stream>>>(d, iters, 12345u + rep);
-            CU(cudaEventRecord(e1, c->stream));
+            CU(cudaEventRecord(e0, c->lanes[0].st));
+            if (mode == 0) k_int_peak<0><<<blocks, 256, 0, c->lanes[0].st>>>(d, iters, 12345u + rep);
+            else if (mode == 1) k_int_peak<1><<<blocks, 256, 0, c->lanes[0].st>>>(d, iters, 12345u + rep);
+            else k_int_peak<2><<<blocks, 256, 0, c->lanes[0].st>>>(d, iters, 12345u + rep);
+            CU(cudaEventRecord(e1, c->lanes[0].st));
             CU(cudaEventSynchronize(e1));
             float ms = 0; CU(cudaEventElapsedTime(&ms, e0, e1));
             if (rep > 0 && ms < best) best = ms;

@@ -2,7 +2,7 @@
 // One launch processes a whole chunk of B independent proofs; per-proof state lives in HBM as
 //   Y   [B][n2][YLD]      u16  sharing inputs: 256 packed secrets | 151 tail randoms   (ss.cpp:13-20)
 //   SH  [B][nslot][SLD]   u16  planes: one row of 1454 party shares per slot           (share_vec.share_y)
-//   BG  [B][NP][140]      u16  beta[70] | gamma[70] per party                          (mpcith_vp_state)
+//   BG  [B][NP][2*BGH]    u16  beta[70]+pad | gamma[70]+pad per party                          (mpcith_vp_state)
 //   TCR [B][NP][32]       u8   party commitments, VWR the same for view hashes
 // Parties are the contiguous (coalesced) axis of every per-party kernel.
 #pragma once
@@ -10,6 +10,8 @@
 #include "gf_gemm.cuh"
 
 namespace kosk {
+
+constexpr int BGH = 144;        // u16 per party of one beta (or gamma) row in BG: 70 values + padding, 16B-aligned
 
 __constant__ u16 c_zeta[128];   // 17^brv7(i) mod q: plain-residue form of kyber/ntt.c:39-56
 
@@ -312,84 +314,145 @@ k_hash_records(const HashSrc hs, u8 *__restrict__ out_rows, u16 *__restrict__ ou
     }
 }
 
-// SHA3-256 over the 1454 x 32-byte digests of one proof (FS tree hash): 342 full rate blocks + 16 bytes.
-// Strictly sequential sponge: one thread per proof (mlwe_prover.cpp:131-135, :445-449).
-__device__ __forceinline__ void tree_hash(uint64_t (&a)[25], const u8 *rows)
-{
-    const uint64_t *src = reinterpret_cast<const uint64_t *>(rows);
-    keccak_zero(a);
-    constexpr int NFULL = TREE_BYTES / 136;            // 342
-#pragma unroll 1
-    for (int blk = 0; blk < NFULL; blk++) {
+// ---------------------------------------------------------------------------------------------
+// Warp-cooperative Keccak-f[1600]: lane t < 25 of a warp holds state word A[x][y], t = x + 5y; theta / pi / chi
+// exchange words with warp shuffles.  Used for the two strictly sequential Fiat-Shamir sponges (343 permutations
+// each, mlwe_prover.cpp:131-135, :445-449), where one proof per warp cuts the latency ~5x against one per thread.
+struct WarpKeccak {
+    int t, x, y, rho, src_pi, l5, l10, l15, l20, lm1, lp1, c1, c2;
+    __device__ __forceinline__ void init()
+    {
+        const int rho_tab[25] = {0, 1, 62, 28, 27, 36, 44, 6, 55, 20, 3, 10, 43, 25, 39, 41, 45, 15, 21, 8, 18, 2, 61, 56, 14};
+        const int lane = threadIdx.x & 31;
+        t = lane < 25 ? lane : 0; x = t % 5; y = t / 5;
+        int r = 0;
 #pragma unroll
-        for (int l = 0; l < 17; l++) a[l] ^= src[blk * 17 + l];
-        keccak_f1600(a);
+        for (int i = 0; i < 25; i++) if (i == t) r = rho_tab[i];
+        rho = r;
+        src_pi = lane < 25 ? ((3 * y + x) % 5) + 5 * x : lane;      // B[x][y] = rol(A[(x+3y)%5][x], ..)
+        l5 = lane < 25 ? (t + 5) % 25 : lane; l10 = lane < 25 ? (t + 10) % 25 : lane;
+        l15 = lane < 25 ? (t + 15) % 25 : lane; l20 = lane < 25 ? (t + 20) % 25 : lane;
+        lm1 = lane < 25 ? (x + 4) % 5 + 5 * y : lane; lp1 = lane < 25 ? (x + 1) % 5 + 5 * y : lane;
+        c1 = lp1; c2 = lane < 25 ? (x + 2) % 5 + 5 * y : lane;
     }
-    a[0] ^= src[NFULL * 17]; a[1] ^= src[NFULL * 17 + 1];   // 46528 - 342*136 = 16 bytes
-    a[2] ^= 0x06ULL; a[16] ^= 0x8000000000000000ULL;
-    keccak_f1600(a);
-}
+    static __device__ __forceinline__ uint64_t shfl(uint64_t v, int src)
+    {
+        const uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)v, src), hi = __shfl_sync(0xffffffffu, (uint32_t)(v >> 32), src);
+        return ((uint64_t)hi << 32) | lo;
+    }
+    __device__ __forceinline__ uint64_t permute(uint64_t a) const
+    {
+        const bool lane0 = (threadIdx.x & 31) == 0;
+#pragma unroll 1
+        for (int r = 0; r < 24; r++) {
+            const uint64_t c = a ^ shfl(a, l5) ^ shfl(a, l10) ^ shfl(a, l15) ^ shfl(a, l20);
+            a ^= shfl(c, lm1) ^ rol64(shfl(c, lp1), 1);
+            uint32_t lo = (uint32_t)a, hi = (uint32_t)(a >> 32);           // rho: rotate left by a per-lane amount
+            if (rho & 32) { const uint32_t tmp = lo; lo = hi; hi = tmp; }
+            const uint32_t nh = __funnelshift_l(lo, hi, rho), nl = __funnelshift_l(hi, lo, rho);
+            const uint64_t b = shfl(((uint64_t)nh << 32) | nl, src_pi);  // pi
+            a = b ^ (~shfl(b, c1) & shfl(b, c2));                          // chi
+            if (lane0) a ^= c_keccak_rc[r];                                // iota
+        }
+        return a;
+    }
+    // SHA3-256 of the 1454 x 32-byte digest rows of one proof; result: lanes 0..3 hold the digest words
+    __device__ __forceinline__ uint64_t tree_hash(const u8 *rows) const
+    {
+        const uint64_t *src = reinterpret_cast<const uint64_t *>(rows);
+        const int lane = threadIdx.x & 31;
+        constexpr int NFULL = TREE_BYTES / 136;        // 342 full rate blocks + 16 bytes
+        uint64_t a = 0, nxt = lane < 17 ? src[lane] : 0;
+#pragma unroll 1
+        for (int blk = 0; blk < NFULL; blk++) {
+            a ^= nxt;
+            nxt = 0;
+            if (blk + 1 < NFULL) { if (lane < 17) nxt = src[(blk + 1) * 17 + lane]; }
+            else if (lane < 2) nxt = src[NFULL * 17 + lane];
+            a = permute(a);
+        }
+        a ^= nxt;
+        if (lane == 2) a ^= 0x06ULL;
+        if (lane == 16) a ^= 0x8000000000000000ULL;
+        return permute(a);
+    }
+    // SHAKE256(digest || 0x01) (kyber_shake256_prf with nonce 1): state after the first permutation
+    __device__ __forceinline__ uint64_t prf1(uint64_t digest_state) const
+    {
+        const int lane = threadIdx.x & 31;
+        uint64_t a = lane < 4 ? digest_state : 0;
+        if (lane == 4) a = 1ULL | (0x1FULL << 8);
+        if (lane == 16) a = 0x8000000000000000ULL;
+        return permute(a);
+    }
+};
 
-// FS-1: alpha = BE16(SHAKE256(SHA3-256(Tcomm_0 || ... ) || 0x01)) mod q and the power table (mlwe_prover.cpp:130-153)
+// FS-1: alpha = BE16(SHAKE256(SHA3-256(Tcomm_0 || ... ) || 0x01)) mod q and the power table (mlwe_prover.cpp:130-153).
+// One warp per proof.
 template <int K>
-__global__ void __launch_bounds__(32) k_fs1(const u8 *__restrict__ TCR, u16 *__restrict__ PW, int B)
+__global__ void __launch_bounds__(128) k_fs1(const u8 *__restrict__ TCR, u16 *__restrict__ PW, int B)
 {
     constexpr int F = MK + 2 * K + 1, NA = MK + 2 * K;
-    const int b = blockIdx.x * 32 + threadIdx.x;
+    __shared__ u16 salpha[4][80];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, b = blockIdx.x * 4 + w;
     if (b >= B) return;
-    uint64_t a[25];
-    tree_hash(a, TCR + (size_t)b * TREE_BYTES);
-    uint64_t dg[4] = {a[0], a[1], a[2], a[3]};
-    prf_begin(a, dg, 1);
-    u16 *pw = PW + (size_t)b * NA * F;
+    WarpKeccak wk; wk.init();
+    uint64_t a = wk.tree_hash(TCR + (size_t)b * TREE_BYTES);
+    a = wk.prf1(a);
 #pragma unroll 1
-    for (int blk = 0; blk < 2; blk++) {
+    for (int blk = 0; blk < 2; blk++) {                 // 2*NA <= 156 bytes = 136 + 20
+        if (lane < 17)
 #pragma unroll
-        for (int v = 0; v < 68; v++) {
-            const int j = blk * 68 + v;
-            if (j < NA) {
-                uint32_t al = lane_be16(a[v >> 2], v & 3) % (uint32_t)Q, x = 1;
-                for (int kk = 0; kk < F; kk++) { pw[j * F + kk] = (u16)x; x = gf_mul(x, al); }
-            }
-        }
-        if (blk == 0) keccak_f1600(a);
+            for (int i = 0; i < 4; i++) { const int j = blk * 68 + 4 * lane + i; if (j < NA) salpha[w][j] = (u16)(lane_be16(a, i) % (uint32_t)Q); }
+        if (blk == 0) a = wk.permute(a);
+    }
+    __syncwarp();
+    u16 *pw = PW + (size_t)b * NA * F;
+    for (int j = lane; j < NA; j += 32) {
+        const uint32_t al = salpha[w][j]; uint32_t xx = 1;
+        for (int kk = 0; kk < F; kk++) { pw[j * F + kk] = (u16)xx; xx = gf_mul(xx, al); }
     }
 }
 
 // FS-2: opened set I from the view hashes, with the reference's linear-probe de-duplication
-// (mlwe_prover.cpp:445-474) and the ascending rest list (:480-490).
-__global__ void __launch_bounds__(32) k_fs2(const u8 *__restrict__ VWR, u16 *__restrict__ Iout, u16 *__restrict__ REST, int B)
+// (mlwe_prover.cpp:445-474: the first free index at or after the drawn one, in draw order) and the ascending
+// rest list (:480-490).  One warp per proof.
+__global__ void __launch_bounds__(128) k_fs2(const u8 *__restrict__ VWR, u16 *__restrict__ Iout, u16 *__restrict__ REST, int B)
 {
-    const int b = blockIdx.x * 32 + threadIdx.x;
+    __shared__ u16 sraw[4][NT + 2];
+    __shared__ uint32_t sused[4][(NP + 31) / 32];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, b = blockIdx.x * 4 + w;
     if (b >= B) return;
-    uint64_t a[25];
-    tree_hash(a, VWR + (size_t)b * TREE_BYTES);
-    uint64_t dg[4] = {a[0], a[1], a[2], a[3]};
-    prf_begin(a, dg, 1);
-    u16 *I = Iout + (size_t)b * NT;
+    WarpKeccak wk; wk.init();
+    uint64_t a = wk.tree_hash(VWR + (size_t)b * TREE_BYTES);
+    a = wk.prf1(a);
 #pragma unroll 1
-    for (int blk = 0; blk < 3; blk++) {               // 300 bytes = 136 + 136 + 28
+    for (int blk = 0; blk < 3; blk++) {                 // 300 bytes = 136 + 136 + 28
+        if (lane < 17)
 #pragma unroll
-        for (int v = 0; v < 68; v++)
-            if (blk * 68 + v < NT) I[blk * 68 + v] = (u16)(lane_be16(a[v >> 2], v & 3) % (uint32_t)NP);
-        if (blk < 2) keccak_f1600(a);
+            for (int i = 0; i < 4; i++) { const int j = blk * 68 + 4 * lane + i; if (j < NT) sraw[w][j] = (u16)(lane_be16(a, i) % (uint32_t)NP); }
+        if (blk < 2) a = wk.permute(a);
     }
-    for (int i = 1; i < NT; i++) {
-        uint32_t cur = I[i]; uint32_t inc = 0; bool dup;
-        do {
-            dup = false;
-            for (int j = 0; j < i; j++)
-                if ((cur + inc) % NP == I[j]) { dup = true; inc = (inc + 1) & 0xFFFF; break; }
-        } while (dup);
-        I[i] = (u16)((cur + inc) % NP);
+    for (int i = lane; i < (NP + 31) / 32; i += 32) sused[w][i] = 0;
+    __syncwarp();
+    u16 *I = Iout + (size_t)b * NT;
+    if (lane == 0) {
+        for (int i = 0; i < NT; i++) {
+            uint32_t c = sraw[w][i];
+            while (sused[w][c >> 5] & (1u << (c & 31))) c = (c + 1 == NP) ? 0 : c + 1;
+            sused[w][c >> 5] |= 1u << (c & 31);
+            I[i] = (u16)c;
+        }
     }
-    // rest list: parties not in I, ascending.  O(N*T) scan is negligible next to the tree hash.
+    __syncwarp();
     u16 *rest = REST + (size_t)b * NR;
     int n = 0;
-    for (int p = 0; p < NP; p++) {
-        bool in = false;
-        for (int j = 0; j < NT; j++) in |= (I[j] == p);
-        if (!in && n < NR) rest[n++] = (u16)p;
+    for (int p0 = 0; p0 < NP; p0 += 32) {
+        const int p = p0 + lane;
+        const bool free_ = p < NP && !(sused[w][p >> 5] & (1u << (p & 31)));
+        const uint32_t m = __ballot_sync(0xffffffffu, free_);
+        if (free_) { const int pos = n + __popc(m & ((1u << lane) - 1)); if (pos < NR) rest[pos] = (u16)p; }
+        n += __popc(m);
     }
 }
 
@@ -399,9 +462,9 @@ __global__ void __launch_bounds__(32) k_fs2(const u8 *__restrict__ VWR, u16 *__r
 //   r[p][j']    = f[p][71] + sum_{k>=1} alpha_{70+j'}^k f[p][k]  j' < 2K      (c0 index quirk)
 // and the same over NTT_f.  CTA = 128 parties x {f, NTT_f}; the power table sits in shared memory.
 template <int K>
-__global__ void __launch_bounds__(256) k_eval(ProveBufs pb)
+__global__ void __launch_bounds__(256, 2) k_eval(ProveBufs pb)
 {
-    constexpr int F = MK + 2 * K + 1, NA = MK + 2 * K, NAP = 80;
+    constexpr int F = MK + 2 * K + 1, NA = MK + 2 * K, NAP = (NA + 3) & ~3;
     const Slots sl = make_slots(K);
     __shared__ __align__(16) int32_t spw[F][NAP];
     const int b = blockIdx.y, tid = threadIdx.x;
@@ -419,20 +482,41 @@ __global__ void __launch_bounds__(256) k_eval(ProveBufs pb)
     int32_t acc[NAP];
 #pragma unroll
     for (int j = 0; j < NAP; j++) acc[j] = 0;
-    int32_t c71 = 0;
-#pragma unroll 1
-    for (int kk = 0; kk < F; kk++) {
-        const int32_t v = gf_center(src[(size_t)kk * SLD]);
-        if (kk == MK + 1) c71 = v;
+    constexpr int U = 5;                     // F = 75/77/79: software-pipelined loads, U shares in flight
+    int32_t v[U];
 #pragma unroll
-        for (int j4 = 0; j4 < NAP / 4; j4++) {
-            const int4 w = *reinterpret_cast<const int4 *>(&spw[kk][4 * j4]);
-            acc[4 * j4] += v * w.x; acc[4 * j4 + 1] += v * w.y; acc[4 * j4 + 2] += v * w.z; acc[4 * j4 + 3] += v * w.w;
+    for (int u = 0; u < U; u++) v[u] = src[(size_t)u * SLD];
+#pragma unroll 1
+    for (int k0 = 0; k0 < F; k0 += U) {
+        int32_t cur[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) { cur[u] = v[u]; if (k0 + U + u < F) v[u] = src[(size_t)(k0 + U + u) * SLD]; }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (k0 + u < F) {
+                const int32_t c = gf_center(cur[u]);
+#pragma unroll
+                for (int j4 = 0; j4 < NAP / 4; j4++) {
+                    const int4 w = *reinterpret_cast<const int4 *>(&spw[k0 + u][4 * j4]);
+                    acc[4 * j4] += c * w.x; acc[4 * j4 + 1] += c * w.y; acc[4 * j4 + 2] += c * w.z; acc[4 * j4 + 3] += c * w.w;
+                }
+            }
         }
     }
-    u16 *bg = pb.BG + ((size_t)b * NP + p) * (2 * MK) + half * MK;
+    const int32_t c71 = gf_center(src[(size_t)(MK + 1) * SLD]);
+    // beta | gamma rows of this party: 9 x 16-byte stores per half (BGH = 144 u16 per half, 16B-aligned)
+    uint4 *bg = reinterpret_cast<uint4 *>(pb.BG + ((size_t)b * NP + p) * (2 * BGH) + half * BGH);
 #pragma unroll
-    for (int j = 0; j < MK; j++) bg[j] = (u16)gf_canon(acc[j]);
+    for (int q = 0; q < BGH / 8; q++) {
+        uint32_t wv[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int j0 = 8 * q + 2 * i, j1 = j0 + 1;
+            const uint32_t lo = j0 < MK ? gf_canon(acc[j0 < NAP ? j0 : 0]) : 0, hi = j1 < MK ? gf_canon(acc[j1 < NAP ? j1 : 0]) : 0;
+            wv[i] = lo | (hi << 16);
+        }
+        bg[q] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+    }
 #pragma unroll
     for (int j = 0; j < K; j++) plane(pb, sl, b, (half ? sl.G0 : sl.B0) + j)[p] = (u16)gf_canon(acc[j]);
 #pragma unroll
@@ -579,9 +663,9 @@ __global__ void __launch_bounds__(128) k_assemble(ProveBufs pb)
         __syncthreads();
         for (int idx = tid; idx < nr * MK; idx += 128) {
             const int r = idx / MK, j = idx % MK, p = sp[r];
-            const u16 *bg = pb.BG + ((size_t)b * NP + p) * (2 * MK);
+            const u16 *bg = pb.BG + ((size_t)b * NP + p) * (2 * BGH);
             *out16(L.o_beta, (size_t)(r0 + r) * MK + j) = bg[j];
-            *out16(L.o_gamma, (size_t)(r0 + r) * MK + j) = bg[MK + j];
+            *out16(L.o_gamma, (size_t)(r0 + r) * MK + j) = bg[BGH + j];
         }
         for (int idx = tid; idx < nr * 8; idx += 128) {         // 32-byte digests as 8 x u32 (proofs are only 4-byte aligned)
             const int r = idx / 8, w = idx % 8, p = sp[r];

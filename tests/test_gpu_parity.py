@@ -80,7 +80,7 @@ def test_prove_matches_reference_golden(ctxs, case):
 @pytest.mark.parametrize("k", [2, 3, 4])
 def test_prove_batch_matches_oracle(ctxs, k):
     """A ragged batch (not a multiple of the chunk, spans two chunks) against the oracle, byte for byte."""
-    ctx = ctxs(k, 8)
+    ctx = ctxs(k, 8, 1)      # one lane: chunks of 8 run back to back, so the scratch holds the last chunk
     n = 11
     seeds = np.stack([np.frombuffer(O.seed_of(1000 + i), np.uint8) for i in range(n)])
     pk, sk, pi = ctx.prove_batch(seeds)
@@ -104,8 +104,8 @@ def test_prove_empty_batch(ctxs):
 def test_prove_is_placement_independent(ctxs):
     """Same seeds through different chunkings / batch positions give the same bytes."""
     seeds = seeds_for_range(5, 0, 6)
-    a = ctxs(2, 8).prove_batch(seeds)
-    b = ctxs(2, 64).prove_batch(seeds[::-1].copy())
+    a = ctxs(2, 8, 1).prove_batch(seeds)
+    b = ctxs(2, 2, 3).prove_batch(seeds[::-1].copy())     # three lanes, sub-batches of two
     for x, y in zip(a, b):
         assert (x == y[::-1]).all()
 
@@ -180,7 +180,7 @@ def test_verify_noncanonical_values_match_oracle(ctxs):
 
 # ---------------- BASELINE config 2 at full size: properties + sampled bit-exactness ----------------
 def test_full_batch_1024_k2(ctxs):
-    ctx = ctxs(2, 1024)
+    ctx = ctxs(2, 512, 2)
     n = 1024
     seeds = seeds_for_range(20240, 0, n)
     pk, sk, pi = ctx.prove_batch(seeds)
