@@ -38,7 +38,8 @@ def parse():
     ap.add_argument("--kyber-k", type=int, default=2)
     ap.add_argument("--batch", type=int, default=1024, help="proofs per rank per step")
     ap.add_argument("--chunk", type=int, default=0, help="proofs per kernel wave (0 = batch / lanes)")
-    ap.add_argument("--lanes", type=int, default=2, help="pipeline lanes (CUDA streams with their own scratch)")
+    ap.add_argument("--lanes", type=int, default=1, help="pipeline lanes (CUDA streams with their own scratch) of the device-resident run")
+    ap.add_argument("--e2e-lanes", type=int, default=8, help="lanes of the host-buffer (e2e) run: sub-batches whose D2H copies overlap compute")
     ap.add_argument("--cpu-sample", type=int, default=8, help="proofs of the bounded single-core CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--verify", action="store_true", help="also time kyber_kosk_verify on the produced proofs")
@@ -150,6 +151,7 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("KOSK_NCCL_DEBUG", "WARN")     # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     k, B = args.kyber_k, args.batch
     chunk = args.chunk or -(-B // args.lanes)
@@ -204,9 +206,11 @@ def run_b200(args):
     h_sk = torch.empty(B * nsk, dtype=torch.uint8).pin_memory()
     h_pi = torch.empty(B * npi, dtype=torch.uint8).pin_memory()
 
+    ctx_e = KoskContext(k, local, -(-B // args.e2e_lanes), args.e2e_lanes) if args.e2e_lanes != args.lanes else ctx
+
     def e2e_step(s):
-        rc = ctx.lib.kosk_b200_prove_batch(ctx._h, B, h_seeds[s].data_ptr(), h_pk.data_ptr(), h_sk.data_ptr(), h_pi.data_ptr())
-        assert rc == 0, ctx.lib.kosk_b200_last_error()
+        rc = ctx_e.lib.kosk_b200_prove_batch(ctx_e._h, B, h_seeds[s].data_ptr(), h_pk.data_ptr(), h_sk.data_ptr(), h_pi.data_ptr())
+        assert rc == 0, ctx_e.lib.kosk_b200_last_error()
     e2e_step(args.steps)
     barrier()
     t0 = time.perf_counter()
@@ -264,7 +268,8 @@ def run_b200(args):
             "config": {"workload": f"Kyber{256 * k} kyber_verifiable_keygen, batch of {B} independent proofs per GPU (BASELINE configs[1])",
                        "kyber_k": k, "batch_per_gpu": B, "chunk": chunk, "lanes": args.lanes, "parallelism": f"proof-sharded x{world}, no collective",
                        "l2": f"per-step working set {B * (npi + 1_500_000) / 1e6:.0f} MB >> 126 MB L2, fresh seeds every step"},
-            "e2e": {"value": world * B * args.steps / e2e_max, "unit": "proofs/s", "h2d_bytes_per_step": B * 32, "d2h_bytes_per_step": B * (npk + nsk + npi)},
+            "e2e": {"value": world * B * args.steps / e2e_max, "unit": "proofs/s", "h2d_bytes_per_step": B * 32, "d2h_bytes_per_step": B * (npk + nsk + npi),
+                    "lanes": args.e2e_lanes, "api": "kosk_b200_prove_batch (host buffers, pinned)"},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "int32-pipe", "kernel": "k_gf_gemm<8> (share evaluation, ss.cpp:23-32)", "achieved": achieved_tmac, "peak": peak_tmac,
@@ -285,6 +290,8 @@ def run_b200(args):
         if not args.no_cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_baseline(k, args.cpu_sample)
         print(json.dumps(out))
+    if ctx_e is not ctx:
+        ctx_e.close()
     ctx.close()
     if world > 1:
         dist.barrier()

@@ -51,8 +51,9 @@ enum { KOSK_PH_KEYGEN = 0, KOSK_PH_EXPAND, KOSK_PH_SHARE1, KOSK_PH_COMMIT, KOSK_
 // different lanes so that latency-bound phases (the sequential Fiat-Shamir sponges), ALU-pipe phases (Keccak) and
 // FMA-pipe phases (share evaluation) of different sub-batches overlap on the SMs, and D2H copies overlap compute.
 struct Lane {
-    cudaStream_t st = nullptr;
-    cudaEvent_t done = nullptr;
+    cudaStream_t st = nullptr;            // main (high priority) stream of the lane
+    cudaStream_t st_lo = nullptr;         // low-priority stream for the long share-evaluation launch
+    cudaEvent_t done = nullptr, ev_a = nullptr, ev_b = nullptr;
     ProveBufs pb{};
     u8 *d_seeds = nullptr, *d_pk = nullptr, *d_sk = nullptr, *d_pi = nullptr, *d_ok = nullptr;   // staging of the host-buffer API
     VerifyBufs vb{};
@@ -61,7 +62,7 @@ struct Lane {
 };
 
 struct kosk_b200_ctx {
-    int k = 0, device = 0, chunk = 0, gemm_regs = 128;
+    int k = 0, device = 0, chunk = 0, gemm_regs = 128, use_prio = 2;
     Slots sl; Layout L;
     uint64_t launches = 0;
     // constant tables
@@ -76,11 +77,11 @@ struct kosk_b200_ctx {
     double phase_ms[KOSK_NPHASE] = {0}; uint64_t phase_calls[KOSK_NPHASE] = {0};
 };
 
-static void prof_mark(kosk_b200_ctx *c, Lane &ln, int phase)
+static void prof_mark(kosk_b200_ctx *c, Lane &ln, int phase, cudaStream_t on = nullptr)
 {
     if (!c->prof) return;
     if (ln.ev_used >= (int)ln.ev.size()) { cudaEvent_t e; cudaEventCreate(&e); ln.ev.push_back(e); }
-    cudaEventRecord(ln.ev[ln.ev_used], ln.st);
+    cudaEventRecord(ln.ev[ln.ev_used], on ? on : ln.st);
     ln.ev_phase.push_back({phase, ln.ev_used});
     ln.ev_used++;
 }
@@ -111,6 +112,9 @@ static void ctx_free(kosk_b200_ctx *c)
         verify_free(ln.vb);
         for (cudaEvent_t e : ln.ev) cudaEventDestroy(e);
         if (ln.done) cudaEventDestroy(ln.done);
+        if (ln.ev_a) cudaEventDestroy(ln.ev_a);
+        if (ln.ev_b) cudaEventDestroy(ln.ev_b);
+        if (ln.st_lo) cudaStreamDestroy(ln.st_lo);
         if (ln.st) cudaStreamDestroy(ln.st);
     }
     if (c->ev_start) cudaEventDestroy(c->ev_start);
@@ -145,6 +149,7 @@ int kosk_b200_create_ex(kosk_b200_ctx **out, int k, int device, int max_chunk, i
     if (nlanes <= 0) nlanes = 2;
     if (nlanes > 8) nlanes = 8;
     { const char *e = getenv("KOSK_B200_GEMM_REGS"); if (e) c->gemm_regs = atoi(e) <= 96 ? 96 : 128; }
+    { const char *e = getenv("KOSK_B200_PRIO"); if (e) c->use_prio = atoi(e); }
     const Slots &sl = c->sl; const Layout &L = c->L;
     const size_t B = (size_t)c->chunk;
 #define ALLOC(ptr, bytes) do { if (cudaMalloc((void **)&(ptr), (bytes)) != cudaSuccess) { ctx_free(c); return fail(KOSK_E_NOMEM, "cudaMalloc failed for " #ptr); } } while (0)
@@ -206,8 +211,24 @@ int kosk_b200_create_ex(kosk_b200_ctx **out, int k, int device, int max_chunk, i
         ALLOC(ln.pb.I, B * NT * 2); ALLOC(ln.pb.REST, B * NR * 2);
         ALLOC(ln.d_seeds, B * 32); ALLOC(ln.d_pk, B * L.pk_bytes); ALLOC(ln.d_sk, B * L.sk_bytes); ALLOC(ln.d_pi, B * L.proof_bytes); ALLOC(ln.d_ok, B);
         if (verify_alloc(ln.vb, k, c->chunk) != 0) { ctx_free(c); return fail(KOSK_E_NOMEM, "cudaMalloc failed for verifier scratch"); }
-        CU(cudaStreamCreateWithFlags(&ln.st, cudaStreamNonBlocking));
+        {
+            // use_prio 0: all lanes equal; 1: per-lane hi/lo stream pair (long GEMM on lo); 2: staggered lanes -- lane 0 runs
+            // ahead at the highest priority and later lanes fill its latency-bound gaps, so sub-batches finish in order and
+            // their D2H copies overlap the compute of the following ones.
+            int lo = 0, hi = 0; CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));      // hi is numerically smaller
+            const int li = (int)(&ln - &c->lanes[0]);
+            if (c->use_prio == 1) {
+                CU(cudaStreamCreateWithPriority(&ln.st, cudaStreamNonBlocking, hi));
+                CU(cudaStreamCreateWithPriority(&ln.st_lo, cudaStreamNonBlocking, lo));
+            } else if (c->use_prio == 2) {
+                CU(cudaStreamCreateWithPriority(&ln.st, cudaStreamNonBlocking, std::min(lo, hi + li)));
+            } else {
+                CU(cudaStreamCreateWithFlags(&ln.st, cudaStreamNonBlocking));
+            }
+        }
         CU(cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ln.ev_a, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ln.ev_b, cudaEventDisableTiming));
     }
     CU(cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming));
     CU(cudaDeviceSynchronize());
@@ -248,8 +269,15 @@ static int prove_chunk(kosk_b200_ctx *c, Lane &ln, int B, const u8 *d_seeds, u8 
     k_expand_f<K><<<(B * sl.F + 63) / 64, 64, 0, st>>>(pb);
     k_ntt_f<K><<<dim3(sl.F, B), 128, 0, st>>>(pb);
     k_tails<K><<<(B * (sl.n1 + K) + 63) / 64, 64, 0, st>>>(pb);
-    prof_mark(c, ln, KOSK_PH_SHARE1);
-    launch_share_eval(c, pb.Y, pb.SH, 0, sl.n1, sl.n2, sl.nslot, B, st);
+    if (ln.st_lo) {          // long FMA-pipe launch on the low-priority stream: other lanes' Keccak / FS kernels get SM slots first
+        CU(cudaEventRecord(ln.ev_a, st)); CU(cudaStreamWaitEvent(ln.st_lo, ln.ev_a, 0));
+        prof_mark(c, ln, KOSK_PH_SHARE1, ln.st_lo);
+        launch_share_eval(c, pb.Y, pb.SH, 0, sl.n1, sl.n2, sl.nslot, B, ln.st_lo);
+        CU(cudaEventRecord(ln.ev_b, ln.st_lo)); CU(cudaStreamWaitEvent(st, ln.ev_b, 0));
+    } else {
+        prof_mark(c, ln, KOSK_PH_SHARE1);
+        launch_share_eval(c, pb.Y, pb.SH, 0, sl.n1, sl.n2, sl.nslot, B, st);
+    }
     prof_mark(c, ln, KOSK_PH_COMMIT);
     HashSrc hc{pb.SH, (long long)sl.nslot * SLD, 1, SLD, SOFF, c->d_tab_commit, nullptr, 0};
     k_hash_records<NCOMMIT><<<dim3(ptiles, B), 128, 0, st>>>(hc, pb.TCR, pb.SH, sl.nslot, sl.TC0);

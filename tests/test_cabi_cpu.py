@@ -55,3 +55,20 @@ def test_sass_is_sm100a(built_lib):
         pytest.skip("cuobjdump not available")
     out = subprocess.run([cuobjdump, "-lelf", built_lib], capture_output=True, text=True).stdout
     assert "sm_100a" in out
+
+
+def test_dropin_header_compiles_like_the_reference_api(built_lib, tmp_path):
+    """include/kosk_dropin.hpp exposes the reference's names and signatures (kosk.hpp:13-24) for every KYBER_K."""
+    import subprocess
+    src = tmp_path / "t.cpp"
+    src.write_text('#include "kosk_dropin.hpp"\n'
+                   'static_assert(sizeof(kyber_keypair) == KYBER_PUBLICKEYBYTES + KYBER_SECRETKEYBYTES, "layout");\n'
+                   'void (*f)(kyber_keypair *, uint8_t *) = &kyber_verifiable_keygen;\n'
+                   'bool (*g)(const uint8_t *, const uint8_t *) = &kyber_kosk_verify;\n'
+                   'int main() { return (int)(MPCITH_PROOF_SIZE == 0); }\n')
+    libdir = os.path.join(ROOT, "mpcith_kyber_kosk_b200")
+    for k, sizes in ((2, 2432), (3, 3584), (4, 4736)):
+        exe = tmp_path / f"t{k}"
+        subprocess.run(["g++", "-std=c++11", f"-DKYBER_K={k}", "-I" + os.path.join(ROOT, "include"), str(src), "-L" + libdir,
+                        "-lkosk_b200", "-Wl,-rpath," + libdir, "-o", str(exe)], check=True)
+        assert subprocess.run([str(exe)]).returncode == 0

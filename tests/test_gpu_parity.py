@@ -197,3 +197,30 @@ def test_full_batch_1024_k2(ctxs):
     swapped = pk.copy(); swapped[[0, 1]] = swapped[[1, 0]]
     ok2 = ctx.verify_batch(pi[:4], swapped[:4])
     assert list(ok2) == [False, False, True, True]
+
+
+# ---------------- drop-in boundary: the reference-shaped C++ API over the C ABI ----------------
+def _fnv(b):
+    h = 14695981039346656037
+    for x in bytes(b):
+        h = ((h ^ x) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    return "%016x" % h
+
+
+@pytest.mark.parametrize("k", [2, 4])
+def test_dropin_cpp_program(built_lib, tmp_path, k):
+    """examples/main_dropin.cpp uses the reference's names (kyber_keypair, kyber_verifiable_keygen,
+    kyber_kosk_verify, MPCITH_PROOF_SIZE) and must reproduce the oracle's bytes for an injected seed."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / f"main_dropin_k{k}")
+    libdir = os.path.join(root, "mpcith_kyber_kosk_b200")
+    subprocess.run(["g++", "-std=c++11", "-O2", f"-DKYBER_K={k}", "-I" + os.path.join(root, "include"),
+                    os.path.join(root, "examples", "main_dropin.cpp"), "-L" + libdir, "-lkosk_b200",
+                    "-Wl,-rpath," + libdir, "-o", exe], check=True)
+    seed = O.seed_of(4242 + k)
+    out = subprocess.run([exe], env=dict(os.environ, KOSK_SEED_HEX=seed.hex()), capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "kosk verify success" in out.stdout and "[tamper] rejected" in out.stdout
+    opk, osk, opi = O.oracle_prove(k, seed)
+    assert f"pk={_fnv(opk)} sk={_fnv(osk)} proof={_fnv(opi)}" in out.stdout
