@@ -52,6 +52,12 @@ int kosk_b200_verifiable_keygen(kosk_b200_ctx *ctx, const uint8_t seed[32], uint
 /* kyber_kosk_verify (kosk.hpp:22-23): returns 1 = accept, 0 = reject, <0 = error.  Host buffers. */
 int kosk_b200_kosk_verify(kosk_b200_ctx *ctx, const uint8_t *pi, const uint8_t *pk);
 
+/* Hardened verifier, a deliberate, switchable deviation from the reference's accept set; default off.
+ * When on, kosk_b200_*verify* additionally rejects (i) any field element >= 3329 anywhere in the proof and (ii) rest-party
+ * shares of t / s_eta / e_eta that do not lie on the interpolated sharing polynomial (the reference reads only the first
+ * 407 of them).  Proofs produced by kosk_b200_*keygen* / the reference prover are unaffected. */
+int kosk_b200_set_strict(kosk_b200_ctx *ctx, int on);
+
 /* Batch mode, host buffers, densely packed: seeds[n][32], pk[n][pk_bytes], sk[n][sk_bytes], pi[n][proof_bytes].
  * Host<->device copies happen inside (pinned buffers are used asynchronously). */
 int kosk_b200_prove_batch(kosk_b200_ctx *ctx, size_t n, const uint8_t *seeds, uint8_t *pk, uint8_t *sk, uint8_t *pi);

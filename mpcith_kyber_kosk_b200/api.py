@@ -17,7 +17,7 @@ EXPORTS = [
     "kosk_b200_prove_batch", "kosk_b200_verify_batch", "kosk_b200_prove_batch_device", "kosk_b200_verify_batch_device",
     "kosk_b200_share_eval", "kosk_b200_sha3_256_rows", "kosk_b200_ntt_rows", "kosk_b200_share_eval_device",
     "kosk_b200_kernel_launches", "kosk_b200_debug_fetch", "kosk_b200_sync",
-    "kosk_b200_set_profiling", "kosk_b200_phase_times", "kosk_b200_int_peak",
+    "kosk_b200_set_strict", "kosk_b200_set_profiling", "kosk_b200_phase_times", "kosk_b200_int_peak",
 ]
 
 _lib = None
@@ -62,6 +62,7 @@ def load_library(path=None):
     lib.kosk_b200_debug_fetch.argtypes = [vp, ctypes.c_char_p, u8p, sz]
     lib.kosk_b200_sync.argtypes = [vp]
     lib.kosk_b200_set_profiling.argtypes = [vp, i32]
+    lib.kosk_b200_set_strict.argtypes = [vp, i32]
     lib.kosk_b200_phase_times.argtypes = [vp, u8p, u8p, i32, i32]
     lib.kosk_b200_int_peak.argtypes = [vp, u8p]
     if path == LIB_PATH:
@@ -186,6 +187,10 @@ class KoskContext:
         return out.view(dtype)
 
     PHASES = ["keygen", "expand", "share1", "commit", "fs1", "eval", "open", "share2", "view", "fs2", "assemble", "verify"]
+
+    def set_strict(self, on=True):
+        """Hardened verifier; default off = the reference's accept set."""
+        self._check(self.lib.kosk_b200_set_strict(self._h, 1 if on else 0), "set_strict")
 
     def set_profiling(self, on=True):
         self._check(self.lib.kosk_b200_set_profiling(self._h, 1 if on else 0), "set_profiling")

@@ -284,7 +284,7 @@ static int prove_chunk(kosk_b200_ctx *c, Lane &ln, int B, const u8 *d_seeds, u8 
     prof_mark(c, ln, KOSK_PH_FS1);
     k_fs1<K><<<(B + 3) / 4, 128, 0, st>>>(pb.TCR, pb.PW, B);
     prof_mark(c, ln, KOSK_PH_EVAL);
-    k_eval<K><<<dim3(ptiles, B), 256, 0, st>>>(pb);
+    k_eval<K><<<dim3(3, B), 256, 0, st>>>(pb);
     prof_mark(c, ln, KOSK_PH_OPEN);
     k_open<K><<<B, 128, 0, st>>>(pb);
     prof_mark(c, ln, KOSK_PH_SHARE2);
@@ -554,6 +554,13 @@ int kosk_b200_debug_fetch(kosk_b200_ctx *c, const char *what, void *out, size_t 
     return KOSK_OK;
 }
 
+
+int kosk_b200_set_strict(kosk_b200_ctx *c, int on)
+{
+    if (!c) return fail(KOSK_E_ARG, "null argument");
+    for (Lane &ln : c->lanes) ln.vb.strict = on != 0;
+    return KOSK_OK;
+}
 
 int kosk_b200_set_profiling(kosk_b200_ctx *c, int on)
 {

@@ -269,15 +269,16 @@ template <int NVALS>
 __global__ void __launch_bounds__(128)
 k_hash_records(const HashSrc hs, u8 *__restrict__ out_rows, u16 *__restrict__ out_planes, int nslot, int out_plane_slot)
 {
-    __shared__ int16_t stab[NVALS];
-    for (int i = threadIdx.x; i < NVALS; i += 128) stab[i] = hs.tab ? hs.tab[i] : (int16_t)i;
+    __shared__ uint32_t soff[NVALS];      // byte offset of record element v from the CTA's (uniform) base
+    for (int i = threadIdx.x; i < NVALS; i += 128) soff[i] = (uint32_t)((hs.tab ? hs.tab[i] : i) * hs.elem_stride * 2);
     __syncthreads();
     const int b = blockIdx.y, idx = blockIdx.x * 128 + threadIdx.x;
     int p = idx;
     if (hs.plist) { if (idx >= hs.nlist) return; p = hs.plist[(size_t)b * hs.nlist + idx]; if (p >= NP) return; }
     else if (idx >= NP) return;
-    const u16 *base = hs.src + (size_t)b * hs.proof_stride + (size_t)idx * hs.item_stride + hs.off0;
-    const size_t es = (size_t)hs.elem_stride;
+    const char *cta_base = reinterpret_cast<const char *>(hs.src + (size_t)b * hs.proof_stride + hs.off0);
+    const uint32_t toff = (uint32_t)(idx * hs.item_stride * 2);
+    auto ld = [&](int v) -> uint64_t { return *reinterpret_cast<const u16 *>(cta_base + (toff + soff[v])); };
     uint64_t a[25];
     keccak_zero(a);
     constexpr int NFULL = (2 * NVALS) / 136, REMV = NVALS - NFULL * 68;   // u16 values left for the last block
@@ -285,10 +286,9 @@ k_hash_records(const HashSrc hs, u8 *__restrict__ out_rows, u16 *__restrict__ ou
     for (int blk = 0; blk < NFULL; blk++) {
 #pragma unroll
         for (int l = 0; l < 17; l++) {
-            uint64_t w = 0;
-#pragma unroll
-            for (int i = 0; i < 4; i++) w |= (uint64_t)base[(size_t)stab[blk * 68 + 4 * l + i] * es] << (16 * i);
-            a[l] ^= w;
+            const uint32_t w0 = (uint32_t)ld(blk * 68 + 4 * l) | ((uint32_t)ld(blk * 68 + 4 * l + 1) << 16);
+            const uint32_t w1 = (uint32_t)ld(blk * 68 + 4 * l + 2) | ((uint32_t)ld(blk * 68 + 4 * l + 3) << 16);
+            a[l] ^= ((uint64_t)w1 << 32) | w0;
         }
         keccak_f1600(a);
     }
@@ -297,7 +297,7 @@ k_hash_records(const HashSrc hs, u8 *__restrict__ out_rows, u16 *__restrict__ ou
         uint64_t w = 0;
 #pragma unroll
         for (int i = 0; i < 4; i++)
-            if (4 * l + i < REMV) w |= (uint64_t)base[(size_t)stab[NFULL * 68 + 4 * l + i] * es] << (16 * i);
+            if (4 * l + i < REMV) w |= ld(NFULL * 68 + 4 * l + i) << (16 * i);
         if (l == REMV / 4) w |= 0x06ULL << (16 * (REMV % 4));
         if (l == 16) w |= 0x8000000000000000ULL;
         a[l] ^= w;
@@ -319,7 +319,7 @@ k_hash_records(const HashSrc hs, u8 *__restrict__ out_rows, u16 *__restrict__ ou
 // exchange words with warp shuffles.  Used for the two strictly sequential Fiat-Shamir sponges (343 permutations
 // each, mlwe_prover.cpp:131-135, :445-449), where one proof per warp cuts the latency ~5x against one per thread.
 struct WarpKeccak {
-    int t, x, y, rho, src_pi, l5, l10, l15, l20, lm1, lp1, c1, c2;
+    int t, x, y, rho, src_pi, src_c1, src_c2, l5, l10, l15, l20, lm1, lp1;
     __device__ __forceinline__ void init()
     {
         const int rho_tab[25] = {0, 1, 62, 28, 27, 36, 44, 6, 55, 20, 3, 10, 43, 25, 39, 41, 45, 15, 21, 8, 18, 2, 61, 56, 14};
@@ -333,7 +333,10 @@ struct WarpKeccak {
         l5 = lane < 25 ? (t + 5) % 25 : lane; l10 = lane < 25 ? (t + 10) % 25 : lane;
         l15 = lane < 25 ? (t + 15) % 25 : lane; l20 = lane < 25 ? (t + 20) % 25 : lane;
         lm1 = lane < 25 ? (x + 4) % 5 + 5 * y : lane; lp1 = lane < 25 ? (x + 1) % 5 + 5 * y : lane;
-        c1 = lp1; c2 = lane < 25 ? (x + 2) % 5 + 5 * y : lane;
+        // chi reads B[x+1][y] and B[x+2][y]; fetch them straight from their pre-pi source lanes (one shuffle stage less)
+        const int x1 = (x + 1) % 5, x2 = (x + 2) % 5;
+        src_c1 = lane < 25 ? ((3 * y + x1) % 5) + 5 * x1 : lane;
+        src_c2 = lane < 25 ? ((3 * y + x2) % 5) + 5 * x2 : lane;
     }
     static __device__ __forceinline__ uint64_t shfl(uint64_t v, int src)
     {
@@ -345,13 +348,15 @@ struct WarpKeccak {
         const bool lane0 = (threadIdx.x & 31) == 0;
 #pragma unroll 1
         for (int r = 0; r < 24; r++) {
+            // theta: column parity (REDUX.XOR over per-column masks was measured 10x slower than four shuffles)
             const uint64_t c = a ^ shfl(a, l5) ^ shfl(a, l10) ^ shfl(a, l15) ^ shfl(a, l20);
             a ^= shfl(c, lm1) ^ rol64(shfl(c, lp1), 1);
             uint32_t lo = (uint32_t)a, hi = (uint32_t)(a >> 32);           // rho: rotate left by a per-lane amount
             if (rho & 32) { const uint32_t tmp = lo; lo = hi; hi = tmp; }
             const uint32_t nh = __funnelshift_l(lo, hi, rho), nl = __funnelshift_l(hi, lo, rho);
-            const uint64_t b = shfl(((uint64_t)nh << 32) | nl, src_pi);  // pi
-            a = b ^ (~shfl(b, c1) & shfl(b, c2));                          // chi
+            const uint64_t ar = ((uint64_t)nh << 32) | nl;
+            const uint64_t b = shfl(ar, src_pi), b1 = shfl(ar, src_c1), b2 = shfl(ar, src_c2);   // pi, fused with chi's two neighbour reads
+            a = b ^ (~b1 & b2);                                            // chi
             if (lane0) a ^= c_keccak_rc[r];                                // iota
         }
         return a;
@@ -461,66 +466,103 @@ __global__ void __launch_bounds__(128) k_fs2(const u8 *__restrict__ VWR, u16 *__
 //   beta[p][j]  = f[p][0]  + sum_{k>=1} alpha_j^k f[p][k]        j < 70
 //   r[p][j']    = f[p][71] + sum_{k>=1} alpha_{70+j'}^k f[p][k]  j' < 2K      (c0 index quirk)
 // and the same over NTT_f.  CTA = 128 parties x {f, NTT_f}; the power table sits in shared memory.
-template <int K>
-__global__ void __launch_bounds__(256, 2) k_eval(ProveBufs pb)
+// Thread = (party pair, {f | NTT_f}, half of the challenge columns): 2 parties x NJ columns of accumulators, so one
+// broadcast LDS.128 of four power-table entries feeds eight IMADs.
+template <int K, int J0, int NJ>
+__device__ __forceinline__ void eval_body(const ProveBufs &pb, const Slots &sl, const int32_t (*spw)[((MK + 2 * K + 3) & ~3)], int b, int half, int p0)
 {
-    constexpr int F = MK + 2 * K + 1, NA = MK + 2 * K, NAP = (NA + 3) & ~3;
-    const Slots sl = make_slots(K);
-    __shared__ __align__(16) int32_t spw[F][NAP];
-    const int b = blockIdx.y, tid = threadIdx.x;
-    const u16 *pw = pb.PW + (size_t)b * NA * F;
-    for (int i = tid; i < F * NAP; i += 256) {
-        int kk = i / NAP, j = i % NAP;
-        int32_t v = 0;
-        if (j < NA) { v = gf_center(pw[j * F + kk]); if (kk == 0 && j >= MK) v = 0; }
-        spw[kk][j] = v;
-    }
-    __syncthreads();
-    const int half = tid >> 7, p = blockIdx.x * 128 + (tid & 127);
-    if (p >= NP) return;
-    const u16 *src = plane(pb, sl, b, half ? sl.Tf0 : sl.f0) + p;
-    int32_t acc[NAP];
+    constexpr int F = MK + 2 * K + 1;
+    const bool two = p0 + 1 < NP;
+    const u16 *src = plane(pb, sl, b, half ? sl.Tf0 : sl.f0) + p0;
+    int32_t acc0[NJ], acc1[NJ];
 #pragma unroll
-    for (int j = 0; j < NAP; j++) acc[j] = 0;
-    constexpr int U = 5;                     // F = 75/77/79: software-pipelined loads, U shares in flight
-    int32_t v[U];
+    for (int j = 0; j < NJ; j++) { acc0[j] = 0; acc1[j] = 0; }
+    constexpr int U = 4;                     // software-pipelined share loads
+    int32_t v0[U], v1[U];
 #pragma unroll
-    for (int u = 0; u < U; u++) v[u] = src[(size_t)u * SLD];
+    for (int u = 0; u < U; u++) { v0[u] = src[(size_t)u * SLD]; v1[u] = two ? src[(size_t)u * SLD + 1] : 0; }
+    int32_t c71a = 0, c71b = 0;
 #pragma unroll 1
     for (int k0 = 0; k0 < F; k0 += U) {
-        int32_t cur[U];
+        int32_t a0[U], a1[U];
 #pragma unroll
-        for (int u = 0; u < U; u++) { cur[u] = v[u]; if (k0 + U + u < F) v[u] = src[(size_t)(k0 + U + u) * SLD]; }
+        for (int u = 0; u < U; u++) {
+            a0[u] = gf_center(v0[u]); a1[u] = gf_center(v1[u]);
+            if (k0 + U + u < F) { v0[u] = src[(size_t)(k0 + U + u) * SLD]; v1[u] = two ? src[(size_t)(k0 + U + u) * SLD + 1] : 0; }
+        }
 #pragma unroll
         for (int u = 0; u < U; u++) {
             if (k0 + u < F) {
-                const int32_t c = gf_center(cur[u]);
+                if (k0 + u == MK + 1) { c71a = a0[u]; c71b = a1[u]; }
 #pragma unroll
-                for (int j4 = 0; j4 < NAP / 4; j4++) {
-                    const int4 w = *reinterpret_cast<const int4 *>(&spw[k0 + u][4 * j4]);
-                    acc[4 * j4] += c * w.x; acc[4 * j4 + 1] += c * w.y; acc[4 * j4 + 2] += c * w.z; acc[4 * j4 + 3] += c * w.w;
+                for (int j4 = 0; j4 < NJ / 4; j4++) {
+                    const int4 w = *reinterpret_cast<const int4 *>(&spw[k0 + u][J0 + 4 * j4]);
+                    acc0[4 * j4] += a0[u] * w.x; acc0[4 * j4 + 1] += a0[u] * w.y; acc0[4 * j4 + 2] += a0[u] * w.z; acc0[4 * j4 + 3] += a0[u] * w.w;
+                    acc1[4 * j4] += a1[u] * w.x; acc1[4 * j4 + 1] += a1[u] * w.y; acc1[4 * j4 + 2] += a1[u] * w.z; acc1[4 * j4 + 3] += a1[u] * w.w;
                 }
             }
         }
     }
-    const int32_t c71 = gf_center(src[(size_t)(MK + 1) * SLD]);
-    // beta | gamma rows of this party: 9 x 16-byte stores per half (BGH = 144 u16 per half, 16B-aligned)
-    uint4 *bg = reinterpret_cast<uint4 *>(pb.BG + ((size_t)b * NP + p) * (2 * BGH) + half * BGH);
 #pragma unroll
-    for (int q = 0; q < BGH / 8; q++) {
-        uint32_t wv[4];
+    for (int pp = 0; pp < 2; pp++) {
+        if (pp == 1 && !two) break;
+        const int p = p0 + pp;
+        const int32_t *acc = pp ? acc1 : acc0;
+        const int32_t c71 = pp ? c71b : c71a;
+        // beta | gamma row of this party: 16-byte stores (BGH = 144 u16 per half-row, 16B-aligned)
+        uint4 *bg = reinterpret_cast<uint4 *>(pb.BG + ((size_t)b * NP + p) * (2 * BGH) + half * BGH + J0);
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const int j0 = 8 * q + 2 * i, j1 = j0 + 1;
-            const uint32_t lo = j0 < MK ? gf_canon(acc[j0 < NAP ? j0 : 0]) : 0, hi = j1 < MK ? gf_canon(acc[j1 < NAP ? j1 : 0]) : 0;
-            wv[i] = lo | (hi << 16);
+        for (int q = 0; q < (NJ + 7) / 8; q++) {
+            if (J0 + 8 * q >= BGH) break;
+            uint32_t wv[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int j0 = 8 * q + 2 * i, j1 = j0 + 1;
+                const uint32_t lo = (j0 < NJ && J0 + j0 < MK) ? gf_canon(acc[j0 < NJ ? j0 : 0]) : 0;
+                const uint32_t hi = (j1 < NJ && J0 + j1 < MK) ? gf_canon(acc[j1 < NJ ? j1 : 0]) : 0;
+                wv[i] = lo | (hi << 16);
+            }
+            bg[q] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
         }
-        bg[q] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+#pragma unroll
+        for (int j = 0; j < NJ; j++) {
+            const int jj = J0 + j;
+            if (jj < K) plane(pb, sl, b, (half ? sl.G0 : sl.B0) + jj)[p] = (u16)gf_canon(acc[j]);
+            if (jj >= MK && jj < MK + 2 * K) plane(pb, sl, b, (half ? sl.TR0 : sl.R0) + (jj - MK))[p] = (u16)gf_canon(acc[j] + c71);
+        }
     }
+}
+
+template <int K>
+__global__ void __launch_bounds__(256, 2) k_eval(ProveBufs pb)
+{
+    constexpr int F = MK + 2 * K + 1, NA = MK + 2 * K, NAP = (NA + 3) & ~3, JSPLIT = 40;
+    const Slots sl = make_slots(K);
+    __shared__ __align__(16) int32_t spw[F][NAP];
+    const int b = blockIdx.y, tid = threadIdx.x;
+    // power table of this proof: [NA][F] u16, read as coalesced 32-bit words and transposed/centered into shared memory
+    const uint32_t *pw2 = reinterpret_cast<const uint32_t *>(pb.PW + (size_t)b * NA * F);       // NA*F is even for K = 2, 3, 4
+    for (int i = tid; i < F * NAP; i += 256) (&spw[0][0])[i] = 0;
+    __syncthreads();
+#pragma unroll 4
+    for (int i = tid; i < NA * F / 2; i += 256) {
+        const uint32_t v = pw2[i];
 #pragma unroll
-    for (int j = 0; j < K; j++) plane(pb, sl, b, (half ? sl.G0 : sl.B0) + j)[p] = (u16)gf_canon(acc[j]);
-#pragma unroll
-    for (int j = 0; j < 2 * K; j++) plane(pb, sl, b, (half ? sl.TR0 : sl.R0) + j)[p] = (u16)gf_canon(acc[MK + j] + c71);
+        for (int h = 0; h < 2; h++) {
+            const int e = 2 * i + h, j = e / F, kk = e % F;
+            if (!(kk == 0 && j >= MK)) spw[kk][j] = gf_center(h ? v >> 16 : v & 0xFFFF);
+        }
+    }
+    __syncthreads();
+    const int w = tid >> 5, lane = tid & 31;
+    const int half = (w >> 2) & 1, jh = (w >> 1) & 1;
+#pragma unroll 1
+    for (int tile = blockIdx.x; tile < (NP + 127) / 128; tile += gridDim.x) {      // several party tiles per CTA amortise the table load
+        const int p0 = tile * 128 + 2 * ((w & 1) * 32 + lane);
+        if (p0 >= NP) continue;
+        if (jh == 0) eval_body<K, 0, JSPLIT>(pb, sl, spw, b, half, p0);
+        else eval_body<K, JSPLIT, NAP - JSPLIT>(pb, sl, spw, b, half, p0);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

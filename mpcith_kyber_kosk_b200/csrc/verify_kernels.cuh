@@ -15,7 +15,7 @@ constexpr int LM1_ROWS = 512;     // 407 targets padded to the GEMM's 128-column
 constexpr int OPLD = 160;         // opened-party values: beta[70] gamma[70] r[2k] NTT_r[2k]
 
 enum VFlag { VF_I = 1, VF_BG = 2, VF_SR = 4, VF_NTT = 8, VF_ASR = 16, VF_T = 32, VF_TREL = 64, VF_ETA = 128,
-             VF_SUBETA = 256, VF_UZ = 512, VF_U2D = 1024, VF_FS2 = 2048 };
+             VF_SUBETA = 256, VF_UZ = 512, VF_U2D = 1024, VF_FS2 = 2048, VF_STRICT = 4096 };
 
 struct VerifyTables { const int16_t *St, *R1, *R2; const u16 *inv; };
 
@@ -28,6 +28,7 @@ struct VerifyBufs {
     u16 *ABG = nullptr, *BS = nullptr, *A1 = nullptr, *YV = nullptr, *A2 = nullptr, *UZ = nullptr, *VSH = nullptr, *U2 = nullptr, *UR = nullptr;
     int16_t *LM1 = nullptr, *LM2 = nullptr;
     int k = 0, chunk = 0;
+    int strict = 0;   // hardened decoding: off by default = the reference's accept set
 };
 
 struct VDims {
@@ -333,6 +334,13 @@ __global__ void __launch_bounds__(128) kv_check_parties(VerifyBufs vb, const u8 
         for (int i = 0; i < K; i++) {
             if (V(i) != pi16(pi, L.o_sr, (size_t)pos * K + i)) f |= VF_SR;              // :232-246
             if (V(K + i) != pi16(pi, L.o_er, (size_t)pos * K + i)) f |= VF_SR;
+            if (vb.strict) {   // the reference only consumes the first 407 rest parties of these fields (mlwe_verifier.cpp:321-323, :390-394)
+                if (V(2 * K + i) != pi16(pi, L.o_t, (size_t)pos * K + i)) f |= VF_STRICT;
+                for (int m = 0; m < E; m++) {
+                    if (V(3 * K + i * E + m) != pi16(pi, L.o_seta, ((size_t)pos * K + i) * E + m)) f |= VF_STRICT;
+                    if (V(3 * K + K * E + i * E + m) != pi16(pi, L.o_eeta, ((size_t)pos * K + i) * E + m)) f |= VF_STRICT;
+                }
+            }
         }
         if (p < D2)                                            // :547-552 rest shares of u^(2d), used raw in gf3329_mul
             for (int r = 0; r < d.n2rows; r++) {
@@ -407,6 +415,22 @@ __global__ void __launch_bounds__(128) kv_final(VerifyBufs vb, u8 *__restrict__ 
     }
 }
 
+// Hardened decoding: every u16 field element of the proof must be a canonical residue (< q).  The reference silently
+// reduces (NTL assignment, gf3329_mul) or never reads some of them.
+template <int K>
+__global__ void __launch_bounds__(256) kv_strict_scan(VerifyBufs vb, const u8 *__restrict__ pis)
+{
+    const Layout L = make_layout(K);
+    const int b = blockIdx.y;
+    const u16 *w = reinterpret_cast<const u16 *>(pis + L.proof_bytes * (size_t)b);
+    const size_t n = L.proof_bytes / 2, i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const size_t off = 2 * i;
+    const bool digest = (off >= L.o_Tcomm && off < L.o_I) || off >= L.o_comm;       // byte strings, not field elements
+    const bool idx = off >= L.o_I && off < L.o_s;                                     // opened-set indices (checked in kv_setup)
+    if (!digest && !idx && w[i] >= Q) atomicOr(&vb.flags[b], VF_STRICT);
+}
+
 template <int K> __global__ void kv_clear(VerifyBufs vb, int B)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -422,6 +446,7 @@ static int verify_chunk_t(VerifyBufs &vb, const VerifyTables &vt, int B, const u
     const int ptiles = (NP + 127) / 128;
     kv_clear<K><<<(B + 127) / 128, 128, 0, st>>>(vb, B); nl++;
     kv_setup<K><<<B, 128, 0, st>>>(vb, d_pi, d_pk); nl++;
+    if (vb.strict) { kv_strict_scan<K><<<dim3((unsigned)((make_layout(K).proof_bytes / 2 + 255) / 256), B), 256, 0, st>>>(vb, d_pi); nl++; }
     {   // V2: commitments of the opened parties
         constexpr int NC = 2 * (K + MK + 2 * K + 1);
         HashSrc hs{vb.CR, (long long)NT * d.crld, d.crld, 1, 0, nullptr, vb.I, NT};

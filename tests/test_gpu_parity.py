@@ -224,3 +224,31 @@ def test_dropin_cpp_program(built_lib, tmp_path, k):
     assert "kosk verify success" in out.stdout and "[tamper] rejected" in out.stdout
     opk, osk, opi = O.oracle_prove(k, seed)
     assert f"pk={_fnv(opk)} sk={_fnv(osk)} proof={_fnv(opi)}" in out.stdout
+
+
+def test_strict_verifier_is_a_superset_of_checks(ctxs):
+    """the switchable hardened decoder rejects what the reference laxly accepts (non-canonical elements,
+    unread t / eta rest shares) and still accepts every honest proof; default (off) stays on the reference's accept set."""
+    k = 2
+    L = O.layout(k)
+    ctx = ctxs(k, 64, 1)
+    opk, osk, opi = O.oracle_prove(k, O.seed_of(5))
+    last = lambda name, nxt: getattr(L, nxt) - 2
+    cases = {}
+    for name, nxt in (("o_t", "o_NTTs"), ("o_seta", "o_eeta"), ("o_eeta", "o_ssub"), ("o_beta", "o_gamma")):
+        t = opi.copy(); t[last(name, nxt)] ^= 1; cases[name + ":last"] = t
+    t = opi.copy(); v = int(t[L.o_t:L.o_t + 2].view(np.uint16)[0]) + 3329
+    t[L.o_t:L.o_t + 2] = np.frombuffer(v.to_bytes(2, "little"), np.uint8); cases["t:+q"] = t
+    cases["honest"] = opi.copy()
+    names = list(cases)
+    batch = np.stack([cases[n] for n in names]); pks = np.repeat(opk[None], len(names), 0)
+    lax = dict(zip(names, ctx.verify_batch(batch, pks)))
+    assert all(lax.values())                                    # reference behaviour: all of these are accepted
+    assert all(O.oracle_verify(k, cases[n], opk) for n in names)
+    ctx.set_strict(True)
+    try:
+        strict = dict(zip(names, ctx.verify_batch(batch, pks)))
+    finally:
+        ctx.set_strict(False)
+    assert strict["honest"] and strict["o_beta:last"]           # beta's unread tail is outside the hardened checks (documented)
+    assert not strict["o_t:last"] and not strict["o_seta:last"] and not strict["o_eeta:last"] and not strict["t:+q"]
