@@ -70,6 +70,16 @@ int kosk_b200_prove_batch_device(kosk_b200_ctx *ctx, size_t n, const uint8_t *d_
 int kosk_b200_verify_batch_device(kosk_b200_ctx *ctx, size_t n, const uint8_t *d_pi, const uint8_t *d_pk,
                                   uint8_t *d_ok, void *stream);
 
+/* Offline / online split.  prepare_randomness + prepare_range_proof (mlwe_prover.cpp:4-59) do not depend
+ * on the key; the reference times them separately (main.cpp:18-28) but has no way to keep them (its (de)serialiser,
+ * mlwe_prover.cpp:61-79, is unused and drops the range-proof half).  pool_create runs that phase for n proofs and keeps
+ * the material (the f / NTT_f / eta sharings) on the device; pool_prove runs only keygen + prove() + encode.  For the
+ * same seeds the outputs are bit-identical to kosk_b200_prove_batch.  Host buffers, synchronous. */
+typedef struct kosk_b200_pool kosk_b200_pool;
+int kosk_b200_pool_create(kosk_b200_ctx *ctx, size_t n, const uint8_t *seeds, kosk_b200_pool **pool);
+int kosk_b200_pool_prove(kosk_b200_pool *pool, uint8_t *pk, uint8_t *sk, uint8_t *pi);
+void kosk_b200_pool_destroy(kosk_b200_pool *pool);
+
 /* Components (BASELINE config 5 microbenches, kernel-level parity tests).
  * share_eval: recompute_share_secrets_ddeg (ss.cpp:76-99) on n rows: y[n][407] -> shares[n][1454]. Host buffers.
  * sha3_256_rows: n independent SHA3-256 over rows of `len` bytes (len even): in[n][len] -> out[n][32].

@@ -17,7 +17,7 @@ EXPORTS = [
     "kosk_b200_prove_batch", "kosk_b200_verify_batch", "kosk_b200_prove_batch_device", "kosk_b200_verify_batch_device",
     "kosk_b200_share_eval", "kosk_b200_sha3_256_rows", "kosk_b200_ntt_rows", "kosk_b200_share_eval_device",
     "kosk_b200_kernel_launches", "kosk_b200_debug_fetch", "kosk_b200_sync",
-    "kosk_b200_set_strict", "kosk_b200_set_profiling", "kosk_b200_phase_times", "kosk_b200_int_peak",
+    "kosk_b200_pool_create", "kosk_b200_pool_prove", "kosk_b200_pool_destroy", "kosk_b200_set_strict", "kosk_b200_set_profiling", "kosk_b200_phase_times", "kosk_b200_int_peak",
 ]
 
 _lib = None
@@ -63,6 +63,10 @@ def load_library(path=None):
     lib.kosk_b200_sync.argtypes = [vp]
     lib.kosk_b200_set_profiling.argtypes = [vp, i32]
     lib.kosk_b200_set_strict.argtypes = [vp, i32]
+    lib.kosk_b200_pool_create.argtypes = [vp, sz, u8p, ctypes.POINTER(vp)]
+    lib.kosk_b200_pool_prove.argtypes = [vp, u8p, u8p, u8p]
+    lib.kosk_b200_pool_destroy.argtypes = [vp]
+    lib.kosk_b200_pool_destroy.restype = None
     lib.kosk_b200_phase_times.argtypes = [vp, u8p, u8p, i32, i32]
     lib.kosk_b200_int_peak.argtypes = [vp, u8p]
     if path == LIB_PATH:
@@ -188,6 +192,14 @@ class KoskContext:
 
     PHASES = ["keygen", "expand", "share1", "commit", "fs1", "eval", "open", "share2", "view", "fs2", "assemble", "verify"]
 
+    # ---- offline / online split ----
+    def pool_create(self, seeds):
+        """Run the key-independent preprocessing for these seeds and keep it on the device."""
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint8).reshape(-1, 32)
+        h = ctypes.c_void_p()
+        self._check(self.lib.kosk_b200_pool_create(self._h, seeds.shape[0], _ptr(seeds), ctypes.byref(h)), "pool_create")
+        return KoskPool(self, h, seeds.shape[0])
+
     def set_strict(self, on=True):
         """Hardened verifier; default off = the reference's accept set."""
         self._check(self.lib.kosk_b200_set_strict(self._h, 1 if on else 0), "set_strict")
@@ -208,6 +220,30 @@ class KoskContext:
 
     def sync(self):
         self._check(self.lib.kosk_b200_sync(self._h), "sync")
+
+
+class KoskPool:
+    """Preprocessed (offline) material of n proofs; prove() runs only the online phase."""
+
+    def __init__(self, ctx, handle, n):
+        self.ctx, self._h, self.n = ctx, handle, n
+
+    def prove(self):
+        c = self.ctx
+        pk, sk, pi = np.empty((self.n, c.pk_bytes), np.uint8), np.empty((self.n, c.sk_bytes), np.uint8), np.empty((self.n, c.proof_bytes), np.uint8)
+        c._check(c.lib.kosk_b200_pool_prove(self._h, _ptr(pk), _ptr(sk), _ptr(pi)), "pool_prove")
+        return pk, sk, pi
+
+    def close(self):
+        if self._h:
+            self.ctx.lib.kosk_b200_pool_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class kyber_keypair:

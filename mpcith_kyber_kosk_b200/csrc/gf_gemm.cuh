@@ -27,7 +27,12 @@ struct GemmArgs {
     int mtotal, ksteps, nvalid, c_off;
     // row m -> storage row (m / rpp) * slots + slot_lo + m % rpp  (planes of one proof are `slots` rows apart)
     int rpp, slot_lo, a_slots, c_slots;
-    int tail;            // 1: also copy A[row][256..406] to C[row][c_off-151 ..] (parties 0..150, ss.cpp:7-11,:77-80)
+    int tail;            // 1: also copy A[row][tail_off .. +150] to C[row][c_off-151 ..] (parties 0..150, ss.cpp:7-11,:77-80)
+    int tail_off;        // element offset of the 151 tail values in an A row (256 unless A was advanced past the secrets)
+    // Constant-secret rows (the eta sharings, mlwe_prover.cpp:41-59): all 256 secrets equal c, so only the 151 tail terms go
+    // through the contraction (A and Bt advanced by 256, ksteps = 10) and c * U[n], U[n] = sum_{j<256} Bt[n][j], is added here.
+    const int16_t *addvec;   // centered U, or nullptr
+    const u16 *scale_src;    // c of row r = scale_src[r * lda] (canonical), same row mapping as A
 };
 
 template <int TM, int NREG>
@@ -114,6 +119,13 @@ __global__ void __maxnreg__(NREG) k_gf_gemm(const GemmArgs g)
         const int m = m0 + (i / 4) * (BM / 2) + ty * 4 + (i & 3);
         if (m >= g.mtotal) continue;
         u16 *dst = Cb + ((size_t)(m / g.rpp) * g.c_slots + g.slot_lo + m % g.rpp) * g.ldc + g.c_off;
+        if (g.addvec) {
+            const int32_t cst = gf_center(g.scale_src[((size_t)(m / g.rpp) * g.a_slots + g.slot_lo + m % g.rpp) * g.lda]);
+#pragma unroll
+            for (int h = 0; h < 2; h++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[i][h * 4 + j] += cst * (int32_t)g.addvec[n0 + h * 64 + tx * 4 + j];
+        }
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             const int x = n0 + h * 64 + tx * 4;
@@ -133,7 +145,7 @@ __global__ void __maxnreg__(NREG) k_gf_gemm(const GemmArgs g)
             const int r = idx / (NT + 1), c = idx % (NT + 1), m = m0 + r;
             if (m >= g.mtotal) continue;
             const size_t ar = (size_t)(m / g.rpp) * g.a_slots + g.slot_lo + m % g.rpp, cr = (size_t)(m / g.rpp) * g.c_slots + g.slot_lo + m % g.rpp;
-            Cb[cr * g.ldc + g.c_off - (NT + 1) + c] = Ab[ar * g.lda + 256 + c];
+            Cb[cr * g.ldc + g.c_off - (NT + 1) + c] = Ab[ar * g.lda + g.tail_off + c];
         }
     }
 }

@@ -44,6 +44,7 @@ static void h_lagrange(std::vector<uint16_t> &out, const std::vector<int> &nodes
     }
 }
 
+enum { PH_OFFLINE = 1, PH_ONLINE = 2 };
 enum { KOSK_PH_KEYGEN = 0, KOSK_PH_EXPAND, KOSK_PH_SHARE1, KOSK_PH_COMMIT, KOSK_PH_FS1, KOSK_PH_EVAL, KOSK_PH_OPEN, KOSK_PH_SHARE2,
        KOSK_PH_VIEW, KOSK_PH_FS2, KOSK_PH_ASSEMBLE, KOSK_PH_VERIFY, KOSK_NPHASE };
 
@@ -67,6 +68,7 @@ struct kosk_b200_ctx {
     uint64_t launches = 0;
     // constant tables
     int16_t *d_St = nullptr;               // [GE_NPAD][YLD] centered share table S (zero padded)
+    int16_t *d_SU = nullptr;               // [GE_NPAD] centered U[x] = sum_{j<256} S[x][j]: share of the all-ones secret vector
     int16_t *d_R1 = nullptr, *d_R2 = nullptr; // verifier: centered recon tables [256][YLD], [256][VR2LD]
     u16 *d_inv = nullptr;                  // [3329] inverses
     int16_t *d_tab_commit = nullptr, *d_tab_view = nullptr;
@@ -98,16 +100,36 @@ static void prof_collect(kosk_b200_ctx *c)
     }
 }
 
+static void free_prove_bufs(ProveBufs &pb)
+{
+    void *lp[] = {pb.Y, pb.SH, pb.BG, pb.TCR, pb.VWR, pb.PW, pb.AH, pb.SHAT, pb.I, pb.REST};
+    for (void *p : lp) if (p) cudaFree(p);
+    pb = ProveBufs{};
+}
+static int alloc_prove_bufs(ProveBufs &pb, const Slots &sl, int k, size_t B)
+{
+#define PA(ptr, bytes, zero) do { if (cudaMalloc((void **)&(ptr), (bytes)) != cudaSuccess) { free_prove_bufs(pb); return -1; } if (zero) cudaMemset((ptr), 0, (bytes)); } while (0)
+    PA(pb.Y, B * sl.n2 * YLD * 2, 1);          // zero: row padding (terms 407..415) must stay 0
+    PA(pb.SH, B * sl.nslot * SLD * 2, 1);
+    PA(pb.BG, B * NP * 2 * BGH * 2, 0);
+    PA(pb.TCR, B * TREE_BYTES, 0); PA(pb.VWR, B * TREE_BYTES, 0);
+    PA(pb.PW, B * (MK + 2 * k) * sl.F * 2, 0);
+    PA(pb.AH, B * k * k * 256 * 2, 0); PA(pb.SHAT, B * k * 256 * 2, 0);
+    PA(pb.I, B * NT * 2, 0); PA(pb.REST, B * NR * 2, 0);
+#undef PA
+    return 0;
+}
+
 static void ctx_free(kosk_b200_ctx *c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    void *ptrs[] = {c->d_St, c->d_R1, c->d_R2, c->d_inv, c->d_tab_commit, c->d_tab_view};
+    void *ptrs[] = {c->d_St, c->d_SU, c->d_R1, c->d_R2, c->d_inv, c->d_tab_commit, c->d_tab_view};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (Lane &ln : c->lanes) {
-        void *lp[] = {ln.pb.Y, ln.pb.SH, ln.pb.BG, ln.pb.TCR, ln.pb.VWR, ln.pb.PW, ln.pb.AH, ln.pb.SHAT, ln.pb.I, ln.pb.REST,
-                      ln.d_seeds, ln.d_pk, ln.d_sk, ln.d_pi, ln.d_ok};
+        free_prove_bufs(ln.pb);
+        void *lp[] = {ln.d_seeds, ln.d_pk, ln.d_sk, ln.d_pi, ln.d_ok};
         for (void *p : lp) if (p) cudaFree(p);
         verify_free(ln.vb);
         for (cudaEvent_t e : ln.ev) cudaEventDestroy(e);
@@ -165,6 +187,9 @@ int kosk_b200_create_ex(kosk_b200_ctx **out, int k, int device, int max_chunk, i
         std::vector<int16_t> St((size_t)GE_NPAD * YLD, 0);
         for (int x = 0; x < NX; x++) for (int j = 0; j < D1; j++) St[(size_t)x * YLD + j] = (int16_t)gf_center(S[(size_t)x * D1 + j]);
         ALLOC(c->d_St, St.size() * 2); CU(cudaMemcpy(c->d_St, St.data(), St.size() * 2, cudaMemcpyHostToDevice));
+        std::vector<int16_t> SU(GE_NPAD, 0);
+        for (int x = 0; x < NX; x++) { uint32_t u = 0; for (int j = 0; j < NL; j++) u = (u + S[(size_t)x * D1 + j]) % Q; SU[x] = (int16_t)gf_center(u); }
+        ALLOC(c->d_SU, SU.size() * 2); CU(cudaMemcpy(c->d_SU, SU.data(), SU.size() * 2, cudaMemcpyHostToDevice));
         // verifier recon tables R1 (256 x 407 over nodes 256..662) and R2 (256 x 813 over nodes 256..1068)
         std::vector<int> n1(D1), n2(D2), tg(NL);
         for (int j = 0; j < D1; j++) n1[j] = 256 + j;
@@ -202,13 +227,7 @@ int kosk_b200_create_ex(kosk_b200_ctx **out, int k, int device, int max_chunk, i
     // ---- per-lane scratch ----
     c->lanes.resize(nlanes);
     for (Lane &ln : c->lanes) {
-        ALLOC(ln.pb.Y, B * sl.n2 * YLD * 2);       CU(cudaMemset(ln.pb.Y, 0, B * sl.n2 * YLD * 2));
-        ALLOC(ln.pb.SH, B * sl.nslot * SLD * 2);   CU(cudaMemset(ln.pb.SH, 0, B * sl.nslot * SLD * 2));
-        ALLOC(ln.pb.BG, B * NP * 2 * BGH * 2);
-        ALLOC(ln.pb.TCR, B * TREE_BYTES); ALLOC(ln.pb.VWR, B * TREE_BYTES);
-        ALLOC(ln.pb.PW, B * (MK + 2 * k) * sl.F * 2);
-        ALLOC(ln.pb.AH, B * k * k * 256 * 2); ALLOC(ln.pb.SHAT, B * k * 256 * 2);
-        ALLOC(ln.pb.I, B * NT * 2); ALLOC(ln.pb.REST, B * NR * 2);
+        if (alloc_prove_bufs(ln.pb, sl, k, B) != 0) { ctx_free(c); return fail(KOSK_E_NOMEM, "cudaMalloc failed for prover scratch"); }
         ALLOC(ln.d_seeds, B * 32); ALLOC(ln.d_pk, B * L.pk_bytes); ALLOC(ln.d_sk, B * L.sk_bytes); ALLOC(ln.d_pi, B * L.proof_bytes); ALLOC(ln.d_ok, B);
         if (verify_alloc(ln.vb, k, c->chunk) != 0) { ctx_free(c); return fail(KOSK_E_NOMEM, "cudaMalloc failed for verifier scratch"); }
         {
@@ -244,40 +263,66 @@ int kosk_b200_lanes(const kosk_b200_ctx *c) { return c ? (int)c->lanes.size() : 
 }  // extern "C"
 
 // ---- launch sequence for one chunk of B proofs on one lane ----
-static void launch_share_eval(kosk_b200_ctx *c, const u16 *Y, u16 *SH, int slot_lo, int rows, int y_slots, int sh_slots, int B, cudaStream_t st)
+static void launch_share_eval(kosk_b200_ctx *c, const u16 *Y, u16 *SH, int slot_lo, int rows, int y_slots, int sh_slots, int B, cudaStream_t st,
+                              bool const_secret = false)
 {
+    if (rows <= 0) return;
     GemmArgs g{};
     g.A = Y; g.Bt = c->d_St; g.C = SH; g.lda = YLD; g.ldb = YLD; g.ldc = SLD;
     g.mtotal = B * rows; g.ksteps = YLD / GE_BK; g.nvalid = NX; g.c_off = SOFF + NT + 1;
-    g.rpp = rows; g.slot_lo = slot_lo; g.a_slots = y_slots; g.c_slots = sh_slots; g.tail = 1;
+    g.rpp = rows; g.slot_lo = slot_lo; g.a_slots = y_slots; g.c_slots = sh_slots; g.tail = 1; g.tail_off = NL;
+    if (const_secret) {      // eta sharings: contraction over the 151 tail terms only, constant part added in the epilogue
+        g.A = Y + NL; g.Bt = c->d_St + NL; g.ksteps = (YLD - NL) / GE_BK; g.tail_off = 0;
+        g.addvec = c->d_SU; g.scale_src = Y;
+    }
     c->launches += (c->gemm_regs <= 96) ? gf_gemm_launch<8, 96>(g, GE_NPAD, 1, st) : gf_gemm_launch<8, 128>(g, GE_NPAD, 1, st);
+}
+// first share evaluation of a prove chunk over slots [lo, hi): the eta-constant sharings [seta0, s0) take the short path
+static void launch_share_eval_prove(kosk_b200_ctx *c, const ProveBufs &pb, int lo, int hi, int B, cudaStream_t st)
+{
+    const Slots &sl = c->sl;
+    const int a_lo = lo, a_hi = std::min(hi, sl.seta0), b_lo = std::max(lo, sl.seta0), b_hi = std::min(hi, sl.s0), c_lo = std::max(lo, sl.s0), c_hi = hi;
+    launch_share_eval(c, pb.Y, pb.SH, a_lo, a_hi - a_lo, sl.n2, sl.nslot, B, st);
+    launch_share_eval(c, pb.Y, pb.SH, b_lo, b_hi - b_lo, sl.n2, sl.nslot, B, st, true);
+    launch_share_eval(c, pb.Y, pb.SH, c_lo, c_hi - c_lo, sl.n2, sl.nslot, B, st);
 }
 
 template <int K>
-static int prove_chunk(kosk_b200_ctx *c, Lane &ln, int B, const u8 *d_seeds, u8 *d_pk, u8 *d_sk, u8 *d_pi)
+static int prove_chunk(kosk_b200_ctx *c, Lane &ln, const ProveBufs &bufs, int B, const u8 *d_seeds, u8 *d_pk, u8 *d_sk, u8 *d_pi, int phases)
 {
+    // phases: PH_OFFLINE = key-independent preprocessing (prepare_randomness + prepare_range_proof, mlwe_prover.cpp:4-59),
+    //         PH_ONLINE  = keygen + prove() + encode; both = kyber_verifiable_keygen
     const Slots &sl = c->sl;
     cudaStream_t st = ln.st;
-    ProveBufs pb = ln.pb;
+    ProveBufs pb = bufs;
     pb.seeds = d_seeds; pb.pk = d_pk; pb.sk = d_sk; pb.pi = d_pi; pb.B = B;
     constexpr int NCOMMIT = 2 * (K + MK + 2 * K + 1), ETA = (K == 2) ? 3 : 2;
     constexpr int NVIEW = 16 + NCOMMIT + 4 * K + 8 * ETA * K;
     const int ptiles = (NP + 127) / 128;
-    prof_mark(c, ln, KOSK_PH_KEYGEN);
-    k_keygen<K><<<B, 128, 0, st>>>(pb);
-    prof_mark(c, ln, KOSK_PH_EXPAND);
-    k_expand_f<K><<<(B * sl.F + 63) / 64, 64, 0, st>>>(pb);
-    k_ntt_f<K><<<dim3(sl.F, B), 128, 0, st>>>(pb);
-    k_tails<K><<<(B * (sl.n1 + K) + 63) / 64, 64, 0, st>>>(pb);
+    const bool off = phases & PH_OFFLINE, on = phases & PH_ONLINE;
+    if (on) {
+        prof_mark(c, ln, KOSK_PH_KEYGEN);
+        k_keygen<K><<<B, 128, 0, st>>>(pb); c->launches++;
+    }
+    if (off) {
+        prof_mark(c, ln, KOSK_PH_EXPAND);
+        k_expand_f<K><<<(B * sl.F + 63) / 64, 64, 0, st>>>(pb);
+        k_ntt_f<K><<<dim3(sl.F, B), 128, 0, st>>>(pb);
+        k_tails<K><<<(B * (sl.n1 + K) + 63) / 64, 64, 0, st>>>(pb);
+        c->launches += 3;
+    }
+    // first share evaluation: slots [0, s0) (f, NTT_f, eta constants) are key-independent, [s0, n1) (s, e, z_j) are not
+    const int lo = off ? 0 : sl.s0, hi = on ? sl.n1 : sl.s0;
     if (ln.st_lo) {          // long FMA-pipe launch on the low-priority stream: other lanes' Keccak / FS kernels get SM slots first
         CU(cudaEventRecord(ln.ev_a, st)); CU(cudaStreamWaitEvent(ln.st_lo, ln.ev_a, 0));
         prof_mark(c, ln, KOSK_PH_SHARE1, ln.st_lo);
-        launch_share_eval(c, pb.Y, pb.SH, 0, sl.n1, sl.n2, sl.nslot, B, ln.st_lo);
+        launch_share_eval_prove(c, pb, lo, hi, B, ln.st_lo);
         CU(cudaEventRecord(ln.ev_b, ln.st_lo)); CU(cudaStreamWaitEvent(st, ln.ev_b, 0));
     } else {
         prof_mark(c, ln, KOSK_PH_SHARE1);
-        launch_share_eval(c, pb.Y, pb.SH, 0, sl.n1, sl.n2, sl.nslot, B, st);
+        launch_share_eval_prove(c, pb, lo, hi, B, st);
     }
+    if (!on) { prof_mark(c, ln, -1); CU(cudaGetLastError()); return KOSK_OK; }
     prof_mark(c, ln, KOSK_PH_COMMIT);
     HashSrc hc{pb.SH, (long long)sl.nslot * SLD, 1, SLD, SOFF, c->d_tab_commit, nullptr, 0};
     k_hash_records<NCOMMIT><<<dim3(ptiles, B), 128, 0, st>>>(hc, pb.TCR, pb.SH, sl.nslot, sl.TC0);
@@ -298,23 +343,23 @@ static int prove_chunk(kosk_b200_ctx *c, Lane &ln, int B, const u8 *d_seeds, u8 
     prof_mark(c, ln, KOSK_PH_ASSEMBLE);
     k_assemble<K><<<dim3((NT + 31) / 32 + (NR + 31) / 32, B), 128, 0, st>>>(pb);
     prof_mark(c, ln, -1);
-    c->launches += 12;
+    c->launches += 8;
     CU(cudaGetLastError());
     return KOSK_OK;
 }
 
-static int prove_chunk_k(kosk_b200_ctx *c, Lane &ln, int B, const u8 *s, u8 *pk, u8 *sk, u8 *pi)
+static int prove_chunk_k(kosk_b200_ctx *c, Lane &ln, const ProveBufs &bufs, int B, const u8 *s, u8 *pk, u8 *sk, u8 *pi, int phases)
 {
     switch (c->k) {
-    case 2: return prove_chunk<2>(c, ln, B, s, pk, sk, pi);
-    case 3: return prove_chunk<3>(c, ln, B, s, pk, sk, pi);
-    default: return prove_chunk<4>(c, ln, B, s, pk, sk, pi);
+    case 2: return prove_chunk<2>(c, ln, bufs, B, s, pk, sk, pi, phases);
+    case 3: return prove_chunk<3>(c, ln, bufs, B, s, pk, sk, pi, phases);
+    default: return prove_chunk<4>(c, ln, bufs, B, s, pk, sk, pi, phases);
     }
 }
 
 static int verify_chunk_lane(kosk_b200_ctx *c, Lane &ln, int B, const u8 *d_pi, const u8 *d_pk, u8 *d_ok)
 {
-    VerifyTables vt{c->d_St, c->d_R1, c->d_R2, c->d_inv};
+    VerifyTables vt{c->d_St, c->d_R1, c->d_R2, c->d_inv, c->d_SU};
     prof_mark(c, ln, KOSK_PH_VERIFY);
     int nl = verify_chunk(c->k, ln.vb, vt, B, d_pi, d_pk, d_ok, ln.st);
     prof_mark(c, ln, -1);
@@ -395,7 +440,7 @@ int kosk_b200_prove_batch_device(kosk_b200_ctx *c, size_t n, const uint8_t *d_se
     size_t i = 0;
     for (size_t o = 0; o < n; o += sub, i++) {
         const int B = (int)std::min<size_t>(sub, n - o);
-        rc = prove_chunk_k(c, c->lanes[i % c->lanes.size()], B, d_seeds + 32 * o, d_pk + L.pk_bytes * o, d_sk + L.sk_bytes * o, d_pi + L.proof_bytes * o);
+        { Lane &ln = c->lanes[i % c->lanes.size()]; rc = prove_chunk_k(c, ln, ln.pb, B, d_seeds + 32 * o, d_pk + L.pk_bytes * o, d_sk + L.sk_bytes * o, d_pi + L.proof_bytes * o, PH_OFFLINE | PH_ONLINE); }
         if (rc) return rc;
     }
     return lanes_join(c, (cudaStream_t)stream);
@@ -412,7 +457,7 @@ int kosk_b200_prove_batch(kosk_b200_ctx *c, size_t n, const uint8_t *seeds, uint
         const int B = (int)std::min<size_t>(sub, n - o);
         Lane &ln = c->lanes[i % c->lanes.size()];
         CU(cudaMemcpyAsync(ln.d_seeds, seeds + 32 * o, 32 * (size_t)B, cudaMemcpyHostToDevice, ln.st));
-        int rc = prove_chunk_k(c, ln, B, ln.d_seeds, ln.d_pk, ln.d_sk, ln.d_pi);
+        int rc = prove_chunk_k(c, ln, ln.pb, B, ln.d_seeds, ln.d_pk, ln.d_sk, ln.d_pi, PH_OFFLINE | PH_ONLINE);
         if (rc) return rc;
         CU(cudaMemcpyAsync(pk + L.pk_bytes * o, ln.d_pk, L.pk_bytes * (size_t)B, cudaMemcpyDeviceToHost, ln.st));
         CU(cudaMemcpyAsync(sk + L.sk_bytes * o, ln.d_sk, L.sk_bytes * (size_t)B, cudaMemcpyDeviceToHost, ln.st));
@@ -469,6 +514,61 @@ int kosk_b200_kosk_verify(kosk_b200_ctx *c, const uint8_t *pi, const uint8_t *pk
     uint8_t ok = 0;
     int rc = kosk_b200_verify_batch(c, 1, pi, pk, &ok);
     return rc ? rc : (int)ok;
+}
+
+// ---- offline / online split ----
+struct kosk_b200_pool {
+    kosk_b200_ctx *ctx; size_t n;
+    ProveBufs pb{};
+    u8 *d_seeds = nullptr, *d_pk = nullptr, *d_sk = nullptr, *d_pi = nullptr;
+};
+
+void kosk_b200_pool_destroy(kosk_b200_pool *p)
+{
+    if (!p) return;
+    cudaSetDevice(p->ctx->device);
+    cudaStreamSynchronize(p->ctx->lanes[0].st);
+    free_prove_bufs(p->pb);
+    void *lp[] = {p->d_seeds, p->d_pk, p->d_sk, p->d_pi};
+    for (void *q : lp) if (q) cudaFree(q);
+    delete p;
+}
+
+int kosk_b200_pool_create(kosk_b200_ctx *c, size_t n, const uint8_t *seeds, kosk_b200_pool **out)
+{
+    if (!c || !seeds || !out || n == 0 || n > 16384) return fail(KOSK_E_ARG, "bad argument (1 <= n <= 16384)");
+    CU(cudaSetDevice(c->device));
+    kosk_b200_pool *p = new kosk_b200_pool; p->ctx = c; p->n = n;
+    if (alloc_prove_bufs(p->pb, c->sl, c->k, n) != 0 || cudaMalloc((void **)&p->d_seeds, 32 * n) != cudaSuccess) {
+        kosk_b200_pool_destroy(p); return fail(KOSK_E_NOMEM, "cudaMalloc failed for the preprocessing pool");
+    }
+    Lane &ln = c->lanes[0];
+    CU(cudaMemcpyAsync(p->d_seeds, seeds, 32 * n, cudaMemcpyHostToDevice, ln.st));
+    int rc = prove_chunk_k(c, ln, p->pb, (int)n, p->d_seeds, nullptr, nullptr, nullptr, PH_OFFLINE);
+    if (rc) { kosk_b200_pool_destroy(p); return rc; }
+    CU(cudaStreamSynchronize(ln.st));
+    *out = p;
+    return KOSK_OK;
+}
+
+int kosk_b200_pool_prove(kosk_b200_pool *p, uint8_t *pk, uint8_t *sk, uint8_t *pi)
+{
+    if (!p || !pk || !sk || !pi) return fail(KOSK_E_ARG, "null argument");
+    kosk_b200_ctx *c = p->ctx;
+    CU(cudaSetDevice(c->device));
+    const Layout &L = c->L; const size_t n = p->n;
+    if (!p->d_pi) {
+        if (cudaMalloc((void **)&p->d_pk, L.pk_bytes * n) != cudaSuccess || cudaMalloc((void **)&p->d_sk, L.sk_bytes * n) != cudaSuccess ||
+            cudaMalloc((void **)&p->d_pi, L.proof_bytes * n) != cudaSuccess) return fail(KOSK_E_NOMEM, "cudaMalloc failed for pool outputs");
+    }
+    Lane &ln = c->lanes[0];
+    int rc = prove_chunk_k(c, ln, p->pb, (int)n, p->d_seeds, p->d_pk, p->d_sk, p->d_pi, PH_ONLINE);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(pk, p->d_pk, L.pk_bytes * n, cudaMemcpyDeviceToHost, ln.st));
+    CU(cudaMemcpyAsync(sk, p->d_sk, L.sk_bytes * n, cudaMemcpyDeviceToHost, ln.st));
+    CU(cudaMemcpyAsync(pi, p->d_pi, L.proof_bytes * n, cudaMemcpyDeviceToHost, ln.st));
+    CU(cudaStreamSynchronize(ln.st));
+    return KOSK_OK;
 }
 
 int kosk_b200_share_eval_device(kosk_b200_ctx *c, size_t n, const uint16_t *d_y, uint16_t *d_planes, void *stream)

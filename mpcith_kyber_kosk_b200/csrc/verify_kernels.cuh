@@ -17,7 +17,7 @@ constexpr int OPLD = 160;         // opened-party values: beta[70] gamma[70] r[2
 enum VFlag { VF_I = 1, VF_BG = 2, VF_SR = 4, VF_NTT = 8, VF_ASR = 16, VF_T = 32, VF_TREL = 64, VF_ETA = 128,
              VF_SUBETA = 256, VF_UZ = 512, VF_U2D = 1024, VF_FS2 = 2048, VF_STRICT = 4096 };
 
-struct VerifyTables { const int16_t *St, *R1, *R2; const u16 *inv; };
+struct VerifyTables { const int16_t *St, *R1, *R2; const u16 *inv; const int16_t *SU; };
 
 struct VerifyBufs {
     int *flags = nullptr;
@@ -480,10 +480,18 @@ static int verify_chunk_t(VerifyBufs &vb, const VerifyTables &vt, int B, const u
         nl += gf_gemm_launch<4>(h, 256, nb, st);
     }
     kv_open<K><<<B, 128, 0, st>>>(vb); nl++;
-    // regenerate every sharing at all 1454 parties: YV x S
-    g = GemmArgs{}; g.A = vb.YV; g.Bt = vt.St; g.C = vb.VSH; g.lda = YLD; g.ldb = YLD; g.ldc = SLD;
-    g.mtotal = B * d.nyrows; g.ksteps = YLD / GE_BK; g.nvalid = NX; g.c_off = SOFF + NT + 1; g.rpp = g.mtotal; g.tail = 1;
-    nl += gf_gemm_launch<8>(g, GE_NPAD, 1, st);
+    // regenerate every sharing at all 1454 parties: YV x S.  Row groups per proof: [0,3K) s+r, e+r, t | [3K, n1rows) the eta
+    // sharings, whose 256 secrets were just checked to be one constant (short path: tail terms only) | [n1rows, nyrows)
+    {
+        const int grp_lo[3] = {0, 3 * K, d.n1rows}, grp_hi[3] = {3 * K, d.n1rows, d.nyrows};
+        for (int gi = 0; gi < 3; gi++) {
+            g = GemmArgs{}; g.A = vb.YV; g.Bt = vt.St; g.C = vb.VSH; g.lda = YLD; g.ldb = YLD; g.ldc = SLD;
+            g.rpp = grp_hi[gi] - grp_lo[gi]; g.slot_lo = grp_lo[gi]; g.a_slots = d.nyrows; g.c_slots = d.nyrows;
+            g.mtotal = B * g.rpp; g.ksteps = YLD / GE_BK; g.nvalid = NX; g.c_off = SOFF + NT + 1; g.tail = 1; g.tail_off = NL;
+            if (gi == 1) { g.A = vb.YV + NL; g.Bt = vt.St + NL; g.ksteps = (YLD - NL) / GE_BK; g.tail_off = 0; g.addvec = vt.SU; g.scale_src = vb.YV; }
+            nl += gf_gemm_launch<8>(g, GE_NPAD, 1, st);
+        }
+    }
     kv_check_parties<K><<<dim3(ptiles, B), 128, 0, st>>>(vb, d_pi); nl++;
     g = GemmArgs{}; g.A = vb.U2; g.Bt = vt.R2; g.C = vb.UR; g.lda = VR2LD; g.ldb = VR2LD; g.ldc = 256;
     g.mtotal = B * d.n2rows; g.ksteps = VR2LD / GE_BK; g.nvalid = 256; g.rpp = g.mtotal;

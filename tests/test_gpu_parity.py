@@ -252,3 +252,20 @@ def test_strict_verifier_is_a_superset_of_checks(ctxs):
         ctx.set_strict(False)
     assert strict["honest"] and strict["o_beta:last"]           # beta's unread tail is outside the hardened checks (documented)
     assert not strict["o_t:last"] and not strict["o_seta:last"] and not strict["o_eeta:last"] and not strict["t:+q"]
+
+
+@pytest.mark.parametrize("k", [2, 3])
+def test_offline_online_split_matches_one_shot(ctxs, k):
+    """preprocessing pool + online-only prove gives the same bytes as kyber_verifiable_keygen."""
+    ctx = ctxs(k, 16, 1)
+    seeds = seeds_for_range(31337, 0, 5)
+    pool = ctx.pool_create(seeds)
+    pk, sk, pi = pool.prove()
+    pk2, sk2, pi2 = pool.prove()                       # the online phase is a pure function of (pool, seeds)
+    pool.close()
+    a = ctx.prove_batch(seeds)
+    for x, y, z in zip(a, (pk, sk, pi), (pk2, sk2, pi2)):
+        assert (x == y).all() and (x == z).all()
+    opk, osk, opi = O.oracle_prove(k, seeds[3])
+    assert (pi[3] == opi).all() and (pk[3] == opk).all() and (sk[3] == osk).all()
+    assert ctx.verify_batch(pi, pk).all()

@@ -95,5 +95,23 @@ out["config5_keccak_commit"] = {
 out["int_peaks"] = peaks
 print(json.dumps({"config5_keccak": out["config5_keccak_commit"]}), flush=True)
 ctx.close()
+# ---- offline / online split (Kyber512, 1024 proofs, host API) ----
+ctx = KoskContext(2, 0, 1024, 1)
+seeds = seeds_for_range(77, 0, 1024)
+pool = ctx.pool_create(seeds); pool.close()
+t0 = time.perf_counter(); pool = ctx.pool_create(seeds); t_off = time.perf_counter() - t0
+ctx.set_profiling(True); ctx.phase_times(reset=True)
+t0 = time.perf_counter(); pk, sk, pi = pool.prove(); t_on = time.perf_counter() - t0
+ph = ctx.phase_times(); ctx.set_profiling(False)
+on_dev_ms = sum(v[0] for v in ph.values())
+p1 = ctx.pool_create(seeds[:1]); p1.prove()
+ts = []
+for _ in range(10):
+    t0 = time.perf_counter(); p1.prove(); ts.append(time.perf_counter() - t0)
+out["f1_offline_online_split"] = {"batch": 1024, "offline_s_incl_alloc": round(t_off, 4), "online_wall_s_incl_d2h": round(t_on, 4),
+                                  "online_device_ms": round(on_dev_ms, 3), "online_proofs_per_s_device": round(1024 / on_dev_ms * 1e3),
+                                  "online_single_proof_latency_ms": round(1e3 * float(np.median(ts)), 3)}
+print(json.dumps({"f1": out["f1_offline_online_split"]}), flush=True)
+pool.close(); p1.close(); ctx.close()
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open("gpurun_out/configs.json", "w"), indent=1)
