@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--e2e-lanes", type=int, default=8, help="lanes of the host-buffer (e2e) run: sub-batches whose D2H copies overlap compute")
     ap.add_argument("--cpu-sample", type=int, default=8, help="proofs of the bounded single-core CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-tensor-probe", action="store_true", help="skip the short measurement of the opt-in tensor-core path")
     ap.add_argument("--verify", action="store_true", help="also time kyber_kosk_verify on the produced proofs")
     return ap.parse_args()
 
@@ -245,9 +246,33 @@ def run_b200(args):
         assert bool(d_ok.all())
         verify_stats = {"verifies_per_s": B * max(1, args.steps // 2) / (v0.elapsed_time(v1) * 1e-3), "batch": B}
 
+    tensor_stats = None
+    if rank == 0 and not args.no_tensor_probe:
+        # opt-in experimental path (NOT the headline): share evaluation on int8 tensor cores, same bytes
+        ctx_t = KoskContext(k, local, chunk, 1, True)
+        for s in range(2):
+            ctx_t.prove_batch_device(B, d_seeds[s].data_ptr(), d_pk.data_ptr(), d_sk.data_ptr(), d_pi.data_ptr(), stream)
+        torch.cuda.synchronize()
+        ctx_t.set_profiling(True); ctx_t.phase_times(reset=True)
+        t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0e.record()
+        for s in range(3):
+            ctx_t.prove_batch_device(B, d_seeds[s].data_ptr(), d_pk.data_ptr(), d_sk.data_ptr(), d_pi.data_ptr(), stream)
+        t1e.record(); torch.cuda.synchronize()
+        pht = ctx_t.phase_times()
+        pi_t = d_pi[:npi].cpu().numpy().copy()
+        tensor_stats = {"proofs_per_s_one_gpu": B * 3 / (t0e.elapsed_time(t1e) * 1e-3), "ms_per_step": t0e.elapsed_time(t1e) / 3,
+                        "share1_ms_per_step": pht["share1"][0] / 3, "peak_int8_mac_per_s_mma_sync": peaks["imma_int8_mac"],
+                        "note": "KOSK_F_TENSOR: limb-split int8 mma.sync share evaluation; experimental, not the plan of record"}
+        ctx_t.close()
+
     if rank == 0:
         import oracle_lib as O
         kind, prove, verify = cpu_oracle()
+        if tensor_stats is not None:
+            opk_t, osk_t, opi_t = prove(k, bytes(d_seeds[2][0].cpu().numpy()))
+            assert (opi_t == pi_t).all(), "tensor-path proof differs from the CPU oracle"
+            tensor_stats["bit_exact_vs_oracle"] = True
         opk, osk, opi = prove(k, bytes(h_seeds[args.steps - 1][0].numpy()))
         assert (opi == pi_np[0]).all() and (opk == pk_np[0]).all(), "measured proof differs from the CPU oracle"
         peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -288,6 +313,8 @@ def run_b200(args):
         }
         if verify_stats:
             out["verify"] = verify_stats
+        if tensor_stats:
+            out["experimental_tensor_path"] = tensor_stats
         if not args.no_cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_baseline(k, args.cpu_sample)
         print(json.dumps(out))

@@ -43,7 +43,10 @@ const char *kosk_b200_version(void);
 int kosk_b200_create(kosk_b200_ctx **ctx, int kyber_k, int device, int max_chunk);
 /* Same, with the number of pipeline lanes made explicit (0 = default 2).  A batch is split into sub-batches of at
  * most max_chunk proofs that run on `lanes` CUDA streams, each with its own scratch, so that sub-batches overlap. */
-int kosk_b200_create_ex(kosk_b200_ctx **ctx, int kyber_k, int device, int max_chunk, int lanes);
+int kosk_b200_create_ex(kosk_b200_ctx **ctx, int kyber_k, int device, int max_chunk, int lanes, int flags);
+/* flags.  KOSK_F_TENSOR (EXPERIMENTAL, off by default; also KOSK_B200_TENSOR=1 with kosk_b200_create): run the prover's
+ * share evaluation on the int8 tensor-core path (limb-split residues, mma.sync) instead of the INT32 pipe.  Same bytes. */
+enum { KOSK_F_TENSOR = 1 };
 int kosk_b200_lanes(const kosk_b200_ctx *ctx);
 void kosk_b200_destroy(kosk_b200_ctx *ctx);
 
@@ -99,8 +102,8 @@ int kosk_b200_sync(kosk_b200_ctx *ctx);
 /* Measurement support.  With profiling on, every prove chunk records CUDA events on its launching stream at the
  * phase boundaries; kosk_b200_phase_times() synchronises and returns accumulated milliseconds and call counts for
  * the KOSK_PH_* phases (order: keygen, expand, share1, commit, fs1, eval, open, share2, view, fs2, assemble, verify).
- * kosk_b200_int_peak() runs issue-rate microbenchmarks and returns thread-level ops/s for IMAD, LOP3 and SHF
- * (the SM integer-pipe roofline denominators). */
+ * kosk_b200_int_peak() runs issue-rate microbenchmarks and returns, in ops_per_s[4], thread-level ops/s for IMAD, LOP3
+ * and SHF (the SM integer-pipe roofline denominators) and int8 MAC/s of warp-level mma.sync (for the opt-in tensor path). */
 #define KOSK_B200_NPHASE 12
 int kosk_b200_set_profiling(kosk_b200_ctx *ctx, int on);
 int kosk_b200_phase_times(kosk_b200_ctx *ctx, double *ms, uint64_t *calls, int n, int reset);

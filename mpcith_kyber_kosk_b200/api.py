@@ -43,7 +43,7 @@ def load_library(path=None):
     lib.kosk_b200_last_error.restype = ctypes.c_char_p
     lib.kosk_b200_version.restype = ctypes.c_char_p
     lib.kosk_b200_create.argtypes = [ctypes.POINTER(vp), i32, i32, i32]
-    lib.kosk_b200_create_ex.argtypes = [ctypes.POINTER(vp), i32, i32, i32, i32]
+    lib.kosk_b200_create_ex.argtypes = [ctypes.POINTER(vp), i32, i32, i32, i32, i32]
     lib.kosk_b200_lanes.argtypes = [vp]
     lib.kosk_b200_destroy.argtypes = [vp]
     lib.kosk_b200_destroy.restype = None
@@ -93,11 +93,11 @@ def _ptr(a):
 class KoskContext:
     """One (device, KYBER_K) instance of the B200 KOSK core."""
 
-    def __init__(self, kyber_k=2, device=0, max_chunk=0, lanes=0):
+    def __init__(self, kyber_k=2, device=0, max_chunk=0, lanes=0, tensor=False):
         self.lib = load_library()
         self.k = kyber_k
         self._h = ctypes.c_void_p()
-        rc = self.lib.kosk_b200_create_ex(ctypes.byref(self._h), kyber_k, device, max_chunk, lanes)
+        rc = self.lib.kosk_b200_create_ex(ctypes.byref(self._h), kyber_k, device, max_chunk, lanes, 1 if tensor else 0)
         if rc != 0:
             raise KoskError(f"kosk_b200_create failed ({rc}): {self.lib.kosk_b200_last_error().decode()}")
         self.pk_bytes, self.sk_bytes, self.proof_bytes = pk_bytes(kyber_k), sk_bytes(kyber_k), proof_bytes(kyber_k)
@@ -214,9 +214,9 @@ class KoskContext:
         return {n: (float(m), int(c)) for n, m, c in zip(self.PHASES, ms, calls)}
 
     def int_peak(self):
-        out = np.zeros(3, np.float64)
+        out = np.zeros(4, np.float64)
         self._check(self.lib.kosk_b200_int_peak(self._h, _ptr(out)), "int_peak")
-        return {"imad": float(out[0]), "lop3": float(out[1]), "shf": float(out[2])}
+        return {"imad": float(out[0]), "lop3": float(out[1]), "shf": float(out[2]), "imma_int8_mac": float(out[3])}
 
     def sync(self):
         self._check(self.lib.kosk_b200_sync(self._h), "sync")

@@ -4,6 +4,7 @@
 #include "../../include/kosk_b200.h"
 #include "prove_kernels.cuh"
 #include "verify_kernels.cuh"
+#include "gf_gemm_imma.cuh"
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstdlib>
@@ -63,11 +64,13 @@ struct Lane {
 };
 
 struct kosk_b200_ctx {
-    int k = 0, device = 0, chunk = 0, gemm_regs = 128, use_prio = 2;
+    int k = 0, device = 0, chunk = 0, gemm_regs = 128, use_prio = 2, use_tensor = 0;
     Slots sl; Layout L;
     uint64_t launches = 0;
     // constant tables
     int16_t *d_St = nullptr;               // [GE_NPAD][YLD] centered share table S (zero padded)
+    int8_t *tmpL0 = nullptr, *tmpL1 = nullptr; size_t tmp_rows = 0;
+    int8_t *d_St0 = nullptr, *d_St1 = nullptr;   // experimental tensor path: 7-bit limb planes of S, [GE_NPAD][YLD] int8
     int16_t *d_SU = nullptr;               // [GE_NPAD] centered U[x] = sum_{j<256} S[x][j]: share of the all-ones secret vector
     int16_t *d_R1 = nullptr, *d_R2 = nullptr; // verifier: centered recon tables [256][YLD], [256][VR2LD]
     u16 *d_inv = nullptr;                  // [3329] inverses
@@ -102,11 +105,11 @@ static void prof_collect(kosk_b200_ctx *c)
 
 static void free_prove_bufs(ProveBufs &pb)
 {
-    void *lp[] = {pb.Y, pb.SH, pb.BG, pb.TCR, pb.VWR, pb.PW, pb.AH, pb.SHAT, pb.I, pb.REST};
+    void *lp[] = {pb.Y, pb.SH, pb.BG, pb.TCR, pb.VWR, pb.PW, pb.AH, pb.SHAT, pb.I, pb.REST, pb.YL0, pb.YL1};
     for (void *p : lp) if (p) cudaFree(p);
     pb = ProveBufs{};
 }
-static int alloc_prove_bufs(ProveBufs &pb, const Slots &sl, int k, size_t B)
+static int alloc_prove_bufs(ProveBufs &pb, const Slots &sl, int k, size_t B, bool tensor)
 {
 #define PA(ptr, bytes, zero) do { if (cudaMalloc((void **)&(ptr), (bytes)) != cudaSuccess) { free_prove_bufs(pb); return -1; } if (zero) cudaMemset((ptr), 0, (bytes)); } while (0)
     PA(pb.Y, B * sl.n2 * YLD * 2, 1);          // zero: row padding (terms 407..415) must stay 0
@@ -116,6 +119,7 @@ static int alloc_prove_bufs(ProveBufs &pb, const Slots &sl, int k, size_t B)
     PA(pb.PW, B * (MK + 2 * k) * sl.F * 2, 0);
     PA(pb.AH, B * k * k * 256 * 2, 0); PA(pb.SHAT, B * k * 256 * 2, 0);
     PA(pb.I, B * NT * 2, 0); PA(pb.REST, B * NR * 2, 0);
+    if (tensor) { PA(pb.YL0, B * sl.n2 * YLD, 1); PA(pb.YL1, B * sl.n2 * YLD, 1); }
 #undef PA
     return 0;
 }
@@ -125,7 +129,7 @@ static void ctx_free(kosk_b200_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    void *ptrs[] = {c->d_St, c->d_SU, c->d_R1, c->d_R2, c->d_inv, c->d_tab_commit, c->d_tab_view};
+    void *ptrs[] = {c->tmpL0, c->tmpL1, c->d_St, c->d_St0, c->d_St1, c->d_SU, c->d_R1, c->d_R2, c->d_inv, c->d_tab_commit, c->d_tab_view};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (Lane &ln : c->lanes) {
         free_prove_bufs(ln.pb);
@@ -154,10 +158,11 @@ const char *kosk_b200_version(void) { return "kosk_b200 0.1 (sm_100a)"; }
 int kosk_b200_create(kosk_b200_ctx **out, int k, int device, int max_chunk)
 {
     const char *e = getenv("KOSK_B200_LANES");
-    return kosk_b200_create_ex(out, k, device, max_chunk, e ? atoi(e) : 0);
+    const char *t = getenv("KOSK_B200_TENSOR");
+    return kosk_b200_create_ex(out, k, device, max_chunk, e ? atoi(e) : 0, (t && atoi(t)) ? KOSK_F_TENSOR : 0);
 }
 
-int kosk_b200_create_ex(kosk_b200_ctx **out, int k, int device, int max_chunk, int nlanes)
+int kosk_b200_create_ex(kosk_b200_ctx **out, int k, int device, int max_chunk, int nlanes, int flags)
 {
     if (!out || k < 2 || k > 4) return fail(KOSK_E_ARG, "kyber_k must be 2, 3 or 4");
     int ndev = 0;
@@ -171,6 +176,7 @@ int kosk_b200_create_ex(kosk_b200_ctx **out, int k, int device, int max_chunk, i
     if (nlanes <= 0) nlanes = 2;
     if (nlanes > 8) nlanes = 8;
     { const char *e = getenv("KOSK_B200_GEMM_REGS"); if (e) c->gemm_regs = atoi(e) <= 96 ? 96 : 128; }
+    c->use_tensor = (flags & KOSK_F_TENSOR) ? 1 : 0;
     { const char *e = getenv("KOSK_B200_PRIO"); if (e) c->use_prio = atoi(e); }
     const Slots &sl = c->sl; const Layout &L = c->L;
     const size_t B = (size_t)c->chunk;
@@ -187,6 +193,12 @@ int kosk_b200_create_ex(kosk_b200_ctx **out, int k, int device, int max_chunk, i
         std::vector<int16_t> St((size_t)GE_NPAD * YLD, 0);
         for (int x = 0; x < NX; x++) for (int j = 0; j < D1; j++) St[(size_t)x * YLD + j] = (int16_t)gf_center(S[(size_t)x * D1 + j]);
         ALLOC(c->d_St, St.size() * 2); CU(cudaMemcpy(c->d_St, St.data(), St.size() * 2, cudaMemcpyHostToDevice));
+        {   // limb planes for the opt-in tensor path: s = 128*s1 + s0, s0 in [-64, 63]
+            std::vector<int8_t> L0(St.size()), L1(St.size());
+            for (size_t i = 0; i < St.size(); i++) { const int v = St[i], v0 = ((v + 64) & 127) - 64; L0[i] = (int8_t)v0; L1[i] = (int8_t)((v - v0) >> 7); }
+            ALLOC(c->d_St0, L0.size()); CU(cudaMemcpy(c->d_St0, L0.data(), L0.size(), cudaMemcpyHostToDevice));
+            ALLOC(c->d_St1, L1.size()); CU(cudaMemcpy(c->d_St1, L1.data(), L1.size(), cudaMemcpyHostToDevice));
+        }
         std::vector<int16_t> SU(GE_NPAD, 0);
         for (int x = 0; x < NX; x++) { uint32_t u = 0; for (int j = 0; j < NL; j++) u = (u + S[(size_t)x * D1 + j]) % Q; SU[x] = (int16_t)gf_center(u); }
         ALLOC(c->d_SU, SU.size() * 2); CU(cudaMemcpy(c->d_SU, SU.data(), SU.size() * 2, cudaMemcpyHostToDevice));
@@ -227,7 +239,7 @@ int kosk_b200_create_ex(kosk_b200_ctx **out, int k, int device, int max_chunk, i
     // ---- per-lane scratch ----
     c->lanes.resize(nlanes);
     for (Lane &ln : c->lanes) {
-        if (alloc_prove_bufs(ln.pb, sl, k, B) != 0) { ctx_free(c); return fail(KOSK_E_NOMEM, "cudaMalloc failed for prover scratch"); }
+        if (alloc_prove_bufs(ln.pb, sl, k, B, c->use_tensor != 0) != 0) { ctx_free(c); return fail(KOSK_E_NOMEM, "cudaMalloc failed for prover scratch"); }
         ALLOC(ln.d_seeds, B * 32); ALLOC(ln.d_pk, B * L.pk_bytes); ALLOC(ln.d_sk, B * L.sk_bytes); ALLOC(ln.d_pi, B * L.proof_bytes); ALLOC(ln.d_ok, B);
         if (verify_alloc(ln.vb, k, c->chunk) != 0) { ctx_free(c); return fail(KOSK_E_NOMEM, "cudaMalloc failed for verifier scratch"); }
         {
@@ -264,16 +276,24 @@ int kosk_b200_lanes(const kosk_b200_ctx *c) { return c ? (int)c->lanes.size() : 
 
 // ---- launch sequence for one chunk of B proofs on one lane ----
 static void launch_share_eval(kosk_b200_ctx *c, const u16 *Y, u16 *SH, int slot_lo, int rows, int y_slots, int sh_slots, int B, cudaStream_t st,
-                              bool const_secret = false)
+                              bool const_secret = false, int8_t *YL0 = nullptr, int8_t *YL1 = nullptr)
 {
     if (rows <= 0) return;
     GemmArgs g{};
     g.A = Y; g.Bt = c->d_St; g.C = SH; g.lda = YLD; g.ldb = YLD; g.ldc = SLD;
     g.mtotal = B * rows; g.ksteps = YLD / GE_BK; g.nvalid = NX; g.c_off = SOFF + NT + 1;
     g.rpp = rows; g.slot_lo = slot_lo; g.a_slots = y_slots; g.c_slots = sh_slots; g.tail = 1; g.tail_off = NL;
+    const int koff = const_secret ? NL : 0;
     if (const_secret) {      // eta sharings: contraction over the 151 tail terms only, constant part added in the epilogue
         g.A = Y + NL; g.Bt = c->d_St + NL; g.ksteps = (YLD - NL) / GE_BK; g.tail_off = 0;
         g.addvec = c->d_SU; g.scale_src = Y;
+    }
+    if (c->use_tensor && YL0) {      // experimental int8 tensor-core path: split the rows into limb planes, then IMMA
+        const size_t nchunks = (size_t)B * rows * (YLD / 8);
+        k_limb_split<<<(unsigned)((nchunks + 255) / 256), 256, 0, st>>>(Y, YL0, YL1, rows, slot_lo, y_slots, YLD, nchunks);
+        ImmaTables tb{c->d_St0 + koff, c->d_St1 + koff, YL0 + koff, YL1 + koff};
+        c->launches += 1 + gf_gemm_imma_launch(g, tb, NX, st);
+        return;
     }
     c->launches += (c->gemm_regs <= 96) ? gf_gemm_launch<8, 96>(g, GE_NPAD, 1, st) : gf_gemm_launch<8, 128>(g, GE_NPAD, 1, st);
 }
@@ -282,9 +302,9 @@ static void launch_share_eval_prove(kosk_b200_ctx *c, const ProveBufs &pb, int l
 {
     const Slots &sl = c->sl;
     const int a_lo = lo, a_hi = std::min(hi, sl.seta0), b_lo = std::max(lo, sl.seta0), b_hi = std::min(hi, sl.s0), c_lo = std::max(lo, sl.s0), c_hi = hi;
-    launch_share_eval(c, pb.Y, pb.SH, a_lo, a_hi - a_lo, sl.n2, sl.nslot, B, st);
-    launch_share_eval(c, pb.Y, pb.SH, b_lo, b_hi - b_lo, sl.n2, sl.nslot, B, st, true);
-    launch_share_eval(c, pb.Y, pb.SH, c_lo, c_hi - c_lo, sl.n2, sl.nslot, B, st);
+    launch_share_eval(c, pb.Y, pb.SH, a_lo, a_hi - a_lo, sl.n2, sl.nslot, B, st, false, pb.YL0, pb.YL1);
+    launch_share_eval(c, pb.Y, pb.SH, b_lo, b_hi - b_lo, sl.n2, sl.nslot, B, st, true, pb.YL0, pb.YL1);
+    launch_share_eval(c, pb.Y, pb.SH, c_lo, c_hi - c_lo, sl.n2, sl.nslot, B, st, false, pb.YL0, pb.YL1);
 }
 
 template <int K>
@@ -333,7 +353,7 @@ static int prove_chunk(kosk_b200_ctx *c, Lane &ln, const ProveBufs &bufs, int B,
     prof_mark(c, ln, KOSK_PH_OPEN);
     k_open<K><<<B, 128, 0, st>>>(pb);
     prof_mark(c, ln, KOSK_PH_SHARE2);
-    launch_share_eval(c, pb.Y, pb.SH, sl.n1, 4 * K, sl.n2, sl.nslot, B, st);
+    launch_share_eval(c, pb.Y, pb.SH, sl.n1, 4 * K, sl.n2, sl.nslot, B, st, false, pb.YL0, pb.YL1);
     prof_mark(c, ln, KOSK_PH_VIEW);
     k_derive<K><<<dim3(ptiles, B), 128, 0, st>>>(pb);
     HashSrc hv{pb.SH, (long long)sl.nslot * SLD, 1, SLD, SOFF, c->d_tab_view, nullptr, 0};
@@ -539,7 +559,7 @@ int kosk_b200_pool_create(kosk_b200_ctx *c, size_t n, const uint8_t *seeds, kosk
     if (!c || !seeds || !out || n == 0 || n > 16384) return fail(KOSK_E_ARG, "bad argument (1 <= n <= 16384)");
     CU(cudaSetDevice(c->device));
     kosk_b200_pool *p = new kosk_b200_pool; p->ctx = c; p->n = n;
-    if (alloc_prove_bufs(p->pb, c->sl, c->k, n) != 0 || cudaMalloc((void **)&p->d_seeds, 32 * n) != cudaSuccess) {
+    if (alloc_prove_bufs(p->pb, c->sl, c->k, n, c->use_tensor != 0) != 0 || cudaMalloc((void **)&p->d_seeds, 32 * n) != cudaSuccess) {
         kosk_b200_pool_destroy(p); return fail(KOSK_E_NOMEM, "cudaMalloc failed for the preprocessing pool");
     }
     Lane &ln = c->lanes[0];
@@ -575,9 +595,15 @@ int kosk_b200_share_eval_device(kosk_b200_ctx *c, size_t n, const uint16_t *d_y,
 {
     if (!c || !d_y || !d_planes) return fail(KOSK_E_ARG, "null argument");
     CU(cudaSetDevice(c->device));
+    if (c->use_tensor && c->tmp_rows < n) {       // grow-only scratch for the limb planes of the caller's rows
+        if (c->tmpL0) { cudaFree(c->tmpL0); cudaFree(c->tmpL1); c->tmpL0 = c->tmpL1 = nullptr; }
+        if (cudaMalloc((void **)&c->tmpL0, n * YLD) != cudaSuccess || cudaMalloc((void **)&c->tmpL1, n * YLD) != cudaSuccess) return fail(KOSK_E_NOMEM, "cudaMalloc failed");
+        c->tmp_rows = n;
+    }
     for (size_t o = 0; o < n; o += (1u << 22)) {
         const int m = (int)std::min<size_t>(1u << 22, n - o);
-        launch_share_eval(c, d_y + o * YLD, d_planes + o * SLD, 0, m, m, m, 1, (cudaStream_t)stream);
+        launch_share_eval(c, d_y + o * YLD, d_planes + o * SLD, 0, m, m, m, 1, (cudaStream_t)stream, false,
+                          c->use_tensor ? c->tmpL0 + o * YLD : nullptr, c->use_tensor ? c->tmpL1 + o * YLD : nullptr);
     }
     CU(cudaGetLastError());
     return KOSK_OK;
@@ -706,7 +732,24 @@ __global__ void __launch_bounds__(256) k_int_peak(uint32_t *out, int iters, uint
     if (acc == 0x12345678u) out[blockIdx.x] = acc;      // keeps the chain live
 }
 
-extern "C" int kosk_b200_int_peak(kosk_b200_ctx *c, double *ops_per_s /* [3]: IMAD, LOP3, SHF thread-ops/s */)
+// warp-level int8 MMA issue rate (legacy mma.sync path): 8 independent accumulator tiles per warp
+__global__ void __launch_bounds__(256) k_imma_peak(int32_t *out, int iters)
+{
+    int32_t d[8][4];
+    uint32_t a[4] = {0x01020304u + threadIdx.x, 0x05060708u, 0x090a0b0cu, 0x0d0e0f10u}, b0 = 0x01010101u * (threadIdx.x & 7), b1 = 0x02020202u;
+#pragma unroll
+    for (int t = 0; t < 8; t++) for (int e = 0; e < 4; e++) d[t][e] = 0;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int t = 0; t < 8; t++) imma_16832(d[t], a, b0 + t, b1);
+    }
+    int32_t acc = 0;
+#pragma unroll
+    for (int t = 0; t < 8; t++) for (int e = 0; e < 4; e++) acc ^= d[t][e];
+    if (acc == 0x12345678) out[blockIdx.x] = acc;
+}
+
+extern "C" int kosk_b200_int_peak(kosk_b200_ctx *c, double *ops_per_s /* [4]: IMAD, LOP3, SHF thread-ops/s, IMMA int8 MAC/s */)
 {
     if (!c || !ops_per_s) return fail(KOSK_E_ARG, "null argument");
     CU(cudaSetDevice(c->device));
@@ -727,6 +770,18 @@ extern "C" int kosk_b200_int_peak(kosk_b200_ctx *c, double *ops_per_s /* [3]: IM
             if (rep > 0 && ms < best) best = ms;
         }
         ops_per_s[mode] = (double)blocks * 256.0 * iters * 64.0 / (best * 1e-3);
+    }
+    {
+        float best = 1e30f; const int it2 = 8192;
+        for (int rep = 0; rep < 4; rep++) {
+            CU(cudaEventRecord(e0, c->lanes[0].st));
+            k_imma_peak<<<blocks, 256, 0, c->lanes[0].st>>>((int32_t *)d, it2);
+            CU(cudaEventRecord(e1, c->lanes[0].st));
+            CU(cudaEventSynchronize(e1));
+            float ms = 0; CU(cudaEventElapsedTime(&ms, e0, e1));
+            if (rep > 0 && ms < best) best = ms;
+        }
+        ops_per_s[3] = (double)blocks * 8.0 * it2 * 8.0 * (16.0 * 8 * 32) / (best * 1e-3);     // warps x iters x tiles x MACs per m16n8k32
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
     return KOSK_OK;

@@ -23,6 +23,7 @@ struct ProveBufs {
     u16 *AH;           // [B][k*k][256] matrix A-hat (NTT domain), row-major A[i][j]
     u16 *SHAT;         // [B][k][256]   s-hat
     u16 *I, *REST;     // [B][150], [B][1304]
+    int8_t *YL0, *YL1; // experimental tensor path only: 7-bit limb planes of Y, [B][n2][YLD] int8
     u8 *pk, *sk, *pi;  // outputs
     int B;
 };

@@ -34,10 +34,10 @@ def ctxs(built_lib):
     from mpcith_kyber_kosk_b200 import KoskContext
     made = {}
 
-    def get(k, chunk=64, lanes=0):
-        if (k, chunk, lanes) not in made:
-            made[(k, chunk, lanes)] = KoskContext(k, 0, chunk, lanes)
-        return made[(k, chunk, lanes)]
+    def get(k, chunk=64, lanes=0, tensor=False):
+        if (k, chunk, lanes, tensor) not in made:
+            made[(k, chunk, lanes, tensor)] = KoskContext(k, 0, chunk, lanes, tensor)
+        return made[(k, chunk, lanes, tensor)]
     yield get
     for c in made.values():
         c.close()

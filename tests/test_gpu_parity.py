@@ -269,3 +269,21 @@ def test_offline_online_split_matches_one_shot(ctxs, k):
     opk, osk, opi = O.oracle_prove(k, seeds[3])
     assert (pi[3] == opi).all() and (pk[3] == opk).all() and (sk[3] == osk).all()
     assert ctx.verify_batch(pi, pk).all()
+
+
+@pytest.mark.parametrize("k", [2, 3, 4])
+def test_experimental_tensor_path_is_bit_identical(ctxs, k):
+    """Opt-in KOSK_F_TENSOR: share evaluation on int8 tensor cores (limb-split residues); same bytes as the INT32 pipe."""
+    ctx = ctxs(k, 16, 1, True)
+    rng = np.random.default_rng(70 + k)
+    y = rng.integers(0, 3329, size=(300, 407), dtype=np.uint16)
+    y[0] = 3328; y[1] = 1664; y[2] = 1665; y[3] = 0
+    got = ctx.share_eval(y)
+    for i in (0, 1, 2, 3, 150, 299):
+        assert (got[i] == O.oracle_share(y[i])).all()
+    seeds = seeds_for_range(900 + k, 0, 3)
+    pk, sk, pi = ctx.prove_batch(seeds)
+    for i in range(3):
+        opk, osk, opi = O.oracle_prove(k, seeds[i])
+        assert (pk[i] == opk).all() and (sk[i] == osk).all() and (pi[i] == opi).all()
+    assert ctx.verify_batch(pi, pk).all()
