@@ -17,6 +17,7 @@ typedef uint8_t u8;
 
 constexpr int GE_BN = 128, GE_BK = 16;
 constexpr int GE_NPAD = ((NX + GE_BN - 1) / GE_BN) * GE_BN;   // 1408 rows of the share table incl. zero padding
+constexpr int GE_NCOLS7 = ((NX + 111) / 112) * 112;           // 1344: columns covered by 112-wide tiles
 
 struct GemmArgs {
     const u16 *A;        // canonical residues (< q), rows padded with zeros to ksteps*16 terms, 16B-aligned rows
@@ -33,21 +34,26 @@ struct GemmArgs {
     // through the contraction (A and Bt advanced by 256, ksteps = 10) and c * U[n], U[n] = sum_{j<256} Bt[n][j], is added here.
     const int16_t *addvec;   // centered U, or nullptr
     const u16 *scale_src;    // c of row r = scale_src[r * lda] (canonical), same row mapping as A
+    int half_last;           // 1: only the first 8 terms of the last 16-term step are non-zero (407 = 25*16 + 7)
 };
 
-template <int TM, int NREG>
+// TN = columns per thread: 8 -> 128-column CTA tile (4 + 4 split), 7 -> 112-column tile (4 + 2 + 1 split).  1303 columns
+// are 12 x 112 = 1344 (3 % padding) instead of 11 x 128 = 1408 (8 %); all shared loads stay conflict-free / broadcast.
+template <int TM, int NREG, int TN>
 __global__ void __maxnreg__(NREG) k_gf_gemm(const GemmArgs g)
 {
-    constexpr int BM = 16 * TM;
+    static_assert(TN == 8 || TN == 7, "TN");
+    constexpr int BM = 16 * TM, BN = 16 * TN;
     __shared__ __align__(16) int32_t As[2][GE_BK][BM];
-    __shared__ __align__(16) int32_t Bs[2][GE_BK][GE_BN];
+    __shared__ __align__(16) int32_t Bs[2][GE_BK][BN];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * GE_BN;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     const u16 *Ab = g.A + (size_t)blockIdx.z * g.a_batch;
     const int16_t *Bb = g.Bt + (size_t)blockIdx.z * g.b_batch;
     u16 *Cb = g.C + (size_t)blockIdx.z * g.c_batch;
     // loader mapping: thread -> (row, 8-term half)
-    const int lrb = tid & 127, lhb = tid >> 7;
+    const bool b_thr = tid < 2 * BN;
+    const int lrb = b_thr ? tid % BN : 0, lhb = b_thr ? tid / BN : 0;
     const int lra = tid & (BM - 1), lha = (tid / BM) & 1;
     const bool a_thr = tid < 2 * BM;
     const int am = m0 + lra;
@@ -55,16 +61,18 @@ __global__ void __maxnreg__(NREG) k_gf_gemm(const GemmArgs g)
     const u16 *a_src = Ab;
     if (a_ok) a_src = Ab + ((size_t)(am / g.rpp) * g.a_slots + g.slot_lo + am % g.rpp) * g.lda + lha * 8;
     const int16_t *b_src = Bb + (size_t)(n0 + lrb) * g.ldb + lhb * 8;
+    // column c of this thread's TN-wide strip sits at tile column col_of(c)
+    auto col_of = [&](int c) { return c < 4 ? tx * 4 + c : (TN == 8 ? 64 + tx * 4 + (c - 4) : (c < 6 ? 64 + tx * 2 + (c - 4) : 96 + tx)); };
 
-    int32_t acc[TM][8];
+    int32_t acc[TM][TN];
 #pragma unroll
     for (int i = 0; i < TM; i++)
 #pragma unroll
-        for (int j = 0; j < 8; j++) acc[i][j] = 0;
+        for (int j = 0; j < TN; j++) acc[i][j] = 0;
 
-    uint4 ra = make_uint4(0, 0, 0, 0), rb;
+    uint4 ra = make_uint4(0, 0, 0, 0), rb = make_uint4(0, 0, 0, 0);
     if (a_ok) ra = *reinterpret_cast<const uint4 *>(a_src);
-    rb = *reinterpret_cast<const uint4 *>(b_src);
+    if (b_thr) rb = *reinterpret_cast<const uint4 *>(b_src);
     auto stage = [&](int buf) {
         const uint32_t wa[4] = {ra.x, ra.y, ra.z, ra.w}, wb[4] = {rb.x, rb.y, rb.z, rb.w};
 #pragma unroll
@@ -74,8 +82,10 @@ __global__ void __maxnreg__(NREG) k_gf_gemm(const GemmArgs g)
                 As[buf][lha * 8 + 2 * i][lra] = a0 > Q / 2 ? a0 - Q : a0;
                 As[buf][lha * 8 + 2 * i + 1][lra] = a1 > Q / 2 ? a1 - Q : a1;
             }
-            Bs[buf][lhb * 8 + 2 * i][lrb] = (int32_t)(int16_t)(wb[i] & 0xFFFF);
-            Bs[buf][lhb * 8 + 2 * i + 1][lrb] = (int32_t)(int16_t)(wb[i] >> 16);
+            if (b_thr) {
+                Bs[buf][lhb * 8 + 2 * i][lrb] = (int32_t)(int16_t)(wb[i] & 0xFFFF);
+                Bs[buf][lhb * 8 + 2 * i + 1][lrb] = (int32_t)(int16_t)(wb[i] >> 16);
+            }
         }
     };
     stage(0);
@@ -85,35 +95,44 @@ __global__ void __maxnreg__(NREG) k_gf_gemm(const GemmArgs g)
         const int buf = kt & 1;
         if (kt + 1 < g.ksteps) {
             if (a_ok) ra = *reinterpret_cast<const uint4 *>(a_src + (kt + 1) * GE_BK);
-            rb = *reinterpret_cast<const uint4 *>(b_src + (kt + 1) * GE_BK);
+            if (b_thr) rb = *reinterpret_cast<const uint4 *>(b_src + (kt + 1) * GE_BK);
         }
-#pragma unroll
-        for (int kk = 0; kk < GE_BK; kk++) {
+        auto mac = [&](int kk) {
             int32_t av[TM], bv[8];
 #pragma unroll
             for (int h = 0; h < TM / 4; h++) {
                 const int4 a4 = *reinterpret_cast<const int4 *>(&As[buf][kk][h * (BM / 2) + ty * 4]);
                 av[4 * h] = a4.x; av[4 * h + 1] = a4.y; av[4 * h + 2] = a4.z; av[4 * h + 3] = a4.w;
             }
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const int4 b4 = *reinterpret_cast<const int4 *>(&Bs[buf][kk][h * 64 + tx * 4]);
-                bv[4 * h] = b4.x; bv[4 * h + 1] = b4.y; bv[4 * h + 2] = b4.z; bv[4 * h + 3] = b4.w;
+            const int4 b4 = *reinterpret_cast<const int4 *>(&Bs[buf][kk][tx * 4]);
+            bv[0] = b4.x; bv[1] = b4.y; bv[2] = b4.z; bv[3] = b4.w;
+            if (TN == 8) {
+                const int4 c4 = *reinterpret_cast<const int4 *>(&Bs[buf][kk][64 + tx * 4]);
+                bv[4] = c4.x; bv[5] = c4.y; bv[6] = c4.z; bv[7] = c4.w;
+            } else {
+                const int2 c2 = *reinterpret_cast<const int2 *>(&Bs[buf][kk][64 + tx * 2]);
+                bv[4] = c2.x; bv[5] = c2.y; bv[6] = Bs[buf][kk][96 + tx]; bv[7] = 0;
             }
 #pragma unroll
             for (int i = 0; i < TM; i++)
 #pragma unroll
-                for (int j = 0; j < 8; j++) acc[i][j] += av[i] * bv[j];
+                for (int j = 0; j < TN; j++) acc[i][j] += av[i] * bv[j];
+        };
+#pragma unroll
+        for (int kk = 0; kk < GE_BK / 2; kk++) mac(kk);
+        if (kt + 1 < g.ksteps || !g.half_last) {      // a 407-term row needs only 8 terms of its 26th step (terms 408..415 are padding)
+#pragma unroll
+            for (int kk = GE_BK / 2; kk < GE_BK; kk++) mac(kk);
         }
         if ((kt & 31) == 31) {          // keep |acc| < 2^31 for rows longer than 512 terms
 #pragma unroll
             for (int i = 0; i < TM; i++)
 #pragma unroll
-                for (int j = 0; j < 8; j++) acc[i][j] = acc[i][j] % Q;
+                for (int j = 0; j < TN; j++) acc[i][j] = acc[i][j] % Q;
         }
         if (kt + 1 < g.ksteps) { stage(buf ^ 1); __syncthreads(); }
     }
-    // epilogue: canonical residues, 8-byte stores along the contiguous (party / coefficient) axis
+    // epilogue: canonical residues, vector stores along the contiguous (party / coefficient) axis
 #pragma unroll
     for (int i = 0; i < TM; i++) {
         const int m = m0 + (i / 4) * (BM / 2) + ty * 4 + (i & 3);
@@ -122,22 +141,22 @@ __global__ void __maxnreg__(NREG) k_gf_gemm(const GemmArgs g)
         if (g.addvec) {
             const int32_t cst = gf_center(g.scale_src[((size_t)(m / g.rpp) * g.a_slots + g.slot_lo + m % g.rpp) * g.lda]);
 #pragma unroll
-            for (int h = 0; h < 2; h++)
-#pragma unroll
-                for (int j = 0; j < 4; j++) acc[i][h * 4 + j] += cst * (int32_t)g.addvec[n0 + h * 64 + tx * 4 + j];
+            for (int j = 0; j < TN; j++) acc[i][j] += cst * (int32_t)g.addvec[n0 + col_of(j)];
         }
+        u16 v[TN];
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const int x = n0 + h * 64 + tx * 4;
-            u16 v[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) v[j] = (u16)gf_canon(acc[i][h * 4 + j]);
-            if (x + 3 < g.nvalid) {
-                *reinterpret_cast<uint2 *>(dst + x) = make_uint2((uint32_t)v[0] | ((uint32_t)v[1] << 16), (uint32_t)v[2] | ((uint32_t)v[3] << 16));
-            } else {
-#pragma unroll
-                for (int j = 0; j < 4; j++) if (x + j < g.nvalid) dst[x + j] = v[j];
-            }
+        for (int j = 0; j < TN; j++) v[j] = (u16)gf_canon(acc[i][j]);
+        auto put4 = [&](int x, const u16 *w) {
+            if (x + 3 < g.nvalid) *reinterpret_cast<uint2 *>(dst + x) = make_uint2((uint32_t)w[0] | ((uint32_t)w[1] << 16), (uint32_t)w[2] | ((uint32_t)w[3] << 16));
+            else { for (int j = 0; j < 4; j++) if (x + j < g.nvalid) dst[x + j] = w[j]; }
+        };
+        put4(n0 + tx * 4, v);
+        if (TN == 8) put4(n0 + 64 + tx * 4, v + 4);
+        else {
+            const int x = n0 + 64 + tx * 2;
+            if (x + 1 < g.nvalid) *reinterpret_cast<uint32_t *>(dst + x) = (uint32_t)v[4] | ((uint32_t)v[5] << 16);
+            else if (x < g.nvalid) dst[x] = v[4];
+            if (n0 + 96 + tx < g.nvalid) dst[n0 + 96 + tx] = v[6];
         }
     }
     if (g.tail && blockIdx.x == 0) {
@@ -151,11 +170,12 @@ __global__ void __maxnreg__(NREG) k_gf_gemm(const GemmArgs g)
 }
 
 // host-side launcher; returns the number of kernels launched
-template <int TM, int NREG = 128>
+// npad = number of Bt rows available (zero padded to a multiple of the column tile)
+template <int TM, int NREG = 128, int TN = 8>
 static inline int gf_gemm_launch(const GemmArgs &g, int npad, int nbatch, cudaStream_t st)
 {
-    dim3 grid(npad / GE_BN, (g.mtotal + 16 * TM - 1) / (16 * TM), nbatch);
-    k_gf_gemm<TM, NREG><<<grid, 256, 0, st>>>(g);
+    dim3 grid(npad / (16 * TN), (g.mtotal + 16 * TM - 1) / (16 * TM), nbatch);
+    k_gf_gemm<TM, NREG, TN><<<grid, 256, 0, st>>>(g);
     return 1;
 }
 

@@ -295,7 +295,8 @@ static void launch_share_eval(kosk_b200_ctx *c, const u16 *Y, u16 *SH, int slot_
         c->launches += 1 + gf_gemm_imma_launch(g, tb, NX, st);
         return;
     }
-    c->launches += (c->gemm_regs <= 96) ? gf_gemm_launch<8, 96>(g, GE_NPAD, 1, st) : gf_gemm_launch<8, 128>(g, GE_NPAD, 1, st);
+    g.half_last = 1;         // terms 407..415 of Y rows and of the S table are zero padding
+    c->launches += (c->gemm_regs <= 96) ? gf_gemm_launch<8, 96, 7>(g, GE_NCOLS7, 1, st) : gf_gemm_launch<8, 128, 7>(g, GE_NCOLS7, 1, st);
 }
 // first share evaluation of a prove chunk over slots [lo, hi): the eta-constant sharings [seta0, s0) take the short path
 static void launch_share_eval_prove(kosk_b200_ctx *c, const ProveBufs &pb, int lo, int hi, int B, cudaStream_t st)

@@ -489,7 +489,8 @@ static int verify_chunk_t(VerifyBufs &vb, const VerifyTables &vt, int B, const u
             g.rpp = grp_hi[gi] - grp_lo[gi]; g.slot_lo = grp_lo[gi]; g.a_slots = d.nyrows; g.c_slots = d.nyrows;
             g.mtotal = B * g.rpp; g.ksteps = YLD / GE_BK; g.nvalid = NX; g.c_off = SOFF + NT + 1; g.tail = 1; g.tail_off = NL;
             if (gi == 1) { g.A = vb.YV + NL; g.Bt = vt.St + NL; g.ksteps = (YLD - NL) / GE_BK; g.tail_off = 0; g.addvec = vt.SU; g.scale_src = vb.YV; }
-            nl += gf_gemm_launch<8>(g, GE_NPAD, 1, st);
+            g.half_last = 1;
+            nl += gf_gemm_launch<8, 128, 7>(g, GE_NCOLS7, 1, st);
         }
     }
     kv_check_parties<K><<<dim3(ptiles, B), 128, 0, st>>>(vb, d_pi); nl++;
