@@ -42,7 +42,8 @@ const char *kosk_b200_version(void);
  * it; 0 = default).  Replaces the reference's compile-time -DKYBER_K (params.hpp:8-10). */
 int kosk_b200_create(kosk_b200_ctx **ctx, int kyber_k, int device, int max_chunk);
 /* Same, with the number of pipeline lanes made explicit (0 = default 2).  A batch is split into sub-batches of at
- * most max_chunk proofs that run on `lanes` CUDA streams, each with its own scratch, so that sub-batches overlap. */
+ * most max_chunk proofs that alternate over `lanes` CUDA streams, each with its own scratch: kernels of consecutive
+ * sub-batches run back to back, host copies of one sub-batch overlap the kernels of the next. */
 int kosk_b200_create_ex(kosk_b200_ctx **ctx, int kyber_k, int device, int max_chunk, int lanes, int flags);
 /* flags.  KOSK_F_TENSOR (EXPERIMENTAL, off by default; also KOSK_B200_TENSOR=1 with kosk_b200_create): run the prover's
  * share evaluation on the int8 tensor-core path (limb-split residues, mma.sync) instead of the INT32 pipe.  Same bytes. */
@@ -65,6 +66,11 @@ int kosk_b200_set_strict(kosk_b200_ctx *ctx, int on);
  * Host<->device copies happen inside (pinned buffers are used asynchronously). */
 int kosk_b200_prove_batch(kosk_b200_ctx *ctx, size_t n, const uint8_t *seeds, uint8_t *pk, uint8_t *sk, uint8_t *pi);
 int kosk_b200_verify_batch(kosk_b200_ctx *ctx, size_t n, const uint8_t *pi, const uint8_t *pk, uint8_t *ok);
+/* Asynchronous form of prove_batch: enqueues H2D of the seeds, the kernels and the D2H of pk/sk/pi on the context's lanes
+ * and returns; kosk_b200_sync() waits for everything enqueued.  Consecutive calls (and the sub-batches of one call)
+ * alternate over the lanes: their kernels run back to back while the D2H copy of one overlaps the kernels of the next.
+ * Host buffers must stay valid (and should be pinned) until kosk_b200_sync returns. */
+int kosk_b200_prove_batch_async(kosk_b200_ctx *ctx, size_t n, const uint8_t *seeds, uint8_t *pk, uint8_t *sk, uint8_t *pi);
 
 /* Batch mode, device-resident buffers (same packing), enqueued on `stream` (a cudaStream_t, NULL = default).
  * Asynchronous: the caller synchronises the stream. */
@@ -98,6 +104,8 @@ int kosk_b200_share_eval_device(kosk_b200_ctx *ctx, size_t n, const uint16_t *d_
 uint64_t kosk_b200_kernel_launches(const kosk_b200_ctx *ctx);
 int kosk_b200_debug_fetch(kosk_b200_ctx *ctx, const char *what, void *out, size_t bytes);
 int kosk_b200_sync(kosk_b200_ctx *ctx);
+/* debug: (lane, phase, ms since the batch started) triples of the last profiled device-buffer batch; returns the count */
+int kosk_b200_debug_trace(kosk_b200_ctx *ctx, double *out, int max_triples);
 
 /* Measurement support.  With profiling on, every prove chunk records CUDA events on its launching stream at the
  * phase boundaries; kosk_b200_phase_times() synchronises and returns accumulated milliseconds and call counts for

@@ -14,9 +14,9 @@ LIB_PATH = os.path.join(_HERE, "libkosk_b200.so")
 EXPORTS = [
     "kosk_b200_pk_bytes", "kosk_b200_sk_bytes", "kosk_b200_proof_bytes", "kosk_b200_last_error", "kosk_b200_version",
     "kosk_b200_create", "kosk_b200_create_ex", "kosk_b200_lanes", "kosk_b200_destroy", "kosk_b200_verifiable_keygen", "kosk_b200_kosk_verify",
-    "kosk_b200_prove_batch", "kosk_b200_verify_batch", "kosk_b200_prove_batch_device", "kosk_b200_verify_batch_device",
+    "kosk_b200_prove_batch", "kosk_b200_prove_batch_async", "kosk_b200_verify_batch", "kosk_b200_prove_batch_device", "kosk_b200_verify_batch_device",
     "kosk_b200_share_eval", "kosk_b200_sha3_256_rows", "kosk_b200_ntt_rows", "kosk_b200_share_eval_device",
-    "kosk_b200_kernel_launches", "kosk_b200_debug_fetch", "kosk_b200_sync",
+    "kosk_b200_kernel_launches", "kosk_b200_debug_fetch", "kosk_b200_debug_trace", "kosk_b200_sync",
     "kosk_b200_pool_create", "kosk_b200_pool_prove", "kosk_b200_pool_destroy", "kosk_b200_set_strict", "kosk_b200_set_profiling", "kosk_b200_phase_times", "kosk_b200_int_peak",
 ]
 
@@ -50,6 +50,7 @@ def load_library(path=None):
     lib.kosk_b200_verifiable_keygen.argtypes = [vp, u8p, u8p, u8p, u8p]
     lib.kosk_b200_kosk_verify.argtypes = [vp, u8p, u8p]
     lib.kosk_b200_prove_batch.argtypes = [vp, sz, u8p, u8p, u8p, u8p]
+    lib.kosk_b200_prove_batch_async.argtypes = [vp, sz, u8p, u8p, u8p, u8p]
     lib.kosk_b200_verify_batch.argtypes = [vp, sz, u8p, u8p, u8p]
     lib.kosk_b200_prove_batch_device.argtypes = [vp, sz, u8p, u8p, u8p, u8p, vp]
     lib.kosk_b200_verify_batch_device.argtypes = [vp, sz, u8p, u8p, u8p, vp]
@@ -61,6 +62,7 @@ def load_library(path=None):
     lib.kosk_b200_kernel_launches.restype = ctypes.c_uint64
     lib.kosk_b200_debug_fetch.argtypes = [vp, ctypes.c_char_p, u8p, sz]
     lib.kosk_b200_sync.argtypes = [vp]
+    lib.kosk_b200_debug_trace.argtypes = [vp, u8p, i32]
     lib.kosk_b200_set_profiling.argtypes = [vp, i32]
     lib.kosk_b200_set_strict.argtypes = [vp, i32]
     lib.kosk_b200_pool_create.argtypes = [vp, sz, u8p, ctypes.POINTER(vp)]
@@ -217,6 +219,12 @@ class KoskContext:
         out = np.zeros(4, np.float64)
         self._check(self.lib.kosk_b200_int_peak(self._h, _ptr(out)), "int_peak")
         return {"imad": float(out[0]), "lop3": float(out[1]), "shf": float(out[2]), "imma_int8_mac": float(out[3])}
+
+    def debug_trace(self, max_triples=4096):
+        out = np.zeros(3 * max_triples, np.float64)
+        n = self._check(self.lib.kosk_b200_debug_trace(self._h, _ptr(out), max_triples), "debug_trace")
+        names = self.PHASES + ["end"]
+        return [(int(out[3 * i]), names[int(out[3 * i + 1])] if out[3 * i + 1] >= 0 else "end", float(out[3 * i + 2])) for i in range(n)]
 
     def sync(self):
         self._check(self.lib.kosk_b200_sync(self._h), "sync")

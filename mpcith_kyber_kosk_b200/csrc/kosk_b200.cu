@@ -53,9 +53,9 @@ enum { KOSK_PH_KEYGEN = 0, KOSK_PH_EXPAND, KOSK_PH_SHARE1, KOSK_PH_COMMIT, KOSK_
 // different lanes so that latency-bound phases (the sequential Fiat-Shamir sponges), ALU-pipe phases (Keccak) and
 // FMA-pipe phases (share evaluation) of different sub-batches overlap on the SMs, and D2H copies overlap compute.
 struct Lane {
-    cudaStream_t st = nullptr;            // main (high priority) stream of the lane
-    cudaStream_t st_lo = nullptr;         // low-priority stream for the long share-evaluation launch
-    cudaEvent_t done = nullptr, ev_a = nullptr, ev_b = nullptr;
+    cudaStream_t st = nullptr;
+    cudaEvent_t done = nullptr;           // everything enqueued on the lane so far (join with the caller's stream)
+    cudaEvent_t computed = nullptr;       // the kernels of the lane's latest sub-batch (the next sub-batch's kernels wait on it)
     ProveBufs pb{};
     u8 *d_seeds = nullptr, *d_pk = nullptr, *d_sk = nullptr, *d_pi = nullptr, *d_ok = nullptr;   // staging of the host-buffer API
     VerifyBufs vb{};
@@ -64,7 +64,9 @@ struct Lane {
 };
 
 struct kosk_b200_ctx {
-    int k = 0, device = 0, chunk = 0, gemm_regs = 128, use_prio = 2, use_tensor = 0;
+    int k = 0, device = 0, chunk = 0, gemm_regs = 128, use_tensor = 0;
+    size_t next_lane = 0;
+    cudaEvent_t last_computed = nullptr;   // compute-done event of the most recently enqueued sub-batch (any lane)
     Slots sl; Layout L;
     uint64_t launches = 0;
     // constant tables
@@ -138,9 +140,7 @@ static void ctx_free(kosk_b200_ctx *c)
         verify_free(ln.vb);
         for (cudaEvent_t e : ln.ev) cudaEventDestroy(e);
         if (ln.done) cudaEventDestroy(ln.done);
-        if (ln.ev_a) cudaEventDestroy(ln.ev_a);
-        if (ln.ev_b) cudaEventDestroy(ln.ev_b);
-        if (ln.st_lo) cudaStreamDestroy(ln.st_lo);
+        if (ln.computed) cudaEventDestroy(ln.computed);
         if (ln.st) cudaStreamDestroy(ln.st);
     }
     if (c->ev_start) cudaEventDestroy(c->ev_start);
@@ -171,13 +171,12 @@ int kosk_b200_create_ex(kosk_b200_ctx **out, int k, int device, int max_chunk, i
     CU(cudaSetDevice(device));
     kosk_b200_ctx *c = new kosk_b200_ctx;
     c->k = k; c->device = device; c->sl = make_slots(k); c->L = make_layout(k);
-    c->chunk = max_chunk > 0 ? max_chunk : 512;
+    c->chunk = max_chunk > 0 ? max_chunk : 1024;
     if (c->chunk > 16384) c->chunk = 16384;
     if (nlanes <= 0) nlanes = 2;
     if (nlanes > 8) nlanes = 8;
     { const char *e = getenv("KOSK_B200_GEMM_REGS"); if (e) c->gemm_regs = atoi(e) <= 96 ? 96 : 128; }
     c->use_tensor = (flags & KOSK_F_TENSOR) ? 1 : 0;
-    { const char *e = getenv("KOSK_B200_PRIO"); if (e) c->use_prio = atoi(e); }
     const Slots &sl = c->sl; const Layout &L = c->L;
     const size_t B = (size_t)c->chunk;
 #define ALLOC(ptr, bytes) do { if (cudaMalloc((void **)&(ptr), (bytes)) != cudaSuccess) { ctx_free(c); return fail(KOSK_E_NOMEM, "cudaMalloc failed for " #ptr); } } while (0)
@@ -242,26 +241,11 @@ int kosk_b200_create_ex(kosk_b200_ctx **out, int k, int device, int max_chunk, i
         if (alloc_prove_bufs(ln.pb, sl, k, B, c->use_tensor != 0) != 0) { ctx_free(c); return fail(KOSK_E_NOMEM, "cudaMalloc failed for prover scratch"); }
         ALLOC(ln.d_seeds, B * 32); ALLOC(ln.d_pk, B * L.pk_bytes); ALLOC(ln.d_sk, B * L.sk_bytes); ALLOC(ln.d_pi, B * L.proof_bytes); ALLOC(ln.d_ok, B);
         if (verify_alloc(ln.vb, k, c->chunk) != 0) { ctx_free(c); return fail(KOSK_E_NOMEM, "cudaMalloc failed for verifier scratch"); }
-        {
-            // use_prio 0: all lanes equal; 1: per-lane hi/lo stream pair (long GEMM on lo); 2: staggered lanes -- lane 0 runs
-            // ahead at the highest priority and later lanes fill its latency-bound gaps, so sub-batches finish in order and
-            // their D2H copies overlap the compute of the following ones.
-            int lo = 0, hi = 0; CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));      // hi is numerically smaller
-            const int li = (int)(&ln - &c->lanes[0]);
-            if (c->use_prio == 1) {
-                CU(cudaStreamCreateWithPriority(&ln.st, cudaStreamNonBlocking, hi));
-                CU(cudaStreamCreateWithPriority(&ln.st_lo, cudaStreamNonBlocking, lo));
-            } else if (c->use_prio == 2) {
-                CU(cudaStreamCreateWithPriority(&ln.st, cudaStreamNonBlocking, std::min(lo, hi + li)));
-            } else {
-                CU(cudaStreamCreateWithFlags(&ln.st, cudaStreamNonBlocking));
-            }
-        }
+        CU(cudaStreamCreateWithFlags(&ln.st, cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming));
-        CU(cudaEventCreateWithFlags(&ln.ev_a, cudaEventDisableTiming));
-        CU(cudaEventCreateWithFlags(&ln.ev_b, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ln.computed, cudaEventDisableTiming));
     }
-    CU(cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming));
+    CU(cudaEventCreate(&c->ev_start));
     CU(cudaDeviceSynchronize());
     *out = c;
     return KOSK_OK;
@@ -321,6 +305,10 @@ static int prove_chunk(kosk_b200_ctx *c, Lane &ln, const ProveBufs &bufs, int B,
     constexpr int NVIEW = 16 + NCOMMIT + 4 * K + 8 * ETA * K;
     const int ptiles = (NP + 127) / 128;
     const bool off = phases & PH_OFFLINE, on = phases & PH_ONLINE;
+    // Lanes pipeline copies against compute, not compute against compute: the kernels of consecutive sub-batches run one
+    // after the other (co-running them was measured to slow the latency-bound FS sponges 3x), while the D2H copy of a
+    // finished sub-batch overlaps the kernels of the next one on the other lane.
+    if (c->last_computed && c->last_computed != ln.computed) CU(cudaStreamWaitEvent(st, c->last_computed, 0));
     if (on) {
         prof_mark(c, ln, KOSK_PH_KEYGEN);
         k_keygen<K><<<B, 128, 0, st>>>(pb); c->launches++;
@@ -334,16 +322,9 @@ static int prove_chunk(kosk_b200_ctx *c, Lane &ln, const ProveBufs &bufs, int B,
     }
     // first share evaluation: slots [0, s0) (f, NTT_f, eta constants) are key-independent, [s0, n1) (s, e, z_j) are not
     const int lo = off ? 0 : sl.s0, hi = on ? sl.n1 : sl.s0;
-    if (ln.st_lo) {          // long FMA-pipe launch on the low-priority stream: other lanes' Keccak / FS kernels get SM slots first
-        CU(cudaEventRecord(ln.ev_a, st)); CU(cudaStreamWaitEvent(ln.st_lo, ln.ev_a, 0));
-        prof_mark(c, ln, KOSK_PH_SHARE1, ln.st_lo);
-        launch_share_eval_prove(c, pb, lo, hi, B, ln.st_lo);
-        CU(cudaEventRecord(ln.ev_b, ln.st_lo)); CU(cudaStreamWaitEvent(st, ln.ev_b, 0));
-    } else {
-        prof_mark(c, ln, KOSK_PH_SHARE1);
-        launch_share_eval_prove(c, pb, lo, hi, B, st);
-    }
-    if (!on) { prof_mark(c, ln, -1); CU(cudaGetLastError()); return KOSK_OK; }
+    prof_mark(c, ln, KOSK_PH_SHARE1);
+    launch_share_eval_prove(c, pb, lo, hi, B, st);
+    if (!on) { prof_mark(c, ln, -1); CU(cudaEventRecord(ln.computed, st)); c->last_computed = ln.computed; CU(cudaGetLastError()); return KOSK_OK; }
     prof_mark(c, ln, KOSK_PH_COMMIT);
     HashSrc hc{pb.SH, (long long)sl.nslot * SLD, 1, SLD, SOFF, c->d_tab_commit, nullptr, 0};
     k_hash_records<NCOMMIT><<<dim3(ptiles, B), 128, 0, st>>>(hc, pb.TCR, pb.SH, sl.nslot, sl.TC0);
@@ -364,6 +345,7 @@ static int prove_chunk(kosk_b200_ctx *c, Lane &ln, const ProveBufs &bufs, int B,
     prof_mark(c, ln, KOSK_PH_ASSEMBLE);
     k_assemble<K><<<dim3((NT + 31) / 32 + (NR + 31) / 32, B), 128, 0, st>>>(pb);
     prof_mark(c, ln, -1);
+    CU(cudaEventRecord(ln.computed, st)); c->last_computed = ln.computed;
     c->launches += 8;
     CU(cudaGetLastError());
     return KOSK_OK;
@@ -381,20 +363,21 @@ static int prove_chunk_k(kosk_b200_ctx *c, Lane &ln, const ProveBufs &bufs, int 
 static int verify_chunk_lane(kosk_b200_ctx *c, Lane &ln, int B, const u8 *d_pi, const u8 *d_pk, u8 *d_ok)
 {
     VerifyTables vt{c->d_St, c->d_R1, c->d_R2, c->d_inv, c->d_SU};
+    if (c->last_computed && c->last_computed != ln.computed) CU(cudaStreamWaitEvent(ln.st, c->last_computed, 0));
     prof_mark(c, ln, KOSK_PH_VERIFY);
     int nl = verify_chunk(c->k, ln.vb, vt, B, d_pi, d_pk, d_ok, ln.st);
     prof_mark(c, ln, -1);
+    CU(cudaEventRecord(ln.computed, ln.st)); c->last_computed = ln.computed;
     if (nl < 0) return fail(KOSK_E_CUDA, "verify launch failed");
     c->launches += nl;
     CU(cudaGetLastError());
     return KOSK_OK;
 }
 
-// sub-batch size: spread n proofs over the lanes, at most `chunk` per wave
+// sub-batch size: at most `chunk` proofs per wave; consecutive sub-batches alternate over the lanes
 static size_t sub_batch(const kosk_b200_ctx *c, size_t n)
 {
-    const size_t L = c->lanes.size();
-    return std::max<size_t>(1, std::min<size_t>((size_t)c->chunk, (n + L - 1) / L));
+    return std::max<size_t>(1, std::min<size_t>((size_t)c->chunk, n));
 }
 // lanes start after everything already enqueued on the caller's stream ...
 static int lanes_fork(kosk_b200_ctx *c, cudaStream_t caller)
@@ -461,7 +444,7 @@ int kosk_b200_prove_batch_device(kosk_b200_ctx *c, size_t n, const uint8_t *d_se
     size_t i = 0;
     for (size_t o = 0; o < n; o += sub, i++) {
         const int B = (int)std::min<size_t>(sub, n - o);
-        { Lane &ln = c->lanes[i % c->lanes.size()]; rc = prove_chunk_k(c, ln, ln.pb, B, d_seeds + 32 * o, d_pk + L.pk_bytes * o, d_sk + L.sk_bytes * o, d_pi + L.proof_bytes * o, PH_OFFLINE | PH_ONLINE); }
+        { Lane &ln = c->lanes[c->next_lane++ % c->lanes.size()]; rc = prove_chunk_k(c, ln, ln.pb, B, d_seeds + 32 * o, d_pk + L.pk_bytes * o, d_sk + L.sk_bytes * o, d_pi + L.proof_bytes * o, PH_OFFLINE | PH_ONLINE); }
         if (rc) return rc;
     }
     return lanes_join(c, (cudaStream_t)stream);
@@ -469,14 +452,21 @@ int kosk_b200_prove_batch_device(kosk_b200_ctx *c, size_t n, const uint8_t *d_se
 
 int kosk_b200_prove_batch(kosk_b200_ctx *c, size_t n, const uint8_t *seeds, uint8_t *pk, uint8_t *sk, uint8_t *pi)
 {
+    int rc = kosk_b200_prove_batch_async(c, n, seeds, pk, sk, pi);
+    if (rc) return rc;
+    for (Lane &ln : c->lanes) CU(cudaStreamSynchronize(ln.st));
+    return KOSK_OK;
+}
+
+int kosk_b200_prove_batch_async(kosk_b200_ctx *c, size_t n, const uint8_t *seeds, uint8_t *pk, uint8_t *sk, uint8_t *pi)
+{
     if (!c || !seeds || !pk || !sk || !pi) return fail(KOSK_E_ARG, "null argument");
     CU(cudaSetDevice(c->device));
     const Layout &L = c->L;
     const size_t sub = sub_batch(c, n);
-    size_t i = 0;
-    for (size_t o = 0; o < n; o += sub, i++) {
+    for (size_t o = 0; o < n; o += sub) {
         const int B = (int)std::min<size_t>(sub, n - o);
-        Lane &ln = c->lanes[i % c->lanes.size()];
+        Lane &ln = c->lanes[c->next_lane++ % c->lanes.size()];
         CU(cudaMemcpyAsync(ln.d_seeds, seeds + 32 * o, 32 * (size_t)B, cudaMemcpyHostToDevice, ln.st));
         int rc = prove_chunk_k(c, ln, ln.pb, B, ln.d_seeds, ln.d_pk, ln.d_sk, ln.d_pi, PH_OFFLINE | PH_ONLINE);
         if (rc) return rc;
@@ -484,7 +474,6 @@ int kosk_b200_prove_batch(kosk_b200_ctx *c, size_t n, const uint8_t *seeds, uint
         CU(cudaMemcpyAsync(sk + L.sk_bytes * o, ln.d_sk, L.sk_bytes * (size_t)B, cudaMemcpyDeviceToHost, ln.st));
         CU(cudaMemcpyAsync(pi + L.proof_bytes * o, ln.d_pi, L.proof_bytes * (size_t)B, cudaMemcpyDeviceToHost, ln.st));
     }
-    for (Lane &ln : c->lanes) CU(cudaStreamSynchronize(ln.st));
     return KOSK_OK;
 }
 
@@ -681,6 +670,24 @@ int kosk_b200_debug_fetch(kosk_b200_ctx *c, const char *what, void *out, size_t 
     return KOSK_OK;
 }
 
+
+// debug: timeline of the phase marks of the last profiled batch: triples (lane, phase, ms since the batch's fork event)
+int kosk_b200_debug_trace(kosk_b200_ctx *c, double *out, int max_triples)
+{
+    if (!c || !out) return fail(KOSK_E_ARG, "null argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaDeviceSynchronize());
+    int n = 0;
+    for (size_t li = 0; li < c->lanes.size(); li++) {
+        Lane &ln = c->lanes[li];
+        for (size_t i = 0; i < ln.ev_phase.size() && n < max_triples; i++) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, c->ev_start, ln.ev[ln.ev_phase[i].second]) != cudaSuccess) ms = -1;
+            out[3 * n] = (double)li; out[3 * n + 1] = ln.ev_phase[i].first; out[3 * n + 2] = ms; n++;
+        }
+    }
+    return n;
+}
 
 int kosk_b200_set_strict(kosk_b200_ctx *c, int on)
 {

@@ -287,3 +287,23 @@ def test_experimental_tensor_path_is_bit_identical(ctxs, k):
         opk, osk, opi = O.oracle_prove(k, seeds[i])
         assert (pk[i] == opk).all() and (sk[i] == osk).all() and (pi[i] == opi).all()
     assert ctx.verify_batch(pi, pk).all()
+
+
+def test_async_pipelined_host_api(ctxs):
+    """kosk_b200_prove_batch_async: three batches in flight over two lanes (kernels back to back, copies overlapped) give
+    the same bytes as the synchronous call, also when a batch spans several sub-batches."""
+    ctx = ctxs(2, 4, 2)
+    lib, h = ctx.lib, ctx._h
+    outs = []
+    for j, n in enumerate((4, 7, 2)):
+        seeds = seeds_for_range(4000 + 100 * j, 0, n)
+        bufs = (np.empty((n, ctx.pk_bytes), np.uint8), np.empty((n, ctx.sk_bytes), np.uint8), np.empty((n, ctx.proof_bytes), np.uint8))
+        assert lib.kosk_b200_prove_batch_async(h, n, seeds.ctypes.data, bufs[0].ctypes.data, bufs[1].ctypes.data, bufs[2].ctypes.data) == 0
+        outs.append((seeds, bufs))
+    ctx.sync()
+    for seeds, bufs in outs:
+        ref = ctx.prove_batch(seeds)
+        for x, y in zip(ref, bufs):
+            assert (x == y).all()
+    opk, osk, opi = O.oracle_prove(2, outs[1][0][6])
+    assert (outs[1][1][2][6] == opi).all()
