@@ -32,7 +32,7 @@ INT_OPS_PER_KECCAK = 7440                # 24 rounds x 155 64-bit logic ops x 2 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--kyber-k", type=int, default=2)
@@ -48,16 +48,17 @@ def parse():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
-    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe).  The sampler runs from
+    process start (nvidia-smi needs a moment to come up); only samples stamped inside [mark_start, mark_stop] are used."""
+    Q = "timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.t0, self.t1 = index, [], None, None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -65,19 +66,30 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_stop(self):
+        self.t1 = time.time()
 
     def stop(self):
         if self.proc:
+            time.sleep(0.05)
             self.proc.terminate()
-        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        inside = [r for t, r in self.rows if self.t0 is not None and self.t0 <= t <= (self.t1 or t) + 0.02]
+        use = inside if inside else [r for _, r in self.rows[-3:]]
+        sm = sorted(int(float(r[1])) for r in use if len(r) > 1 and r[1].replace(".", "").isdigit())
         reasons = set()
-        for r in self.rows:
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+        for r in use:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+        mx = [int(float(r[2])) for r in use if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        pw = [float(r[3]) for r in use if len(r) > 3 and r[3].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None, "reasons": sorted(reasons),
+                "samples": len(inside), "power_w_max": max(pw) if pw else None}
 
 
 def cpu_oracle():
@@ -151,6 +163,9 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device (the KOSK core has no CPU path; use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     if world > 1:
         os.environ["NCCL_DEBUG"] = os.environ.get("KOSK_NCCL_DEBUG", "WARN")     # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
@@ -181,9 +196,7 @@ def run_b200(args):
     barrier()
     ctx.set_profiling(True)
     ctx.phase_times(reset=True)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    sampler.mark_start()
     l0 = ctx.kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -192,6 +205,7 @@ def run_b200(args):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
+    sampler.mark_stop()
     launches = ctx.kernel_launches() - l0
     phases = ctx.phase_times(reset=True)
     ctx.set_profiling(False)
@@ -301,7 +315,7 @@ def run_b200(args):
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "int32-pipe", "kernel": "k_gf_gemm<8> (share evaluation, ss.cpp:23-32; first share-eval phase = 3 launches: f/NTT_f | eta constants | s,e,z)", "achieved": achieved_tmac, "peak": peak_tmac,
-                         "unit": "TMAC/s", "frac": (achieved_tmac / peak_tmac) if achieved_tmac else None, "traffic": None,
+                         "unit": "TMAC/s", "frac": (achieved_tmac / peak_tmac) if achieved_tmac else None, "traffic": ncu_traffic(k, B),
                          "peak_source": "IMAD issue-rate microbenchmark run in this process (MEASURED_PEAKS.json has no integer entry)",
                          "ms_per_launch": ms_per_launch, "share_of_step": sh_ms / ms if ms else None},
             "roofline_hbm": {"bound": "hbm", "achieved": bytes_per_launch / (ms_per_launch * 1e-3) / 1e9 if sh_calls else None, "peak": hbm_peak, "unit": "GB/s",
@@ -327,6 +341,18 @@ def run_b200(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def ncu_traffic(k, B):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the share-evaluation launches of one step, from the committed
+    `ncu --set full` capture (profiles/ncu_share_eval.json); only valid for the configuration that was profiled."""
+    path = os.path.join(ROOT, "profiles", "ncu_share_eval.json")
+    if not os.path.exists(path):
+        return None
+    d = json.load(open(path))
+    if d.get("kyber_k") != k or d.get("batch") != B:
+        return None
+    return {"dram_bytes_per_step": d["dram_bytes_read"] + d["dram_bytes_write"], "unit": "B", "source": d.get("source")}
 
 
 def ctx_rows(k):

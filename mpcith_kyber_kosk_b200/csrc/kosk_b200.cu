@@ -64,7 +64,7 @@ struct Lane {
 };
 
 struct kosk_b200_ctx {
-    int k = 0, device = 0, chunk = 0, gemm_regs = 128, use_tensor = 0;
+    int k = 0, device = 0, chunk = 0, use_tensor = 0;
     size_t next_lane = 0;
     cudaEvent_t last_computed = nullptr;   // compute-done event of the most recently enqueued sub-batch (any lane)
     Slots sl; Layout L;
@@ -175,7 +175,6 @@ int kosk_b200_create_ex(kosk_b200_ctx **out, int k, int device, int max_chunk, i
     if (c->chunk > 16384) c->chunk = 16384;
     if (nlanes <= 0) nlanes = 2;
     if (nlanes > 8) nlanes = 8;
-    { const char *e = getenv("KOSK_B200_GEMM_REGS"); if (e) c->gemm_regs = atoi(e) <= 96 ? 96 : 128; }
     c->use_tensor = (flags & KOSK_F_TENSOR) ? 1 : 0;
     const Slots &sl = c->sl; const Layout &L = c->L;
     const size_t B = (size_t)c->chunk;
@@ -280,7 +279,7 @@ static void launch_share_eval(kosk_b200_ctx *c, const u16 *Y, u16 *SH, int slot_
         return;
     }
     g.half_last = 1;         // terms 407..415 of Y rows and of the S table are zero padding
-    c->launches += (c->gemm_regs <= 96) ? gf_gemm_launch<8, 96, 7>(g, GE_NCOLS7, 1, st) : gf_gemm_launch<8, 128, 7>(g, GE_NCOLS7, 1, st);
+    c->launches += gf_gemm_launch<8, 128, 7>(g, GE_NCOLS7, 1, st);
 }
 // first share evaluation of a prove chunk over slots [lo, hi): the eta-constant sharings [seta0, s0) take the short path
 static void launch_share_eval_prove(kosk_b200_ctx *c, const ProveBufs &pb, int lo, int hi, int B, cudaStream_t st)

@@ -5,8 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from mpcith_kyber_kosk_b200 import KoskContext
 from mpcith_kyber_kosk_b200.sharding import seeds_for_range
 
-def run(k, B, lanes, chunk, prio, steps=4):
-    os.environ["KOSK_B200_PRIO"] = str(prio)
+def run(k, B, lanes, chunk, steps=4, **_ignored):
     ctx = KoskContext(k, 0, chunk, lanes)
     hs = [torch.from_numpy(seeds_for_range(7, s * B, (s + 1) * B)).pin_memory() for s in range(steps + 1)]
     h_pk = torch.empty(B * ctx.pk_bytes, dtype=torch.uint8).pin_memory(); h_sk = torch.empty(B * ctx.sk_bytes, dtype=torch.uint8).pin_memory()
@@ -17,7 +16,7 @@ def run(k, B, lanes, chunk, prio, steps=4):
     t0 = time.perf_counter()
     for s in range(steps): step(s)
     torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / steps
-    print(json.dumps({"k": k, "B": B, "lanes": lanes, "chunk": chunk, "prio": prio, "ms": round(dt * 1e3, 2), "e2e_proofs_s": round(B / dt)}), flush=True)
+    print(json.dumps({"k": k, "B": B, "lanes": lanes, "chunk": chunk, "ms": round(dt * 1e3, 2), "e2e_proofs_s": round(B / dt)}), flush=True)
     ctx.close()
 
 if __name__ == "__main__":

@@ -1,12 +1,11 @@
-"""Timing sweep of the device-resident prove path over (lanes, chunk, GEMM register cap). Run under gpurun."""
+"""Timing sweep of the device-resident prove (and verify) path over batch / chunk / lanes / tensor flag. Run under gpurun."""
 import os, sys, json
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from mpcith_kyber_kosk_b200 import KoskContext
 from mpcith_kyber_kosk_b200.sharding import seeds_for_range
 
-def run(k, B, lanes, chunk, regs, steps=4, verify=False, prio=0, tensor=0):
-    os.environ["KOSK_B200_GEMM_REGS"] = str(regs); os.environ["KOSK_B200_PRIO"] = str(prio)
+def run(k, B, lanes, chunk, steps=4, verify=False, tensor=0, **_ignored):
     ctx = KoskContext(k, 0, chunk, lanes, bool(tensor))
     dev = torch.device("cuda", 0)
     seeds = [torch.from_numpy(seeds_for_range(99, s * B, (s + 1) * B)).to(dev) for s in range(steps + 2)]
@@ -20,7 +19,7 @@ def run(k, B, lanes, chunk, regs, steps=4, verify=False, prio=0, tensor=0):
     for s in range(steps): ctx.prove_batch_device(B, seeds[2 + s].data_ptr(), d_pk.data_ptr(), d_sk.data_ptr(), d_pi.data_ptr(), st)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
-    out = {"k": k, "B": B, "lanes": lanes, "chunk": chunk, "regs": regs, "prio": prio, "tensor": tensor, "ms": round(ms, 3), "proofs_s": round(B / ms * 1e3)}
+    out = {"k": k, "B": B, "lanes": lanes, "chunk": chunk, "tensor": tensor, "ms": round(ms, 3), "proofs_s": round(B / ms * 1e3)}
     if verify:
         ctx.verify_batch_device(B, d_pi.data_ptr(), d_pk.data_ptr(), d_ok.data_ptr(), st); torch.cuda.synchronize()
         e0.record()

@@ -4,8 +4,7 @@ import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from mpcith_kyber_kosk_b200 import KoskContext
 from mpcith_kyber_kosk_b200.sharding import seeds_for_range
-k, B, lanes, chunk, prio, regs = (int(x) for x in sys.argv[1:7])
-os.environ["KOSK_B200_PRIO"] = str(prio); os.environ["KOSK_B200_GEMM_REGS"] = str(regs)
+k, B, lanes, chunk = (int(x) for x in sys.argv[1:5])
 ctx = KoskContext(k, 0, chunk, lanes)
 dev = torch.device("cuda", 0)
 seeds = torch.from_numpy(seeds_for_range(3, 0, B)).to(dev)
