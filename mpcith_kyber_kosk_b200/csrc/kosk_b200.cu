@@ -49,9 +49,9 @@ enum { PH_OFFLINE = 1, PH_ONLINE = 2 };
 enum { KOSK_PH_KEYGEN = 0, KOSK_PH_EXPAND, KOSK_PH_SHARE1, KOSK_PH_COMMIT, KOSK_PH_FS1, KOSK_PH_EVAL, KOSK_PH_OPEN, KOSK_PH_SHARE2,
        KOSK_PH_VIEW, KOSK_PH_FS2, KOSK_PH_ASSEMBLE, KOSK_PH_VERIFY, KOSK_NPHASE };
 
-// One pipeline lane: a stream plus the per-chunk scratch of one sub-batch.  Independent sub-batches run on
-// different lanes so that latency-bound phases (the sequential Fiat-Shamir sponges), ALU-pipe phases (Keccak) and
-// FMA-pipe phases (share evaluation) of different sub-batches overlap on the SMs, and D2H copies overlap compute.
+// One pipeline lane: a stream plus the per-chunk scratch and staging buffers of one sub-batch.  Consecutive sub-batches
+// alternate over the lanes; an event chain keeps their kernels back to back (co-running them was measured to be a loss)
+// while the host copies of one sub-batch overlap the kernels of the next.
 struct Lane {
     cudaStream_t st = nullptr;
     cudaEvent_t done = nullptr;           // everything enqueued on the lane so far (join with the caller's stream)
@@ -76,6 +76,7 @@ struct kosk_b200_ctx {
     int16_t *d_SU = nullptr;               // [GE_NPAD] centered U[x] = sum_{j<256} S[x][j]: share of the all-ones secret vector
     int16_t *d_R1 = nullptr, *d_R2 = nullptr; // verifier: centered recon tables [256][YLD], [256][VR2LD]
     u16 *d_inv = nullptr;                  // [3329] inverses
+    u16 *d_fact = nullptr;                 // [2][FACT_N] factorials and inverse factorials mod q (verifier's Lagrange weights)
     int16_t *d_tab_commit = nullptr, *d_tab_view = nullptr;
     std::vector<Lane> lanes;
     cudaEvent_t ev_start = nullptr;
@@ -131,7 +132,7 @@ static void ctx_free(kosk_b200_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    void *ptrs[] = {c->tmpL0, c->tmpL1, c->d_St, c->d_St0, c->d_St1, c->d_SU, c->d_R1, c->d_R2, c->d_inv, c->d_tab_commit, c->d_tab_view};
+    void *ptrs[] = {c->d_fact, c->tmpL0, c->tmpL1, c->d_St, c->d_St0, c->d_St1, c->d_SU, c->d_R1, c->d_R2, c->d_inv, c->d_tab_commit, c->d_tab_view};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (Lane &ln : c->lanes) {
         free_prove_bufs(ln.pb);
@@ -213,6 +214,9 @@ int kosk_b200_create_ex(kosk_b200_ctx **out, int k, int device, int max_chunk, i
         ALLOC(c->d_R2, R2p.size() * 2); CU(cudaMemcpy(c->d_R2, R2p.data(), R2p.size() * 2, cudaMemcpyHostToDevice));
         std::vector<uint16_t> inv(Q, 0); for (int a = 1; a < Q; a++) inv[a] = (uint16_t)h_pow(a, Q - 2);
         ALLOC(c->d_inv, Q * 2); CU(cudaMemcpy(c->d_inv, inv.data(), Q * 2, cudaMemcpyHostToDevice));
+        std::vector<uint16_t> fc(2 * FACT_N);
+        { uint32_t f = 1; for (int i = 0; i < FACT_N; i++) { if (i) f = f * i % Q; fc[i] = (uint16_t)f; fc[FACT_N + i] = inv[f]; } }
+        ALLOC(c->d_fact, fc.size() * 2); CU(cudaMemcpy(c->d_fact, fc.data(), fc.size() * 2, cudaMemcpyHostToDevice));
         // hashed-record slot tables: commitment (mlwe_prover.cpp:117-126) and view (:398-443)
         std::vector<int16_t> tc, tv;
         for (int j = 0; j < k; j++) tc.push_back((int16_t)(sl.s0 + j));
@@ -361,7 +365,7 @@ static int prove_chunk_k(kosk_b200_ctx *c, Lane &ln, const ProveBufs &bufs, int 
 
 static int verify_chunk_lane(kosk_b200_ctx *c, Lane &ln, int B, const u8 *d_pi, const u8 *d_pk, u8 *d_ok)
 {
-    VerifyTables vt{c->d_St, c->d_R1, c->d_R2, c->d_inv, c->d_SU};
+    VerifyTables vt{c->d_St, c->d_R1, c->d_R2, c->d_inv, c->d_SU, c->d_fact};
     if (c->last_computed && c->last_computed != ln.computed) CU(cudaStreamWaitEvent(ln.st, c->last_computed, 0));
     prof_mark(c, ln, KOSK_PH_VERIFY);
     int nl = verify_chunk(c->k, ln.vb, vt, B, d_pi, d_pk, d_ok, ln.st);

@@ -17,7 +17,7 @@ constexpr int OPLD = 160;         // opened-party values: beta[70] gamma[70] r[2
 enum VFlag { VF_I = 1, VF_BG = 2, VF_SR = 4, VF_NTT = 8, VF_ASR = 16, VF_T = 32, VF_TREL = 64, VF_ETA = 128,
              VF_SUBETA = 256, VF_UZ = 512, VF_U2D = 1024, VF_FS2 = 2048, VF_STRICT = 4096 };
 
-struct VerifyTables { const int16_t *St, *R1, *R2; const u16 *inv; const int16_t *SU; };
+struct VerifyTables { const int16_t *St, *R1, *R2; const u16 *inv; const int16_t *SU; const u16 *fact; /* [2][FACT_N]: i!, 1/i! */ };
 
 struct VerifyBufs {
     int *flags = nullptr;
@@ -147,31 +147,48 @@ __global__ void __launch_bounds__(128) kv_setup(VerifyBufs vb, const u8 *__restr
 
 // V4 + V8 (mlwe_verifier.cpp:67-89, :148-170): beta/gamma/r/NTT_r of the opened parties.
 // Exact reference semantics: the sum starts from the raw (possibly non-canonical) share f[c0] and every step is
-// gf3329_add(acc, gf3329_mul(pow, f)); with a canonical first term this equals plain mod-q arithmetic.
+// gf3329_add(acc, gf3329_mul(pow, f)); with a canonical first term this equals plain mod-q arithmetic, which is what the
+// fast path computes (shares held as centered residues in registers, one IMAD per term, one reduction per output).
 template <int K>
 __global__ void __launch_bounds__(320) kv_eval_opened(VerifyBufs vb)
 {
-    constexpr int F = MK + 2 * K + 1, NA = MK + 2 * K;
+    constexpr int F = MK + 2 * K + 1, NA = MK + 2 * K, FP = (F + 3) & ~3;
     const VDims d = make_vdims(K);
     const int b = blockIdx.x, tid = threadIdx.x;
-    __shared__ u16 spw[NA][F];
-    for (int i = tid; i < NA * F; i += 320) spw[i / F][i % F] = vb.PW[(size_t)b * NA * F + i];
+    __shared__ __align__(16) int32_t spw[NA][FP];          // centered powers, row j = challenge j
+    for (int i = tid; i < NA * FP; i += 320) {
+        const int j = i / FP, kk = i % FP;
+        spw[j][kk] = kk < F ? gf_center(vb.PW[(size_t)b * NA * F + j * F + kk]) : 0;
+    }
     __syncthreads();
     if (tid >= 2 * NT) return;
     const int i = tid >> 1, half = tid & 1;
     const u16 *f = vb.CR + ((size_t)b * NT + i) * d.crld + 2 * K + half * F;
     u16 *out = vb.OPV + ((size_t)b * NT + i) * OPLD;
+    int32_t fr[FP];
+#pragma unroll
+    for (int kk = 0; kk < FP; kk++) fr[kk] = kk < F ? gf_center(f[kk] % (uint32_t)Q) : 0;
+    const bool canon0 = f[0] < Q, canon71 = f[MK + 1] < Q;
+    const int32_t c0 = fr[0], c71 = fr[MK + 1];
+#pragma unroll 1
     for (int j = 0; j < NA; j++) {
-        const int c0 = j < MK ? 0 : MK + 1;
-        u16 acc = f[c0];
-        if (acc < Q) {
-            uint32_t s = 0;                                   // lazy: 78 * 3328^2 < 2^32
-            for (int kk = 1; kk < F; kk++) s += (uint32_t)spw[j][kk] * (f[kk] % (uint32_t)Q);
-            acc = (u16)((s + acc) % (uint32_t)Q);
-        } else {
-            for (int kk = 1; kk < F; kk++) acc = ref_add(acc, (u16)(((uint32_t)spw[j][kk] * f[kk]) % (uint32_t)Q));
+        const bool fast = j < MK ? canon0 : canon71;
+        u16 res;
+        if (fast) {
+            int32_t acc = 0;                                 // 78 * 1664^2 < 2^31; the k = 0 term is replaced by the c0 share below
+#pragma unroll
+            for (int k4 = 0; k4 < FP / 4; k4++) {
+                const int4 w = *reinterpret_cast<const int4 *>(&spw[j][4 * k4]);
+                acc += fr[4 * k4] * w.x + fr[4 * k4 + 1] * w.y + fr[4 * k4 + 2] * w.z + fr[4 * k4 + 3] * w.w;
+            }
+            acc += (j < MK ? c0 : c71) - fr[0] * spw[j][0];
+            res = (u16)gf_canon(acc);
+        } else {                                             // non-canonical first term: the reference's u16 chain, verbatim
+            u16 acc = f[j < MK ? 0 : MK + 1];
+            for (int kk = 1; kk < F; kk++) acc = ref_add(acc, (u16)(((uint32_t)gf_canon(spw[j][kk]) * f[kk]) % (uint32_t)Q));
+            res = acc;
         }
-        if (j < MK) out[half * MK + j] = acc; else out[2 * MK + half * 2 * K + (j - MK)] = acc;
+        if (j < MK) out[half * MK + j] = res; else out[2 * MK + half * 2 * K + (j - MK)] = res;
     }
 }
 
@@ -216,26 +233,55 @@ __global__ void __launch_bounds__(128) kv_gather(VerifyBufs vb, const u8 *__rest
 // Per-proof Lagrange matrices over the rest-party nodes x_k = rest[k] + 256 (barycentric form):
 //   LM1[t][k] = l_k^{x_0..x_406}(t), t = 0..406 (a target that is itself a node gives a unit row);
 //   LM2[t][k] = l_k^{x_0..x_812}(t), t = 0..255.
-__global__ void __launch_bounds__(256) kv_lagrange(VerifyBufs vb, const u16 *__restrict__ inv_g)
+// The nodes are the integers of [256, hi] minus at most 150 "holes" (opened parties), so the O(n^2) products of the
+// barycentric weights and of P(t) = prod_m (t - x_m) collapse to factorials times a product over the holes:
+//   prod_{m != k} (x_k - x_m) = (x_k-256)! (hi-x_k)! (-1)^(hi-x_k) / prod_h (x_k - h)
+//   prod_m (t - x_m)          = (-1)^(hi-255) (hi-t)! / (255-t)! / prod_h (t - h)                      (t < 256)
+//                             = (t-256)! (hi-t)! (-1)^(hi-t) / prod_{h != t} (t - h)                  (t a hole in [256, hi])
+constexpr int FACT_N = 1712;      // factorials up to hi <= 1709
+__global__ void __launch_bounds__(256) kv_lagrange(VerifyBufs vb, const u16 *__restrict__ inv_g, const u16 *__restrict__ fact_g)
 {
     const int b = blockIdx.x, tid = threadIdx.x;
-    __shared__ u16 x[D2], w[D2], P[D1], inv[Q];
+    __shared__ u16 x[D2], w[D2], P[D1], inv[Q], fact[FACT_N], ifact[FACT_N], hole[NT];
     __shared__ int16_t hit[D1];
+    __shared__ int nh;
     for (int i = tid; i < Q; i += 256) inv[i] = inv_g[i];
+    for (int i = tid; i < FACT_N; i += 256) { fact[i] = fact_g[i]; ifact[i] = fact_g[FACT_N + i]; }
     for (int i = tid; i < D2; i += 256) x[i] = (u16)(vb.REST[(size_t)b * NR + i] + 256);
     __syncthreads();
     for (int pass = 0; pass < 2; pass++) {
         const int n = pass ? D2 : D1, nt = pass ? 256 : D1, ld = pass ? VR2LD : YLD;
         int16_t *out = pass ? vb.LM2 + (size_t)b * 256 * VR2LD : vb.LM1 + (size_t)b * LM1_ROWS * YLD;
+        const int hi = x[n - 1];
+        if (tid == 0) {                                   // holes of [256, hi]: opened parties below the last node
+            int c = 0;
+            for (int i = 0; i < NT; i++) { const int h = vb.I[(size_t)b * NT + i] + 256; if (h < hi) hole[c++] = (u16)h; }
+            nh = c;
+        }
+        __syncthreads();
         for (int k = tid; k < n; k += 256) {
-            uint32_t dprod = 1; const uint32_t xk = x[k];
-            for (int m = 0; m < n; m++) if (m != k) dprod = gf_mul(dprod, gf_sub(xk, x[m]));
-            w[k] = inv[dprod];
+            const uint32_t xk = x[k];
+            uint32_t num = 1;
+            for (int i = 0; i < nh; i++) num = gf_mul(num, gf_sub(xk, hole[i]));
+            uint32_t v = gf_mul(gf_mul(num, ifact[xk - 256]), ifact[hi - xk]);
+            if ((hi - xk) & 1) v = gf_sub(0, v);
+            w[k] = (u16)v;
         }
         for (int t = tid; t < nt; t += 256) {
-            uint32_t full = 1; int h = -1;
-            for (int m = 0; m < n; m++) { const uint32_t dd = gf_sub((uint32_t)t, x[m]); if (dd == 0) h = m; else full = gf_mul(full, dd); }
-            P[t] = (u16)full; hit[t] = (int16_t)h;
+            uint32_t den = 1; int h = -1;
+            if (t >= 256) {                               // only in pass 0: t is a node (unit row) or a hole
+                int lo = 0, up = n - 1;                   // x ascending: binary search
+                while (lo < up) { const int mid = (lo + up) >> 1; if (x[mid] < t) lo = mid + 1; else up = mid; }
+                if (x[lo] == t) h = lo;
+            }
+            uint32_t v = 0;
+            if (h < 0) {
+                for (int i = 0; i < nh; i++) { const uint32_t dd = gf_sub((uint32_t)t, hole[i]); if (dd) den = gf_mul(den, dd); }
+                if (t < 256) { v = gf_mul(fact[hi - t], ifact[255 - t]); if ((hi - 255) & 1) v = gf_sub(0, v); }
+                else { v = gf_mul(fact[t - 256], fact[hi - t]); if ((hi - t) & 1) v = gf_sub(0, v); }
+                v = gf_mul(v, inv[den]);
+            }
+            P[t] = (u16)v; hit[t] = (int16_t)h;
         }
         __syncthreads();
         for (int idx = tid; idx < nt * n; idx += 256) {
@@ -455,7 +501,7 @@ static int verify_chunk_t(VerifyBufs &vb, const VerifyTables &vt, int B, const u
     k_fs1<K><<<(B + 3) / 4, 128, 0, st>>>(vb.TCR, vb.PW, B); nl++;
     kv_eval_opened<K><<<B, 320, 0, st>>>(vb); nl++;
     kv_gather<K><<<dim3(2 * MK + d.n1rows + d.n2rows, B), 128, 0, st>>>(vb, d_pi); nl++;
-    kv_lagrange<<<B, 256, 0, st>>>(vb, vt.inv); nl++;
+    kv_lagrange<<<B, 256, 0, st>>>(vb, vt.inv, vt.fact); nl++;
     GemmArgs g{};
     // beta/gamma reconstruction: ABG x R1
     g = GemmArgs{}; g.A = vb.ABG; g.Bt = vt.R1; g.C = vb.BS; g.lda = YLD; g.ldb = YLD; g.ldc = 256;
