@@ -64,7 +64,8 @@ struct Lane {
 };
 
 struct kosk_b200_ctx {
-    int k = 0, device = 0, chunk = 0, use_tensor = 0;
+    int k = 0, device = 0, chunk = 0, use_tensor = 0, fuse_fs = 1, fuse_max = 128;
+    int *d_status = nullptr;               // device word set by a kernel that gave up waiting (never expected)
     size_t next_lane = 0;
     cudaEvent_t last_computed = nullptr;   // compute-done event of the most recently enqueued sub-batch (any lane)
     Slots sl; Layout L;
@@ -132,7 +133,7 @@ static void ctx_free(kosk_b200_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    void *ptrs[] = {c->d_fact, c->tmpL0, c->tmpL1, c->d_St, c->d_St0, c->d_St1, c->d_SU, c->d_R1, c->d_R2, c->d_inv, c->d_tab_commit, c->d_tab_view};
+    void *ptrs[] = {c->d_status, c->d_fact, c->tmpL0, c->tmpL1, c->d_St, c->d_St0, c->d_St1, c->d_SU, c->d_R1, c->d_R2, c->d_inv, c->d_tab_commit, c->d_tab_view};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (Lane &ln : c->lanes) {
         free_prove_bufs(ln.pb);
@@ -177,6 +178,8 @@ int kosk_b200_create_ex(kosk_b200_ctx **out, int k, int device, int max_chunk, i
     if (nlanes <= 0) nlanes = 2;
     if (nlanes > 8) nlanes = 8;
     c->use_tensor = (flags & KOSK_F_TENSOR) ? 1 : 0;
+    { const char *e = getenv("KOSK_B200_FUSE_FS"); if (e) c->fuse_fs = atoi(e); }
+    { const char *e = getenv("KOSK_B200_FUSE_MAX"); if (e) c->fuse_max = atoi(e); }
     const Slots &sl = c->sl; const Layout &L = c->L;
     const size_t B = (size_t)c->chunk;
 #define ALLOC(ptr, bytes) do { if (cudaMalloc((void **)&(ptr), (bytes)) != cudaSuccess) { ctx_free(c); return fail(KOSK_E_NOMEM, "cudaMalloc failed for " #ptr); } } while (0)
@@ -238,6 +241,7 @@ int kosk_b200_create_ex(kosk_b200_ctx **out, int k, int device, int max_chunk, i
         ALLOC(c->d_tab_commit, tc.size() * 2); CU(cudaMemcpy(c->d_tab_commit, tc.data(), tc.size() * 2, cudaMemcpyHostToDevice));
         ALLOC(c->d_tab_view, tv.size() * 2); CU(cudaMemcpy(c->d_tab_view, tv.data(), tv.size() * 2, cudaMemcpyHostToDevice));
     }
+    ALLOC(c->d_status, 4); CU(cudaMemset(c->d_status, 0, 4));
     // ---- per-lane scratch ----
     c->lanes.resize(nlanes);
     for (Lane &ln : c->lanes) {
@@ -256,7 +260,16 @@ int kosk_b200_create_ex(kosk_b200_ctx **out, int k, int device, int max_chunk, i
 
 void kosk_b200_destroy(kosk_b200_ctx *c) { ctx_free(c); }
 uint64_t kosk_b200_kernel_launches(const kosk_b200_ctx *c) { return c ? c->launches : 0; }
-int kosk_b200_sync(kosk_b200_ctx *c) { if (!c) return KOSK_E_ARG; CU(cudaSetDevice(c->device)); for (Lane &ln : c->lanes) CU(cudaStreamSynchronize(ln.st)); return KOSK_OK; }
+int kosk_b200_sync(kosk_b200_ctx *c)
+{
+    if (!c) return KOSK_E_ARG;
+    CU(cudaSetDevice(c->device));
+    for (Lane &ln : c->lanes) CU(cudaStreamSynchronize(ln.st));
+    int st = 0;
+    CU(cudaMemcpy(&st, c->d_status, 4, cudaMemcpyDeviceToHost));
+    if (st) return fail(KOSK_E_CUDA, "a kernel gave up waiting for its producer warps (internal error)");
+    return KOSK_OK;
+}
 int kosk_b200_lanes(const kosk_b200_ctx *c) { return c ? (int)c->lanes.size() : 0; }
 
 }  // extern "C"
@@ -330,9 +343,18 @@ static int prove_chunk(kosk_b200_ctx *c, Lane &ln, const ProveBufs &bufs, int B,
     if (!on) { prof_mark(c, ln, -1); CU(cudaEventRecord(ln.computed, st)); c->last_computed = ln.computed; CU(cudaGetLastError()); return KOSK_OK; }
     prof_mark(c, ln, KOSK_PH_COMMIT);
     HashSrc hc{pb.SH, (long long)sl.nslot * SLD, 1, SLD, SOFF, c->d_tab_commit, nullptr, 0};
-    k_hash_records<NCOMMIT><<<dim3(ptiles, B), 128, 0, st>>>(hc, pb.TCR, pb.SH, sl.nslot, sl.TC0);
-    prof_mark(c, ln, KOSK_PH_FS1);
-    k_fs1<K><<<(B + 3) / 4, 128, 0, st>>>(pb.TCR, pb.PW, B);
+    // Latency mode (small sub-batches): commit hashes and the FS-1 sponge of a proof in one CTA, so the sponge starts while the
+    // parties are still being hashed.  For large sub-batches the fused form is hash-throughput bound on the SM sub-partitions
+    // that host hasher warps (registers allow only 2 hasher warps per proof at 1024 proofs in flight) and gains nothing.
+    const bool fuse = c->fuse_fs && B <= c->fuse_max;
+    if (fuse) {
+        k_hash_fs<K, NCOMMIT, 1, 2><<<B, 96, 0, st>>>(hc, pb.TCR, pb.SH, sl.nslot, sl.TC0, pb.PW, nullptr, nullptr, c->d_status);
+        prof_mark(c, ln, KOSK_PH_FS1);
+    } else {
+        k_hash_records<NCOMMIT><<<dim3(ptiles, B), 128, 0, st>>>(hc, pb.TCR, pb.SH, sl.nslot, sl.TC0);
+        prof_mark(c, ln, KOSK_PH_FS1);
+        k_fs1<K><<<(B + 3) / 4, 128, 0, st>>>(pb.TCR, pb.PW, B);
+    }
     prof_mark(c, ln, KOSK_PH_EVAL);
     k_eval<K><<<dim3(3, B), 256, 0, st>>>(pb);
     prof_mark(c, ln, KOSK_PH_OPEN);
@@ -342,14 +364,19 @@ static int prove_chunk(kosk_b200_ctx *c, Lane &ln, const ProveBufs &bufs, int B,
     prof_mark(c, ln, KOSK_PH_VIEW);
     k_derive<K><<<dim3(ptiles, B), 128, 0, st>>>(pb);
     HashSrc hv{pb.SH, (long long)sl.nslot * SLD, 1, SLD, SOFF, c->d_tab_view, nullptr, 0};
-    k_hash_records<NVIEW><<<dim3(ptiles, B), 128, 0, st>>>(hv, pb.VWR, nullptr, 0, 0);
-    prof_mark(c, ln, KOSK_PH_FS2);
-    k_fs2<<<(B + 3) / 4, 128, 0, st>>>(pb.VWR, pb.I, pb.REST, B);
+    if (fuse) {
+        k_hash_fs<K, NVIEW, 2, 2><<<B, 96, 0, st>>>(hv, pb.VWR, nullptr, 0, 0, nullptr, pb.I, pb.REST, c->d_status);
+        prof_mark(c, ln, KOSK_PH_FS2);
+    } else {
+        k_hash_records<NVIEW><<<dim3(ptiles, B), 128, 0, st>>>(hv, pb.VWR, nullptr, 0, 0);
+        prof_mark(c, ln, KOSK_PH_FS2);
+        k_fs2<<<(B + 3) / 4, 128, 0, st>>>(pb.VWR, pb.I, pb.REST, B);
+    }
     prof_mark(c, ln, KOSK_PH_ASSEMBLE);
     k_assemble<K><<<dim3((NT + 31) / 32 + (NR + 31) / 32, B), 128, 0, st>>>(pb);
     prof_mark(c, ln, -1);
     CU(cudaEventRecord(ln.computed, st)); c->last_computed = ln.computed;
-    c->launches += 8;
+    c->launches += fuse ? 6 : 8;
     CU(cudaGetLastError());
     return KOSK_OK;
 }
@@ -457,8 +484,7 @@ int kosk_b200_prove_batch(kosk_b200_ctx *c, size_t n, const uint8_t *seeds, uint
 {
     int rc = kosk_b200_prove_batch_async(c, n, seeds, pk, sk, pi);
     if (rc) return rc;
-    for (Lane &ln : c->lanes) CU(cudaStreamSynchronize(ln.st));
-    return KOSK_OK;
+    return kosk_b200_sync(c);
 }
 
 int kosk_b200_prove_batch_async(kosk_b200_ctx *c, size_t n, const uint8_t *seeds, uint8_t *pk, uint8_t *sk, uint8_t *pi)

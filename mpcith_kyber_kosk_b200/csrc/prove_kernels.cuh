@@ -266,21 +266,11 @@ struct HashSrc {
     const int16_t *tab;      // nullptr = identity
     const u16 *plist; int nlist;   // nullptr: items are parties 0..NP-1; else item idx -> output party plist[b][idx]
 };
+// SHA3-256 of one record; element v is the u16 at cta_base + toff + soff[v].  Digest in a[0..3].
 template <int NVALS>
-__global__ void __launch_bounds__(128)
-k_hash_records(const HashSrc hs, u8 *__restrict__ out_rows, u16 *__restrict__ out_planes, int nslot, int out_plane_slot)
+__device__ __forceinline__ void hash_record(uint64_t (&a)[25], const char *cta_base, uint32_t toff, const uint32_t *soff)
 {
-    __shared__ uint32_t soff[NVALS];      // byte offset of record element v from the CTA's (uniform) base
-    for (int i = threadIdx.x; i < NVALS; i += 128) soff[i] = (uint32_t)((hs.tab ? hs.tab[i] : i) * hs.elem_stride * 2);
-    __syncthreads();
-    const int b = blockIdx.y, idx = blockIdx.x * 128 + threadIdx.x;
-    int p = idx;
-    if (hs.plist) { if (idx >= hs.nlist) return; p = hs.plist[(size_t)b * hs.nlist + idx]; if (p >= NP) return; }
-    else if (idx >= NP) return;
-    const char *cta_base = reinterpret_cast<const char *>(hs.src + (size_t)b * hs.proof_stride + hs.off0);
-    const uint32_t toff = (uint32_t)(idx * hs.item_stride * 2);
     auto ld = [&](int v) -> uint64_t { return *reinterpret_cast<const u16 *>(cta_base + (toff + soff[v])); };
-    uint64_t a[25];
     keccak_zero(a);
     constexpr int NFULL = (2 * NVALS) / 136, REMV = NVALS - NFULL * 68;   // u16 values left for the last block
 #pragma unroll 1
@@ -304,6 +294,22 @@ k_hash_records(const HashSrc hs, u8 *__restrict__ out_rows, u16 *__restrict__ ou
         a[l] ^= w;
     }
     keccak_f1600(a);
+}
+
+template <int NVALS>
+__global__ void __launch_bounds__(128)
+k_hash_records(const HashSrc hs, u8 *__restrict__ out_rows, u16 *__restrict__ out_planes, int nslot, int out_plane_slot)
+{
+    __shared__ uint32_t soff[NVALS];      // byte offset of record element v from the CTA's (uniform) base
+    for (int i = threadIdx.x; i < NVALS; i += 128) soff[i] = (uint32_t)((hs.tab ? hs.tab[i] : i) * hs.elem_stride * 2);
+    __syncthreads();
+    const int b = blockIdx.y, idx = blockIdx.x * 128 + threadIdx.x;
+    int p = idx;
+    if (hs.plist) { if (idx >= hs.nlist) return; p = hs.plist[(size_t)b * hs.nlist + idx]; if (p >= NP) return; }
+    else if (idx >= NP) return;
+    const char *cta_base = reinterpret_cast<const char *>(hs.src + (size_t)b * hs.proof_stride + hs.off0);
+    uint64_t a[25];
+    hash_record<NVALS>(a, cta_base, (uint32_t)(idx * hs.item_stride * 2), soff);
     if (out_rows) {
         uint64_t *o = reinterpret_cast<uint64_t *>(out_rows + ((size_t)b * NP + p) * 32);
         o[0] = a[0]; o[1] = a[1]; o[2] = a[2]; o[3] = a[3];
@@ -459,6 +465,130 @@ __global__ void __launch_bounds__(128) k_fs2(const u8 *__restrict__ VWR, u16 *__
         const uint32_t m = __ballot_sync(0xffffffffu, free_);
         if (free_) { const int pos = n + __popc(m & ((1u << lane) - 1)); if (pos < NR) rest[pos] = (u16)p; }
         n += __popc(m);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused per-proof record hashing + Fiat-Shamir sponge (prover): one CTA per proof.  Warps 1..NHW hash the 1454 party
+// records in party order (thread per party, register-resident Keccak, ALU-pipe bound) and publish how far they are in a
+// shared-memory counter; warp 0 runs the strictly sequential 343-permutation tree hash (warp-cooperative Keccak, latency
+// bound) over the digests as they become available, then expands the challenge.  The sponge's latency, 1.06 / 1.35 ms
+// as a kernel of its own, hides behind the hashing of the same proofs.  Hashers never wait, so the CTA cannot deadlock;
+// the sponge warp's spin is bounded and reports through *status.
+//   MODE 1: commitments -> Tcomm rows + planes, FS-1 -> power table PW      (mlwe_prover.cpp:116-153)
+//   MODE 2: view hashes -> VWR rows,            FS-2 -> I, rest list        (mlwe_prover.cpp:395-490)
+template <int K, int NVALS, int MODE, int NHW>
+__global__ void __launch_bounds__(32 * (NHW + 1))
+k_hash_fs(const HashSrc hs, u8 *__restrict__ rows, u16 *__restrict__ out_planes, int nslot, int out_plane_slot,
+          u16 *__restrict__ PW, u16 *__restrict__ Iout, u16 *__restrict__ REST, int *__restrict__ status)
+{
+    constexpr int F = MK + 2 * K + 1, NA = MK + 2 * K;
+    constexpr int PASS = 32 * NHW, NPASS = (NP + PASS - 1) / PASS;
+    __shared__ uint32_t soff[NVALS];
+    __shared__ int s_done[NHW];                     // passes completed by each hasher warp
+    __shared__ u16 sval[NT + 2];                    // alpha (MODE 1) or raw opened indices (MODE 2)
+    __shared__ uint32_t sused[(NP + 31) / 32];
+    const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < NVALS; i += blockDim.x) soff[i] = (uint32_t)((hs.tab ? hs.tab[i] : i) * hs.elem_stride * 2);
+    if (threadIdx.x < NHW) s_done[threadIdx.x] = 0;
+    __syncthreads();
+    u8 *myrows = rows + (size_t)b * TREE_BYTES;
+    if (warp > 0) {
+        // ---- hashers ----
+        const int h = warp - 1;
+        const char *cta_base = reinterpret_cast<const char *>(hs.src + (size_t)b * hs.proof_stride + hs.off0);
+        for (int j = 0; j < NPASS; j++) {
+            const int p = j * PASS + 32 * h + lane;
+            if (p < NP) {
+                uint64_t a[25];
+                hash_record<NVALS>(a, cta_base, (uint32_t)(p * hs.item_stride * 2), soff);
+                uint64_t *o = reinterpret_cast<uint64_t *>(myrows + (size_t)p * 32);
+                o[0] = a[0]; o[1] = a[1]; o[2] = a[2]; o[3] = a[3];
+                if (out_planes) {
+                    u16 *q = out_planes + ((size_t)b * nslot + out_plane_slot) * SLD + SOFF + p;
+#pragma unroll
+                    for (int i = 0; i < 16; i++) q[(size_t)i * SLD] = (u16)(a[i >> 2] >> (16 * (i & 3)));
+                }
+            }
+            __threadfence_block();                  // digests visible to the sponge warp before the counter moves
+            __syncwarp();
+            if (lane == 0) reinterpret_cast<volatile int *>(s_done)[h] = j + 1;
+        }
+        return;
+    }
+    // ---- sponge warp ----
+    WarpKeccak wk; wk.init();
+    const uint64_t *src = reinterpret_cast<const uint64_t *>(myrows);
+    constexpr int NFULL = TREE_BYTES / 136;         // 342 full rate blocks + 16 bytes
+    auto wait_party = [&](int pmax) {               // all digests of parties <= pmax written?
+        const int j = pmax / PASS, hh = (pmax % PASS) / 32;
+        int spins = 0;
+        for (;;) {
+            bool ok = true;
+#pragma unroll
+            for (int w2 = 0; w2 < NHW; w2++) ok &= reinterpret_cast<volatile int *>(s_done)[w2] >= (w2 <= hh ? j + 1 : j);
+            if (ok) break;
+            __nanosleep(200);
+            if (++spins > (1 << 24)) { if (lane == 0) atomicExch(status, 1); break; }     // ~ seconds: report instead of hanging
+        }
+        __threadfence_block();
+    };
+    uint64_t a = 0;
+#pragma unroll 1
+    for (int blk = 0; blk < NFULL; blk++) {
+        wait_party(min(NP - 1, (136 * blk + 135) / 32));
+        if (lane < 17) a ^= __ldcg(src + blk * 17 + lane);
+        a = wk.permute(a);
+    }
+    wait_party(NP - 1);
+    if (lane < 2) a ^= __ldcg(src + NFULL * 17 + lane);
+    if (lane == 2) a ^= 0x06ULL;
+    if (lane == 16) a ^= 0x8000000000000000ULL;
+    a = wk.permute(a);
+    a = wk.prf1(a);
+    if (MODE == 1) {
+#pragma unroll 1
+        for (int blk = 0; blk < 2; blk++) {         // 2*NA <= 156 bytes = 136 + 20
+            if (lane < 17)
+#pragma unroll
+                for (int i = 0; i < 4; i++) { const int j = blk * 68 + 4 * lane + i; if (j < NA) sval[j] = (u16)(lane_be16(a, i) % (uint32_t)Q); }
+            if (blk == 0) a = wk.permute(a);
+        }
+        __syncwarp();
+        u16 *pw = PW + (size_t)b * NA * F;
+        for (int j = lane; j < NA; j += 32) {
+            const uint32_t al = sval[j]; uint32_t xx = 1;
+            for (int kk = 0; kk < F; kk++) { pw[j * F + kk] = (u16)xx; xx = gf_mul(xx, al); }
+        }
+    } else {
+#pragma unroll 1
+        for (int blk = 0; blk < 3; blk++) {         // 300 bytes = 136 + 136 + 28
+            if (lane < 17)
+#pragma unroll
+                for (int i = 0; i < 4; i++) { const int j = blk * 68 + 4 * lane + i; if (j < NT) sval[j] = (u16)(lane_be16(a, i) % (uint32_t)NP); }
+            if (blk < 2) a = wk.permute(a);
+        }
+        for (int i = lane; i < (NP + 31) / 32; i += 32) sused[i] = 0;
+        __syncwarp();
+        u16 *I = Iout + (size_t)b * NT;
+        if (lane == 0) {
+            for (int i = 0; i < NT; i++) {          // linear-probe de-duplication (mlwe_prover.cpp:459-474)
+                uint32_t c = sval[i];
+                while (sused[c >> 5] & (1u << (c & 31))) c = (c + 1 == NP) ? 0 : c + 1;
+                sused[c >> 5] |= 1u << (c & 31);
+                I[i] = (u16)c;
+            }
+        }
+        __syncwarp();
+        u16 *rest = REST + (size_t)b * NR;
+        int n = 0;
+        for (int p0 = 0; p0 < NP; p0 += 32) {
+            const int p = p0 + lane;
+            const bool free_ = p < NP && !(sused[p >> 5] & (1u << (p & 31)));
+            const uint32_t m = __ballot_sync(0xffffffffu, free_);
+            if (free_) { const int pos = n + __popc(m & ((1u << lane) - 1)); if (pos < NR) rest[pos] = (u16)p; }
+            n += __popc(m);
+        }
     }
 }
 
