@@ -505,17 +505,17 @@ static int verify_chunk_t(VerifyBufs &vb, const VerifyTables &vt, int B, const u
     GemmArgs g{};
     // beta/gamma reconstruction: ABG x R1
     g = GemmArgs{}; g.A = vb.ABG; g.Bt = vt.R1; g.C = vb.BS; g.lda = YLD; g.ldb = YLD; g.ldc = 256;
-    g.mtotal = B * 2 * MK; g.ksteps = YLD / GE_BK; g.nvalid = 256; g.rpp = g.mtotal; g.c_off = 0;
+    g.mtotal = B * 2 * MK; g.ksteps = YLD / GE_BK; g.nvalid = 256; g.rpp = g.mtotal; g.c_off = 0; g.half_last = 1;
     nl += gf_gemm_launch<8>(g, 256, 1, st);
     kv_check_bg<<<dim3(MK, B), 128, 0, st>>>(vb); nl++;
     // interpolation-apply, one Lagrange matrix per proof (batched over blockIdx.z)
     g = GemmArgs{}; g.A = vb.A1; g.Bt = vb.LM1; g.C = vb.YV; g.lda = YLD; g.ldb = YLD; g.ldc = YLD;
     g.a_batch = (long long)d.n1rows * YLD; g.b_batch = (long long)LM1_ROWS * YLD; g.c_batch = (long long)d.nyrows * YLD;
-    g.mtotal = d.n1rows; g.ksteps = YLD / GE_BK; g.nvalid = D1; g.rpp = g.mtotal;
+    g.mtotal = d.n1rows; g.ksteps = YLD / GE_BK; g.nvalid = D1; g.rpp = g.mtotal; g.half_last = 1;
     for (int o = 0; o < B; o += 32768) {
         GemmArgs h = g; const int nb = min(32768, B - o);
         h.A += (size_t)o * g.a_batch; h.Bt += (size_t)o * g.b_batch; h.C += (size_t)o * g.c_batch;
-        nl += gf_gemm_launch<4>(h, LM1_ROWS, nb, st);
+        nl += gf_gemm_launch<4, 128, 7>(h, 448, nb, st);      // 407 targets in four 112-column tiles (LM1 has 512 zero-padded rows)
     }
     g = GemmArgs{}; g.A = vb.A2; g.Bt = vb.LM2; g.C = vb.UZ; g.lda = VR2LD; g.ldb = VR2LD; g.ldc = 256;
     g.a_batch = (long long)d.n2rows * VR2LD; g.b_batch = (long long)256 * VR2LD; g.c_batch = (long long)d.n2rows * 256;
