@@ -35,6 +35,8 @@ struct GemmArgs {
     const int16_t *addvec;   // centered U, or nullptr
     const u16 *scale_src;    // c of row r = scale_src[r * lda] (canonical), same row mapping as A
     int half_last;           // 1: only the first 8 terms of the last 16-term step are non-zero (407 = 25*16 + 7)
+    const u16 *colscale;     // optional per-column factor (canonical), applied after the reduction: C[m][n] = acc * colscale[n] mod q
+    long long colscale_batch;
 };
 
 // TN = columns per thread: 8 -> 128-column CTA tile (4 + 4 split), 7 -> 112-column tile (4 + 2 + 1 split).  1303 columns
@@ -146,6 +148,11 @@ __global__ void __maxnreg__(NREG) k_gf_gemm(const GemmArgs g)
         u16 v[TN];
 #pragma unroll
         for (int j = 0; j < TN; j++) v[j] = (u16)gf_canon(acc[i][j]);
+        if (g.colscale) {
+            const u16 *cs = g.colscale + (size_t)blockIdx.z * g.colscale_batch + n0;
+#pragma unroll
+            for (int j = 0; j < TN; j++) v[j] = (u16)gf_mul(v[j], cs[col_of(j)]);
+        }
         auto put4 = [&](int x, const u16 *w) {
             if (x + 3 < g.nvalid) *reinterpret_cast<uint2 *>(dst + x) = make_uint2((uint32_t)w[0] | ((uint32_t)w[1] << 16), (uint32_t)w[2] | ((uint32_t)w[3] << 16));
             else { for (int j = 0; j < 4; j++) if (x + j < g.nvalid) dst[x + j] = w[j]; }

@@ -27,6 +27,7 @@ struct VerifyBufs {
     u16 *CR = nullptr, *VR = nullptr, *OPV = nullptr, *UOP = nullptr;
     u16 *ABG = nullptr, *BS = nullptr, *A1 = nullptr, *YV = nullptr, *A2 = nullptr, *UZ = nullptr, *VSH = nullptr, *U2 = nullptr, *UR = nullptr;
     int16_t *LM1 = nullptr, *LM2 = nullptr;
+    u16 *W1 = nullptr, *W2 = nullptr, *PT1 = nullptr, *PT2 = nullptr;   // barycentric weights per node / P(t) per target
     int k = 0, chunk = 0;
     int strict = 0;   // hardened decoding: off by default = the reference's accept set
 };
@@ -46,7 +47,7 @@ KOSK_HD VDims make_vdims(int k)
 static inline void verify_free(VerifyBufs &v)
 {
     void *p[] = {v.flags, v.I, v.REST, v.I2, v.REST2, v.POS, v.AH, v.TPK, v.PW, v.TCR, v.VWR, v.CR, v.VR, v.OPV, v.UOP,
-                 v.ABG, v.BS, v.A1, v.YV, v.A2, v.UZ, v.VSH, v.U2, v.UR, v.LM1, v.LM2};
+                 v.ABG, v.BS, v.A1, v.YV, v.A2, v.UZ, v.VSH, v.U2, v.UR, v.LM1, v.LM2, v.W1, v.W2, v.PT1, v.PT2};
     for (void *q : p) if (q) cudaFree(q);
     v = VerifyBufs{};
 }
@@ -64,6 +65,7 @@ static inline int verify_alloc(VerifyBufs &v, int k, int chunk)
     VA(v.A2, B * d.n2rows * VR2LD * 2, 1); VA(v.UZ, B * d.n2rows * 256 * 2, 0);
     VA(v.VSH, B * d.nyrows * SLD * 2, 1); VA(v.U2, B * d.n2rows * VR2LD * 2, 1); VA(v.UR, B * d.n2rows * 256 * 2, 0);
     VA(v.LM1, B * LM1_ROWS * YLD * 2, 1); VA(v.LM2, B * 256 * VR2LD * 2, 1);
+    VA(v.W1, B * YLD * 2, 1); VA(v.W2, B * VR2LD * 2, 1); VA(v.PT1, B * LM1_ROWS * 2, 1); VA(v.PT2, B * 256 * 2, 1);
 #undef VA
     return 0;
 }
@@ -195,8 +197,8 @@ __global__ void __launch_bounds__(320) kv_eval_opened(VerifyBufs vb)
 // Row gathers for the table / interpolation contractions (values reduced mod q exactly where the reference
 // reduces them: gf3329_mul in recon_* and the NTL ZZ_p assignment in the interpolation inputs).
 //   ABG[j*2+w][p]  p<407: beta/gamma share of party p      (mlwe_verifier.cpp:97-108)
-//   A1 [row][j]    j<407: sr, er, t, s_eta, e_eta shares of rest party j   (:178-186, :320-324, :390-395)
-//   A2 [row][j]    j<813: u_s, u_e shares of rest party j  (:503-508)
+//   A1 [row][j]    j<407: sr, er, t, s_eta, e_eta shares of rest party j, times the barycentric weight w_j  (:178-186, :320-324, :390-395)
+//   A2 [row][j]    j<813: u_s, u_e shares of rest party j, times w_j  (:503-508)
 template <int K>
 __global__ void __launch_bounds__(128) kv_gather(VerifyBufs vb, const u8 *__restrict__ pis)
 {
@@ -221,18 +223,22 @@ __global__ void __launch_bounds__(128) kv_gather(VerifyBufs vb, const u8 *__rest
         else if (r < 3 * K + K * d.E) { off = L.o_seta; mul = K * d.E; add = r - 3 * K; }
         else { off = L.o_eeta; mul = K * d.E; add = r - 3 * K - K * d.E; }
         u16 *dst = vb.A1 + ((size_t)b * d.n1rows + r) * YLD;
-        for (int j = tid; j < D1; j += 128) dst[j] = (u16)(pi16(pi, off, (size_t)j * mul + add) % (uint32_t)Q);
+        const u16 *w1 = vb.W1 + (size_t)b * YLD;
+        for (int j = tid; j < D1; j += 128) dst[j] = (u16)gf_mul(pi16(pi, off, (size_t)j * mul + add) % (uint32_t)Q, w1[j]);
     } else {
         const int r = row - 2 * MK - d.n1rows;              // r = w*K*M + i*M + m
         const int w = r / (K * d.M), im = r % (K * d.M);
         u16 *dst = vb.A2 + ((size_t)b * d.n2rows + r) * VR2LD;
-        for (int j = tid; j < D2; j += 128) dst[j] = (u16)(pi16(pi, w ? L.o_ue : L.o_us, (size_t)j * K * d.M + im) % (uint32_t)Q);
+        const u16 *w2 = vb.W2 + (size_t)b * VR2LD;
+        for (int j = tid; j < D2; j += 128) dst[j] = (u16)gf_mul(pi16(pi, w ? L.o_ue : L.o_us, (size_t)j * K * d.M + im) % (uint32_t)Q, w2[j]);
     }
 }
 
 // Per-proof Lagrange matrices over the rest-party nodes x_k = rest[k] + 256 (barycentric form):
-//   LM1[t][k] = l_k^{x_0..x_406}(t), t = 0..406 (a target that is itself a node gives a unit row);
-//   LM2[t][k] = l_k^{x_0..x_812}(t), t = 0..255.
+//   l_k(t) = P(t) * w_k / (t - x_k): the GEMM operand holds only LM[t][k] = 1/(t - x_k); the weights w_k scale the
+//   gathered input rows (kv_gather) and P(t) scales the output columns (GemmArgs.colscale).  A target that is itself
+//   a node (t = x_h, only for t in 256..406) gets the row 1/w_h * delta_kh with P(t) = 1, i.e. the share y_h itself.
+//   LM1: t = 0..406 over x_0..x_406;  LM2: t = 0..255 over x_0..x_812.
 // The nodes are the integers of [256, hi] minus at most 150 "holes" (opened parties), so the O(n^2) products of the
 // barycentric weights and of P(t) = prod_m (t - x_m) collapse to factorials times a product over the holes:
 //   prod_{m != k} (x_k - x_m) = (x_k-256)! (hi-x_k)! (-1)^(hi-x_k) / prod_h (x_k - h)
@@ -266,6 +272,7 @@ __global__ void __launch_bounds__(256) kv_lagrange(VerifyBufs vb, const u16 *__r
             uint32_t v = gf_mul(gf_mul(num, ifact[xk - 256]), ifact[hi - xk]);
             if ((hi - xk) & 1) v = gf_sub(0, v);
             w[k] = (u16)v;
+            (pass ? vb.W2 + (size_t)b * VR2LD : vb.W1 + (size_t)b * YLD)[k] = (u16)v;
         }
         for (int t = tid; t < nt; t += 256) {
             uint32_t den = 1; int h = -1;
@@ -282,13 +289,14 @@ __global__ void __launch_bounds__(256) kv_lagrange(VerifyBufs vb, const u16 *__r
                 v = gf_mul(v, inv[den]);
             }
             P[t] = (u16)v; hit[t] = (int16_t)h;
+            (pass ? vb.PT2 + (size_t)b * 256 : vb.PT1 + (size_t)b * LM1_ROWS)[t] = (u16)(h >= 0 ? 1 : v);
         }
         __syncthreads();
         for (int idx = tid; idx < nt * n; idx += 256) {
             const int t = idx / n, k = idx % n;
             int32_t v;
-            if (hit[t] >= 0) v = (k == hit[t]);
-            else v = gf_center(gf_mul(gf_mul(P[t], w[k]), inv[gf_sub((uint32_t)t, x[k])]));
+            if (hit[t] >= 0) v = (k == hit[t]) ? gf_center(inv[w[k]]) : 0;
+            else v = gf_center(inv[gf_sub((uint32_t)t, x[k])]);
             out[(size_t)t * ld + k] = (int16_t)v;
         }
         __syncthreads();
@@ -500,8 +508,8 @@ static int verify_chunk_t(VerifyBufs &vb, const VerifyTables &vt, int B, const u
     }
     k_fs1<K><<<(B + 3) / 4, 128, 0, st>>>(vb.TCR, vb.PW, B); nl++;
     kv_eval_opened<K><<<B, 320, 0, st>>>(vb); nl++;
-    kv_gather<K><<<dim3(2 * MK + d.n1rows + d.n2rows, B), 128, 0, st>>>(vb, d_pi); nl++;
     kv_lagrange<<<B, 256, 0, st>>>(vb, vt.inv, vt.fact); nl++;
+    kv_gather<K><<<dim3(2 * MK + d.n1rows + d.n2rows, B), 128, 0, st>>>(vb, d_pi); nl++;
     GemmArgs g{};
     // beta/gamma reconstruction: ABG x R1
     g = GemmArgs{}; g.A = vb.ABG; g.Bt = vt.R1; g.C = vb.BS; g.lda = YLD; g.ldb = YLD; g.ldc = 256;
@@ -512,17 +520,19 @@ static int verify_chunk_t(VerifyBufs &vb, const VerifyTables &vt, int B, const u
     g = GemmArgs{}; g.A = vb.A1; g.Bt = vb.LM1; g.C = vb.YV; g.lda = YLD; g.ldb = YLD; g.ldc = YLD;
     g.a_batch = (long long)d.n1rows * YLD; g.b_batch = (long long)LM1_ROWS * YLD; g.c_batch = (long long)d.nyrows * YLD;
     g.mtotal = d.n1rows; g.ksteps = YLD / GE_BK; g.nvalid = D1; g.rpp = g.mtotal; g.half_last = 1;
+    g.colscale = vb.PT1; g.colscale_batch = LM1_ROWS;
     for (int o = 0; o < B; o += 32768) {
         GemmArgs h = g; const int nb = min(32768, B - o);
-        h.A += (size_t)o * g.a_batch; h.Bt += (size_t)o * g.b_batch; h.C += (size_t)o * g.c_batch;
+        h.A += (size_t)o * g.a_batch; h.Bt += (size_t)o * g.b_batch; h.C += (size_t)o * g.c_batch; h.colscale += (size_t)o * g.colscale_batch;
         nl += gf_gemm_launch<4, 128, 7>(h, 448, nb, st);      // 407 targets in four 112-column tiles (LM1 has 512 zero-padded rows)
     }
     g = GemmArgs{}; g.A = vb.A2; g.Bt = vb.LM2; g.C = vb.UZ; g.lda = VR2LD; g.ldb = VR2LD; g.ldc = 256;
     g.a_batch = (long long)d.n2rows * VR2LD; g.b_batch = (long long)256 * VR2LD; g.c_batch = (long long)d.n2rows * 256;
     g.mtotal = d.n2rows; g.ksteps = VR2LD / GE_BK; g.nvalid = 256; g.rpp = g.mtotal;
+    g.colscale = vb.PT2; g.colscale_batch = 256;
     for (int o = 0; o < B; o += 32768) {
         GemmArgs h = g; const int nb = min(32768, B - o);
-        h.A += (size_t)o * g.a_batch; h.Bt += (size_t)o * g.b_batch; h.C += (size_t)o * g.c_batch;
+        h.A += (size_t)o * g.a_batch; h.Bt += (size_t)o * g.b_batch; h.C += (size_t)o * g.c_batch; h.colscale += (size_t)o * g.colscale_batch;
         nl += gf_gemm_launch<4>(h, 256, nb, st);
     }
     kv_open<K><<<B, 128, 0, st>>>(vb); nl++;
