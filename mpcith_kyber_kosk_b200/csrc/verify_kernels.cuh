@@ -24,7 +24,7 @@ struct VerifyBufs {
     u16 *I = nullptr, *REST = nullptr, *I2 = nullptr, *REST2 = nullptr; int16_t *POS = nullptr;
     u16 *AH = nullptr, *TPK = nullptr, *PW = nullptr;
     u8 *TCR = nullptr, *VWR = nullptr;
-    u16 *CR = nullptr, *VR = nullptr, *OPV = nullptr, *UOP = nullptr;
+    u16 *CR = nullptr, *VR = nullptr, *OPV = nullptr;
     u16 *ABG = nullptr, *BS = nullptr, *A1 = nullptr, *YV = nullptr, *A2 = nullptr, *UZ = nullptr, *VSH = nullptr, *U2 = nullptr, *UR = nullptr;
     int16_t *LM1 = nullptr, *LM2 = nullptr;
     u16 *W1 = nullptr, *W2 = nullptr, *PT1 = nullptr, *PT2 = nullptr;   // barycentric weights per node / P(t) per target
@@ -46,7 +46,7 @@ KOSK_HD VDims make_vdims(int k)
 
 static inline void verify_free(VerifyBufs &v)
 {
-    void *p[] = {v.flags, v.I, v.REST, v.I2, v.REST2, v.POS, v.AH, v.TPK, v.PW, v.TCR, v.VWR, v.CR, v.VR, v.OPV, v.UOP,
+    void *p[] = {v.flags, v.I, v.REST, v.I2, v.REST2, v.POS, v.AH, v.TPK, v.PW, v.TCR, v.VWR, v.CR, v.VR, v.OPV,
                  v.ABG, v.BS, v.A1, v.YV, v.A2, v.UZ, v.VSH, v.U2, v.UR, v.LM1, v.LM2, v.W1, v.W2, v.PT1, v.PT2};
     for (void *q : p) if (q) cudaFree(q);
     v = VerifyBufs{};
@@ -59,7 +59,7 @@ static inline int verify_alloc(VerifyBufs &v, int k, int chunk)
     VA(v.flags, B * 4, 1); VA(v.I, B * NT * 2, 0); VA(v.REST, B * NR * 2, 0); VA(v.I2, B * NT * 2, 0); VA(v.REST2, B * NR * 2, 0); VA(v.POS, B * NP * 2, 0);
     VA(v.AH, B * k * k * 256 * 2, 0); VA(v.TPK, B * k * 256 * 2, 0); VA(v.PW, B * d.NA * d.F * 2, 0);
     VA(v.TCR, B * TREE_BYTES, 0); VA(v.VWR, B * TREE_BYTES, 0);
-    VA(v.CR, B * NT * d.crld * 2, 1); VA(v.VR, B * NT * d.vrld * 2, 1); VA(v.OPV, B * NT * OPLD * 2, 1); VA(v.UOP, B * NT * d.n2rows * 2, 1);
+    VA(v.CR, B * NT * d.crld * 2, 1); VA(v.VR, B * NT * d.vrld * 2, 1); VA(v.OPV, B * NT * OPLD * 2, 1);
     VA(v.ABG, B * 2 * MK * YLD * 2, 1); VA(v.BS, B * 2 * MK * 256 * 2, 0);
     VA(v.A1, B * d.n1rows * YLD * 2, 1); VA(v.YV, B * d.nyrows * YLD * 2, 1);
     VA(v.A2, B * d.n2rows * VR2LD * 2, 1); VA(v.UZ, B * d.n2rows * 256 * 2, 0);
