@@ -153,6 +153,15 @@ def run_b200(args):
     import numpy as np
     import torch
     import torch.distributed as dist
+    from mpcith_kyber_kosk_b200 import build as _build
+    if int(os.environ.get("LOCAL_RANK", "0")) == 0:
+        _build.build()                                     # no-op when libkosk_b200.so is up to date (it normally travels with the repo)
+    else:                                                  # other local ranks wait for rank 0's build, if one was needed
+        t_wait = time.time()
+        while _build.needs_build() and time.time() - t_wait < 600:
+            time.sleep(2)
+        if time.time() - t_wait > 1:
+            time.sleep(3)
     from mpcith_kyber_kosk_b200 import KoskContext
     from mpcith_kyber_kosk_b200.sharding import seeds_for_range
 
