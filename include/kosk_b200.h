@@ -89,6 +89,32 @@ int kosk_b200_pool_create(kosk_b200_ctx *ctx, size_t n, const uint8_t *seeds, ko
 int kosk_b200_pool_prove(kosk_b200_pool *pool, uint8_t *pk, uint8_t *sk, uint8_t *pi);
 void kosk_b200_pool_destroy(kosk_b200_pool *pool);
 
+/* Struct-level API: the reference's lower-level entry points, used directly by main.cpp:16-59, on byte
+ * images of the reference's own structs (x86-64 layout, no padding):
+ *   inst  = mlwe_inst          (mlwe_prover.hpp:34-37): int16 A[K][K][256] | t[K][256] | s[K][256] | e[K][256]
+ *   rand  = mpcith_randomness  (mlwe_prover.hpp:39-44): u16 f[F][256] | NTT_f[F][256] | share_vec f_shares[F] | NTT_f_shares[F]
+ *   eta   = mpcith_range_proof (mlwe_prover.hpp:46-49): share_vec s_eta_shares[K][E] | e_eta_shares[K][E]
+ *   share_vec (ss.hpp:33-37)   = size_t len | u16 share_x[1454] | u16 share_y[1454]; len is written as 0 (the reference leaves
+ *                                it uninitialised), share_x[p] = p + 256
+ *   pi    = mpcith_proof       (mlwe_prover.hpp:57-75) = the proof bytes; encode/decode_mpcith_proof are memcpy
+ * Randomness: the reference draws from one global randombytes(); here the context holds the KOSK counter-mode DRBG state
+ * (seed, number of calls made so far) and every function below consumes exactly the calls its reference counterpart makes
+ * (prepare_randomness 3F, prepare_range_proof 2KE, kyber_keygen 1, prove 3K + 4*eta*K), so any call order gives the bytes the
+ * reference gives under the same randombytes definition.  kyber_verifiable_keygen's own order is keygen, prepare_randomness,
+ * prepare_range_proof, prove (kosk.cpp:72-86).  prove() assumes rand / eta were produced by the two prepare functions (the
+ * clear f / NTT_f vectors are consistent with their sharings, the eta sharings hide the constants -eta..eta).
+ * Single instance per call, host buffers, synchronous. */
+size_t kosk_b200_inst_bytes(int kyber_k);
+size_t kosk_b200_randomness_bytes(int kyber_k);
+size_t kosk_b200_range_proof_bytes(int kyber_k);
+int kosk_b200_rng_reset(kosk_b200_ctx *ctx, const uint8_t seed[32]);      /* seed the DRBG, call counter = 0 */
+uint32_t kosk_b200_rng_calls(const kosk_b200_ctx *ctx);
+int kosk_b200_prepare_randomness(kosk_b200_ctx *ctx, void *rand);          /* mlwe_prover.cpp:4-39 */
+int kosk_b200_prepare_range_proof(kosk_b200_ctx *ctx, void *eta);          /* mlwe_prover.cpp:41-59 */
+int kosk_b200_keygen(kosk_b200_ctx *ctx, uint8_t *pk, uint8_t *sk, void *inst /* may be NULL */);   /* kosk.cpp:4-70 */
+int kosk_b200_prove(kosk_b200_ctx *ctx, uint8_t *pi, const void *inst, const void *rand, const void *eta);   /* mlwe_prover.cpp:81-538 */
+int kosk_b200_verify(kosk_b200_ctx *ctx, const uint8_t *pi, const void *inst);   /* mlwe_verifier.cpp:4-686; 1 accept, 0 reject, <0 error */
+
 /* Components (BASELINE config 5 microbenches, kernel-level parity tests).
  * share_eval: recompute_share_secrets_ddeg (ss.cpp:76-99) on n rows: y[n][407] -> shares[n][1454]. Host buffers.
  * sha3_256_rows: n independent SHA3-256 over rows of `len` bytes (len even): in[n][len] -> out[n][32].

@@ -17,6 +17,8 @@ EXPORTS = [
     "kosk_b200_prove_batch", "kosk_b200_prove_batch_async", "kosk_b200_verify_batch", "kosk_b200_prove_batch_device", "kosk_b200_verify_batch_device",
     "kosk_b200_share_eval", "kosk_b200_sha3_256_rows", "kosk_b200_ntt_rows", "kosk_b200_share_eval_device",
     "kosk_b200_kernel_launches", "kosk_b200_debug_fetch", "kosk_b200_debug_trace", "kosk_b200_sync",
+    "kosk_b200_inst_bytes", "kosk_b200_randomness_bytes", "kosk_b200_range_proof_bytes", "kosk_b200_rng_reset", "kosk_b200_rng_calls",
+    "kosk_b200_prepare_randomness", "kosk_b200_prepare_range_proof", "kosk_b200_keygen", "kosk_b200_prove", "kosk_b200_verify",
     "kosk_b200_pool_create", "kosk_b200_pool_prove", "kosk_b200_pool_destroy", "kosk_b200_set_strict", "kosk_b200_set_profiling", "kosk_b200_phase_times", "kosk_b200_int_peak",
 ]
 
@@ -37,7 +39,7 @@ def load_library(path=None):
         raise KoskError(f"{path} not found: build it with `python -m mpcith_kyber_kosk_b200.build` (no CPU fallback exists)")
     lib = ctypes.CDLL(path)
     vp, sz, i32, u8p = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p
-    for n in ("kosk_b200_pk_bytes", "kosk_b200_sk_bytes", "kosk_b200_proof_bytes"):
+    for n in ("kosk_b200_pk_bytes", "kosk_b200_sk_bytes", "kosk_b200_proof_bytes", "kosk_b200_inst_bytes", "kosk_b200_randomness_bytes", "kosk_b200_range_proof_bytes"):
         getattr(lib, n).restype = sz
         getattr(lib, n).argtypes = [i32]
     lib.kosk_b200_last_error.restype = ctypes.c_char_p
@@ -69,6 +71,14 @@ def load_library(path=None):
     lib.kosk_b200_pool_prove.argtypes = [vp, u8p, u8p, u8p]
     lib.kosk_b200_pool_destroy.argtypes = [vp]
     lib.kosk_b200_pool_destroy.restype = None
+    lib.kosk_b200_rng_reset.argtypes = [vp, u8p]
+    lib.kosk_b200_rng_calls.argtypes = [vp]
+    lib.kosk_b200_rng_calls.restype = ctypes.c_uint32
+    lib.kosk_b200_prepare_randomness.argtypes = [vp, u8p]
+    lib.kosk_b200_prepare_range_proof.argtypes = [vp, u8p]
+    lib.kosk_b200_keygen.argtypes = [vp, u8p, u8p, u8p]
+    lib.kosk_b200_prove.argtypes = [vp, u8p, u8p, u8p, u8p]
+    lib.kosk_b200_verify.argtypes = [vp, u8p, u8p]
     lib.kosk_b200_phase_times.argtypes = [vp, u8p, u8p, i32, i32]
     lib.kosk_b200_int_peak.argtypes = [vp, u8p]
     if path == LIB_PATH:
@@ -131,6 +141,47 @@ class KoskContext:
         if a.size != self.proof_bytes or b.size != self.pk_bytes:
             raise KoskError("bad proof or pk length")
         return self._check(self.lib.kosk_b200_kosk_verify(self._h, _ptr(a), _ptr(b)), "kosk_verify") == 1
+
+    # ---- struct-level API (reference mlwe_prover.hpp:77-99, mlwe_verifier.hpp:14-15, kosk.hpp:17-18) ----
+    # Structs travel as byte images with the reference's layout (include/kosk_b200.h); the context holds the DRBG state.
+    def rng_reset(self, seed):
+        s = np.frombuffer(bytes(seed), dtype=np.uint8)
+        self._check(self.lib.kosk_b200_rng_reset(self._h, _ptr(s)), "rng_reset")
+
+    def rng_calls(self):
+        return int(self.lib.kosk_b200_rng_calls(self._h))
+
+    def prepare_randomness(self):
+        out = np.empty(self.lib.kosk_b200_randomness_bytes(self.k), np.uint8)
+        self._check(self.lib.kosk_b200_prepare_randomness(self._h, _ptr(out)), "prepare_randomness")
+        return out
+
+    def prepare_range_proof(self):
+        out = np.empty(self.lib.kosk_b200_range_proof_bytes(self.k), np.uint8)
+        self._check(self.lib.kosk_b200_prepare_range_proof(self._h, _ptr(out)), "prepare_range_proof")
+        return out
+
+    def kyber_keygen(self):
+        """kyber_keygen (kosk.cpp:4-70): returns (pk, sk, mlwe_inst image)."""
+        pk, sk = np.empty(self.pk_bytes, np.uint8), np.empty(self.sk_bytes, np.uint8)
+        inst = np.empty(self.lib.kosk_b200_inst_bytes(self.k), np.uint8)
+        self._check(self.lib.kosk_b200_keygen(self._h, _ptr(pk), _ptr(sk), _ptr(inst)), "kyber_keygen")
+        return bytes(pk), bytes(sk), inst
+
+    def prove(self, inst, rand, eta):
+        inst, rand, eta = (np.ascontiguousarray(x, dtype=np.uint8) for x in (inst, rand, eta))
+        if (inst.size, rand.size, eta.size) != (self.lib.kosk_b200_inst_bytes(self.k), self.lib.kosk_b200_randomness_bytes(self.k), self.lib.kosk_b200_range_proof_bytes(self.k)):
+            raise KoskError("bad struct image length")
+        pi = np.empty(self.proof_bytes, np.uint8)
+        self._check(self.lib.kosk_b200_prove(self._h, _ptr(pi), _ptr(inst), _ptr(rand), _ptr(eta)), "prove")
+        return bytes(pi)
+
+    def verify(self, pi, inst):
+        a = np.frombuffer(bytes(pi), dtype=np.uint8)
+        inst = np.ascontiguousarray(inst, dtype=np.uint8)
+        if a.size != self.proof_bytes or inst.size != self.lib.kosk_b200_inst_bytes(self.k):
+            raise KoskError("bad proof or mlwe_inst length")
+        return self._check(self.lib.kosk_b200_verify(self._h, _ptr(a), _ptr(inst)), "verify") == 1
 
     # ---- batch, host buffers ----
     def prove_batch(self, seeds, out=None):

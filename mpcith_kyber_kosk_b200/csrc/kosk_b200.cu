@@ -45,7 +45,10 @@ static void h_lagrange(std::vector<uint16_t> &out, const std::vector<int> &nodes
     }
 }
 
-enum { PH_OFFLINE = 1, PH_ONLINE = 2 };
+enum { PH_OFFLINE = 1, PH_ONLINE = 2, PH_NOKEYGEN = 4 /* raw prove(): the instance comes from the caller */ };
+struct RawState;
+static RawState *raw_new();
+static void raw_delete(RawState *);
 enum { KOSK_PH_KEYGEN = 0, KOSK_PH_EXPAND, KOSK_PH_SHARE1, KOSK_PH_COMMIT, KOSK_PH_FS1, KOSK_PH_EVAL, KOSK_PH_OPEN, KOSK_PH_SHARE2,
        KOSK_PH_VIEW, KOSK_PH_FS2, KOSK_PH_ASSEMBLE, KOSK_PH_VERIFY, KOSK_NPHASE };
 
@@ -84,6 +87,7 @@ struct kosk_b200_ctx {
     // optional phase timing with CUDA events on the launching stream (bench.py roofline)
     bool prof = false;
     double phase_ms[KOSK_NPHASE] = {0}; uint64_t phase_calls[KOSK_NPHASE] = {0};
+    RawState *raw = nullptr;               // struct-level API (raw_api.cuh): DRBG state and staging buffers
 };
 
 static void prof_mark(kosk_b200_ctx *c, Lane &ln, int phase, cudaStream_t on = nullptr)
@@ -125,6 +129,7 @@ static int alloc_prove_bufs(ProveBufs &pb, const Slots &sl, int k, size_t B, boo
     PA(pb.I, B * NT * 2, 0); PA(pb.REST, B * NR * 2, 0);
     if (tensor) { PA(pb.YL0, B * sl.n2 * YLD, 1); PA(pb.YL1, B * sl.n2 * YLD, 1); }
 #undef PA
+    set_default_calls(pb, sl);
     return 0;
 }
 
@@ -146,6 +151,7 @@ static void ctx_free(kosk_b200_ctx *c)
         if (ln.st) cudaStreamDestroy(ln.st);
     }
     if (c->ev_start) cudaEventDestroy(c->ev_start);
+    raw_delete(c->raw);
     delete c;
 }
 
@@ -173,6 +179,7 @@ int kosk_b200_create_ex(kosk_b200_ctx **out, int k, int device, int max_chunk, i
     CU(cudaSetDevice(device));
     kosk_b200_ctx *c = new kosk_b200_ctx;
     c->k = k; c->device = device; c->sl = make_slots(k); c->L = make_layout(k);
+    c->raw = raw_new();
     c->chunk = max_chunk > 0 ? max_chunk : 1024;
     if (c->chunk > 16384) c->chunk = 16384;
     if (nlanes <= 0) nlanes = 2;
@@ -325,7 +332,7 @@ static int prove_chunk(kosk_b200_ctx *c, Lane &ln, const ProveBufs &bufs, int B,
     // after the other (co-running them was measured to slow the latency-bound FS sponges 3x), while the D2H copy of a
     // finished sub-batch overlaps the kernels of the next one on the other lane.
     if (c->last_computed && c->last_computed != ln.computed) CU(cudaStreamWaitEvent(st, c->last_computed, 0));
-    if (on) {
+    if (on && !(phases & PH_NOKEYGEN)) {
         prof_mark(c, ln, KOSK_PH_KEYGEN);
         k_keygen<K><<<B, 128, 0, st>>>(pb); c->launches++;
     }
@@ -744,6 +751,10 @@ int kosk_b200_phase_times(kosk_b200_ctx *c, double *ms, uint64_t *calls, int n, 
 }
 
 }  // extern "C"
+
+#include "raw_api.cuh"
+static RawState *raw_new() { return new RawState; }
+static void raw_delete(RawState *r) { if (r) { raw_free(*r); delete r; } }
 
 // ---- integer-pipe issue-rate microbenchmarks (roofline denominators; MEASURED_PEAKS.json has no integer entry) ----
 template <int MODE>

@@ -26,7 +26,16 @@ struct ProveBufs {
     int8_t *YL0, *YL1; // experimental tensor path only: 7-bit limb planes of Y, [B][n2][YLD] int8
     u8 *pk, *sk, *pi;  // outputs
     int B;
+    // randombytes() call numbers (KOSK counter-mode DRBG) of the first call made by kyber_keygen, prepare_randomness,
+    // prepare_range_proof and prove.  kyber_verifiable_keygen order (kosk.cpp:72-86): 0, 1, 1+3F, c_se0;
+    // the struct-level API (raw_api.cuh) numbers them by the caller's own call order, as the reference's global RNG would.
+    int cb_key, cb_rand, cb_eta, cb_prove;
+    int tails_mask;    // k_tails: 1 = f / NTT_f sharings, 2 = eta sharings, 4 = sharings made inside prove() (s, e, z_j, A s)
 };
+__host__ __device__ inline void set_default_calls(ProveBufs &pb, const Slots &sl)
+{
+    pb.cb_key = 0; pb.cb_rand = sl.c_seed0; pb.cb_eta = sl.c_eta0; pb.cb_prove = sl.c_se0; pb.tails_mask = 7;
+}
 
 __device__ __forceinline__ u16 *yrow(const ProveBufs &pb, const Slots &sl, int b, int slot) { return pb.Y + ((size_t)b * sl.n2 + slot) * YLD; }
 __device__ __forceinline__ u16 *plane(const ProveBufs &pb, const Slots &sl, int b, int slot) { return pb.SH + ((size_t)b * sl.nslot + slot) * SLD + SOFF; }
@@ -75,7 +84,7 @@ __global__ void __launch_bounds__(128) k_keygen(ProveBufs pb)
         uint64_t sd[4], a[25];
         const uint64_t *gs = reinterpret_cast<const uint64_t *>(pb.seeds + 32 * (size_t)b);
         for (int i = 0; i < 4; i++) sd[i] = gs[i];
-        drbg_begin(a, sd, 0);                       // randombytes(buf, 64): only bytes 0..31 are used (kosk.cpp:12-14)
+        drbg_begin(a, sd, pb.cb_key);               // randombytes(buf, 64): only bytes 0..31 are used (kosk.cpp:12-14)
         uint64_t c0 = a[0], c1 = a[1], c2 = a[2], c3 = a[3];
         keccak_zero(a);                             // sha3_512(coins || K): rate 72
         a[0] = c0; a[1] = c1; a[2] = c2; a[3] = c3; a[4] = (uint64_t)K | (0x06ULL << 8); a[8] = 0x8000000000000000ULL;
@@ -181,7 +190,7 @@ __global__ void __launch_bounds__(64) k_expand_f(ProveBufs pb)
     const uint64_t *gs = reinterpret_cast<const uint64_t *>(pb.seeds + 32 * (size_t)b);
 #pragma unroll
     for (int w = 0; w < 4; w++) sd[w] = gs[w];
-    drbg_begin(a, sd, sl.c_seed0 + i);
+    drbg_begin(a, sd, pb.cb_rand + i);
     uint64_t key[4] = {a[0], a[1], a[2], a[3]};
     prf_begin(a, key, (u8)i);
     u16 *dst = yrow(pb, sl, b, sl.f0 + i);
@@ -221,18 +230,22 @@ __global__ void __launch_bounds__(64) k_tails(ProveBufs pb)
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= pb.B * nfresh) return;
     const int b = gid / nfresh, idx = gid % nfresh;
-    int slot, call;
+    // call numbers relative to the first call of prepare_randomness (F seeds, then f_i / NTT_f_i alternating,
+    // mlwe_prover.cpp:8-38), prepare_range_proof (s / e alternating, :41-59) and prove (s_i / e_i alternating :89-101,
+    // [A s]_i :292-323, z chains :338-392)
+    int slot, call, group;
     if (idx < sl.n1) {
         slot = idx;
-        if (slot < sl.Tf0) call = sl.c_f0 + 2 * (slot - sl.f0);
-        else if (slot < sl.seta0) call = sl.c_f0 + 2 * (slot - sl.Tf0) + 1;
-        else if (slot < sl.eeta0) call = sl.c_eta0 + 2 * (slot - sl.seta0);
-        else if (slot < sl.s0) call = sl.c_eta0 + 2 * (slot - sl.eeta0) + 1;
-        else if (slot < sl.e0) call = sl.c_se0 + 2 * (slot - sl.s0);
-        else if (slot < sl.zs0) call = sl.c_se0 + 2 * (slot - sl.e0) + 1;
-        else if (slot < sl.ze0) call = sl.c_z0 + 2 * (slot - sl.zs0);
-        else call = sl.c_z0 + 2 * (slot - sl.ze0) + 1;
-    } else { slot = sl.As0 + (idx - sl.n1); call = sl.c_As0 + (idx - sl.n1); }
+        if (slot < sl.Tf0) { call = pb.cb_rand + sl.F + 2 * (slot - sl.f0); group = 1; }
+        else if (slot < sl.seta0) { call = pb.cb_rand + sl.F + 2 * (slot - sl.Tf0) + 1; group = 1; }
+        else if (slot < sl.eeta0) { call = pb.cb_eta + 2 * (slot - sl.seta0); group = 2; }
+        else if (slot < sl.s0) { call = pb.cb_eta + 2 * (slot - sl.eeta0) + 1; group = 2; }
+        else if (slot < sl.e0) { call = pb.cb_prove + 2 * (slot - sl.s0); group = 4; }
+        else if (slot < sl.zs0) { call = pb.cb_prove + 2 * (slot - sl.e0) + 1; group = 4; }
+        else if (slot < sl.ze0) { call = pb.cb_prove + 3 * K + 2 * (slot - sl.zs0); group = 4; }
+        else { call = pb.cb_prove + 3 * K + 2 * (slot - sl.ze0) + 1; group = 4; }
+    } else { slot = sl.As0 + (idx - sl.n1); call = pb.cb_prove + 2 * K + (idx - sl.n1); group = 4; }
+    if (!(pb.tails_mask & group)) return;
     uint64_t sd[4], a[25];
     const uint64_t *gs = reinterpret_cast<const uint64_t *>(pb.seeds + 32 * (size_t)b);
 #pragma unroll

@@ -30,6 +30,7 @@ struct VerifyBufs {
     u16 *W1 = nullptr, *W2 = nullptr, *PT1 = nullptr, *PT2 = nullptr;   // barycentric weights per node / P(t) per target
     int k = 0, chunk = 0;
     int strict = 0;   // hardened decoding: off by default = the reference's accept set
+    int raw_inst = 0; // verify() on a caller-supplied mlwe_inst (raw_api.cuh): AH / TPK are preloaded, pk is not parsed
 };
 
 struct VDims {
@@ -109,12 +110,12 @@ __global__ void __launch_bounds__(128) kv_setup(VerifyBufs vb, const u8 *__restr
     { int j = base[tid];
       for (int p = tid * PER; p < min(NP, tid * PER + PER); p++) if (cnt[p] == 0) { vb.REST[(size_t)b * NR + j] = (u16)p; vb.POS[(size_t)b * NP + p] = (int16_t)j; j++; } }
     // t from pk: polyvec_frombytes (kyber/poly.c:151-158), raw 12-bit values
-    for (int i = 0; i < K; i++) {
+    if (!vb.raw_inst) for (int i = 0; i < K; i++) {
         const u8 *a = pk + 384 * i + 3 * tid;
         vb.TPK[((size_t)b * K + i) * 256 + 2 * tid] = (u16)((a[0] | ((u16)a[1] << 8)) & 0xFFF);
         vb.TPK[((size_t)b * K + i) * 256 + 2 * tid + 1] = (u16)(((a[1] >> 4) | ((u16)a[2] << 4)) & 0xFFF);
     }
-    if (tid < K * K) {      // gen_matrix (indcpa.c:168-193)
+    if (tid < K * K && !vb.raw_inst) {      // gen_matrix (indcpa.c:168-193)
         const int i = tid / K, j = tid % K;
         ByteSponge sp; sp.init(168);
         sp.absorb(pk + 384 * K, 32);

@@ -9,7 +9,8 @@
 #include <time.h>
 
 namespace {
-struct job { int op; const uint8_t *seed; int mode; uint8_t *pk, *sk, *pi; const uint8_t *cpi, *cpk; int ok; };
+struct job { int op; const uint8_t *seed; int mode; uint8_t *pk, *sk, *pi; const uint8_t *cpi, *cpk; int ok;
+             uint8_t *rand_img, *eta_img, *inst_img; const uint8_t *cinst; };
 void *run(void *p)
 {
     job *j = (job *)p;
@@ -20,8 +21,27 @@ void *run(void *p)
         memcpy(j->pk, kp->pk, KYBER_PUBLICKEYBYTES);
         memcpy(j->sk, kp->sk, KYBER_SECRETKEYBYTES);
         delete kp;
-    } else {
+    } else if (j->op == 1) {
         j->ok = kyber_kosk_verify(j->cpi, j->cpk) ? 1 : 0;
+    } else if (j->op == 2) {          /* the struct-level sequence of main.cpp:16-59 */
+        kosk_rng_reset(j->seed, j->mode);
+        mpcith_randomness *rnd = new mpcith_randomness; mpcith_range_proof *eta = new mpcith_range_proof;
+        mlwe_inst *inst = new mlwe_inst; kyber_keypair *kp = new kyber_keypair; mpcith_proof *pi = new mpcith_proof;
+        memset(rnd, 0, sizeof *rnd); memset(eta, 0, sizeof *eta);      /* share_vec.len is never written by the reference */
+        prepare_randomness(rnd);
+        prepare_range_proof(eta);
+        kyber_keygen(kp, inst);
+        prove(pi, inst, rnd, eta);
+        j->ok = verify(pi, inst) ? 1 : 0;
+        memcpy(j->rand_img, rnd, sizeof *rnd); memcpy(j->eta_img, eta, sizeof *eta); memcpy(j->inst_img, inst, sizeof *inst);
+        memcpy(j->pk, kp->pk, KYBER_PUBLICKEYBYTES); memcpy(j->sk, kp->sk, KYBER_SECRETKEYBYTES);
+        encode_mpcith_proof(j->pi, pi);
+        delete rnd; delete eta; delete inst; delete kp; delete pi;
+    } else {                          /* verify() on a raw instance */
+        mpcith_proof *pi = new mpcith_proof; mlwe_inst *inst = new mlwe_inst;
+        decode_mpcith_proof(pi, j->cpi); memcpy(inst, j->cinst, sizeof *inst);
+        j->ok = verify(pi, inst) ? 1 : 0;
+        delete pi; delete inst;
     }
     return 0;
 }
@@ -39,11 +59,25 @@ size_t ref_sk_bytes(void) { return KYBER_SECRETKEYBYTES; }
 size_t ref_proof_bytes(void) { return MPCITH_PROOF_SIZE; }
 void ref_verifiable_keygen(const uint8_t seed[32], int rng_mode, uint8_t *pk, uint8_t *sk, uint8_t *pi)
 {
-    job j = {0, seed, rng_mode, pk, sk, pi, 0, 0, 0}; big_stack(&j);
+    job j = {0, seed, rng_mode, pk, sk, pi, 0, 0, 0, 0, 0, 0, 0}; big_stack(&j);
 }
 int ref_kosk_verify(const uint8_t *pi, const uint8_t *pk)
 {
-    job j = {1, 0, 0, 0, 0, 0, pi, pk, 0}; big_stack(&j); return j.ok;
+    job j = {1, 0, 0, 0, 0, 0, pi, pk, 0, 0, 0, 0, 0}; big_stack(&j); return j.ok;
 }
 uint32_t ref_rng_calls(void) { return 0; }
+size_t ref_inst_bytes(void) { return sizeof(mlwe_inst); }
+size_t ref_randomness_bytes(void) { return sizeof(mpcith_randomness); }
+size_t ref_range_proof_bytes(void) { return sizeof(mpcith_range_proof); }
+size_t ref_share_vec_bytes(void) { return sizeof(share_vec); }
+/* main.cpp:16-59 in the reference's own call order: prepare_randomness, prepare_range_proof, kyber_keygen, prove, verify */
+int ref_struct_sequence(const uint8_t seed[32], int rng_mode, uint8_t *rand_img, uint8_t *eta_img, uint8_t *inst_img,
+                        uint8_t *pk, uint8_t *sk, uint8_t *pi)
+{
+    job j = {2, seed, rng_mode, pk, sk, pi, 0, 0, 0, rand_img, eta_img, inst_img, 0}; big_stack(&j); return j.ok;
+}
+int ref_verify_struct(const uint8_t *pi, const uint8_t *inst_img)
+{
+    job j = {3, 0, 0, 0, 0, 0, pi, 0, 0, 0, 0, 0, inst_img}; big_stack(&j); return j.ok;
+}
 }

@@ -119,6 +119,10 @@ def ref(k):
             lib.ref_verifiable_keygen.argtypes = [vp, ctypes.c_int, vp, vp, vp]
             lib.ref_verifiable_keygen.restype = None
             lib.ref_kosk_verify.argtypes = [vp, vp]
+            for n in ("ref_inst_bytes", "ref_randomness_bytes", "ref_range_proof_bytes", "ref_share_vec_bytes"):
+                getattr(lib, n).restype = ctypes.c_size_t
+            lib.ref_struct_sequence.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, vp, vp]
+            lib.ref_verify_struct.argtypes = [vp, vp]
             _refs[k] = lib
     return _refs[k]
 
@@ -135,6 +139,44 @@ def ref_verify(k, pi, pk):
     pi = np.ascontiguousarray(pi, dtype=np.uint8)
     pk = np.ascontiguousarray(pk, dtype=np.uint8)
     return ref(k).ref_kosk_verify(_p(pi), _p(pk)) == 1
+
+
+# ---- struct-level API (reference main.cpp:16-59): byte images of mpcith_randomness / mpcith_range_proof / mlwe_inst ----
+SHARE_VEC_BYTES = 8 + 4 * 1454
+
+
+def struct_sizes(k):
+    F, E = 70 + 2 * k + 1, 2 * (3 if k == 2 else 2) + 1
+    return {"inst": (k * k + 3 * k) * 512, "rand": F * (1024 + 2 * SHARE_VEC_BYTES), "eta": 2 * k * E * SHARE_VEC_BYTES,
+            "rand_shares_off": 1024 * F, "F": F, "E": E}
+
+
+def mask_share_vec_len(img, first_off):
+    """share_vec.len (ss.hpp:34) is never written by the reference: zero it before comparing images."""
+    img = np.array(img, dtype=np.uint8, copy=True)
+    for o in range(first_off, img.size, SHARE_VEC_BYTES):
+        img[o:o + 8] = 0
+    return img
+
+
+def ref_struct_sequence(k, seed, rng_mode=0):
+    """prepare_randomness, prepare_range_proof, kyber_keygen, prove, verify of the unmodified reference, in main.cpp's order."""
+    L, S = layout(k), struct_sizes(k)
+    lib = ref(k)
+    assert (lib.ref_inst_bytes(), lib.ref_randomness_bytes(), lib.ref_range_proof_bytes(), lib.ref_share_vec_bytes()) == \
+        (S["inst"], S["rand"], S["eta"], SHARE_VEC_BYTES)
+    seed = np.frombuffer(bytes(seed), dtype=np.uint8).copy()
+    rnd, eta, inst = np.zeros(S["rand"], np.uint8), np.zeros(S["eta"], np.uint8), np.zeros(S["inst"], np.uint8)
+    pk, sk, pi = np.zeros(L.pk_bytes, np.uint8), np.zeros(L.sk_bytes, np.uint8), np.zeros(L.proof_bytes, np.uint8)
+    ok = lib.ref_struct_sequence(_p(seed), rng_mode, _p(rnd), _p(eta), _p(inst), _p(pk), _p(sk), _p(pi))
+    return {"rand": mask_share_vec_len(rnd, S["rand_shares_off"]), "eta": mask_share_vec_len(eta, 0), "inst": inst,
+            "pk": pk, "sk": sk, "pi": pi, "ok": ok == 1}
+
+
+def ref_verify_struct(k, pi, inst):
+    pi = np.frombuffer(bytes(pi), dtype=np.uint8).copy()
+    inst = np.ascontiguousarray(inst, dtype=np.uint8)
+    return ref(k).ref_verify_struct(_p(pi), _p(inst)) == 1
 
 
 def seed_of(i, tag=b"kosk-b200"):

@@ -72,3 +72,16 @@ def test_dropin_header_compiles_like_the_reference_api(built_lib, tmp_path):
         subprocess.run(["g++", "-std=c++11", f"-DKYBER_K={k}", "-I" + os.path.join(ROOT, "include"), str(src), "-L" + libdir,
                         "-lkosk_b200", "-Wl,-rpath," + libdir, "-o", str(exe)], check=True)
         assert subprocess.run([str(exe)]).returncode == 0
+
+
+def test_struct_image_sizes_match_reference_structs(built_lib):
+    """kosk_b200_{inst,randomness,range_proof}_bytes == sizeof(mlwe_inst / mpcith_randomness / mpcith_range_proof)."""
+    import oracle_lib as O
+    lib = pkg.load_library()
+    for k in (2, 3, 4):
+        S = O.struct_sizes(k)
+        assert (lib.kosk_b200_inst_bytes(k), lib.kosk_b200_randomness_bytes(k), lib.kosk_b200_range_proof_bytes(k)) == (S["inst"], S["rand"], S["eta"])
+        r = O.ref(k)
+        if r is not None:      # the compiler's own sizeof of the reference structs
+            assert (r.ref_inst_bytes(), r.ref_randomness_bytes(), r.ref_range_proof_bytes(), r.ref_share_vec_bytes()) == (S["inst"], S["rand"], S["eta"], O.SHARE_VEC_BYTES)
+    assert lib.kosk_b200_inst_bytes(9) == 0

@@ -360,3 +360,68 @@ def test_unfused_path_large_chunk_k3(ctxs):
     for i in (0, 159):
         opk, osk, opi = O.oracle_prove(3, seeds[i])
         assert (pi[i] == opi).all() and (pk[i] == opk).all()
+
+
+# ---------------- struct-level API (reference main.cpp:16-59) ----------------
+STRUCT_GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "kosk_struct_golden.json")))
+
+
+def _struct_sequence(ctx, seed):
+    ctx.rng_reset(seed)
+    rand = ctx.prepare_randomness()
+    eta = ctx.prepare_range_proof()
+    pk, sk, inst = ctx.kyber_keygen()
+    pi = ctx.prove(inst, rand, eta)
+    return {"rand": rand, "eta": eta, "inst": inst, "pk": pk, "sk": sk, "pi": pi}
+
+
+@pytest.mark.parametrize("case", STRUCT_GOLDEN["cases"], ids=lambda c: f"k{c['k']}s{c['seed_index']}")
+def test_struct_sequence_matches_reference_golden(ctxs, case):
+    """prepare_randomness, prepare_range_proof, kyber_keygen, prove in main.cpp's order: every struct image equals the reference's."""
+    k = case["k"]
+    ctx = ctxs(k)
+    got = _struct_sequence(ctx, bytes.fromhex(case["seed"]))
+    for n in ("inst", "pk", "sk", "rand", "eta", "pi"):
+        assert hashlib.sha256(bytes(got[n])).hexdigest() == case[n + "_sha256"], n
+    S = O.struct_sizes(k)
+    assert ctx.rng_calls() == 3 * S["F"] + 2 * k * S["E"] + 1 + 3 * k + 4 * (3 if k == 2 else 2) * k
+    assert ctx.verify(got["pi"], got["inst"]) is True
+    bad = bytearray(got["pi"]); bad[0] ^= 1           # an opened party's f share (hashed into its commitment)
+    assert ctx.verify(bytes(bad), got["inst"]) is False
+    inst = got["inst"].copy(); inst[(k * k) * 512 + 10] ^= 1          # one coefficient of t
+    assert ctx.verify(got["pi"], inst) is False
+
+
+@pytest.mark.parametrize("k", [2, 3, 4])
+def test_struct_sequence_against_live_reference(ctxs, k):
+    if O.ref(k) is None:
+        pytest.skip("oracle/_ref not built on this box")
+    seed = O.seed_of(77 + k)
+    ctx = ctxs(k)
+    got = _struct_sequence(ctx, seed)
+    want = O.ref_struct_sequence(k, seed)
+    assert want["ok"]
+    for n in ("inst", "pk", "sk", "rand", "eta", "pi"):
+        assert bytes(got[n]) == bytes(want[n]), n
+    assert O.ref_verify_struct(k, got["pi"], got["inst"]) is True       # the reference's verify() accepts the GPU proof
+    assert ctx.verify(want["pi"], want["inst"]) is True                 # and the GPU verify() accepts the reference's
+
+
+@pytest.mark.parametrize("k", [2, 3, 4])
+def test_struct_calls_in_keygen_order_equal_verifiable_keygen(ctxs, k):
+    """kosk.cpp:72-86 is keygen, prepare_randomness, prepare_range_proof, prove: the same four calls must give the same bytes."""
+    ctx = ctxs(k)
+    seed = O.seed_of(300 + k)
+    pk0, sk0, pi0 = ctx.verifiable_keygen(seed)
+    ctx.rng_reset(seed)
+    pk, sk, inst = ctx.kyber_keygen()
+    rand = ctx.prepare_randomness()
+    eta = ctx.prepare_range_proof()
+    pi = ctx.prove(inst, rand, eta)
+    assert (pk, sk, pi) == (pk0, sk0, pi0)
+    assert ctx.kosk_verify(pi, pk) is True and ctx.verify(pi, inst) is True
+    # preprocessing is key-independent (main.cpp:18-31): the same rand/eta prove a second, different key
+    pk2, sk2, inst2 = ctx.kyber_keygen()
+    assert pk2 != pk
+    pi2 = ctx.prove(inst2, rand, eta)
+    assert ctx.kosk_verify(pi2, pk2) is True and ctx.kosk_verify(pi2, pk) is False

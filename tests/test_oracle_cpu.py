@@ -137,3 +137,22 @@ def test_oracle_matches_reference_live(k):
     for x, y in zip(a, b):
         assert (x == y).all()
     assert O.ref_verify(k, a[2], a[0]) and O.oracle_verify(k, a[2], a[0])
+
+
+def test_struct_golden_is_what_the_reference_produces():
+    """tests/golden/kosk_struct_golden.json pins the struct-level sequence (main.cpp:16-59) of the unmodified reference."""
+    import hashlib
+    import json
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "kosk_struct_golden.json")))
+    assert len(g["cases"]) == 6 and all(c["verify"] for c in g["cases"])
+    case = g["cases"][0]
+    if O.ref(case["k"]) is None:
+        pytest.skip("oracle/_ref not built (no /root/reference on this box)")
+    r = O.ref_struct_sequence(case["k"], bytes.fromhex(case["seed"]))
+    assert r["ok"]
+    for n in ("rand", "eta", "inst", "pk", "sk", "pi"):
+        assert hashlib.sha256(bytes(r[n])).hexdigest() == case[n + "_sha256"], n
+    # the struct-level proof differs from kyber_verifiable_keygen's for the same seed only through the call order
+    pk, sk, pi = O.ref_prove(case["k"], bytes.fromhex(case["seed"]))
+    assert bytes(pk) != bytes(r["pk"])
+    assert O.ref_verify_struct(case["k"], r["pi"], r["inst"])
