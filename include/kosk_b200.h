@@ -115,6 +115,21 @@ int kosk_b200_keygen(kosk_b200_ctx *ctx, uint8_t *pk, uint8_t *sk, void *inst /*
 int kosk_b200_prove(kosk_b200_ctx *ctx, uint8_t *pi, const void *inst, const void *rand, const void *eta);   /* mlwe_prover.cpp:81-538 */
 int kosk_b200_verify(kosk_b200_ctx *ctx, const uint8_t *pi, const void *inst);   /* mlwe_verifier.cpp:4-686; 1 accept, 0 reject, <0 error */
 
+/* Kyber KEM on the keys this library generates (the step after keygen in main.cpp:98-113).
+ * ct_bytes = KYBER_CIPHERTEXTBYTES (kyber/params.h:53): 768 / 1088 / 1568; shared secrets are KYBER_SSBYTES = 32 bytes.
+ *   kem_enc_derand_batch: crypto_kem_enc_derand (kyber/kem.c:76-97) for n independent (pk, coins) pairs, coins[n][32]
+ *   kem_dec_batch:        crypto_kem_dec (kyber/kem.c:139-169), implicit rejection included
+ *   kem_enc / kem_dec:    the reference's single calls; kem_enc draws its 32 coins as the next randombytes() call of the
+ *                         context DRBG (kosk_b200_rng_reset), as crypto_kem_enc does from the global RNG (kem.c:114-122)
+ * Host buffers, synchronous; the *_device forms take device pointers and enqueue on `stream`. */
+size_t kosk_b200_ct_bytes(int kyber_k);
+int kosk_b200_kem_enc_derand_batch(kosk_b200_ctx *ctx, size_t n, const uint8_t *pk, const uint8_t *coins, uint8_t *ct, uint8_t *ss);
+int kosk_b200_kem_dec_batch(kosk_b200_ctx *ctx, size_t n, const uint8_t *ct, const uint8_t *sk, uint8_t *ss);
+int kosk_b200_kem_enc_derand_batch_device(kosk_b200_ctx *ctx, size_t n, const uint8_t *d_pk, const uint8_t *d_coins, uint8_t *d_ct, uint8_t *d_ss, void *stream);
+int kosk_b200_kem_dec_batch_device(kosk_b200_ctx *ctx, size_t n, const uint8_t *d_ct, const uint8_t *d_sk, uint8_t *d_ss, void *stream);
+int kosk_b200_kem_enc(kosk_b200_ctx *ctx, uint8_t *ct, uint8_t *ss, const uint8_t *pk);
+int kosk_b200_kem_dec(kosk_b200_ctx *ctx, uint8_t *ss, const uint8_t *ct, const uint8_t *sk);
+
 /* Components (BASELINE config 5 microbenches, kernel-level parity tests).
  * share_eval: recompute_share_secrets_ddeg (ss.cpp:76-99) on n rows: y[n][407] -> shares[n][1454]. Host buffers.
  * sha3_256_rows: n independent SHA3-256 over rows of `len` bytes (len even): in[n][len] -> out[n][32].

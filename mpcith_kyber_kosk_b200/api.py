@@ -19,6 +19,8 @@ EXPORTS = [
     "kosk_b200_kernel_launches", "kosk_b200_debug_fetch", "kosk_b200_debug_trace", "kosk_b200_sync",
     "kosk_b200_inst_bytes", "kosk_b200_randomness_bytes", "kosk_b200_range_proof_bytes", "kosk_b200_rng_reset", "kosk_b200_rng_calls",
     "kosk_b200_prepare_randomness", "kosk_b200_prepare_range_proof", "kosk_b200_keygen", "kosk_b200_prove", "kosk_b200_verify",
+    "kosk_b200_ct_bytes", "kosk_b200_kem_enc_derand_batch", "kosk_b200_kem_dec_batch", "kosk_b200_kem_enc_derand_batch_device", "kosk_b200_kem_dec_batch_device",
+    "kosk_b200_kem_enc", "kosk_b200_kem_dec",
     "kosk_b200_pool_create", "kosk_b200_pool_prove", "kosk_b200_pool_destroy", "kosk_b200_set_strict", "kosk_b200_set_profiling", "kosk_b200_phase_times", "kosk_b200_int_peak",
 ]
 
@@ -39,7 +41,7 @@ def load_library(path=None):
         raise KoskError(f"{path} not found: build it with `python -m mpcith_kyber_kosk_b200.build` (no CPU fallback exists)")
     lib = ctypes.CDLL(path)
     vp, sz, i32, u8p = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p
-    for n in ("kosk_b200_pk_bytes", "kosk_b200_sk_bytes", "kosk_b200_proof_bytes", "kosk_b200_inst_bytes", "kosk_b200_randomness_bytes", "kosk_b200_range_proof_bytes"):
+    for n in ("kosk_b200_pk_bytes", "kosk_b200_sk_bytes", "kosk_b200_proof_bytes", "kosk_b200_inst_bytes", "kosk_b200_randomness_bytes", "kosk_b200_range_proof_bytes", "kosk_b200_ct_bytes"):
         getattr(lib, n).restype = sz
         getattr(lib, n).argtypes = [i32]
     lib.kosk_b200_last_error.restype = ctypes.c_char_p
@@ -79,6 +81,12 @@ def load_library(path=None):
     lib.kosk_b200_keygen.argtypes = [vp, u8p, u8p, u8p]
     lib.kosk_b200_prove.argtypes = [vp, u8p, u8p, u8p, u8p]
     lib.kosk_b200_verify.argtypes = [vp, u8p, u8p]
+    lib.kosk_b200_kem_enc_derand_batch.argtypes = [vp, sz, u8p, u8p, u8p, u8p]
+    lib.kosk_b200_kem_dec_batch.argtypes = [vp, sz, u8p, u8p, u8p]
+    lib.kosk_b200_kem_enc_derand_batch_device.argtypes = [vp, sz, u8p, u8p, u8p, u8p, vp]
+    lib.kosk_b200_kem_dec_batch_device.argtypes = [vp, sz, u8p, u8p, u8p, vp]
+    lib.kosk_b200_kem_enc.argtypes = [vp, u8p, u8p, u8p]
+    lib.kosk_b200_kem_dec.argtypes = [vp, u8p, u8p, u8p]
     lib.kosk_b200_phase_times.argtypes = [vp, u8p, u8p, i32, i32]
     lib.kosk_b200_int_peak.argtypes = [vp, u8p]
     if path == LIB_PATH:
@@ -182,6 +190,54 @@ class KoskContext:
         if a.size != self.proof_bytes or inst.size != self.lib.kosk_b200_inst_bytes(self.k):
             raise KoskError("bad proof or mlwe_inst length")
         return self._check(self.lib.kosk_b200_verify(self._h, _ptr(a), _ptr(inst)), "verify") == 1
+
+    # ---- Kyber KEM on the generated keys (reference kyber/kem.c:76-169) ----
+    @property
+    def ct_bytes(self):
+        return self.lib.kosk_b200_ct_bytes(self.k)
+
+    def kem_enc_derand_batch(self, pk, coins):
+        pk = np.ascontiguousarray(pk, dtype=np.uint8).reshape(-1, self.pk_bytes)
+        coins = np.ascontiguousarray(coins, dtype=np.uint8).reshape(-1, 32)
+        n = pk.shape[0]
+        if coins.shape[0] != n:
+            raise KoskError("pk / coins batch mismatch")
+        ct, ss = np.empty((n, self.ct_bytes), np.uint8), np.empty((n, 32), np.uint8)
+        self._check(self.lib.kosk_b200_kem_enc_derand_batch(self._h, n, _ptr(pk), _ptr(coins), _ptr(ct), _ptr(ss)), "kem_enc_derand_batch")
+        return ct, ss
+
+    def kem_dec_batch(self, ct, sk):
+        ct = np.ascontiguousarray(ct, dtype=np.uint8).reshape(-1, self.ct_bytes)
+        sk = np.ascontiguousarray(sk, dtype=np.uint8).reshape(-1, self.sk_bytes)
+        n = ct.shape[0]
+        if sk.shape[0] != n:
+            raise KoskError("ct / sk batch mismatch")
+        ss = np.empty((n, 32), np.uint8)
+        self._check(self.lib.kosk_b200_kem_dec_batch(self._h, n, _ptr(ct), _ptr(sk), _ptr(ss)), "kem_dec_batch")
+        return ss
+
+    def crypto_kem_enc(self, pk):
+        """crypto_kem_enc (kem.c:114-122): returns (ct, ss); the coins are the next call of the context DRBG."""
+        pk = np.frombuffer(bytes(pk), dtype=np.uint8)
+        ct, ss = np.empty(self.ct_bytes, np.uint8), np.empty(32, np.uint8)
+        self._check(self.lib.kosk_b200_kem_enc(self._h, _ptr(ct), _ptr(ss), _ptr(pk)), "kem_enc")
+        return bytes(ct), bytes(ss)
+
+    def crypto_kem_dec(self, ct, sk):
+        ct, sk = np.frombuffer(bytes(ct), dtype=np.uint8), np.frombuffer(bytes(sk), dtype=np.uint8)
+        if ct.size != self.ct_bytes or sk.size != self.sk_bytes:
+            raise KoskError("bad ct or sk length")
+        ss = np.empty(32, np.uint8)
+        self._check(self.lib.kosk_b200_kem_dec(self._h, _ptr(ss), _ptr(ct), _ptr(sk)), "kem_dec")
+        return bytes(ss)
+
+    def kem_enc_derand_batch_device(self, n, d_pk, d_coins, d_ct, d_ss, stream=0):
+        vp = ctypes.c_void_p
+        self._check(self.lib.kosk_b200_kem_enc_derand_batch_device(self._h, n, vp(d_pk), vp(d_coins), vp(d_ct), vp(d_ss), vp(stream)), "kem_enc_derand_batch_device")
+
+    def kem_dec_batch_device(self, n, d_ct, d_sk, d_ss, stream=0):
+        vp = ctypes.c_void_p
+        self._check(self.lib.kosk_b200_kem_dec_batch_device(self._h, n, vp(d_ct), vp(d_sk), vp(d_ss), vp(stream)), "kem_dec_batch_device")
 
     # ---- batch, host buffers ----
     def prove_batch(self, seeds, out=None):

@@ -1,0 +1,409 @@
+// kem_kernels.cuh -- Kyber KEM encapsulation / decapsulation for keys made by the KOSK keygen: the step
+// main.cpp:98-113 runs right after kyber_verifiable_keygen.  Replaces reference kyber/kem.c:76-169 (crypto_kem_enc_derand,
+// crypto_kem_enc, crypto_kem_dec), kyber/indcpa.c:260-336 (indcpa_enc / indcpa_dec, gen_at = gen_matrix transposed :168-193),
+// kyber/poly.c:21-221 (compress / decompress / frommsg / tomsg, getnoise_eta1/eta2), kyber/polyvec.c:16-138, kyber/ntt.c:106-126
+// (invntt) and kyber_shake256_rkprf (symmetric-shake.c:64-73).  One CTA of 128 threads per encapsulation / decapsulation,
+// everything in shared memory, residues canonical in [0, q): every value that reaches a ciphertext or message byte is a
+// function of the coefficient mod q only, so any exact representation gives the reference's bytes.
+// Included by kosk_b200.cu after the context definition.
+#pragma once
+
+namespace kosk {
+
+__constant__ u16 c_zeta_inv[128];       // inverses of c_zeta (plain residues)
+
+struct KemDims { int k, eta1, du, dv, pvc, pc, ct_bytes; };
+KOSK_HD KemDims kem_dims(int k)
+{
+    KemDims d; d.k = k; d.eta1 = (k == 2) ? 3 : 2; d.du = (k == 4) ? 11 : 10; d.dv = (k == 4) ? 5 : 4;
+    d.pvc = k * 32 * d.du; d.pc = 32 * d.dv; d.ct_bytes = d.pvc + d.pc;       // kyber/params.h:29-41,53
+    return d;
+}
+
+// inverse of ntt256_block: Gentleman-Sande butterflies with the inverse twiddles, then 128^-1 = 3303 (kyber/ntt.c:106-126)
+__device__ __forceinline__ void invntt256_block(u16 *p, int tid)
+{
+    for (int len = 2; len <= 128; len <<= 1) {
+        const int grp = tid / len, j = grp * 2 * len + (tid % len);
+        const uint32_t zi = c_zeta_inv[128 / len + grp];
+        const uint32_t a = p[j], b = p[j + len];
+        p[j] = (u16)gf_add(a, b);
+        p[j + len] = (u16)gf_mul(gf_sub(a, b), zi);
+        __syncthreads();
+    }
+    p[tid] = (u16)gf_mul(p[tid], 3303); p[tid + 128] = (u16)gf_mul(p[tid + 128], 3303);
+    __syncthreads();
+}
+
+// centered binomial sample from a PRF stream (kyber/cbd.c:58-107), canonical residues
+template <int ETA>
+__device__ __forceinline__ void cbd_stream(ByteSponge &sp, u16 *dst)
+{
+    if (ETA == 2) {
+        for (int i = 0; i < 32; i++) {
+            uint32_t t = sp.next(); t |= (uint32_t)sp.next() << 8; t |= (uint32_t)sp.next() << 16; t |= (uint32_t)sp.next() << 24;
+            const uint32_t d = (t & 0x55555555u) + ((t >> 1) & 0x55555555u);
+            for (int j = 0; j < 8; j++) { const int x = (int)((d >> (4 * j)) & 3) - (int)((d >> (4 * j + 2)) & 3); dst[8 * i + j] = (u16)(x < 0 ? x + Q : x); }
+        }
+    } else {
+        for (int i = 0; i < 64; i++) {
+            uint32_t t = sp.next(); t |= (uint32_t)sp.next() << 8; t |= (uint32_t)sp.next() << 16;
+            const uint32_t d = (t & 0x249249u) + ((t >> 1) & 0x249249u) + ((t >> 2) & 0x249249u);
+            for (int j = 0; j < 4; j++) { const int x = (int)((d >> (6 * j)) & 7) - (int)((d >> (6 * j + 3)) & 7); dst[4 * i + j] = (u16)(x < 0 ? x + Q : x); }
+        }
+    }
+}
+
+template <int K>
+struct KemSmem {
+    u16 At[K * K][256];                       // A^T in the NTT domain (gen_at)
+    u16 sp[K][256], ep[K][256], b[K][256], t[K][256];
+    u16 epp[256], v[256];
+    uint32_t mw[8];                           // message bits (dec)
+    u8 m[32], coins[32], kr[64], hpk[32];
+    u8 ct[K * 352 + 160];
+    int fail;
+};
+
+// compress_d(x) = round(2^d x / q) mod 2^d with the reference's multiply-shift constants (poly.c:29-33,:48-52, polyvec.c:29-35,:57-63)
+__device__ __forceinline__ uint32_t compress_d(uint32_t x, int d)
+{
+    if (d == 4) return ((((x << 4) + 1665) * 80635u) >> 28) & 0xF;
+    if (d == 5) return ((((x << 5) + 1664) * 40318u) >> 27) & 0x1F;
+    if (d == 10) return (uint32_t)(((((uint64_t)x << 10) + 1665) * 1290167ull) >> 32) & 0x3FF;
+    return (uint32_t)(((((uint64_t)x << 11) + 1664) * 645084ull) >> 31) & 0x7FF;
+}
+__device__ __forceinline__ uint32_t decompress_d(uint32_t t, int d) { return (t * (uint32_t)Q + (1u << (d - 1))) >> d; }
+
+// little-endian bit packing of `cnt` d-bit values into bytes (the byte patterns of poly_compress / polyvec_compress)
+__device__ __forceinline__ void pack_bits(u8 *dst, const uint32_t *t, int cnt, int d)
+{
+    uint64_t acc = 0; int have = 0, o = 0;
+    for (int i = 0; i < cnt; i++) {
+        acc |= (uint64_t)t[i] << have; have += d;
+        while (have >= 8) { dst[o++] = (u8)acc; acc >>= 8; have -= 8; }
+    }
+}
+__device__ __forceinline__ void unpack_bits(uint32_t *t, const u8 *src, int cnt, int d)
+{
+    uint64_t acc = 0; int have = 0, o = 0;
+    for (int i = 0; i < cnt; i++) {
+        while (have < d) { acc |= (uint64_t)src[o++] << have; have += 8; }
+        t[i] = (uint32_t)acc & ((1u << d) - 1); acc >>= d; have -= d;
+    }
+}
+
+// part of indcpa_enc that needs only the public key: A^T = gen_at(seed) and t-hat = polyvec_frombytes(pk) (indcpa.c:273-276)
+template <int K>
+__device__ __forceinline__ void enc_public(KemSmem<K> &S, const u8 *pk, int tid, int first_thread)
+{
+    const int g = tid - first_thread;
+    if (g >= 0 && g < K * K) {
+        const int i = g / K, j = g % K;
+        ByteSponge sp; sp.init(168);
+        sp.absorb(pk + 384 * K, 32);
+        u8 ij[2] = {(u8)i, (u8)j}; sp.absorb(ij, 2); sp.finalize(0x1F);      // transposed: xof_absorb(seed, i, j), indcpa.c:176-179
+        int ctr = 0;
+        while (ctr < 256) {
+            const uint32_t b0 = sp.next(), b1 = sp.next(), b2 = sp.next();
+            const uint32_t v0 = (b0 | (b1 << 8)) & 0xFFF, v1 = ((b1 >> 4) | (b2 << 4)) & 0xFFF;
+            if (v0 < (uint32_t)Q) S.At[g][ctr++] = (u16)v0;
+            if (ctr < 256 && v1 < (uint32_t)Q) S.At[g][ctr++] = (u16)v1;
+        }
+    }
+    for (int i = 0; i < K; i++) {
+        const u8 *a = pk + 384 * i + 3 * tid;
+        S.t[i][2 * tid] = (u16)(((a[0] | ((uint32_t)a[1] << 8)) & 0xFFF) % Q);          // raw 12-bit values act mod q in basemul
+        S.t[i][2 * tid + 1] = (u16)((((a[1] >> 4) | ((uint32_t)a[2] << 4)) & 0xFFF) % Q);
+    }
+}
+
+// the rest of indcpa_enc (indcpa.c:278-303): needs S.m, S.coins, S.At, S.t; leaves the ciphertext in S.ct
+template <int K>
+__device__ __forceinline__ void enc_secret(KemSmem<K> &S, int tid)
+{
+    constexpr int ETA1 = (K == 2) ? 3 : 2, DU = (K == 4) ? 11 : 10, DV = (K == 4) ? 5 : 4;
+    if (tid < 2 * K + 1) {
+        ByteSponge sp; sp.init(136);
+        sp.absorb(S.coins, 32);
+        u8 nonce = (u8)tid; sp.absorb(&nonce, 1); sp.finalize(0x1F);
+        if (tid < K) cbd_stream<ETA1>(sp, S.sp[tid]);
+        else if (tid < 2 * K) cbd_stream<2>(sp, S.ep[tid - K]);
+        else cbd_stream<2>(sp, S.epp);
+    }
+    __syncthreads();
+    for (int i = 0; i < K; i++) ntt256_block(S.sp[i], tid);
+    for (int i = 0; i <= K; i++) {                 // b_i = A^T[i] o sp ; i == K: v = t o sp
+        uint32_t a0 = 0, a1 = 0;
+        for (int j = 0; j < K; j++) {
+            const u16 *row = i < K ? S.At[i * K + j] : S.t[j];
+            uint32_t r0, r1;
+            basemul_pair(r0, r1, row[2 * tid], row[2 * tid + 1], S.sp[j][2 * tid], S.sp[j][2 * tid + 1], tid);
+            a0 = gf_add(a0, r0); a1 = gf_add(a1, r1);
+        }
+        u16 *dst = i < K ? S.b[i] : S.v;
+        dst[2 * tid] = (u16)a0; dst[2 * tid + 1] = (u16)a1;
+    }
+    __syncthreads();
+    for (int i = 0; i < K; i++) invntt256_block(S.b[i], tid);
+    invntt256_block(S.v, tid);
+    for (int c = tid; c < 256; c += 128) {
+        for (int i = 0; i < K; i++) S.b[i][c] = (u16)gf_add(S.b[i][c], S.ep[i][c]);
+        const uint32_t mbit = (S.m[c >> 3] >> (c & 7)) & 1;                            // poly_frommsg: (q+1)/2 per set bit
+        S.v[c] = (u16)gf_add(gf_add(S.v[c], S.epp[c]), mbit ? (Q + 1) / 2 : 0);
+    }
+    __syncthreads();
+    // pack_ciphertext: polyvec_compress(b) || poly_compress(v)
+    constexpr int GU = (DU == 10) ? 4 : 8, NGU = 256 / GU, BU = GU * DU / 8;
+    for (int g = tid; g < K * NGU; g += 128) {
+        const int i = g / NGU, q0 = (g % NGU) * GU;
+        uint32_t t[8];
+        for (int x = 0; x < GU; x++) t[x] = compress_d(S.b[i][q0 + x], DU);
+        pack_bits(S.ct + (size_t)i * 32 * DU + (g % NGU) * BU, t, GU, DU);
+    }
+    if (tid < 32) {
+        uint32_t t[8];
+        for (int x = 0; x < 8; x++) t[x] = compress_d(S.v[8 * tid + x], DV);
+        pack_bits(S.ct + K * 32 * DU + tid * DV, t, 8, DV);
+    }
+    __syncthreads();
+}
+
+// crypto_kem_enc_derand (kem.c:76-97); coins = the 32 random bytes of crypto_kem_enc (kem.c:114-122).  With `seeds` set the
+// coins are drawn inside the kernel as randombytes() call number calls[b] of the KOSK DRBG seeded with seeds[b].
+template <int K>
+__global__ void __launch_bounds__(128) k_kem_enc(const u8 *__restrict__ pks, const u8 *__restrict__ coins, const u8 *__restrict__ seeds,
+                                                 uint32_t call, u8 *__restrict__ cts, u8 *__restrict__ sss, int n)
+{
+    __shared__ KemSmem<K> S;
+    const KemDims d = kem_dims(K);
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const u8 *pk = pks + (size_t)(384 * K + 32) * b;
+    if (tid == 0) {
+        if (seeds) {
+            uint64_t sd[4], a[25];
+            for (int i = 0; i < 4; i++) { uint64_t w = 0; for (int j = 0; j < 8; j++) w |= (uint64_t)seeds[32 * (size_t)b + 8 * i + j] << (8 * j); sd[i] = w; }
+            drbg_begin(a, sd, call);
+            for (int i = 0; i < 32; i++) S.m[i] = (u8)(a[i >> 3] >> (8 * (i & 7)));
+        } else for (int i = 0; i < 32; i++) S.m[i] = coins[32 * (size_t)b + i];
+        ByteSponge sp; sp.init(136); sp.absorb(pk, 384 * K + 32); sp.finalize(0x06);          // hash_h(pk)
+        for (int i = 0; i < 32; i++) S.hpk[i] = sp.next();
+        sp.init(72); sp.absorb(S.m, 32); sp.absorb(S.hpk, 32); sp.finalize(0x06);             // hash_g(m || H(pk))
+        for (int i = 0; i < 64; i++) S.kr[i] = sp.next();
+        for (int i = 0; i < 32; i++) S.coins[i] = S.kr[32 + i];
+    }
+    enc_public<K>(S, pk, tid, 32);           // A^T on the second warp while thread 0 hashes
+    __syncthreads();
+    enc_secret<K>(S, tid);
+    for (int i = tid; i < d.ct_bytes; i += 128) cts[(size_t)d.ct_bytes * b + i] = S.ct[i];
+    if (tid < 32) sss[32 * (size_t)b + tid] = S.kr[tid];
+}
+
+// crypto_kem_dec (kem.c:139-169) with indcpa_dec (indcpa.c:318-336)
+template <int K>
+__global__ void __launch_bounds__(128) k_kem_dec(const u8 *__restrict__ cts, const u8 *__restrict__ sks, u8 *__restrict__ sss, int n)
+{
+    __shared__ KemSmem<K> S;
+    constexpr int DU = (K == 4) ? 11 : 10, DV = (K == 4) ? 5 : 4;
+    const KemDims d = kem_dims(K);
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const u8 *ct = cts + (size_t)d.ct_bytes * b, *sk = sks + (size_t)(768 * K + 96) * b, *pk = sk + 384 * K;
+    // unpack_ciphertext + unpack_sk
+    constexpr int GU = (DU == 10) ? 4 : 8, NGU = 256 / GU, BU = GU * DU / 8;
+    for (int g = tid; g < K * NGU; g += 128) {
+        const int i = g / NGU, q0 = (g % NGU) * GU;
+        uint32_t t[8];
+        unpack_bits(t, ct + (size_t)i * 32 * DU + (g % NGU) * BU, GU, DU);
+        for (int x = 0; x < GU; x++) S.b[i][q0 + x] = (u16)decompress_d(t[x], DU);
+    }
+    if (tid < 32) {
+        uint32_t t[8];
+        unpack_bits(t, ct + K * 32 * DU + tid * DV, 8, DV);
+        for (int x = 0; x < 8; x++) S.v[8 * tid + x] = (u16)decompress_d(t[x], DV);
+    }
+    for (int i = 0; i < K; i++) {
+        const u8 *a = sk + 384 * i + 3 * tid;
+        S.sp[i][2 * tid] = (u16)(((a[0] | ((uint32_t)a[1] << 8)) & 0xFFF) % Q);
+        S.sp[i][2 * tid + 1] = (u16)((((a[1] >> 4) | ((uint32_t)a[2] << 4)) & 0xFFF) % Q);
+    }
+    if (tid < 8) S.mw[tid] = 0;
+    enc_public<K>(S, pk, tid, 32);           // for the re-encryption; independent of the message
+    __syncthreads();
+    for (int i = 0; i < K; i++) ntt256_block(S.b[i], tid);
+    {
+        uint32_t a0 = 0, a1 = 0;
+        for (int j = 0; j < K; j++) {
+            uint32_t r0, r1;
+            basemul_pair(r0, r1, S.sp[j][2 * tid], S.sp[j][2 * tid + 1], S.b[j][2 * tid], S.b[j][2 * tid + 1], tid);
+            a0 = gf_add(a0, r0); a1 = gf_add(a1, r1);
+        }
+        S.epp[2 * tid] = (u16)a0; S.epp[2 * tid + 1] = (u16)a1;
+    }
+    __syncthreads();
+    invntt256_block(S.epp, tid);
+    for (int c = tid; c < 256; c += 128) {
+        // poly_tomsg on the centered representative (poly_reduce), in the reference's 32-bit arithmetic (poly.c:208-219)
+        uint32_t t = (uint32_t)gf_center(gf_sub(S.v[c], S.epp[c]));
+        t <<= 1; t += 1665; t *= 80635u; t >>= 28; t &= 1;
+        if (t) atomicOr(&S.mw[c >> 5], 1u << (c & 31));
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int i = 0; i < 32; i++) S.m[i] = (u8)(S.mw[i >> 2] >> (8 * (i & 3)));
+        ByteSponge sp; sp.init(72); sp.absorb(S.m, 32); sp.absorb(sk + 768 * K + 32, 32); sp.finalize(0x06);    // hash_g(m' || H(pk) from sk)
+        for (int i = 0; i < 64; i++) S.kr[i] = sp.next();
+        for (int i = 0; i < 32; i++) S.coins[i] = S.kr[32 + i];
+        S.fail = 0;
+    }
+    __syncthreads();
+    enc_secret<K>(S, tid);
+    int bad = 0;
+    for (int i = tid; i < d.ct_bytes; i += 128) bad |= S.ct[i] != ct[i];
+    if (bad) atomicOr(&S.fail, 1);
+    __syncthreads();
+    if (tid == 0) {
+        if (S.fail) {                        // implicit rejection: rkprf(z, ct) = SHAKE256(z || ct) (symmetric-shake.c:64-73)
+            ByteSponge sp; sp.init(136); sp.absorb(sk + 768 * K + 64, 32); sp.absorb(ct, d.ct_bytes); sp.finalize(0x1F);
+            for (int i = 0; i < 32; i++) sss[32 * (size_t)b + i] = sp.next();
+        } else for (int i = 0; i < 32; i++) sss[32 * (size_t)b + i] = S.kr[i];
+    }
+}
+
+}  // namespace kosk
+
+// ---- host side ----
+struct KemState {
+    u8 *d_a = nullptr, *d_b = nullptr, *d_c = nullptr, *d_d = nullptr; size_t cap = 0;       // grow-only staging of the host-buffer API
+    bool tables = false;
+};
+static void kem_free(KemState &ks)
+{
+    void *p[] = {ks.d_a, ks.d_b, ks.d_c, ks.d_d};
+    for (void *q : p) if (q) cudaFree(q);
+    ks = KemState{};
+}
+static int kem_tables(kosk_b200_ctx *c)
+{
+    if (c->kem->tables) return KOSK_OK;
+    uint16_t hz[128];
+    for (int i = 0; i < 128; i++) { int br = 0; for (int b = 0; b < 7; b++) br |= ((i >> b) & 1) << (6 - b); hz[i] = (uint16_t)h_pow(h_pow(17, br), Q - 2); }
+    CU(cudaMemcpyToSymbol(c_zeta_inv, hz, sizeof hz));
+    c->kem->tables = true;
+    return KOSK_OK;
+}
+static int kem_reserve(kosk_b200_ctx *c, size_t n)
+{
+    KemState &ks = *c->kem;
+    if (n <= ks.cap) return KOSK_OK;
+    kem_free(ks); ks.tables = false;
+    const size_t sk = c->L.sk_bytes, ctb = (size_t)kem_dims(c->k).ct_bytes;
+    if (cudaMalloc((void **)&ks.d_a, n * sk) != cudaSuccess || cudaMalloc((void **)&ks.d_b, n * ctb) != cudaSuccess ||
+        cudaMalloc((void **)&ks.d_c, n * 32) != cudaSuccess || cudaMalloc((void **)&ks.d_d, n * 32) != cudaSuccess) { kem_free(ks); return fail(KOSK_E_NOMEM, "cudaMalloc failed for KEM staging"); }
+    ks.cap = n;
+    return KOSK_OK;
+}
+static int kem_enc_launch(kosk_b200_ctx *c, size_t n, const u8 *d_pk, const u8 *d_coins, const u8 *d_seeds, uint32_t call, u8 *d_ct, u8 *d_ss, cudaStream_t st)
+{
+    int rc = kem_tables(c); if (rc) return rc;
+    for (size_t o = 0; o < n; o += 1u << 20) {
+        const int m = (int)std::min<size_t>(1u << 20, n - o);
+        const u8 *pk = d_pk + c->L.pk_bytes * o, *co = d_coins ? d_coins + 32 * o : nullptr, *se = d_seeds ? d_seeds + 32 * o : nullptr;
+        u8 *ct = d_ct + (size_t)kem_dims(c->k).ct_bytes * o, *ss = d_ss + 32 * o;
+        switch (c->k) {
+        case 2: k_kem_enc<2><<<m, 128, 0, st>>>(pk, co, se, call, ct, ss, m); break;
+        case 3: k_kem_enc<3><<<m, 128, 0, st>>>(pk, co, se, call, ct, ss, m); break;
+        default: k_kem_enc<4><<<m, 128, 0, st>>>(pk, co, se, call, ct, ss, m); break;
+        }
+        c->launches++;
+    }
+    CU(cudaGetLastError());
+    return KOSK_OK;
+}
+static int kem_dec_launch(kosk_b200_ctx *c, size_t n, const u8 *d_ct, const u8 *d_sk, u8 *d_ss, cudaStream_t st)
+{
+    int rc = kem_tables(c); if (rc) return rc;
+    for (size_t o = 0; o < n; o += 1u << 20) {
+        const int m = (int)std::min<size_t>(1u << 20, n - o);
+        const u8 *ct = d_ct + (size_t)kem_dims(c->k).ct_bytes * o, *sk = d_sk + c->L.sk_bytes * o; u8 *ss = d_ss + 32 * o;
+        switch (c->k) {
+        case 2: k_kem_dec<2><<<m, 128, 0, st>>>(ct, sk, ss, m); break;
+        case 3: k_kem_dec<3><<<m, 128, 0, st>>>(ct, sk, ss, m); break;
+        default: k_kem_dec<4><<<m, 128, 0, st>>>(ct, sk, ss, m); break;
+        }
+        c->launches++;
+    }
+    CU(cudaGetLastError());
+    return KOSK_OK;
+}
+
+extern "C" {
+
+size_t kosk_b200_ct_bytes(int k) { return (k >= 2 && k <= 4) ? (size_t)kem_dims(k).ct_bytes : 0; }
+
+int kosk_b200_kem_enc_derand_batch_device(kosk_b200_ctx *c, size_t n, const uint8_t *d_pk, const uint8_t *d_coins, uint8_t *d_ct, uint8_t *d_ss, void *stream)
+{
+    if (!c || !d_pk || !d_coins || !d_ct || !d_ss) return fail(KOSK_E_ARG, "null argument");
+    CU(cudaSetDevice(c->device));
+    return n ? kem_enc_launch(c, n, d_pk, d_coins, nullptr, 0, d_ct, d_ss, (cudaStream_t)stream) : KOSK_OK;
+}
+int kosk_b200_kem_dec_batch_device(kosk_b200_ctx *c, size_t n, const uint8_t *d_ct, const uint8_t *d_sk, uint8_t *d_ss, void *stream)
+{
+    if (!c || !d_ct || !d_sk || !d_ss) return fail(KOSK_E_ARG, "null argument");
+    CU(cudaSetDevice(c->device));
+    return n ? kem_dec_launch(c, n, d_ct, d_sk, d_ss, (cudaStream_t)stream) : KOSK_OK;
+}
+
+static int kem_enc_host(kosk_b200_ctx *c, size_t n, const uint8_t *pk, const uint8_t *coins, const uint8_t *seed, uint32_t call, uint8_t *ct, uint8_t *ss)
+{
+    CU(cudaSetDevice(c->device));
+    if (n == 0) return KOSK_OK;
+    int rc = kem_reserve(c, n); if (rc) return rc;
+    KemState &ks = *c->kem; cudaStream_t st = c->lanes[0].st;
+    const size_t ctb = (size_t)kem_dims(c->k).ct_bytes;
+    CU(cudaMemcpyAsync(ks.d_a, pk, n * c->L.pk_bytes, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ks.d_c, coins ? coins : seed, n * 32, cudaMemcpyHostToDevice, st));
+    rc = kem_enc_launch(c, n, ks.d_a, coins ? ks.d_c : nullptr, coins ? nullptr : ks.d_c, call, ks.d_b, ks.d_d, st);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(ct, ks.d_b, n * ctb, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(ss, ks.d_d, n * 32, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return KOSK_OK;
+}
+
+int kosk_b200_kem_enc_derand_batch(kosk_b200_ctx *c, size_t n, const uint8_t *pk, const uint8_t *coins, uint8_t *ct, uint8_t *ss)
+{
+    if (!c || !pk || !coins || !ct || !ss) return fail(KOSK_E_ARG, "null argument");
+    return kem_enc_host(c, n, pk, coins, nullptr, 0, ct, ss);
+}
+
+int kosk_b200_kem_dec_batch(kosk_b200_ctx *c, size_t n, const uint8_t *ct, const uint8_t *sk, uint8_t *ss)
+{
+    if (!c || !ct || !sk || !ss) return fail(KOSK_E_ARG, "null argument");
+    CU(cudaSetDevice(c->device));
+    if (n == 0) return KOSK_OK;
+    int rc = kem_reserve(c, n); if (rc) return rc;
+    KemState &ks = *c->kem; cudaStream_t st = c->lanes[0].st;
+    const size_t ctb = (size_t)kem_dims(c->k).ct_bytes;
+    CU(cudaMemcpyAsync(ks.d_a, sk, n * c->L.sk_bytes, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ks.d_b, ct, n * ctb, cudaMemcpyHostToDevice, st));
+    rc = kem_dec_launch(c, n, ks.d_b, ks.d_a, ks.d_d, st);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(ss, ks.d_d, n * 32, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return KOSK_OK;
+}
+
+// crypto_kem_enc (kem.c:114-122): coins = randombytes(32) = the next call of the context DRBG (kosk_b200_rng_reset)
+int kosk_b200_kem_enc(kosk_b200_ctx *c, uint8_t *ct, uint8_t *ss, const uint8_t *pk)
+{
+    if (!c || !ct || !ss || !pk) return fail(KOSK_E_ARG, "null argument");
+    int rc = kem_enc_host(c, 1, pk, nullptr, c->raw->seed, c->raw->calls, ct, ss);
+    if (!rc) c->raw->calls += 1;
+    return rc;
+}
+int kosk_b200_kem_dec(kosk_b200_ctx *c, uint8_t *ss, const uint8_t *ct, const uint8_t *sk)
+{
+    return kosk_b200_kem_dec_batch(c, 1, ct, sk, ss);
+}
+
+}  // extern "C"

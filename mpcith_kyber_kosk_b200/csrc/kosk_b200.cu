@@ -49,6 +49,9 @@ enum { PH_OFFLINE = 1, PH_ONLINE = 2, PH_NOKEYGEN = 4 /* raw prove(): the instan
 struct RawState;
 static RawState *raw_new();
 static void raw_delete(RawState *);
+struct KemState;
+static KemState *kem_new();
+static void kem_delete(KemState *);
 enum { KOSK_PH_KEYGEN = 0, KOSK_PH_EXPAND, KOSK_PH_SHARE1, KOSK_PH_COMMIT, KOSK_PH_FS1, KOSK_PH_EVAL, KOSK_PH_OPEN, KOSK_PH_SHARE2,
        KOSK_PH_VIEW, KOSK_PH_FS2, KOSK_PH_ASSEMBLE, KOSK_PH_VERIFY, KOSK_NPHASE };
 
@@ -88,6 +91,7 @@ struct kosk_b200_ctx {
     bool prof = false;
     double phase_ms[KOSK_NPHASE] = {0}; uint64_t phase_calls[KOSK_NPHASE] = {0};
     RawState *raw = nullptr;               // struct-level API (raw_api.cuh): DRBG state and staging buffers
+    KemState *kem = nullptr;               // Kyber KEM encaps / decaps (kem_kernels.cuh)
 };
 
 static void prof_mark(kosk_b200_ctx *c, Lane &ln, int phase, cudaStream_t on = nullptr)
@@ -152,6 +156,7 @@ static void ctx_free(kosk_b200_ctx *c)
     }
     if (c->ev_start) cudaEventDestroy(c->ev_start);
     raw_delete(c->raw);
+    kem_delete(c->kem);
     delete c;
 }
 
@@ -179,7 +184,7 @@ int kosk_b200_create_ex(kosk_b200_ctx **out, int k, int device, int max_chunk, i
     CU(cudaSetDevice(device));
     kosk_b200_ctx *c = new kosk_b200_ctx;
     c->k = k; c->device = device; c->sl = make_slots(k); c->L = make_layout(k);
-    c->raw = raw_new();
+    c->raw = raw_new(); c->kem = kem_new();
     c->chunk = max_chunk > 0 ? max_chunk : 1024;
     if (c->chunk > 16384) c->chunk = 16384;
     if (nlanes <= 0) nlanes = 2;
@@ -755,6 +760,9 @@ int kosk_b200_phase_times(kosk_b200_ctx *c, double *ms, uint64_t *calls, int n, 
 #include "raw_api.cuh"
 static RawState *raw_new() { return new RawState; }
 static void raw_delete(RawState *r) { if (r) { raw_free(*r); delete r; } }
+#include "kem_kernels.cuh"
+static KemState *kem_new() { return new KemState; }
+static void kem_delete(KemState *k) { if (k) { kem_free(*k); delete k; } }
 
 // ---- integer-pipe issue-rate microbenchmarks (roofline denominators; MEASURED_PEAKS.json has no integer entry) ----
 template <int MODE>

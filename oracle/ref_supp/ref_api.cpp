@@ -4,6 +4,9 @@
  * stack: mlwe_prover.cpp:103, kosk.cpp:77-84) and under the deterministic randombytes of
  * oracle/ok_rng.c. */
 #include "kosk.hpp"
+extern "C" {
+#include "kyber/kem.h"
+}
 #include "../ok_rng.h"
 #include <pthread.h>
 #include <time.h>
@@ -75,6 +78,18 @@ int ref_struct_sequence(const uint8_t seed[32], int rng_mode, uint8_t *rand_img,
                         uint8_t *pk, uint8_t *sk, uint8_t *pi)
 {
     job j = {2, seed, rng_mode, pk, sk, pi, 0, 0, 0, rand_img, eta_img, inst_img, 0}; big_stack(&j); return j.ok;
+}
+/* Kyber KEM of the reference (kyber/kem.c:76-169); small stack frames, no helper thread needed */
+size_t ref_ct_bytes(void) { return KYBER_CIPHERTEXTBYTES; }
+void ref_kem_enc_derand(uint8_t *ct, uint8_t *ss, const uint8_t *pk, const uint8_t *coins) { crypto_kem_enc_derand(ct, ss, pk, coins); }
+void ref_kem_dec(uint8_t *ss, const uint8_t *ct, const uint8_t *sk) { crypto_kem_dec(ss, ct, sk); }
+/* crypto_kem_enc under the counter DRBG positioned at call number `call` */
+void ref_kem_enc_at(const uint8_t seed[32], uint32_t call, uint8_t *ct, uint8_t *ss, const uint8_t *pk)
+{
+    kosk_rng_reset(seed, KOSK_RNG_COUNTER);
+    uint8_t junk[1];
+    for (uint32_t i = 0; i < call; i++) randombytes(junk, 1);
+    crypto_kem_enc(ct, ss, pk);
 }
 int ref_verify_struct(const uint8_t *pi, const uint8_t *inst_img)
 {

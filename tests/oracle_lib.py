@@ -123,6 +123,13 @@ def ref(k):
                 getattr(lib, n).restype = ctypes.c_size_t
             lib.ref_struct_sequence.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, vp, vp]
             lib.ref_verify_struct.argtypes = [vp, vp]
+            lib.ref_ct_bytes.restype = ctypes.c_size_t
+            lib.ref_kem_enc_derand.argtypes = [vp, vp, vp, vp]
+            lib.ref_kem_enc_derand.restype = None
+            lib.ref_kem_dec.argtypes = [vp, vp, vp]
+            lib.ref_kem_dec.restype = None
+            lib.ref_kem_enc_at.argtypes = [vp, ctypes.c_uint32, vp, vp, vp]
+            lib.ref_kem_enc_at.restype = None
             _refs[k] = lib
     return _refs[k]
 
@@ -177,6 +184,35 @@ def ref_verify_struct(k, pi, inst):
     pi = np.frombuffer(bytes(pi), dtype=np.uint8).copy()
     inst = np.ascontiguousarray(inst, dtype=np.uint8)
     return ref(k).ref_verify_struct(_p(pi), _p(inst)) == 1
+
+
+# ---- Kyber KEM of the unmodified reference (kyber/kem.c) ----
+CT_BYTES = {2: 768, 3: 1088, 4: 1568}
+
+
+def _u8(x):
+    return np.frombuffer(bytes(x), dtype=np.uint8).copy()
+
+
+def ref_kem_enc_derand(k, pk, coins):
+    pk, coins = _u8(pk), _u8(coins)
+    ct, ss = np.zeros(ref(k).ref_ct_bytes(), np.uint8), np.zeros(32, np.uint8)
+    ref(k).ref_kem_enc_derand(_p(ct), _p(ss), _p(pk), _p(coins))
+    return ct, ss
+
+
+def ref_kem_dec(k, ct, sk):
+    ct, sk = _u8(ct), _u8(sk)
+    ss = np.zeros(32, np.uint8)
+    ref(k).ref_kem_dec(_p(ss), _p(ct), _p(sk))
+    return ss
+
+
+def ref_kem_enc_at(k, seed, call, pk):
+    seed, pk = _u8(seed), _u8(pk)
+    ct, ss = np.zeros(ref(k).ref_ct_bytes(), np.uint8), np.zeros(32, np.uint8)
+    ref(k).ref_kem_enc_at(_p(seed), call, _p(ct), _p(ss), _p(pk))
+    return ct, ss
 
 
 def seed_of(i, tag=b"kosk-b200"):

@@ -425,3 +425,70 @@ def test_struct_calls_in_keygen_order_equal_verifiable_keygen(ctxs, k):
     assert pk2 != pk
     pi2 = ctx.prove(inst2, rand, eta)
     assert ctx.kosk_verify(pi2, pk2) is True and ctx.kosk_verify(pi2, pk) is False
+
+
+# ---------------- Kyber KEM on the generated keys (reference kyber/kem.c:76-169, main.cpp:98-113) ----------------
+KEM_GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "kosk_kem_golden.json")))
+
+
+@pytest.mark.parametrize("case", KEM_GOLDEN["cases"], ids=lambda c: f"k{c['k']}key{c['key_index']}c{c['coins_index']}")
+def test_kem_matches_reference_golden(ctxs, case):
+    k = case["k"]
+    ctx = ctxs(k)
+    pk, sk, _ = ctx.verifiable_keygen(O.seed_of(case["key_index"]))
+    assert hashlib.sha256(pk).hexdigest() == case["pk_sha256"]
+    coins = O.seed_of(case["coins_index"], b"kem-coins")
+    ct, ss = ctx.kem_enc_derand_batch(np.frombuffer(pk, np.uint8), np.frombuffer(coins, np.uint8))
+    assert ct.shape == (1, O.CT_BYTES[k]) == (1, ctx.ct_bytes)
+    assert hashlib.sha256(bytes(ct[0])).hexdigest() == case["ct_sha256"]
+    assert bytes(ss[0]).hex() == case["ss"]
+    assert ctx.crypto_kem_dec(bytes(ct[0]), sk).hex() == case["ss"]
+    bad = ct[0].copy(); bad[7] ^= 0x10                                    # implicit rejection: SHAKE256(z || ct)
+    assert ctx.crypto_kem_dec(bytes(bad), sk).hex() == case["ss_reject_byte7"]
+    bad = ct[0].copy(); bad[-1] ^= 0x80
+    assert ctx.crypto_kem_dec(bytes(bad), sk).hex() == case["ss_reject_last"]
+
+
+@pytest.mark.parametrize("k", [2, 3, 4])
+def test_kem_batch_roundtrip_and_live_reference(ctxs, k):
+    """encaps -> decaps round trip on a batch of GPU-made keys; sampled rows against the live reference when it is present."""
+    ctx = ctxs(k)
+    n = 96
+    pk, sk, _ = ctx.prove_batch(seeds_for_range(500 + k, 0, n))
+    rng = np.random.default_rng(40 + k)
+    coins = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    ct, ss = ctx.kem_enc_derand_batch(pk, coins)
+    assert (ctx.kem_dec_batch(ct, sk) == ss).all()
+    assert len({bytes(r) for r in ss}) == n
+    # wrong key / tampered ciphertext: decapsulation returns the rejection key, never the encapsulated secret
+    rolled = np.roll(sk, 1, axis=0)
+    assert not (ctx.kem_dec_batch(ct, rolled) == ss).all(axis=1).any()
+    t = ct.copy(); t[:, 3] ^= 1
+    rej = ctx.kem_dec_batch(t, sk)
+    assert not (rej == ss).all(axis=1).any()
+    z = sk[:, -32:]
+    for i in (0, n - 1):
+        assert bytes(rej[i]) == hashlib.shake_256(bytes(z[i]) + bytes(t[i])).digest(32)
+    if O.ref(k) is not None:
+        for i in (0, 17, n - 1):
+            rct, rss = O.ref_kem_enc_derand(k, pk[i], coins[i])
+            assert bytes(rct) == bytes(ct[i]) and bytes(rss) == bytes(ss[i])
+            assert bytes(O.ref_kem_dec(k, t[i], sk[i])) == bytes(rej[i])
+            assert bytes(O.ref_kem_dec(k, ct[i], rolled[i])) == bytes(ctx.kem_dec_batch(ct[i:i + 1], rolled[i:i + 1])[0])
+
+
+@pytest.mark.parametrize("k", [2, 3, 4])
+def test_main_cpp_sequence_with_kem(ctxs, k):
+    """The whole of main.cpp under one DRBG: struct-level prove/verify, kyber_verifiable_keygen + kosk_verify, then
+    crypto_kem_enc (coins = the next randombytes call) and crypto_kem_dec."""
+    ctx = ctxs(k)
+    seed = O.seed_of(900 + k)
+    got = _struct_sequence(ctx, seed)
+    assert ctx.verify(got["pi"], got["inst"]) is True
+    calls = ctx.rng_calls()
+    ct, ss = ctx.crypto_kem_enc(got["pk"])
+    assert ctx.rng_calls() == calls + 1
+    assert ctx.crypto_kem_dec(ct, got["sk"]) == ss
+    if O.ref(k) is not None:
+        rct, rss = O.ref_kem_enc_at(k, seed, calls, got["pk"])
+        assert bytes(rct) == ct and bytes(rss) == ss
