@@ -109,6 +109,7 @@ size_t kosk_b200_randomness_bytes(int kyber_k);
 size_t kosk_b200_range_proof_bytes(int kyber_k);
 int kosk_b200_rng_reset(kosk_b200_ctx *ctx, const uint8_t seed[32]);      /* seed the DRBG, call counter = 0 */
 uint32_t kosk_b200_rng_calls(const kosk_b200_ctx *ctx);
+int kosk_b200_verifiable_keygen_rng(kosk_b200_ctx *ctx, uint8_t *pk, uint8_t *sk, uint8_t *pi);   /* kosk.cpp:72-86 on the context DRBG */
 int kosk_b200_prepare_randomness(kosk_b200_ctx *ctx, void *rand);          /* mlwe_prover.cpp:4-39 */
 int kosk_b200_prepare_range_proof(kosk_b200_ctx *ctx, void *eta);          /* mlwe_prover.cpp:41-59 */
 int kosk_b200_keygen(kosk_b200_ctx *ctx, uint8_t *pk, uint8_t *sk, void *inst /* may be NULL */);   /* kosk.cpp:4-70 */

@@ -17,7 +17,7 @@ EXPORTS = [
     "kosk_b200_prove_batch", "kosk_b200_prove_batch_async", "kosk_b200_verify_batch", "kosk_b200_prove_batch_device", "kosk_b200_verify_batch_device",
     "kosk_b200_share_eval", "kosk_b200_sha3_256_rows", "kosk_b200_ntt_rows", "kosk_b200_share_eval_device",
     "kosk_b200_kernel_launches", "kosk_b200_debug_fetch", "kosk_b200_debug_trace", "kosk_b200_sync",
-    "kosk_b200_inst_bytes", "kosk_b200_randomness_bytes", "kosk_b200_range_proof_bytes", "kosk_b200_rng_reset", "kosk_b200_rng_calls",
+    "kosk_b200_inst_bytes", "kosk_b200_randomness_bytes", "kosk_b200_range_proof_bytes", "kosk_b200_rng_reset", "kosk_b200_rng_calls", "kosk_b200_verifiable_keygen_rng",
     "kosk_b200_prepare_randomness", "kosk_b200_prepare_range_proof", "kosk_b200_keygen", "kosk_b200_prove", "kosk_b200_verify",
     "kosk_b200_ct_bytes", "kosk_b200_kem_enc_derand_batch", "kosk_b200_kem_dec_batch", "kosk_b200_kem_enc_derand_batch_device", "kosk_b200_kem_dec_batch_device",
     "kosk_b200_kem_enc", "kosk_b200_kem_dec",
@@ -76,6 +76,7 @@ def load_library(path=None):
     lib.kosk_b200_rng_reset.argtypes = [vp, u8p]
     lib.kosk_b200_rng_calls.argtypes = [vp]
     lib.kosk_b200_rng_calls.restype = ctypes.c_uint32
+    lib.kosk_b200_verifiable_keygen_rng.argtypes = [vp, u8p, u8p, u8p]
     lib.kosk_b200_prepare_randomness.argtypes = [vp, u8p]
     lib.kosk_b200_prepare_range_proof.argtypes = [vp, u8p]
     lib.kosk_b200_keygen.argtypes = [vp, u8p, u8p, u8p]
@@ -158,6 +159,12 @@ class KoskContext:
 
     def rng_calls(self):
         return int(self.lib.kosk_b200_rng_calls(self._h))
+
+    def verifiable_keygen_rng(self):
+        """kyber_verifiable_keygen on the context DRBG (continues the call counter instead of starting a fresh seed)."""
+        pk, sk, pi = np.empty(self.pk_bytes, np.uint8), np.empty(self.sk_bytes, np.uint8), np.empty(self.proof_bytes, np.uint8)
+        self._check(self.lib.kosk_b200_verifiable_keygen_rng(self._h, _ptr(pk), _ptr(sk), _ptr(pi)), "verifiable_keygen_rng")
+        return bytes(pk), bytes(sk), bytes(pi)
 
     def prepare_randomness(self):
         out = np.empty(self.lib.kosk_b200_randomness_bytes(self.k), np.uint8)

@@ -171,6 +171,25 @@ int kosk_b200_rng_reset(kosk_b200_ctx *c, const uint8_t seed[32])
 }
 uint32_t kosk_b200_rng_calls(const kosk_b200_ctx *c) { return c ? c->raw->calls : 0; }
 
+// kyber_verifiable_keygen (kosk.cpp:72-86) drawing from the context DRBG at its current call number, like every other
+// function of this file (the seeded form kosk_b200_verifiable_keygen starts a fresh DRBG per proof instead)
+int kosk_b200_verifiable_keygen_rng(kosk_b200_ctx *c, uint8_t *pk, uint8_t *sk, uint8_t *pi)
+{
+    if (!c || !pk || !sk || !pi) return fail(KOSK_E_ARG, "null argument");
+    Lane *ln; ProveBufs pb; int rc = raw_begin(c, ln, pb); if (rc) return rc;
+    RawState &rs = *c->raw;
+    const int base = (int)rs.calls;
+    pb.cb_key += base; pb.cb_rand += base; pb.cb_eta += base; pb.cb_prove += base;
+    rc = prove_chunk_k(c, *ln, pb, 1, ln->d_seeds, ln->d_pk, ln->d_sk, ln->d_pi, PH_OFFLINE | PH_ONLINE);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(pk, ln->d_pk, c->L.pk_bytes, cudaMemcpyDeviceToHost, ln->st));
+    CU(cudaMemcpyAsync(sk, ln->d_sk, c->L.sk_bytes, cudaMemcpyDeviceToHost, ln->st));
+    CU(cudaMemcpyAsync(pi, ln->d_pi, c->L.proof_bytes, cudaMemcpyDeviceToHost, ln->st));
+    CU(cudaStreamSynchronize(ln->st));
+    rs.calls += (uint32_t)c->sl.ncalls;
+    return KOSK_OK;
+}
+
 int kosk_b200_prepare_randomness(kosk_b200_ctx *c, void *rand_image)
 {
     if (!c || !rand_image) return fail(KOSK_E_ARG, "null argument");

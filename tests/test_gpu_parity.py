@@ -492,3 +492,24 @@ def test_main_cpp_sequence_with_kem(ctxs, k):
     if O.ref(k) is not None:
         rct, rss = O.ref_kem_enc_at(k, seed, calls, got["pk"])
         assert bytes(rct) == ct and bytes(rss) == ss
+
+
+@pytest.mark.parametrize("k", [2, 3, 4])
+def test_reference_main_cpp_runs_against_the_library(k):
+    """The reference's UNMODIFIED main.cpp (struct-level prove/verify, kyber_verifiable_keygen + kyber_kosk_verify, KEM
+    encaps/decaps) compiled against include/dropin/ and linked with libkosk_b200.so (`make -C oracle dropin-main`, done by
+    __graft_entry__.build() where /root/reference exists; the binary travels to the GPU box)."""
+    import subprocess
+    exe = os.path.join(O.ORACLE_DIR, "_ref", f"main_dropin_k{k}")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/main_dropin_k* not built (no /root/reference in this checkout)")
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    for line in ("[result] mlwe verify success", "[result] kyber kosk verify success", "[result] decapsulated ss is the same as the encapsulated",
+                 f"[proof size] {ctypes_proof_kib(k)} kilobytes"):
+        assert line in out.stdout, out.stdout
+
+
+def ctypes_proof_kib(k):
+    from mpcith_kyber_kosk_b200 import proof_bytes
+    return proof_bytes(k) // 1024
