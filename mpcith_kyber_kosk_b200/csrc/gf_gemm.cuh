@@ -186,4 +186,13 @@ static inline int gf_gemm_launch(const GemmArgs &g, int npad, int nbatch, cudaSt
     return 1;
 }
 
+// Tile height by occupancy: when 128-row tiles would not give every SM a CTA (a handful of proofs in flight), 64-row tiles
+// halve the latency of a tile; throughput-sized launches keep the 128-row tile.
+template <int TN>
+static inline int gf_gemm_launch_auto(const GemmArgs &g, int npad, int nbatch, cudaStream_t st)
+{
+    const long long ctas = (long long)(npad / (16 * TN)) * ((g.mtotal + 127) / 128) * nbatch;
+    return ctas < 148 ? gf_gemm_launch<4, 128, TN>(g, npad, nbatch, st) : gf_gemm_launch<8, 128, TN>(g, npad, nbatch, st);
+}
+
 }  // namespace kosk

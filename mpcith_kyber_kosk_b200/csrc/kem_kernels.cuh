@@ -35,30 +35,12 @@ __device__ __forceinline__ void invntt256_block(u16 *p, int tid)
     __syncthreads();
 }
 
-// centered binomial sample from a PRF stream (kyber/cbd.c:58-107), canonical residues
-template <int ETA>
-__device__ __forceinline__ void cbd_stream(ByteSponge &sp, u16 *dst)
-{
-    if (ETA == 2) {
-        for (int i = 0; i < 32; i++) {
-            uint32_t t = sp.next(); t |= (uint32_t)sp.next() << 8; t |= (uint32_t)sp.next() << 16; t |= (uint32_t)sp.next() << 24;
-            const uint32_t d = (t & 0x55555555u) + ((t >> 1) & 0x55555555u);
-            for (int j = 0; j < 8; j++) { const int x = (int)((d >> (4 * j)) & 3) - (int)((d >> (4 * j + 2)) & 3); dst[8 * i + j] = (u16)(x < 0 ? x + Q : x); }
-        }
-    } else {
-        for (int i = 0; i < 64; i++) {
-            uint32_t t = sp.next(); t |= (uint32_t)sp.next() << 8; t |= (uint32_t)sp.next() << 16;
-            const uint32_t d = (t & 0x249249u) + ((t >> 1) & 0x249249u) + ((t >> 2) & 0x249249u);
-            for (int j = 0; j < 4; j++) { const int x = (int)((d >> (6 * j)) & 7) - (int)((d >> (6 * j + 3)) & 7); dst[4 * i + j] = (u16)(x < 0 ? x + Q : x); }
-        }
-    }
-}
-
 template <int K>
 struct KemSmem {
     u16 At[K * K][256];                       // A^T in the NTT domain (gen_at)
     u16 sp[K][256], ep[K][256], b[K][256], t[K][256];
     u16 epp[256], v[256];
+    uint64_t blk[K * K > 2 * K + 1 ? K * K : 2 * K + 1][24];   // per-thread sponge output blocks of the samplers
     uint32_t mw[8];                           // message bits (dec)
     u8 m[32], coins[32], kr[64], hpk[32];
     u8 ct[K * 352 + 160];
@@ -98,18 +80,10 @@ template <int K>
 __device__ __forceinline__ void enc_public(KemSmem<K> &S, const u8 *pk, int tid, int first_thread)
 {
     const int g = tid - first_thread;
-    if (g >= 0 && g < K * K) {
-        const int i = g / K, j = g % K;
-        ByteSponge sp; sp.init(168);
-        sp.absorb(pk + 384 * K, 32);
-        u8 ij[2] = {(u8)i, (u8)j}; sp.absorb(ij, 2); sp.finalize(0x1F);      // transposed: xof_absorb(seed, i, j), indcpa.c:176-179
-        int ctr = 0;
-        while (ctr < 256) {
-            const uint32_t b0 = sp.next(), b1 = sp.next(), b2 = sp.next();
-            const uint32_t v0 = (b0 | (b1 << 8)) & 0xFFF, v1 = ((b1 >> 4) | (b2 << 4)) & 0xFFF;
-            if (v0 < (uint32_t)Q) S.At[g][ctr++] = (u16)v0;
-            if (ctr < 256 && v1 < (uint32_t)Q) S.At[g][ctr++] = (u16)v1;
-        }
+    if (g >= 0 && g < K * K) {                     // transposed: xof_absorb(seed, i, j), indcpa.c:176-179
+        uint64_t sd[4];
+        for (int w = 0; w < 4; w++) { uint64_t v = 0; for (int q = 0; q < 8; q++) v |= (uint64_t)pk[384 * K + 8 * w + q] << (8 * q); sd[w] = v; }
+        xof_rej_uniform(S.At[g], sd, (uint32_t)(g / K), (uint32_t)(g % K), S.blk[g]);
     }
     for (int i = 0; i < K; i++) {
         const u8 *a = pk + 384 * i + 3 * tid;
@@ -123,13 +97,12 @@ template <int K>
 __device__ __forceinline__ void enc_secret(KemSmem<K> &S, int tid)
 {
     constexpr int ETA1 = (K == 2) ? 3 : 2, DU = (K == 4) ? 11 : 10, DV = (K == 4) ? 5 : 4;
-    if (tid < 2 * K + 1) {
-        ByteSponge sp; sp.init(136);
-        sp.absorb(S.coins, 32);
-        u8 nonce = (u8)tid; sp.absorb(&nonce, 1); sp.finalize(0x1F);
-        if (tid < K) cbd_stream<ETA1>(sp, S.sp[tid]);
-        else if (tid < 2 * K) cbd_stream<2>(sp, S.ep[tid - K]);
-        else cbd_stream<2>(sp, S.epp);
+    if (tid < 2 * K + 1) {                         // getnoise_eta1 x K, getnoise_eta2 x (K + 1), nonces 0..2K (indcpa.c:278-282)
+        uint64_t key[4];
+        for (int w = 0; w < 4; w++) { uint64_t v = 0; for (int q = 0; q < 8; q++) v |= (uint64_t)S.coins[8 * w + q] << (8 * q); key[w] = v; }
+        if (tid < K) prf_cbd<ETA1>(S.sp[tid], key, (u8)tid, S.blk[tid]);
+        else if (tid < 2 * K) prf_cbd<2>(S.ep[tid - K], key, (u8)tid, S.blk[tid]);
+        else prf_cbd<2>(S.epp, key, (u8)tid, S.blk[tid]);
     }
     __syncthreads();
     for (int i = 0; i < K; i++) ntt256_block(S.sp[i], tid);

@@ -308,7 +308,8 @@ static void launch_share_eval(kosk_b200_ctx *c, const u16 *Y, u16 *SH, int slot_
         return;
     }
     g.half_last = 1;         // terms 407..415 of Y rows and of the S table are zero padding
-    c->launches += gf_gemm_launch<8, 128, 7>(g, GE_NCOLS7, 1, st);
+    // latency mode: a handful of proofs does not fill the 148 SMs with 128-row tiles; 64-row tiles halve the time of a tile
+    c->launches += gf_gemm_launch_auto<7>(g, GE_NCOLS7, 1, st);
 }
 // first share evaluation of a prove chunk over slots [lo, hi): the eta-constant sharings [seta0, s0) take the short path
 static void launch_share_eval_prove(kosk_b200_ctx *c, const ProveBufs &pb, int lo, int hi, int B, cudaStream_t st)
@@ -368,7 +369,7 @@ static int prove_chunk(kosk_b200_ctx *c, Lane &ln, const ProveBufs &bufs, int B,
         k_fs1<K><<<(B + 3) / 4, 128, 0, st>>>(pb.TCR, pb.PW, B);
     }
     prof_mark(c, ln, KOSK_PH_EVAL);
-    k_eval<K><<<dim3(3, B), 256, 0, st>>>(pb);
+    k_eval<K><<<dim3(B < 16 ? (NP + 127) / 128 : 3, B), 256, 0, st>>>(pb);     // few proofs: one party tile per CTA (latency); many: 4 tiles per CTA amortise the table load
     prof_mark(c, ln, KOSK_PH_OPEN);
     k_open<K><<<B, 128, 0, st>>>(pb);
     prof_mark(c, ln, KOSK_PH_SHARE2);

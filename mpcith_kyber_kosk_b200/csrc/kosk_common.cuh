@@ -15,6 +15,9 @@
 
 namespace kosk {
 
+typedef uint16_t u16;
+typedef uint8_t u8;
+
 constexpr int Q = 3329;
 constexpr int NP = 1454;          // MPCITH_N parties
 constexpr int NT = 150;           // MPCITH_T opened parties

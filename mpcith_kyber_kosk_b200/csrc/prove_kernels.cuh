@@ -64,8 +64,62 @@ __device__ __forceinline__ void basemul_pair(uint32_t &r0, uint32_t &r1, uint32_
 }
 
 // ---------------------------------------------------------------------------------------------
+// Thread-level samplers with the Keccak state in registers; `blk` is scratch private to the thread (shared memory).
+// SHAKE128(seed || b0 || b1) -> 256 residues by 12-bit rejection: gen_matrix / rej_uniform (indcpa.c:124-193).
+__device__ __forceinline__ void xof_rej_uniform(u16 *dst, const uint64_t seed[4], uint32_t b0, uint32_t b1, uint64_t *blk /* [21] */)
+{
+    uint64_t a[25];
+    keccak_zero(a);
+    a[0] = seed[0]; a[1] = seed[1]; a[2] = seed[2]; a[3] = seed[3];
+    a[4] = (uint64_t)b0 | ((uint64_t)b1 << 8) | (0x1FULL << 16);
+    a[20] = 0x8000000000000000ULL;                  // rate 168 = lanes 0..20
+    int ctr = 0;
+    while (ctr < 256) {
+        keccak_f1600(a);
+#pragma unroll
+        for (int l = 0; l < 21; l++) blk[l] = a[l];
+        const u8 *p = reinterpret_cast<const u8 *>(blk);
+        for (int g = 0; g < 56 && ctr < 256; g++) {
+            const uint32_t x0 = p[3 * g], x1 = p[3 * g + 1], x2 = p[3 * g + 2];
+            const uint32_t v0 = (x0 | (x1 << 8)) & 0xFFF, v1 = ((x1 >> 4) | (x2 << 4)) & 0xFFF;
+            if (v0 < (uint32_t)Q) dst[ctr++] = (u16)v0;
+            if (ctr < 256 && v1 < (uint32_t)Q) dst[ctr++] = (u16)v1;
+        }
+    }
+}
+// CBD_eta(SHAKE256(key || nonce)): poly_getnoise_eta1/eta2 (poly.c:225-249, cbd.c:58-107), canonical residues
+template <int ETA>
+__device__ __forceinline__ void prf_cbd(u16 *dst, const uint64_t key[4], u8 nonce, uint64_t *blk /* [24] */)
+{
+    uint64_t a[25];
+    prf_begin(a, key, nonce);
+#pragma unroll
+    for (int l = 0; l < 17; l++) blk[l] = a[l];
+    if (ETA == 3) {                                 // 192 bytes = 136 + 56
+        keccak_f1600(a);
+#pragma unroll
+        for (int l = 0; l < 7; l++) blk[17 + l] = a[l];
+    }
+    const u8 *p = reinterpret_cast<const u8 *>(blk);
+    if (ETA == 2) {
+        for (int i = 0; i < 32; i++) {
+            const uint32_t t = reinterpret_cast<const uint32_t *>(p)[i];
+            const uint32_t d = (t & 0x55555555u) + ((t >> 1) & 0x55555555u);
+            for (int j = 0; j < 8; j++) { const int x = (int)((d >> (4 * j)) & 3) - (int)((d >> (4 * j + 2)) & 3); dst[8 * i + j] = (u16)(x < 0 ? x + Q : x); }
+        }
+    } else {
+        for (int i = 0; i < 64; i++) {
+            const uint32_t t = (uint32_t)p[3 * i] | ((uint32_t)p[3 * i + 1] << 8) | ((uint32_t)p[3 * i + 2] << 16);
+            const uint32_t d = (t & 0x249249u) + ((t >> 1) & 0x249249u) + ((t >> 2) & 0x249249u);
+            for (int j = 0; j < 4; j++) { const int x = (int)((d >> (6 * j)) & 7) - (int)((d >> (6 * j + 3)) & 7); dst[4 * i + j] = (u16)(x < 0 ? x + Q : x); }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Keygen: kosk.cpp:4-70 (gen_matrix indcpa.c:168-193, poly_getnoise_eta1 poly.c:225-230, cbd.c:58-107,
-// polyvec_ntt, basemul_acc + tomont, tobytes poly.c:124-139).  One CTA of 128 threads per proof.
+// polyvec_ntt, basemul_acc + tomont, tobytes poly.c:124-139).  One CTA of 128 threads per proof: the two seed hashes and
+// H(pk) run warp-cooperatively on warp 0, the K*K matrix XOFs on the lanes of warp 0 and the 2K noise PRFs on warp 1.
 // Also emits the secrets of the s/e sharings and of the range-proof products z_j (mlwe_prover.cpp:338-372:
 // recon_secrets_2ddeg of a product sharing is the pointwise product of the secrets).
 template <int K>
@@ -78,51 +132,32 @@ __global__ void __launch_bounds__(128) k_keygen(ProveBufs pb)
     __shared__ u16 sA[K * K][256];
     __shared__ u16 sS[K][256], sE[K][256], sSh[K][256], sEh[K][256], sT[K][256];
     __shared__ uint64_t sSeed[8];
-    __shared__ u8 sPk[384 * K + 32];
+    __shared__ uint64_t sBlk[K * K + 2 * K][24];
+    __shared__ __align__(8) u8 sPk[384 * K + 32];
 
-    if (tid == 0) {
-        uint64_t sd[4], a[25];
+    if (tid < 32) {
+        // randombytes(buf, 64) (only bytes 0..31 are used, kosk.cpp:12-14), then sha3_512(coins || K): one state word per lane
+        WarpKeccak wk; wk.init();
         const uint64_t *gs = reinterpret_cast<const uint64_t *>(pb.seeds + 32 * (size_t)b);
-        for (int i = 0; i < 4; i++) sd[i] = gs[i];
-        drbg_begin(a, sd, pb.cb_key);               // randombytes(buf, 64): only bytes 0..31 are used (kosk.cpp:12-14)
-        uint64_t c0 = a[0], c1 = a[1], c2 = a[2], c3 = a[3];
-        keccak_zero(a);                             // sha3_512(coins || K): rate 72
-        a[0] = c0; a[1] = c1; a[2] = c2; a[3] = c3; a[4] = (uint64_t)K | (0x06ULL << 8); a[8] = 0x8000000000000000ULL;
-        keccak_f1600(a);
-        for (int i = 0; i < 8; i++) sSeed[i] = a[i];
+        uint64_t a = 0;
+        if (tid < 4) a = gs[tid];
+        if (tid == 4) a = (uint64_t)(uint32_t)pb.cb_key | (0x1FULL << 32);
+        if (tid == 16) a = 0x8000000000000000ULL;              // SHAKE256 rate 136 = lanes 0..16
+        a = wk.permute(a);
+        if (tid >= 4) a = 0;
+        if (tid == 4) a = (uint64_t)K | (0x06ULL << 8);
+        if (tid == 8) a = 0x8000000000000000ULL;               // SHA3-512 rate 72 = lanes 0..8
+        a = wk.permute(a);
+        if (tid < 8) sSeed[tid] = a;
     }
     __syncthreads();
     if (tid < K * K) {                              // A[i][j] <- SHAKE128(publicseed || j || i), 12-bit rejection
-        const int i = tid / K, j = tid % K;
-        ByteSponge sp; sp.init(168);
-        sp.absorb(reinterpret_cast<const u8 *>(sSeed), 32);
-        u8 ji[2] = {(u8)j, (u8)i}; sp.absorb(ji, 2); sp.finalize(0x1F);
-        int ctr = 0;
-        while (ctr < 256) {
-            uint32_t b0 = sp.next(), b1 = sp.next(), b2 = sp.next();
-            uint32_t v0 = (b0 | (b1 << 8)) & 0xFFF, v1 = ((b1 >> 4) | (b2 << 4)) & 0xFFF;
-            if (v0 < (uint32_t)Q) sA[tid][ctr++] = (u16)v0;
-            if (ctr < 256 && v1 < (uint32_t)Q) sA[tid][ctr++] = (u16)v1;
-        }
-    } else if (tid < K * K + 2 * K) {               // noise: PRF(noiseseed, nonce) -> CBD_eta
-        const int idx = tid - K * K;
-        u16 *dst = idx < K ? sS[idx] : sE[idx - K];
-        ByteSponge sp; sp.init(136);
-        sp.absorb(reinterpret_cast<const u8 *>(sSeed + 4), 32);
-        u8 nonce = (u8)idx; sp.absorb(&nonce, 1); sp.finalize(0x1F);
-        if (ETA == 2) {
-            for (int i = 0; i < 32; i++) {
-                uint32_t t = sp.next(); t |= (uint32_t)sp.next() << 8; t |= (uint32_t)sp.next() << 16; t |= (uint32_t)sp.next() << 24;
-                uint32_t d = (t & 0x55555555u) + ((t >> 1) & 0x55555555u);
-                for (int j = 0; j < 8; j++) { int x = (int)((d >> (4 * j)) & 3) - (int)((d >> (4 * j + 2)) & 3); dst[8 * i + j] = (u16)(x < 0 ? x + Q : x); }
-            }
-        } else {
-            for (int i = 0; i < 64; i++) {
-                uint32_t t = sp.next(); t |= (uint32_t)sp.next() << 8; t |= (uint32_t)sp.next() << 16;
-                uint32_t d = (t & 0x249249u) + ((t >> 1) & 0x249249u) + ((t >> 2) & 0x249249u);
-                for (int j = 0; j < 4; j++) { int x = (int)((d >> (6 * j)) & 7) - (int)((d >> (6 * j + 3)) & 7); dst[4 * i + j] = (u16)(x < 0 ? x + Q : x); }
-            }
-        }
+        const uint64_t ps[4] = {sSeed[0], sSeed[1], sSeed[2], sSeed[3]};
+        xof_rej_uniform(sA[tid], ps, (uint32_t)(tid % K), (uint32_t)(tid / K), sBlk[tid]);
+    } else if (tid >= 32 && tid < 32 + 2 * K) {     // noise: PRF(noiseseed, nonce) -> CBD_eta
+        const int idx = tid - 32;
+        const uint64_t ns[4] = {sSeed[4], sSeed[5], sSeed[6], sSeed[7]};
+        prf_cbd<ETA>(idx < K ? sS[idx] : sE[idx - K], ns, (u8)idx, sBlk[K * K + idx]);
     }
     __syncthreads();
     // secrets of [s_i], [e_i] and of the 2*eta range-proof products z_j = prod_{m<=j+1} (x - eta_m)
@@ -167,9 +202,19 @@ __global__ void __launch_bounds__(128) k_keygen(ProveBufs pb)
     __syncthreads();
     for (int i = tid; i < 384 * K + 32; i += 128) { pk[i] = sPk[i]; sk[384 * K + i] = sPk[i]; }
     if (tid < 32) sk[L.sk_bytes - 32 + tid] = reinterpret_cast<const u8 *>(sSeed + 4)[tid];
-    if (tid == 0) {
-        ByteSponge sp; sp.init(136); sp.absorb(sPk, 384 * K + 32); sp.finalize(0x06);
-        for (int i = 0; i < 32; i++) sk[L.sk_bytes - 64 + i] = sp.next();
+    if (tid < 32) {                                 // sha3_256(pk), warp-cooperative: 800 / 1184 / 1568 bytes = 5 / 8 / 11 full blocks + 15 / 12 / 9 words
+        WarpKeccak wk; wk.init();
+        constexpr int NB = (384 * K + 32) / 136, REMW = ((384 * K + 32) % 136) / 8;
+        static_assert((384 * K + 32) % 8 == 0, "pk is a whole number of sponge words");
+        const uint64_t *w = reinterpret_cast<const uint64_t *>(sPk);
+        uint64_t a = 0;
+#pragma unroll 1
+        for (int blk = 0; blk < NB; blk++) { if (tid < 17) a ^= w[blk * 17 + tid]; a = wk.permute(a); }
+        if (tid < REMW) a ^= w[NB * 17 + tid];
+        if (tid == REMW) a ^= 0x06ULL;
+        if (tid == 16) a ^= 0x8000000000000000ULL;
+        a = wk.permute(a);
+        if (tid < 4) for (int i = 0; i < 8; i++) sk[L.sk_bytes - 64 + 8 * tid + i] = (u8)(a >> (8 * i));
     }
     // keep A-hat and s-hat for the online phase
     for (int i = tid; i < K * K * 256; i += 128) pb.AH[(size_t)b * K * K * 256 + i] = (&sA[0][0])[i];
@@ -333,84 +378,6 @@ k_hash_records(const HashSrc hs, u8 *__restrict__ out_rows, u16 *__restrict__ ou
         for (int i = 0; i < 16; i++) o[(size_t)i * SLD] = (u16)(a[i >> 2] >> (16 * (i & 3)));
     }
 }
-
-// ---------------------------------------------------------------------------------------------
-// Warp-cooperative Keccak-f[1600]: lane t < 25 of a warp holds state word A[x][y], t = x + 5y; theta / pi / chi
-// exchange words with warp shuffles.  Used for the two strictly sequential Fiat-Shamir sponges (343 permutations
-// each, mlwe_prover.cpp:131-135, :445-449), where one proof per warp cuts the latency ~5x against one per thread.
-struct WarpKeccak {
-    int t, x, y, rho, src_pi, src_c1, src_c2, l5, l10, l15, l20, lm1, lp1;
-    __device__ __forceinline__ void init()
-    {
-        const int rho_tab[25] = {0, 1, 62, 28, 27, 36, 44, 6, 55, 20, 3, 10, 43, 25, 39, 41, 45, 15, 21, 8, 18, 2, 61, 56, 14};
-        const int lane = threadIdx.x & 31;
-        t = lane < 25 ? lane : 0; x = t % 5; y = t / 5;
-        int r = 0;
-#pragma unroll
-        for (int i = 0; i < 25; i++) if (i == t) r = rho_tab[i];
-        rho = r;
-        src_pi = lane < 25 ? ((3 * y + x) % 5) + 5 * x : lane;      // B[x][y] = rol(A[(x+3y)%5][x], ..)
-        l5 = lane < 25 ? (t + 5) % 25 : lane; l10 = lane < 25 ? (t + 10) % 25 : lane;
-        l15 = lane < 25 ? (t + 15) % 25 : lane; l20 = lane < 25 ? (t + 20) % 25 : lane;
-        lm1 = lane < 25 ? (x + 4) % 5 + 5 * y : lane; lp1 = lane < 25 ? (x + 1) % 5 + 5 * y : lane;
-        // chi reads B[x+1][y] and B[x+2][y]; fetch them straight from their pre-pi source lanes (one shuffle stage less)
-        const int x1 = (x + 1) % 5, x2 = (x + 2) % 5;
-        src_c1 = lane < 25 ? ((3 * y + x1) % 5) + 5 * x1 : lane;
-        src_c2 = lane < 25 ? ((3 * y + x2) % 5) + 5 * x2 : lane;
-    }
-    static __device__ __forceinline__ uint64_t shfl(uint64_t v, int src)
-    {
-        const uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)v, src), hi = __shfl_sync(0xffffffffu, (uint32_t)(v >> 32), src);
-        return ((uint64_t)hi << 32) | lo;
-    }
-    __device__ __forceinline__ uint64_t permute(uint64_t a) const
-    {
-        const bool lane0 = (threadIdx.x & 31) == 0;
-#pragma unroll 1
-        for (int r = 0; r < 24; r++) {
-            // theta: column parity (REDUX.XOR over per-column masks was measured 10x slower than four shuffles)
-            const uint64_t c = a ^ shfl(a, l5) ^ shfl(a, l10) ^ shfl(a, l15) ^ shfl(a, l20);
-            a ^= shfl(c, lm1) ^ rol64(shfl(c, lp1), 1);
-            uint32_t lo = (uint32_t)a, hi = (uint32_t)(a >> 32);           // rho: rotate left by a per-lane amount
-            if (rho & 32) { const uint32_t tmp = lo; lo = hi; hi = tmp; }
-            const uint32_t nh = __funnelshift_l(lo, hi, rho), nl = __funnelshift_l(hi, lo, rho);
-            const uint64_t ar = ((uint64_t)nh << 32) | nl;
-            const uint64_t b = shfl(ar, src_pi), b1 = shfl(ar, src_c1), b2 = shfl(ar, src_c2);   // pi, fused with chi's two neighbour reads
-            a = b ^ (~b1 & b2);                                            // chi
-            if (lane0) a ^= c_keccak_rc[r];                                // iota
-        }
-        return a;
-    }
-    // SHA3-256 of the 1454 x 32-byte digest rows of one proof; result: lanes 0..3 hold the digest words
-    __device__ __forceinline__ uint64_t tree_hash(const u8 *rows) const
-    {
-        const uint64_t *src = reinterpret_cast<const uint64_t *>(rows);
-        const int lane = threadIdx.x & 31;
-        constexpr int NFULL = TREE_BYTES / 136;        // 342 full rate blocks + 16 bytes
-        uint64_t a = 0, nxt = lane < 17 ? src[lane] : 0;
-#pragma unroll 1
-        for (int blk = 0; blk < NFULL; blk++) {
-            a ^= nxt;
-            nxt = 0;
-            if (blk + 1 < NFULL) { if (lane < 17) nxt = src[(blk + 1) * 17 + lane]; }
-            else if (lane < 2) nxt = src[NFULL * 17 + lane];
-            a = permute(a);
-        }
-        a ^= nxt;
-        if (lane == 2) a ^= 0x06ULL;
-        if (lane == 16) a ^= 0x8000000000000000ULL;
-        return permute(a);
-    }
-    // SHAKE256(digest || 0x01) (kyber_shake256_prf with nonce 1): state after the first permutation
-    __device__ __forceinline__ uint64_t prf1(uint64_t digest_state) const
-    {
-        const int lane = threadIdx.x & 31;
-        uint64_t a = lane < 4 ? digest_state : 0;
-        if (lane == 4) a = 1ULL | (0x1FULL << 8);
-        if (lane == 16) a = 0x8000000000000000ULL;
-        return permute(a);
-    }
-};
 
 // FS-1: alpha = BE16(SHAKE256(SHA3-256(Tcomm_0 || ... ) || 0x01)) mod q and the power table (mlwe_prover.cpp:130-153).
 // One warp per proof.

@@ -115,19 +115,11 @@ __global__ void __launch_bounds__(128) kv_setup(VerifyBufs vb, const u8 *__restr
         vb.TPK[((size_t)b * K + i) * 256 + 2 * tid] = (u16)((a[0] | ((u16)a[1] << 8)) & 0xFFF);
         vb.TPK[((size_t)b * K + i) * 256 + 2 * tid + 1] = (u16)(((a[1] >> 4) | ((u16)a[2] << 4)) & 0xFFF);
     }
-    if (tid < K * K && !vb.raw_inst) {      // gen_matrix (indcpa.c:168-193)
-        const int i = tid / K, j = tid % K;
-        ByteSponge sp; sp.init(168);
-        sp.absorb(pk + 384 * K, 32);
-        u8 ji[2] = {(u8)j, (u8)i}; sp.absorb(ji, 2); sp.finalize(0x1F);
-        u16 *dst = vb.AH + ((size_t)b * K * K + tid) * 256;
-        int ctr = 0;
-        while (ctr < 256) {
-            uint32_t b0 = sp.next(), b1 = sp.next(), b2 = sp.next();
-            uint32_t v0 = (b0 | (b1 << 8)) & 0xFFF, v1 = ((b1 >> 4) | (b2 << 4)) & 0xFFF;
-            if (v0 < (uint32_t)Q) dst[ctr++] = (u16)v0;
-            if (ctr < 256 && v1 < (uint32_t)Q) dst[ctr++] = (u16)v1;
-        }
+    if (tid < K * K && !vb.raw_inst) {      // gen_matrix (indcpa.c:168-193): A[i][j] <- SHAKE128(seed || j || i)
+        __shared__ uint64_t sBlk[K * K][21];
+        uint64_t sd[4];
+        for (int w = 0; w < 4; w++) { uint64_t v = 0; for (int q = 0; q < 8; q++) v |= (uint64_t)pk[384 * K + 8 * w + q] << (8 * q); sd[w] = v; }
+        xof_rej_uniform(vb.AH + ((size_t)b * K * K + tid) * 256, sd, (uint32_t)(tid % K), (uint32_t)(tid / K), sBlk[tid]);
     }
     __syncthreads();   // REST visible block-wide (written by this block)
     for (int idx = tid; idx < NR * 8; idx += 128) {
@@ -515,7 +507,7 @@ static int verify_chunk_t(VerifyBufs &vb, const VerifyTables &vt, int B, const u
     // beta/gamma reconstruction: ABG x R1
     g = GemmArgs{}; g.A = vb.ABG; g.Bt = vt.R1; g.C = vb.BS; g.lda = YLD; g.ldb = YLD; g.ldc = 256;
     g.mtotal = B * 2 * MK; g.ksteps = YLD / GE_BK; g.nvalid = 256; g.rpp = g.mtotal; g.c_off = 0; g.half_last = 1;
-    nl += gf_gemm_launch<8>(g, 256, 1, st);
+    nl += gf_gemm_launch_auto<8>(g, 256, 1, st);
     kv_check_bg<<<dim3(MK, B), 128, 0, st>>>(vb); nl++;
     // interpolation-apply, one Lagrange matrix per proof (batched over blockIdx.z)
     g = GemmArgs{}; g.A = vb.A1; g.Bt = vb.LM1; g.C = vb.YV; g.lda = YLD; g.ldb = YLD; g.ldc = YLD;
@@ -547,13 +539,13 @@ static int verify_chunk_t(VerifyBufs &vb, const VerifyTables &vt, int B, const u
             g.mtotal = B * g.rpp; g.ksteps = YLD / GE_BK; g.nvalid = NX; g.c_off = SOFF + NT + 1; g.tail = 1; g.tail_off = NL;
             if (gi == 1) { g.A = vb.YV + NL; g.Bt = vt.St + NL; g.ksteps = (YLD - NL) / GE_BK; g.tail_off = 0; g.addvec = vt.SU; g.scale_src = vb.YV; }
             g.half_last = 1;
-            nl += gf_gemm_launch<8, 128, 7>(g, GE_NCOLS7, 1, st);
+            nl += gf_gemm_launch_auto<7>(g, GE_NCOLS7, 1, st);
         }
     }
     kv_check_parties<K><<<dim3(ptiles, B), 128, 0, st>>>(vb, d_pi); nl++;
     g = GemmArgs{}; g.A = vb.U2; g.Bt = vt.R2; g.C = vb.UR; g.lda = VR2LD; g.ldb = VR2LD; g.ldc = 256;
     g.mtotal = B * d.n2rows; g.ksteps = VR2LD / GE_BK; g.nvalid = 256; g.rpp = g.mtotal;
-    nl += gf_gemm_launch<8>(g, 256, 1, st);
+    nl += gf_gemm_launch_auto<8>(g, 256, 1, st);
     {   // V16: view hashes of the opened parties, FS-2, compare
         constexpr int ETA = (K == 2) ? 3 : 2, NV = 16 + 2 * (K + MK + 2 * K + 1) + 4 * K + 8 * ETA * K;
         HashSrc hs{vb.VR, (long long)NT * d.vrld, d.vrld, 1, 0, nullptr, vb.I, NT};
