@@ -259,7 +259,7 @@ def run_b200(args):
     tv = time.perf_counter() - tv0
     assert ok.all(), "a measured proof failed verification"
     verify_stats = None
-    if args.verify:
+    if True:                                               # kyber_kosk_verify throughput on the proofs just produced (device-resident)
         d_ok = torch.empty(B, dtype=torch.uint8, device=dev)
         d_pi.copy_(h_pi.to(dev)); d_pk.copy_(h_pk.to(dev))
         ctx.verify_batch_device(B, d_pi.data_ptr(), d_pk.data_ptr(), d_ok.data_ptr(), stream)
@@ -270,7 +270,28 @@ def run_b200(args):
             ctx.verify_batch_device(B, d_pi.data_ptr(), d_pk.data_ptr(), d_ok.data_ptr(), stream)
         v1.record(); torch.cuda.synchronize()
         assert bool(d_ok.all())
-        verify_stats = {"verifies_per_s": B * max(1, args.steps // 2) / (v0.elapsed_time(v1) * 1e-3), "batch": B}
+        tvm = torch.tensor([v0.elapsed_time(v1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tvm, op=dist.ReduceOp.MAX)
+        verify_stats = {"verifies_per_s": world * B * max(1, args.steps // 2) / (float(tvm.item()) * 1e-3), "batch_per_gpu": B,
+                        "note": "kyber_kosk_verify, device-resident proofs, CUDA events, max over ranks"}
+
+    # ---- single-proof latency (BASELINE configs[2]): host API, one seed in -> pk, sk, proof out / proof in -> accept bit out
+    ctx_l = KoskContext(k, local, 8, 1)
+    ls = seeds_for_range(1 << 34, rank * 64, rank * 64 + 24)
+    lp = ctx_l.prove_batch(ls[:1])
+    tp, tvv = [], []
+    for i in range(1, 17):
+        t0l = time.perf_counter(); lp = ctx_l.prove_batch(ls[i:i + 1]); tp.append(time.perf_counter() - t0l)
+    for i in range(16):
+        t0l = time.perf_counter(); okl = ctx_l.verify_batch(lp[2], lp[0]); tvv.append(time.perf_counter() - t0l)
+    assert okl.all()
+    ctx_l.close()
+    lat = torch.tensor([float(np.median(tp)) * 1e3, float(np.median(tvv)) * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(lat, op=dist.ReduceOp.MAX)
+    latency_stats = {"prove_ms": float(lat[0].item()), "verify_ms": float(lat[1].item()),
+                     "note": "median of 16 single calls through the host-buffer C ABI (copies included), max over ranks; one proof uses one GPU"}
 
     tensor_stats = None
     if rank == 0 and not args.no_tensor_probe:
@@ -339,6 +360,7 @@ def run_b200(args):
         }
         if verify_stats:
             out["verify"] = verify_stats
+        out["single_proof_latency"] = latency_stats
         if tensor_stats:
             out["experimental_tensor_path"] = tensor_stats
         if not args.no_cpu_baseline and world == 1:

@@ -113,5 +113,36 @@ out["f1_offline_online_split"] = {"batch": 1024, "offline_s_incl_alloc": round(t
                                   "online_single_proof_latency_ms": round(1e3 * float(np.median(ts)), 3)}
 print(json.dumps({"f1": out["f1_offline_online_split"]}), flush=True)
 pool.close(); p1.close(); ctx.close()
+# ---- struct-level API and Kyber KEM on the generated keys ----
+f23 = {}
+for k in (2, 3, 4):
+    ctx = KoskContext(k, 0, 1024, 1)
+    ctx.rng_reset(bytes(range(32)))
+    rand = ctx.prepare_randomness(); eta = ctx.prepare_range_proof(); pk, sk, inst = ctx.kyber_keygen(); pi = ctx.prove(inst, rand, eta)
+    def wall(fn, n=10):
+        ts = []
+        for _ in range(n):
+            t0 = time.perf_counter(); fn(); ts.append(time.perf_counter() - t0)
+        return round(1e3 * float(np.median(ts)), 3)
+    row = {"prepare_randomness_ms": wall(ctx.prepare_randomness), "prepare_range_proof_ms": wall(ctx.prepare_range_proof),
+           "kyber_keygen_ms": wall(ctx.kyber_keygen), "prove_ms": wall(lambda: ctx.prove(inst, rand, eta)), "verify_ms": wall(lambda: ctx.verify(pi, inst))}
+    n = 16384
+    pks, sks, _ = ctx.prove_batch(seeds_for_range(9, 0, 1024))
+    reps = n // 1024
+    d_pk = torch.from_numpy(np.tile(pks, (reps, 1))).to(dev); d_sk = torch.from_numpy(np.tile(sks, (reps, 1))).to(dev)
+    d_coins = torch.randint(0, 256, (n, 32), dtype=torch.uint8, device=dev)
+    d_ct = torch.empty(n * ctx.ct_bytes, dtype=torch.uint8, device=dev); d_ss = torch.empty(n * 32, dtype=torch.uint8, device=dev); d_ss2 = torch.empty(n * 32, dtype=torch.uint8, device=dev)
+    e_ms = ev_time(lambda: ctx.kem_enc_derand_batch_device(n, d_pk.data_ptr(), d_coins.data_ptr(), d_ct.data_ptr(), d_ss.data_ptr(), st), 5)
+    d_ms = ev_time(lambda: ctx.kem_dec_batch_device(n, d_ct.data_ptr(), d_sk.data_ptr(), d_ss2.data_ptr(), st), 5)
+    assert bool((d_ss == d_ss2).all())
+    row.update({"kem_batch": n, "kem_enc_per_s": round(n / e_ms * 1e3), "kem_dec_per_s": round(n / d_ms * 1e3),
+                "kem_enc_single_ms": wall(lambda: ctx.crypto_kem_enc(bytes(pks[0]))), "kem_dec_single_ms": None})
+    ct1, ss1 = ctx.crypto_kem_enc(bytes(pks[0]))
+    row["kem_dec_single_ms"] = wall(lambda: ctx.crypto_kem_dec(ct1, bytes(sks[0])))
+    f23[f"kyber{256*k}"] = row
+    ctx.close()
+    del d_pk, d_sk, d_ct
+out["f2_struct_api_and_f3_kem"] = f23
+print(json.dumps({"f2_f3": f23}), flush=True)
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open("gpurun_out/configs.json", "w"), indent=1)
