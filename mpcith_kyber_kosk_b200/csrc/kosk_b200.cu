@@ -70,7 +70,7 @@ struct Lane {
 };
 
 struct kosk_b200_ctx {
-    int k = 0, device = 0, chunk = 0, use_tensor = 0, fuse_fs = 1, fuse_max = 128;
+    int k = 0, device = 0, chunk = 0, use_tensor = 0, fuse_fs = 0, fuse_max = 128;
     int *d_status = nullptr;               // device word set by a kernel that gave up waiting (never expected)
     size_t next_lane = 0;
     cudaEvent_t last_computed = nullptr;   // compute-done event of the most recently enqueued sub-batch (any lane)
@@ -356,9 +356,10 @@ static int prove_chunk(kosk_b200_ctx *c, Lane &ln, const ProveBufs &bufs, int B,
     if (!on) { prof_mark(c, ln, -1); CU(cudaEventRecord(ln.computed, st)); c->last_computed = ln.computed; CU(cudaGetLastError()); return KOSK_OK; }
     prof_mark(c, ln, KOSK_PH_COMMIT);
     HashSrc hc{pb.SH, (long long)sl.nslot * SLD, 1, SLD, SOFF, c->d_tab_commit, nullptr, 0};
-    // Latency mode (small sub-batches): commit hashes and the FS-1 sponge of a proof in one CTA, so the sponge starts while the
-    // parties are still being hashed.  For large sub-batches the fused form is hash-throughput bound on the SM sub-partitions
-    // that host hasher warps (registers allow only 2 hasher warps per proof at 1024 proofs in flight) and gains nothing.
+    // Fused form (opt-in, KOSK_B200_FUSE_FS=1, sub-batches <= fuse_max): commit hashes and the FS-1 sponge of a proof in one CTA, so
+    // the sponge starts while the parties are still being hashed.  Off by default: its sponge warp shares an SM with the hasher warps
+    // and runs 2.9 us per permutation against 2.6 us for the standalone sponge kernel, which costs more than the 25 us of hashing
+    // it hides (single proof: 2.53 ms fused, 2.37 ms unfused); for large sub-batches it is hash-throughput bound and gains nothing.
     const bool fuse = c->fuse_fs && B <= c->fuse_max;
     if (fuse) {
         k_hash_fs<K, NCOMMIT, 1, 2><<<B, 96, 0, st>>>(hc, pb.TCR, pb.SH, sl.nslot, sl.TC0, pb.PW, nullptr, nullptr, c->d_status);
