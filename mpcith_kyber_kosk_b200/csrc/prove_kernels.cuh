@@ -228,24 +228,35 @@ template <int K>
 __global__ void __launch_bounds__(64) k_expand_f(ProveBufs pb)
 {
     const Slots sl = make_slots(K);
-    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= pb.B * sl.F) return;
-    const int b = gid / sl.F, i = gid % sl.F;
-    uint64_t sd[4], a[25];
-    const uint64_t *gs = reinterpret_cast<const uint64_t *>(pb.seeds + 32 * (size_t)b);
+    // rows are staged in shared memory and written out by the whole CTA: a thread storing its own row directly touches one 32-byte
+    // sector per 2-byte element (rows are 832 bytes apart)
+    __shared__ __align__(16) u16 srow[64][256 + 8];
+    const int gid0 = blockIdx.x * 64, gid = gid0 + threadIdx.x, total = pb.B * sl.F;
+    if (gid < total) {
+        const int b = gid / sl.F, i = gid % sl.F;
+        uint64_t sd[4], a[25];
+        const uint64_t *gs = reinterpret_cast<const uint64_t *>(pb.seeds + 32 * (size_t)b);
 #pragma unroll
-    for (int w = 0; w < 4; w++) sd[w] = gs[w];
-    drbg_begin(a, sd, pb.cb_rand + i);
-    uint64_t key[4] = {a[0], a[1], a[2], a[3]};
-    prf_begin(a, key, (u8)i);
-    u16 *dst = yrow(pb, sl, b, sl.f0 + i);
+        for (int w = 0; w < 4; w++) sd[w] = gs[w];
+        drbg_begin(a, sd, pb.cb_rand + i);
+        uint64_t key[4] = {a[0], a[1], a[2], a[3]};
+        prf_begin(a, key, (u8)i);
+        u16 *dst = srow[threadIdx.x];
 #pragma unroll 1
-    for (int blk = 0; blk < 4; blk++) {             // 512 bytes = 3 x 136 + 104
+        for (int blk = 0; blk < 4; blk++) {             // 512 bytes = 3 x 136 + 104
 #pragma unroll
-        for (int v = 0; v < 68; v++) {
-            if (blk * 68 + v < 256) dst[blk * 68 + v] = (u16)(lane_be16(a[v >> 2], v & 3) % (uint32_t)Q);
+            for (int v = 0; v < 68; v++) {
+                if (blk * 68 + v < 256) dst[blk * 68 + v] = (u16)(lane_be16(a[v >> 2], v & 3) % (uint32_t)Q);
+            }
+            if (blk < 3) keccak_f1600(a);
         }
-        if (blk < 3) keccak_f1600(a);
+    }
+    __syncthreads();
+    const int nrow = min(64, total - gid0);
+    for (int idx = threadIdx.x; idx < nrow * 32; idx += 64) {         // 32 x 16-byte chunks per row
+        const int r = idx >> 5, c = idx & 31, g = gid0 + r;
+        u16 *dst = yrow(pb, sl, g / sl.F, sl.f0 + g % sl.F);
+        reinterpret_cast<uint4 *>(dst)[c] = reinterpret_cast<const uint4 *>(srow[r])[c];
     }
 }
 
@@ -272,44 +283,62 @@ __global__ void __launch_bounds__(64) k_tails(ProveBufs pb)
 {
     const Slots sl = make_slots(K);
     const int nfresh = sl.n1 + K;                   // all challenge-independent sharings + [A s]
-    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= pb.B * nfresh) return;
-    const int b = gid / nfresh, idx = gid % nfresh;
-    // call numbers relative to the first call of prepare_randomness (F seeds, then f_i / NTT_f_i alternating,
-    // mlwe_prover.cpp:8-38), prepare_range_proof (s / e alternating, :41-59) and prove (s_i / e_i alternating :89-101,
-    // [A s]_i :292-323, z chains :338-392)
-    int slot, call, group;
-    if (idx < sl.n1) {
-        slot = idx;
-        if (slot < sl.Tf0) { call = pb.cb_rand + sl.F + 2 * (slot - sl.f0); group = 1; }
-        else if (slot < sl.seta0) { call = pb.cb_rand + sl.F + 2 * (slot - sl.Tf0) + 1; group = 1; }
-        else if (slot < sl.eeta0) { call = pb.cb_eta + 2 * (slot - sl.seta0); group = 2; }
-        else if (slot < sl.s0) { call = pb.cb_eta + 2 * (slot - sl.eeta0) + 1; group = 2; }
-        else if (slot < sl.e0) { call = pb.cb_prove + 2 * (slot - sl.s0); group = 4; }
-        else if (slot < sl.zs0) { call = pb.cb_prove + 2 * (slot - sl.e0) + 1; group = 4; }
-        else if (slot < sl.ze0) { call = pb.cb_prove + 3 * K + 2 * (slot - sl.zs0); group = 4; }
-        else { call = pb.cb_prove + 3 * K + 2 * (slot - sl.ze0) + 1; group = 4; }
-    } else { slot = sl.As0 + (idx - sl.n1); call = pb.cb_prove + 2 * K + (idx - sl.n1); group = 4; }
-    if (!(pb.tails_mask & group)) return;
-    uint64_t sd[4], a[25];
-    const uint64_t *gs = reinterpret_cast<const uint64_t *>(pb.seeds + 32 * (size_t)b);
+    // tails are staged in shared memory and written out by the whole CTA (see k_expand_f); srow[t][0..159] = Y row elements 256..415
+    __shared__ __align__(16) u16 srow[64][YLD - 256];
+    __shared__ int sslot[64];                       // slot of the row, -1 = not produced by this launch
+    const int gid0 = blockIdx.x * 64, gid = gid0 + threadIdx.x, total = pb.B * nfresh;
+    sslot[threadIdx.x] = -1;
+    if (gid < total) {
+        const int b = gid / nfresh, idx = gid % nfresh;
+        // call numbers relative to the first call of prepare_randomness (F seeds, then f_i / NTT_f_i alternating,
+        // mlwe_prover.cpp:8-38), prepare_range_proof (s / e alternating, :41-59) and prove (s_i / e_i alternating :89-101,
+        // [A s]_i :292-323, z chains :338-392)
+        int slot, call, group;
+        if (idx < sl.n1) {
+            slot = idx;
+            if (slot < sl.Tf0) { call = pb.cb_rand + sl.F + 2 * (slot - sl.f0); group = 1; }
+            else if (slot < sl.seta0) { call = pb.cb_rand + sl.F + 2 * (slot - sl.Tf0) + 1; group = 1; }
+            else if (slot < sl.eeta0) { call = pb.cb_eta + 2 * (slot - sl.seta0); group = 2; }
+            else if (slot < sl.s0) { call = pb.cb_eta + 2 * (slot - sl.eeta0) + 1; group = 2; }
+            else if (slot < sl.e0) { call = pb.cb_prove + 2 * (slot - sl.s0); group = 4; }
+            else if (slot < sl.zs0) { call = pb.cb_prove + 2 * (slot - sl.e0) + 1; group = 4; }
+            else if (slot < sl.ze0) { call = pb.cb_prove + 3 * K + 2 * (slot - sl.zs0); group = 4; }
+            else { call = pb.cb_prove + 3 * K + 2 * (slot - sl.ze0) + 1; group = 4; }
+        } else { slot = sl.As0 + (idx - sl.n1); call = pb.cb_prove + 2 * K + (idx - sl.n1); group = 4; }
+        if (pb.tails_mask & group) {
+            sslot[threadIdx.x] = slot;
+            uint64_t sd[4], a[25];
+            const uint64_t *gs = reinterpret_cast<const uint64_t *>(pb.seeds + 32 * (size_t)b);
 #pragma unroll
-    for (int w = 0; w < 4; w++) sd[w] = gs[w];
-    drbg_begin(a, sd, call);
-    u16 *dst = yrow(pb, sl, b, slot);
+            for (int w = 0; w < 4; w++) sd[w] = gs[w];
+            drbg_begin(a, sd, call);
+            u16 *dst = srow[threadIdx.x];
 #pragma unroll 1
-    for (int blk = 0; blk < 3; blk++) {             // 302 bytes = 136 + 136 + 30
+            for (int blk = 0; blk < 3; blk++) {     // 302 bytes = 136 + 136 + 30
 #pragma unroll
-        for (int v = 0; v < 68; v++) {
-            if (blk * 68 + v <= NT) dst[256 + blk * 68 + v] = (u16)(lane_be16(a[v >> 2], v & 3) % (uint32_t)Q);
+                for (int v = 0; v < 68; v++) {
+                    if (blk * 68 + v <= NT) dst[blk * 68 + v] = (u16)(lane_be16(a[v >> 2], v & 3) % (uint32_t)Q);
+                }
+                if (blk < 2) keccak_f1600(a);
+            }
+            for (int c = NT + 1; c < YLD - 256; c++) dst[c] = 0;      // row padding (terms 407..415) must be zero
         }
-        if (blk < 2) keccak_f1600(a);
     }
-    for (int c = D1; c < YLD; c++) dst[c] = 0;
-    if (slot >= sl.seta0 && slot < sl.s0) {
-        int j = (slot - sl.seta0) % sl.E;           // same constant for the s and e copies
-        u16 ev = (u16)((j - sl.eta + Q) % Q);
-        for (int c = 0; c < 256; c++) dst[c] = ev;
+    __syncthreads();
+    const int nrow = min(64, total - gid0);
+    constexpr int CH = (YLD - 256) / 8;             // 20 x 16-byte chunks of tail + padding per row
+    for (int idx = threadIdx.x; idx < nrow * CH; idx += 64) {
+        const int r = idx / CH, c = idx % CH, slot = sslot[r];
+        if (slot < 0) continue;
+        u16 *dst = yrow(pb, sl, (gid0 + r) / nfresh, slot) + 256;
+        reinterpret_cast<uint4 *>(dst)[c] = reinterpret_cast<const uint4 *>(srow[r])[c];
+    }
+    // constant secrets of the eta sharings (mlwe_prover.cpp:42-48): same constant for the s and e copies
+    for (int idx = threadIdx.x; idx < nrow * 32; idx += 64) {
+        const int r = idx >> 5, c = idx & 31, slot = sslot[r];
+        if (slot < sl.seta0 || slot >= sl.s0) continue;
+        const uint32_t ev = (uint32_t)(((slot - sl.seta0) % sl.E - sl.eta + Q) % Q), w = ev | (ev << 16);
+        reinterpret_cast<uint4 *>(yrow(pb, sl, (gid0 + r) / nfresh, slot))[c] = make_uint4(w, w, w, w);
     }
 }
 
