@@ -62,6 +62,7 @@ struct Lane {
     cudaStream_t st = nullptr;
     cudaEvent_t done = nullptr;           // everything enqueued on the lane so far (join with the caller's stream)
     cudaEvent_t computed = nullptr;       // the kernels of the lane's latest sub-batch (the next sub-batch's kernels wait on it)
+    cudaEvent_t pre_tail = nullptr;       // ... up to its view hashes: FS-2 and the assembly may overlap the next sub-batch (tail overlap)
     ProveBufs pb{};
     u8 *d_seeds = nullptr, *d_pk = nullptr, *d_sk = nullptr, *d_pi = nullptr, *d_ok = nullptr;   // staging of the host-buffer API
     VerifyBufs vb{};
@@ -74,6 +75,8 @@ struct kosk_b200_ctx {
     int *d_status = nullptr;               // device word set by a kernel that gave up waiting (never expected)
     size_t next_lane = 0;
     cudaEvent_t last_computed = nullptr;   // compute-done event of the most recently enqueued sub-batch (any lane)
+    cudaEvent_t last_gate = nullptr;       // event the next prove sub-batch waits for: last_computed, or the previous sub-batch's pre_tail
+    int overlap_tail = 1;                  // KOSK_B200_OVERLAP_TAIL: let a sub-batch start while the previous one runs FS-2 + assembly
     Slots sl; Layout L;
     uint64_t launches = 0;
     // constant tables
@@ -152,6 +155,7 @@ static void ctx_free(kosk_b200_ctx *c)
         for (cudaEvent_t e : ln.ev) cudaEventDestroy(e);
         if (ln.done) cudaEventDestroy(ln.done);
         if (ln.computed) cudaEventDestroy(ln.computed);
+        if (ln.pre_tail) cudaEventDestroy(ln.pre_tail);
         if (ln.st) cudaStreamDestroy(ln.st);
     }
     if (c->ev_start) cudaEventDestroy(c->ev_start);
@@ -192,6 +196,7 @@ int kosk_b200_create_ex(kosk_b200_ctx **out, int k, int device, int max_chunk, i
     c->use_tensor = (flags & KOSK_F_TENSOR) ? 1 : 0;
     { const char *e = getenv("KOSK_B200_FUSE_FS"); if (e) c->fuse_fs = atoi(e); }
     { const char *e = getenv("KOSK_B200_FUSE_MAX"); if (e) c->fuse_max = atoi(e); }
+    { const char *e = getenv("KOSK_B200_OVERLAP_TAIL"); if (e) c->overlap_tail = atoi(e); }
     const Slots &sl = c->sl; const Layout &L = c->L;
     const size_t B = (size_t)c->chunk;
 #define ALLOC(ptr, bytes) do { if (cudaMalloc((void **)&(ptr), (bytes)) != cudaSuccess) { ctx_free(c); return fail(KOSK_E_NOMEM, "cudaMalloc failed for " #ptr); } } while (0)
@@ -263,6 +268,7 @@ int kosk_b200_create_ex(kosk_b200_ctx **out, int k, int device, int max_chunk, i
         CU(cudaStreamCreateWithFlags(&ln.st, cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&ln.computed, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ln.pre_tail, cudaEventDisableTiming));
     }
     CU(cudaEventCreate(&c->ev_start));
     CU(cudaDeviceSynchronize());
@@ -334,10 +340,13 @@ static int prove_chunk(kosk_b200_ctx *c, Lane &ln, const ProveBufs &bufs, int B,
     constexpr int NVIEW = 16 + NCOMMIT + 4 * K + 8 * ETA * K;
     const int ptiles = (NP + 127) / 128;
     const bool off = phases & PH_OFFLINE, on = phases & PH_ONLINE;
+    cudaEvent_t tail_gate = nullptr;
     // Lanes pipeline copies against compute, not compute against compute: the kernels of consecutive sub-batches run one
     // after the other (co-running them was measured to slow the latency-bound FS sponges 3x), while the D2H copy of a
     // finished sub-batch overlaps the kernels of the next one on the other lane.
-    if (c->last_computed && c->last_computed != ln.computed) CU(cudaStreamWaitEvent(st, c->last_computed, 0));
+    // Tail overlap: the previous sub-batch's FS-2 sponge (one latency-bound warp per proof, ~20 % of the issue slots) and its
+    // assembly (HBM-bound gather) leave the integer pipes to this sub-batch's keygen / expansion / share evaluation.
+    if (c->last_gate && c->last_gate != ln.computed && c->last_gate != ln.pre_tail) CU(cudaStreamWaitEvent(st, c->last_gate, 0));
     if (on && !(phases & PH_NOKEYGEN)) {
         prof_mark(c, ln, KOSK_PH_KEYGEN);
         k_keygen<K><<<B, 128, 0, st>>>(pb); c->launches++;
@@ -353,7 +362,7 @@ static int prove_chunk(kosk_b200_ctx *c, Lane &ln, const ProveBufs &bufs, int B,
     const int lo = off ? 0 : sl.s0, hi = on ? sl.n1 : sl.s0;
     prof_mark(c, ln, KOSK_PH_SHARE1);
     launch_share_eval_prove(c, pb, lo, hi, B, st);
-    if (!on) { prof_mark(c, ln, -1); CU(cudaEventRecord(ln.computed, st)); c->last_computed = ln.computed; CU(cudaGetLastError()); return KOSK_OK; }
+    if (!on) { prof_mark(c, ln, -1); CU(cudaEventRecord(ln.computed, st)); c->last_computed = c->last_gate = ln.computed; CU(cudaGetLastError()); return KOSK_OK; }
     prof_mark(c, ln, KOSK_PH_COMMIT);
     HashSrc hc{pb.SH, (long long)sl.nslot * SLD, 1, SLD, SOFF, c->d_tab_commit, nullptr, 0};
     // Fused form (opt-in, KOSK_B200_FUSE_FS=1, sub-batches <= fuse_max): commit hashes and the FS-1 sponge of a proof in one CTA, so
@@ -383,6 +392,7 @@ static int prove_chunk(kosk_b200_ctx *c, Lane &ln, const ProveBufs &bufs, int B,
         prof_mark(c, ln, KOSK_PH_FS2);
     } else {
         k_hash_records<NVIEW><<<dim3(ptiles, B), 128, 0, st>>>(hv, pb.VWR, nullptr, 0, 0);
+        if (c->overlap_tail && c->lanes.size() > 1) { CU(cudaEventRecord(ln.pre_tail, st)); tail_gate = ln.pre_tail; }
         prof_mark(c, ln, KOSK_PH_FS2);
         k_fs2<<<(B + 3) / 4, 128, 0, st>>>(pb.VWR, pb.I, pb.REST, B);
     }
@@ -390,6 +400,7 @@ static int prove_chunk(kosk_b200_ctx *c, Lane &ln, const ProveBufs &bufs, int B,
     k_assemble<K><<<dim3((NT + 31) / 32 + (NR + 31) / 32, B), 128, 0, st>>>(pb);
     prof_mark(c, ln, -1);
     CU(cudaEventRecord(ln.computed, st)); c->last_computed = ln.computed;
+    c->last_gate = tail_gate ? tail_gate : ln.computed;
     c->launches += fuse ? 6 : 8;
     CU(cudaGetLastError());
     return KOSK_OK;
@@ -411,7 +422,7 @@ static int verify_chunk_lane(kosk_b200_ctx *c, Lane &ln, int B, const u8 *d_pi, 
     prof_mark(c, ln, KOSK_PH_VERIFY);
     int nl = verify_chunk(c->k, ln.vb, vt, B, d_pi, d_pk, d_ok, ln.st);
     prof_mark(c, ln, -1);
-    CU(cudaEventRecord(ln.computed, ln.st)); c->last_computed = ln.computed;
+    CU(cudaEventRecord(ln.computed, ln.st)); c->last_computed = c->last_gate = ln.computed;
     if (nl < 0) return fail(KOSK_E_CUDA, "verify launch failed");
     c->launches += nl;
     CU(cudaGetLastError());
