@@ -37,6 +37,7 @@ struct GemmArgs {
     int half_last;           // 1: only the first 8 terms of the last 16-term step are non-zero (407 = 25*16 + 7)
     const u16 *colscale;     // optional per-column factor (canonical), applied after the reduction: C[m][n] = acc * colscale[n] mod q
     long long colscale_batch;
+    int colscale_by_group;   // 1: the factor row is chosen by the row's group m / rpp (one proof) instead of blockIdx.z
 };
 
 // TN = columns per thread: 8 -> 128-column CTA tile (4 + 4 split), 7 -> 112-column tile (4 + 2 + 1 split).  1303 columns
@@ -149,7 +150,7 @@ __global__ void __maxnreg__(NREG) k_gf_gemm(const GemmArgs g)
 #pragma unroll
         for (int j = 0; j < TN; j++) v[j] = (u16)gf_canon(acc[i][j]);
         if (g.colscale) {
-            const u16 *cs = g.colscale + (size_t)blockIdx.z * g.colscale_batch + n0;
+            const u16 *cs = g.colscale + (size_t)(g.colscale_by_group ? m / g.rpp : blockIdx.z) * g.colscale_batch + n0;
 #pragma unroll
             for (int j = 0; j < TN; j++) v[j] = (u16)gf_mul(v[j], cs[col_of(j)]);
         }

@@ -85,6 +85,7 @@ struct kosk_b200_ctx {
     int8_t *d_St0 = nullptr, *d_St1 = nullptr;   // experimental tensor path: 7-bit limb planes of S, [GE_NPAD][YLD] int8
     int16_t *d_SU = nullptr;               // [GE_NPAD] centered U[x] = sum_{j<256} S[x][j]: share of the all-ones secret vector
     int16_t *d_R1 = nullptr, *d_R2 = nullptr; // verifier: centered recon tables [256][YLD], [256][VR2LD]
+    int16_t *d_U1 = nullptr, *d_U2 = nullptr; // verifier: Cauchy interpolation operands 1 / (t - (p + 256)), [U1_ROWS][KP1], [256][KP2]
     u16 *d_inv = nullptr;                  // [3329] inverses
     u16 *d_fact = nullptr;                 // [2][FACT_N] factorials and inverse factorials mod q (verifier's Lagrange weights)
     int16_t *d_tab_commit = nullptr, *d_tab_view = nullptr;
@@ -145,7 +146,7 @@ static void ctx_free(kosk_b200_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    void *ptrs[] = {c->d_status, c->d_fact, c->tmpL0, c->tmpL1, c->d_St, c->d_St0, c->d_St1, c->d_SU, c->d_R1, c->d_R2, c->d_inv, c->d_tab_commit, c->d_tab_view};
+    void *ptrs[] = {c->d_U1, c->d_U2, c->d_status, c->d_fact, c->tmpL0, c->tmpL1, c->d_St, c->d_St0, c->d_St1, c->d_SU, c->d_R1, c->d_R2, c->d_inv, c->d_tab_commit, c->d_tab_view};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (Lane &ln : c->lanes) {
         free_prove_bufs(ln.pb);
@@ -234,6 +235,13 @@ int kosk_b200_create_ex(kosk_b200_ctx **out, int k, int device, int max_chunk, i
         ALLOC(c->d_R2, R2p.size() * 2); CU(cudaMemcpy(c->d_R2, R2p.data(), R2p.size() * 2, cudaMemcpyHostToDevice));
         std::vector<uint16_t> inv(Q, 0); for (int a = 1; a < Q; a++) inv[a] = (uint16_t)h_pow(a, Q - 2);
         ALLOC(c->d_inv, Q * 2); CU(cudaMemcpy(c->d_inv, inv.data(), Q * 2, cudaMemcpyHostToDevice));
+        {   // Cauchy operands of the verifier's interpolation (mlwe_verifier.cpp:188-224 etc.): U[t][p] = 1 / (t - (p + 256)), 0 where t is the node
+            std::vector<int16_t> U1((size_t)U1_ROWS * KP1, 0), U2((size_t)NL * KP2, 0);
+            for (int t = 0; t < D1; t++) for (int p = 0; p < KP1; p++) { const int dd = ((t - p - 256) % Q + Q) % Q; U1[(size_t)t * KP1 + p] = (int16_t)(dd ? gf_center(inv[dd]) : 0); }
+            for (int t = 0; t < NL; t++) for (int p = 0; p < KP2; p++) { const int dd = ((t - p - 256) % Q + Q) % Q; U2[(size_t)t * KP2 + p] = (int16_t)gf_center(inv[dd]); }
+            ALLOC(c->d_U1, U1.size() * 2); CU(cudaMemcpy(c->d_U1, U1.data(), U1.size() * 2, cudaMemcpyHostToDevice));
+            ALLOC(c->d_U2, U2.size() * 2); CU(cudaMemcpy(c->d_U2, U2.data(), U2.size() * 2, cudaMemcpyHostToDevice));
+        }
         std::vector<uint16_t> fc(2 * FACT_N);
         { uint32_t f = 1; for (int i = 0; i < FACT_N; i++) { if (i) f = f * i % Q; fc[i] = (uint16_t)f; fc[FACT_N + i] = inv[f]; } }
         ALLOC(c->d_fact, fc.size() * 2); CU(cudaMemcpy(c->d_fact, fc.data(), fc.size() * 2, cudaMemcpyHostToDevice));
@@ -417,7 +425,7 @@ static int prove_chunk_k(kosk_b200_ctx *c, Lane &ln, const ProveBufs &bufs, int 
 
 static int verify_chunk_lane(kosk_b200_ctx *c, Lane &ln, int B, const u8 *d_pi, const u8 *d_pk, u8 *d_ok)
 {
-    VerifyTables vt{c->d_St, c->d_R1, c->d_R2, c->d_inv, c->d_SU, c->d_fact};
+    VerifyTables vt{c->d_St, c->d_R1, c->d_R2, c->d_inv, c->d_SU, c->d_fact, c->d_U1, c->d_U2};
     if (c->last_computed && c->last_computed != ln.computed) CU(cudaStreamWaitEvent(ln.st, c->last_computed, 0));
     prof_mark(c, ln, KOSK_PH_VERIFY);
     int nl = verify_chunk(c->k, ln.vb, vt, B, d_pi, d_pk, d_ok, ln.st);

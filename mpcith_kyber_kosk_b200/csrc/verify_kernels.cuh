@@ -11,13 +11,18 @@
 namespace kosk {
 
 constexpr int VR2LD = 816;        // row stride of 813-term rows (16B-aligned rows, 51 k-steps)
-constexpr int LM1_ROWS = 512;     // 407 targets padded to the GEMM's 128-column tiles
+constexpr int LM1_ROWS = 512;     // 407 targets padded to the GEMM's column tiles (stride of PT1)
+// Interpolation operands indexed by PARTY (not by rest-set position): the first 407 (813) rest parties lie among parties
+// 0..556 (0..962) because at most 150 parties are opened, so one fixed Cauchy matrix U[t][p] = 1 / (t - (p + 256)) serves every proof.
+constexpr int KP1 = 560, KP2 = 976;          // party columns of the two operands (multiples of the 16-term k-step)
+constexpr int U1_ROWS = 448;                 // 407 targets in four 112-column tiles
 constexpr int OPLD = 160;         // opened-party values: beta[70] gamma[70] r[2k] NTT_r[2k]
 
 enum VFlag { VF_I = 1, VF_BG = 2, VF_SR = 4, VF_NTT = 8, VF_ASR = 16, VF_T = 32, VF_TREL = 64, VF_ETA = 128,
              VF_SUBETA = 256, VF_UZ = 512, VF_U2D = 1024, VF_FS2 = 2048, VF_STRICT = 4096 };
 
-struct VerifyTables { const int16_t *St, *R1, *R2; const u16 *inv; const int16_t *SU; const u16 *fact; /* [2][FACT_N]: i!, 1/i! */ };
+struct VerifyTables { const int16_t *St, *R1, *R2; const u16 *inv; const int16_t *SU; const u16 *fact; /* [2][FACT_N]: i!, 1/i! */
+                      const int16_t *U1, *U2; /* Cauchy operands [U1_ROWS][KP1], [256][KP2], centered */ };
 
 struct VerifyBufs {
     int *flags = nullptr;
@@ -26,7 +31,6 @@ struct VerifyBufs {
     u8 *TCR = nullptr, *VWR = nullptr;
     u16 *CR = nullptr, *VR = nullptr, *OPV = nullptr;
     u16 *ABG = nullptr, *BS = nullptr, *A1 = nullptr, *YV = nullptr, *A2 = nullptr, *UZ = nullptr, *VSH = nullptr, *U2 = nullptr, *UR = nullptr;
-    int16_t *LM1 = nullptr, *LM2 = nullptr;
     u16 *W1 = nullptr, *W2 = nullptr, *PT1 = nullptr, *PT2 = nullptr;   // barycentric weights per node / P(t) per target
     int k = 0, chunk = 0;
     int strict = 0;   // hardened decoding: off by default = the reference's accept set
@@ -48,7 +52,7 @@ KOSK_HD VDims make_vdims(int k)
 static inline void verify_free(VerifyBufs &v)
 {
     void *p[] = {v.flags, v.I, v.REST, v.I2, v.REST2, v.POS, v.AH, v.TPK, v.PW, v.TCR, v.VWR, v.CR, v.VR, v.OPV,
-                 v.ABG, v.BS, v.A1, v.YV, v.A2, v.UZ, v.VSH, v.U2, v.UR, v.LM1, v.LM2, v.W1, v.W2, v.PT1, v.PT2};
+                 v.ABG, v.BS, v.A1, v.YV, v.A2, v.UZ, v.VSH, v.U2, v.UR, v.W1, v.W2, v.PT1, v.PT2};
     for (void *q : p) if (q) cudaFree(q);
     v = VerifyBufs{};
 }
@@ -62,10 +66,9 @@ static inline int verify_alloc(VerifyBufs &v, int k, int chunk)
     VA(v.TCR, B * TREE_BYTES, 0); VA(v.VWR, B * TREE_BYTES, 0);
     VA(v.CR, B * NT * d.crld * 2, 1); VA(v.VR, B * NT * d.vrld * 2, 1); VA(v.OPV, B * NT * OPLD * 2, 1);
     VA(v.ABG, B * 2 * MK * YLD * 2, 1); VA(v.BS, B * 2 * MK * 256 * 2, 0);
-    VA(v.A1, B * d.n1rows * YLD * 2, 1); VA(v.YV, B * d.nyrows * YLD * 2, 1);
-    VA(v.A2, B * d.n2rows * VR2LD * 2, 1); VA(v.UZ, B * d.n2rows * 256 * 2, 0);
+    VA(v.A1, B * d.n1rows * KP1 * 2, 1); VA(v.YV, B * d.nyrows * YLD * 2, 1);
+    VA(v.A2, B * d.n2rows * KP2 * 2, 1); VA(v.UZ, B * d.n2rows * 256 * 2, 0);
     VA(v.VSH, B * d.nyrows * SLD * 2, 1); VA(v.U2, B * d.n2rows * VR2LD * 2, 1); VA(v.UR, B * d.n2rows * 256 * 2, 0);
-    VA(v.LM1, B * LM1_ROWS * YLD * 2, 1); VA(v.LM2, B * 256 * VR2LD * 2, 1);
     VA(v.W1, B * YLD * 2, 1); VA(v.W2, B * VR2LD * 2, 1); VA(v.PT1, B * LM1_ROWS * 2, 1); VA(v.PT2, B * 256 * 2, 1);
 #undef VA
     return 0;
@@ -215,42 +218,71 @@ __global__ void __launch_bounds__(128) kv_gather(VerifyBufs vb, const u8 *__rest
         else if (r < 3 * K) { off = L.o_t; mul = K; add = r - 2 * K; }
         else if (r < 3 * K + K * d.E) { off = L.o_seta; mul = K * d.E; add = r - 3 * K; }
         else { off = L.o_eeta; mul = K * d.E; add = r - 3 * K - K * d.E; }
-        u16 *dst = vb.A1 + ((size_t)b * d.n1rows + r) * YLD;
+        // operand row indexed by party: share * barycentric weight at the first 407 rest parties, 0 at opened / later parties
+        u16 *dst = vb.A1 + ((size_t)b * d.n1rows + r) * KP1;
         const u16 *w1 = vb.W1 + (size_t)b * YLD;
-        for (int j = tid; j < D1; j += 128) dst[j] = (u16)gf_mul(pi16(pi, off, (size_t)j * mul + add) % (uint32_t)Q, w1[j]);
+        const int16_t *pos = vb.POS + (size_t)b * NP;
+        for (int p = tid; p < KP1; p += 128) {
+            const int j = pos[p];
+            dst[p] = (j >= 0 && j < D1) ? (u16)gf_mul(pi16(pi, off, (size_t)j * mul + add) % (uint32_t)Q, w1[j]) : (u16)0;
+        }
     } else {
         const int r = row - 2 * MK - d.n1rows;              // r = w*K*M + i*M + m
         const int w = r / (K * d.M), im = r % (K * d.M);
-        u16 *dst = vb.A2 + ((size_t)b * d.n2rows + r) * VR2LD;
+        u16 *dst = vb.A2 + ((size_t)b * d.n2rows + r) * KP2;
         const u16 *w2 = vb.W2 + (size_t)b * VR2LD;
-        for (int j = tid; j < D2; j += 128) dst[j] = (u16)gf_mul(pi16(pi, w ? L.o_ue : L.o_us, (size_t)j * K * d.M + im) % (uint32_t)Q, w2[j]);
+        const int16_t *pos = vb.POS + (size_t)b * NP;
+        for (int p = tid; p < KP2; p += 128) {
+            const int j = pos[p];
+            dst[p] = (j >= 0 && j < D2) ? (u16)gf_mul(pi16(pi, w ? L.o_ue : L.o_us, (size_t)j * K * d.M + im) % (uint32_t)Q, w2[j]) : (u16)0;
+        }
     }
 }
 
-// Per-proof Lagrange matrices over the rest-party nodes x_k = rest[k] + 256 (barycentric form):
-//   l_k(t) = P(t) * w_k / (t - x_k): the GEMM operand holds only LM[t][k] = 1/(t - x_k); the weights w_k scale the
-//   gathered input rows (kv_gather) and P(t) scales the output columns (GemmArgs.colscale).  A target that is itself
-//   a node (t = x_h, only for t in 256..406) gets the row 1/w_h * delta_kh with P(t) = 1, i.e. the share y_h itself.
-//   LM1: t = 0..406 over x_0..x_406;  LM2: t = 0..255 over x_0..x_812.
+// Targets 256..406 of the d-degree interpolation are themselves nodes when party t - 256 is a rest party: the interpolant passes
+// through the share, so the value is the share itself (the Cauchy operand has a zero there and P(t) = 0).  grid (n1rows, B).
+template <int K>
+__global__ void __launch_bounds__(160) kv_node_targets(VerifyBufs vb, const u8 *__restrict__ pis)
+{
+    const Layout L = make_layout(K);
+    const VDims d = make_vdims(K);
+    const int b = blockIdx.y, r = blockIdx.x, p = threadIdx.x;
+    if (p > NT) return;
+    const int j = vb.POS[(size_t)b * NP + p];
+    if (j < 0) return;                                      // opened party: interpolated like any other target
+    const u8 *pi = pis + L.proof_bytes * (size_t)b;
+    size_t off; int mul, add;
+    if (r < K) { off = L.o_sr; mul = K; add = r; }
+    else if (r < 2 * K) { off = L.o_er; mul = K; add = r - K; }
+    else if (r < 3 * K) { off = L.o_t; mul = K; add = r - 2 * K; }
+    else if (r < 3 * K + K * d.E) { off = L.o_seta; mul = K * d.E; add = r - 3 * K; }
+    else { off = L.o_eeta; mul = K * d.E; add = r - 3 * K - K * d.E; }
+    vb.YV[((size_t)b * d.nyrows + r) * YLD + 256 + p] = (u16)(pi16(pi, off, (size_t)j * mul + add) % (uint32_t)Q);
+}
+
+// Lagrange interpolation over the rest-party nodes x_k = rest[k] + 256 in barycentric form,
+//   l_k(t) = P(t) * w_k / (t - x_k):
+// the GEMM operand is the fixed Cauchy matrix 1 / (t - x) (VerifyTables.U1 / U2, indexed by party); the weights w_k scale the
+// gathered input rows (kv_gather) and P(t) scales the output columns (GemmArgs.colscale).  This kernel computes w_k and P(t) per proof.
+//   d-degree:  t = 0..406 over x_0..x_406;  2d-degree: t = 0..255 over x_0..x_812.
 // The nodes are the integers of [256, hi] minus at most 150 "holes" (opened parties), so the O(n^2) products of the
 // barycentric weights and of P(t) = prod_m (t - x_m) collapse to factorials times a product over the holes:
 //   prod_{m != k} (x_k - x_m) = (x_k-256)! (hi-x_k)! (-1)^(hi-x_k) / prod_h (x_k - h)
 //   prod_m (t - x_m)          = (-1)^(hi-255) (hi-t)! / (255-t)! / prod_h (t - h)                      (t < 256)
 //                             = (t-256)! (hi-t)! (-1)^(hi-t) / prod_{h != t} (t - h)                  (t a hole in [256, hi])
+// A target that is itself a node (t = x_h, only for t in 256..406) has P(t) = 0; kv_node_targets writes the share there.
 constexpr int FACT_N = 1712;      // factorials up to hi <= 1709
 __global__ void __launch_bounds__(256) kv_lagrange(VerifyBufs vb, const u16 *__restrict__ inv_g, const u16 *__restrict__ fact_g)
 {
     const int b = blockIdx.x, tid = threadIdx.x;
-    __shared__ u16 x[D2], w[D2], P[D1], inv[Q], fact[FACT_N], ifact[FACT_N], hole[NT];
-    __shared__ int16_t hit[D1];
+    __shared__ u16 x[D2], inv[Q], fact[FACT_N], ifact[FACT_N], hole[NT];
     __shared__ int nh;
     for (int i = tid; i < Q; i += 256) inv[i] = inv_g[i];
     for (int i = tid; i < FACT_N; i += 256) { fact[i] = fact_g[i]; ifact[i] = fact_g[FACT_N + i]; }
     for (int i = tid; i < D2; i += 256) x[i] = (u16)(vb.REST[(size_t)b * NR + i] + 256);
     __syncthreads();
     for (int pass = 0; pass < 2; pass++) {
-        const int n = pass ? D2 : D1, nt = pass ? 256 : D1, ld = pass ? VR2LD : YLD;
-        int16_t *out = pass ? vb.LM2 + (size_t)b * 256 * VR2LD : vb.LM1 + (size_t)b * LM1_ROWS * YLD;
+        const int n = pass ? D2 : D1, nt = pass ? 256 : D1;
         const int hi = x[n - 1];
         if (tid == 0) {                                   // holes of [256, hi]: opened parties below the last node
             int c = 0;
@@ -264,33 +296,19 @@ __global__ void __launch_bounds__(256) kv_lagrange(VerifyBufs vb, const u16 *__r
             for (int i = 0; i < nh; i++) num = gf_mul(num, gf_sub(xk, hole[i]));
             uint32_t v = gf_mul(gf_mul(num, ifact[xk - 256]), ifact[hi - xk]);
             if ((hi - xk) & 1) v = gf_sub(0, v);
-            w[k] = (u16)v;
             (pass ? vb.W2 + (size_t)b * VR2LD : vb.W1 + (size_t)b * YLD)[k] = (u16)v;
         }
         for (int t = tid; t < nt; t += 256) {
-            uint32_t den = 1; int h = -1;
-            if (t >= 256) {                               // only in pass 0: t is a node (unit row) or a hole
-                int lo = 0, up = n - 1;                   // x ascending: binary search
-                while (lo < up) { const int mid = (lo + up) >> 1; if (x[mid] < t) lo = mid + 1; else up = mid; }
-                if (x[lo] == t) h = lo;
-            }
+            uint32_t den = 1; bool node = false;
+            if (t >= 256) node = vb.POS[(size_t)b * NP + (t - 256)] >= 0;       // only in pass 0: party t - 256 is a rest party = a node
             uint32_t v = 0;
-            if (h < 0) {
+            if (!node) {
                 for (int i = 0; i < nh; i++) { const uint32_t dd = gf_sub((uint32_t)t, hole[i]); if (dd) den = gf_mul(den, dd); }
                 if (t < 256) { v = gf_mul(fact[hi - t], ifact[255 - t]); if ((hi - 255) & 1) v = gf_sub(0, v); }
                 else { v = gf_mul(fact[t - 256], fact[hi - t]); if ((hi - t) & 1) v = gf_sub(0, v); }
                 v = gf_mul(v, inv[den]);
             }
-            P[t] = (u16)v; hit[t] = (int16_t)h;
-            (pass ? vb.PT2 + (size_t)b * 256 : vb.PT1 + (size_t)b * LM1_ROWS)[t] = (u16)(h >= 0 ? 1 : v);
-        }
-        __syncthreads();
-        for (int idx = tid; idx < nt * n; idx += 256) {
-            const int t = idx / n, k = idx % n;
-            int32_t v;
-            if (hit[t] >= 0) v = (k == hit[t]) ? gf_center(inv[w[k]]) : 0;
-            else v = gf_center(inv[gf_sub((uint32_t)t, x[k])]);
-            out[(size_t)t * ld + k] = (int16_t)v;
+            (pass ? vb.PT2 + (size_t)b * 256 : vb.PT1 + (size_t)b * LM1_ROWS)[t] = (u16)v;
         }
         __syncthreads();
     }
@@ -509,25 +527,16 @@ static int verify_chunk_t(VerifyBufs &vb, const VerifyTables &vt, int B, const u
     g.mtotal = B * 2 * MK; g.ksteps = YLD / GE_BK; g.nvalid = 256; g.rpp = g.mtotal; g.c_off = 0; g.half_last = 1;
     nl += gf_gemm_launch_auto<8>(g, 256, 1, st);
     kv_check_bg<<<dim3(MK, B), 128, 0, st>>>(vb); nl++;
-    // interpolation-apply, one Lagrange matrix per proof (batched over blockIdx.z)
-    g = GemmArgs{}; g.A = vb.A1; g.Bt = vb.LM1; g.C = vb.YV; g.lda = YLD; g.ldb = YLD; g.ldc = YLD;
-    g.a_batch = (long long)d.n1rows * YLD; g.b_batch = (long long)LM1_ROWS * YLD; g.c_batch = (long long)d.nyrows * YLD;
-    g.mtotal = d.n1rows; g.ksteps = YLD / GE_BK; g.nvalid = D1; g.rpp = g.mtotal; g.half_last = 1;
-    g.colscale = vb.PT1; g.colscale_batch = LM1_ROWS;
-    for (int o = 0; o < B; o += 32768) {
-        GemmArgs h = g; const int nb = min(32768, B - o);
-        h.A += (size_t)o * g.a_batch; h.Bt += (size_t)o * g.b_batch; h.C += (size_t)o * g.c_batch; h.colscale += (size_t)o * g.colscale_batch;
-        nl += gf_gemm_launch<4, 128, 7>(h, 448, nb, st);      // 407 targets in four 112-column tiles (LM1 has 512 zero-padded rows)
-    }
-    g = GemmArgs{}; g.A = vb.A2; g.Bt = vb.LM2; g.C = vb.UZ; g.lda = VR2LD; g.ldb = VR2LD; g.ldc = 256;
-    g.a_batch = (long long)d.n2rows * VR2LD; g.b_batch = (long long)256 * VR2LD; g.c_batch = (long long)d.n2rows * 256;
-    g.mtotal = d.n2rows; g.ksteps = VR2LD / GE_BK; g.nvalid = 256; g.rpp = g.mtotal;
-    g.colscale = vb.PT2; g.colscale_batch = 256;
-    for (int o = 0; o < B; o += 32768) {
-        GemmArgs h = g; const int nb = min(32768, B - o);
-        h.A += (size_t)o * g.a_batch; h.Bt += (size_t)o * g.b_batch; h.C += (size_t)o * g.c_batch; h.colscale += (size_t)o * g.colscale_batch;
-        nl += gf_gemm_launch<4>(h, 256, nb, st);
-    }
+    // interpolation-apply: rows of all proofs against the fixed Cauchy operands, columns scaled by each proof's P(t)
+    g = GemmArgs{}; g.A = vb.A1; g.Bt = vt.U1; g.C = vb.YV; g.lda = KP1; g.ldb = KP1; g.ldc = YLD;
+    g.mtotal = B * d.n1rows; g.ksteps = KP1 / GE_BK; g.nvalid = D1; g.rpp = d.n1rows; g.a_slots = d.n1rows; g.c_slots = d.nyrows;
+    g.colscale = vb.PT1; g.colscale_batch = LM1_ROWS; g.colscale_by_group = 1;
+    nl += gf_gemm_launch_auto<7>(g, U1_ROWS, 1, st);
+    kv_node_targets<K><<<dim3(d.n1rows, B), 160, 0, st>>>(vb, d_pi); nl++;
+    g = GemmArgs{}; g.A = vb.A2; g.Bt = vt.U2; g.C = vb.UZ; g.lda = KP2; g.ldb = KP2; g.ldc = 256;
+    g.mtotal = B * d.n2rows; g.ksteps = KP2 / GE_BK; g.nvalid = 256; g.rpp = d.n2rows; g.a_slots = d.n2rows; g.c_slots = d.n2rows;
+    g.colscale = vb.PT2; g.colscale_batch = 256; g.colscale_by_group = 1;
+    nl += gf_gemm_launch_auto<8>(g, 256, 1, st);
     kv_open<K><<<B, 128, 0, st>>>(vb); nl++;
     // regenerate every sharing at all 1454 parties: YV x S.  Row groups per proof: [0,3K) s+r, e+r, t | [3K, n1rows) the eta
     // sharings, whose 256 secrets were just checked to be one constant (short path: tail terms only) | [n1rows, nyrows)
