@@ -9,6 +9,7 @@
 // that every shared-memory read is a conflict-free (or broadcast) LDS.128; register-staged double buffering.
 #pragma once
 #include "kosk_common.cuh"
+#include <algorithm>
 
 namespace kosk {
 
@@ -38,11 +39,15 @@ struct GemmArgs {
     const u16 *colscale;     // optional per-column factor (canonical), applied after the reduction: C[m][n] = acc * colscale[n] mod q
     long long colscale_batch;
     int colscale_by_group;   // 1: the factor row is chosen by the row's group m / rpp (one proof) instead of blockIdx.z
+    // Latency mode (a handful of rows): split-K over blockIdx.z.  Every slice writes its raw int32 accumulators to
+    // ws[slice][row][ws_ld]; k_gf_gemm_finish sums the slices and runs the epilogue.  ws = nullptr disables it.
+    int32_t *ws; long long ws_elems; int ws_ld;
 };
+constexpr long long GE_WS_ELEMS = 6ll << 20;      // 24 MB of int32 partial sums per scratch set
 
 // TN = columns per thread: 8 -> 128-column CTA tile (4 + 4 split), 7 -> 112-column tile (4 + 2 + 1 split).  1303 columns
 // are 12 x 112 = 1344 (3 % padding) instead of 11 x 128 = 1408 (8 %); all shared loads stay conflict-free / broadcast.
-template <int TM, int NREG, int TN>
+template <int TM, int NREG, int TN, bool SPLITK = false>
 __global__ void __maxnreg__(NREG) k_gf_gemm(const GemmArgs g)
 {
     static_assert(TN == 8 || TN == 7, "TN");
@@ -51,9 +56,12 @@ __global__ void __maxnreg__(NREG) k_gf_gemm(const GemmArgs g)
     __shared__ __align__(16) int32_t Bs[2][GE_BK][BN];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-    const u16 *Ab = g.A + (size_t)blockIdx.z * g.a_batch;
-    const int16_t *Bb = g.Bt + (size_t)blockIdx.z * g.b_batch;
-    u16 *Cb = g.C + (size_t)blockIdx.z * g.c_batch;
+    const int zb = SPLITK ? 0 : blockIdx.z;
+    const int kt_lo = SPLITK ? (int)((long long)blockIdx.z * g.ksteps / gridDim.z) : 0;
+    const int kt_hi = SPLITK ? (int)((long long)(blockIdx.z + 1) * g.ksteps / gridDim.z) : g.ksteps;
+    const u16 *Ab = g.A + (size_t)zb * g.a_batch;
+    const int16_t *Bb = g.Bt + (size_t)zb * g.b_batch;
+    u16 *Cb = g.C + (size_t)zb * g.c_batch;
     // loader mapping: thread -> (row, 8-term half)
     const bool b_thr = tid < 2 * BN;
     const int lrb = b_thr ? tid % BN : 0, lhb = b_thr ? tid / BN : 0;
@@ -64,6 +72,7 @@ __global__ void __maxnreg__(NREG) k_gf_gemm(const GemmArgs g)
     const u16 *a_src = Ab;
     if (a_ok) a_src = Ab + ((size_t)(am / g.rpp) * g.a_slots + g.slot_lo + am % g.rpp) * g.lda + lha * 8;
     const int16_t *b_src = Bb + (size_t)(n0 + lrb) * g.ldb + lhb * 8;
+    if (SPLITK) { a_src += (size_t)kt_lo * GE_BK; b_src += (size_t)kt_lo * GE_BK; }
     // column c of this thread's TN-wide strip sits at tile column col_of(c)
     auto col_of = [&](int c) { return c < 4 ? tx * 4 + c : (TN == 8 ? 64 + tx * 4 + (c - 4) : (c < 6 ? 64 + tx * 2 + (c - 4) : 96 + tx)); };
 
@@ -94,11 +103,11 @@ __global__ void __maxnreg__(NREG) k_gf_gemm(const GemmArgs g)
     stage(0);
     __syncthreads();
 #pragma unroll 1
-    for (int kt = 0; kt < g.ksteps; kt++) {
-        const int buf = kt & 1;
-        if (kt + 1 < g.ksteps) {
-            if (a_ok) ra = *reinterpret_cast<const uint4 *>(a_src + (kt + 1) * GE_BK);
-            if (b_thr) rb = *reinterpret_cast<const uint4 *>(b_src + (kt + 1) * GE_BK);
+    for (int kt = kt_lo; kt < kt_hi; kt++) {
+        const int buf = (kt - kt_lo) & 1;
+        if (kt + 1 < kt_hi) {
+            if (a_ok) ra = *reinterpret_cast<const uint4 *>(a_src + (kt + 1 - kt_lo) * GE_BK);
+            if (b_thr) rb = *reinterpret_cast<const uint4 *>(b_src + (kt + 1 - kt_lo) * GE_BK);
         }
         auto mac = [&](int kk) {
             int32_t av[TM], bv[8];
@@ -133,7 +142,18 @@ __global__ void __maxnreg__(NREG) k_gf_gemm(const GemmArgs g)
 #pragma unroll
                 for (int j = 0; j < TN; j++) acc[i][j] = acc[i][j] % Q;
         }
-        if (kt + 1 < g.ksteps) { stage(buf ^ 1); __syncthreads(); }
+        if (kt + 1 < kt_hi) { stage(buf ^ 1); __syncthreads(); }
+    }
+    if (SPLITK) {            // raw partial sums of this k-slice; the epilogue runs in k_gf_gemm_finish
+#pragma unroll
+        for (int i = 0; i < TM; i++) {
+            const int m = m0 + (i / 4) * (BM / 2) + ty * 4 + (i & 3);
+            if (m >= g.mtotal) continue;
+            int32_t *w = g.ws + ((size_t)blockIdx.z * g.mtotal + m) * g.ws_ld + n0;
+#pragma unroll
+            for (int j = 0; j < TN; j++) w[col_of(j)] = acc[i][j];
+        }
+        return;
     }
     // epilogue: canonical residues, vector stores along the contiguous (party / coefficient) axis
 #pragma unroll
@@ -177,6 +197,23 @@ __global__ void __maxnreg__(NREG) k_gf_gemm(const GemmArgs g)
     }
 }
 
+// second pass of the split-K form: sum the k-slices and run the epilogue of k_gf_gemm (one thread per output element)
+__global__ void __launch_bounds__(256) k_gf_gemm_finish(const GemmArgs g, int nslices)
+{
+    const int m = blockIdx.y, n = blockIdx.x * 256 + threadIdx.x;
+    const size_t ar = (size_t)(m / g.rpp) * g.a_slots + g.slot_lo + m % g.rpp, cr = (size_t)(m / g.rpp) * g.c_slots + g.slot_lo + m % g.rpp;
+    if (n < g.nvalid) {
+        long long sum = 0;
+        for (int z = 0; z < nslices; z++) sum += g.ws[((size_t)z * g.mtotal + m) * g.ws_ld + n];
+        if (g.addvec) sum += (long long)gf_center(g.scale_src[ar * g.lda]) * (long long)g.addvec[n];
+        long long r = sum % Q; if (r < 0) r += Q;
+        uint32_t v = (uint32_t)r;
+        if (g.colscale) v = gf_mul(v, g.colscale[(size_t)(g.colscale_by_group ? m / g.rpp : 0) * g.colscale_batch + n]);
+        g.C[cr * g.ldc + g.c_off + n] = (u16)v;
+    }
+    if (g.tail && n <= NT) g.C[cr * g.ldc + g.c_off - (NT + 1) + n] = g.A[ar * g.lda + g.tail_off + n];
+}
+
 // host-side launcher; returns the number of kernels launched
 // npad = number of Bt rows available (zero padded to a multiple of the column tile)
 template <int TM, int NREG = 128, int TN = 8>
@@ -193,7 +230,18 @@ template <int TN>
 static inline int gf_gemm_launch_auto(const GemmArgs &g, int npad, int nbatch, cudaStream_t st)
 {
     const long long ctas = (long long)(npad / (16 * TN)) * ((g.mtotal + 127) / 128) * nbatch;
-    return ctas < 148 ? gf_gemm_launch<4, 128, TN>(g, npad, nbatch, st) : gf_gemm_launch<8, 128, TN>(g, npad, nbatch, st);
+    if (ctas >= 148) return gf_gemm_launch<8, 128, TN>(g, npad, nbatch, st);
+    const int ctas64 = (npad / (16 * TN)) * ((g.mtotal + 63) / 64);
+    int nz = std::min(std::min(8, g.ksteps / 4), 148 / std::max(1, ctas64));
+    if (nbatch == 1 && g.ws && nz >= 2 && (long long)nz * g.mtotal * npad <= g.ws_elems) {
+        // a handful of rows: 64-row tiles, k split over blockIdx.z so that the launch covers the SMs, then the epilogue pass
+        GemmArgs h = g; h.ws_ld = npad;
+        dim3 grid(npad / (16 * TN), (g.mtotal + 63) / 64, nz);
+        k_gf_gemm<4, 128, TN, true><<<grid, 256, 0, st>>>(h);
+        k_gf_gemm_finish<<<dim3((std::max(g.nvalid, NT + 1) + 255) / 256, g.mtotal), 256, 0, st>>>(h, nz);
+        return 2;
+    }
+    return gf_gemm_launch<4, 128, TN>(g, npad, nbatch, st);
 }
 
 }  // namespace kosk

@@ -121,7 +121,7 @@ static void prof_collect(kosk_b200_ctx *c)
 
 static void free_prove_bufs(ProveBufs &pb)
 {
-    void *lp[] = {pb.Y, pb.SH, pb.BG, pb.TCR, pb.VWR, pb.PW, pb.AH, pb.SHAT, pb.I, pb.REST, pb.YL0, pb.YL1};
+    void *lp[] = {pb.Y, pb.SH, pb.BG, pb.TCR, pb.VWR, pb.PW, pb.AH, pb.SHAT, pb.I, pb.REST, pb.YL0, pb.YL1, pb.WS};
     for (void *p : lp) if (p) cudaFree(p);
     pb = ProveBufs{};
 }
@@ -136,6 +136,7 @@ static int alloc_prove_bufs(ProveBufs &pb, const Slots &sl, int k, size_t B, boo
     PA(pb.AH, B * k * k * 256 * 2, 0); PA(pb.SHAT, B * k * 256 * 2, 0);
     PA(pb.I, B * NT * 2, 0); PA(pb.REST, B * NR * 2, 0);
     if (tensor) { PA(pb.YL0, B * sl.n2 * YLD, 1); PA(pb.YL1, B * sl.n2 * YLD, 1); }
+    PA(pb.WS, (size_t)GE_WS_ELEMS * 4, 0);
 #undef PA
     set_default_calls(pb, sl);
     return 0;
@@ -302,10 +303,11 @@ int kosk_b200_lanes(const kosk_b200_ctx *c) { return c ? (int)c->lanes.size() : 
 
 // ---- launch sequence for one chunk of B proofs on one lane ----
 static void launch_share_eval(kosk_b200_ctx *c, const u16 *Y, u16 *SH, int slot_lo, int rows, int y_slots, int sh_slots, int B, cudaStream_t st,
-                              bool const_secret = false, int8_t *YL0 = nullptr, int8_t *YL1 = nullptr)
+                              bool const_secret = false, int8_t *YL0 = nullptr, int8_t *YL1 = nullptr, int32_t *ws = nullptr)
 {
     if (rows <= 0) return;
     GemmArgs g{};
+    g.ws = ws; g.ws_elems = GE_WS_ELEMS;
     g.A = Y; g.Bt = c->d_St; g.C = SH; g.lda = YLD; g.ldb = YLD; g.ldc = SLD;
     g.mtotal = B * rows; g.ksteps = YLD / GE_BK; g.nvalid = NX; g.c_off = SOFF + NT + 1;
     g.rpp = rows; g.slot_lo = slot_lo; g.a_slots = y_slots; g.c_slots = sh_slots; g.tail = 1; g.tail_off = NL;
@@ -330,9 +332,9 @@ static void launch_share_eval_prove(kosk_b200_ctx *c, const ProveBufs &pb, int l
 {
     const Slots &sl = c->sl;
     const int a_lo = lo, a_hi = std::min(hi, sl.seta0), b_lo = std::max(lo, sl.seta0), b_hi = std::min(hi, sl.s0), c_lo = std::max(lo, sl.s0), c_hi = hi;
-    launch_share_eval(c, pb.Y, pb.SH, a_lo, a_hi - a_lo, sl.n2, sl.nslot, B, st, false, pb.YL0, pb.YL1);
-    launch_share_eval(c, pb.Y, pb.SH, b_lo, b_hi - b_lo, sl.n2, sl.nslot, B, st, true, pb.YL0, pb.YL1);
-    launch_share_eval(c, pb.Y, pb.SH, c_lo, c_hi - c_lo, sl.n2, sl.nslot, B, st, false, pb.YL0, pb.YL1);
+    launch_share_eval(c, pb.Y, pb.SH, a_lo, a_hi - a_lo, sl.n2, sl.nslot, B, st, false, pb.YL0, pb.YL1, pb.WS);
+    launch_share_eval(c, pb.Y, pb.SH, b_lo, b_hi - b_lo, sl.n2, sl.nslot, B, st, true, pb.YL0, pb.YL1, pb.WS);
+    launch_share_eval(c, pb.Y, pb.SH, c_lo, c_hi - c_lo, sl.n2, sl.nslot, B, st, false, pb.YL0, pb.YL1, pb.WS);
 }
 
 template <int K>
@@ -391,7 +393,7 @@ static int prove_chunk(kosk_b200_ctx *c, Lane &ln, const ProveBufs &bufs, int B,
     prof_mark(c, ln, KOSK_PH_OPEN);
     k_open<K><<<B, 128, 0, st>>>(pb);
     prof_mark(c, ln, KOSK_PH_SHARE2);
-    launch_share_eval(c, pb.Y, pb.SH, sl.n1, 4 * K, sl.n2, sl.nslot, B, st, false, pb.YL0, pb.YL1);
+    launch_share_eval(c, pb.Y, pb.SH, sl.n1, 4 * K, sl.n2, sl.nslot, B, st, false, pb.YL0, pb.YL1, pb.WS);
     prof_mark(c, ln, KOSK_PH_VIEW);
     k_derive<K><<<dim3(ptiles, B), 128, 0, st>>>(pb);
     HashSrc hv{pb.SH, (long long)sl.nslot * SLD, 1, SLD, SOFF, c->d_tab_view, nullptr, 0};

@@ -24,6 +24,7 @@ struct ProveBufs {
     u16 *SHAT;         // [B][k][256]   s-hat
     u16 *I, *REST;     // [B][150], [B][1304]
     int8_t *YL0, *YL1; // experimental tensor path only: 7-bit limb planes of Y, [B][n2][YLD] int8
+    int32_t *WS;       // [GE_WS_ELEMS] partial sums of the split-K share evaluation (latency mode, a handful of proofs)
     u8 *pk, *sk, *pi;  // outputs
     int B;
     // randombytes() call numbers (KOSK counter-mode DRBG) of the first call made by kyber_keygen, prepare_randomness,

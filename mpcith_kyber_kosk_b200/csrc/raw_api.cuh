@@ -198,7 +198,7 @@ int kosk_b200_prepare_randomness(kosk_b200_ctx *c, void *rand_image)
     pb.cb_rand = (int)rs.calls; pb.tails_mask = 1;
     RAW_DISPATCH(launch_expand, pb, sl, ln->st);
     RAW_DISPATCH(launch_tails, pb, sl, ln->st);
-    launch_share_eval(c, pb.Y, pb.SH, sl.f0, 2 * sl.F, sl.n2, sl.nslot, 1, ln->st);
+    launch_share_eval(c, pb.Y, pb.SH, sl.f0, 2 * sl.F, sl.n2, sl.nslot, 1, ln->st, false, nullptr, nullptr, pb.WS);
     k_export_secrets<<<2 * sl.F, 256, 0, ln->st>>>(pb, sl.n2, sl.f0, reinterpret_cast<u16 *>(rs.d_rand));
     k_export_share_vecs<<<2 * sl.F, 256, 0, ln->st>>>(pb, sl.nslot, sl.f0, rs.d_rand + sz.rand_fsh);
     c->launches += 5;
@@ -215,7 +215,7 @@ int kosk_b200_prepare_range_proof(kosk_b200_ctx *c, void *eta_image)
     const Slots &sl = c->sl; const RawSizes sz = raw_sizes(c->k); RawState &rs = *c->raw;
     pb.cb_eta = (int)rs.calls; pb.tails_mask = 2;
     RAW_DISPATCH(launch_tails, pb, sl, ln->st);
-    launch_share_eval(c, pb.Y, pb.SH, sl.seta0, 2 * c->k * sl.E, sl.n2, sl.nslot, 1, ln->st, true);
+    launch_share_eval(c, pb.Y, pb.SH, sl.seta0, 2 * c->k * sl.E, sl.n2, sl.nslot, 1, ln->st, true, nullptr, nullptr, pb.WS);
     k_export_share_vecs<<<2 * c->k * sl.E, 256, 0, ln->st>>>(pb, sl.nslot, sl.seta0, rs.d_eta);
     c->launches += 2;
     CU(cudaMemcpyAsync(eta_image, rs.d_eta, sz.eta, cudaMemcpyDeviceToHost, ln->st));

@@ -32,6 +32,7 @@ struct VerifyBufs {
     u16 *CR = nullptr, *VR = nullptr, *OPV = nullptr;
     u16 *ABG = nullptr, *BS = nullptr, *A1 = nullptr, *YV = nullptr, *A2 = nullptr, *UZ = nullptr, *VSH = nullptr, *U2 = nullptr, *UR = nullptr;
     u16 *W1 = nullptr, *W2 = nullptr, *PT1 = nullptr, *PT2 = nullptr;   // barycentric weights per node / P(t) per target
+    int32_t *WS = nullptr;                                              // split-K partial sums (latency mode of the GEMMs)
     int k = 0, chunk = 0;
     int strict = 0;   // hardened decoding: off by default = the reference's accept set
     int raw_inst = 0; // verify() on a caller-supplied mlwe_inst (raw_api.cuh): AH / TPK are preloaded, pk is not parsed
@@ -52,7 +53,7 @@ KOSK_HD VDims make_vdims(int k)
 static inline void verify_free(VerifyBufs &v)
 {
     void *p[] = {v.flags, v.I, v.REST, v.I2, v.REST2, v.POS, v.AH, v.TPK, v.PW, v.TCR, v.VWR, v.CR, v.VR, v.OPV,
-                 v.ABG, v.BS, v.A1, v.YV, v.A2, v.UZ, v.VSH, v.U2, v.UR, v.W1, v.W2, v.PT1, v.PT2};
+                 v.ABG, v.BS, v.A1, v.YV, v.A2, v.UZ, v.VSH, v.U2, v.UR, v.W1, v.W2, v.PT1, v.PT2, v.WS};
     for (void *q : p) if (q) cudaFree(q);
     v = VerifyBufs{};
 }
@@ -69,6 +70,7 @@ static inline int verify_alloc(VerifyBufs &v, int k, int chunk)
     VA(v.A1, B * d.n1rows * KP1 * 2, 1); VA(v.YV, B * d.nyrows * YLD * 2, 1);
     VA(v.A2, B * d.n2rows * KP2 * 2, 1); VA(v.UZ, B * d.n2rows * 256 * 2, 0);
     VA(v.VSH, B * d.nyrows * SLD * 2, 1); VA(v.U2, B * d.n2rows * VR2LD * 2, 1); VA(v.UR, B * d.n2rows * 256 * 2, 0);
+    VA(v.WS, (size_t)GE_WS_ELEMS * 4, 0);
     VA(v.W1, B * YLD * 2, 1); VA(v.W2, B * VR2LD * 2, 1); VA(v.PT1, B * LM1_ROWS * 2, 1); VA(v.PT2, B * 256 * 2, 1);
 #undef VA
     return 0;
@@ -124,15 +126,25 @@ __global__ void __launch_bounds__(128) kv_setup(VerifyBufs vb, const u8 *__restr
         for (int w = 0; w < 4; w++) { uint64_t v = 0; for (int q = 0; q < 8; q++) v |= (uint64_t)pk[384 * K + 8 * w + q] << (8 * q); sd[w] = v; }
         xof_rej_uniform(vb.AH + ((size_t)b * K * K + tid) * 256, sd, (uint32_t)(tid % K), (uint32_t)(tid / K), sBlk[tid]);
     }
-    __syncthreads();   // REST visible block-wide (written by this block)
-    for (int idx = tid; idx < NR * 8; idx += 128) {
+}
+
+// Second half of the setup, spread over several CTAs per proof (latency of a single verification): the rest parties' commitment /
+// view digests copied into the per-party digest rows (mlwe_verifier.cpp:36-38, :645-647) and the commit records of the opened
+// parties (:23-33), row-major.  grid (SETUP_COPY_CTAS, B).
+constexpr int SETUP_COPY_CTAS = 8;
+template <int K>
+__global__ void __launch_bounds__(128) kv_setup_copy(VerifyBufs vb, const u8 *__restrict__ pis)
+{
+    const Layout L = make_layout(K);
+    const VDims d = make_vdims(K);
+    const int b = blockIdx.y, t0 = blockIdx.x * 128 + threadIdx.x, stride = gridDim.x * 128;
+    const u8 *pi = pis + L.proof_bytes * (size_t)b;
+    for (int idx = t0; idx < NR * 8; idx += stride) {
         const int j = idx / 8, w = idx % 8, p = vb.REST[(size_t)b * NR + j];
         reinterpret_cast<uint32_t *>(vb.TCR + ((size_t)b * NP + p) * 32)[w] = reinterpret_cast<const uint32_t *>(pi + L.o_Tcomm)[(size_t)j * 8 + w];
         reinterpret_cast<uint32_t *>(vb.VWR + ((size_t)b * NP + p) * 32)[w] = reinterpret_cast<const uint32_t *>(pi + L.o_comm)[(size_t)j * 8 + w];
     }
-    // commit records of the opened parties (mlwe_verifier.cpp:23-33), row-major
-    const VDims d = make_vdims(K);
-    for (int idx = tid; idx < NT * d.nc; idx += 128) {
+    for (int idx = t0; idx < NT * d.nc; idx += stride) {
         const int i = idx / d.nc, v = idx % d.nc;
         u16 x;
         if (v < K) x = pi16(pi, L.o_s, i * K + v);
@@ -511,6 +523,7 @@ static int verify_chunk_t(VerifyBufs &vb, const VerifyTables &vt, int B, const u
     const int ptiles = (NP + 127) / 128;
     kv_clear<K><<<(B + 127) / 128, 128, 0, st>>>(vb, B); nl++;
     kv_setup<K><<<B, 128, 0, st>>>(vb, d_pi, d_pk); nl++;
+    kv_setup_copy<K><<<dim3(SETUP_COPY_CTAS, B), 128, 0, st>>>(vb, d_pi); nl++;
     if (vb.strict) { kv_strict_scan<K><<<dim3((unsigned)((make_layout(K).proof_bytes / 2 + 255) / 256), B), 256, 0, st>>>(vb, d_pi); nl++; }
     {   // V2: commitments of the opened parties
         constexpr int NC = 2 * (K + MK + 2 * K + 1);
@@ -523,17 +536,17 @@ static int verify_chunk_t(VerifyBufs &vb, const VerifyTables &vt, int B, const u
     kv_gather<K><<<dim3(2 * MK + d.n1rows + d.n2rows, B), 128, 0, st>>>(vb, d_pi); nl++;
     GemmArgs g{};
     // beta/gamma reconstruction: ABG x R1
-    g = GemmArgs{}; g.A = vb.ABG; g.Bt = vt.R1; g.C = vb.BS; g.lda = YLD; g.ldb = YLD; g.ldc = 256;
+    g = GemmArgs{}; g.ws = vb.WS; g.ws_elems = GE_WS_ELEMS; g.A = vb.ABG; g.Bt = vt.R1; g.C = vb.BS; g.lda = YLD; g.ldb = YLD; g.ldc = 256;
     g.mtotal = B * 2 * MK; g.ksteps = YLD / GE_BK; g.nvalid = 256; g.rpp = g.mtotal; g.c_off = 0; g.half_last = 1;
     nl += gf_gemm_launch_auto<8>(g, 256, 1, st);
     kv_check_bg<<<dim3(MK, B), 128, 0, st>>>(vb); nl++;
     // interpolation-apply: rows of all proofs against the fixed Cauchy operands, columns scaled by each proof's P(t)
-    g = GemmArgs{}; g.A = vb.A1; g.Bt = vt.U1; g.C = vb.YV; g.lda = KP1; g.ldb = KP1; g.ldc = YLD;
+    g = GemmArgs{}; g.ws = vb.WS; g.ws_elems = GE_WS_ELEMS; g.A = vb.A1; g.Bt = vt.U1; g.C = vb.YV; g.lda = KP1; g.ldb = KP1; g.ldc = YLD;
     g.mtotal = B * d.n1rows; g.ksteps = KP1 / GE_BK; g.nvalid = D1; g.rpp = d.n1rows; g.a_slots = d.n1rows; g.c_slots = d.nyrows;
     g.colscale = vb.PT1; g.colscale_batch = LM1_ROWS; g.colscale_by_group = 1;
     nl += gf_gemm_launch_auto<7>(g, U1_ROWS, 1, st);
     kv_node_targets<K><<<dim3(d.n1rows, B), 160, 0, st>>>(vb, d_pi); nl++;
-    g = GemmArgs{}; g.A = vb.A2; g.Bt = vt.U2; g.C = vb.UZ; g.lda = KP2; g.ldb = KP2; g.ldc = 256;
+    g = GemmArgs{}; g.ws = vb.WS; g.ws_elems = GE_WS_ELEMS; g.A = vb.A2; g.Bt = vt.U2; g.C = vb.UZ; g.lda = KP2; g.ldb = KP2; g.ldc = 256;
     g.mtotal = B * d.n2rows; g.ksteps = KP2 / GE_BK; g.nvalid = 256; g.rpp = d.n2rows; g.a_slots = d.n2rows; g.c_slots = d.n2rows;
     g.colscale = vb.PT2; g.colscale_batch = 256; g.colscale_by_group = 1;
     nl += gf_gemm_launch_auto<8>(g, 256, 1, st);
@@ -543,7 +556,7 @@ static int verify_chunk_t(VerifyBufs &vb, const VerifyTables &vt, int B, const u
     {
         const int grp_lo[3] = {0, 3 * K, d.n1rows}, grp_hi[3] = {3 * K, d.n1rows, d.nyrows};
         for (int gi = 0; gi < 3; gi++) {
-            g = GemmArgs{}; g.A = vb.YV; g.Bt = vt.St; g.C = vb.VSH; g.lda = YLD; g.ldb = YLD; g.ldc = SLD;
+            g = GemmArgs{}; g.ws = vb.WS; g.ws_elems = GE_WS_ELEMS; g.A = vb.YV; g.Bt = vt.St; g.C = vb.VSH; g.lda = YLD; g.ldb = YLD; g.ldc = SLD;
             g.rpp = grp_hi[gi] - grp_lo[gi]; g.slot_lo = grp_lo[gi]; g.a_slots = d.nyrows; g.c_slots = d.nyrows;
             g.mtotal = B * g.rpp; g.ksteps = YLD / GE_BK; g.nvalid = NX; g.c_off = SOFF + NT + 1; g.tail = 1; g.tail_off = NL;
             if (gi == 1) { g.A = vb.YV + NL; g.Bt = vt.St + NL; g.ksteps = (YLD - NL) / GE_BK; g.tail_off = 0; g.addvec = vt.SU; g.scale_src = vb.YV; }
@@ -552,7 +565,7 @@ static int verify_chunk_t(VerifyBufs &vb, const VerifyTables &vt, int B, const u
         }
     }
     kv_check_parties<K><<<dim3(ptiles, B), 128, 0, st>>>(vb, d_pi); nl++;
-    g = GemmArgs{}; g.A = vb.U2; g.Bt = vt.R2; g.C = vb.UR; g.lda = VR2LD; g.ldb = VR2LD; g.ldc = 256;
+    g = GemmArgs{}; g.ws = vb.WS; g.ws_elems = GE_WS_ELEMS; g.A = vb.U2; g.Bt = vt.R2; g.C = vb.UR; g.lda = VR2LD; g.ldb = VR2LD; g.ldc = 256;
     g.mtotal = B * d.n2rows; g.ksteps = VR2LD / GE_BK; g.nvalid = 256; g.rpp = g.mtotal;
     nl += gf_gemm_launch_auto<8>(g, 256, 1, st);
     {   // V16: view hashes of the opened parties, FS-2, compare
