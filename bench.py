@@ -203,7 +203,10 @@ def run_b200(args):
     if rank == 0:
         sampler.start()
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("KOSK_NCCL_DEBUG", "WARN")     # keep stdout to the one JSON line
+        # keep stdout to the one JSON line: NCCL's banner / debug output (it prints to stdout by default) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        if "KOSK_NCCL_DEBUG" in os.environ:
+            os.environ["NCCL_DEBUG"] = os.environ["KOSK_NCCL_DEBUG"]
         dist.init_process_group("nccl", device_id=dev)
     k, B = args.kyber_k, args.batch
     chunk = args.chunk or -(-B // args.lanes)
