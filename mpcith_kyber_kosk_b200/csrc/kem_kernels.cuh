@@ -75,6 +75,34 @@ __device__ __forceinline__ void unpack_bits(uint32_t *t, const u8 *src, int cnt,
     }
 }
 
+// hash_g(a[32] || b[32]) = SHA3-512 of 64 bytes, warp-cooperative (one state word per lane); all 32 lanes of a warp call it,
+// out[64] is written by lanes 0..7
+__device__ __forceinline__ void warp_hash_g(const WarpKeccak &wk, const u8 *a, const u8 *b, u8 *out)
+{
+    const int lane = threadIdx.x & 31;
+    uint64_t w = 0;
+    if (lane < 8) { const u8 *src = lane < 4 ? a + 8 * lane : b + 8 * (lane - 4); for (int q = 0; q < 8; q++) w |= (uint64_t)src[q] << (8 * q); }
+    if (lane == 8) w = 0x06ULL | 0x8000000000000000ULL;              // rate 72: pad starts and ends in word 8
+    w = wk.permute(w);
+    if (lane < 8) for (int q = 0; q < 8; q++) out[8 * lane + q] = (u8)(w >> (8 * q));
+}
+// hash_h(pk) = SHA3-256 of 384K + 32 bytes (a whole number of 8-byte words), warp-cooperative; out[32] written by lanes 0..3
+template <int K>
+__device__ __forceinline__ void warp_hash_h_pk(const WarpKeccak &wk, const u8 *pk, u8 *out)
+{
+    const int lane = threadIdx.x & 31;
+    constexpr int NB = (384 * K + 32) / 136, REMW = ((384 * K + 32) % 136) / 8;
+    auto word = [&](int i) -> uint64_t { uint64_t v = 0; for (int q = 0; q < 8; q++) v |= (uint64_t)pk[8 * i + q] << (8 * q); return v; };
+    uint64_t a = 0;
+#pragma unroll 1
+    for (int blk = 0; blk < NB; blk++) { if (lane < 17) a ^= word(blk * 17 + lane); a = wk.permute(a); }
+    if (lane < REMW) a ^= word(NB * 17 + lane);
+    if (lane == REMW) a ^= 0x06ULL;
+    if (lane == 16) a ^= 0x8000000000000000ULL;
+    a = wk.permute(a);
+    if (lane < 4) for (int q = 0; q < 8; q++) out[8 * lane + q] = (u8)(a >> (8 * q));
+}
+
 // part of indcpa_enc that needs only the public key: A^T = gen_at(seed) and t-hat = polyvec_frombytes(pk) (indcpa.c:273-276)
 template <int K>
 __device__ __forceinline__ void enc_public(KemSmem<K> &S, const u8 *pk, int tid, int first_thread)
@@ -152,20 +180,23 @@ __global__ void __launch_bounds__(128) k_kem_enc(const u8 *__restrict__ pks, con
     const KemDims d = kem_dims(K);
     const int b = blockIdx.x, tid = threadIdx.x;
     const u8 *pk = pks + (size_t)(384 * K + 32) * b;
-    if (tid == 0) {
+    if (tid < 32) {                          // warp 0: coins, hash_h(pk), hash_g(m || H(pk)), one state word per lane
+        WarpKeccak wk; wk.init();
         if (seeds) {
-            uint64_t sd[4], a[25];
-            for (int i = 0; i < 4; i++) { uint64_t w = 0; for (int j = 0; j < 8; j++) w |= (uint64_t)seeds[32 * (size_t)b + 8 * i + j] << (8 * j); sd[i] = w; }
-            drbg_begin(a, sd, call);
-            for (int i = 0; i < 32; i++) S.m[i] = (u8)(a[i >> 3] >> (8 * (i & 7)));
-        } else for (int i = 0; i < 32; i++) S.m[i] = coins[32 * (size_t)b + i];
-        ByteSponge sp; sp.init(136); sp.absorb(pk, 384 * K + 32); sp.finalize(0x06);          // hash_h(pk)
-        for (int i = 0; i < 32; i++) S.hpk[i] = sp.next();
-        sp.init(72); sp.absorb(S.m, 32); sp.absorb(S.hpk, 32); sp.finalize(0x06);             // hash_g(m || H(pk))
-        for (int i = 0; i < 64; i++) S.kr[i] = sp.next();
-        for (int i = 0; i < 32; i++) S.coins[i] = S.kr[32 + i];
+            uint64_t a = 0;
+            if (tid < 4) for (int j = 0; j < 8; j++) a |= (uint64_t)seeds[32 * (size_t)b + 8 * tid + j] << (8 * j);
+            if (tid == 4) a = (uint64_t)call | (0x1FULL << 32);
+            if (tid == 16) a = 0x8000000000000000ULL;
+            a = wk.permute(a);
+            if (tid < 4) for (int j = 0; j < 8; j++) S.m[8 * tid + j] = (u8)(a >> (8 * j));
+        } else S.m[tid] = coins[32 * (size_t)b + tid];
+        warp_hash_h_pk<K>(wk, pk, S.hpk);
+        __syncwarp();
+        warp_hash_g(wk, S.m, S.hpk, S.kr);
+        __syncwarp();
+        S.coins[tid] = S.kr[32 + tid];
     }
-    enc_public<K>(S, pk, tid, 32);           // A^T on the second warp while thread 0 hashes
+    enc_public<K>(S, pk, tid, 32);           // A^T on the second warp while warp 0 hashes
     __syncthreads();
     enc_secret<K>(S, tid);
     for (int i = tid; i < d.ct_bytes; i += 128) cts[(size_t)d.ct_bytes * b + i] = S.ct[i];
@@ -221,12 +252,14 @@ __global__ void __launch_bounds__(128) k_kem_dec(const u8 *__restrict__ cts, con
         if (t) atomicOr(&S.mw[c >> 5], 1u << (c & 31));
     }
     __syncthreads();
-    if (tid == 0) {
-        for (int i = 0; i < 32; i++) S.m[i] = (u8)(S.mw[i >> 2] >> (8 * (i & 3)));
-        ByteSponge sp; sp.init(72); sp.absorb(S.m, 32); sp.absorb(sk + 768 * K + 32, 32); sp.finalize(0x06);    // hash_g(m' || H(pk) from sk)
-        for (int i = 0; i < 64; i++) S.kr[i] = sp.next();
-        for (int i = 0; i < 32; i++) S.coins[i] = S.kr[32 + i];
-        S.fail = 0;
+    if (tid < 32) {                          // hash_g(m' || H(pk) from sk), warp-cooperative
+        WarpKeccak wk; wk.init();
+        S.m[tid] = (u8)(S.mw[tid >> 2] >> (8 * (tid & 3)));
+        __syncwarp();
+        warp_hash_g(wk, S.m, sk + 768 * K + 32, S.kr);
+        __syncwarp();
+        S.coins[tid] = S.kr[32 + tid];
+        if (tid == 0) S.fail = 0;
     }
     __syncthreads();
     enc_secret<K>(S, tid);

@@ -513,3 +513,24 @@ def test_reference_main_cpp_runs_against_the_library(k):
 def ctypes_proof_kib(k):
     from mpcith_kyber_kosk_b200 import proof_bytes
     return proof_bytes(k) // 1024
+
+
+@pytest.mark.parametrize("k", [2, 3, 4])
+def test_kem_arbitrary_bytes_match_live_reference(ctxs, k):
+    """Inputs a well-formed key pair never produces: 12-bit coefficients >= q in pk / sk (the reference reduces them implicitly in
+    its Montgomery arithmetic) and random ciphertext bytes (every bit pattern decompresses): same bytes out as the reference."""
+    if O.ref(k) is None:
+        pytest.skip("oracle/_ref not built on this box")
+    ctx = ctxs(k)
+    rng = np.random.default_rng(70 + k)
+    n = 6
+    pk = rng.integers(0, 256, size=(n, ctx.pk_bytes), dtype=np.uint8)
+    sk = rng.integers(0, 256, size=(n, ctx.sk_bytes), dtype=np.uint8)
+    coins = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    ct, ss = ctx.kem_enc_derand_batch(pk, coins)
+    rct = rng.integers(0, 256, size=(n, ctx.ct_bytes), dtype=np.uint8)
+    dss = ctx.kem_dec_batch(rct, sk)
+    for i in range(n):
+        wct, wss = O.ref_kem_enc_derand(k, pk[i], coins[i])
+        assert bytes(wct) == bytes(ct[i]) and bytes(wss) == bytes(ss[i])
+        assert bytes(O.ref_kem_dec(k, rct[i], sk[i])) == bytes(dss[i])
