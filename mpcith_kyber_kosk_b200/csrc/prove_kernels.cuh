@@ -823,10 +823,20 @@ __global__ void __launch_bounds__(128) k_assemble(ProveBufs pb)
         const int r0 = blockIdx.x * ROWS, nr = min(ROWS, NT - r0);
         if (tid < nr) { sp[tid] = I[r0 + tid]; *out16(L.o_I, r0 + tid) = sp[tid]; }
         __syncthreads();
-        for (int idx = tid; idx < nr * F; idx += 128) {
-            const int r = idx / F, j = idx % F, p = sp[r];
-            *out16(L.o_f, (size_t)(r0 + r) * F + j) = (u16)P(sl.f0 + j, p);
-            *out16(L.o_Tf, (size_t)(r0 + r) * F + j) = (u16)P(sl.Tf0 + j, p);
+        // every element of an opened party sits in a different plane (one 32-byte sector per 2 useful bytes): keep eight gathers in
+        // flight per thread, the loop is bound by DRAM latency otherwise
+        for (int base = tid; base < nr * F; base += 128 * 4) {
+            uint32_t vf[4], vt[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int idx = base + u * 128;
+                if (idx < nr * F) { const int r = idx / F, j = idx % F, p = sp[r]; vf[u] = P(sl.f0 + j, p); vt[u] = P(sl.Tf0 + j, p); }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int idx = base + u * 128;
+                if (idx < nr * F) { const int r = idx / F, j = idx % F; *out16(L.o_f, (size_t)(r0 + r) * F + j) = (u16)vf[u]; *out16(L.o_Tf, (size_t)(r0 + r) * F + j) = (u16)vt[u]; }
+            }
         }
         for (int idx = tid; idx < nr * K; idx += 128) {
             const int r = idx / K, j = idx % K, p = sp[r];
