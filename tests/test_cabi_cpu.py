@@ -85,3 +85,44 @@ def test_struct_image_sizes_match_reference_structs(built_lib):
         if r is not None:      # the compiler's own sizeof of the reference structs
             assert (r.ref_inst_bytes(), r.ref_randomness_bytes(), r.ref_range_proof_bytes(), r.ref_share_vec_bytes()) == (S["inst"], S["rand"], S["eta"], O.SHARE_VEC_BYTES)
     assert lib.kosk_b200_inst_bytes(9) == 0
+
+
+def test_dropin_header_exposes_the_struct_level_api(built_lib, tmp_path):
+    """kosk_dropin.hpp / include/dropin/*: the reference's struct types (same sizes as the reference's own sizeof, when oracle/_ref is
+    there to ask), the struct-level functions of mlwe_prover.hpp:77-99 / mlwe_verifier.hpp:14-15 / kosk.hpp:17-18 and the KEM calls,
+    with the reference's signatures, for every KYBER_K (compile + link only: no GPU needed)."""
+    import subprocess
+    import oracle_lib as O
+    src = tmp_path / "t.cpp"
+    src.write_text('#include "mlwe_prover.hpp"\n#include "kosk.hpp"\n#include "params.hpp"\n'
+                   'using namespace NTL;\n'
+                   'void (*f1)(mpcith_randomness *) = &prepare_randomness;\n'
+                   'void (*f2)(mpcith_range_proof *) = &prepare_range_proof;\n'
+                   'void (*f3)(kyber_keypair *, mlwe_inst *) = &kyber_keygen;\n'
+                   'void (*f4)(mpcith_proof *, const mlwe_inst *, const mpcith_randomness *, const mpcith_range_proof *) = &prove;\n'
+                   'bool (*f5)(const mpcith_proof *, const mlwe_inst *) = &verify;\n'
+                   'void (*f6)(uint8_t *, const mpcith_proof *) = &encode_mpcith_proof;\n'
+                   'void (*f7)(mpcith_proof *, const uint8_t *) = &decode_mpcith_proof;\n'
+                   'int (*f8)(uint8_t *, uint8_t *, const uint8_t *) = &crypto_kem_enc;\n'
+                   'int (*f9)(uint8_t *, const uint8_t *, const uint8_t *) = &crypto_kem_dec;\n'
+                   '#include <stdio.h>\n'
+                   'int main() { printf("%zu %zu %zu %zu %zu %d %d\\n", sizeof(mlwe_inst), sizeof(mpcith_randomness), sizeof(mpcith_range_proof),\n'
+                   '                    sizeof(share_vec), (size_t)MPCITH_PROOF_SIZE, (int)KYBER_CIPHERTEXTBYTES, (int)KYBER_SSBYTES); return 0; }\n')
+    libdir = os.path.join(ROOT, "mpcith_kyber_kosk_b200")
+    for k in (2, 3, 4):
+        exe = tmp_path / f"t{k}"
+        subprocess.run(["g++", "-std=c++11", f"-DKYBER_K={k}", "-I" + os.path.join(ROOT, "include", "dropin"), str(src), "-L" + libdir,
+                        "-lkosk_b200", "-Wl,-rpath," + libdir, "-o", str(exe)], check=True)
+        got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+        S = O.struct_sizes(k)
+        assert got == [S["inst"], S["rand"], S["eta"], O.SHARE_VEC_BYTES, pkg.proof_bytes(k), O.CT_BYTES[k], 32]
+
+
+def test_reference_main_cpp_compiles_against_dropin_headers(built_lib):
+    """`make -C oracle dropin-main`: the reference's unmodified main.cpp against include/dropin/ + libkosk_b200.so (the GPU suite runs it)."""
+    import subprocess
+    if not os.path.exists("/root/reference/main.cpp"):
+        pytest.skip("no /root/reference in this checkout")
+    subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "dropin-main"], check=True, capture_output=True)
+    for k in (2, 3, 4):
+        assert os.path.exists(os.path.join(ROOT, "oracle", "_ref", f"main_dropin_k{k}"))
