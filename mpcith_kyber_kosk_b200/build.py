@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libkosk_b200.so")
 SOURCES = ["kosk_b200.cu"]
-HEADERS = ["kosk_common.cuh", "keccak.cuh", "gf_gemm.cuh", "gf_gemm_imma.cuh", "prove_kernels.cuh", "verify_kernels.cuh", "raw_api.cuh", "kem_kernels.cuh"]
+HEADERS = ["kosk_common.cuh", "keccak.cuh", "gf_gemm.cuh", "gf_gemm_imma.cuh", "prove_kernels.cuh", "verify_kernels.cuh", "raw_api.cuh", "kem_kernels.cuh", "share_ntt.cuh"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared", "-cudart", "static",

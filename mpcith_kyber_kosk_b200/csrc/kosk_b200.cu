@@ -5,6 +5,7 @@
 #include "prove_kernels.cuh"
 #include "verify_kernels.cuh"
 #include "gf_gemm_imma.cuh"
+#include "share_ntt.cuh"
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstdlib>
@@ -77,6 +78,9 @@ struct kosk_b200_ctx {
     cudaEvent_t last_computed = nullptr;   // compute-done event of the most recently enqueued sub-batch (any lane)
     cudaEvent_t last_gate = nullptr;       // event the next prove sub-batch waits for: last_computed, or the previous sub-batch's pre_tail
     int overlap_tail = 1;                  // KOSK_B200_OVERLAP_TAIL: let a sub-batch start while the previous one runs FS-2 + assembly
+    int use_ntt = 1;                       // KOSK_B200_SHARE_NTT: share evaluation as a blocked NTT convolution (share_ntt.cuh) instead of the dense table GEMM
+    int16_t *d_sn = nullptr;               // its tables: tw[512] | khat[SN_NK*256] | wj[512] | px[1408]
+    ShareNttTables sn{};
     Slots sl; Layout L;
     uint64_t launches = 0;
     // constant tables
@@ -147,7 +151,7 @@ static void ctx_free(kosk_b200_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    void *ptrs[] = {c->d_U1, c->d_U2, c->d_status, c->d_fact, c->tmpL0, c->tmpL1, c->d_St, c->d_St0, c->d_St1, c->d_SU, c->d_R1, c->d_R2, c->d_inv, c->d_tab_commit, c->d_tab_view};
+    void *ptrs[] = {c->d_sn, c->d_U1, c->d_U2, c->d_status, c->d_fact, c->tmpL0, c->tmpL1, c->d_St, c->d_St0, c->d_St1, c->d_SU, c->d_R1, c->d_R2, c->d_inv, c->d_tab_commit, c->d_tab_view};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (Lane &ln : c->lanes) {
         free_prove_bufs(ln.pb);
@@ -199,6 +203,8 @@ int kosk_b200_create_ex(kosk_b200_ctx **out, int k, int device, int max_chunk, i
     { const char *e = getenv("KOSK_B200_FUSE_FS"); if (e) c->fuse_fs = atoi(e); }
     { const char *e = getenv("KOSK_B200_FUSE_MAX"); if (e) c->fuse_max = atoi(e); }
     { const char *e = getenv("KOSK_B200_OVERLAP_TAIL"); if (e) c->overlap_tail = atoi(e); }
+    { const char *e = getenv("KOSK_B200_SHARE_NTT"); if (e) c->use_ntt = atoi(e); }
+    if (c->use_tensor) c->use_ntt = 0;
     const Slots &sl = c->sl; const Layout &L = c->L;
     const size_t B = (size_t)c->chunk;
 #define ALLOC(ptr, bytes) do { if (cudaMalloc((void **)&(ptr), (bytes)) != cudaSuccess) { ctx_free(c); return fail(KOSK_E_NOMEM, "cudaMalloc failed for " #ptr); } } while (0)
@@ -242,6 +248,14 @@ int kosk_b200_create_ex(kosk_b200_ctx **out, int k, int device, int max_chunk, i
             for (int t = 0; t < NL; t++) for (int p = 0; p < KP2; p++) { const int dd = ((t - p - 256) % Q + Q) % Q; U2[(size_t)t * KP2 + p] = (int16_t)gf_center(inv[dd]); }
             ALLOC(c->d_U1, U1.size() * 2); CU(cudaMemcpy(c->d_U1, U1.data(), U1.size() * 2, cudaMemcpyHostToDevice));
             ALLOC(c->d_U2, U2.size() * 2); CU(cudaMemcpy(c->d_U2, U2.data(), U2.size() * 2, cudaMemcpyHostToDevice));
+        }
+        {   // tables of the NTT-convolution share evaluation (share_ntt.cuh)
+            const ShareNttHost sh = share_ntt_tables();
+            CU(cudaMemcpyToSymbol(c_sn_w16f, sh.w16f.data(), 256 * 4)); CU(cudaMemcpyToSymbol(c_sn_w16i, sh.w16i.data(), 256 * 4));
+            std::vector<int16_t> all; all.insert(all.end(), sh.tw.begin(), sh.tw.end()); all.insert(all.end(), sh.khat.begin(), sh.khat.end());
+            all.insert(all.end(), sh.wj.begin(), sh.wj.end()); all.insert(all.end(), sh.px.begin(), sh.px.end());
+            ALLOC(c->d_sn, all.size() * 2); CU(cudaMemcpy(c->d_sn, all.data(), all.size() * 2, cudaMemcpyHostToDevice));
+            c->sn.tw = c->d_sn; c->sn.khat = c->d_sn + 512; c->sn.wj = c->sn.khat + SN_NK * 256; c->sn.px = c->sn.wj + 512;
         }
         std::vector<uint16_t> fc(2 * FACT_N);
         { uint32_t f = 1; for (int i = 0; i < FACT_N; i++) { if (i) f = f * i % Q; fc[i] = (uint16_t)f; fc[FACT_N + i] = inv[f]; } }
@@ -311,6 +325,12 @@ static void launch_share_eval(kosk_b200_ctx *c, const u16 *Y, u16 *SH, int slot_
     g.A = Y; g.Bt = c->d_St; g.C = SH; g.lda = YLD; g.ldb = YLD; g.ldc = SLD;
     g.mtotal = B * rows; g.ksteps = YLD / GE_BK; g.nvalid = NX; g.c_off = SOFF + NT + 1;
     g.rpp = rows; g.slot_lo = slot_lo; g.a_slots = y_slots; g.c_slots = sh_slots; g.tail = 1; g.tail_off = NL;
+    if (c->use_ntt && !(c->use_tensor && YL0)) {      // one warp per sharing; constant-secret rows need no special case here
+        const int ctas = std::min((g.mtotal + SN_WARPS - 1) / SN_WARPS, 148 * 8);
+        k_share_ntt<<<ctas, 32 * SN_WARPS, 0, st>>>(g, c->sn);
+        c->launches += 1;
+        return;
+    }
     const int koff = const_secret ? NL : 0;
     if (const_secret) {      // eta sharings: contraction over the 151 tail terms only, constant part added in the epilogue
         g.A = Y + NL; g.Bt = c->d_St + NL; g.ksteps = (YLD - NL) / GE_BK; g.tail_off = 0;
@@ -427,7 +447,7 @@ static int prove_chunk_k(kosk_b200_ctx *c, Lane &ln, const ProveBufs &bufs, int 
 
 static int verify_chunk_lane(kosk_b200_ctx *c, Lane &ln, int B, const u8 *d_pi, const u8 *d_pk, u8 *d_ok)
 {
-    VerifyTables vt{c->d_St, c->d_R1, c->d_R2, c->d_inv, c->d_SU, c->d_fact, c->d_U1, c->d_U2};
+    VerifyTables vt{c->d_St, c->d_R1, c->d_R2, c->d_inv, c->d_SU, c->d_fact, c->d_U1, c->d_U2, c->use_ntt ? &c->sn : nullptr};
     if (c->last_computed && c->last_computed != ln.computed) CU(cudaStreamWaitEvent(ln.st, c->last_computed, 0));
     prof_mark(c, ln, KOSK_PH_VERIFY);
     int nl = verify_chunk(c->k, ln.vb, vt, B, d_pi, d_pk, d_ok, ln.st);

@@ -1,0 +1,188 @@
+// share_ntt.cuh -- packed-Shamir share evaluation as a blocked cyclic convolution over GF(3329).
+// Same function as the table mat-vec of share_secrets_ddeg / recompute_share_secrets_ddeg (reference ss.cpp:23-32, :88-97):
+//   share[151 + x] = sum_{j<407} S[x][j] y[j],   S[x][j] = l_j(x + 407) over the nodes 0..406   
+// but S is never formed.  In barycentric form S[x][j] = P(x) * w_j / (x + 407 - j) with w_j = 1 / prod_{m != j} (j - m) and
+// P(x) = prod_{m<407} (x + 407 - m), so the sum is a convolution of u_j = w_j y_j with the fixed sequence c[m] = 1 / m
+// (m = 1..1709), scaled by P(x).  GF(3329) has 256-th roots of unity (17 generates them: the Kyber NTT's root), so the
+// convolution is cut into 128-wide input blocks i (4 of them) and output blocks o (11): block (o, i) is a length-256 cyclic
+// convolution with the kernel segment K_{o-i}[d] = c[128 (o - i) + 407 + d], d in [-127, 127], and
+//   out block o = INTT( sum_i NTT(K_{o-i}) . NTT(u block i) ) [0..127].
+// Per sharing: 4 forward and 11 inverse 256-point NTTs plus 11 x 4 x 256 pointwise MACs, about 115 k IMADs instead of the
+// 530 k MACs of the dense table (every value is a field element, so the result is the same canonical residue).
+// A 256-point NTT is done as 16 x 16 (n = 16 a + b, k = k1 + 16 k2): a 16-point DFT down the columns, the twiddle
+// w^(b k1), a 16-point DFT along the rows; the 16-point DFTs are plain 16 x 16 mat-vecs whose coefficients are IMAD
+// constant-bank operands.  One warp per sharing; its two half-warps run two NTTs at a time (two input blocks, then two output
+// blocks), lane = column (then row) of the 16 x 16 matrix, transposed once per NTT through shared memory.
+// Arithmetic: int32 lazy sums of at most 16 products of a residue in (-q, q) with a centered constant (|.| <= 1664), then
+// Kyber's Montgomery reduction (kyber/reduce.c:16-23, R = 2^16); all tables carry the factor R.
+#pragma once
+#include "gf_gemm.cuh"
+#include <vector>
+
+namespace kosk {
+
+constexpr int SN_NIN = 4, SN_NOUT = 11, SN_NK = SN_NIN + SN_NOUT - 1;   // kernel segments o - i in [-3, 10]
+constexpr int SN_WARPS = 4;                                              // sharings in flight per CTA
+
+__constant__ int32_t c_sn_w16f[256], c_sn_w16i[256];   // w16^(+-a k) * R, centered; w16 = 17^16
+
+struct ShareNttTables {
+    const int16_t *tw;       // [2][16][16]  17^(+-b k1) * R (symmetric in b, k1)
+    const int16_t *khat;     // [SN_NK][16 k2][16 k1]  NTT(K_delta)[k1 + 16 k2] / 256 * R
+    const int16_t *wj;       // [512]   w_j * R (0 for j >= 407)
+    const int16_t *px;       // [1408]  P(x) * R (0 for x >= 1303)
+};
+
+__device__ __forceinline__ int32_t sn_montred(int32_t a)            // a * 2^-16 mod q in (-q, q) for |a| < q * 2^15
+{
+    const int32_t t = (int32_t)(int16_t)(a * -3327);               // q^-1 mod 2^16 = -3327 (kyber/reduce.h)
+    return (a - t * Q) >> 16;
+}
+
+// rows of g.A (407 values, canonical) -> rows of g.C (1454 shares: parties 0..150 hold the 151 tail values verbatim)
+__global__ void __launch_bounds__(32 * SN_WARPS) k_share_ntt(const GemmArgs g, const ShareNttTables tb)
+{
+    __shared__ int16_t s_kh[SN_NK * 256];
+    __shared__ int16_t s_tw[2 * 256];
+    __shared__ int16_t s_uh[SN_WARPS][SN_NIN][256];
+    __shared__ int32_t s_t[SN_WARPS][2][16 * 17];
+    for (int i = threadIdx.x; i < SN_NK * 256; i += blockDim.x) s_kh[i] = tb.khat[i];
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) s_tw[i] = tb.tw[i];
+    __syncthreads();
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, hw = lane >> 4, c = lane & 15;
+    int16_t (*uh)[256] = s_uh[wid];
+    int32_t *T = s_t[wid][hw];
+    for (int m = blockIdx.x * SN_WARPS + wid; m < g.mtotal; m += gridDim.x * SN_WARPS) {
+        const u16 *yrow = g.A + ((size_t)(m / g.rpp) * g.a_slots + g.slot_lo + m % g.rpp) * g.lda;
+        u16 *dst = g.C + ((size_t)(m / g.rpp) * g.c_slots + g.slot_lo + m % g.rpp) * g.ldc + g.c_off;
+        for (int t = lane; t <= NT; t += 32) dst[t - (NT + 1)] = yrow[g.tail_off + t];
+        // ---- forward: u_j = w_j y_j, NTT of the four zero-padded 128-wide blocks (two per pass) ----
+#pragma unroll 1
+        for (int it = 0; it < SN_NIN / 2; it++) {
+            const int blk = 2 * it + hw;
+            int32_t x[8];
+#pragma unroll
+            for (int a = 0; a < 8; a++) {
+                const int j = 128 * blk + 16 * a + c;
+                x[a] = j < D1 ? sn_montred((int32_t)yrow[j] * (int32_t)__ldg(tb.wj + j)) : 0;
+            }
+            int32_t y[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                int32_t acc = 0;
+#pragma unroll
+                for (int a = 0; a < 8; a++) acc += x[a] * c_sn_w16f[a * 16 + k];
+                y[k] = sn_montred(sn_montred(acc) * (int32_t)s_tw[k * 16 + c]);
+            }
+#pragma unroll
+            for (int k = 0; k < 16; k++) T[k * 17 + c] = y[k];
+            __syncwarp();
+            int32_t in[16];
+#pragma unroll
+            for (int b = 0; b < 16; b++) in[b] = T[c * 17 + b];
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                int32_t acc = 0;
+#pragma unroll
+                for (int b = 0; b < 16; b++) acc += in[b] * c_sn_w16f[b * 16 + k];
+                uh[blk][k * 16 + c] = (int16_t)sn_montred(acc);
+            }
+            __syncwarp();
+        }
+        // ---- inverse: output blocks two per pass ----
+#pragma unroll 1
+        for (int it = 0; it < (SN_NOUT + 1) / 2; it++) {
+            const int o = 2 * it + hw;
+            const bool live = o < SN_NOUT;
+            int32_t O[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                int32_t acc = 0;
+                if (live) {
+#pragma unroll
+                    for (int i = 0; i < SN_NIN; i++) acc += (int32_t)uh[i][k * 16 + c] * (int32_t)s_kh[(o - i + SN_NIN - 1) * 256 + k * 16 + c];
+                }
+                O[k] = sn_montred(acc);
+            }
+            int32_t v[16];
+#pragma unroll
+            for (int b = 0; b < 16; b++) {
+                int32_t acc = 0;
+#pragma unroll
+                for (int k = 0; k < 16; k++) acc += O[k] * c_sn_w16i[k * 16 + b];
+                v[b] = sn_montred(sn_montred(acc) * (int32_t)s_tw[256 + b * 16 + c]);
+            }
+#pragma unroll
+            for (int b = 0; b < 16; b++) T[b * 17 + c] = v[b];
+            __syncwarp();
+            int32_t in[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) in[k] = T[c * 17 + k];
+#pragma unroll
+            for (int a = 0; a < 8; a++) {
+                int32_t acc = 0;
+#pragma unroll
+                for (int k = 0; k < 16; k++) acc += in[k] * c_sn_w16i[k * 16 + a];
+                const int xo = 128 * o + 16 * a + c;
+                if (live && xo < NX) {
+                    int32_t r = sn_montred(sn_montred(acc) * (int32_t)__ldg(tb.px + xo));
+                    dst[xo] = (u16)(r < 0 ? r + Q : r);
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// ---- host: table construction (plain modular arithmetic, once per context) ----
+struct ShareNttHost {
+    std::vector<int32_t> w16f, w16i;
+    std::vector<int16_t> tw, khat, wj, px;
+};
+static inline ShareNttHost share_ntt_tables()
+{
+    auto pw = [](uint32_t b, uint32_t e) { uint32_t r = 1; b %= Q; while (e) { if (e & 1) r = r * b % Q; b = b * b % Q; e >>= 1; } return r; };
+    auto inv = [&](uint32_t a) { return pw(a % Q, Q - 2); };
+    const uint32_t R = (1u << 16) % Q, om = 17, iom = inv(17), om16 = pw(om, 16), iom16 = inv(om16);
+    auto mont = [&](uint32_t v) { return (int32_t)gf_center(v % Q * R % Q); };
+    ShareNttHost h;
+    h.w16f.resize(256); h.w16i.resize(256); h.tw.resize(512);
+    for (int a = 0; a < 16; a++)
+        for (int k = 0; k < 16; k++) {
+            h.w16f[a * 16 + k] = mont(pw(om16, a * k)); h.w16i[a * 16 + k] = mont(pw(iom16, a * k));
+            h.tw[a * 16 + k] = (int16_t)mont(pw(om, a * k)); h.tw[256 + a * 16 + k] = (int16_t)mont(pw(iom, a * k));
+        }
+    // Lagrange weights over the nodes 0..406 and P(x) at x + 407
+    h.wj.assign(512, 0); h.px.assign(1408, 0);
+    for (int j = 0; j < D1; j++) {
+        uint32_t d = 1;
+        for (int m = 0; m < D1; m++) if (m != j) d = d * (uint32_t)((j - m + Q) % Q) % Q;
+        h.wj[j] = (int16_t)mont(inv(d));
+    }
+    for (int x = 0; x < NX; x++) {
+        uint32_t p = 1;
+        for (int m = 0; m < D1; m++) p = p * (uint32_t)((x + D1 - m) % Q) % Q;
+        h.px[x] = (int16_t)mont(p);
+    }
+    // kernel segments and their 256-point NTTs, index k = k1 + 16 k2 stored at [k2][k1], scaled by 1/256
+    std::vector<uint32_t> opw(256);
+    for (int i = 0; i < 256; i++) opw[i] = pw(om, i);
+    const uint32_t i256 = inv(256);
+    h.khat.assign((size_t)SN_NK * 256, 0);
+    for (int dl = -(SN_NIN - 1); dl < SN_NOUT; dl++) {
+        uint32_t K[256];
+        for (int t = 0; t < 256; t++) {
+            const int d = t < 128 ? t : t - 256, mm = 128 * dl + D1 + d;
+            K[t] = (t == 128 || mm < 1 || mm >= Q) ? 0 : inv((uint32_t)mm);
+        }
+        for (int k = 0; k < 256; k++) {
+            uint32_t s = 0;
+            for (int t = 0; t < 256; t++) s = (s + K[t] * opw[(t * k) & 255]) % Q;
+            const int k1 = k & 15, k2 = k >> 4;
+            h.khat[(size_t)(dl + SN_NIN - 1) * 256 + k2 * 16 + k1] = (int16_t)mont(s * i256 % Q);
+        }
+    }
+    return h;
+}
+
+}  // namespace kosk

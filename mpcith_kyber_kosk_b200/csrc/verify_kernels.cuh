@@ -6,6 +6,7 @@
 // applied with the same integer-pipe GEMM as the prover's share evaluation.
 #pragma once
 #include "prove_kernels.cuh"
+#include "share_ntt.cuh"
 #include <cuda_runtime.h>
 
 namespace kosk {
@@ -22,7 +23,8 @@ enum VFlag { VF_I = 1, VF_BG = 2, VF_SR = 4, VF_NTT = 8, VF_ASR = 16, VF_T = 32,
              VF_SUBETA = 256, VF_UZ = 512, VF_U2D = 1024, VF_FS2 = 2048, VF_STRICT = 4096 };
 
 struct VerifyTables { const int16_t *St, *R1, *R2; const u16 *inv; const int16_t *SU; const u16 *fact; /* [2][FACT_N]: i!, 1/i! */
-                      const int16_t *U1, *U2; /* Cauchy operands [U1_ROWS][KP1], [256][KP2], centered */ };
+                      const int16_t *U1, *U2; /* Cauchy operands [U1_ROWS][KP1], [256][KP2], centered */
+                      const ShareNttTables *sn; /* share evaluation as an NTT convolution (share_ntt.cuh); nullptr = dense table GEMM */ };
 
 struct VerifyBufs {
     int *flags = nullptr;
@@ -553,7 +555,11 @@ static int verify_chunk_t(VerifyBufs &vb, const VerifyTables &vt, int B, const u
     kv_open<K><<<B, 128, 0, st>>>(vb); nl++;
     // regenerate every sharing at all 1454 parties: YV x S.  Row groups per proof: [0,3K) s+r, e+r, t | [3K, n1rows) the eta
     // sharings, whose 256 secrets were just checked to be one constant (short path: tail terms only) | [n1rows, nyrows)
-    {
+    if (vt.sn) {
+        g = GemmArgs{}; g.A = vb.YV; g.C = vb.VSH; g.lda = YLD; g.ldc = SLD; g.rpp = d.nyrows; g.slot_lo = 0; g.a_slots = d.nyrows; g.c_slots = d.nyrows;
+        g.mtotal = B * d.nyrows; g.c_off = SOFF + NT + 1; g.tail = 1; g.tail_off = NL;
+        k_share_ntt<<<std::min((g.mtotal + SN_WARPS - 1) / SN_WARPS, 148 * 8), 32 * SN_WARPS, 0, st>>>(g, *vt.sn); nl++;
+    } else {
         const int grp_lo[3] = {0, 3 * K, d.n1rows}, grp_hi[3] = {3 * K, d.n1rows, d.nyrows};
         for (int gi = 0; gi < 3; gi++) {
             g = GemmArgs{}; g.ws = vb.WS; g.ws_elems = GE_WS_ELEMS; g.A = vb.YV; g.Bt = vt.St; g.C = vb.VSH; g.lda = YLD; g.ldb = YLD; g.ldc = SLD;
