@@ -40,7 +40,7 @@ __device__ __forceinline__ int32_t sn_montred(int32_t a)            // a * 2^-16
 }
 
 // rows of g.A (407 values, canonical) -> rows of g.C (1454 shares: parties 0..150 hold the 151 tail values verbatim)
-__global__ void __launch_bounds__(32 * SN_WARPS) k_share_ntt(const GemmArgs g, const ShareNttTables tb)
+__global__ void __launch_bounds__(32 * SN_WARPS, 4) k_share_ntt(const GemmArgs g, const ShareNttTables tb)
 {
     __shared__ int16_t s_kh[SN_NK * 256];
     __shared__ int16_t s_tw[2 * 256];
@@ -67,12 +67,14 @@ __global__ void __launch_bounds__(32 * SN_WARPS) k_share_ntt(const GemmArgs g, c
                 x[a] = j < D1 ? sn_montred((int32_t)yrow[j] * (int32_t)__ldg(tb.wj + j)) : 0;
             }
             int32_t y[16];
+            // w16^(a (k + 8)) = (-1)^a w16^(a k): even and odd inputs are summed once for the output pair (k, k + 8)
 #pragma unroll
-            for (int k = 0; k < 16; k++) {
-                int32_t acc = 0;
+            for (int k = 0; k < 8; k++) {
+                int32_t ev = 0, od = 0;
 #pragma unroll
-                for (int a = 0; a < 8; a++) acc += x[a] * c_sn_w16f[a * 16 + k];
-                y[k] = sn_montred(sn_montred(acc) * (int32_t)s_tw[k * 16 + c]);
+                for (int a = 0; a < 8; a += 2) { ev += x[a] * c_sn_w16f[a * 16 + k]; od += x[a + 1] * c_sn_w16f[(a + 1) * 16 + k]; }
+                y[k] = sn_montred(sn_montred(ev + od) * (int32_t)s_tw[k * 16 + c]);
+                y[k + 8] = sn_montred(sn_montred(ev - od) * (int32_t)s_tw[(k + 8) * 16 + c]);
             }
 #pragma unroll
             for (int k = 0; k < 16; k++) T[k * 17 + c] = y[k];
@@ -81,11 +83,12 @@ __global__ void __launch_bounds__(32 * SN_WARPS) k_share_ntt(const GemmArgs g, c
 #pragma unroll
             for (int b = 0; b < 16; b++) in[b] = T[c * 17 + b];
 #pragma unroll
-            for (int k = 0; k < 16; k++) {
-                int32_t acc = 0;
+            for (int k = 0; k < 8; k++) {
+                int32_t ev = 0, od = 0;
 #pragma unroll
-                for (int b = 0; b < 16; b++) acc += in[b] * c_sn_w16f[b * 16 + k];
-                uh[blk][k * 16 + c] = (int16_t)sn_montred(acc);
+                for (int b = 0; b < 16; b += 2) { ev += in[b] * c_sn_w16f[b * 16 + k]; od += in[b + 1] * c_sn_w16f[(b + 1) * 16 + k]; }
+                uh[blk][k * 16 + c] = (int16_t)sn_montred(ev + od);
+                uh[blk][(k + 8) * 16 + c] = (int16_t)sn_montred(ev - od);
             }
             __syncwarp();
         }
@@ -106,11 +109,12 @@ __global__ void __launch_bounds__(32 * SN_WARPS) k_share_ntt(const GemmArgs g, c
             }
             int32_t v[16];
 #pragma unroll
-            for (int b = 0; b < 16; b++) {
-                int32_t acc = 0;
+            for (int b = 0; b < 8; b++) {
+                int32_t ev = 0, od = 0;
 #pragma unroll
-                for (int k = 0; k < 16; k++) acc += O[k] * c_sn_w16i[k * 16 + b];
-                v[b] = sn_montred(sn_montred(acc) * (int32_t)s_tw[256 + b * 16 + c]);
+                for (int k = 0; k < 16; k += 2) { ev += O[k] * c_sn_w16i[k * 16 + b]; od += O[k + 1] * c_sn_w16i[(k + 1) * 16 + b]; }
+                v[b] = sn_montred(sn_montred(ev + od) * (int32_t)s_tw[256 + b * 16 + c]);
+                v[b + 8] = sn_montred(sn_montred(ev - od) * (int32_t)s_tw[256 + (b + 8) * 16 + c]);
             }
 #pragma unroll
             for (int b = 0; b < 16; b++) T[b * 17 + c] = v[b];
