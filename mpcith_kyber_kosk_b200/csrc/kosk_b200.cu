@@ -79,7 +79,7 @@ struct kosk_b200_ctx {
     cudaEvent_t last_gate = nullptr;       // event the next prove sub-batch waits for: last_computed, or the previous sub-batch's pre_tail
     int overlap_tail = 1;                  // KOSK_B200_OVERLAP_TAIL: let a sub-batch start while the previous one runs FS-2 + assembly
     int use_ntt = 1;                       // KOSK_B200_SHARE_NTT: share evaluation as a blocked NTT convolution (share_ntt.cuh) instead of the dense table GEMM
-    int16_t *d_sn = nullptr;               // its tables: tw[512] | khat[SN_NK*256] | wj[512] | px[1408]
+    int16_t *d_sn = nullptr;               // its tables: tw[512] | khat[SN_NK*16*SN_LD] | wj[512] | px[1408]
     ShareNttTables sn{};
     Slots sl; Layout L;
     uint64_t launches = 0;
@@ -255,7 +255,7 @@ int kosk_b200_create_ex(kosk_b200_ctx **out, int k, int device, int max_chunk, i
             std::vector<int16_t> all; all.insert(all.end(), sh.tw.begin(), sh.tw.end()); all.insert(all.end(), sh.khat.begin(), sh.khat.end());
             all.insert(all.end(), sh.wj.begin(), sh.wj.end()); all.insert(all.end(), sh.px.begin(), sh.px.end());
             ALLOC(c->d_sn, all.size() * 2); CU(cudaMemcpy(c->d_sn, all.data(), all.size() * 2, cudaMemcpyHostToDevice));
-            c->sn.tw = c->d_sn; c->sn.khat = c->d_sn + 512; c->sn.wj = c->sn.khat + SN_NK * 256; c->sn.px = c->sn.wj + 512;
+            c->sn.tw = c->d_sn; c->sn.khat = c->d_sn + 512; c->sn.wj = c->sn.khat + SN_NK * 16 * SN_LD; c->sn.px = c->sn.wj + 512;
         }
         std::vector<uint16_t> fc(2 * FACT_N);
         { uint32_t f = 1; for (int i = 0; i < FACT_N; i++) { if (i) f = f * i % Q; fc[i] = (uint16_t)f; fc[FACT_N + i] = inv[f]; } }

@@ -23,12 +23,13 @@ namespace kosk {
 
 constexpr int SN_NIN = 4, SN_NOUT = 11, SN_NK = SN_NIN + SN_NOUT - 1;   // kernel segments o - i in [-3, 10]
 constexpr int SN_WARPS = 4;                                              // sharings in flight per CTA
+constexpr int SN_LD = 24;               // int16 per k1 row of a spectrum in shared memory: 16 values (k2) + pad, so that the 128-bit row reads of a quarter-warp hit distinct banks
 
 __constant__ int32_t c_sn_w16f[256], c_sn_w16i[256];   // w16^(+-a k) * R, centered; w16 = 17^16
 
 struct ShareNttTables {
     const int16_t *tw;       // [2][16][16]  17^(+-b k1) * R (symmetric in b, k1)
-    const int16_t *khat;     // [SN_NK][16 k2][16 k1]  NTT(K_delta)[k1 + 16 k2] / 256 * R
+    const int16_t *khat;     // [SN_NK][16 k1][SN_LD]  NTT(K_delta)[k1 + 16 k2] / 256 * R at [k1][k2]
     const int16_t *wj;       // [512]   w_j * R (0 for j >= 407)
     const int16_t *px;       // [1408]  P(x) * R (0 for x >= 1303)
 };
@@ -42,15 +43,17 @@ __device__ __forceinline__ int32_t sn_montred(int32_t a)            // a * 2^-16
 // rows of g.A (407 values, canonical) -> rows of g.C (1454 shares: parties 0..150 hold the 151 tail values verbatim)
 __global__ void __launch_bounds__(32 * SN_WARPS, 4) k_share_ntt(const GemmArgs g, const ShareNttTables tb)
 {
-    __shared__ int16_t s_kh[SN_NK * 256];
+    __shared__ __align__(16) int16_t s_kh[SN_NK * 16 * SN_LD];
     __shared__ int16_t s_tw[2 * 256];
-    __shared__ int16_t s_uh[SN_WARPS][SN_NIN][256];
+    __shared__ __align__(16) int16_t s_uh[SN_WARPS][SN_NIN][16 * SN_LD];
     __shared__ int32_t s_t[SN_WARPS][2][16 * 17];
-    for (int i = threadIdx.x; i < SN_NK * 256; i += blockDim.x) s_kh[i] = tb.khat[i];
+    for (int i = threadIdx.x; i < SN_NK * 16 * SN_LD; i += blockDim.x) s_kh[i] = tb.khat[i];
     for (int i = threadIdx.x; i < 512; i += blockDim.x) s_tw[i] = tb.tw[i];
     __syncthreads();
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, hw = lane >> 4, c = lane & 15;
-    int16_t (*uh)[256] = s_uh[wid];
+    int16_t (*uh)[16 * SN_LD] = s_uh[wid];
+    auto lo16 = [](uint32_t w) -> int32_t { return (int32_t)(int16_t)(w & 0xFFFFu); };
+    auto hi16 = [](uint32_t w) -> int32_t { return (int32_t)w >> 16; };
     int32_t *T = s_t[wid][hw];
     for (int m = blockIdx.x * SN_WARPS + wid; m < g.mtotal; m += gridDim.x * SN_WARPS) {
         const u16 *yrow = g.A + ((size_t)(m / g.rpp) * g.a_slots + g.slot_lo + m % g.rpp) * g.lda;
@@ -82,13 +85,20 @@ __global__ void __launch_bounds__(32 * SN_WARPS, 4) k_share_ntt(const GemmArgs g
             int32_t in[16];
 #pragma unroll
             for (int b = 0; b < 16; b++) in[b] = T[c * 17 + b];
+            int32_t X[16];
 #pragma unroll
             for (int k = 0; k < 8; k++) {
                 int32_t ev = 0, od = 0;
 #pragma unroll
                 for (int b = 0; b < 16; b += 2) { ev += in[b] * c_sn_w16f[b * 16 + k]; od += in[b + 1] * c_sn_w16f[(b + 1) * 16 + k]; }
-                uh[blk][k * 16 + c] = (int16_t)sn_montred(ev + od);
-                uh[blk][(k + 8) * 16 + c] = (int16_t)sn_montred(ev - od);
+                X[k] = sn_montred(ev + od); X[k + 8] = sn_montred(ev - od);
+            }
+            {   // row k1 = c of the spectrum: 16 values (k2) as two 128-bit stores
+                uint32_t w[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) w[k] = ((uint32_t)X[2 * k] & 0xFFFFu) | ((uint32_t)X[2 * k + 1] << 16);
+                uint4 *p = reinterpret_cast<uint4 *>(&uh[blk][c * SN_LD]);
+                p[0] = make_uint4(w[0], w[1], w[2], w[3]); p[1] = make_uint4(w[4], w[5], w[6], w[7]);
             }
             __syncwarp();
         }
@@ -98,14 +108,29 @@ __global__ void __launch_bounds__(32 * SN_WARPS, 4) k_share_ntt(const GemmArgs g
             const int o = 2 * it + hw;
             const bool live = o < SN_NOUT;
             int32_t O[16];
+            {
+                int32_t acc[16];
 #pragma unroll
-            for (int k = 0; k < 16; k++) {
-                int32_t acc = 0;
+                for (int k = 0; k < 16; k++) acc[k] = 0;
                 if (live) {
 #pragma unroll
-                    for (int i = 0; i < SN_NIN; i++) acc += (int32_t)uh[i][k * 16 + c] * (int32_t)s_kh[(o - i + SN_NIN - 1) * 256 + k * 16 + c];
+                    for (int i = 0; i < SN_NIN; i++) {
+                        const uint4 *pu = reinterpret_cast<const uint4 *>(&uh[i][c * SN_LD]);
+                        const uint4 *pk = reinterpret_cast<const uint4 *>(&s_kh[((o - i + SN_NIN - 1) * 16 + c) * SN_LD]);
+#pragma unroll
+                        for (int h2 = 0; h2 < 2; h2++) {
+                            const uint4 u4 = pu[h2], k4 = pk[h2];
+                            const uint32_t uw[4] = {u4.x, u4.y, u4.z, u4.w}, kw[4] = {k4.x, k4.y, k4.z, k4.w};
+#pragma unroll
+                            for (int e = 0; e < 4; e++) {
+                                acc[8 * h2 + 2 * e] += lo16(uw[e]) * lo16(kw[e]);
+                                acc[8 * h2 + 2 * e + 1] += hi16(uw[e]) * hi16(kw[e]);
+                            }
+                        }
+                    }
                 }
-                O[k] = sn_montred(acc);
+#pragma unroll
+                for (int k = 0; k < 16; k++) O[k] = sn_montred(acc[k]);
             }
             int32_t v[16];
 #pragma unroll
@@ -172,7 +197,7 @@ static inline ShareNttHost share_ntt_tables()
     std::vector<uint32_t> opw(256);
     for (int i = 0; i < 256; i++) opw[i] = pw(om, i);
     const uint32_t i256 = inv(256);
-    h.khat.assign((size_t)SN_NK * 256, 0);
+    h.khat.assign((size_t)SN_NK * 16 * SN_LD, 0);
     for (int dl = -(SN_NIN - 1); dl < SN_NOUT; dl++) {
         uint32_t K[256];
         for (int t = 0; t < 256; t++) {
@@ -183,7 +208,7 @@ static inline ShareNttHost share_ntt_tables()
             uint32_t s = 0;
             for (int t = 0; t < 256; t++) s = (s + K[t] * opw[(t * k) & 255]) % Q;
             const int k1 = k & 15, k2 = k >> 4;
-            h.khat[(size_t)(dl + SN_NIN - 1) * 256 + k2 * 16 + k1] = (int16_t)mont(s * i256 % Q);
+            h.khat[((size_t)(dl + SN_NIN - 1) * 16 + k1) * SN_LD + k2] = (int16_t)mont(s * i256 % Q);
         }
     }
     return h;
