@@ -351,6 +351,10 @@ static void launch_share_eval(kosk_b200_ctx *c, const u16 *Y, u16 *SH, int slot_
 static void launch_share_eval_prove(kosk_b200_ctx *c, const ProveBufs &pb, int lo, int hi, int B, cudaStream_t st)
 {
     const Slots &sl = c->sl;
+    if (c->use_ntt && !c->use_tensor) {      // the NTT-convolution kernel has no short path to select: one launch over all slots
+        launch_share_eval(c, pb.Y, pb.SH, lo, hi - lo, sl.n2, sl.nslot, B, st, false, nullptr, nullptr, pb.WS);
+        return;
+    }
     const int a_lo = lo, a_hi = std::min(hi, sl.seta0), b_lo = std::max(lo, sl.seta0), b_hi = std::min(hi, sl.s0), c_lo = std::max(lo, sl.s0), c_hi = hi;
     launch_share_eval(c, pb.Y, pb.SH, a_lo, a_hi - a_lo, sl.n2, sl.nslot, B, st, false, pb.YL0, pb.YL1, pb.WS);
     launch_share_eval(c, pb.Y, pb.SH, b_lo, b_hi - b_lo, sl.n2, sl.nslot, B, st, true, pb.YL0, pb.YL1, pb.WS);

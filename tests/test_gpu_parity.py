@@ -534,3 +534,39 @@ def test_kem_arbitrary_bytes_match_live_reference(ctxs, k):
         wct, wss = O.ref_kem_enc_derand(k, pk[i], coins[i])
         assert bytes(wct) == bytes(ct[i]) and bytes(wss) == bytes(ss[i])
         assert bytes(O.ref_kem_dec(k, rct[i], sk[i])) == bytes(dss[i])
+
+
+@pytest.mark.parametrize("k", [2, 3, 4])
+def test_dense_table_share_eval_matches_ntt_convolution(k):
+    """The share evaluation runs as a blocked NTT convolution (share_ntt.cuh) by default and as the dense 1303 x 407 table GEMM
+    (gf_gemm.cuh) with KOSK_B200_SHARE_NTT=0: same shares, same proofs, same verify results, and both equal the oracle."""
+    from mpcith_kyber_kosk_b200 import KoskContext
+    rng = np.random.default_rng(90 + k)
+    y = rng.integers(0, 3329, size=(37, 407), dtype=np.uint16)
+    y[0] = 3328; y[1] = 0; y[2, :256] = 5
+    seeds = seeds_for_range(4000 + k, 0, 5)
+    out = {}
+    for mode in ("1", "0"):
+        old = os.environ.get("KOSK_B200_SHARE_NTT")
+        os.environ["KOSK_B200_SHARE_NTT"] = mode
+        try:
+            ctx = KoskContext(k, 0, 8)
+        finally:
+            if old is None:
+                os.environ.pop("KOSK_B200_SHARE_NTT", None)
+            else:
+                os.environ["KOSK_B200_SHARE_NTT"] = old
+        sh = ctx.share_eval(y)
+        pk, sk, pi = ctx.prove_batch(seeds)
+        ok = ctx.verify_batch(pi, pk)
+        bad = pi.copy(); bad[:, 0] ^= 1
+        rej = ctx.verify_batch(bad, pk)
+        out[mode] = (sh, pk.copy(), sk.copy(), pi.copy(), ok, rej)
+        ctx.close()
+    for a, b in zip(out["1"], out["0"]):
+        assert (a == b).all()
+    assert out["1"][4].all() and not out["1"][5].any()
+    for i in (0, 1, 2, 36):
+        assert (out["1"][0][i] == O.oracle_share(y[i])).all()
+    opk, osk, opi = O.oracle_prove(k, bytes(seeds[0]))
+    assert (out["1"][3][0] == opi).all() and (out["1"][1][0] == opk).all()
