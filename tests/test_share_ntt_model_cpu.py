@@ -1,0 +1,59 @@
+"""CPU suite: the identity behind csrc/share_ntt.cuh, checked against the oracle's table mat-vec (ko_share_ddeg, reference ss.cpp:76-99)
+in plain Python integers -- no GPU, no Montgomery form: a packed-Shamir sharing is P(x) * sum_j c[x + 407 - j] * (w_j y_j) with c[m] = 1/m,
+and that Toeplitz product equals the blocked length-256 cyclic convolutions over GF(3329) (4 input blocks, 11 output blocks, root 17)."""
+import numpy as np
+
+import oracle_lib as O
+
+Q, D1, NX = 3329, 407, 1303
+
+
+def _inv(a):
+    return pow(int(a) % Q, Q - 2, Q)
+
+
+def _ntt(v, root):
+    n = len(v)
+    pw = [pow(root, i, Q) for i in range(n)]
+    return [sum(v[t] * pw[(t * k) % n] for t in range(n)) % Q for k in range(n)]
+
+
+def test_blocked_ntt_convolution_equals_the_share_table():
+    assert pow(17, 256, Q) == 1 and pow(17, 128, Q) == Q - 1          # 17 generates the 256-th roots of unity (the Kyber NTT's root)
+    w, P = [], []
+    for j in range(D1):
+        d = 1
+        for m in range(D1):
+            if m != j:
+                d = d * ((j - m) % Q) % Q
+        w.append(_inv(d))
+    for x in range(NX):
+        p = 1
+        for m in range(D1):
+            p = p * ((x + D1 - m) % Q) % Q
+        P.append(p)
+    c = [0] + [_inv(m) for m in range(1, Q)]
+    rng = np.random.default_rng(3)
+    y = rng.integers(0, Q, size=D1, dtype=np.uint16)
+    want = O.oracle_share(y)                                            # parties 0..150 = tail, 151.. = S y
+    assert (want[:151] == y[256:]).all()
+    u = [w[j] * int(y[j]) % Q for j in range(D1)] + [0] * (512 - D1)
+    U = [_ntt(u[128 * i:128 * i + 128] + [0] * 128, 17) for i in range(4)]
+    spectra = {}
+    for dl in range(-3, 11):                                            # kernel segment K_dl[d] = c[128 dl + 407 + d], d in [-127, 127]
+        K = [0] * 256
+        for t in range(256):
+            d = t if t < 128 else t - 256
+            m = 128 * dl + D1 + d
+            K[t] = c[m] if (t != 128 and 1 <= m < Q) else 0
+        spectra[dl] = _ntt(K, 17)
+    i256, iom = _inv(256), _inv(17)
+    got = np.zeros(NX, np.int64)
+    for o in (0, 5, 10):                                                # first, a middle and the last (partial) output block
+        acc = [sum(spectra[o - i][n] * U[i][n] for i in range(4)) % Q for n in range(256)]
+        blk = _ntt(acc, iom)
+        for t in range(128):
+            x = 128 * o + t
+            if x < NX:
+                got[x] = blk[t] * i256 % Q * P[x] % Q
+                assert got[x] == want[151 + x], (o, t)
