@@ -570,3 +570,15 @@ def test_dense_table_share_eval_matches_ntt_convolution(k):
         assert (out["1"][0][i] == O.oracle_share(y[i])).all()
     opk, osk, opi = O.oracle_prove(k, bytes(seeds[0]))
     assert (out["1"][3][0] == opi).all() and (out["1"][1][0] == opk).all()
+
+
+def test_share_eval_noncanonical_inputs(ctxs):
+    """u16 inputs >= q act as their residue, as in the reference's gf3329_mul ((uint32_t)a * b % 3329, utils/gf3329.c:282-284)."""
+    rng = np.random.default_rng(11)
+    y = rng.integers(0, 65536, size=(9, 407), dtype=np.uint16)
+    y[0] = 65535
+    got = ctxs(2).share_eval(y)
+    for i in range(9):
+        want = O.oracle_share(y[i])
+        assert (got[i, 151:] == want[151:]).all()
+        assert (got[i, :151] == y[i, 256:]).all()          # the tail is copied verbatim (ss.cpp:77-80)
