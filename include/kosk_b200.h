@@ -124,6 +124,10 @@ int kosk_b200_verify(kosk_b200_ctx *ctx, const uint8_t *pi, const void *inst);  
  *                         context DRBG (kosk_b200_rng_reset), as crypto_kem_enc does from the global RNG (kem.c:114-122)
  * Host buffers, synchronous; the *_device forms take device pointers and enqueue on `stream`. */
 size_t kosk_b200_ct_bytes(int kyber_k);
+/* crypto_kem_keypair_derand (kyber/kem.c:23-33) for n coins[n][64] (d | z), and crypto_kem_keypair (kem.c:47-58) with the 64 coins drawn
+ * as the next call of the context DRBG.  Same keys as kyber_keygen (kosk.cpp:4-70) for the same d, except sk's last 32 bytes (z). */
+int kosk_b200_kem_keypair_derand_batch(kosk_b200_ctx *ctx, size_t n, const uint8_t *coins, uint8_t *pk, uint8_t *sk);
+int kosk_b200_kem_keypair(kosk_b200_ctx *ctx, uint8_t *pk, uint8_t *sk);
 int kosk_b200_kem_enc_derand_batch(kosk_b200_ctx *ctx, size_t n, const uint8_t *pk, const uint8_t *coins, uint8_t *ct, uint8_t *ss);
 int kosk_b200_kem_dec_batch(kosk_b200_ctx *ctx, size_t n, const uint8_t *ct, const uint8_t *sk, uint8_t *ss);
 int kosk_b200_kem_enc_derand_batch_device(kosk_b200_ctx *ctx, size_t n, const uint8_t *d_pk, const uint8_t *d_coins, uint8_t *d_ct, uint8_t *d_ss, void *stream);

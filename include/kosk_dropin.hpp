@@ -157,9 +157,11 @@ inline void encode_mpcith_proof(uint8_t *buf, const mpcith_proof *pi) { memcpy(b
 inline void decode_mpcith_proof(mpcith_proof *pi, const uint8_t *buf) { memcpy(pi, buf, sizeof(mpcith_proof)); }     /* :545-630, field by field = the same bytes */
 
 /* ---- Kyber KEM on the generated keys (kyber/kem.h:29-33; main.cpp:98-113) ---- */
+inline int kosk_dropin_kem_keypair(uint8_t *pk, uint8_t *sk) { kosk_dropin_detail::ok(kosk_b200_kem_keypair(kosk_dropin_detail::state().ctx, pk, sk)); return 0; }
 inline int kosk_dropin_kem_enc(uint8_t *ct, uint8_t *ss, const uint8_t *pk) { kosk_dropin_detail::ok(kosk_b200_kem_enc(kosk_dropin_detail::state().ctx, ct, ss, pk)); return 0; }
 inline int kosk_dropin_kem_dec(uint8_t *ss, const uint8_t *ct, const uint8_t *sk) { kosk_dropin_detail::ok(kosk_b200_kem_dec(kosk_dropin_detail::state().ctx, ss, ct, sk)); return 0; }
 #ifndef crypto_kem_enc      /* the reference namespaces these through macros as well (kyber/kem.h:26-33) */
+#define crypto_kem_keypair kosk_dropin_kem_keypair
 #define crypto_kem_enc kosk_dropin_kem_enc
 #define crypto_kem_dec kosk_dropin_kem_dec
 #endif

@@ -20,7 +20,7 @@ EXPORTS = [
     "kosk_b200_inst_bytes", "kosk_b200_randomness_bytes", "kosk_b200_range_proof_bytes", "kosk_b200_rng_reset", "kosk_b200_rng_calls", "kosk_b200_verifiable_keygen_rng",
     "kosk_b200_prepare_randomness", "kosk_b200_prepare_range_proof", "kosk_b200_keygen", "kosk_b200_prove", "kosk_b200_verify",
     "kosk_b200_ct_bytes", "kosk_b200_kem_enc_derand_batch", "kosk_b200_kem_dec_batch", "kosk_b200_kem_enc_derand_batch_device", "kosk_b200_kem_dec_batch_device",
-    "kosk_b200_kem_enc", "kosk_b200_kem_dec",
+    "kosk_b200_kem_enc", "kosk_b200_kem_dec", "kosk_b200_kem_keypair_derand_batch", "kosk_b200_kem_keypair",
     "kosk_b200_pool_create", "kosk_b200_pool_prove", "kosk_b200_pool_destroy", "kosk_b200_set_strict", "kosk_b200_set_profiling", "kosk_b200_phase_times", "kosk_b200_int_peak",
 ]
 
@@ -86,6 +86,8 @@ def load_library(path=None):
     lib.kosk_b200_kem_dec_batch.argtypes = [vp, sz, u8p, u8p, u8p]
     lib.kosk_b200_kem_enc_derand_batch_device.argtypes = [vp, sz, u8p, u8p, u8p, u8p, vp]
     lib.kosk_b200_kem_dec_batch_device.argtypes = [vp, sz, u8p, u8p, u8p, vp]
+    lib.kosk_b200_kem_keypair_derand_batch.argtypes = [vp, sz, u8p, u8p, u8p]
+    lib.kosk_b200_kem_keypair.argtypes = [vp, u8p, u8p]
     lib.kosk_b200_kem_enc.argtypes = [vp, u8p, u8p, u8p]
     lib.kosk_b200_kem_dec.argtypes = [vp, u8p, u8p, u8p]
     lib.kosk_b200_phase_times.argtypes = [vp, u8p, u8p, i32, i32]
@@ -202,6 +204,20 @@ class KoskContext:
     @property
     def ct_bytes(self):
         return self.lib.kosk_b200_ct_bytes(self.k)
+
+    def kem_keypair_derand_batch(self, coins):
+        """crypto_kem_keypair_derand (kem.c:23-33) for coins[n][64]: returns (pk[n], sk[n])."""
+        coins = np.ascontiguousarray(coins, dtype=np.uint8).reshape(-1, 64)
+        n = coins.shape[0]
+        pk, sk = np.empty((n, self.pk_bytes), np.uint8), np.empty((n, self.sk_bytes), np.uint8)
+        self._check(self.lib.kosk_b200_kem_keypair_derand_batch(self._h, n, _ptr(coins), _ptr(pk), _ptr(sk)), "kem_keypair_derand_batch")
+        return pk, sk
+
+    def crypto_kem_keypair(self):
+        """crypto_kem_keypair (kem.c:47-58): the 64 coins are the next call of the context DRBG."""
+        pk, sk = np.empty(self.pk_bytes, np.uint8), np.empty(self.sk_bytes, np.uint8)
+        self._check(self.lib.kosk_b200_kem_keypair(self._h, _ptr(pk), _ptr(sk)), "kem_keypair")
+        return bytes(pk), bytes(sk)
 
     def kem_enc_derand_batch(self, pk, coins):
         pk = np.ascontiguousarray(pk, dtype=np.uint8).reshape(-1, self.pk_bytes)

@@ -280,11 +280,12 @@ __global__ void __launch_bounds__(128) k_kem_dec(const u8 *__restrict__ cts, con
 // ---- host side ----
 struct KemState {
     u8 *d_a = nullptr, *d_b = nullptr, *d_c = nullptr, *d_d = nullptr; size_t cap = 0;       // grow-only staging of the host-buffer API
+    u8 *d_coins64 = nullptr;                                                                   // [chunk][64] coins of crypto_kem_keypair_derand
     bool tables = false;
 };
 static void kem_free(KemState &ks)
 {
-    void *p[] = {ks.d_a, ks.d_b, ks.d_c, ks.d_d};
+    void *p[] = {ks.d_a, ks.d_b, ks.d_c, ks.d_d, ks.d_coins64};
     for (void *q : p) if (q) cudaFree(q);
     ks = KemState{};
 }
@@ -342,6 +343,8 @@ static int kem_dec_launch(kosk_b200_ctx *c, size_t n, const u8 *d_ct, const u8 *
     return KOSK_OK;
 }
 
+template <int K> static void kem_launch_keygen(const ProveBufs &pb, int B, cudaStream_t st) { k_keygen<K><<<B, 128, 0, st>>>(pb); }
+
 extern "C" {
 
 size_t kosk_b200_ct_bytes(int k) { return (k >= 2 && k <= 4) ? (size_t)kem_dims(k).ct_bytes : 0; }
@@ -397,6 +400,40 @@ int kosk_b200_kem_dec_batch(kosk_b200_ctx *c, size_t n, const uint8_t *ct, const
     CU(cudaMemcpyAsync(ss, ks.d_d, n * 32, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     return KOSK_OK;
+}
+
+// crypto_kem_keypair_derand / crypto_kem_keypair (kem.c:23-58): the keygen kernel of the KOSK path with z taken from the coins
+static int kem_keypair_host(kosk_b200_ctx *c, size_t n, const uint8_t *coins /* [n][64] or nullptr = one DRBG call */, uint8_t *pk, uint8_t *sk)
+{
+    CU(cudaSetDevice(c->device));
+    KemState &ks = *c->kem; Lane &ln = c->lanes[0];
+    if (coins && !ks.d_coins64 && cudaMalloc((void **)&ks.d_coins64, (size_t)c->chunk * 64) != cudaSuccess) return fail(KOSK_E_NOMEM, "cudaMalloc failed for KEM coins");
+    CU(cudaStreamSynchronize(ln.st));
+    for (size_t o = 0; o < n; o += (size_t)c->chunk) {
+        const int B = (int)std::min<size_t>((size_t)c->chunk, n - o);
+        ProveBufs pb = ln.pb; pb.seeds = ln.d_seeds; pb.pk = ln.d_pk; pb.sk = ln.d_sk; pb.pi = ln.d_pi; pb.B = B;
+        if (coins) { CU(cudaMemcpyAsync(ks.d_coins64, coins + 64 * o, 64 * (size_t)B, cudaMemcpyHostToDevice, ln.st)); pb.kem_mode = 1; pb.kem_coins = ks.d_coins64; }
+        else { CU(cudaMemcpyAsync(ln.d_seeds, c->raw->seed, 32, cudaMemcpyHostToDevice, ln.st)); pb.kem_mode = 2; pb.cb_key = (int)c->raw->calls; }
+        switch (c->k) { case 2: kem_launch_keygen<2>(pb, B, ln.st); break; case 3: kem_launch_keygen<3>(pb, B, ln.st); break; default: kem_launch_keygen<4>(pb, B, ln.st); }
+        c->launches++;
+        CU(cudaMemcpyAsync(pk + c->L.pk_bytes * o, ln.d_pk, c->L.pk_bytes * (size_t)B, cudaMemcpyDeviceToHost, ln.st));
+        CU(cudaMemcpyAsync(sk + c->L.sk_bytes * o, ln.d_sk, c->L.sk_bytes * (size_t)B, cudaMemcpyDeviceToHost, ln.st));
+        CU(cudaStreamSynchronize(ln.st));
+    }
+    CU(cudaGetLastError());
+    return KOSK_OK;
+}
+int kosk_b200_kem_keypair_derand_batch(kosk_b200_ctx *c, size_t n, const uint8_t *coins, uint8_t *pk, uint8_t *sk)
+{
+    if (!c || !coins || !pk || !sk) return fail(KOSK_E_ARG, "null argument");
+    return n ? kem_keypair_host(c, n, coins, pk, sk) : KOSK_OK;
+}
+int kosk_b200_kem_keypair(kosk_b200_ctx *c, uint8_t *pk, uint8_t *sk)
+{
+    if (!c || !pk || !sk) return fail(KOSK_E_ARG, "null argument");
+    int rc = kem_keypair_host(c, 1, nullptr, pk, sk);
+    if (!rc) c->raw->calls += 1;                 // randombytes(coins, 64), kem.c:52
+    return rc;
 }
 
 // crypto_kem_enc (kem.c:114-122): coins = randombytes(32) = the next call of the context DRBG (kosk_b200_rng_reset)

@@ -32,10 +32,14 @@ struct ProveBufs {
     // the struct-level API (raw_api.cuh) numbers them by the caller's own call order, as the reference's global RNG would.
     int cb_key, cb_rand, cb_eta, cb_prove;
     int tails_mask;    // k_tails: 1 = f / NTT_f sharings, 2 = eta sharings, 4 = sharings made inside prove() (s, e, z_j, A s)
+    // k_keygen as crypto_kem_keypair (kyber/kem.c:23-58) instead of kyber_keygen (kosk.cpp:4-70): 0 = kyber_keygen (z = the noise seed,
+    // kosk.cpp:66-68), 1 = crypto_kem_keypair_derand on kem_coins[B][64] (d | z), 2 = crypto_kem_keypair (d | z = one 64-byte DRBG call)
+    int kem_mode; const u8 *kem_coins;
 };
 __host__ __device__ inline void set_default_calls(ProveBufs &pb, const Slots &sl)
 {
     pb.cb_key = 0; pb.cb_rand = sl.c_seed0; pb.cb_eta = sl.c_eta0; pb.cb_prove = sl.c_se0; pb.tails_mask = 7;
+    pb.kem_mode = 0; pb.kem_coins = nullptr;
 }
 
 __device__ __forceinline__ u16 *yrow(const ProveBufs &pb, const Slots &sl, int b, int slot) { return pb.Y + ((size_t)b * sl.n2 + slot) * YLD; }
@@ -132,19 +136,24 @@ __global__ void __launch_bounds__(128) k_keygen(ProveBufs pb)
     const int b = blockIdx.x, tid = threadIdx.x;
     __shared__ u16 sA[K * K][256];
     __shared__ u16 sS[K][256], sE[K][256], sSh[K][256], sEh[K][256], sT[K][256];
-    __shared__ uint64_t sSeed[8];
+    __shared__ uint64_t sSeed[8], sZ[4];
     __shared__ uint64_t sBlk[K * K + 2 * K][24];
     __shared__ __align__(8) u8 sPk[384 * K + 32];
 
     if (tid < 32) {
         // randombytes(buf, 64) (only bytes 0..31 are used, kosk.cpp:12-14), then sha3_512(coins || K): one state word per lane
         WarpKeccak wk; wk.init();
-        const uint64_t *gs = reinterpret_cast<const uint64_t *>(pb.seeds + 32 * (size_t)b);
         uint64_t a = 0;
-        if (tid < 4) a = gs[tid];
-        if (tid == 4) a = (uint64_t)(uint32_t)pb.cb_key | (0x1FULL << 32);
-        if (tid == 16) a = 0x8000000000000000ULL;              // SHAKE256 rate 136 = lanes 0..16
-        a = wk.permute(a);
+        if (pb.kem_mode == 1) {                                // explicit coins: d = coins[0..31], z = coins[32..63]
+            if (tid < 8) for (int q = 0; q < 8; q++) a |= (uint64_t)pb.kem_coins[64 * (size_t)b + 8 * tid + q] << (8 * q);
+        } else {
+            const uint64_t *gs = reinterpret_cast<const uint64_t *>(pb.seeds + 32 * (size_t)b);
+            if (tid < 4) a = gs[tid];
+            if (tid == 4) a = (uint64_t)(uint32_t)pb.cb_key | (0x1FULL << 32);
+            if (tid == 16) a = 0x8000000000000000ULL;              // SHAKE256 rate 136 = lanes 0..16
+            a = wk.permute(a);
+        }
+        if (tid >= 4 && tid < 8) sZ[tid - 4] = a;              // bytes 32..63 of the random block: z of crypto_kem_keypair
         if (tid >= 4) a = 0;
         if (tid == 4) a = (uint64_t)K | (0x06ULL << 8);
         if (tid == 8) a = 0x8000000000000000ULL;               // SHA3-512 rate 72 = lanes 0..8
@@ -202,7 +211,7 @@ __global__ void __launch_bounds__(128) k_keygen(ProveBufs pb)
     if (tid < 32) sPk[384 * K + tid] = reinterpret_cast<const u8 *>(sSeed)[tid];
     __syncthreads();
     for (int i = tid; i < 384 * K + 32; i += 128) { pk[i] = sPk[i]; sk[384 * K + i] = sPk[i]; }
-    if (tid < 32) sk[L.sk_bytes - 32 + tid] = reinterpret_cast<const u8 *>(sSeed + 4)[tid];
+    if (tid < 32) sk[L.sk_bytes - 32 + tid] = pb.kem_mode ? reinterpret_cast<const u8 *>(sZ)[tid] : reinterpret_cast<const u8 *>(sSeed + 4)[tid];
     if (tid < 32) {                                 // sha3_256(pk), warp-cooperative: 800 / 1184 / 1568 bytes = 5 / 8 / 11 full blocks + 15 / 12 / 9 words
         WarpKeccak wk; wk.init();
         constexpr int NB = (384 * K + 32) / 136, REMW = ((384 * K + 32) % 136) / 8;

@@ -83,6 +83,15 @@ int ref_struct_sequence(const uint8_t seed[32], int rng_mode, uint8_t *rand_img,
 size_t ref_ct_bytes(void) { return KYBER_CIPHERTEXTBYTES; }
 void ref_kem_enc_derand(uint8_t *ct, uint8_t *ss, const uint8_t *pk, const uint8_t *coins) { crypto_kem_enc_derand(ct, ss, pk, coins); }
 void ref_kem_dec(uint8_t *ss, const uint8_t *ct, const uint8_t *sk) { crypto_kem_dec(ss, ct, sk); }
+void ref_kem_keypair_derand(uint8_t *pk, uint8_t *sk, const uint8_t *coins) { crypto_kem_keypair_derand(pk, sk, coins); }
+/* crypto_kem_keypair under the counter DRBG positioned at call number `call` */
+void ref_kem_keypair_at(const uint8_t seed[32], uint32_t call, uint8_t *pk, uint8_t *sk)
+{
+    kosk_rng_reset(seed, KOSK_RNG_COUNTER);
+    uint8_t junk[1];
+    for (uint32_t i = 0; i < call; i++) randombytes(junk, 1);
+    crypto_kem_keypair(pk, sk);
+}
 /* crypto_kem_enc under the counter DRBG positioned at call number `call` */
 void ref_kem_enc_at(const uint8_t seed[32], uint32_t call, uint8_t *ct, uint8_t *ss, const uint8_t *pk)
 {

@@ -128,6 +128,10 @@ def ref(k):
             lib.ref_kem_enc_derand.restype = None
             lib.ref_kem_dec.argtypes = [vp, vp, vp]
             lib.ref_kem_dec.restype = None
+            lib.ref_kem_keypair_derand.argtypes = [vp, vp, vp]
+            lib.ref_kem_keypair_derand.restype = None
+            lib.ref_kem_keypair_at.argtypes = [vp, ctypes.c_uint32, vp, vp]
+            lib.ref_kem_keypair_at.restype = None
             lib.ref_kem_enc_at.argtypes = [vp, ctypes.c_uint32, vp, vp, vp]
             lib.ref_kem_enc_at.restype = None
             _refs[k] = lib
@@ -206,6 +210,22 @@ def ref_kem_dec(k, ct, sk):
     ss = np.zeros(32, np.uint8)
     ref(k).ref_kem_dec(_p(ss), _p(ct), _p(sk))
     return ss
+
+
+def ref_kem_keypair_derand(k, coins):
+    L = layout(k)
+    coins = _u8(coins)
+    pk, sk = np.zeros(L.pk_bytes, np.uint8), np.zeros(L.sk_bytes, np.uint8)
+    ref(k).ref_kem_keypair_derand(_p(pk), _p(sk), _p(coins))
+    return pk, sk
+
+
+def ref_kem_keypair_at(k, seed, call):
+    L = layout(k)
+    seed = _u8(seed)
+    pk, sk = np.zeros(L.pk_bytes, np.uint8), np.zeros(L.sk_bytes, np.uint8)
+    ref(k).ref_kem_keypair_at(_p(seed), call, _p(pk), _p(sk))
+    return pk, sk
 
 
 def ref_kem_enc_at(k, seed, call, pk):

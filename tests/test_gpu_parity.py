@@ -582,3 +582,31 @@ def test_share_eval_noncanonical_inputs(ctxs):
         want = O.oracle_share(y[i])
         assert (got[i, 151:] == want[151:]).all()
         assert (got[i, :151] == y[i, 256:]).all()          # the tail is copied verbatim (ss.cpp:77-80)
+
+
+@pytest.mark.parametrize("k", [2, 3, 4])
+def test_kem_keypair_matches_reference(ctxs, k):
+    """crypto_kem_keypair_derand / crypto_kem_keypair (kyber/kem.c:23-58): same pk as kyber_keygen for the same d, z from the coins;
+    keys work with encaps / decaps; bytes equal the live reference's when it is present."""
+    ctx = ctxs(k)
+    rng = np.random.default_rng(120 + k)
+    coins = rng.integers(0, 256, size=(70, 64), dtype=np.uint8)          # > chunk (64): exercises the chunk loop
+    pk, sk = ctx.kem_keypair_derand_batch(coins)
+    assert (sk[:, -32:] == coins[:, 32:]).all()                             # z
+    assert (sk[:, 384 * k:384 * k + ctx.pk_bytes] == pk).all()
+    for i in (0, 69):
+        assert bytes(sk[i, -64:-32]) == hashlib.sha3_256(bytes(pk[i])).digest()
+    ct, ss = ctx.kem_enc_derand_batch(pk, coins[:, :32])
+    assert (ctx.kem_dec_batch(ct, sk) == ss).all()
+    seed = O.seed_of(640 + k)
+    ctx.rng_reset(seed)
+    ctx.prepare_range_proof()                                               # move the DRBG off call 0
+    calls = ctx.rng_calls()
+    pk1, sk1 = ctx.crypto_kem_keypair()
+    assert ctx.rng_calls() == calls + 1
+    if O.ref(k) is not None:
+        for i in (0, 33, 69):
+            rpk, rsk = O.ref_kem_keypair_derand(k, coins[i])
+            assert bytes(rpk) == bytes(pk[i]) and bytes(rsk) == bytes(sk[i])
+        rpk, rsk = O.ref_kem_keypair_at(k, seed, calls)
+        assert bytes(rpk) == pk1 and bytes(rsk) == sk1
