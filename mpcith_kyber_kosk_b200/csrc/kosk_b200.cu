@@ -79,7 +79,7 @@ struct kosk_b200_ctx {
     cudaEvent_t last_gate = nullptr;       // event the next prove sub-batch waits for: last_computed, or the previous sub-batch's pre_tail
     int overlap_tail = 1;                  // KOSK_B200_OVERLAP_TAIL: let a sub-batch start while the previous one runs FS-2 + assembly
     int use_ntt = 1;                       // KOSK_B200_SHARE_NTT: share evaluation as a blocked NTT convolution (share_ntt.cuh) instead of the dense table GEMM
-    int16_t *d_sn = nullptr;               // its tables: tw[512] | khat[SN_NK*16*SN_LD] | wj[512] | px[1408]
+    int16_t *d_sn = nullptr;               // its tables (ShareNttTables), one allocation
     ShareNttTables sn{};
     Slots sl; Layout L;
     uint64_t launches = 0;
@@ -252,10 +252,13 @@ int kosk_b200_create_ex(kosk_b200_ctx **out, int k, int device, int max_chunk, i
         {   // tables of the NTT-convolution share evaluation (share_ntt.cuh)
             const ShareNttHost sh = share_ntt_tables();
             CU(cudaMemcpyToSymbol(c_sn_w16f, sh.w16f.data(), 256 * 4)); CU(cudaMemcpyToSymbol(c_sn_w16i, sh.w16i.data(), 256 * 4));
-            std::vector<int16_t> all; all.insert(all.end(), sh.tw.begin(), sh.tw.end()); all.insert(all.end(), sh.khat.begin(), sh.khat.end());
-            all.insert(all.end(), sh.wj.begin(), sh.wj.end()); all.insert(all.end(), sh.px.begin(), sh.px.end());
+            std::vector<int16_t> all;
+            const std::vector<int16_t> *parts[] = {&sh.tw, &sh.kh_share, &sh.kh_m256, &sh.wj, &sh.wj2, &sh.px, &sh.pr1, &sh.pr2};
+            size_t offs[8]; int np = 0;
+            for (const std::vector<int16_t> *v : parts) { offs[np++] = all.size(); all.insert(all.end(), v->begin(), v->end()); while (all.size() % 8) all.push_back(0); }
             ALLOC(c->d_sn, all.size() * 2); CU(cudaMemcpy(c->d_sn, all.data(), all.size() * 2, cudaMemcpyHostToDevice));
-            c->sn.tw = c->d_sn; c->sn.khat = c->d_sn + 512; c->sn.wj = c->sn.khat + SN_NK * 16 * SN_LD; c->sn.px = c->sn.wj + 512;
+            c->sn.tw = c->d_sn + offs[0]; c->sn.kh_share = c->d_sn + offs[1]; c->sn.kh_m256 = c->d_sn + offs[2]; c->sn.wj = c->d_sn + offs[3];
+            c->sn.wj2 = c->d_sn + offs[4]; c->sn.px = c->d_sn + offs[5]; c->sn.pr1 = c->d_sn + offs[6]; c->sn.pr2 = c->d_sn + offs[7];
         }
         std::vector<uint16_t> fc(2 * FACT_N);
         { uint32_t f = 1; for (int i = 0; i < FACT_N; i++) { if (i) f = f * i % Q; fc[i] = (uint16_t)f; fc[FACT_N + i] = inv[f]; } }
@@ -326,9 +329,7 @@ static void launch_share_eval(kosk_b200_ctx *c, const u16 *Y, u16 *SH, int slot_
     g.mtotal = B * rows; g.ksteps = YLD / GE_BK; g.nvalid = NX; g.c_off = SOFF + NT + 1;
     g.rpp = rows; g.slot_lo = slot_lo; g.a_slots = y_slots; g.c_slots = sh_slots; g.tail = 1; g.tail_off = NL;
     if (c->use_ntt && !(c->use_tensor && YL0)) {      // one warp per sharing; constant-secret rows need no special case here
-        const int ctas = std::min((g.mtotal + SN_WARPS - 1) / SN_WARPS, 148 * 8);
-        k_share_ntt<<<ctas, 32 * SN_WARPS, 0, st>>>(g, c->sn);
-        c->launches += 1;
+        c->launches += conv_ntt_launch<SN_NIN, SN_NOUT>(share_conv_args(g, c->sn), st);
         return;
     }
     const int koff = const_secret ? NL : 0;

@@ -21,17 +21,28 @@
 
 namespace kosk {
 
-constexpr int SN_NIN = 4, SN_NOUT = 11, SN_NK = SN_NIN + SN_NOUT - 1;   // kernel segments o - i in [-3, 10]
-constexpr int SN_WARPS = 4;                                              // sharings in flight per CTA
+constexpr int SN_NIN = 4, SN_NOUT = 11;                                  // the sharing: 407 inputs in 4 blocks, 1303 outputs in 11
+constexpr int SN_WARPS = 4;                                              // rows in flight per CTA
 constexpr int SN_LD = 24;               // int16 per k1 row of a spectrum in shared memory: 16 values (k2) + pad, so that the 128-bit row reads of a quarter-warp hit distinct banks
 
 __constant__ int32_t c_sn_w16f[256], c_sn_w16i[256];   // w16^(+-a k) * R, centered; w16 = 17^16
 
-struct ShareNttTables {
+// One Toeplitz product per row:  C[row][c_off + x] = post[x] * sum_j c[x - j + OFF] * (pre[j] * A[row][j]),  c[m] = 1/m (0 for m = 0),
+// x < nout <= 128 NOUT, j < nin <= 128 NIN.  OFF lives in the kernel-segment table `khat` ([NIN + NOUT - 1] segments for o - i).
+//   sharing (ss.cpp:23-32, :88-97)                 OFF = 407,  pre = w_j,      post = P(x)        (4, 11)
+//   recon_secrets_ddeg / _2ddeg (ss.cpp:37-73)      OFF = -256, pre = w_j,      post = P'(i)       (4, 2) / (7, 2)
+//   verifier interpolation (mlwe_verifier.cpp:188-224 etc.), rows already scaled by the per-proof weights, columns = parties
+//                                                   OFF = -256, pre = none,     post = per-proof P(t) (5, 4) / (8, 2)
+struct ConvArgs {
+    const u16 *A; u16 *C; long long lda, ldc;
+    int mtotal, rpp, slot_lo, a_slots, c_slots, c_off;   // row m -> storage row (m / rpp) * slots + slot_lo + m % rpp
+    int nin, nout;
+    int tail, tail_off;                                  // sharing: copy the 151 tail values to parties 0..150
     const int16_t *tw;       // [2][16][16]  17^(+-b k1) * R (symmetric in b, k1)
-    const int16_t *khat;     // [SN_NK][16 k1][SN_LD]  NTT(K_delta)[k1 + 16 k2] / 256 * R at [k1][k2]
-    const int16_t *wj;       // [512]   w_j * R (0 for j >= 407)
-    const int16_t *px;       // [1408]  P(x) * R (0 for x >= 1303)
+    const int16_t *khat;     // [NIN + NOUT - 1][16 k1][SN_LD]  NTT(K_delta)[k1 + 16 k2] / 256 * R at [k1][k2], delta = o - i
+    const int16_t *pre;      // [128 NIN] input factors * R, or nullptr
+    const u16 *post;         // output factors * R mod q as 16-bit patterns (int16 centered or u16 canonical: both are residues)
+    long long post_group;    // 0: one table; else the table of row m starts at post + (m / rpp) * post_group, entries are u16
 };
 
 __device__ __forceinline__ int32_t sn_montred(int32_t a)            // a * 2^-16 mod q in (-q, q) for |a| < q * 2^15
@@ -40,34 +51,38 @@ __device__ __forceinline__ int32_t sn_montred(int32_t a)            // a * 2^-16
     return (a - t * Q) >> 16;
 }
 
-// rows of g.A (407 values, canonical) -> rows of g.C (1454 shares: parties 0..150 hold the 151 tail values verbatim)
-__global__ void __launch_bounds__(32 * SN_WARPS, 4) k_share_ntt(const GemmArgs g, const ShareNttTables tb)
+template <int NIN, int NOUT>
+__global__ void __launch_bounds__(32 * SN_WARPS, (NIN <= 5 ? 4 : 3)) k_conv_ntt(const ConvArgs g)
 {
-    __shared__ __align__(16) int16_t s_kh[SN_NK * 16 * SN_LD];
+    constexpr int NK = NIN + NOUT - 1, NINP = (NIN + 1) & ~1;
+    __shared__ __align__(16) int16_t s_kh[NK * 16 * SN_LD];
     __shared__ int16_t s_tw[2 * 256];
-    __shared__ __align__(16) int16_t s_uh[SN_WARPS][SN_NIN][16 * SN_LD];
+    __shared__ __align__(16) int16_t s_uh[SN_WARPS][NINP][16 * SN_LD];
     __shared__ int32_t s_t[SN_WARPS][2][16 * 17];
-    for (int i = threadIdx.x; i < SN_NK * 16 * SN_LD; i += blockDim.x) s_kh[i] = tb.khat[i];
-    for (int i = threadIdx.x; i < 512; i += blockDim.x) s_tw[i] = tb.tw[i];
+    for (int i = threadIdx.x; i < NK * 16 * SN_LD; i += blockDim.x) s_kh[i] = g.khat[i];
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) s_tw[i] = g.tw[i];
     __syncthreads();
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, hw = lane >> 4, c = lane & 15;
     int16_t (*uh)[16 * SN_LD] = s_uh[wid];
+    int32_t *T = s_t[wid][hw];
     auto lo16 = [](uint32_t w) -> int32_t { return (int32_t)(int16_t)(w & 0xFFFFu); };
     auto hi16 = [](uint32_t w) -> int32_t { return (int32_t)w >> 16; };
-    int32_t *T = s_t[wid][hw];
     for (int m = blockIdx.x * SN_WARPS + wid; m < g.mtotal; m += gridDim.x * SN_WARPS) {
         const u16 *yrow = g.A + ((size_t)(m / g.rpp) * g.a_slots + g.slot_lo + m % g.rpp) * g.lda;
         u16 *dst = g.C + ((size_t)(m / g.rpp) * g.c_slots + g.slot_lo + m % g.rpp) * g.ldc + g.c_off;
-        for (int t = lane; t <= NT; t += 32) dst[t - (NT + 1)] = yrow[g.tail_off + t];
-        // ---- forward: u_j = w_j y_j, NTT of the four zero-padded 128-wide blocks (two per pass) ----
+        const u16 *post = g.post + (g.post_group ? (size_t)(m / g.rpp) * g.post_group : 0);
+        if (g.tail) for (int t = lane; t <= NT; t += 32) dst[t - (NT + 1)] = yrow[g.tail_off + t];
+        // ---- forward: u_j = pre_j A_j, NTT of the zero-padded 128-wide input blocks (two per pass) ----
 #pragma unroll 1
-        for (int it = 0; it < SN_NIN / 2; it++) {
+        for (int it = 0; it < NINP / 2; it++) {
             const int blk = 2 * it + hw;
             int32_t x[8];
 #pragma unroll
             for (int a = 0; a < 8; a++) {
                 const int j = 128 * blk + 16 * a + c;
-                x[a] = j < D1 ? sn_montred((int32_t)yrow[j] * (int32_t)__ldg(tb.wj + j)) : 0;
+                int32_t v = 0;
+                if (j < g.nin) v = g.pre ? sn_montred((int32_t)yrow[j] * (int32_t)__ldg(g.pre + j)) : (int32_t)yrow[j];
+                x[a] = v;
             }
             int32_t y[16];
             // w16^(a (k + 8)) = (-1)^a w16^(a k): even and odd inputs are summed once for the output pair (k, k + 8)
@@ -104,9 +119,9 @@ __global__ void __launch_bounds__(32 * SN_WARPS, 4) k_share_ntt(const GemmArgs g
         }
         // ---- inverse: output blocks two per pass ----
 #pragma unroll 1
-        for (int it = 0; it < (SN_NOUT + 1) / 2; it++) {
+        for (int it = 0; it < (NOUT + 1) / 2; it++) {
             const int o = 2 * it + hw;
-            const bool live = o < SN_NOUT;
+            const bool live = o < NOUT;
             int32_t O[16];
             {
                 int32_t acc[16];
@@ -114,9 +129,9 @@ __global__ void __launch_bounds__(32 * SN_WARPS, 4) k_share_ntt(const GemmArgs g
                 for (int k = 0; k < 16; k++) acc[k] = 0;
                 if (live) {
 #pragma unroll
-                    for (int i = 0; i < SN_NIN; i++) {
+                    for (int i = 0; i < NIN; i++) {
                         const uint4 *pu = reinterpret_cast<const uint4 *>(&uh[i][c * SN_LD]);
-                        const uint4 *pk = reinterpret_cast<const uint4 *>(&s_kh[((o - i + SN_NIN - 1) * 16 + c) * SN_LD]);
+                        const uint4 *pk = reinterpret_cast<const uint4 *>(&s_kh[((o - i + NIN - 1) * 16 + c) * SN_LD]);
 #pragma unroll
                         for (int h2 = 0; h2 < 2; h2++) {
                             const uint4 u4 = pu[h2], k4 = pk[h2];
@@ -153,8 +168,9 @@ __global__ void __launch_bounds__(32 * SN_WARPS, 4) k_share_ntt(const GemmArgs g
 #pragma unroll
                 for (int k = 0; k < 16; k++) acc += in[k] * c_sn_w16i[k * 16 + a];
                 const int xo = 128 * o + 16 * a + c;
-                if (live && xo < NX) {
-                    int32_t r = sn_montred(sn_montred(acc) * (int32_t)__ldg(tb.px + xo));
+                if (live && xo < g.nout) {
+                    const int32_t pf = g.post_group ? (int32_t)post[xo] : (int32_t)(int16_t)__ldg(post + xo);
+                    int32_t r = sn_montred(sn_montred(acc) * pf);
                     dst[xo] = (u16)(r < 0 ? r + Q : r);
                 }
             }
@@ -163,10 +179,40 @@ __global__ void __launch_bounds__(32 * SN_WARPS, 4) k_share_ntt(const GemmArgs g
     }
 }
 
+template <int NIN, int NOUT>
+static inline int conv_ntt_launch(const ConvArgs &g, cudaStream_t st)
+{
+    const int ctas = std::min((g.mtotal + SN_WARPS - 1) / SN_WARPS, 148 * 8);
+    if (ctas > 0) k_conv_ntt<NIN, NOUT><<<ctas, 32 * SN_WARPS, 0, st>>>(g);
+    return 1;
+}
+
+// device tables of all Toeplitz products of the KOSK path (one allocation per context)
+struct ShareNttTables {
+    const int16_t *tw;
+    const int16_t *kh_share;      // OFF = 407, (4, 11)
+    const int16_t *kh_m256;       // OFF = -256: segments delta in [-7, 3]; a product with (NIN, NOUT) starts at delta = -(NIN - 1)
+    const int16_t *wj;            // [512]   w_j * R over 407 consecutive nodes (0 beyond)
+    const int16_t *wj2;           // [896]   the same over 813 consecutive nodes
+    const int16_t *px;            // [1408]  P(x) * R of the sharing
+    const int16_t *pr1, *pr2;     // [256]   prod_m (i - 256 - m) * R for m < 407 / m < 813 (recon_secrets_ddeg / _2ddeg)
+};
+constexpr int SN_M256_DMIN = -7, SN_M256_DMAX = 3;
+__host__ __device__ inline const int16_t *sn_kh_m256(const ShareNttTables &t, int nin) { return t.kh_m256 + (size_t)(-(nin - 1) - SN_M256_DMIN) * 16 * SN_LD; }
+// the sharing of the rows described by a GemmArgs (row mapping, A / C, tail) as a Toeplitz product
+static inline ConvArgs share_conv_args(const GemmArgs &g, const ShareNttTables &t)
+{
+    ConvArgs a{};
+    a.A = g.A; a.C = g.C; a.lda = g.lda; a.ldc = g.ldc; a.mtotal = g.mtotal; a.rpp = g.rpp; a.slot_lo = g.slot_lo; a.a_slots = g.a_slots; a.c_slots = g.c_slots;
+    a.c_off = g.c_off; a.nin = D1; a.nout = NX; a.tail = g.tail; a.tail_off = g.tail_off;
+    a.tw = t.tw; a.khat = t.kh_share; a.pre = t.wj; a.post = reinterpret_cast<const u16 *>(t.px); a.post_group = 0;
+    return a;
+}
+
 // ---- host: table construction (plain modular arithmetic, once per context) ----
 struct ShareNttHost {
     std::vector<int32_t> w16f, w16i;
-    std::vector<int16_t> tw, khat, wj, px;
+    std::vector<int16_t> tw, kh_share, kh_m256, wj, wj2, px, pr1, pr2;
 };
 static inline ShareNttHost share_ntt_tables()
 {
@@ -181,36 +227,53 @@ static inline ShareNttHost share_ntt_tables()
             h.w16f[a * 16 + k] = mont(pw(om16, a * k)); h.w16i[a * 16 + k] = mont(pw(iom16, a * k));
             h.tw[a * 16 + k] = (int16_t)mont(pw(om, a * k)); h.tw[256 + a * 16 + k] = (int16_t)mont(pw(iom, a * k));
         }
-    // Lagrange weights over the nodes 0..406 and P(x) at x + 407
-    h.wj.assign(512, 0); h.px.assign(1408, 0);
-    for (int j = 0; j < D1; j++) {
-        uint32_t d = 1;
-        for (int m = 0; m < D1; m++) if (m != j) d = d * (uint32_t)((j - m + Q) % Q) % Q;
-        h.wj[j] = (int16_t)mont(inv(d));
-    }
+    // barycentric weights over n consecutive nodes: w_j = 1 / prod_{m != j} (j - m)
+    auto weights = [&](int n, int padded) {
+        std::vector<int16_t> w(padded, 0);
+        for (int j = 0; j < n; j++) {
+            uint32_t d = 1;
+            for (int m = 0; m < n; m++) if (m != j) d = d * (uint32_t)(((j - m) % Q + Q) % Q) % Q;
+            w[j] = (int16_t)mont(inv(d));
+        }
+        return w;
+    };
+    h.wj = weights(D1, 512); h.wj2 = weights(D2, 896);
+    // P at the targets: the sharing evaluates at x + 407 over the nodes 0..406; the reconstructions at i over the nodes 256..256+n-1
+    h.px.assign(1408, 0); h.pr1.assign(256, 0); h.pr2.assign(256, 0);
     for (int x = 0; x < NX; x++) {
         uint32_t p = 1;
         for (int m = 0; m < D1; m++) p = p * (uint32_t)((x + D1 - m) % Q) % Q;
         h.px[x] = (int16_t)mont(p);
     }
-    // kernel segments and their 256-point NTTs, index k = k1 + 16 k2 stored at [k2][k1], scaled by 1/256
+    for (int i = 0; i < NL; i++) {
+        uint32_t p1 = 1, p2 = 1;
+        for (int m = 0; m < D2; m++) { const uint32_t f = (uint32_t)(((i - 256 - m) % Q + Q) % Q); p2 = p2 * f % Q; if (m < D1) p1 = p1 * f % Q; }
+        h.pr1[i] = (int16_t)mont(p1); h.pr2[i] = (int16_t)mont(p2);
+    }
+    // kernel segments K_delta[d] = c[128 delta + OFF + d], d in [-127, 127], c[m] = 1/m (0 when m = 0 mod q), and their 256-point
+    // NTTs, index k = k1 + 16 k2 stored at [k1][k2], scaled by 1/256
     std::vector<uint32_t> opw(256);
     for (int i = 0; i < 256; i++) opw[i] = pw(om, i);
     const uint32_t i256 = inv(256);
-    h.khat.assign((size_t)SN_NK * 16 * SN_LD, 0);
-    for (int dl = -(SN_NIN - 1); dl < SN_NOUT; dl++) {
-        uint32_t K[256];
-        for (int t = 0; t < 256; t++) {
-            const int d = t < 128 ? t : t - 256, mm = 128 * dl + D1 + d;
-            K[t] = (t == 128 || mm < 1 || mm >= Q) ? 0 : inv((uint32_t)mm);
+    auto segments = [&](int off, int dmin, int dmax) {
+        std::vector<int16_t> out((size_t)(dmax - dmin + 1) * 16 * SN_LD, 0);
+        for (int dl = dmin; dl <= dmax; dl++) {
+            uint32_t K[256];
+            for (int t = 0; t < 256; t++) {
+                const int d = t < 128 ? t : t - 256;
+                const int mm = ((128 * dl + off + d) % Q + Q) % Q;
+                K[t] = (t == 128 || mm == 0) ? 0 : inv((uint32_t)mm);
+            }
+            for (int k = 0; k < 256; k++) {
+                uint32_t s = 0;
+                for (int t = 0; t < 256; t++) s = (s + K[t] * opw[(t * k) & 255]) % Q;
+                out[((size_t)(dl - dmin) * 16 + (k & 15)) * SN_LD + (k >> 4)] = (int16_t)mont(s * i256 % Q);
+            }
         }
-        for (int k = 0; k < 256; k++) {
-            uint32_t s = 0;
-            for (int t = 0; t < 256; t++) s = (s + K[t] * opw[(t * k) & 255]) % Q;
-            const int k1 = k & 15, k2 = k >> 4;
-            h.khat[((size_t)(dl + SN_NIN - 1) * 16 + k1) * SN_LD + k2] = (int16_t)mont(s * i256 % Q);
-        }
-    }
+        return out;
+    };
+    h.kh_share = segments(D1, -(SN_NIN - 1), SN_NOUT - 1);
+    h.kh_m256 = segments(-256, SN_M256_DMIN, SN_M256_DMAX);
     return h;
 }
 

@@ -38,6 +38,7 @@ struct VerifyBufs {
     int k = 0, chunk = 0;
     int strict = 0;   // hardened decoding: off by default = the reference's accept set
     int raw_inst = 0; // verify() on a caller-supplied mlwe_inst (raw_api.cuh): AH / TPK are preloaded, pk is not parsed
+    int pt_mont = 0;  // P(t) tables carry the Montgomery factor 2^16 (the NTT-convolution path consumes them; the dense GEMM path does not)
 };
 
 struct VDims {
@@ -322,6 +323,7 @@ __global__ void __launch_bounds__(256) kv_lagrange(VerifyBufs vb, const u16 *__r
                 else { v = gf_mul(fact[t - 256], fact[hi - t]); if ((hi - t) & 1) v = gf_sub(0, v); }
                 v = gf_mul(v, inv[den]);
             }
+            if (vb.pt_mont) v = gf_mul(v, (1u << 16) % Q);
             (pass ? vb.PT2 + (size_t)b * 256 : vb.PT1 + (size_t)b * LM1_ROWS)[t] = (u16)v;
         }
         __syncthreads();
@@ -523,6 +525,7 @@ static int verify_chunk_t(VerifyBufs &vb, const VerifyTables &vt, int B, const u
     const VDims d = make_vdims(K);
     int nl = 0;
     const int ptiles = (NP + 127) / 128;
+    vb.pt_mont = vt.sn != nullptr;
     kv_clear<K><<<(B + 127) / 128, 128, 0, st>>>(vb, B); nl++;
     kv_setup<K><<<B, 128, 0, st>>>(vb, d_pi, d_pk); nl++;
     kv_setup_copy<K><<<dim3(SETUP_COPY_CTAS, B), 128, 0, st>>>(vb, d_pi); nl++;
@@ -537,28 +540,45 @@ static int verify_chunk_t(VerifyBufs &vb, const VerifyTables &vt, int B, const u
     kv_lagrange<<<B, 256, 0, st>>>(vb, vt.inv, vt.fact); nl++;
     kv_gather<K><<<dim3(2 * MK + d.n1rows + d.n2rows, B), 128, 0, st>>>(vb, d_pi); nl++;
     GemmArgs g{};
-    // beta/gamma reconstruction: ABG x R1
-    g = GemmArgs{}; g.ws = vb.WS; g.ws_elems = GE_WS_ELEMS; g.A = vb.ABG; g.Bt = vt.R1; g.C = vb.BS; g.lda = YLD; g.ldb = YLD; g.ldc = 256;
-    g.mtotal = B * 2 * MK; g.ksteps = YLD / GE_BK; g.nvalid = 256; g.rpp = g.mtotal; g.c_off = 0; g.half_last = 1;
-    nl += gf_gemm_launch_auto<8>(g, 256, 1, st);
+    ConvArgs cv{};
+    // beta/gamma reconstruction: ABG x R1 (recon_secrets_ddeg, ss.cpp:37-54)
+    if (vt.sn) {
+        cv = ConvArgs{}; cv.A = vb.ABG; cv.C = vb.BS; cv.lda = YLD; cv.ldc = 256; cv.mtotal = B * 2 * MK; cv.rpp = cv.mtotal; cv.nin = D1; cv.nout = 256;
+        cv.tw = vt.sn->tw; cv.khat = sn_kh_m256(*vt.sn, 4); cv.pre = vt.sn->wj; cv.post = reinterpret_cast<const u16 *>(vt.sn->pr1);
+        nl += conv_ntt_launch<4, 2>(cv, st);
+    } else {
+        g = GemmArgs{}; g.ws = vb.WS; g.ws_elems = GE_WS_ELEMS; g.A = vb.ABG; g.Bt = vt.R1; g.C = vb.BS; g.lda = YLD; g.ldb = YLD; g.ldc = 256;
+        g.mtotal = B * 2 * MK; g.ksteps = YLD / GE_BK; g.nvalid = 256; g.rpp = g.mtotal; g.c_off = 0; g.half_last = 1;
+        nl += gf_gemm_launch_auto<8>(g, 256, 1, st);
+    }
     kv_check_bg<<<dim3(MK, B), 128, 0, st>>>(vb); nl++;
-    // interpolation-apply: rows of all proofs against the fixed Cauchy operands, columns scaled by each proof's P(t)
-    g = GemmArgs{}; g.ws = vb.WS; g.ws_elems = GE_WS_ELEMS; g.A = vb.A1; g.Bt = vt.U1; g.C = vb.YV; g.lda = KP1; g.ldb = KP1; g.ldc = YLD;
-    g.mtotal = B * d.n1rows; g.ksteps = KP1 / GE_BK; g.nvalid = D1; g.rpp = d.n1rows; g.a_slots = d.n1rows; g.c_slots = d.nyrows;
-    g.colscale = vb.PT1; g.colscale_batch = LM1_ROWS; g.colscale_by_group = 1;
-    nl += gf_gemm_launch_auto<7>(g, U1_ROWS, 1, st);
-    kv_node_targets<K><<<dim3(d.n1rows, B), 160, 0, st>>>(vb, d_pi); nl++;
-    g = GemmArgs{}; g.ws = vb.WS; g.ws_elems = GE_WS_ELEMS; g.A = vb.A2; g.Bt = vt.U2; g.C = vb.UZ; g.lda = KP2; g.ldb = KP2; g.ldc = 256;
-    g.mtotal = B * d.n2rows; g.ksteps = KP2 / GE_BK; g.nvalid = 256; g.rpp = d.n2rows; g.a_slots = d.n2rows; g.c_slots = d.n2rows;
-    g.colscale = vb.PT2; g.colscale_batch = 256; g.colscale_by_group = 1;
-    nl += gf_gemm_launch_auto<8>(g, 256, 1, st);
+    // interpolation-apply: rows of all proofs against the fixed Cauchy operand 1 / (t - (p + 256)), columns scaled by each proof's P(t)
+    if (vt.sn) {
+        cv = ConvArgs{}; cv.A = vb.A1; cv.C = vb.YV; cv.lda = KP1; cv.ldc = YLD; cv.mtotal = B * d.n1rows; cv.rpp = d.n1rows; cv.a_slots = d.n1rows; cv.c_slots = d.nyrows;
+        cv.nin = KP1; cv.nout = D1; cv.tw = vt.sn->tw; cv.khat = sn_kh_m256(*vt.sn, 5); cv.post = vb.PT1; cv.post_group = LM1_ROWS;
+        nl += conv_ntt_launch<5, 4>(cv, st);
+        kv_node_targets<K><<<dim3(d.n1rows, B), 160, 0, st>>>(vb, d_pi); nl++;
+        cv = ConvArgs{}; cv.A = vb.A2; cv.C = vb.UZ; cv.lda = KP2; cv.ldc = 256; cv.mtotal = B * d.n2rows; cv.rpp = d.n2rows; cv.a_slots = d.n2rows; cv.c_slots = d.n2rows;
+        cv.nin = KP2; cv.nout = 256; cv.tw = vt.sn->tw; cv.khat = sn_kh_m256(*vt.sn, 8); cv.post = vb.PT2; cv.post_group = 256;
+        nl += conv_ntt_launch<8, 2>(cv, st);
+    } else {
+        g = GemmArgs{}; g.ws = vb.WS; g.ws_elems = GE_WS_ELEMS; g.A = vb.A1; g.Bt = vt.U1; g.C = vb.YV; g.lda = KP1; g.ldb = KP1; g.ldc = YLD;
+        g.mtotal = B * d.n1rows; g.ksteps = KP1 / GE_BK; g.nvalid = D1; g.rpp = d.n1rows; g.a_slots = d.n1rows; g.c_slots = d.nyrows;
+        g.colscale = vb.PT1; g.colscale_batch = LM1_ROWS; g.colscale_by_group = 1;
+        nl += gf_gemm_launch_auto<7>(g, U1_ROWS, 1, st);
+        kv_node_targets<K><<<dim3(d.n1rows, B), 160, 0, st>>>(vb, d_pi); nl++;
+        g = GemmArgs{}; g.ws = vb.WS; g.ws_elems = GE_WS_ELEMS; g.A = vb.A2; g.Bt = vt.U2; g.C = vb.UZ; g.lda = KP2; g.ldb = KP2; g.ldc = 256;
+        g.mtotal = B * d.n2rows; g.ksteps = KP2 / GE_BK; g.nvalid = 256; g.rpp = d.n2rows; g.a_slots = d.n2rows; g.c_slots = d.n2rows;
+        g.colscale = vb.PT2; g.colscale_batch = 256; g.colscale_by_group = 1;
+        nl += gf_gemm_launch_auto<8>(g, 256, 1, st);
+    }
     kv_open<K><<<B, 128, 0, st>>>(vb); nl++;
     // regenerate every sharing at all 1454 parties: YV x S.  Row groups per proof: [0,3K) s+r, e+r, t | [3K, n1rows) the eta
     // sharings, whose 256 secrets were just checked to be one constant (short path: tail terms only) | [n1rows, nyrows)
     if (vt.sn) {
         g = GemmArgs{}; g.A = vb.YV; g.C = vb.VSH; g.lda = YLD; g.ldc = SLD; g.rpp = d.nyrows; g.slot_lo = 0; g.a_slots = d.nyrows; g.c_slots = d.nyrows;
         g.mtotal = B * d.nyrows; g.c_off = SOFF + NT + 1; g.tail = 1; g.tail_off = NL;
-        k_share_ntt<<<std::min((g.mtotal + SN_WARPS - 1) / SN_WARPS, 148 * 8), 32 * SN_WARPS, 0, st>>>(g, *vt.sn); nl++;
+        nl += conv_ntt_launch<SN_NIN, SN_NOUT>(share_conv_args(g, *vt.sn), st);
     } else {
         const int grp_lo[3] = {0, 3 * K, d.n1rows}, grp_hi[3] = {3 * K, d.n1rows, d.nyrows};
         for (int gi = 0; gi < 3; gi++) {
@@ -571,9 +591,15 @@ static int verify_chunk_t(VerifyBufs &vb, const VerifyTables &vt, int B, const u
         }
     }
     kv_check_parties<K><<<dim3(ptiles, B), 128, 0, st>>>(vb, d_pi); nl++;
-    g = GemmArgs{}; g.ws = vb.WS; g.ws_elems = GE_WS_ELEMS; g.A = vb.U2; g.Bt = vt.R2; g.C = vb.UR; g.lda = VR2LD; g.ldb = VR2LD; g.ldc = 256;
-    g.mtotal = B * d.n2rows; g.ksteps = VR2LD / GE_BK; g.nvalid = 256; g.rpp = g.mtotal;
-    nl += gf_gemm_launch_auto<8>(g, 256, 1, st);
+    if (vt.sn) {      // recon_secrets_2ddeg over parties 0..812 (ss.cpp:56-73)
+        cv = ConvArgs{}; cv.A = vb.U2; cv.C = vb.UR; cv.lda = VR2LD; cv.ldc = 256; cv.mtotal = B * d.n2rows; cv.rpp = cv.mtotal; cv.nin = D2; cv.nout = 256;
+        cv.tw = vt.sn->tw; cv.khat = sn_kh_m256(*vt.sn, 7); cv.pre = vt.sn->wj2; cv.post = reinterpret_cast<const u16 *>(vt.sn->pr2);
+        nl += conv_ntt_launch<7, 2>(cv, st);
+    } else {
+        g = GemmArgs{}; g.ws = vb.WS; g.ws_elems = GE_WS_ELEMS; g.A = vb.U2; g.Bt = vt.R2; g.C = vb.UR; g.lda = VR2LD; g.ldb = VR2LD; g.ldc = 256;
+        g.mtotal = B * d.n2rows; g.ksteps = VR2LD / GE_BK; g.nvalid = 256; g.rpp = g.mtotal;
+        nl += gf_gemm_launch_auto<8>(g, 256, 1, st);
+    }
     {   // V16: view hashes of the opened parties, FS-2, compare
         constexpr int ETA = (K == 2) ? 3 : 2, NV = 16 + 2 * (K + MK + 2 * K + 1) + 4 * K + 8 * ETA * K;
         HashSrc hs{vb.VR, (long long)NT * d.vrld, d.vrld, 1, 0, nullptr, vb.I, NT};
