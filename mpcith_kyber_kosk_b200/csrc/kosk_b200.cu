@@ -329,7 +329,7 @@ static void launch_share_eval(kosk_b200_ctx *c, const u16 *Y, u16 *SH, int slot_
     g.mtotal = B * rows; g.ksteps = YLD / GE_BK; g.nvalid = NX; g.c_off = SOFF + NT + 1;
     g.rpp = rows; g.slot_lo = slot_lo; g.a_slots = y_slots; g.c_slots = sh_slots; g.tail = 1; g.tail_off = NL;
     if (c->use_ntt && !(c->use_tensor && YL0)) {      // one warp per sharing; constant-secret rows need no special case here
-        c->launches += conv_ntt_launch<SN_NIN, SN_NOUT>(share_conv_args(g, c->sn), st);
+        c->launches += share_ntt_launch(share_conv_args(g, c->sn), st);
         return;
     }
     const int koff = const_secret ? NL : 0;

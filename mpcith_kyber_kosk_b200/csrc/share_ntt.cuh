@@ -36,7 +36,6 @@ __constant__ int32_t c_sn_w16f[256], c_sn_w16i[256];   // w16^(+-a k) * R, cente
 struct ConvArgs {
     const u16 *A; u16 *C; long long lda, ldc;
     int mtotal, rpp, slot_lo, a_slots, c_slots, c_off;   // row m -> storage row (m / rpp) * slots + slot_lo + m % rpp
-    int nin, nout;
     int tail, tail_off;                                  // sharing: copy the 151 tail values to parties 0..150
     const int16_t *tw;       // [2][16][16]  17^(+-b k1) * R (symmetric in b, k1)
     const int16_t *khat;     // [NIN + NOUT - 1][16 k1][SN_LD]  NTT(K_delta)[k1 + 16 k2] / 256 * R at [k1][k2], delta = o - i
@@ -51,7 +50,9 @@ __device__ __forceinline__ int32_t sn_montred(int32_t a)            // a * 2^-16
     return (a - t * Q) >> 16;
 }
 
-template <int NIN, int NOUT>
+// NINV / NOUTV = valid inputs / outputs, PRE = input factors present, PGROUP = per-row-group output factors: compile-time, so that
+// the sharing's kernel carries none of the other products' branches
+template <int NIN, int NOUT, int NINV, int NOUTV, bool PRE, bool PGROUP>
 __global__ void __launch_bounds__(32 * SN_WARPS, (NIN <= 5 ? 4 : 3)) k_conv_ntt(const ConvArgs g)
 {
     constexpr int NK = NIN + NOUT - 1, NINP = (NIN + 1) & ~1;
@@ -70,7 +71,7 @@ __global__ void __launch_bounds__(32 * SN_WARPS, (NIN <= 5 ? 4 : 3)) k_conv_ntt(
     for (int m = blockIdx.x * SN_WARPS + wid; m < g.mtotal; m += gridDim.x * SN_WARPS) {
         const u16 *yrow = g.A + ((size_t)(m / g.rpp) * g.a_slots + g.slot_lo + m % g.rpp) * g.lda;
         u16 *dst = g.C + ((size_t)(m / g.rpp) * g.c_slots + g.slot_lo + m % g.rpp) * g.ldc + g.c_off;
-        const u16 *post = g.post + (g.post_group ? (size_t)(m / g.rpp) * g.post_group : 0);
+        const u16 *post = g.post + (PGROUP ? (size_t)(m / g.rpp) * g.post_group : 0);
         if (g.tail) for (int t = lane; t <= NT; t += 32) dst[t - (NT + 1)] = yrow[g.tail_off + t];
         // ---- forward: u_j = pre_j A_j, NTT of the zero-padded 128-wide input blocks (two per pass) ----
 #pragma unroll 1
@@ -81,7 +82,7 @@ __global__ void __launch_bounds__(32 * SN_WARPS, (NIN <= 5 ? 4 : 3)) k_conv_ntt(
             for (int a = 0; a < 8; a++) {
                 const int j = 128 * blk + 16 * a + c;
                 int32_t v = 0;
-                if (j < g.nin) v = g.pre ? sn_montred((int32_t)yrow[j] * (int32_t)__ldg(g.pre + j)) : (int32_t)yrow[j];
+                if (j < NINV) v = PRE ? sn_montred((int32_t)yrow[j] * (int32_t)__ldg(g.pre + j)) : (int32_t)yrow[j];
                 x[a] = v;
             }
             int32_t y[16];
@@ -168,8 +169,8 @@ __global__ void __launch_bounds__(32 * SN_WARPS, (NIN <= 5 ? 4 : 3)) k_conv_ntt(
 #pragma unroll
                 for (int k = 0; k < 16; k++) acc += in[k] * c_sn_w16i[k * 16 + a];
                 const int xo = 128 * o + 16 * a + c;
-                if (live && xo < g.nout) {
-                    const int32_t pf = g.post_group ? (int32_t)post[xo] : (int32_t)(int16_t)__ldg(post + xo);
+                if (live && xo < NOUTV) {
+                    const int32_t pf = PGROUP ? (int32_t)post[xo] : (int32_t)(int16_t)__ldg(post + xo);
                     int32_t r = sn_montred(sn_montred(acc) * pf);
                     dst[xo] = (u16)(r < 0 ? r + Q : r);
                 }
@@ -179,13 +180,14 @@ __global__ void __launch_bounds__(32 * SN_WARPS, (NIN <= 5 ? 4 : 3)) k_conv_ntt(
     }
 }
 
-template <int NIN, int NOUT>
+template <int NIN, int NOUT, int NINV, int NOUTV, bool PRE, bool PGROUP>
 static inline int conv_ntt_launch(const ConvArgs &g, cudaStream_t st)
 {
     const int ctas = std::min((g.mtotal + SN_WARPS - 1) / SN_WARPS, 148 * 8);
-    if (ctas > 0) k_conv_ntt<NIN, NOUT><<<ctas, 32 * SN_WARPS, 0, st>>>(g);
+    if (ctas > 0) k_conv_ntt<NIN, NOUT, NINV, NOUTV, PRE, PGROUP><<<ctas, 32 * SN_WARPS, 0, st>>>(g);
     return 1;
 }
+static inline int share_ntt_launch(const ConvArgs &g, cudaStream_t st) { return conv_ntt_launch<SN_NIN, SN_NOUT, D1, NX, true, false>(g, st); }
 
 // device tables of all Toeplitz products of the KOSK path (one allocation per context)
 struct ShareNttTables {
@@ -204,7 +206,7 @@ static inline ConvArgs share_conv_args(const GemmArgs &g, const ShareNttTables &
 {
     ConvArgs a{};
     a.A = g.A; a.C = g.C; a.lda = g.lda; a.ldc = g.ldc; a.mtotal = g.mtotal; a.rpp = g.rpp; a.slot_lo = g.slot_lo; a.a_slots = g.a_slots; a.c_slots = g.c_slots;
-    a.c_off = g.c_off; a.nin = D1; a.nout = NX; a.tail = g.tail; a.tail_off = g.tail_off;
+    a.c_off = g.c_off; a.tail = g.tail; a.tail_off = g.tail_off;
     a.tw = t.tw; a.khat = t.kh_share; a.pre = t.wj; a.post = reinterpret_cast<const u16 *>(t.px); a.post_group = 0;
     return a;
 }
