@@ -67,6 +67,7 @@ struct Lane {
     ProveBufs pb{};
     u8 *d_seeds = nullptr, *d_pk = nullptr, *d_sk = nullptr, *d_pi = nullptr, *d_ok = nullptr;   // staging of the host-buffer API
     VerifyBufs vb{};
+    VerifySide vside{};                     // second stream of the verifier (challenge-independent chain), KOSK_B200_VERIFY_SIDE=0 disables it
     std::vector<cudaEvent_t> ev; int ev_used = 0;
     std::vector<std::pair<int, int>> ev_phase;     // (phase id, event index of its start); end = next event
 };
@@ -162,6 +163,9 @@ static void ctx_free(kosk_b200_ctx *c)
         if (ln.done) cudaEventDestroy(ln.done);
         if (ln.computed) cudaEventDestroy(ln.computed);
         if (ln.pre_tail) cudaEventDestroy(ln.pre_tail);
+        if (ln.vside.fork) cudaEventDestroy(ln.vside.fork);
+        if (ln.vside.join) cudaEventDestroy(ln.vside.join);
+        if (ln.vside.st) cudaStreamDestroy(ln.vside.st);
         if (ln.st) cudaStreamDestroy(ln.st);
     }
     if (c->ev_start) cudaEventDestroy(c->ev_start);
@@ -295,6 +299,12 @@ int kosk_b200_create_ex(kosk_b200_ctx **out, int k, int device, int max_chunk, i
         CU(cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&ln.computed, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&ln.pre_tail, cudaEventDisableTiming));
+        { const char *e = getenv("KOSK_B200_VERIFY_SIDE");
+          if (!e || atoi(e)) {
+              CU(cudaStreamCreateWithFlags(&ln.vside.st, cudaStreamNonBlocking));
+              CU(cudaEventCreateWithFlags(&ln.vside.fork, cudaEventDisableTiming));
+              CU(cudaEventCreateWithFlags(&ln.vside.join, cudaEventDisableTiming));
+          } }
     }
     CU(cudaEventCreate(&c->ev_start));
     CU(cudaDeviceSynchronize());
@@ -455,7 +465,7 @@ static int verify_chunk_lane(kosk_b200_ctx *c, Lane &ln, int B, const u8 *d_pi, 
     VerifyTables vt{c->d_St, c->d_R1, c->d_R2, c->d_inv, c->d_SU, c->d_fact, c->d_U1, c->d_U2, c->use_ntt ? &c->sn : nullptr};
     if (c->last_computed && c->last_computed != ln.computed) CU(cudaStreamWaitEvent(ln.st, c->last_computed, 0));
     prof_mark(c, ln, KOSK_PH_VERIFY);
-    int nl = verify_chunk(c->k, ln.vb, vt, B, d_pi, d_pk, d_ok, ln.st);
+    int nl = verify_chunk(c->k, ln.vb, vt, B, d_pi, d_pk, d_ok, ln.st, ln.vside);
     prof_mark(c, ln, -1);
     CU(cudaEventRecord(ln.computed, ln.st)); c->last_computed = c->last_gate = ln.computed;
     if (nl < 0) return fail(KOSK_E_CUDA, "verify launch failed");

@@ -211,11 +211,11 @@ __global__ void __launch_bounds__(320) kv_eval_opened(VerifyBufs vb)
 //   A1 [row][j]    j<407: sr, er, t, s_eta, e_eta shares of rest party j, times the barycentric weight w_j  (:178-186, :320-324, :390-395)
 //   A2 [row][j]    j<813: u_s, u_e shares of rest party j, times w_j  (:503-508)
 template <int K>
-__global__ void __launch_bounds__(128) kv_gather(VerifyBufs vb, const u8 *__restrict__ pis)
+__global__ void __launch_bounds__(128) kv_gather(VerifyBufs vb, const u8 *__restrict__ pis, int row0)
 {
     const Layout L = make_layout(K);
     const VDims d = make_vdims(K);
-    const int b = blockIdx.y, row = blockIdx.x, tid = threadIdx.x;
+    const int b = blockIdx.y, row = blockIdx.x + row0, tid = threadIdx.x;
     const u8 *pi = pis + L.proof_bytes * (size_t)b;
     if (row < 2 * MK) {
         const int j = row >> 1, w = row & 1;
@@ -519,8 +519,12 @@ template <int K> __global__ void kv_clear(VerifyBufs vb, int B)
 }
 
 // launch sequence; returns the number of kernels launched or -1
+// Side stream: everything that does not depend on the FS-1 challenges (Lagrange weights, the interpolations, the checks on the
+// interpolated secrets, the regeneration of the sharings) runs on `side` next to commit hashes -> FS-1 sponge (one latency-bound warp per
+// proof) -> opened-party evaluation -> beta/gamma reconstruction on the main stream; the two join before the per-party checks.
+struct VerifySide { cudaStream_t st = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
 template <int K>
-static int verify_chunk_t(VerifyBufs &vb, const VerifyTables &vt, int B, const u8 *d_pi, const u8 *d_pk, u8 *d_ok, cudaStream_t st)
+static int verify_chunk_t(VerifyBufs &vb, const VerifyTables &vt, int B, const u8 *d_pi, const u8 *d_pk, u8 *d_ok, cudaStream_t st, const VerifySide &sd)
 {
     const VDims d = make_vdims(K);
     int nl = 0;
@@ -530,17 +534,64 @@ static int verify_chunk_t(VerifyBufs &vb, const VerifyTables &vt, int B, const u
     kv_setup<K><<<B, 128, 0, st>>>(vb, d_pi, d_pk); nl++;
     kv_setup_copy<K><<<dim3(SETUP_COPY_CTAS, B), 128, 0, st>>>(vb, d_pi); nl++;
     if (vb.strict) { kv_strict_scan<K><<<dim3((unsigned)((make_layout(K).proof_bytes / 2 + 255) / 256), B), 256, 0, st>>>(vb, d_pi); nl++; }
-    {   // V2: commitments of the opened parties
+    // the NTT-convolution path has no shared scratch between the two chains (the dense GEMMs share the split-K workspace)
+    const bool fork = sd.st != nullptr && vt.sn != nullptr;
+    cudaStream_t s2 = fork ? sd.st : st;
+    if (fork) { cudaEventRecord(sd.fork, st); cudaStreamWaitEvent(s2, sd.fork, 0); }
+    GemmArgs g{};
+    ConvArgs cv{};
+    // ---- main chain: V2 commitments of the opened parties, FS-1, opened-party evaluation, beta/gamma reconstruction ----
+    {
         constexpr int NC = 2 * (K + MK + 2 * K + 1);
         HashSrc hs{vb.CR, (long long)NT * d.crld, d.crld, 1, 0, nullptr, vb.I, NT};
         k_hash_records<NC><<<dim3(2, B), 128, 0, st>>>(hs, vb.TCR, nullptr, 0, 0); nl++;
     }
     k_fs1<K><<<(B + 3) / 4, 128, 0, st>>>(vb.TCR, vb.PW, B); nl++;
     kv_eval_opened<K><<<B, 320, 0, st>>>(vb); nl++;
-    kv_lagrange<<<B, 256, 0, st>>>(vb, vt.inv, vt.fact); nl++;
-    kv_gather<K><<<dim3(2 * MK + d.n1rows + d.n2rows, B), 128, 0, st>>>(vb, d_pi); nl++;
-    GemmArgs g{};
-    ConvArgs cv{};
+    // ---- side chain (independent of the challenges) ----
+    kv_lagrange<<<B, 256, 0, s2>>>(vb, vt.inv, vt.fact); nl++;
+    kv_gather<K><<<dim3(d.n1rows + d.n2rows, B), 128, 0, s2>>>(vb, d_pi, 2 * MK); nl++;
+    // interpolation-apply: rows of all proofs against the fixed Cauchy operand 1 / (t - (p + 256)), columns scaled by each proof's P(t)
+    if (vt.sn) {
+        cv = ConvArgs{}; cv.A = vb.A1; cv.C = vb.YV; cv.lda = KP1; cv.ldc = YLD; cv.mtotal = B * d.n1rows; cv.rpp = d.n1rows; cv.a_slots = d.n1rows; cv.c_slots = d.nyrows;
+        cv.tw = vt.sn->tw; cv.khat = sn_kh_m256(*vt.sn, 5); cv.post = vb.PT1; cv.post_group = LM1_ROWS;
+        nl += conv_ntt_launch<5, 4, KP1, D1, false, true>(cv, s2);
+        kv_node_targets<K><<<dim3(d.n1rows, B), 160, 0, s2>>>(vb, d_pi); nl++;
+        cv = ConvArgs{}; cv.A = vb.A2; cv.C = vb.UZ; cv.lda = KP2; cv.ldc = 256; cv.mtotal = B * d.n2rows; cv.rpp = d.n2rows; cv.a_slots = d.n2rows; cv.c_slots = d.n2rows;
+        cv.tw = vt.sn->tw; cv.khat = sn_kh_m256(*vt.sn, 8); cv.post = vb.PT2; cv.post_group = 256;
+        nl += conv_ntt_launch<8, 2, KP2, 256, false, true>(cv, s2);
+    } else {
+        g = GemmArgs{}; g.ws = vb.WS; g.ws_elems = GE_WS_ELEMS; g.A = vb.A1; g.Bt = vt.U1; g.C = vb.YV; g.lda = KP1; g.ldb = KP1; g.ldc = YLD;
+        g.mtotal = B * d.n1rows; g.ksteps = KP1 / GE_BK; g.nvalid = D1; g.rpp = d.n1rows; g.a_slots = d.n1rows; g.c_slots = d.nyrows;
+        g.colscale = vb.PT1; g.colscale_batch = LM1_ROWS; g.colscale_by_group = 1;
+        nl += gf_gemm_launch_auto<7>(g, U1_ROWS, 1, s2);
+        kv_node_targets<K><<<dim3(d.n1rows, B), 160, 0, s2>>>(vb, d_pi); nl++;
+        g = GemmArgs{}; g.ws = vb.WS; g.ws_elems = GE_WS_ELEMS; g.A = vb.A2; g.Bt = vt.U2; g.C = vb.UZ; g.lda = KP2; g.ldb = KP2; g.ldc = 256;
+        g.mtotal = B * d.n2rows; g.ksteps = KP2 / GE_BK; g.nvalid = 256; g.rpp = d.n2rows; g.a_slots = d.n2rows; g.c_slots = d.n2rows;
+        g.colscale = vb.PT2; g.colscale_batch = 256; g.colscale_by_group = 1;
+        nl += gf_gemm_launch_auto<8>(g, 256, 1, s2);
+    }
+    kv_open<K><<<B, 128, 0, s2>>>(vb); nl++;
+    // regenerate every sharing at all 1454 parties: YV x S.  Row groups per proof: [0,3K) s+r, e+r, t | [3K, n1rows) the eta
+    // sharings, whose 256 secrets were just checked to be one constant (short path: tail terms only) | [n1rows, nyrows)
+    if (vt.sn) {
+        g = GemmArgs{}; g.A = vb.YV; g.C = vb.VSH; g.lda = YLD; g.ldc = SLD; g.rpp = d.nyrows; g.slot_lo = 0; g.a_slots = d.nyrows; g.c_slots = d.nyrows;
+        g.mtotal = B * d.nyrows; g.c_off = SOFF + NT + 1; g.tail = 1; g.tail_off = NL;
+        nl += share_ntt_launch(share_conv_args(g, *vt.sn), s2);
+    } else {
+        const int grp_lo[3] = {0, 3 * K, d.n1rows}, grp_hi[3] = {3 * K, d.n1rows, d.nyrows};
+        for (int gi = 0; gi < 3; gi++) {
+            g = GemmArgs{}; g.ws = vb.WS; g.ws_elems = GE_WS_ELEMS; g.A = vb.YV; g.Bt = vt.St; g.C = vb.VSH; g.lda = YLD; g.ldb = YLD; g.ldc = SLD;
+            g.rpp = grp_hi[gi] - grp_lo[gi]; g.slot_lo = grp_lo[gi]; g.a_slots = d.nyrows; g.c_slots = d.nyrows;
+            g.mtotal = B * g.rpp; g.ksteps = YLD / GE_BK; g.nvalid = NX; g.c_off = SOFF + NT + 1; g.tail = 1; g.tail_off = NL;
+            if (gi == 1) { g.A = vb.YV + NL; g.Bt = vt.St + NL; g.ksteps = (YLD - NL) / GE_BK; g.tail_off = 0; g.addvec = vt.SU; g.scale_src = vb.YV; }
+            g.half_last = 1;
+            nl += gf_gemm_launch_auto<7>(g, GE_NCOLS7, 1, s2);
+        }
+    }
+    if (fork) cudaEventRecord(sd.join, s2);
+    // ---- main chain, continued: beta/gamma of parties 0..406 (rest: from the proof, opened: just evaluated), reconstruction, NTT check ----
+    kv_gather<K><<<dim3(2 * MK, B), 128, 0, st>>>(vb, d_pi, 0); nl++;
     // beta/gamma reconstruction: ABG x R1 (recon_secrets_ddeg, ss.cpp:37-54)
     if (vt.sn) {
         cv = ConvArgs{}; cv.A = vb.ABG; cv.C = vb.BS; cv.lda = YLD; cv.ldc = 256; cv.mtotal = B * 2 * MK; cv.rpp = cv.mtotal;
@@ -552,44 +603,7 @@ static int verify_chunk_t(VerifyBufs &vb, const VerifyTables &vt, int B, const u
         nl += gf_gemm_launch_auto<8>(g, 256, 1, st);
     }
     kv_check_bg<<<dim3(MK, B), 128, 0, st>>>(vb); nl++;
-    // interpolation-apply: rows of all proofs against the fixed Cauchy operand 1 / (t - (p + 256)), columns scaled by each proof's P(t)
-    if (vt.sn) {
-        cv = ConvArgs{}; cv.A = vb.A1; cv.C = vb.YV; cv.lda = KP1; cv.ldc = YLD; cv.mtotal = B * d.n1rows; cv.rpp = d.n1rows; cv.a_slots = d.n1rows; cv.c_slots = d.nyrows;
-        cv.tw = vt.sn->tw; cv.khat = sn_kh_m256(*vt.sn, 5); cv.post = vb.PT1; cv.post_group = LM1_ROWS;
-        nl += conv_ntt_launch<5, 4, KP1, D1, false, true>(cv, st);
-        kv_node_targets<K><<<dim3(d.n1rows, B), 160, 0, st>>>(vb, d_pi); nl++;
-        cv = ConvArgs{}; cv.A = vb.A2; cv.C = vb.UZ; cv.lda = KP2; cv.ldc = 256; cv.mtotal = B * d.n2rows; cv.rpp = d.n2rows; cv.a_slots = d.n2rows; cv.c_slots = d.n2rows;
-        cv.tw = vt.sn->tw; cv.khat = sn_kh_m256(*vt.sn, 8); cv.post = vb.PT2; cv.post_group = 256;
-        nl += conv_ntt_launch<8, 2, KP2, 256, false, true>(cv, st);
-    } else {
-        g = GemmArgs{}; g.ws = vb.WS; g.ws_elems = GE_WS_ELEMS; g.A = vb.A1; g.Bt = vt.U1; g.C = vb.YV; g.lda = KP1; g.ldb = KP1; g.ldc = YLD;
-        g.mtotal = B * d.n1rows; g.ksteps = KP1 / GE_BK; g.nvalid = D1; g.rpp = d.n1rows; g.a_slots = d.n1rows; g.c_slots = d.nyrows;
-        g.colscale = vb.PT1; g.colscale_batch = LM1_ROWS; g.colscale_by_group = 1;
-        nl += gf_gemm_launch_auto<7>(g, U1_ROWS, 1, st);
-        kv_node_targets<K><<<dim3(d.n1rows, B), 160, 0, st>>>(vb, d_pi); nl++;
-        g = GemmArgs{}; g.ws = vb.WS; g.ws_elems = GE_WS_ELEMS; g.A = vb.A2; g.Bt = vt.U2; g.C = vb.UZ; g.lda = KP2; g.ldb = KP2; g.ldc = 256;
-        g.mtotal = B * d.n2rows; g.ksteps = KP2 / GE_BK; g.nvalid = 256; g.rpp = d.n2rows; g.a_slots = d.n2rows; g.c_slots = d.n2rows;
-        g.colscale = vb.PT2; g.colscale_batch = 256; g.colscale_by_group = 1;
-        nl += gf_gemm_launch_auto<8>(g, 256, 1, st);
-    }
-    kv_open<K><<<B, 128, 0, st>>>(vb); nl++;
-    // regenerate every sharing at all 1454 parties: YV x S.  Row groups per proof: [0,3K) s+r, e+r, t | [3K, n1rows) the eta
-    // sharings, whose 256 secrets were just checked to be one constant (short path: tail terms only) | [n1rows, nyrows)
-    if (vt.sn) {
-        g = GemmArgs{}; g.A = vb.YV; g.C = vb.VSH; g.lda = YLD; g.ldc = SLD; g.rpp = d.nyrows; g.slot_lo = 0; g.a_slots = d.nyrows; g.c_slots = d.nyrows;
-        g.mtotal = B * d.nyrows; g.c_off = SOFF + NT + 1; g.tail = 1; g.tail_off = NL;
-        nl += share_ntt_launch(share_conv_args(g, *vt.sn), st);
-    } else {
-        const int grp_lo[3] = {0, 3 * K, d.n1rows}, grp_hi[3] = {3 * K, d.n1rows, d.nyrows};
-        for (int gi = 0; gi < 3; gi++) {
-            g = GemmArgs{}; g.ws = vb.WS; g.ws_elems = GE_WS_ELEMS; g.A = vb.YV; g.Bt = vt.St; g.C = vb.VSH; g.lda = YLD; g.ldb = YLD; g.ldc = SLD;
-            g.rpp = grp_hi[gi] - grp_lo[gi]; g.slot_lo = grp_lo[gi]; g.a_slots = d.nyrows; g.c_slots = d.nyrows;
-            g.mtotal = B * g.rpp; g.ksteps = YLD / GE_BK; g.nvalid = NX; g.c_off = SOFF + NT + 1; g.tail = 1; g.tail_off = NL;
-            if (gi == 1) { g.A = vb.YV + NL; g.Bt = vt.St + NL; g.ksteps = (YLD - NL) / GE_BK; g.tail_off = 0; g.addvec = vt.SU; g.scale_src = vb.YV; }
-            g.half_last = 1;
-            nl += gf_gemm_launch_auto<7>(g, GE_NCOLS7, 1, st);
-        }
-    }
+    if (fork) cudaStreamWaitEvent(st, sd.join, 0);
     kv_check_parties<K><<<dim3(ptiles, B), 128, 0, st>>>(vb, d_pi); nl++;
     if (vt.sn) {      // recon_secrets_2ddeg over parties 0..812 (ss.cpp:56-73)
         cv = ConvArgs{}; cv.A = vb.U2; cv.C = vb.UR; cv.lda = VR2LD; cv.ldc = 256; cv.mtotal = B * d.n2rows; cv.rpp = cv.mtotal;
@@ -610,12 +624,12 @@ static int verify_chunk_t(VerifyBufs &vb, const VerifyTables &vt, int B, const u
     return cudaGetLastError() == cudaSuccess ? nl : -1;
 }
 
-static inline int verify_chunk(int k, VerifyBufs &vb, const VerifyTables &vt, int B, const u8 *d_pi, const u8 *d_pk, u8 *d_ok, cudaStream_t st)
+static inline int verify_chunk(int k, VerifyBufs &vb, const VerifyTables &vt, int B, const u8 *d_pi, const u8 *d_pk, u8 *d_ok, cudaStream_t st, const VerifySide &sd)
 {
     switch (k) {
-    case 2: return verify_chunk_t<2>(vb, vt, B, d_pi, d_pk, d_ok, st);
-    case 3: return verify_chunk_t<3>(vb, vt, B, d_pi, d_pk, d_ok, st);
-    default: return verify_chunk_t<4>(vb, vt, B, d_pi, d_pk, d_ok, st);
+    case 2: return verify_chunk_t<2>(vb, vt, B, d_pi, d_pk, d_ok, st, sd);
+    case 3: return verify_chunk_t<3>(vb, vt, B, d_pi, d_pk, d_ok, st, sd);
+    default: return verify_chunk_t<4>(vb, vt, B, d_pi, d_pk, d_ok, st, sd);
     }
 }
 
