@@ -78,6 +78,7 @@ struct kosk_b200_ctx {
     size_t next_lane = 0;
     cudaEvent_t last_computed = nullptr;   // compute-done event of the most recently enqueued sub-batch (any lane)
     cudaEvent_t last_gate = nullptr;       // event the next prove sub-batch waits for: last_computed, or the previous sub-batch's pre_tail
+    int overlap_fs1 = 0;                   // KOSK_B200_OVERLAP_FS1=1: eta / z_j sharings on the lane's side stream next to commit hashes + FS-1 (measured: a loss, off)
     int overlap_tail = 1;                  // KOSK_B200_OVERLAP_TAIL: let a sub-batch start while the previous one runs FS-2 + assembly
     int use_ntt = 1;                       // KOSK_B200_SHARE_NTT: share evaluation as a blocked NTT convolution (share_ntt.cuh) instead of the dense table GEMM
     int16_t *d_sn = nullptr;               // its tables (ShareNttTables), one allocation
@@ -207,6 +208,7 @@ int kosk_b200_create_ex(kosk_b200_ctx **out, int k, int device, int max_chunk, i
     { const char *e = getenv("KOSK_B200_FUSE_FS"); if (e) c->fuse_fs = atoi(e); }
     { const char *e = getenv("KOSK_B200_FUSE_MAX"); if (e) c->fuse_max = atoi(e); }
     { const char *e = getenv("KOSK_B200_OVERLAP_TAIL"); if (e) c->overlap_tail = atoi(e); }
+    { const char *e = getenv("KOSK_B200_OVERLAP_FS1"); if (e) c->overlap_fs1 = atoi(e); }
     { const char *e = getenv("KOSK_B200_SHARE_NTT"); if (e) c->use_ntt = atoi(e); }
     if (c->use_tensor) c->use_ntt = 0;
     const Slots &sl = c->sl; const Layout &L = c->L;
@@ -406,7 +408,19 @@ static int prove_chunk(kosk_b200_ctx *c, Lane &ln, const ProveBufs &bufs, int B,
     // first share evaluation: slots [0, s0) (f, NTT_f, eta constants) are key-independent, [s0, n1) (s, e, z_j) are not
     const int lo = off ? 0 : sl.s0, hi = on ? sl.n1 : sl.s0;
     prof_mark(c, ln, KOSK_PH_SHARE1);
-    launch_share_eval_prove(c, pb, lo, hi, B, st);
+    // The commitments hash only the s, e, f and NTT_f sharings (mlwe_prover.cpp:117-126): when a whole kyber_verifiable_keygen runs here, the
+    // eta-constant and z_j sharings (52 of 206 per proof) are evaluated on the lane's side stream, next to commit hashes -> FS-1 sponge
+    // (one latency-bound warp per proof) -> eval -> open, and joined before k_derive reads them.  Opt-in (KOSK_B200_OVERLAP_FS1=1): measured
+    // 107.7 k vs 110.6 k proofs/s -- next to the convolution kernel the sponge slows more than the 0.57 ms of share evaluation it hides.
+    const bool side = c->overlap_fs1 && off && on && c->use_ntt && !c->use_tensor && ln.vside.st != nullptr;
+    if (side) {
+        CU(cudaEventRecord(ln.vside.fork, st)); CU(cudaStreamWaitEvent(ln.vside.st, ln.vside.fork, 0));
+        launch_share_eval(c, pb.Y, pb.SH, sl.f0, sl.seta0 - sl.f0, sl.n2, sl.nslot, B, st, false, nullptr, nullptr, pb.WS);
+        launch_share_eval(c, pb.Y, pb.SH, sl.s0, sl.zs0 - sl.s0, sl.n2, sl.nslot, B, st, false, nullptr, nullptr, pb.WS);
+        launch_share_eval(c, pb.Y, pb.SH, sl.seta0, sl.s0 - sl.seta0, sl.n2, sl.nslot, B, ln.vside.st, false, nullptr, nullptr, pb.WS);
+        launch_share_eval(c, pb.Y, pb.SH, sl.zs0, sl.n1 - sl.zs0, sl.n2, sl.nslot, B, ln.vside.st, false, nullptr, nullptr, pb.WS);
+        CU(cudaEventRecord(ln.vside.join, ln.vside.st));
+    } else launch_share_eval_prove(c, pb, lo, hi, B, st);
     if (!on) { prof_mark(c, ln, -1); CU(cudaEventRecord(ln.computed, st)); c->last_computed = c->last_gate = ln.computed; CU(cudaGetLastError()); return KOSK_OK; }
     prof_mark(c, ln, KOSK_PH_COMMIT);
     HashSrc hc{pb.SH, (long long)sl.nslot * SLD, 1, SLD, SOFF, c->d_tab_commit, nullptr, 0};
@@ -430,6 +444,7 @@ static int prove_chunk(kosk_b200_ctx *c, Lane &ln, const ProveBufs &bufs, int B,
     prof_mark(c, ln, KOSK_PH_SHARE2);
     launch_share_eval(c, pb.Y, pb.SH, sl.n1, 4 * K, sl.n2, sl.nslot, B, st, false, pb.YL0, pb.YL1, pb.WS);
     prof_mark(c, ln, KOSK_PH_VIEW);
+    if (side) CU(cudaStreamWaitEvent(st, ln.vside.join, 0));
     k_derive<K><<<dim3(ptiles, B), 128, 0, st>>>(pb);
     HashSrc hv{pb.SH, (long long)sl.nslot * SLD, 1, SLD, SOFF, c->d_tab_view, nullptr, 0};
     if (fuse) {
