@@ -394,17 +394,23 @@ static int prove_chunk(kosk_b200_ctx *c, Lane &ln, const ProveBufs &bufs, int B,
     // Tail overlap: the previous sub-batch's FS-2 sponge (one latency-bound warp per proof, ~20 % of the issue slots) and its
     // assembly (HBM-bound gather) leave the integer pipes to this sub-batch's keygen / expansion / share evaluation.
     if (c->last_gate && c->last_gate != ln.computed && c->last_gate != ln.pre_tail) CU(cudaStreamWaitEvent(st, c->last_gate, 0));
+    // Latency mode: the key-independent expansion (PRF, NTT, sharing tails) does not depend on keygen; with a handful of proofs in flight the
+    // two run side by side on the lane's two streams (each is a short chain of small kernels) and join before the share evaluation.
+    const bool kside = on && off && !(phases & PH_NOKEYGEN) && B <= 16 && ln.vside.st != nullptr;
+    cudaStream_t se = kside ? ln.vside.st : st;
+    if (kside) { CU(cudaEventRecord(ln.vside.fork, st)); CU(cudaStreamWaitEvent(se, ln.vside.fork, 0)); }
     if (on && !(phases & PH_NOKEYGEN)) {
         prof_mark(c, ln, KOSK_PH_KEYGEN);
         k_keygen<K><<<B, 128, 0, st>>>(pb); c->launches++;
     }
     if (off) {
         prof_mark(c, ln, KOSK_PH_EXPAND);
-        k_expand_f<K><<<(B * sl.F + 63) / 64, 64, 0, st>>>(pb);
-        k_ntt_f<K><<<dim3(sl.F, B), 128, 0, st>>>(pb);
-        k_tails<K><<<(B * (sl.n1 + K) + 63) / 64, 64, 0, st>>>(pb);
+        k_expand_f<K><<<(B * sl.F + 63) / 64, 64, 0, se>>>(pb);
+        k_ntt_f<K><<<dim3(sl.F, B), 128, 0, se>>>(pb);
+        k_tails<K><<<(B * (sl.n1 + K) + 63) / 64, 64, 0, se>>>(pb);
         c->launches += 3;
     }
+    if (kside) { CU(cudaEventRecord(ln.vside.join, se)); CU(cudaStreamWaitEvent(st, ln.vside.join, 0)); }
     // first share evaluation: slots [0, s0) (f, NTT_f, eta constants) are key-independent, [s0, n1) (s, e, z_j) are not
     const int lo = off ? 0 : sl.s0, hi = on ? sl.n1 : sl.s0;
     prof_mark(c, ln, KOSK_PH_SHARE1);
