@@ -38,7 +38,10 @@ size_t kosk_b200_proof_bytes(int kyber_k);
 const char *kosk_b200_last_error(void);
 const char *kosk_b200_version(void);
 
-/* Context: one per (device, KYBER_K).  max_chunk = proofs processed per kernel wave (scratch is sized for
+/* Threading: a context serialises its callers (every entry point takes the context's lock); use one context per thread for
+ * concurrency.  A context cannot be destroyed while preprocessing pools created from it are alive (kosk_b200_destroy then keeps
+ * the context and records an error).
+ * Context: one per (device, KYBER_K).  max_chunk = proofs processed per kernel wave (scratch is sized for
  * it; 0 = default).  Replaces the reference's compile-time -DKYBER_K (params.hpp:8-10). */
 int kosk_b200_create(kosk_b200_ctx **ctx, int kyber_k, int device, int max_chunk);
 /* Same, with the number of pipeline lanes made explicit (0 = default 2).  A batch is split into sub-batches of at
@@ -62,7 +65,9 @@ int kosk_b200_kosk_verify(kosk_b200_ctx *ctx, const uint8_t *pi, const uint8_t *
  * 407 of them).  Proofs produced by kosk_b200_*keygen* / the reference prover are unaffected. */
 int kosk_b200_set_strict(kosk_b200_ctx *ctx, int on);
 
-/* Batch mode, host buffers, densely packed: seeds[n][32], pk[n][pk_bytes], sk[n][sk_bytes], pi[n][proof_bytes].
+/* Alignment: device-resident seeds (d_seeds) must be 8-byte aligned and device-resident proofs (d_pi) 4-byte aligned (cudaMalloc'd
+ * buffers are); host buffers may have any alignment.
+ * Batch mode, host buffers, densely packed: seeds[n][32], pk[n][pk_bytes], sk[n][sk_bytes], pi[n][proof_bytes].
  * Host<->device copies happen inside (pinned buffers are used asynchronously). */
 int kosk_b200_prove_batch(kosk_b200_ctx *ctx, size_t n, const uint8_t *seeds, uint8_t *pk, uint8_t *sk, uint8_t *pi);
 int kosk_b200_verify_batch(kosk_b200_ctx *ctx, size_t n, const uint8_t *pi, const uint8_t *pk, uint8_t *ok);
@@ -71,6 +76,36 @@ int kosk_b200_verify_batch(kosk_b200_ctx *ctx, size_t n, const uint8_t *pi, cons
  * alternate over the lanes: their kernels run back to back while the D2H copy of one overlaps the kernels of the next.
  * Host buffers must stay valid (and should be pinned) until kosk_b200_sync returns. */
 int kosk_b200_prove_batch_async(kosk_b200_ctx *ctx, size_t n, const uint8_t *seeds, uint8_t *pk, uint8_t *sk, uint8_t *pi);
+
+/* Compact wire format.  struct mpcith_proof (mlwe_prover.hpp:57-75) stores every GF(3329) element and every
+ * party index as a uint16_t; encode_mpcith_proof (mlwe_prover.cpp:540-543) is a memcpy of it.  The wire image holds the same
+ * fields in the same order with 12 bits per u16 (two elements per three bytes, little-endian as in kyber/poly.c:124-139) and
+ * the two digest arrays (Tcomm, comm) verbatim, every segment 16-byte aligned:
+ *     wire = pack12(f_shares .. gamma_shares) | pad | Tcomm | pack12(I .. u_e_2ddeg_shares) | pad | comm
+ * 519 136 / 531 616 / 578 992 bytes for Kyber512 / 768 / 1024 instead of 664 340 / 680 980 / 744 148.  Every proof whose u16
+ * fields are all < 4096 has a wire image (every proof a prover emits does); decoding is the exact inverse.
+ *
+ * The host-buffer batch calls above move proofs over PCIe, which bounds them (one B200 proves faster than a Gen5 x16 link
+ * carries 664 KB proofs).  With the wire mode on (default; KOSK_B200_WIRE=0 or kosk_b200_set_wire(ctx, 0, 0) turns it off) they
+ * pack on the device, copy the compact bytes in slices into a pinned staging buffer and expand them into the caller's pi[]
+ * (reference layout, unchanged; the buffer need not be pinned) on `threads` host worker threads while later slices are still
+ * on the link; verify_batch packs on those threads and unpacks on the device.  A sub-batch containing a proof with a u16 >= 4096
+ * travels in the reference layout instead (same verdicts).  Calls with fewer than 8 proofs always use the reference layout.
+ * The *_packed calls hand the compact bytes to / take them from the caller: wire[n][wire_bytes]. */
+size_t kosk_b200_wire_bytes(int kyber_k);
+int kosk_b200_set_wire(kosk_b200_ctx *ctx, int mode /* 0 | 1 */, int threads /* 0 = keep / default (KOSK_B200_WIRE_THREADS) */);
+int kosk_b200_wire_info(const kosk_b200_ctx *ctx, int *mode, int *threads, const char **simd);
+int kosk_b200_prove_batch_packed(kosk_b200_ctx *ctx, size_t n, const uint8_t *seeds, uint8_t *pk, uint8_t *sk, uint8_t *wire);
+int kosk_b200_prove_batch_packed_async(kosk_b200_ctx *ctx, size_t n, const uint8_t *seeds, uint8_t *pk, uint8_t *sk, uint8_t *wire);
+int kosk_b200_verify_batch_packed(kosk_b200_ctx *ctx, size_t n, const uint8_t *wire, const uint8_t *pk, uint8_t *ok);
+/* device-resident conversion, enqueued on `stream`: d_pi 4-byte aligned, d_wire 16-byte aligned */
+int kosk_b200_wire_pack_device(kosk_b200_ctx *ctx, size_t n, const uint8_t *d_pi, uint8_t *d_wire, void *stream);
+int kosk_b200_wire_unpack_device(kosk_b200_ctx *ctx, size_t n, const uint8_t *d_wire, uint8_t *d_pi, void *stream);
+/* host codec (no context, no device; a byte-format conversion like encode/decode_mpcith_proof, mlwe_prover.cpp:540-630):
+ * wire_pack fails with KOSK_E_ARG if some u16 of a proof is >= 4096.  threads <= 1: on the calling thread. */
+int kosk_b200_wire_pack(int kyber_k, size_t n, const uint8_t *pi, uint8_t *wire, int threads);
+int kosk_b200_wire_unpack(int kyber_k, size_t n, const uint8_t *wire, uint8_t *pi, int threads);
+const char *kosk_b200_wire_simd(void);      /* "avx512vbmi" | "avx2" | "scalar" */
 
 /* Batch mode, device-resident buffers (same packing), enqueued on `stream` (a cudaStream_t, NULL = default).
  * Asynchronous: the caller synchronises the stream. */

@@ -105,16 +105,29 @@ static_assert(sizeof(share_vec) == 5824 && sizeof(mlwe_inst) == (KYBER_K * KYBER
 namespace kosk_dropin_detail {
 struct State { kosk_b200_ctx *ctx; };
 inline void die() { fprintf(stderr, "kosk_b200: %s\n", kosk_b200_last_error()); abort(); }   /* the reference aborts on RNG failure; there is no CPU fallback */
+inline void reseed(kosk_b200_ctx *ctx)
+{
+    uint8_t seed[32];
+    if (getrandom(seed, 32, 0) != 32) abort();
+    if (kosk_b200_rng_reset(ctx, seed) != KOSK_OK) die();
+}
+inline State make_state()
+{
+    State s = {nullptr};
+    const char *dev = getenv("KOSK_B200_DEVICE");
+    if (kosk_b200_create(&s.ctx, KYBER_K, dev ? atoi(dev) : 0, 64) != KOSK_OK) die();
+    reseed(s.ctx);
+    return s;
+}
+/* One process-wide context and DRBG stand in for the reference's stack state and OS RNG.  Thread safety: the static is initialised
+ * once (C++11), every C-ABI call takes the context's lock, and each function below is ONE such call, so concurrent callers are
+ * serialised, never interleaved (the reference's functions are re-entrant; these are merely thread-safe).  The DRBG addresses its
+ * calls with a 32-bit counter (include/kosk_b200.h): long before it could wrap, a fresh seed is drawn from the OS and the
+ * counter restarts, so no randomness is ever replayed. */
 inline State &state()
 {
-    static State s = {nullptr};
-    if (!s.ctx) {
-        const char *dev = getenv("KOSK_B200_DEVICE");
-        if (kosk_b200_create(&s.ctx, KYBER_K, dev ? atoi(dev) : 0, 64) != KOSK_OK) die();
-        uint8_t seed[32];
-        if (getrandom(seed, 32, 0) != 32) abort();
-        if (kosk_b200_rng_reset(s.ctx, seed) != KOSK_OK) die();
-    }
+    static State s = make_state();
+    if (kosk_b200_rng_calls(s.ctx) > (1u << 30)) reseed(s.ctx);
     return s;
 }
 inline void ok(int rc) { if (rc != KOSK_OK) die(); }

@@ -21,6 +21,8 @@ EXPORTS = [
     "kosk_b200_prepare_randomness", "kosk_b200_prepare_range_proof", "kosk_b200_keygen", "kosk_b200_prove", "kosk_b200_verify",
     "kosk_b200_ct_bytes", "kosk_b200_kem_enc_derand_batch", "kosk_b200_kem_dec_batch", "kosk_b200_kem_enc_derand_batch_device", "kosk_b200_kem_dec_batch_device",
     "kosk_b200_kem_enc", "kosk_b200_kem_dec", "kosk_b200_kem_keypair_derand_batch", "kosk_b200_kem_keypair",
+    "kosk_b200_wire_bytes", "kosk_b200_set_wire", "kosk_b200_wire_info", "kosk_b200_prove_batch_packed", "kosk_b200_prove_batch_packed_async", "kosk_b200_verify_batch_packed",
+    "kosk_b200_wire_pack_device", "kosk_b200_wire_unpack_device", "kosk_b200_wire_pack", "kosk_b200_wire_unpack", "kosk_b200_wire_simd",
     "kosk_b200_pool_create", "kosk_b200_pool_prove", "kosk_b200_pool_destroy", "kosk_b200_set_strict", "kosk_b200_set_profiling", "kosk_b200_phase_times", "kosk_b200_int_peak",
 ]
 
@@ -41,7 +43,8 @@ def load_library(path=None):
         raise KoskError(f"{path} not found: build it with `python -m mpcith_kyber_kosk_b200.build` (no CPU fallback exists)")
     lib = ctypes.CDLL(path)
     vp, sz, i32, u8p = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p
-    for n in ("kosk_b200_pk_bytes", "kosk_b200_sk_bytes", "kosk_b200_proof_bytes", "kosk_b200_inst_bytes", "kosk_b200_randomness_bytes", "kosk_b200_range_proof_bytes", "kosk_b200_ct_bytes"):
+    for n in ("kosk_b200_pk_bytes", "kosk_b200_sk_bytes", "kosk_b200_proof_bytes", "kosk_b200_inst_bytes", "kosk_b200_randomness_bytes", "kosk_b200_range_proof_bytes", "kosk_b200_ct_bytes",
+              "kosk_b200_wire_bytes"):
         getattr(lib, n).restype = sz
         getattr(lib, n).argtypes = [i32]
     lib.kosk_b200_last_error.restype = ctypes.c_char_p
@@ -90,6 +93,16 @@ def load_library(path=None):
     lib.kosk_b200_kem_keypair.argtypes = [vp, u8p, u8p]
     lib.kosk_b200_kem_enc.argtypes = [vp, u8p, u8p, u8p]
     lib.kosk_b200_kem_dec.argtypes = [vp, u8p, u8p, u8p]
+    lib.kosk_b200_set_wire.argtypes = [vp, i32, i32]
+    lib.kosk_b200_wire_info.argtypes = [vp, ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(ctypes.c_char_p)]
+    lib.kosk_b200_prove_batch_packed.argtypes = [vp, sz, u8p, u8p, u8p, u8p]
+    lib.kosk_b200_prove_batch_packed_async.argtypes = [vp, sz, u8p, u8p, u8p, u8p]
+    lib.kosk_b200_verify_batch_packed.argtypes = [vp, sz, u8p, u8p, u8p]
+    lib.kosk_b200_wire_pack_device.argtypes = [vp, sz, u8p, u8p, vp]
+    lib.kosk_b200_wire_unpack_device.argtypes = [vp, sz, u8p, u8p, vp]
+    lib.kosk_b200_wire_pack.argtypes = [i32, sz, u8p, u8p, i32]
+    lib.kosk_b200_wire_unpack.argtypes = [i32, sz, u8p, u8p, i32]
+    lib.kosk_b200_wire_simd.restype = ctypes.c_char_p
     lib.kosk_b200_phase_times.argtypes = [vp, u8p, u8p, i32, i32]
     lib.kosk_b200_int_peak.argtypes = [vp, u8p]
     if path == LIB_PATH:
@@ -109,8 +122,38 @@ def proof_bytes(k):
     return load_library().kosk_b200_proof_bytes(k)
 
 
+def wire_bytes(k):
+    return load_library().kosk_b200_wire_bytes(k)
+
+
 def _ptr(a):
     return ctypes.c_void_p(a.ctypes.data)
+
+
+def wire_pack(k, pi, threads=1):
+    """Host codec: proofs in the reference layout (pi[n][proof_bytes]) -> compact wire images (include/kosk_b200.h)."""
+    lib = load_library()
+    pi = np.ascontiguousarray(pi, dtype=np.uint8).reshape(-1, proof_bytes(k))
+    out = np.empty((pi.shape[0], wire_bytes(k)), np.uint8)
+    rc = lib.kosk_b200_wire_pack(k, pi.shape[0], _ptr(pi), _ptr(out), threads)
+    if rc != 0:
+        raise KoskError(f"wire_pack failed ({rc}): {lib.kosk_b200_last_error().decode()}")
+    return out
+
+
+def wire_unpack(k, wire, threads=1):
+    """Host codec: compact wire images -> proofs in the reference layout."""
+    lib = load_library()
+    wire = np.ascontiguousarray(wire, dtype=np.uint8).reshape(-1, wire_bytes(k))
+    out = np.empty((wire.shape[0], proof_bytes(k)), np.uint8)
+    rc = lib.kosk_b200_wire_unpack(k, wire.shape[0], _ptr(wire), _ptr(out), threads)
+    if rc != 0:
+        raise KoskError(f"wire_unpack failed ({rc}): {lib.kosk_b200_last_error().decode()}")
+    return out
+
+
+def wire_simd():
+    return load_library().kosk_b200_wire_simd().decode()
 
 
 class KoskContext:
@@ -124,6 +167,7 @@ class KoskContext:
         if rc != 0:
             raise KoskError(f"kosk_b200_create failed ({rc}): {self.lib.kosk_b200_last_error().decode()}")
         self.pk_bytes, self.sk_bytes, self.proof_bytes = pk_bytes(kyber_k), sk_bytes(kyber_k), proof_bytes(kyber_k)
+        self.wire_bytes = wire_bytes(kyber_k)
 
     def close(self):
         if self._h:
@@ -281,6 +325,44 @@ class KoskContext:
         ok = np.zeros(n, np.uint8)
         self._check(self.lib.kosk_b200_verify_batch(self._h, n, _ptr(pi), _ptr(pk), _ptr(ok)), "verify_batch")
         return ok.astype(bool)
+
+    # ---- compact wire format ----
+    def set_wire(self, mode=1, threads=0):
+        """Host-buffer batch calls move proofs over the link as 12-bit wire images (1, default) or as struct bytes (0)."""
+        self._check(self.lib.kosk_b200_set_wire(self._h, int(mode), int(threads)), "set_wire")
+
+    def wire_info(self):
+        m, t, sname = ctypes.c_int(), ctypes.c_int(), ctypes.c_char_p()
+        self._check(self.lib.kosk_b200_wire_info(self._h, ctypes.byref(m), ctypes.byref(t), ctypes.byref(sname)), "wire_info")
+        return {"mode": m.value, "threads": t.value, "simd": (sname.value or b"").decode()}
+
+    def prove_batch_packed(self, seeds, out=None):
+        """prove_batch whose proofs come back as compact wire images: returns (pk, sk, wire[n][wire_bytes])."""
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint8).reshape(-1, 32)
+        n = seeds.shape[0]
+        if out is None:
+            out = (np.empty((n, self.pk_bytes), np.uint8), np.empty((n, self.sk_bytes), np.uint8), np.empty((n, self.wire_bytes), np.uint8))
+        pk, sk, wire = out
+        self._check(self.lib.kosk_b200_prove_batch_packed(self._h, n, _ptr(seeds), _ptr(pk), _ptr(sk), _ptr(wire)), "prove_batch_packed")
+        return pk, sk, wire
+
+    def verify_batch_packed(self, wire, pk):
+        wire = np.ascontiguousarray(wire, dtype=np.uint8).reshape(-1, self.wire_bytes)
+        pk = np.ascontiguousarray(pk, dtype=np.uint8).reshape(-1, self.pk_bytes)
+        n = wire.shape[0]
+        if pk.shape[0] != n:
+            raise KoskError("wire / pk batch mismatch")
+        ok = np.zeros(n, np.uint8)
+        self._check(self.lib.kosk_b200_verify_batch_packed(self._h, n, _ptr(wire), _ptr(pk), _ptr(ok)), "verify_batch_packed")
+        return ok.astype(bool)
+
+    def wire_pack_device(self, n, d_pi, d_wire, stream=0):
+        vp = ctypes.c_void_p
+        self._check(self.lib.kosk_b200_wire_pack_device(self._h, n, vp(d_pi), vp(d_wire), vp(stream)), "wire_pack_device")
+
+    def wire_unpack_device(self, n, d_wire, d_pi, stream=0):
+        vp = ctypes.c_void_p
+        self._check(self.lib.kosk_b200_wire_unpack_device(self._h, n, vp(d_wire), vp(d_pi), vp(stream)), "wire_unpack_device")
 
     # ---- batch, device pointers (integers), asynchronous on `stream` ----
     def prove_batch_device(self, n, d_seeds, d_pk, d_sk, d_pi, stream=0):

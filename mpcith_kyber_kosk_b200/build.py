@@ -11,7 +11,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libkosk_b200.so")
 SOURCES = ["kosk_b200.cu"]
-HEADERS = ["kosk_common.cuh", "keccak.cuh", "gf_gemm.cuh", "gf_gemm_imma.cuh", "prove_kernels.cuh", "verify_kernels.cuh", "raw_api.cuh", "kem_kernels.cuh", "share_ntt.cuh"]
+HOST_SOURCES = ["wire_host.cpp"]          # host-only code (SIMD byte codec + worker pool of the compact wire format): g++, linked into the same library
+HEADERS = ["kosk_common.cuh", "keccak.cuh", "gf_gemm.cuh", "gf_gemm_imma.cuh", "prove_kernels.cuh", "verify_kernels.cuh", "raw_api.cuh", "kem_kernels.cuh", "share_ntt.cuh",
+           "wire_kernels.cuh", "wire_host.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared", "-cudart", "static",
@@ -29,14 +31,21 @@ def needs_build():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.join(HERE, "..", "include", "kosk_b200.h")]
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HOST_SOURCES + HEADERS] + [os.path.join(HERE, "..", "include", "kosk_b200.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    objs = []
+    for src in HOST_SOURCES:
+        obj = os.path.join(CSRC, src.rsplit(".", 1)[0] + ".o")
+        r = subprocess.run(["g++", "-O3", "-std=c++17", "-fPIC", "-pthread", "-c", os.path.join(CSRC, src), "-o", obj], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("g++ failed:\n" + r.stdout + r.stderr)
+        objs.append(obj)
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES] + objs + ["-lpthread"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)

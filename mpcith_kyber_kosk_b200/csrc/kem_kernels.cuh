@@ -249,7 +249,9 @@ __global__ void __launch_bounds__(128) k_kem_dec(const u8 *__restrict__ cts, con
         // poly_tomsg on the centered representative (poly_reduce), in the reference's 32-bit arithmetic (poly.c:208-219)
         uint32_t t = (uint32_t)gf_center(gf_sub(S.v[c], S.epp[c]));
         t <<= 1; t += 1665; t *= 80635u; t >>= 28; t &= 1;
-        if (t) atomicOr(&S.mw[c >> 5], 1u << (c & 31));
+        // no branch on the message bit: a warp covers 32 consecutive coefficients, the ballot is their message word
+        const uint32_t word = __ballot_sync(0xffffffffu, t != 0);
+        if ((tid & 31) == 0) S.mw[c >> 5] = word;
     }
     __syncthreads();
     if (tid < 32) {                          // hash_g(m' || H(pk) from sk), warp-cooperative
@@ -265,13 +267,32 @@ __global__ void __launch_bounds__(128) k_kem_dec(const u8 *__restrict__ cts, con
     enc_secret<K>(S, tid);
     int bad = 0;
     for (int i = tid; i < d.ct_bytes; i += 128) bad |= S.ct[i] != ct[i];
-    if (bad) atomicOr(&S.fail, 1);
+    atomicOr(&S.fail, bad);                  // unconditional: no path depends on whether the re-encryption matched
     __syncthreads();
-    if (tid == 0) {
-        if (S.fail) {                        // implicit rejection: rkprf(z, ct) = SHAKE256(z || ct) (symmetric-shake.c:64-73)
-            ByteSponge sp; sp.init(136); sp.absorb(sk + 768 * K + 64, 32); sp.absorb(ct, d.ct_bytes); sp.finalize(0x1F);
-            for (int i = 0; i < 32; i++) sss[32 * (size_t)b + i] = sp.next();
-        } else for (int i = 0; i < 32; i++) sss[32 * (size_t)b + i] = S.kr[i];
+    // Implicit rejection (kem.c:157-166): rkprf(z, ct) = SHAKE256(z || ct) (symmetric-shake.c:64-73) is ALWAYS computed, warp-cooperatively,
+    // and the output is selected with a mask like the reference's verify() + cmov_int: accepted and rejected ciphertexts do the same work.
+    if (tid < 32) {
+        WarpKeccak wk; wk.init();
+        constexpr int CTB = K * 32 * DU + 32 * DV, NW = 4 + CTB / 8, NB = NW / 17, REM = NW % 17;
+        static_assert(CTB % 8 == 0, "ciphertext is a whole number of sponge words");
+        const uint64_t *zw = reinterpret_cast<const uint64_t *>(sk + 768 * K + 64), *cw = reinterpret_cast<const uint64_t *>(ct);
+        auto word = [&](int i) -> uint64_t { return i < 4 ? zw[i] : cw[i - 4]; };
+        uint64_t a = 0;
+#pragma unroll 1
+        for (int blk = 0; blk < NB; blk++) { if (tid < 17) a ^= word(blk * 17 + tid); a = wk.permute(a); }
+        if (tid < REM) a ^= word(NB * 17 + tid);
+        if (tid == REM) a ^= 0x1FULL;
+        if (tid == 16) a ^= 0x8000000000000000ULL;
+        a = wk.permute(a);
+        if (tid < 4) {
+            uint64_t kr = 0;
+#pragma unroll
+            for (int i = 0; i < 8; i++) kr |= (uint64_t)S.kr[8 * tid + i] << (8 * i);
+            const uint64_t mask = 0ULL - (uint64_t)(S.fail != 0);
+            const uint64_t out = kr ^ (mask & (kr ^ a));
+#pragma unroll
+            for (int i = 0; i < 8; i++) sss[32 * (size_t)b + 8 * tid + i] = (u8)(out >> (8 * i));
+        }
     }
 }
 
@@ -352,12 +373,14 @@ size_t kosk_b200_ct_bytes(int k) { return (k >= 2 && k <= 4) ? (size_t)kem_dims(
 int kosk_b200_kem_enc_derand_batch_device(kosk_b200_ctx *c, size_t n, const uint8_t *d_pk, const uint8_t *d_coins, uint8_t *d_ct, uint8_t *d_ss, void *stream)
 {
     if (!c || !d_pk || !d_coins || !d_ct || !d_ss) return fail(KOSK_E_ARG, "null argument");
+    LOCK(c);
     CU(cudaSetDevice(c->device));
     return n ? kem_enc_launch(c, n, d_pk, d_coins, nullptr, 0, d_ct, d_ss, (cudaStream_t)stream) : KOSK_OK;
 }
 int kosk_b200_kem_dec_batch_device(kosk_b200_ctx *c, size_t n, const uint8_t *d_ct, const uint8_t *d_sk, uint8_t *d_ss, void *stream)
 {
     if (!c || !d_ct || !d_sk || !d_ss) return fail(KOSK_E_ARG, "null argument");
+    LOCK(c);
     CU(cudaSetDevice(c->device));
     return n ? kem_dec_launch(c, n, d_ct, d_sk, d_ss, (cudaStream_t)stream) : KOSK_OK;
 }
@@ -382,12 +405,14 @@ static int kem_enc_host(kosk_b200_ctx *c, size_t n, const uint8_t *pk, const uin
 int kosk_b200_kem_enc_derand_batch(kosk_b200_ctx *c, size_t n, const uint8_t *pk, const uint8_t *coins, uint8_t *ct, uint8_t *ss)
 {
     if (!c || !pk || !coins || !ct || !ss) return fail(KOSK_E_ARG, "null argument");
+    LOCK(c);
     return kem_enc_host(c, n, pk, coins, nullptr, 0, ct, ss);
 }
 
 int kosk_b200_kem_dec_batch(kosk_b200_ctx *c, size_t n, const uint8_t *ct, const uint8_t *sk, uint8_t *ss)
 {
     if (!c || !ct || !sk || !ss) return fail(KOSK_E_ARG, "null argument");
+    LOCK(c);
     CU(cudaSetDevice(c->device));
     if (n == 0) return KOSK_OK;
     int rc = kem_reserve(c, n); if (rc) return rc;
@@ -426,11 +451,13 @@ static int kem_keypair_host(kosk_b200_ctx *c, size_t n, const uint8_t *coins /* 
 int kosk_b200_kem_keypair_derand_batch(kosk_b200_ctx *c, size_t n, const uint8_t *coins, uint8_t *pk, uint8_t *sk)
 {
     if (!c || !coins || !pk || !sk) return fail(KOSK_E_ARG, "null argument");
+    LOCK(c);
     return n ? kem_keypair_host(c, n, coins, pk, sk) : KOSK_OK;
 }
 int kosk_b200_kem_keypair(kosk_b200_ctx *c, uint8_t *pk, uint8_t *sk)
 {
     if (!c || !pk || !sk) return fail(KOSK_E_ARG, "null argument");
+    LOCK(c);
     int rc = kem_keypair_host(c, 1, nullptr, pk, sk);
     if (!rc) c->raw->calls += 1;                 // randombytes(coins, 64), kem.c:52
     return rc;
@@ -440,6 +467,7 @@ int kosk_b200_kem_keypair(kosk_b200_ctx *c, uint8_t *pk, uint8_t *sk)
 int kosk_b200_kem_enc(kosk_b200_ctx *c, uint8_t *ct, uint8_t *ss, const uint8_t *pk)
 {
     if (!c || !ct || !ss || !pk) return fail(KOSK_E_ARG, "null argument");
+    LOCK(c);
     int rc = kem_enc_host(c, 1, pk, nullptr, c->raw->seed, c->raw->calls, ct, ss);
     if (!rc) c->raw->calls += 1;
     return rc;

@@ -6,12 +6,16 @@
 #include "verify_kernels.cuh"
 #include "gf_gemm_imma.cuh"
 #include "share_ntt.cuh"
+#include "wire_kernels.cuh"
+#include "wire_host.h"
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
+#include <mutex>
+#include <thread>
 #include <algorithm>
 #include <utility>
 
@@ -23,6 +27,13 @@ static int fail(int code, const std::string &msg) { g_err = msg; return code; }
     do {                                                                                                 \
         cudaError_t e_ = (call);                                                                         \
         if (e_ != cudaSuccess) return fail(KOSK_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+// inside kosk_b200_create_ex after the context exists: release it (and every table allocated so far) before reporting the error
+#define CUC(call)                                                                                        \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) { ctx_free(c); return fail(KOSK_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } \
     } while (0)
 
 // ---- one-time host table construction (the reference's missing utils/precomputed_kyber.c) ----
@@ -70,6 +81,12 @@ struct Lane {
     VerifySide vside{};                     // second stream of the verifier (challenge-independent chain), KOSK_B200_VERIFY_SIDE=0 disables it
     std::vector<cudaEvent_t> ev; int ev_used = 0;
     std::vector<std::pair<int, int>> ev_phase;     // (phase id, event index of its start); end = next event
+    // compact wire format (wire_kernels.cuh / wire_host.h): device and pinned host staging of the packed proofs of one sub-batch,
+    // one event per D2H slice (the unpack workers wait on it), and the event after the lane's latest H2D from h_wire
+    u8 *d_wire = nullptr, *h_wire = nullptr;
+    std::vector<cudaEvent_t> wev;
+    cudaEvent_t h2d_done = nullptr; bool h2d_pending = false;
+    volatile int wire_flag = 0;                    // set by a worker whose event wait failed
 };
 
 struct kosk_b200_ctx {
@@ -102,7 +119,14 @@ struct kosk_b200_ctx {
     double phase_ms[KOSK_NPHASE] = {0}; uint64_t phase_calls[KOSK_NPHASE] = {0};
     RawState *raw = nullptr;               // struct-level API (raw_api.cuh): DRBG state and staging buffers
     KemState *kem = nullptr;               // Kyber KEM encaps / decaps (kem_kernels.cuh)
+    // Host-buffer batch calls: 0 = the proofs cross the link as struct mpcith_proof bytes (one cudaMemcpyAsync per buffer, round-1 behaviour),
+    // 1 = as the compact wire format, packed / unpacked on the device and expanded / packed by the worker pool on the host
+    int wire_mode = 1, wire_threads = 0, wire_slice = 64;
+    WirePool *wpool = nullptr;
+    int live_pools = 0;                    // preprocessing pools created from this context and not yet destroyed
+    std::recursive_mutex mu;               // one caller at a time: the lanes' scratch and the DRBG state are per context
 };
+#define LOCK(c) std::lock_guard<std::recursive_mutex> lock_((c)->mu)
 
 static void prof_mark(kosk_b200_ctx *c, Lane &ln, int phase, cudaStream_t on = nullptr)
 {
@@ -131,6 +155,12 @@ static void free_prove_bufs(ProveBufs &pb)
     for (void *p : lp) if (p) cudaFree(p);
     pb = ProveBufs{};
 }
+static void scrub_prove_bufs(ProveBufs &pb, const Slots &sl, int k, size_t B)
+{
+    if (pb.Y) cudaMemset(pb.Y, 0, B * sl.n2 * YLD * 2);
+    if (pb.SH) cudaMemset(pb.SH, 0, B * sl.nslot * SLD * 2);
+    if (pb.SHAT) cudaMemset(pb.SHAT, 0, B * k * 256 * 2);
+}
 static int alloc_prove_bufs(ProveBufs &pb, const Slots &sl, int k, size_t B, bool tensor)
 {
 #define PA(ptr, bytes, zero) do { if (cudaMalloc((void **)&(ptr), (bytes)) != cudaSuccess) { free_prove_bufs(pb); return -1; } if (zero) cudaMemset((ptr), 0, (bytes)); } while (0)
@@ -153,12 +183,21 @@ static void ctx_free(kosk_b200_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
+    wire_pool_destroy(c->wpool); c->wpool = nullptr;
     void *ptrs[] = {c->d_sn, c->d_U1, c->d_U2, c->d_status, c->d_fact, c->tmpL0, c->tmpL1, c->d_St, c->d_St0, c->d_St1, c->d_SU, c->d_R1, c->d_R2, c->d_inv, c->d_tab_commit, c->d_tab_view};
     for (void *p : ptrs) if (p) cudaFree(p);
+    const size_t Bc = (size_t)c->chunk;
     for (Lane &ln : c->lanes) {
+        // scratch that held seeds, s, e and secret keys is cleared before it goes back to the allocator
+        if (ln.d_seeds) cudaMemset(ln.d_seeds, 0, Bc * 32);
+        if (ln.d_sk) cudaMemset(ln.d_sk, 0, Bc * c->L.sk_bytes);
+        scrub_prove_bufs(ln.pb, c->sl, c->k, Bc);
         free_prove_bufs(ln.pb);
-        void *lp[] = {ln.d_seeds, ln.d_pk, ln.d_sk, ln.d_pi, ln.d_ok};
+        void *lp[] = {ln.d_seeds, ln.d_pk, ln.d_sk, ln.d_pi, ln.d_ok, ln.d_wire};
         for (void *p : lp) if (p) cudaFree(p);
+        if (ln.h_wire) cudaFreeHost(ln.h_wire);
+        for (cudaEvent_t e : ln.wev) cudaEventDestroy(e);
+        if (ln.h2d_done) cudaEventDestroy(ln.h2d_done);
         verify_free(ln.vb);
         for (cudaEvent_t e : ln.ev) cudaEventDestroy(e);
         if (ln.done) cudaEventDestroy(ln.done);
@@ -173,6 +212,15 @@ static void ctx_free(kosk_b200_ctx *c)
     raw_delete(c->raw);
     kem_delete(c->kem);
     delete c;
+}
+
+// device status word: set by a kernel that gave up waiting (never expected); read after the streams are idle
+static int check_status(kosk_b200_ctx *c)
+{
+    int st = 0;
+    CU(cudaMemcpy(&st, c->d_status, 4, cudaMemcpyDeviceToHost));
+    if (st) return fail(KOSK_E_CUDA, "a kernel gave up waiting for its producer warps (internal error)");
+    return KOSK_OK;
 }
 
 extern "C" {
@@ -211,6 +259,8 @@ int kosk_b200_create_ex(kosk_b200_ctx **out, int k, int device, int max_chunk, i
     { const char *e = getenv("KOSK_B200_OVERLAP_FS1"); if (e) c->overlap_fs1 = atoi(e); }
     { const char *e = getenv("KOSK_B200_SHARE_NTT"); if (e) c->use_ntt = atoi(e); }
     if (c->use_tensor) c->use_ntt = 0;
+    { const char *e = getenv("KOSK_B200_WIRE"); if (e) c->wire_mode = atoi(e) ? 1 : 0; }
+    { const char *e = getenv("KOSK_B200_WIRE_SLICE"); if (e && atoi(e) > 0) c->wire_slice = atoi(e); }
     const Slots &sl = c->sl; const Layout &L = c->L;
     const size_t B = (size_t)c->chunk;
 #define ALLOC(ptr, bytes) do { if (cudaMalloc((void **)&(ptr), (bytes)) != cudaSuccess) { ctx_free(c); return fail(KOSK_E_NOMEM, "cudaMalloc failed for " #ptr); } } while (0)
@@ -218,23 +268,23 @@ int kosk_b200_create_ex(kosk_b200_ctx **out, int k, int device, int max_chunk, i
     {
         uint16_t hz[128];
         for (int i = 0; i < 128; i++) { int br = 0; for (int b = 0; b < 7; b++) br |= ((i >> b) & 1) << (6 - b); hz[i] = (uint16_t)h_pow(17, br); }
-        CU(cudaMemcpyToSymbol(c_zeta, hz, sizeof hz));
+        CUC(cudaMemcpyToSymbol(c_zeta, hz, sizeof hz));
         std::vector<int> nodes(D1), targets(NX);
         for (int j = 0; j < D1; j++) nodes[j] = j;
         for (int x = 0; x < NX; x++) targets[x] = x + D1;
         std::vector<uint16_t> S; h_lagrange(S, nodes, targets);
         std::vector<int16_t> St((size_t)GE_NPAD * YLD, 0);
         for (int x = 0; x < NX; x++) for (int j = 0; j < D1; j++) St[(size_t)x * YLD + j] = (int16_t)gf_center(S[(size_t)x * D1 + j]);
-        ALLOC(c->d_St, St.size() * 2); CU(cudaMemcpy(c->d_St, St.data(), St.size() * 2, cudaMemcpyHostToDevice));
+        ALLOC(c->d_St, St.size() * 2); CUC(cudaMemcpy(c->d_St, St.data(), St.size() * 2, cudaMemcpyHostToDevice));
         {   // limb planes for the opt-in tensor path: s = 128*s1 + s0, s0 in [-64, 63]
             std::vector<int8_t> L0(St.size()), L1(St.size());
             for (size_t i = 0; i < St.size(); i++) { const int v = St[i], v0 = ((v + 64) & 127) - 64; L0[i] = (int8_t)v0; L1[i] = (int8_t)((v - v0) >> 7); }
-            ALLOC(c->d_St0, L0.size()); CU(cudaMemcpy(c->d_St0, L0.data(), L0.size(), cudaMemcpyHostToDevice));
-            ALLOC(c->d_St1, L1.size()); CU(cudaMemcpy(c->d_St1, L1.data(), L1.size(), cudaMemcpyHostToDevice));
+            ALLOC(c->d_St0, L0.size()); CUC(cudaMemcpy(c->d_St0, L0.data(), L0.size(), cudaMemcpyHostToDevice));
+            ALLOC(c->d_St1, L1.size()); CUC(cudaMemcpy(c->d_St1, L1.data(), L1.size(), cudaMemcpyHostToDevice));
         }
         std::vector<int16_t> SU(GE_NPAD, 0);
         for (int x = 0; x < NX; x++) { uint32_t u = 0; for (int j = 0; j < NL; j++) u = (u + S[(size_t)x * D1 + j]) % Q; SU[x] = (int16_t)gf_center(u); }
-        ALLOC(c->d_SU, SU.size() * 2); CU(cudaMemcpy(c->d_SU, SU.data(), SU.size() * 2, cudaMemcpyHostToDevice));
+        ALLOC(c->d_SU, SU.size() * 2); CUC(cudaMemcpy(c->d_SU, SU.data(), SU.size() * 2, cudaMemcpyHostToDevice));
         // verifier recon tables R1 (256 x 407 over nodes 256..662) and R2 (256 x 813 over nodes 256..1068)
         std::vector<int> n1(D1), n2(D2), tg(NL);
         for (int j = 0; j < D1; j++) n1[j] = 256 + j;
@@ -244,31 +294,31 @@ int kosk_b200_create_ex(kosk_b200_ctx **out, int k, int device, int max_chunk, i
         std::vector<int16_t> R1p((size_t)NL * YLD, 0), R2p((size_t)NL * VR2LD, 0);
         for (int i = 0; i < NL; i++) { for (int j = 0; j < D1; j++) R1p[(size_t)i * YLD + j] = (int16_t)gf_center(R1[(size_t)i * D1 + j]);
                                        for (int j = 0; j < D2; j++) R2p[(size_t)i * VR2LD + j] = (int16_t)gf_center(R2[(size_t)i * D2 + j]); }
-        ALLOC(c->d_R1, R1p.size() * 2); CU(cudaMemcpy(c->d_R1, R1p.data(), R1p.size() * 2, cudaMemcpyHostToDevice));
-        ALLOC(c->d_R2, R2p.size() * 2); CU(cudaMemcpy(c->d_R2, R2p.data(), R2p.size() * 2, cudaMemcpyHostToDevice));
+        ALLOC(c->d_R1, R1p.size() * 2); CUC(cudaMemcpy(c->d_R1, R1p.data(), R1p.size() * 2, cudaMemcpyHostToDevice));
+        ALLOC(c->d_R2, R2p.size() * 2); CUC(cudaMemcpy(c->d_R2, R2p.data(), R2p.size() * 2, cudaMemcpyHostToDevice));
         std::vector<uint16_t> inv(Q, 0); for (int a = 1; a < Q; a++) inv[a] = (uint16_t)h_pow(a, Q - 2);
-        ALLOC(c->d_inv, Q * 2); CU(cudaMemcpy(c->d_inv, inv.data(), Q * 2, cudaMemcpyHostToDevice));
+        ALLOC(c->d_inv, Q * 2); CUC(cudaMemcpy(c->d_inv, inv.data(), Q * 2, cudaMemcpyHostToDevice));
         {   // Cauchy operands of the verifier's interpolation (mlwe_verifier.cpp:188-224 etc.): U[t][p] = 1 / (t - (p + 256)), 0 where t is the node
             std::vector<int16_t> U1((size_t)U1_ROWS * KP1, 0), U2((size_t)NL * KP2, 0);
             for (int t = 0; t < D1; t++) for (int p = 0; p < KP1; p++) { const int dd = ((t - p - 256) % Q + Q) % Q; U1[(size_t)t * KP1 + p] = (int16_t)(dd ? gf_center(inv[dd]) : 0); }
             for (int t = 0; t < NL; t++) for (int p = 0; p < KP2; p++) { const int dd = ((t - p - 256) % Q + Q) % Q; U2[(size_t)t * KP2 + p] = (int16_t)gf_center(inv[dd]); }
-            ALLOC(c->d_U1, U1.size() * 2); CU(cudaMemcpy(c->d_U1, U1.data(), U1.size() * 2, cudaMemcpyHostToDevice));
-            ALLOC(c->d_U2, U2.size() * 2); CU(cudaMemcpy(c->d_U2, U2.data(), U2.size() * 2, cudaMemcpyHostToDevice));
+            ALLOC(c->d_U1, U1.size() * 2); CUC(cudaMemcpy(c->d_U1, U1.data(), U1.size() * 2, cudaMemcpyHostToDevice));
+            ALLOC(c->d_U2, U2.size() * 2); CUC(cudaMemcpy(c->d_U2, U2.data(), U2.size() * 2, cudaMemcpyHostToDevice));
         }
         {   // tables of the NTT-convolution share evaluation (share_ntt.cuh)
             const ShareNttHost sh = share_ntt_tables();
-            CU(cudaMemcpyToSymbol(c_sn_w16f, sh.w16f.data(), 256 * 4)); CU(cudaMemcpyToSymbol(c_sn_w16i, sh.w16i.data(), 256 * 4));
+            CUC(cudaMemcpyToSymbol(c_sn_w16f, sh.w16f.data(), 256 * 4)); CUC(cudaMemcpyToSymbol(c_sn_w16i, sh.w16i.data(), 256 * 4));
             std::vector<int16_t> all;
             const std::vector<int16_t> *parts[] = {&sh.tw, &sh.kh_share, &sh.kh_m256, &sh.wj, &sh.wj2, &sh.px, &sh.pr1, &sh.pr2};
             size_t offs[8]; int np = 0;
             for (const std::vector<int16_t> *v : parts) { offs[np++] = all.size(); all.insert(all.end(), v->begin(), v->end()); while (all.size() % 8) all.push_back(0); }
-            ALLOC(c->d_sn, all.size() * 2); CU(cudaMemcpy(c->d_sn, all.data(), all.size() * 2, cudaMemcpyHostToDevice));
+            ALLOC(c->d_sn, all.size() * 2); CUC(cudaMemcpy(c->d_sn, all.data(), all.size() * 2, cudaMemcpyHostToDevice));
             c->sn.tw = c->d_sn + offs[0]; c->sn.kh_share = c->d_sn + offs[1]; c->sn.kh_m256 = c->d_sn + offs[2]; c->sn.wj = c->d_sn + offs[3];
             c->sn.wj2 = c->d_sn + offs[4]; c->sn.px = c->d_sn + offs[5]; c->sn.pr1 = c->d_sn + offs[6]; c->sn.pr2 = c->d_sn + offs[7];
         }
         std::vector<uint16_t> fc(2 * FACT_N);
         { uint32_t f = 1; for (int i = 0; i < FACT_N; i++) { if (i) f = f * i % Q; fc[i] = (uint16_t)f; fc[FACT_N + i] = inv[f]; } }
-        ALLOC(c->d_fact, fc.size() * 2); CU(cudaMemcpy(c->d_fact, fc.data(), fc.size() * 2, cudaMemcpyHostToDevice));
+        ALLOC(c->d_fact, fc.size() * 2); CUC(cudaMemcpy(c->d_fact, fc.data(), fc.size() * 2, cudaMemcpyHostToDevice));
         // hashed-record slot tables: commitment (mlwe_prover.cpp:117-126) and view (:398-443)
         std::vector<int16_t> tc, tv;
         for (int j = 0; j < k; j++) tc.push_back((int16_t)(sl.s0 + j));
@@ -287,44 +337,48 @@ int kosk_b200_create_ex(kosk_b200_ctx **out, int k, int device, int max_chunk, i
             for (int m = 0; m < sl.M; m++) tv.push_back((int16_t)(sl.US0 + j * sl.M + m));
             for (int m = 0; m < sl.M; m++) tv.push_back((int16_t)(sl.UE0 + j * sl.M + m));
         }
-        ALLOC(c->d_tab_commit, tc.size() * 2); CU(cudaMemcpy(c->d_tab_commit, tc.data(), tc.size() * 2, cudaMemcpyHostToDevice));
-        ALLOC(c->d_tab_view, tv.size() * 2); CU(cudaMemcpy(c->d_tab_view, tv.data(), tv.size() * 2, cudaMemcpyHostToDevice));
+        ALLOC(c->d_tab_commit, tc.size() * 2); CUC(cudaMemcpy(c->d_tab_commit, tc.data(), tc.size() * 2, cudaMemcpyHostToDevice));
+        ALLOC(c->d_tab_view, tv.size() * 2); CUC(cudaMemcpy(c->d_tab_view, tv.data(), tv.size() * 2, cudaMemcpyHostToDevice));
     }
-    ALLOC(c->d_status, 4); CU(cudaMemset(c->d_status, 0, 4));
+    ALLOC(c->d_status, 4); CUC(cudaMemset(c->d_status, 0, 4));
     // ---- per-lane scratch ----
     c->lanes.resize(nlanes);
     for (Lane &ln : c->lanes) {
         if (alloc_prove_bufs(ln.pb, sl, k, B, c->use_tensor != 0) != 0) { ctx_free(c); return fail(KOSK_E_NOMEM, "cudaMalloc failed for prover scratch"); }
         ALLOC(ln.d_seeds, B * 32); ALLOC(ln.d_pk, B * L.pk_bytes); ALLOC(ln.d_sk, B * L.sk_bytes); ALLOC(ln.d_pi, B * L.proof_bytes); ALLOC(ln.d_ok, B);
         if (verify_alloc(ln.vb, k, c->chunk) != 0) { ctx_free(c); return fail(KOSK_E_NOMEM, "cudaMalloc failed for verifier scratch"); }
-        CU(cudaStreamCreateWithFlags(&ln.st, cudaStreamNonBlocking));
-        CU(cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming));
-        CU(cudaEventCreateWithFlags(&ln.computed, cudaEventDisableTiming));
-        CU(cudaEventCreateWithFlags(&ln.pre_tail, cudaEventDisableTiming));
+        CUC(cudaStreamCreateWithFlags(&ln.st, cudaStreamNonBlocking));
+        CUC(cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming));
+        CUC(cudaEventCreateWithFlags(&ln.computed, cudaEventDisableTiming));
+        CUC(cudaEventCreateWithFlags(&ln.pre_tail, cudaEventDisableTiming));
         { const char *e = getenv("KOSK_B200_VERIFY_SIDE");
           if (!e || atoi(e)) {
-              CU(cudaStreamCreateWithFlags(&ln.vside.st, cudaStreamNonBlocking));
-              CU(cudaEventCreateWithFlags(&ln.vside.fork, cudaEventDisableTiming));
-              CU(cudaEventCreateWithFlags(&ln.vside.join, cudaEventDisableTiming));
+              CUC(cudaStreamCreateWithFlags(&ln.vside.st, cudaStreamNonBlocking));
+              CUC(cudaEventCreateWithFlags(&ln.vside.fork, cudaEventDisableTiming));
+              CUC(cudaEventCreateWithFlags(&ln.vside.join, cudaEventDisableTiming));
           } }
     }
-    CU(cudaEventCreate(&c->ev_start));
-    CU(cudaDeviceSynchronize());
+    CUC(cudaEventCreate(&c->ev_start));
+    CUC(cudaDeviceSynchronize());
     *out = c;
     return KOSK_OK;
 }
 
-void kosk_b200_destroy(kosk_b200_ctx *c) { ctx_free(c); }
+void kosk_b200_destroy(kosk_b200_ctx *c)
+{
+    if (c && c->live_pools > 0) { fail(KOSK_E_ARG, "kosk_b200_destroy: the context still has preprocessing pools; destroy them first (context kept)"); return; }
+    ctx_free(c);
+}
 uint64_t kosk_b200_kernel_launches(const kosk_b200_ctx *c) { return c ? c->launches : 0; }
 int kosk_b200_sync(kosk_b200_ctx *c)
 {
     if (!c) return KOSK_E_ARG;
     CU(cudaSetDevice(c->device));
+    LOCK(c);
     for (Lane &ln : c->lanes) CU(cudaStreamSynchronize(ln.st));
-    int st = 0;
-    CU(cudaMemcpy(&st, c->d_status, 4, cudaMemcpyDeviceToHost));
-    if (st) return fail(KOSK_E_CUDA, "a kernel gave up waiting for its producer warps (internal error)");
-    return KOSK_OK;
+    if (c->wpool) wire_pool_wait_all(c->wpool);       // packed proofs still being expanded into the caller's buffers
+    for (Lane &ln : c->lanes) if (ln.wire_flag) { ln.wire_flag = 0; return fail(KOSK_E_CUDA, "a D2H slice of the compact wire path failed"); }
+    return check_status(c);
 }
 int kosk_b200_lanes(const kosk_b200_ctx *c) { return c ? (int)c->lanes.size() : 0; }
 
@@ -514,6 +568,14 @@ static int lanes_join(kosk_b200_ctx *c, cudaStream_t caller)
     return KOSK_OK;
 }
 
+// device allocation released on every return path of the component entry points
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes); }
+    template <typename T> T *as() const { return static_cast<T *>(p); }
+};
+
 // ---- generic component kernels ----
 __global__ void __launch_bounds__(128) k_ntt_rows(u16 *a)
 {
@@ -557,44 +619,116 @@ extern "C" {
 int kosk_b200_prove_batch_device(kosk_b200_ctx *c, size_t n, const uint8_t *d_seeds, uint8_t *d_pk, uint8_t *d_sk, uint8_t *d_pi, void *stream)
 {
     if (!c || !d_seeds || !d_pk || !d_sk || !d_pi) return fail(KOSK_E_ARG, "null argument");
+    if (((uintptr_t)d_seeds & 7) || ((uintptr_t)d_pi & 3)) return fail(KOSK_E_ARG, "misaligned device buffer (d_seeds: 8 bytes, d_pi: 4 bytes)");
+    LOCK(c);
     CU(cudaSetDevice(c->device));
     if (n == 0) return KOSK_OK;
     const Layout &L = c->L;
     int rc = lanes_fork(c, (cudaStream_t)stream); if (rc) return rc;
     const size_t sub = sub_batch(c, n);
-    size_t i = 0;
-    for (size_t o = 0; o < n; o += sub, i++) {
+    for (size_t o = 0; o < n && !rc; o += sub) {
         const int B = (int)std::min<size_t>(sub, n - o);
-        { Lane &ln = c->lanes[c->next_lane++ % c->lanes.size()]; rc = prove_chunk_k(c, ln, ln.pb, B, d_seeds + 32 * o, d_pk + L.pk_bytes * o, d_sk + L.sk_bytes * o, d_pi + L.proof_bytes * o, PH_OFFLINE | PH_ONLINE); }
-        if (rc) return rc;
+        Lane &ln = c->lanes[c->next_lane++ % c->lanes.size()];
+        rc = prove_chunk_k(c, ln, ln.pb, B, d_seeds + 32 * o, d_pk + L.pk_bytes * o, d_sk + L.sk_bytes * o, d_pi + L.proof_bytes * o, PH_OFFLINE | PH_ONLINE);
     }
-    return lanes_join(c, (cudaStream_t)stream);
+    // the caller's stream is ordered after whatever was enqueued on the lanes, also when a later sub-batch failed to launch
+    const int rj = lanes_join(c, (cudaStream_t)stream);
+    return rc ? rc : rj;
 }
 
 int kosk_b200_prove_batch(kosk_b200_ctx *c, size_t n, const uint8_t *seeds, uint8_t *pk, uint8_t *sk, uint8_t *pi)
 {
     int rc = kosk_b200_prove_batch_async(c, n, seeds, pk, sk, pi);
-    if (rc) return rc;
-    return kosk_b200_sync(c);
+    const int rs = c ? kosk_b200_sync(c) : KOSK_OK;      // also after a mid-batch error: nothing may still be writing the caller's buffers
+    return rc ? rc : rs;
+}
+
+// ---- compact wire format on the host-buffer paths (wire_kernels.cuh, wire_host.h) ----
+static int wire_wait_event(void *gate) { return cudaEventSynchronize((cudaEvent_t)gate) == cudaSuccess ? 0 : 1; }
+static int wire_default_threads()
+{
+    if (const char *e = getenv("KOSK_B200_WIRE_THREADS")) { const int t = atoi(e); if (t > 0) return t; }
+    const unsigned hc = std::thread::hardware_concurrency();
+    return (int)std::min(16u, std::max(2u, hc / 2));
+}
+// worker pool on first use; per lane the packed device buffer and (host_too) the pinned staging buffer with its slice events
+static int wire_ensure(kosk_b200_ctx *c, Lane *ln, bool host_too)
+{
+    const WireLayout W = make_wire_layout(c->k);
+    if (host_too && !c->wpool) c->wpool = wire_pool_create(c->wire_threads > 0 ? c->wire_threads : wire_default_threads(), wire_wait_event);
+    if (!ln) return KOSK_OK;
+    const size_t bytes = (size_t)c->chunk * W.wire_bytes;
+    if (!ln->d_wire) {
+        if (cudaMalloc((void **)&ln->d_wire, bytes) != cudaSuccess) { ln->d_wire = nullptr; return fail(KOSK_E_NOMEM, "cudaMalloc failed for the packed proofs"); }
+    }
+    if (host_too && !ln->h_wire) {
+        if (cudaHostAlloc((void **)&ln->h_wire, bytes, cudaHostAllocDefault) != cudaSuccess) { ln->h_wire = nullptr; return fail(KOSK_E_NOMEM, "cudaHostAlloc failed for the wire staging buffer"); }
+        const int nsl = (c->chunk + c->wire_slice - 1) / c->wire_slice;
+        ln->wev.resize(nsl);
+        for (cudaEvent_t &e : ln->wev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ln->h2d_done, cudaEventDisableTiming));
+    }
+    return KOSK_OK;
+}
+
+// packed = the caller keeps the compact bytes (out = wire[n][wire_bytes]); else out = pi[n][proof_bytes] in the reference layout
+static int prove_async_impl(kosk_b200_ctx *c, size_t n, const uint8_t *seeds, uint8_t *pk, uint8_t *sk, uint8_t *out, bool packed)
+{
+    if (!c || !seeds || !pk || !sk || !out) return fail(KOSK_E_ARG, "null argument");
+    LOCK(c);
+    CU(cudaSetDevice(c->device));
+    const Layout &L = c->L;
+    const WireLayout W = make_wire_layout(c->k);
+    // a handful of proofs is latency-bound: the pack kernel and the hand-over to a worker cost more than the bytes saved on the link
+    const bool wire = packed || (c->wire_mode != 0 && n >= 8);
+    const size_t sub = sub_batch(c, n);
+    for (size_t o = 0; o < n; o += sub) {
+        const int B = (int)std::min<size_t>(sub, n - o);
+        const size_t li = c->next_lane++ % c->lanes.size();
+        Lane &ln = c->lanes[li];
+        if (wire) {
+            int rc = wire_ensure(c, &ln, !packed); if (rc) return rc;
+            if (!packed) wire_pool_wait_group(c->wpool, (int)li);         // the lane's staging buffer has been expanded
+        }
+        CU(cudaMemcpyAsync(ln.d_seeds, seeds + 32 * o, 32 * (size_t)B, cudaMemcpyHostToDevice, ln.st));
+        int rc = prove_chunk_k(c, ln, ln.pb, B, ln.d_seeds, ln.d_pk, ln.d_sk, ln.d_pi, PH_OFFLINE | PH_ONLINE);
+        if (rc) return rc;
+        if (wire) { c->launches += wire_launch(true, ln.d_pi, ln.d_wire, c->k, B, ln.st); CU(cudaGetLastError()); }
+        CU(cudaMemcpyAsync(pk + L.pk_bytes * o, ln.d_pk, L.pk_bytes * (size_t)B, cudaMemcpyDeviceToHost, ln.st));
+        CU(cudaMemcpyAsync(sk + L.sk_bytes * o, ln.d_sk, L.sk_bytes * (size_t)B, cudaMemcpyDeviceToHost, ln.st));
+        if (!wire) {
+            CU(cudaMemcpyAsync(out + L.proof_bytes * o, ln.d_pi, L.proof_bytes * (size_t)B, cudaMemcpyDeviceToHost, ln.st));
+        } else if (packed) {
+            CU(cudaMemcpyAsync(out + W.wire_bytes * o, ln.d_wire, W.wire_bytes * (size_t)B, cudaMemcpyDeviceToHost, ln.st));
+        } else {
+            // the packed proofs cross the link in slices; the workers expand a slice into the caller's buffer as soon as its event fires,
+            // while the following slices are still on the link
+            for (int s0 = 0; s0 < B; s0 += c->wire_slice) {
+                const int ns = std::min(c->wire_slice, B - s0);
+                cudaEvent_t ev = ln.wev[s0 / c->wire_slice];
+                CU(cudaMemcpyAsync(ln.h_wire + W.wire_bytes * (size_t)s0, ln.d_wire + W.wire_bytes * (size_t)s0, W.wire_bytes * (size_t)ns, cudaMemcpyDeviceToHost, ln.st));
+                CU(cudaEventRecord(ev, ln.st));
+                for (int j = 0; j < ns; j += 2)
+                    wire_pool_submit(c->wpool, 0, c->k, (size_t)std::min(2, ns - j), ln.h_wire + W.wire_bytes * (size_t)(s0 + j), out + L.proof_bytes * (o + s0 + j), ev, (int)li, &ln.wire_flag);
+            }
+        }
+    }
+    return KOSK_OK;
 }
 
 int kosk_b200_prove_batch_async(kosk_b200_ctx *c, size_t n, const uint8_t *seeds, uint8_t *pk, uint8_t *sk, uint8_t *pi)
 {
-    if (!c || !seeds || !pk || !sk || !pi) return fail(KOSK_E_ARG, "null argument");
-    CU(cudaSetDevice(c->device));
-    const Layout &L = c->L;
-    const size_t sub = sub_batch(c, n);
-    for (size_t o = 0; o < n; o += sub) {
-        const int B = (int)std::min<size_t>(sub, n - o);
-        Lane &ln = c->lanes[c->next_lane++ % c->lanes.size()];
-        CU(cudaMemcpyAsync(ln.d_seeds, seeds + 32 * o, 32 * (size_t)B, cudaMemcpyHostToDevice, ln.st));
-        int rc = prove_chunk_k(c, ln, ln.pb, B, ln.d_seeds, ln.d_pk, ln.d_sk, ln.d_pi, PH_OFFLINE | PH_ONLINE);
-        if (rc) return rc;
-        CU(cudaMemcpyAsync(pk + L.pk_bytes * o, ln.d_pk, L.pk_bytes * (size_t)B, cudaMemcpyDeviceToHost, ln.st));
-        CU(cudaMemcpyAsync(sk + L.sk_bytes * o, ln.d_sk, L.sk_bytes * (size_t)B, cudaMemcpyDeviceToHost, ln.st));
-        CU(cudaMemcpyAsync(pi + L.proof_bytes * o, ln.d_pi, L.proof_bytes * (size_t)B, cudaMemcpyDeviceToHost, ln.st));
-    }
-    return KOSK_OK;
+    return prove_async_impl(c, n, seeds, pk, sk, pi, false);
+}
+int kosk_b200_prove_batch_packed_async(kosk_b200_ctx *c, size_t n, const uint8_t *seeds, uint8_t *pk, uint8_t *sk, uint8_t *wire)
+{
+    return prove_async_impl(c, n, seeds, pk, sk, wire, true);
+}
+int kosk_b200_prove_batch_packed(kosk_b200_ctx *c, size_t n, const uint8_t *seeds, uint8_t *pk, uint8_t *sk, uint8_t *wire)
+{
+    int rc = prove_async_impl(c, n, seeds, pk, sk, wire, true);
+    const int rs = c ? kosk_b200_sync(c) : KOSK_OK;
+    return rc ? rc : rs;
 }
 
 int kosk_b200_verifiable_keygen(kosk_b200_ctx *c, const uint8_t seed[32], uint8_t *pk, uint8_t *sk, uint8_t *pi)
@@ -605,38 +739,71 @@ int kosk_b200_verifiable_keygen(kosk_b200_ctx *c, const uint8_t seed[32], uint8_
 int kosk_b200_verify_batch_device(kosk_b200_ctx *c, size_t n, const uint8_t *d_pi, const uint8_t *d_pk, uint8_t *d_ok, void *stream)
 {
     if (!c || !d_pi || !d_pk || !d_ok) return fail(KOSK_E_ARG, "null argument");
+    if ((uintptr_t)d_pi & 3) return fail(KOSK_E_ARG, "misaligned device buffer (d_pi: 4 bytes)");
+    LOCK(c);
     CU(cudaSetDevice(c->device));
     if (n == 0) return KOSK_OK;
     const Layout &L = c->L;
     int rc = lanes_fork(c, (cudaStream_t)stream); if (rc) return rc;
     const size_t sub = sub_batch(c, n);
     size_t i = 0;
-    for (size_t o = 0; o < n; o += sub, i++) {
+    for (size_t o = 0; o < n && !rc; o += sub, i++) {
         const int B = (int)std::min<size_t>(sub, n - o);
         rc = verify_chunk_lane(c, c->lanes[i % c->lanes.size()], B, d_pi + L.proof_bytes * o, d_pk + L.pk_bytes * o, d_ok + o);
-        if (rc) return rc;
     }
-    return lanes_join(c, (cudaStream_t)stream);
+    const int rj = lanes_join(c, (cudaStream_t)stream);
+    return rc ? rc : rj;
+}
+
+// packed: in = wire[n][wire_bytes]; else in = pi[n][proof_bytes] (reference layout), packed on the host when the wire mode is on
+static int verify_batch_impl(kosk_b200_ctx *c, size_t n, const uint8_t *in, const uint8_t *pk, uint8_t *ok, bool packed)
+{
+    if (!c || !in || !pk || !ok) return fail(KOSK_E_ARG, "null argument");
+    LOCK(c);
+    CU(cudaSetDevice(c->device));
+    const Layout &L = c->L;
+    const WireLayout W = make_wire_layout(c->k);
+    // a single proof is latency-bound: packing it on the host costs more than the 145 KB it saves on the link
+    const bool wire = packed || (c->wire_mode != 0 && n >= 8);
+    const size_t sub = sub_batch(c, n);
+    size_t i = 0;
+    int rc = KOSK_OK;
+    for (size_t o = 0; o < n && !rc; o += sub, i++) {
+        const int B = (int)std::min<size_t>(sub, n - o);
+        Lane &ln = c->lanes[i % c->lanes.size()];
+        bool raw = !wire;
+        if (wire) {
+            rc = wire_ensure(c, &ln, !packed); if (rc) break;
+            if (!packed) {
+                if (ln.h2d_pending) { CU(cudaEventSynchronize(ln.h2d_done)); ln.h2d_pending = false; }      // the previous copy out of the staging buffer
+                // a proof with a u16 >= 4096 has no wire image: such a sub-batch crosses the link in the reference layout (same verdicts)
+                raw = wire_pool_run(c->wpool, 1, c->k, (size_t)B, in + L.proof_bytes * o, ln.h_wire) != 0;
+            }
+        }
+        if (raw) {
+            CU(cudaMemcpyAsync(ln.d_pi, in + L.proof_bytes * o, L.proof_bytes * (size_t)B, cudaMemcpyHostToDevice, ln.st));
+        } else {
+            CU(cudaMemcpyAsync(ln.d_wire, packed ? in + W.wire_bytes * o : ln.h_wire, W.wire_bytes * (size_t)B, cudaMemcpyHostToDevice, ln.st));
+            if (!packed) { CU(cudaEventRecord(ln.h2d_done, ln.st)); ln.h2d_pending = true; }
+            c->launches += wire_launch(false, ln.d_wire, ln.d_pi, c->k, B, ln.st);
+        }
+        CU(cudaMemcpyAsync(ln.d_pk, pk + L.pk_bytes * o, L.pk_bytes * (size_t)B, cudaMemcpyHostToDevice, ln.st));
+        rc = verify_chunk_lane(c, ln, B, ln.d_pi, ln.d_pk, ln.d_ok);
+        if (rc) break;
+        CU(cudaMemcpyAsync(ok + o, ln.d_ok, (size_t)B, cudaMemcpyDeviceToHost, ln.st));
+    }
+    for (Lane &ln : c->lanes) { cudaError_t e = cudaStreamSynchronize(ln.st); if (e != cudaSuccess && !rc) rc = fail(KOSK_E_CUDA, cudaGetErrorString(e)); ln.h2d_pending = false; }
+    if (rc) return rc;
+    return check_status(c);
 }
 
 int kosk_b200_verify_batch(kosk_b200_ctx *c, size_t n, const uint8_t *pi, const uint8_t *pk, uint8_t *ok)
 {
-    if (!c || !pi || !pk || !ok) return fail(KOSK_E_ARG, "null argument");
-    CU(cudaSetDevice(c->device));
-    const Layout &L = c->L;
-    const size_t sub = sub_batch(c, n);
-    size_t i = 0;
-    for (size_t o = 0; o < n; o += sub, i++) {
-        const int B = (int)std::min<size_t>(sub, n - o);
-        Lane &ln = c->lanes[i % c->lanes.size()];
-        CU(cudaMemcpyAsync(ln.d_pi, pi + L.proof_bytes * o, L.proof_bytes * (size_t)B, cudaMemcpyHostToDevice, ln.st));
-        CU(cudaMemcpyAsync(ln.d_pk, pk + L.pk_bytes * o, L.pk_bytes * (size_t)B, cudaMemcpyHostToDevice, ln.st));
-        int rc = verify_chunk_lane(c, ln, B, ln.d_pi, ln.d_pk, ln.d_ok);
-        if (rc) return rc;
-        CU(cudaMemcpyAsync(ok + o, ln.d_ok, (size_t)B, cudaMemcpyDeviceToHost, ln.st));
-    }
-    for (Lane &ln : c->lanes) CU(cudaStreamSynchronize(ln.st));
-    return KOSK_OK;
+    return verify_batch_impl(c, n, pi, pk, ok, false);
+}
+int kosk_b200_verify_batch_packed(kosk_b200_ctx *c, size_t n, const uint8_t *wire, const uint8_t *pk, uint8_t *ok)
+{
+    return verify_batch_impl(c, n, wire, pk, ok, true);
 }
 
 int kosk_b200_kosk_verify(kosk_b200_ctx *c, const uint8_t *pi, const uint8_t *pk)
@@ -645,6 +812,67 @@ int kosk_b200_kosk_verify(kosk_b200_ctx *c, const uint8_t *pi, const uint8_t *pk
     int rc = kosk_b200_verify_batch(c, 1, pi, pk, &ok);
     return rc ? rc : (int)ok;
 }
+
+size_t kosk_b200_wire_bytes(int k) { return (k >= 2 && k <= 4) ? make_wire_layout(k).wire_bytes : 0; }
+
+int kosk_b200_set_wire(kosk_b200_ctx *c, int mode, int threads)
+{
+    if (!c || mode < 0 || mode > 1) return fail(KOSK_E_ARG, "bad argument");
+    LOCK(c);
+    int rc = kosk_b200_sync(c); if (rc) return rc;
+    c->wire_mode = mode;
+    if (threads > 0 && threads != c->wire_threads) { c->wire_threads = threads; wire_pool_destroy(c->wpool); c->wpool = nullptr; }
+    return KOSK_OK;
+}
+int kosk_b200_wire_info(const kosk_b200_ctx *c, int *mode, int *threads, const char **simd)
+{
+    if (!c) return fail(KOSK_E_ARG, "null argument");
+    if (mode) *mode = c->wire_mode;
+    if (threads) *threads = c->wpool ? wire_pool_threads(c->wpool) : (c->wire_threads > 0 ? c->wire_threads : wire_default_threads());
+    if (simd) *simd = wire_simd_name();
+    return KOSK_OK;
+}
+
+int kosk_b200_wire_pack_device(kosk_b200_ctx *c, size_t n, const uint8_t *d_pi, uint8_t *d_wire, void *stream)
+{
+    if (!c || !d_pi || !d_wire || ((uintptr_t)d_pi & 3) || ((uintptr_t)d_wire & 15)) return fail(KOSK_E_ARG, "null or misaligned argument (d_pi: 4 bytes, d_wire: 16 bytes)");
+    LOCK(c);
+    CU(cudaSetDevice(c->device));
+    for (size_t o = 0; o < n; o += 32768) c->launches += wire_launch(true, d_pi + c->L.proof_bytes * o, d_wire + make_wire_layout(c->k).wire_bytes * o, c->k, (int)std::min<size_t>(32768, n - o), (cudaStream_t)stream);
+    CU(cudaGetLastError());
+    return KOSK_OK;
+}
+int kosk_b200_wire_unpack_device(kosk_b200_ctx *c, size_t n, const uint8_t *d_wire, uint8_t *d_pi, void *stream)
+{
+    if (!c || !d_pi || !d_wire || ((uintptr_t)d_pi & 3) || ((uintptr_t)d_wire & 15)) return fail(KOSK_E_ARG, "null or misaligned argument (d_pi: 4 bytes, d_wire: 16 bytes)");
+    LOCK(c);
+    CU(cudaSetDevice(c->device));
+    for (size_t o = 0; o < n; o += 32768) c->launches += wire_launch(false, d_wire + make_wire_layout(c->k).wire_bytes * o, d_pi + c->L.proof_bytes * o, c->k, (int)std::min<size_t>(32768, n - o), (cudaStream_t)stream);
+    CU(cudaGetLastError());
+    return KOSK_OK;
+}
+
+// host codec, no context and no device: wire[n][wire_bytes] <-> pi[n][proof_bytes]; threads <= 1 runs on the calling thread
+static int wire_host_run(int kind, int k, size_t n, const uint8_t *src, uint8_t *dst, int threads)
+{
+    if (k < 2 || k > 4 || !src || !dst) return fail(KOSK_E_ARG, "bad argument");
+    const WireLayout W = make_wire_layout(k);
+    if (threads <= 1 || n < 2) {
+        int bad = 0;
+        for (size_t i = 0; i < n; i++) {
+            if (kind == 0) wire_unpack_proof(k, src + i * W.wire_bytes, dst + i * W.proof_bytes);
+            else bad |= wire_pack_proof(k, src + i * W.proof_bytes, dst + i * W.wire_bytes);
+        }
+        return bad ? fail(KOSK_E_ARG, "a proof holds a u16 >= 4096 and has no wire image") : KOSK_OK;
+    }
+    WirePool *p = wire_pool_create(threads, nullptr);
+    const int bad = wire_pool_run(p, kind, k, n, src, dst);
+    wire_pool_destroy(p);
+    return bad ? fail(KOSK_E_ARG, "a proof holds a u16 >= 4096 and has no wire image") : KOSK_OK;
+}
+int kosk_b200_wire_pack(int k, size_t n, const uint8_t *pi, uint8_t *wire, int threads) { return wire_host_run(1, k, n, pi, wire, threads); }
+int kosk_b200_wire_unpack(int k, size_t n, const uint8_t *wire, uint8_t *pi, int threads) { return wire_host_run(0, k, n, wire, pi, threads); }
+const char *kosk_b200_wire_simd(void) { return wire_simd_name(); }
 
 // ---- offline / online split ----
 struct kosk_b200_pool {
@@ -656,9 +884,14 @@ struct kosk_b200_pool {
 void kosk_b200_pool_destroy(kosk_b200_pool *p)
 {
     if (!p) return;
+    LOCK(p->ctx);
     cudaSetDevice(p->ctx->device);
     cudaStreamSynchronize(p->ctx->lanes[0].st);
+    if (p->d_seeds) cudaMemset(p->d_seeds, 0, 32 * p->n);
+    if (p->d_sk) cudaMemset(p->d_sk, 0, p->ctx->L.sk_bytes * p->n);
+    scrub_prove_bufs(p->pb, p->ctx->sl, p->ctx->k, p->n);
     free_prove_bufs(p->pb);
+    p->ctx->live_pools--;
     void *lp[] = {p->d_seeds, p->d_pk, p->d_sk, p->d_pi};
     for (void *q : lp) if (q) cudaFree(q);
     delete p;
@@ -667,16 +900,17 @@ void kosk_b200_pool_destroy(kosk_b200_pool *p)
 int kosk_b200_pool_create(kosk_b200_ctx *c, size_t n, const uint8_t *seeds, kosk_b200_pool **out)
 {
     if (!c || !seeds || !out || n == 0 || n > 16384) return fail(KOSK_E_ARG, "bad argument (1 <= n <= 16384)");
+    LOCK(c);
     CU(cudaSetDevice(c->device));
-    kosk_b200_pool *p = new kosk_b200_pool; p->ctx = c; p->n = n;
+    kosk_b200_pool *p = new kosk_b200_pool; p->ctx = c; p->n = n; c->live_pools++;
     if (alloc_prove_bufs(p->pb, c->sl, c->k, n, c->use_tensor != 0) != 0 || cudaMalloc((void **)&p->d_seeds, 32 * n) != cudaSuccess) {
         kosk_b200_pool_destroy(p); return fail(KOSK_E_NOMEM, "cudaMalloc failed for the preprocessing pool");
     }
     Lane &ln = c->lanes[0];
-    CU(cudaMemcpyAsync(p->d_seeds, seeds, 32 * n, cudaMemcpyHostToDevice, ln.st));
+    if (cudaMemcpyAsync(p->d_seeds, seeds, 32 * n, cudaMemcpyHostToDevice, ln.st) != cudaSuccess) { kosk_b200_pool_destroy(p); return fail(KOSK_E_CUDA, "seed copy failed"); }
     int rc = prove_chunk_k(c, ln, p->pb, (int)n, p->d_seeds, nullptr, nullptr, nullptr, PH_OFFLINE);
     if (rc) { kosk_b200_pool_destroy(p); return rc; }
-    CU(cudaStreamSynchronize(ln.st));
+    if (cudaStreamSynchronize(ln.st) != cudaSuccess) { kosk_b200_pool_destroy(p); return fail(KOSK_E_CUDA, "preprocessing failed"); }
     *out = p;
     return KOSK_OK;
 }
@@ -685,6 +919,7 @@ int kosk_b200_pool_prove(kosk_b200_pool *p, uint8_t *pk, uint8_t *sk, uint8_t *p
 {
     if (!p || !pk || !sk || !pi) return fail(KOSK_E_ARG, "null argument");
     kosk_b200_ctx *c = p->ctx;
+    LOCK(c);
     CU(cudaSetDevice(c->device));
     const Layout &L = c->L; const size_t n = p->n;
     if (!p->d_pi) {
@@ -704,6 +939,7 @@ int kosk_b200_pool_prove(kosk_b200_pool *p, uint8_t *pk, uint8_t *sk, uint8_t *p
 int kosk_b200_share_eval_device(kosk_b200_ctx *c, size_t n, const uint16_t *d_y, uint16_t *d_planes, void *stream)
 {
     if (!c || !d_y || !d_planes) return fail(KOSK_E_ARG, "null argument");
+    LOCK(c);
     CU(cudaSetDevice(c->device));
     if (c->use_tensor && c->tmp_rows < n) {       // grow-only scratch for the limb planes of the caller's rows
         if (c->tmpL0) { cudaFree(c->tmpL0); cudaFree(c->tmpL1); c->tmpL0 = c->tmpL1 = nullptr; }
@@ -722,17 +958,18 @@ int kosk_b200_share_eval_device(kosk_b200_ctx *c, size_t n, const uint16_t *d_y,
 int kosk_b200_share_eval(kosk_b200_ctx *c, size_t n, const uint16_t *y, uint16_t *shares)
 {
     if (!c || !y || !shares) return fail(KOSK_E_ARG, "null argument");
+    LOCK(c);
     CU(cudaSetDevice(c->device));
-    u16 *dy = nullptr, *dp = nullptr;
+    DevBuf by, bp;
     std::vector<u16> hy(n * YLD, 0), hp(n * SLD);
     for (size_t r = 0; r < n; r++) memcpy(&hy[r * YLD], y + r * D1, D1 * 2);
-    CU(cudaMalloc(&dy, hy.size() * 2 + 16)); CU(cudaMalloc(&dp, hp.size() * 2 + 16));
+    CU(by.alloc(hy.size() * 2 + 16)); CU(bp.alloc(hp.size() * 2 + 16));
+    u16 *dy = by.as<u16>(), *dp = bp.as<u16>();
     CU(cudaMemcpy(dy, hy.data(), hy.size() * 2, cudaMemcpyHostToDevice));
     int rc = kosk_b200_share_eval_device(c, n, dy, dp, c->lanes[0].st);
-    if (!rc) { cudaError_t e = cudaStreamSynchronize(c->lanes[0].st); if (e != cudaSuccess) rc = fail(KOSK_E_CUDA, cudaGetErrorString(e)); }
-    if (!rc) { cudaError_t e = cudaMemcpy(hp.data(), dp, hp.size() * 2, cudaMemcpyDeviceToHost); if (e != cudaSuccess) rc = fail(KOSK_E_CUDA, cudaGetErrorString(e)); }
-    cudaFree(dy); cudaFree(dp);
     if (rc) return rc;
+    CU(cudaStreamSynchronize(c->lanes[0].st));
+    CU(cudaMemcpy(hp.data(), dp, hp.size() * 2, cudaMemcpyDeviceToHost));
     for (size_t r = 0; r < n; r++) memcpy(shares + r * NP, &hp[r * SLD + SOFF], NP * 2);
     return KOSK_OK;
 }
@@ -740,36 +977,37 @@ int kosk_b200_share_eval(kosk_b200_ctx *c, size_t n, const uint16_t *y, uint16_t
 int kosk_b200_sha3_256_rows(kosk_b200_ctx *c, size_t n, size_t len, const uint8_t *in, uint8_t *out)
 {
     if (!c || !in || !out || n == 0) return fail(KOSK_E_ARG, "bad argument");
+    LOCK(c);
     CU(cudaSetDevice(c->device));
-    u8 *di = nullptr, *dout = nullptr;
-    CU(cudaMalloc(&di, n * len + 16)); CU(cudaMalloc(&dout, n * 32));
+    DevBuf bi, bo;
+    CU(bi.alloc(n * len + 16)); CU(bo.alloc(n * 32));
+    u8 *di = bi.as<u8>(), *dout = bo.as<u8>();
     CU(cudaMemcpy(di, in, n * len, cudaMemcpyHostToDevice));
     k_sha3_rows<<<(unsigned)((n + 63) / 64), 64, 0, c->lanes[0].st>>>(di, dout, n, len); c->launches++;
-    cudaError_t e = cudaStreamSynchronize(c->lanes[0].st);
-    if (e == cudaSuccess) e = cudaMemcpy(out, dout, n * 32, cudaMemcpyDeviceToHost);
-    cudaFree(di); cudaFree(dout);
-    if (e != cudaSuccess) return fail(KOSK_E_CUDA, cudaGetErrorString(e));
+    CU(cudaStreamSynchronize(c->lanes[0].st));
+    CU(cudaMemcpy(out, dout, n * 32, cudaMemcpyDeviceToHost));
     return KOSK_OK;
 }
 
 int kosk_b200_ntt_rows(kosk_b200_ctx *c, size_t n, uint16_t *a)
 {
     if (!c || !a || n == 0) return fail(KOSK_E_ARG, "bad argument");
+    LOCK(c);
     CU(cudaSetDevice(c->device));
-    u16 *d = nullptr;
-    CU(cudaMalloc(&d, n * 512));
+    DevBuf bd;
+    CU(bd.alloc(n * 512));
+    u16 *d = bd.as<u16>();
     CU(cudaMemcpy(d, a, n * 512, cudaMemcpyHostToDevice));
     k_ntt_rows<<<(unsigned)n, 128, 0, c->lanes[0].st>>>(d); c->launches++;
-    cudaError_t e = cudaStreamSynchronize(c->lanes[0].st);
-    if (e == cudaSuccess) e = cudaMemcpy(a, d, n * 512, cudaMemcpyDeviceToHost);
-    cudaFree(d);
-    if (e != cudaSuccess) return fail(KOSK_E_CUDA, cudaGetErrorString(e));
+    CU(cudaStreamSynchronize(c->lanes[0].st));
+    CU(cudaMemcpy(a, d, n * 512, cudaMemcpyDeviceToHost));
     return KOSK_OK;
 }
 
 int kosk_b200_debug_fetch(kosk_b200_ctx *c, const char *what, void *out, size_t bytes)
 {
     if (!c || !what || !out) return fail(KOSK_E_ARG, "null argument");
+    LOCK(c);
     CU(cudaSetDevice(c->device));
     CU(cudaDeviceSynchronize());
     const Slots &sl = c->sl;
@@ -795,6 +1033,7 @@ int kosk_b200_debug_fetch(kosk_b200_ctx *c, const char *what, void *out, size_t 
 int kosk_b200_debug_trace(kosk_b200_ctx *c, double *out, int max_triples)
 {
     if (!c || !out) return fail(KOSK_E_ARG, "null argument");
+    LOCK(c);
     CU(cudaSetDevice(c->device));
     CU(cudaDeviceSynchronize());
     int n = 0;
@@ -812,6 +1051,7 @@ int kosk_b200_debug_trace(kosk_b200_ctx *c, double *out, int max_triples)
 int kosk_b200_set_strict(kosk_b200_ctx *c, int on)
 {
     if (!c) return fail(KOSK_E_ARG, "null argument");
+    LOCK(c);
     for (Lane &ln : c->lanes) ln.vb.strict = on != 0;
     return KOSK_OK;
 }
@@ -819,6 +1059,7 @@ int kosk_b200_set_strict(kosk_b200_ctx *c, int on)
 int kosk_b200_set_profiling(kosk_b200_ctx *c, int on)
 {
     if (!c) return fail(KOSK_E_ARG, "null argument");
+    LOCK(c);
     c->prof = on != 0;
     return KOSK_OK;
 }
@@ -826,6 +1067,7 @@ int kosk_b200_set_profiling(kosk_b200_ctx *c, int on)
 int kosk_b200_phase_times(kosk_b200_ctx *c, double *ms, uint64_t *calls, int n, int reset)
 {
     if (!c || !ms || !calls) return fail(KOSK_E_ARG, "null argument");
+    LOCK(c);
     CU(cudaSetDevice(c->device));
     CU(cudaDeviceSynchronize());
     prof_collect(c);

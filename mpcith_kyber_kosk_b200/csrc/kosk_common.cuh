@@ -60,6 +60,30 @@ KOSK_HD Layout make_layout(int k)
     return L;
 }
 
+// ---- compact wire format of a proof: the same fields in the same order, field elements as 12 bits ----
+// struct mpcith_proof is u16 field elements (and the u16 party indices I) around two byte arrays (Tcomm, comm).  On the wire the
+// two u16 runs A = [f .. gamma] and B = [I .. u_e] are packed two elements per three bytes, little-endian like kyber/poly.c:124-139
+// (b0 = a0, b1 = a0 >> 8 | a1 << 4, b2 = a1 >> 4), the digests are copied, every segment starts 16-byte aligned:
+//   wire = pack12(A) | pad | Tcomm[NR][32] | pack12(B) | pad | comm[NR][32]          519 136 / 531 616 / 578 992 bytes for K = 2 / 3 / 4
+// Every u16 < 4096 is representable (all canonical proofs are); decoding is the exact inverse.
+struct WireLayout {
+    uint32_t nA, nB;                       // u16 elements of the two runs (both even for K = 2, 3, 4)
+    size_t o_A, o_Tcomm, o_B, o_comm, proof_bytes;    // byte offsets in struct mpcith_proof
+    size_t w_A, w_Tcomm, w_B, w_comm, wire_bytes;     // byte offsets on the wire
+};
+KOSK_HD WireLayout make_wire_layout(int k)
+{
+    const Layout L = make_layout(k);
+    WireLayout W;
+    W.o_A = 0; W.o_Tcomm = L.o_Tcomm; W.o_B = L.o_I; W.o_comm = L.o_comm; W.proof_bytes = L.proof_bytes;
+    W.nA = (uint32_t)(L.o_Tcomm / 2); W.nB = (uint32_t)((L.o_comm - L.o_I) / 2);
+    const size_t HB = (size_t)NR * 32;
+    auto al = [](size_t x) { return (x + 15) & ~(size_t)15; };
+    W.w_A = 0; W.w_Tcomm = al(((size_t)W.nA + 1) / 2 * 3); W.w_B = W.w_Tcomm + HB;
+    W.w_comm = al(W.w_B + ((size_t)W.nB + 1) / 2 * 3); W.wire_bytes = al(W.w_comm + HB);
+    return W;
+}
+
 // ---- plane map: every per-party u16 quantity of one proof lives in plane[slot][party] ----
 // Slots < n2 are sharings produced by the share-evaluation kernel from a Y row (256 secrets | 151 tail);
 // the first n1 of them have no dependence on the Fiat-Shamir challenge and go through one launch.

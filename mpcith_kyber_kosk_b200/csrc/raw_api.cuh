@@ -149,6 +149,8 @@ template <int K> static void launch_keygen(const ProveBufs &pb, cudaStream_t st)
 static int raw_begin(kosk_b200_ctx *c, Lane *&ln, ProveBufs &pb)
 {
     CU(cudaSetDevice(c->device));
+    // the DRBG addresses randombytes() calls with LE32(call number): refuse to come near the wrap instead of replaying randomness
+    if (c->raw->calls > 0x7FF00000u) return fail(KOSK_E_ARG, "DRBG call counter exhausted: re-seed with kosk_b200_rng_reset");
     int rc = raw_prepare(c, *c->raw); if (rc) return rc;
     ln = &c->lanes[0];
     CU(cudaStreamSynchronize(ln->st));
@@ -166,6 +168,7 @@ size_t kosk_b200_range_proof_bytes(int k) { return (k >= 2 && k <= 4) ? raw_size
 int kosk_b200_rng_reset(kosk_b200_ctx *c, const uint8_t seed[32])
 {
     if (!c || !seed) return fail(KOSK_E_ARG, "null argument");
+    LOCK(c);
     memcpy(c->raw->seed, seed, 32); c->raw->calls = 0;
     return KOSK_OK;
 }
@@ -176,6 +179,7 @@ uint32_t kosk_b200_rng_calls(const kosk_b200_ctx *c) { return c ? c->raw->calls 
 int kosk_b200_verifiable_keygen_rng(kosk_b200_ctx *c, uint8_t *pk, uint8_t *sk, uint8_t *pi)
 {
     if (!c || !pk || !sk || !pi) return fail(KOSK_E_ARG, "null argument");
+    LOCK(c);
     Lane *ln; ProveBufs pb; int rc = raw_begin(c, ln, pb); if (rc) return rc;
     RawState &rs = *c->raw;
     const int base = (int)rs.calls;
@@ -193,6 +197,7 @@ int kosk_b200_verifiable_keygen_rng(kosk_b200_ctx *c, uint8_t *pk, uint8_t *sk, 
 int kosk_b200_prepare_randomness(kosk_b200_ctx *c, void *rand_image)
 {
     if (!c || !rand_image) return fail(KOSK_E_ARG, "null argument");
+    LOCK(c);
     Lane *ln; ProveBufs pb; int rc = raw_begin(c, ln, pb); if (rc) return rc;
     const Slots &sl = c->sl; const RawSizes sz = raw_sizes(c->k); RawState &rs = *c->raw;
     pb.cb_rand = (int)rs.calls; pb.tails_mask = 1;
@@ -211,6 +216,7 @@ int kosk_b200_prepare_randomness(kosk_b200_ctx *c, void *rand_image)
 int kosk_b200_prepare_range_proof(kosk_b200_ctx *c, void *eta_image)
 {
     if (!c || !eta_image) return fail(KOSK_E_ARG, "null argument");
+    LOCK(c);
     Lane *ln; ProveBufs pb; int rc = raw_begin(c, ln, pb); if (rc) return rc;
     const Slots &sl = c->sl; const RawSizes sz = raw_sizes(c->k); RawState &rs = *c->raw;
     pb.cb_eta = (int)rs.calls; pb.tails_mask = 2;
@@ -227,6 +233,7 @@ int kosk_b200_prepare_range_proof(kosk_b200_ctx *c, void *eta_image)
 int kosk_b200_keygen(kosk_b200_ctx *c, uint8_t *pk, uint8_t *sk, void *inst_image)
 {
     if (!c || !pk || !sk) return fail(KOSK_E_ARG, "null argument");
+    LOCK(c);
     Lane *ln; ProveBufs pb; int rc = raw_begin(c, ln, pb); if (rc) return rc;
     const RawSizes sz = raw_sizes(c->k); RawState &rs = *c->raw;
     pb.cb_key = (int)rs.calls;
@@ -245,6 +252,7 @@ int kosk_b200_keygen(kosk_b200_ctx *c, uint8_t *pk, uint8_t *sk, void *inst_imag
 int kosk_b200_prove(kosk_b200_ctx *c, uint8_t *pi, const void *inst_image, const void *rand_image, const void *eta_image)
 {
     if (!c || !pi || !inst_image || !rand_image || !eta_image) return fail(KOSK_E_ARG, "null argument");
+    LOCK(c);
     Lane *ln; ProveBufs pb; int rc = raw_begin(c, ln, pb); if (rc) return rc;
     const Slots &sl = c->sl; const RawSizes sz = raw_sizes(c->k); RawState &rs = *c->raw;
     CU(cudaMemcpyAsync(rs.d_rand, rand_image, sz.rand, cudaMemcpyHostToDevice, ln->st));
@@ -266,13 +274,22 @@ int kosk_b200_prove(kosk_b200_ctx *c, uint8_t *pi, const void *inst_image, const
 int kosk_b200_verify(kosk_b200_ctx *c, const uint8_t *pi, const void *inst_image)
 {
     if (!c || !pi || !inst_image) return fail(KOSK_E_ARG, "null argument");
+    LOCK(c);
     CU(cudaSetDevice(c->device));
     Lane &ln = c->lanes[0];
     const int K = c->k;
     // A and t as the verifier consumes them: encode_to_gf3329 of the int16 coefficients (mlwe_verifier.cpp:289, :358)
     const int16_t *inst = static_cast<const int16_t *>(inst_image);
     std::vector<u16> at((size_t)(K * K + K) * 256);
-    for (size_t i = 0; i < at.size(); i++) { int v = inst[i] % Q; at[i] = (u16)(v < 0 ? v + Q : v); }
+    // encode_to_gf3329 (gf3329.c:308-310) only adds q to negative values.  A enters products, where the reference's u16 % q arithmetic makes
+    // the reduction of that u16 neutral; t is COMPARED with recomputed canonical shares (mlwe_verifier.cpp:358-376), so it must stay
+    // unreduced: an instance whose t has non-canonical coefficients is rejected, as in the reference.
+    const size_t nA = (size_t)K * K * 256;
+    for (size_t i = 0; i < at.size(); i++) {
+        const int v = inst[i];
+        const u16 enc = (u16)(v < 0 ? v + Q : v);
+        at[i] = i < nA ? (u16)(enc % Q) : enc;
+    }
     CU(cudaStreamSynchronize(ln.st));
     CU(cudaMemcpyAsync(ln.vb.AH, at.data(), (size_t)K * K * 512, cudaMemcpyHostToDevice, ln.st));
     CU(cudaMemcpyAsync(ln.vb.TPK, at.data() + (size_t)K * K * 256, (size_t)K * 512, cudaMemcpyHostToDevice, ln.st));
