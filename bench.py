@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--lanes", type=int, default=1, help="pipeline lanes (CUDA streams with their own scratch) of the device-resident run")
     ap.add_argument("--e2e-lanes", type=int, default=2, help="lanes of the host-buffer (e2e) run: the D2H copies of one step overlap the kernels of the next")
     ap.add_argument("--wire-threads", type=int, default=0, help="host worker threads per rank expanding wire images (0 = cpus / local ranks, 2..16)")
+    ap.add_argument("--wire-percent", default="", help="comma list of packed shares (0..100) the e2e calibration tries (default 0,50,75,100)")
     ap.add_argument("--cpu-sample", type=int, default=8, help="proofs of the bounded single-core CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-tensor-probe", action="store_true", help="skip the short measurement of the opt-in tensor-core path")
@@ -270,39 +271,41 @@ def run_b200(args):
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
     wire_threads = args.wire_threads or max(2, min(16, len(os.sched_getaffinity(0)) // max(1, local_world)))
 
-    def e2e_run(fn_name, outsel):
+    def e2e_run(fn_name, steps):
         fn = getattr(ctx_e.lib, fn_name)
 
         def e2e_step(s):
             o = h_out[s % 2]
-            rc = fn(ctx_e._h, B, h_seeds[s].data_ptr(), o[0].data_ptr(), o[1].data_ptr(), o[outsel].data_ptr())
+            rc = fn(ctx_e._h, B, h_seeds[s % len(h_seeds)].data_ptr(), o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr())
             assert rc == 0, ctx_e.lib.kosk_b200_last_error()
-        e2e_step(args.steps); ctx_e.sync()
+        for w in range(max(2, args.e2e_lanes)):             # every lane (and its staging buffers) has run once
+            e2e_step(args.steps - w)
+        ctx_e.sync()
         barrier()
         t0 = time.perf_counter()
-        for s in range(args.steps):
+        for s in range(steps):
             e2e_step(s)
         ctx_e.sync()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        t = torch.tensor([dt / steps], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-    e2e_modes = {}
-    ctx_e.set_wire(0)
-    e2e_modes["raw"] = e2e_run("kosk_b200_prove_batch_async", 2)
-    ctx_e.set_wire(1, wire_threads)
-    e2e_modes["wire"] = e2e_run("kosk_b200_prove_batch_async", 2)
-    e2e_link = min(e2e_modes, key=e2e_modes.get)
-    if e2e_link != "wire":                                  # leave the headline mode's bytes in h_out for the checks below
-        ctx_e.set_wire(0)
-        e2e_modes["raw"] = min(e2e_modes["raw"], e2e_run("kosk_b200_prove_batch_async", 2))
-    e2e_max = e2e_modes[e2e_link]
+        return float(t.item())                              # seconds per step, max over ranks
+    # calibration: which share of the proofs should travel packed on THIS host (link bytes vs host memory bandwidth); short runs
+    cal_steps = max(3, args.steps // 4)
+    e2e_cal = {}
+    for pct in ([int(x) for x in args.wire_percent.split(",")] if args.wire_percent else [0, 50, 75, 100]):
+        ctx_e.set_wire(pct, wire_threads)
+        e2e_cal[pct] = e2e_run("kosk_b200_prove_batch_async", cal_steps)
+    wire_pct = min(e2e_cal, key=e2e_cal.get)
+    ctx_e.set_wire(wire_pct, wire_threads)
+    e2e_step_s = e2e_run("kosk_b200_prove_batch_async", args.steps)
+    e2e_max = e2e_step_s * args.steps
     h_pk, h_sk, h_pi = h_out[(args.steps - 1) % 2]
     h_pi_copy = h_pi.clone()
     # the caller keeps the compact bytes (kosk_b200_prove_batch_packed_async): same buffers, only wire_bytes per proof are written
-    e2e_packed = e2e_run("kosk_b200_prove_batch_packed_async", 2)
+    e2e_packed = e2e_run("kosk_b200_prove_batch_packed_async", args.steps) * args.steps
     h_wire_last = h_pi[:B * ctx_e.wire_bytes].clone().pin_memory()
     h_pi.copy_(h_pi_copy)
 
@@ -334,34 +337,38 @@ def run_b200(args):
         # end to end: proofs and public keys in pinned HOST buffers (reference layout), accept bits back on the host, through
         # kosk_b200_verify_batch (synchronous; its sub-batches alternate over two lanes so the H2D of one overlaps the kernels of the
         # previous one); link = raw struct bytes vs 12-bit wire images packed by the host workers; and the packed API
-        ctx_v = KoskContext(k, local, max(1, B // 4), 2)
-        h_ok = torch.zeros(B, dtype=torch.uint8).pin_memory()
-        vsteps = max(2, args.steps // 2)
+        ctx_v = KoskContext(k, local, B, 2)
+        h_oks = [torch.zeros(B, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        vsteps = max(4, args.steps // 2)
 
-        def verify_e2e(fn_name, src):
+        def verify_e2e(fn_name, src, steps):
             fn = getattr(ctx_v.lib, fn_name)
-            assert fn(ctx_v._h, B, src.data_ptr(), h_pk.data_ptr(), h_ok.data_ptr()) == 0
+            for w in range(2):
+                assert fn(ctx_v._h, B, src.data_ptr(), h_pk.data_ptr(), h_oks[w].data_ptr()) == 0
+            ctx_v.sync()
             barrier()
             t0v = time.perf_counter()
-            for _ in range(vsteps):
-                assert fn(ctx_v._h, B, src.data_ptr(), h_pk.data_ptr(), h_ok.data_ptr()) == 0
+            for s_ in range(steps):
+                assert fn(ctx_v._h, B, src.data_ptr(), h_pk.data_ptr(), h_oks[s_ % 2].data_ptr()) == 0
+            ctx_v.sync()
             dtv = time.perf_counter() - t0v
-            assert bool(h_ok.all())
+            assert bool(h_oks[0].all()) and bool(h_oks[1].all())
             tt = torch.tensor([dtv], dtype=torch.float64, device=dev)
             if world > 1:
                 dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            return world * B * vsteps / float(tt.item())
+            return world * B * steps / float(tt.item())
         ve = {}
-        ctx_v.set_wire(0)
-        ve["raw"] = verify_e2e("kosk_b200_verify_batch", h_pi)
-        ctx_v.set_wire(1, wire_threads)
-        ve["wire"] = verify_e2e("kosk_b200_verify_batch", h_pi)
-        ve_packed = verify_e2e("kosk_b200_verify_batch_packed", h_wire_last)
-        vlink = max(ve, key=ve.get)
-        verify_stats["e2e"] = {"value": ve[vlink], "unit": "verifies/s", "link": vlink, "by_link": ve,
-                               "h2d_bytes_per_step": B * (npk + (ctx_v.wire_bytes if vlink == "wire" else npi)), "d2h_bytes_per_step": B,
+        for pct in e2e_cal:
+            ctx_v.set_wire(pct, wire_threads)
+            ve[pct] = verify_e2e("kosk_b200_verify_batch_async", h_pi, max(3, vsteps // 2))
+        vpct = max(ve, key=ve.get)
+        ctx_v.set_wire(vpct, wire_threads)
+        ve_best = verify_e2e("kosk_b200_verify_batch_async", h_pi, vsteps)
+        ve_packed = verify_e2e("kosk_b200_verify_batch_packed_async", h_wire_last, vsteps)
+        verify_stats["e2e"] = {"value": ve_best, "unit": "verifies/s", "wire_percent": vpct, "calibration_verifies_per_s": {str(p_): v for p_, v in ve.items()},
+                               "h2d_bytes_per_step": B * npk + (B * vpct // 100) * ctx_v.wire_bytes + (B - B * vpct // 100) * npi, "d2h_bytes_per_step": B,
                                "packed_api": {"value": ve_packed, "unit": "verifies/s", "h2d_bytes_per_step": B * (npk + ctx_v.wire_bytes)},
-                               "api": "kosk_b200_verify_batch (host buffers in the reference layout, pinned; chunk B/4 x 2 lanes)"}
+                               "api": "kosk_b200_verify_batch_async + kosk_b200_sync (host buffers in the reference layout, pinned; 2 lanes: the H2D of one call overlaps the kernels of the previous one)"}
         ctx_v.close()
 
     # ---- single-proof latency (BASELINE configs[2]): host API, one seed in -> pk, sk, proof out / proof in -> accept bit out
@@ -445,9 +452,10 @@ def run_b200(args):
                        "kyber_k": k, "batch_per_gpu": B, "chunk": chunk, "lanes": args.lanes, "parallelism": f"proof-sharded x{world}, no collective",
                        "l2": f"per-step working set {B * (npi + 1_500_000) / 1e6:.0f} MB >> 126 MB L2, fresh seeds every step"},
             "e2e": {"value": world * B * args.steps / e2e_max, "unit": "proofs/s", "h2d_bytes_per_step": B * 32,
-                    "d2h_bytes_per_step": B * (npk + nsk + (ctx_e.wire_bytes if e2e_link == "wire" else npi)),
-                    "lanes": args.e2e_lanes, "link": e2e_link, "wire_threads": wire_threads, "wire_simd": ctx_e.wire_info()["simd"],
-                    "by_link": {m: world * B * args.steps / v for m, v in e2e_modes.items()},
+                    "d2h_bytes_per_step": B * (npk + nsk) + (B * wire_pct // 100) * ctx_e.wire_bytes + (B - B * wire_pct // 100) * npi,
+                    "lanes": args.e2e_lanes, "link": f"{wire_pct}% of the proofs as 12-bit wire images, the rest as struct bytes",
+                    "wire_percent": wire_pct, "wire_threads": wire_threads, "wire_simd": ctx_e.wire_info()["simd"],
+                    "calibration_proofs_per_s": {str(p_): world * B / v for p_, v in e2e_cal.items()}, "calibration_steps": cal_steps,
                     "packed_api": {"value": world * B * args.steps / e2e_packed, "unit": "proofs/s", "d2h_bytes_per_step": B * (npk + nsk + ctx_e.wire_bytes),
                                    "api": "kosk_b200_prove_batch_packed_async: the caller keeps the 12-bit wire images"},
                     "api": "kosk_b200_prove_batch_async + kosk_b200_sync (host buffers in the reference layout, pinned; step i+1 computes while step i copies out)"},

@@ -76,6 +76,10 @@ int kosk_b200_verify_batch(kosk_b200_ctx *ctx, size_t n, const uint8_t *pi, cons
  * alternate over the lanes: their kernels run back to back while the D2H copy of one overlaps the kernels of the next.
  * Host buffers must stay valid (and should be pinned) until kosk_b200_sync returns. */
 int kosk_b200_prove_batch_async(kosk_b200_ctx *ctx, size_t n, const uint8_t *seeds, uint8_t *pk, uint8_t *sk, uint8_t *pi);
+/* Asynchronous form of verify_batch: the H2D of one call's proofs overlaps the kernels of the previous call on the other lane;
+ * ok[] is valid after kosk_b200_sync().  pi / pk / ok must stay valid until then (pi may be reused as soon as the call returns
+ * when the wire mode packed it into the context's staging buffer, but do not rely on it). */
+int kosk_b200_verify_batch_async(kosk_b200_ctx *ctx, size_t n, const uint8_t *pi, const uint8_t *pk, uint8_t *ok);
 
 /* Compact wire format.  struct mpcith_proof (mlwe_prover.hpp:57-75) stores every GF(3329) element and every
  * party index as a uint16_t; encode_mpcith_proof (mlwe_prover.cpp:540-543) is a memcpy of it.  The wire image holds the same
@@ -86,18 +90,24 @@ int kosk_b200_prove_batch_async(kosk_b200_ctx *ctx, size_t n, const uint8_t *see
  * fields are all < 4096 has a wire image (every proof a prover emits does); decoding is the exact inverse.
  *
  * The host-buffer batch calls above move proofs over PCIe, which bounds them (one B200 proves faster than a Gen5 x16 link
- * carries 664 KB proofs).  With the wire mode on (default; KOSK_B200_WIRE=0 or kosk_b200_set_wire(ctx, 0, 0) turns it off) they
- * pack on the device, copy the compact bytes in slices into a pinned staging buffer and expand them into the caller's pi[]
- * (reference layout, unchanged; the buffer need not be pinned) on `threads` host worker threads while later slices are still
- * on the link; verify_batch packs on those threads and unpacks on the device.  A sub-batch containing a proof with a u16 >= 4096
- * travels in the reference layout instead (same verdicts).  Calls with fewer than 8 proofs always use the reference layout.
+ * carries 664 KB proofs).  In wire mode (default 100; KOSK_B200_WIRE=<percent> or kosk_b200_set_wire) `percent` of the proofs
+ * cross the link as wire images: prove packs on the device, copies the compact bytes in slices into a pinned staging buffer and
+ * expands them into the caller's pi[] (reference layout, unchanged) on `threads` host worker threads while later slices are
+ * still on the link; verify_batch packs on those threads and unpacks on the device.  The remaining proofs cross it as struct
+ * bytes straight between the caller's buffer and the device, which costs the host nothing: the link favours 100, a host short
+ * of memory bandwidth something lower (bench.py calibrates it), 0 is the round-1 behaviour.  The caller-visible bytes are the
+ * same for every setting.  A verify sub-batch containing a proof with a u16 >= 4096 travels as struct bytes (same verdicts).
+ * Calls with fewer than 8 proofs always use struct bytes (latency).
  * The *_packed calls hand the compact bytes to / take them from the caller: wire[n][wire_bytes]. */
 size_t kosk_b200_wire_bytes(int kyber_k);
-int kosk_b200_set_wire(kosk_b200_ctx *ctx, int mode /* 0 | 1 */, int threads /* 0 = keep / default (KOSK_B200_WIRE_THREADS) */);
+int kosk_b200_set_wire(kosk_b200_ctx *ctx, int percent /* 0..100 */, int threads /* 0 = keep / default (KOSK_B200_WIRE_THREADS) */);
 int kosk_b200_wire_info(const kosk_b200_ctx *ctx, int *mode, int *threads, const char **simd);
+/* instrumentation: out[4] = {ns the gate thread waited for D2H slices, slices, ns summed over the workers spent converting, proofs converted} */
+int kosk_b200_wire_stats(kosk_b200_ctx *ctx, uint64_t *out, int reset);
 int kosk_b200_prove_batch_packed(kosk_b200_ctx *ctx, size_t n, const uint8_t *seeds, uint8_t *pk, uint8_t *sk, uint8_t *wire);
 int kosk_b200_prove_batch_packed_async(kosk_b200_ctx *ctx, size_t n, const uint8_t *seeds, uint8_t *pk, uint8_t *sk, uint8_t *wire);
 int kosk_b200_verify_batch_packed(kosk_b200_ctx *ctx, size_t n, const uint8_t *wire, const uint8_t *pk, uint8_t *ok);
+int kosk_b200_verify_batch_packed_async(kosk_b200_ctx *ctx, size_t n, const uint8_t *wire, const uint8_t *pk, uint8_t *ok);
 /* device-resident conversion, enqueued on `stream`: d_pi 4-byte aligned, d_wire 16-byte aligned */
 int kosk_b200_wire_pack_device(kosk_b200_ctx *ctx, size_t n, const uint8_t *d_pi, uint8_t *d_wire, void *stream);
 int kosk_b200_wire_unpack_device(kosk_b200_ctx *ctx, size_t n, const uint8_t *d_wire, uint8_t *d_pi, void *stream);
@@ -177,6 +187,13 @@ int kosk_b200_kem_dec(kosk_b200_ctx *ctx, uint8_t *ss, const uint8_t *ct, const 
 int kosk_b200_share_eval(kosk_b200_ctx *ctx, size_t n, const uint16_t *y, uint16_t *shares);
 int kosk_b200_sha3_256_rows(kosk_b200_ctx *ctx, size_t n, size_t len, const uint8_t *in, uint8_t *out);
 int kosk_b200_ntt_rows(kosk_b200_ctx *ctx, size_t n, uint16_t *a);
+/* recon_rows: recon_secrets_ddeg (degree2 = 0, ss.cpp:37-54: shares[n][407] of parties 0..406) or recon_secrets_2ddeg (degree2 = 1,
+ * ss.cpp:56-73: shares[n][813] of parties 0..812) -> secrets[n][256].
+ * interp_rows: the verifier's interpolation through the rest-party nodes (NTL interpolate + eval, mlwe_verifier.cpp:188-224, :510-543):
+ * opened[150] = the opened parties; row r holds the shares of the first 407 (813) rest parties in ascending party order; out[n][407]
+ * = the interpolant at x = 0..406 (degree2 = 0) or out[n][256] = at x = 0..255 (degree2 = 1).  n <= 4096. */
+int kosk_b200_recon_rows(kosk_b200_ctx *ctx, int degree2, size_t n, const uint16_t *shares, uint16_t *secrets);
+int kosk_b200_interp_rows(kosk_b200_ctx *ctx, int degree2, const uint16_t *opened, size_t n, const uint16_t *shares, uint16_t *out);
 /* device-resident share_eval for benchmarking: d_y[n][416] (zero padded rows), d_planes[n][1456] */
 int kosk_b200_share_eval_device(kosk_b200_ctx *ctx, size_t n, const uint16_t *d_y, uint16_t *d_planes, void *stream);
 

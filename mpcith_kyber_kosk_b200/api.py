@@ -15,13 +15,14 @@ EXPORTS = [
     "kosk_b200_pk_bytes", "kosk_b200_sk_bytes", "kosk_b200_proof_bytes", "kosk_b200_last_error", "kosk_b200_version",
     "kosk_b200_create", "kosk_b200_create_ex", "kosk_b200_lanes", "kosk_b200_destroy", "kosk_b200_verifiable_keygen", "kosk_b200_kosk_verify",
     "kosk_b200_prove_batch", "kosk_b200_prove_batch_async", "kosk_b200_verify_batch", "kosk_b200_prove_batch_device", "kosk_b200_verify_batch_device",
-    "kosk_b200_share_eval", "kosk_b200_sha3_256_rows", "kosk_b200_ntt_rows", "kosk_b200_share_eval_device",
+    "kosk_b200_share_eval", "kosk_b200_recon_rows", "kosk_b200_interp_rows", "kosk_b200_sha3_256_rows", "kosk_b200_ntt_rows", "kosk_b200_share_eval_device",
     "kosk_b200_kernel_launches", "kosk_b200_debug_fetch", "kosk_b200_debug_trace", "kosk_b200_sync",
     "kosk_b200_inst_bytes", "kosk_b200_randomness_bytes", "kosk_b200_range_proof_bytes", "kosk_b200_rng_reset", "kosk_b200_rng_calls", "kosk_b200_verifiable_keygen_rng",
     "kosk_b200_prepare_randomness", "kosk_b200_prepare_range_proof", "kosk_b200_keygen", "kosk_b200_prove", "kosk_b200_verify",
     "kosk_b200_ct_bytes", "kosk_b200_kem_enc_derand_batch", "kosk_b200_kem_dec_batch", "kosk_b200_kem_enc_derand_batch_device", "kosk_b200_kem_dec_batch_device",
     "kosk_b200_kem_enc", "kosk_b200_kem_dec", "kosk_b200_kem_keypair_derand_batch", "kosk_b200_kem_keypair",
-    "kosk_b200_wire_bytes", "kosk_b200_set_wire", "kosk_b200_wire_info", "kosk_b200_prove_batch_packed", "kosk_b200_prove_batch_packed_async", "kosk_b200_verify_batch_packed",
+    "kosk_b200_wire_bytes", "kosk_b200_set_wire", "kosk_b200_wire_info", "kosk_b200_wire_stats", "kosk_b200_prove_batch_packed", "kosk_b200_prove_batch_packed_async", "kosk_b200_verify_batch_packed",
+    "kosk_b200_verify_batch_async", "kosk_b200_verify_batch_packed_async",
     "kosk_b200_wire_pack_device", "kosk_b200_wire_unpack_device", "kosk_b200_wire_pack", "kosk_b200_wire_unpack", "kosk_b200_wire_simd",
     "kosk_b200_pool_create", "kosk_b200_pool_prove", "kosk_b200_pool_destroy", "kosk_b200_set_strict", "kosk_b200_set_profiling", "kosk_b200_phase_times", "kosk_b200_int_peak",
 ]
@@ -62,6 +63,8 @@ def load_library(path=None):
     lib.kosk_b200_prove_batch_device.argtypes = [vp, sz, u8p, u8p, u8p, u8p, vp]
     lib.kosk_b200_verify_batch_device.argtypes = [vp, sz, u8p, u8p, u8p, vp]
     lib.kosk_b200_share_eval.argtypes = [vp, sz, u8p, u8p]
+    lib.kosk_b200_recon_rows.argtypes = [vp, i32, sz, u8p, u8p]
+    lib.kosk_b200_interp_rows.argtypes = [vp, i32, u8p, sz, u8p, u8p]
     lib.kosk_b200_sha3_256_rows.argtypes = [vp, sz, sz, u8p, u8p]
     lib.kosk_b200_ntt_rows.argtypes = [vp, sz, u8p]
     lib.kosk_b200_share_eval_device.argtypes = [vp, sz, u8p, u8p, vp]
@@ -95,9 +98,12 @@ def load_library(path=None):
     lib.kosk_b200_kem_dec.argtypes = [vp, u8p, u8p, u8p]
     lib.kosk_b200_set_wire.argtypes = [vp, i32, i32]
     lib.kosk_b200_wire_info.argtypes = [vp, ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(ctypes.c_char_p)]
+    lib.kosk_b200_wire_stats.argtypes = [vp, u8p, i32]
     lib.kosk_b200_prove_batch_packed.argtypes = [vp, sz, u8p, u8p, u8p, u8p]
     lib.kosk_b200_prove_batch_packed_async.argtypes = [vp, sz, u8p, u8p, u8p, u8p]
     lib.kosk_b200_verify_batch_packed.argtypes = [vp, sz, u8p, u8p, u8p]
+    lib.kosk_b200_verify_batch_async.argtypes = [vp, sz, u8p, u8p, u8p]
+    lib.kosk_b200_verify_batch_packed_async.argtypes = [vp, sz, u8p, u8p, u8p]
     lib.kosk_b200_wire_pack_device.argtypes = [vp, sz, u8p, u8p, vp]
     lib.kosk_b200_wire_unpack_device.argtypes = [vp, sz, u8p, u8p, vp]
     lib.kosk_b200_wire_pack.argtypes = [i32, sz, u8p, u8p, i32]
@@ -327,14 +333,19 @@ class KoskContext:
         return ok.astype(bool)
 
     # ---- compact wire format ----
-    def set_wire(self, mode=1, threads=0):
-        """Host-buffer batch calls move proofs over the link as 12-bit wire images (1, default) or as struct bytes (0)."""
-        self._check(self.lib.kosk_b200_set_wire(self._h, int(mode), int(threads)), "set_wire")
+    def set_wire(self, percent=100, threads=0):
+        """Share (0..100 %) of the proofs that the host-buffer batch calls move over the link as 12-bit wire images; the rest as struct bytes."""
+        self._check(self.lib.kosk_b200_set_wire(self._h, int(percent), int(threads)), "set_wire")
 
     def wire_info(self):
         m, t, sname = ctypes.c_int(), ctypes.c_int(), ctypes.c_char_p()
         self._check(self.lib.kosk_b200_wire_info(self._h, ctypes.byref(m), ctypes.byref(t), ctypes.byref(sname)), "wire_info")
         return {"mode": m.value, "threads": t.value, "simd": (sname.value or b"").decode()}
+
+    def wire_stats(self, reset=True):
+        out = np.zeros(4, np.uint64)
+        self._check(self.lib.kosk_b200_wire_stats(self._h, _ptr(out), 1 if reset else 0), "wire_stats")
+        return {"gate_wait_ms": float(out[0]) / 1e6, "slices": int(out[1]), "worker_ms_total": float(out[2]) / 1e6, "proofs": int(out[3])}
 
     def prove_batch_packed(self, seeds, out=None):
         """prove_batch whose proofs come back as compact wire images: returns (pk, sk, wire[n][wire_bytes])."""
@@ -382,6 +393,23 @@ class KoskContext:
         y = np.ascontiguousarray(y, dtype=np.uint16).reshape(-1, 407)
         out = np.empty((y.shape[0], 1454), np.uint16)
         self._check(self.lib.kosk_b200_share_eval(self._h, y.shape[0], _ptr(y), _ptr(out)), "share_eval")
+        return out
+
+    def recon_rows(self, shares, degree2=False):
+        """recon_secrets_ddeg / _2ddeg (ss.cpp:37-73) on rows of 407 / 813 party shares -> 256 secrets each."""
+        nn = 813 if degree2 else 407
+        shares = np.ascontiguousarray(shares, dtype=np.uint16).reshape(-1, nn)
+        out = np.empty((shares.shape[0], 256), np.uint16)
+        self._check(self.lib.kosk_b200_recon_rows(self._h, 1 if degree2 else 0, shares.shape[0], _ptr(shares), _ptr(out)), "recon_rows")
+        return out
+
+    def interp_rows(self, opened, shares, degree2=False):
+        """The verifier's interpolation through the first 407 / 813 rest-party nodes, evaluated at 0..406 / 0..255."""
+        nn, nt = (813, 256) if degree2 else (407, 407)
+        opened = np.ascontiguousarray(opened, dtype=np.uint16).reshape(150)
+        shares = np.ascontiguousarray(shares, dtype=np.uint16).reshape(-1, nn)
+        out = np.empty((shares.shape[0], nt), np.uint16)
+        self._check(self.lib.kosk_b200_interp_rows(self._h, 1 if degree2 else 0, _ptr(opened), shares.shape[0], _ptr(shares), _ptr(out)), "interp_rows")
         return out
 
     def sha3_256_rows(self, rows):

@@ -13,7 +13,7 @@ LIB = os.path.join(HERE, "libkosk_b200.so")
 SOURCES = ["kosk_b200.cu"]
 HOST_SOURCES = ["wire_host.cpp"]          # host-only code (SIMD byte codec + worker pool of the compact wire format): g++, linked into the same library
 HEADERS = ["kosk_common.cuh", "keccak.cuh", "gf_gemm.cuh", "gf_gemm_imma.cuh", "prove_kernels.cuh", "verify_kernels.cuh", "raw_api.cuh", "kem_kernels.cuh", "share_ntt.cuh",
-           "wire_kernels.cuh", "wire_host.h"]
+           "wire_kernels.cuh", "wire_host.h", "component_api.cuh"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared", "-cudart", "static",

@@ -15,6 +15,9 @@
 #include <string>
 #include <vector>
 #include <mutex>
+#include <memory>
+#include <atomic>
+#include <chrono>
 #include <thread>
 #include <algorithm>
 #include <utility>
@@ -85,6 +88,7 @@ struct Lane {
     // one event per D2H slice (the unpack workers wait on it), and the event after the lane's latest H2D from h_wire
     u8 *d_wire = nullptr, *h_wire = nullptr;
     std::vector<cudaEvent_t> wev;
+    std::unique_ptr<std::atomic<int>[]> wctr;      // per slice: unpack jobs still reading that slice of h_wire
     cudaEvent_t h2d_done = nullptr; bool h2d_pending = false;
     volatile int wire_flag = 0;                    // set by a worker whose event wait failed
 };
@@ -119,9 +123,10 @@ struct kosk_b200_ctx {
     double phase_ms[KOSK_NPHASE] = {0}; uint64_t phase_calls[KOSK_NPHASE] = {0};
     RawState *raw = nullptr;               // struct-level API (raw_api.cuh): DRBG state and staging buffers
     KemState *kem = nullptr;               // Kyber KEM encaps / decaps (kem_kernels.cuh)
-    // Host-buffer batch calls: 0 = the proofs cross the link as struct mpcith_proof bytes (one cudaMemcpyAsync per buffer, round-1 behaviour),
-    // 1 = as the compact wire format, packed / unpacked on the device and expanded / packed by the worker pool on the host
-    int wire_mode = 1, wire_threads = 0, wire_slice = 64;
+    // Host-buffer batch calls: wire_mode = percentage of the proofs that cross the link in the compact wire format (packed / unpacked on the
+    // device, expanded / packed by the worker pool on the host); the others cross it as struct mpcith_proof bytes straight between the
+    // caller's buffer and the device (round-1 behaviour = 0).  The link favours 100, a host short of memory bandwidth something lower.
+    int wire_mode = 100, wire_threads = 0, wire_slice = 16, wire_acc = 0;
     WirePool *wpool = nullptr;
     int live_pools = 0;                    // preprocessing pools created from this context and not yet destroyed
     std::recursive_mutex mu;               // one caller at a time: the lanes' scratch and the DRBG state are per context
@@ -259,7 +264,7 @@ int kosk_b200_create_ex(kosk_b200_ctx **out, int k, int device, int max_chunk, i
     { const char *e = getenv("KOSK_B200_OVERLAP_FS1"); if (e) c->overlap_fs1 = atoi(e); }
     { const char *e = getenv("KOSK_B200_SHARE_NTT"); if (e) c->use_ntt = atoi(e); }
     if (c->use_tensor) c->use_ntt = 0;
-    { const char *e = getenv("KOSK_B200_WIRE"); if (e) c->wire_mode = atoi(e) ? 1 : 0; }
+    { const char *e = getenv("KOSK_B200_WIRE"); if (e) c->wire_mode = std::min(100, std::max(0, atoi(e))); }
     { const char *e = getenv("KOSK_B200_WIRE_SLICE"); if (e && atoi(e) > 0) c->wire_slice = atoi(e); }
     const Slots &sl = c->sl; const Layout &L = c->L;
     const size_t B = (size_t)c->chunk;
@@ -644,29 +649,43 @@ int kosk_b200_prove_batch(kosk_b200_ctx *c, size_t n, const uint8_t *seeds, uint
 }
 
 // ---- compact wire format on the host-buffer paths (wire_kernels.cuh, wire_host.h) ----
-static int wire_wait_event(void *gate) { return cudaEventSynchronize((cudaEvent_t)gate) == cudaSuccess ? 0 : 1; }
+// the gate thread polls: a blocking-sync event makes the copy engine raise an interrupt per slice (measured: +1 ms per 64 slices of link
+// idle time), a spinning cudaEventSynchronize burns a core that the unpack workers need
+static int wire_wait_event(void *gate)
+{
+    for (;;) {
+        const cudaError_t e = cudaEventQuery((cudaEvent_t)gate);
+        if (e == cudaSuccess) return 0;
+        if (e != cudaErrorNotReady) return 1;
+        std::this_thread::sleep_for(std::chrono::microseconds(20));
+    }
+}
 static int wire_default_threads()
 {
     if (const char *e = getenv("KOSK_B200_WIRE_THREADS")) { const int t = atoi(e); if (t > 0) return t; }
     const unsigned hc = std::thread::hardware_concurrency();
     return (int)std::min(16u, std::max(2u, hc / 2));
 }
-// worker pool on first use; per lane the packed device buffer and (host_too) the pinned staging buffer with its slice events
-static int wire_ensure(kosk_b200_ctx *c, Lane *ln, bool host_too)
+// worker pool on first use; for every lane the packed device buffer and (host_too) the pinned staging buffer with its slice events.
+// All lanes at once: pinning half a gigabyte takes a quarter of a second, which must not land in the middle of a pipelined run.
+static int wire_ensure(kosk_b200_ctx *c, bool host_too)
 {
     const WireLayout W = make_wire_layout(c->k);
     if (host_too && !c->wpool) c->wpool = wire_pool_create(c->wire_threads > 0 ? c->wire_threads : wire_default_threads(), wire_wait_event);
-    if (!ln) return KOSK_OK;
     const size_t bytes = (size_t)c->chunk * W.wire_bytes;
-    if (!ln->d_wire) {
-        if (cudaMalloc((void **)&ln->d_wire, bytes) != cudaSuccess) { ln->d_wire = nullptr; return fail(KOSK_E_NOMEM, "cudaMalloc failed for the packed proofs"); }
-    }
-    if (host_too && !ln->h_wire) {
-        if (cudaHostAlloc((void **)&ln->h_wire, bytes, cudaHostAllocDefault) != cudaSuccess) { ln->h_wire = nullptr; return fail(KOSK_E_NOMEM, "cudaHostAlloc failed for the wire staging buffer"); }
-        const int nsl = (c->chunk + c->wire_slice - 1) / c->wire_slice;
-        ln->wev.resize(nsl);
-        for (cudaEvent_t &e : ln->wev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        CU(cudaEventCreateWithFlags(&ln->h2d_done, cudaEventDisableTiming));
+    for (Lane &ln : c->lanes) {
+        if (!ln.d_wire) {
+            if (cudaMalloc((void **)&ln.d_wire, bytes) != cudaSuccess) { ln.d_wire = nullptr; return fail(KOSK_E_NOMEM, "cudaMalloc failed for the packed proofs"); }
+        }
+        if (host_too && !ln.h_wire) {
+            if (cudaHostAlloc((void **)&ln.h_wire, bytes, cudaHostAllocDefault) != cudaSuccess) { ln.h_wire = nullptr; return fail(KOSK_E_NOMEM, "cudaHostAlloc failed for the wire staging buffer"); }
+            const int nsl = (c->chunk + c->wire_slice - 1) / c->wire_slice;
+            ln.wev.resize(nsl);
+            for (cudaEvent_t &e : ln.wev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            ln.wctr.reset(new std::atomic<int>[nsl]);
+            for (int i = 0; i < nsl; i++) ln.wctr[i].store(0);
+            CU(cudaEventCreateWithFlags(&ln.h2d_done, cudaEventDisableTiming));
+        }
     }
     return KOSK_OK;
 }
@@ -687,12 +706,13 @@ static int prove_async_impl(kosk_b200_ctx *c, size_t n, const uint8_t *seeds, ui
         const size_t li = c->next_lane++ % c->lanes.size();
         Lane &ln = c->lanes[li];
         if (wire) {
-            int rc = wire_ensure(c, &ln, !packed); if (rc) return rc;
-            if (!packed) wire_pool_wait_group(c->wpool, (int)li);         // the lane's staging buffer has been expanded
+            int rc = wire_ensure(c, !packed); if (rc) return rc;
         }
+        wire_pool_trace(c->wpool, 10, li);
         CU(cudaMemcpyAsync(ln.d_seeds, seeds + 32 * o, 32 * (size_t)B, cudaMemcpyHostToDevice, ln.st));
         int rc = prove_chunk_k(c, ln, ln.pb, B, ln.d_seeds, ln.d_pk, ln.d_sk, ln.d_pi, PH_OFFLINE | PH_ONLINE);
         if (rc) return rc;
+        wire_pool_trace(c->wpool, 11, li);
         if (wire) { c->launches += wire_launch(true, ln.d_pi, ln.d_wire, c->k, B, ln.st); CU(cudaGetLastError()); }
         CU(cudaMemcpyAsync(pk + L.pk_bytes * o, ln.d_pk, L.pk_bytes * (size_t)B, cudaMemcpyDeviceToHost, ln.st));
         CU(cudaMemcpyAsync(sk + L.sk_bytes * o, ln.d_sk, L.sk_bytes * (size_t)B, cudaMemcpyDeviceToHost, ln.st));
@@ -701,16 +721,27 @@ static int prove_async_impl(kosk_b200_ctx *c, size_t n, const uint8_t *seeds, ui
         } else if (packed) {
             CU(cudaMemcpyAsync(out + W.wire_bytes * o, ln.d_wire, W.wire_bytes * (size_t)B, cudaMemcpyDeviceToHost, ln.st));
         } else {
-            // the packed proofs cross the link in slices; the workers expand a slice into the caller's buffer as soon as its event fires,
-            // while the following slices are still on the link
+            // the proofs cross the link in slices.  A packed slice lands in the staging buffer and the workers expand it into the caller's
+            // buffer as soon as its event fires, while the following slices are still on the link; a raw slice (error-diffused share of
+            // 100 - wire_mode percent) goes straight from d_pi to the caller's buffer and costs the host nothing.
             for (int s0 = 0; s0 < B; s0 += c->wire_slice) {
                 const int ns = std::min(c->wire_slice, B - s0);
-                cudaEvent_t ev = ln.wev[s0 / c->wire_slice];
+                c->wire_acc += c->wire_mode;
+                if (c->wire_acc < 100) {
+                    CU(cudaMemcpyAsync(out + L.proof_bytes * (o + s0), ln.d_pi + L.proof_bytes * (size_t)s0, L.proof_bytes * (size_t)ns, cudaMemcpyDeviceToHost, ln.st));
+                    continue;
+                }
+                c->wire_acc -= 100;
+                const int si = s0 / c->wire_slice;
+                cudaEvent_t ev = ln.wev[si];
+                // the kernels of this sub-batch are already enqueued; only the copy into a slice of the staging buffer waits until the
+                // workers have expanded what the lane's previous sub-batch left there
+                wire_pool_wait_counter(c->wpool, &ln.wctr[si]);
                 CU(cudaMemcpyAsync(ln.h_wire + W.wire_bytes * (size_t)s0, ln.d_wire + W.wire_bytes * (size_t)s0, W.wire_bytes * (size_t)ns, cudaMemcpyDeviceToHost, ln.st));
                 CU(cudaEventRecord(ev, ln.st));
-                for (int j = 0; j < ns; j += 2)
-                    wire_pool_submit(c->wpool, 0, c->k, (size_t)std::min(2, ns - j), ln.h_wire + W.wire_bytes * (size_t)(s0 + j), out + L.proof_bytes * (o + s0 + j), ev, (int)li, &ln.wire_flag);
+                wire_pool_submit(c->wpool, ev, 0, c->k, (size_t)ns, 1, ln.h_wire + W.wire_bytes * (size_t)s0, out + L.proof_bytes * (o + s0), &ln.wctr[si], &ln.wire_flag);
             }
+            wire_pool_trace(c->wpool, 12, li);
         }
     }
     return KOSK_OK;
@@ -756,7 +787,7 @@ int kosk_b200_verify_batch_device(kosk_b200_ctx *c, size_t n, const uint8_t *d_p
 }
 
 // packed: in = wire[n][wire_bytes]; else in = pi[n][proof_bytes] (reference layout), packed on the host when the wire mode is on
-static int verify_batch_impl(kosk_b200_ctx *c, size_t n, const uint8_t *in, const uint8_t *pk, uint8_t *ok, bool packed)
+static int verify_batch_impl(kosk_b200_ctx *c, size_t n, const uint8_t *in, const uint8_t *pk, uint8_t *ok, bool packed, bool async)
 {
     if (!c || !in || !pk || !ok) return fail(KOSK_E_ARG, "null argument");
     LOCK(c);
@@ -766,32 +797,35 @@ static int verify_batch_impl(kosk_b200_ctx *c, size_t n, const uint8_t *in, cons
     // a single proof is latency-bound: packing it on the host costs more than the 145 KB it saves on the link
     const bool wire = packed || (c->wire_mode != 0 && n >= 8);
     const size_t sub = sub_batch(c, n);
-    size_t i = 0;
     int rc = KOSK_OK;
-    for (size_t o = 0; o < n && !rc; o += sub, i++) {
+    for (size_t o = 0; o < n && !rc; o += sub) {
         const int B = (int)std::min<size_t>(sub, n - o);
-        Lane &ln = c->lanes[i % c->lanes.size()];
-        bool raw = !wire;
-        if (wire) {
-            rc = wire_ensure(c, &ln, !packed); if (rc) break;
-            if (!packed) {
-                if (ln.h2d_pending) { CU(cudaEventSynchronize(ln.h2d_done)); ln.h2d_pending = false; }      // the previous copy out of the staging buffer
-                // a proof with a u16 >= 4096 has no wire image: such a sub-batch crosses the link in the reference layout (same verdicts)
-                raw = wire_pool_run(c->wpool, 1, c->k, (size_t)B, in + L.proof_bytes * o, ln.h_wire) != 0;
+        Lane &ln = c->lanes[c->next_lane++ % c->lanes.size()];
+        // proofs [0, np) of the sub-batch travel packed, [np, B) as struct bytes straight from the caller's buffer (that copy is enqueued
+        // first, so it is on the link while the workers pack)
+        int np = !wire ? 0 : packed ? B : (int)((size_t)B * c->wire_mode / 100);
+        if (wire) { rc = wire_ensure(c, !packed); if (rc) break; }
+        if (!packed && np < B)
+            CU(cudaMemcpyAsync(ln.d_pi + L.proof_bytes * (size_t)np, in + L.proof_bytes * (o + np), L.proof_bytes * (size_t)(B - np), cudaMemcpyHostToDevice, ln.st));
+        if (np > 0 && !packed) {
+            if (ln.h2d_pending) { CU(cudaEventSynchronize(ln.h2d_done)); ln.h2d_pending = false; }      // the previous copy out of the staging buffer
+            // a proof with a u16 >= 4096 has no wire image: such a sub-batch crosses the link in the reference layout (same verdicts)
+            if (wire_pool_run(c->wpool, 1, c->k, (size_t)np, in + L.proof_bytes * o, ln.h_wire) != 0) {
+                CU(cudaMemcpyAsync(ln.d_pi, in + L.proof_bytes * o, L.proof_bytes * (size_t)np, cudaMemcpyHostToDevice, ln.st));
+                np = 0;
             }
         }
-        if (raw) {
-            CU(cudaMemcpyAsync(ln.d_pi, in + L.proof_bytes * o, L.proof_bytes * (size_t)B, cudaMemcpyHostToDevice, ln.st));
-        } else {
-            CU(cudaMemcpyAsync(ln.d_wire, packed ? in + W.wire_bytes * o : ln.h_wire, W.wire_bytes * (size_t)B, cudaMemcpyHostToDevice, ln.st));
+        if (np > 0) {
+            CU(cudaMemcpyAsync(ln.d_wire, packed ? in + W.wire_bytes * o : ln.h_wire, W.wire_bytes * (size_t)np, cudaMemcpyHostToDevice, ln.st));
             if (!packed) { CU(cudaEventRecord(ln.h2d_done, ln.st)); ln.h2d_pending = true; }
-            c->launches += wire_launch(false, ln.d_wire, ln.d_pi, c->k, B, ln.st);
+            c->launches += wire_launch(false, ln.d_wire, ln.d_pi, c->k, np, ln.st);
         }
         CU(cudaMemcpyAsync(ln.d_pk, pk + L.pk_bytes * o, L.pk_bytes * (size_t)B, cudaMemcpyHostToDevice, ln.st));
         rc = verify_chunk_lane(c, ln, B, ln.d_pi, ln.d_pk, ln.d_ok);
         if (rc) break;
         CU(cudaMemcpyAsync(ok + o, ln.d_ok, (size_t)B, cudaMemcpyDeviceToHost, ln.st));
     }
+    if (async && !rc) return KOSK_OK;                      // the caller waits with kosk_b200_sync
     for (Lane &ln : c->lanes) { cudaError_t e = cudaStreamSynchronize(ln.st); if (e != cudaSuccess && !rc) rc = fail(KOSK_E_CUDA, cudaGetErrorString(e)); ln.h2d_pending = false; }
     if (rc) return rc;
     return check_status(c);
@@ -799,11 +833,19 @@ static int verify_batch_impl(kosk_b200_ctx *c, size_t n, const uint8_t *in, cons
 
 int kosk_b200_verify_batch(kosk_b200_ctx *c, size_t n, const uint8_t *pi, const uint8_t *pk, uint8_t *ok)
 {
-    return verify_batch_impl(c, n, pi, pk, ok, false);
+    return verify_batch_impl(c, n, pi, pk, ok, false, false);
+}
+int kosk_b200_verify_batch_async(kosk_b200_ctx *c, size_t n, const uint8_t *pi, const uint8_t *pk, uint8_t *ok)
+{
+    return verify_batch_impl(c, n, pi, pk, ok, false, true);
+}
+int kosk_b200_verify_batch_packed_async(kosk_b200_ctx *c, size_t n, const uint8_t *wire, const uint8_t *pk, uint8_t *ok)
+{
+    return verify_batch_impl(c, n, wire, pk, ok, true, true);
 }
 int kosk_b200_verify_batch_packed(kosk_b200_ctx *c, size_t n, const uint8_t *wire, const uint8_t *pk, uint8_t *ok)
 {
-    return verify_batch_impl(c, n, wire, pk, ok, true);
+    return verify_batch_impl(c, n, wire, pk, ok, true, false);
 }
 
 int kosk_b200_kosk_verify(kosk_b200_ctx *c, const uint8_t *pi, const uint8_t *pk)
@@ -817,7 +859,7 @@ size_t kosk_b200_wire_bytes(int k) { return (k >= 2 && k <= 4) ? make_wire_layou
 
 int kosk_b200_set_wire(kosk_b200_ctx *c, int mode, int threads)
 {
-    if (!c || mode < 0 || mode > 1) return fail(KOSK_E_ARG, "bad argument");
+    if (!c || mode < 0 || mode > 100) return fail(KOSK_E_ARG, "bad argument");
     LOCK(c);
     int rc = kosk_b200_sync(c); if (rc) return rc;
     c->wire_mode = mode;
@@ -830,6 +872,17 @@ int kosk_b200_wire_info(const kosk_b200_ctx *c, int *mode, int *threads, const c
     if (mode) *mode = c->wire_mode;
     if (threads) *threads = c->wpool ? wire_pool_threads(c->wpool) : (c->wire_threads > 0 ? c->wire_threads : wire_default_threads());
     if (simd) *simd = wire_simd_name();
+    return KOSK_OK;
+}
+
+// instrumentation of the wire pipeline: out[0] = ns the gate thread spent waiting for D2H slices, [1] = slices, [2] = ns summed over
+// the workers spent converting, [3] = jobs (one proof each); reset != 0 clears the counters
+int kosk_b200_wire_stats(kosk_b200_ctx *c, uint64_t *out, int reset)
+{
+    if (!c || !out) return fail(KOSK_E_ARG, "null argument");
+    LOCK(c);
+    out[0] = out[1] = out[2] = out[3] = 0;
+    if (c->wpool) wire_pool_stats(c->wpool, out, reset);
     return KOSK_OK;
 }
 
@@ -1078,6 +1131,7 @@ int kosk_b200_phase_times(kosk_b200_ctx *c, double *ms, uint64_t *calls, int n, 
 
 }  // extern "C"
 
+#include "component_api.cuh"
 #include "raw_api.cuh"
 static RawState *raw_new() { return new RawState; }
 static void raw_delete(RawState *r) { if (r) { raw_free(*r); delete r; } }

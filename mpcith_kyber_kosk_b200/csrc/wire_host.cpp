@@ -3,7 +3,9 @@
 #include "kosk_common.cuh"
 #include <immintrin.h>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <deque>
@@ -160,17 +162,53 @@ int wire_pack_proof(int k, const uint8_t *pi, uint8_t *wire)
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int WIRE_NGROUP = 16;
-struct WireJob { int kind, k; size_t n; const uint8_t *src; uint8_t *dst; void *gate; int group; volatile int *flag; };
+struct WireJob { int kind, k; size_t n; const uint8_t *src; uint8_t *dst; std::atomic<int> *ctr; volatile int *flag; };
+struct WireGated { void *gate; std::vector<WireJob> jobs; };
 struct WirePool {
     std::vector<std::thread> th;
+    std::thread gate_th;                   // the only thread that waits on gates (device events): workers never block on the device
     std::mutex m;
-    std::condition_variable cv, cv_done;
+    std::condition_variable cv, cv_gate, cv_done;
     std::deque<WireJob> q;
-    size_t pending[WIRE_NGROUP] = {0};
+    std::deque<WireGated> gq;
+    size_t pending = 0;                    // jobs submitted and not finished (gated ones included)
     bool stop = false;
     wire_wait_fn wait = nullptr;
+    std::atomic<uint64_t> st_gate_ns{0}, st_job_ns{0}, st_jobs{0}, st_gates{0};   // instrumentation (wire_pool_stats)
+    // KOSK_B200_WIRE_TRACE=<file>: (kind, id, ns) records of the pipeline, dumped when the pool is destroyed (measurement only)
+    std::mutex tm; std::vector<uint64_t> trace; const char *trace_path = nullptr;
 };
+static inline uint64_t now_ns() { return (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+void wire_pool_trace(WirePool *p, int kind, uint64_t id)
+{
+    if (!p || !p->trace_path) return;
+    const uint64_t t = now_ns();
+    std::lock_guard<std::mutex> lk(p->tm);
+    p->trace.push_back((uint64_t)kind); p->trace.push_back(id); p->trace.push_back(t);
+}
+static int g_skip = -1;         // KOSK_B200_WIRE_DEBUG_SKIP=1 (measurement only): jobs convert nothing, to time the link side of the pipeline alone
+static void wire_run_job(const WireJob &j, int bad)
+{
+    if (g_skip < 0) { const char *e = getenv("KOSK_B200_WIRE_DEBUG_SKIP"); g_skip = (e && atoi(e)) ? 1 : 0; }
+    if (!bad && !g_skip) {
+        const WireLayout W = make_wire_layout(j.k);
+        for (size_t i = 0; i < j.n; i++) {
+            if (j.kind == 0) wire_unpack_proof(j.k, j.src + i * W.wire_bytes, j.dst + i * W.proof_bytes);
+            else bad |= wire_pack_proof(j.k, j.src + i * W.proof_bytes, j.dst + i * W.wire_bytes);
+        }
+    }
+    if (bad && j.flag) *j.flag = 1;
+}
+static void wire_finish(WirePool *p, const WireJob *jobs, size_t n)
+{
+    {
+        std::lock_guard<std::mutex> lk(p->m);
+        for (size_t i = 0; i < n; i++) if (jobs[i].ctr) jobs[i].ctr->fetch_sub(1);
+        p->pending -= n;
+    }
+    p->cv_done.notify_all();
+}
 
 static void wire_worker(WirePool *p)
 {
@@ -182,21 +220,36 @@ static void wire_worker(WirePool *p)
             if (p->q.empty()) return;
             j = p->q.front(); p->q.pop_front();
         }
-        int bad = 0;
-        if (j.gate && p->wait && p->wait(j.gate) != 0) bad = 1;
-        if (!bad) {
-            const WireLayout W = make_wire_layout(j.k);
-            for (size_t i = 0; i < j.n; i++) {
-                if (j.kind == 0) wire_unpack_proof(j.k, j.src + i * W.wire_bytes, j.dst + i * W.proof_bytes);
-                else bad |= wire_pack_proof(j.k, j.src + i * W.proof_bytes, j.dst + i * W.wire_bytes);
-            }
-        }
-        if (bad && j.flag) *j.flag = 1;
+        const uint64_t t0 = now_ns();
+        wire_run_job(j, 0);
+        p->st_job_ns += now_ns() - t0; p->st_jobs++;
+        wire_pool_trace(p, 2, now_ns() - t0);
+        wire_finish(p, &j, 1);
+    }
+}
+
+// gated groups are released to the workers in submission order once their gate has fired (slices land in stream order)
+static void wire_gate_thread(WirePool *p)
+{
+    for (;;) {
+        WireGated g;
         {
-            std::lock_guard<std::mutex> lk(p->m);
-            p->pending[j.group]--;
+            std::unique_lock<std::mutex> lk(p->m);
+            p->cv_gate.wait(lk, [&] { return p->stop || !p->gq.empty(); });
+            if (p->gq.empty()) return;
+            g = std::move(p->gq.front()); p->gq.pop_front();
         }
-        p->cv_done.notify_all();
+        const uint64_t t0 = now_ns();
+        const int bad = (g.gate && p->wait && p->wait(g.gate) != 0) ? 1 : 0;
+        p->st_gate_ns += now_ns() - t0; p->st_gates++;
+        wire_pool_trace(p, 1, g.jobs.size());
+        if (bad) {                         // the copy failed: nothing to convert, report through the jobs' flags
+            for (const WireJob &j : g.jobs) wire_run_job(j, 1);
+            wire_finish(p, g.jobs.data(), g.jobs.size());
+            continue;
+        }
+        { std::lock_guard<std::mutex> lk(p->m); for (const WireJob &j : g.jobs) p->q.push_back(j); }
+        p->cv.notify_all();
     }
 }
 
@@ -207,7 +260,9 @@ WirePool *wire_pool_create(int threads, wire_wait_fn wait)
     if (threads > 64) threads = 64;
     WirePool *p = new WirePool;
     p->wait = wait;
+    p->trace_path = getenv("KOSK_B200_WIRE_TRACE");
     for (int i = 0; i < threads; i++) p->th.emplace_back(wire_worker, p);
+    if (wait) p->gate_th = std::thread(wire_gate_thread, p);
     return p;
 }
 void wire_pool_destroy(WirePool *p)
@@ -215,39 +270,54 @@ void wire_pool_destroy(WirePool *p)
     if (!p) return;
     wire_pool_wait_all(p);
     { std::lock_guard<std::mutex> lk(p->m); p->stop = true; }
-    p->cv.notify_all();
+    p->cv.notify_all(); p->cv_gate.notify_all();
     for (std::thread &t : p->th) t.join();
+    if (p->gate_th.joinable()) p->gate_th.join();
+    if (p->trace_path && !p->trace.empty()) {
+        if (FILE *f = fopen(p->trace_path, "w")) { for (size_t i = 0; i + 2 < p->trace.size(); i += 3) fprintf(f, "%llu %llu %llu\n", (unsigned long long)p->trace[i], (unsigned long long)p->trace[i + 1], (unsigned long long)p->trace[i + 2]); fclose(f); }
+    }
     delete p;
 }
 int wire_pool_threads(const WirePool *p) { return p ? (int)p->th.size() : 0; }
-
-void wire_pool_submit(WirePool *p, int kind, int k, size_t n, const uint8_t *src, uint8_t *dst, void *gate, int group, volatile int *flag)
+void wire_pool_stats(WirePool *p, uint64_t out[4], int reset)
 {
+    out[0] = p->st_gate_ns; out[1] = p->st_gates; out[2] = p->st_job_ns; out[3] = p->st_jobs;
+    if (reset) { p->st_gate_ns = 0; p->st_gates = 0; p->st_job_ns = 0; p->st_jobs = 0; }
+}
+
+void wire_pool_submit(WirePool *p, void *gate, int kind, int k, size_t n, size_t per_job, const uint8_t *src, uint8_t *dst, std::atomic<int> *ctr, volatile int *flag)
+{
+    const WireLayout W = make_wire_layout(k);
+    const size_t sin = kind == 0 ? W.wire_bytes : W.proof_bytes, sout = kind == 0 ? W.proof_bytes : W.wire_bytes;
+    WireGated g; g.gate = gate;
+    if (per_job < 1) per_job = 1;
+    for (size_t o = 0; o < n; o += per_job) g.jobs.push_back(WireJob{kind, k, per_job < n - o ? per_job : n - o, src + o * sin, dst + o * sout, ctr, flag});
+    const bool gated = gate != nullptr && p->wait != nullptr;
     {
         std::lock_guard<std::mutex> lk(p->m);
-        p->q.push_back(WireJob{kind, k, n, src, dst, gate, group & (WIRE_NGROUP - 1), flag});
-        p->pending[group & (WIRE_NGROUP - 1)]++;
+        if (ctr) ctr->fetch_add((int)g.jobs.size());
+        p->pending += g.jobs.size();
+        if (gated) p->gq.push_back(std::move(g));
+        else for (const WireJob &j : g.jobs) p->q.push_back(j);
     }
-    p->cv.notify_one();
+    if (gated) p->cv_gate.notify_one(); else p->cv.notify_all();
 }
-void wire_pool_wait_group(WirePool *p, int group)
+void wire_pool_wait_counter(WirePool *p, std::atomic<int> *ctr)
 {
     std::unique_lock<std::mutex> lk(p->m);
-    p->cv_done.wait(lk, [&] { return p->pending[group & (WIRE_NGROUP - 1)] == 0; });
+    p->cv_done.wait(lk, [&] { return ctr->load() == 0; });
 }
 void wire_pool_wait_all(WirePool *p)
 {
     std::unique_lock<std::mutex> lk(p->m);
-    p->cv_done.wait(lk, [&] { for (int g = 0; g < WIRE_NGROUP; g++) if (p->pending[g]) return false; return true; });
+    p->cv_done.wait(lk, [&] { return p->pending == 0; });
 }
 int wire_pool_run(WirePool *p, int kind, int k, size_t n, const uint8_t *src, uint8_t *dst)
 {
-    const WireLayout W = make_wire_layout(k);
-    const size_t sin = kind == 0 ? W.wire_bytes : W.proof_bytes, sout = kind == 0 ? W.proof_bytes : W.wire_bytes;
     volatile int flag = 0;
-    const size_t per = n >= 8 * p->th.size() ? 2 : 1;
-    for (size_t o = 0; o < n; o += per) wire_pool_submit(p, kind, k, per < n - o ? per : n - o, src + o * sin, dst + o * sout, nullptr, WIRE_NGROUP - 1, &flag);
-    wire_pool_wait_group(p, WIRE_NGROUP - 1);
+    std::atomic<int> ctr{0};
+    wire_pool_submit(p, nullptr, kind, k, n, n >= 8 * p->th.size() ? 2 : 1, src, dst, &ctr, &flag);
+    wire_pool_wait_counter(p, &ctr);
     return flag;
 }
 

@@ -37,8 +37,8 @@ def test_wire_mode_prove_equals_oracle_and_raw_mode(ctxs, k):
     n = 21
     seeds = seeds_for_range(77, 0, n)
     ctx = pkg.KoskContext(k, 0, 8, 2)
-    ctx.set_wire(1, 3)
-    assert ctx.wire_info()["mode"] == 1
+    ctx.set_wire(100, 3)
+    assert ctx.wire_info()["mode"] == 100
     l0 = ctx.kernel_launches()
     pk, sk, pi = ctx.prove_batch(seeds)
     assert ctx.kernel_launches() > l0
@@ -59,11 +59,15 @@ def test_wire_mode_prove_equals_oracle_and_raw_mode(ctxs, k):
     bad[5, O.layout(k).o_Tcomm + 9] ^= 0x80   # a digest byte
     bad[9, 2] = 0x00; bad[9, 3] = 0x20  # an element >= 4096: not representable, the sub-batch goes raw
     want = np.ones(n, bool); want[[3, 5, 9]] = False
-    ctx.set_wire(1)
-    got_wire = ctx.verify_batch(bad, pk)
     ctx.set_wire(0)
     got_raw = ctx.verify_batch(bad, pk)
-    assert (got_wire == got_raw).all() and (got_raw == want).all()
+    assert (got_raw == want).all()
+    for pct in (100, 60):              # all packed / a split of packed and struct-byte proofs inside every sub-batch
+        ctx.set_wire(pct)
+        assert (ctx.verify_batch(bad, pk) == want).all(), pct
+    ctx.set_wire(60)
+    pk6, sk6, pi6 = ctx.prove_batch(seeds)
+    assert (pi6 == pi).all() and (pk6 == pk).all() and (sk6 == sk).all()
     wb = pkg.wire_pack(k, np.delete(bad, 9, axis=0), 2)
     assert (ctx.verify_batch_packed(wb, np.delete(pk, 9, axis=0)) == np.delete(want, 9)).all()
     ctx.close()
@@ -74,12 +78,12 @@ def test_wire_mode_async_pipeline_many_steps(ctxs):
     checked through the device verifier and, sampled, against the oracle)."""
     k, B, steps = 2, 48, 5
     ctx = pkg.KoskContext(k, 0, B, 2)
-    ctx.set_wire(1, 4)
+    ctx.set_wire(70, 4)               # slices alternate between the packed and the struct-byte route
     outs = []
     seeds = [seeds_for_range(1 << 20, s * B, (s + 1) * B) for s in range(steps)]
     pin = [torch.from_numpy(s).pin_memory() for s in seeds]
     for s in range(steps):
-        o = (np.zeros((B, ctx.pk_bytes), np.uint8), np.zeros((B, ctx.sk_bytes), np.uint8), np.zeros((B, ctx.proof_bytes), np.uint8))
+        o = tuple(torch.zeros((B, nb), dtype=torch.uint8).pin_memory().numpy() for nb in (ctx.pk_bytes, ctx.sk_bytes, ctx.proof_bytes))
         rc = ctx.lib.kosk_b200_prove_batch_async(ctx._h, B, pin[s].data_ptr(), o[0].ctypes.data, o[1].ctypes.data, o[2].ctypes.data)
         assert rc == 0
         outs.append(o)

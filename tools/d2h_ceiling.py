@@ -143,6 +143,11 @@ def main():
             lib.kosk_b200_wire_unpack(k, n_un, ctypes.c_void_p(w.ctypes.data), ctypes.c_void_p(out.ctypes.data), t)
         s = allmax(time.perf_counter() - t0)
         entry = {"proofs_per_s": world * 3 * n_un / s, "out_gbs": world * 3 * n_un * pkg.proof_bytes(k) / s / 1e9}
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            lib.kosk_b200_wire_pack(k, n_un, ctypes.c_void_p(pi.ctypes.data), ctypes.c_void_p(w.ctypes.data), t)
+        entry["pack_proofs_per_s"] = world * 3 * n_un / allmax(time.perf_counter() - t0)
         # ... with the link busy: a thread keeps copying wire-sized buffers D2H while the codec runs
         stop = threading.Event()
         moved = [0]
