@@ -24,6 +24,15 @@
 #include <sys/random.h>
 #include "kosk_b200.h"
 
+/* KOSK_DROPIN_SHIM (defined only by csrc/dropin_shim.cpp): the functions below are emitted as the exported, non-inline symbols
+ * of libkosk_kyber{512,768,1024}.so, with the reference's own (C++-mangled) names, so that OBJECT files compiled against the
+ * reference's headers link against the shim unchanged (binary drop-in).  Everywhere else they are inline (source drop-in). */
+#ifdef KOSK_DROPIN_SHIM
+#define KOSK_DROPIN_API __attribute__((visibility("default")))
+#else
+#define KOSK_DROPIN_API inline
+#endif
+
 #ifndef KYBER_K
 #define KYBER_K 2 /* Change this for different security strengths (params.hpp:8-10) */
 #endif
@@ -135,17 +144,17 @@ inline void ok(int rc) { if (rc != KOSK_OK) die(); }
 
 /* Re-seed the DRBG that stands in for the reference's global randombytes() and restart its call counter (testing /
  * reproducibility): everything after this call is a deterministic function of `seed`. */
-inline void kosk_dropin_set_seed(const uint8_t seed[32])
+KOSK_DROPIN_API void kosk_dropin_set_seed(const uint8_t seed[32])
 {
     kosk_dropin_detail::ok(kosk_b200_rng_reset(kosk_dropin_detail::state().ctx, seed));
 }
 
-inline void kyber_verifiable_keygen(kyber_keypair *keypair, uint8_t *pi)
+KOSK_DROPIN_API void kyber_verifiable_keygen(kyber_keypair *keypair, uint8_t *pi)
 {
     kosk_dropin_detail::ok(kosk_b200_verifiable_keygen_rng(kosk_dropin_detail::state().ctx, keypair->pk, keypair->sk, pi));
 }
 
-inline bool kyber_kosk_verify(const uint8_t *pi, const uint8_t *pk)
+KOSK_DROPIN_API bool kyber_kosk_verify(const uint8_t *pi, const uint8_t *pk)
 {
     const int r = kosk_b200_kosk_verify(kosk_dropin_detail::state().ctx, pi, pk);
     if (r < 0) { fprintf(stderr, "kosk_b200: %s\n", kosk_b200_last_error()); abort(); }
@@ -153,26 +162,26 @@ inline bool kyber_kosk_verify(const uint8_t *pi, const uint8_t *pk)
 }
 
 /* ---- struct-level API (mlwe_prover.hpp:77-99, mlwe_verifier.hpp:14-15, kosk.hpp:17-18) ---- */
-inline void prepare_randomness(mpcith_randomness *rand) { kosk_dropin_detail::ok(kosk_b200_prepare_randomness(kosk_dropin_detail::state().ctx, rand)); }
-inline void prepare_range_proof(mpcith_range_proof *eta_shares) { kosk_dropin_detail::ok(kosk_b200_prepare_range_proof(kosk_dropin_detail::state().ctx, eta_shares)); }
-inline void kyber_keygen(kyber_keypair *keypair, mlwe_inst *raw_key) { kosk_dropin_detail::ok(kosk_b200_keygen(kosk_dropin_detail::state().ctx, keypair->pk, keypair->sk, raw_key)); }
-inline void prove(mpcith_proof *pi, const mlwe_inst *mlwe, const mpcith_randomness *rand, const mpcith_range_proof *eta_share)
+KOSK_DROPIN_API void prepare_randomness(mpcith_randomness *rand) { kosk_dropin_detail::ok(kosk_b200_prepare_randomness(kosk_dropin_detail::state().ctx, rand)); }
+KOSK_DROPIN_API void prepare_range_proof(mpcith_range_proof *eta_shares) { kosk_dropin_detail::ok(kosk_b200_prepare_range_proof(kosk_dropin_detail::state().ctx, eta_shares)); }
+KOSK_DROPIN_API void kyber_keygen(kyber_keypair *keypair, mlwe_inst *raw_key) { kosk_dropin_detail::ok(kosk_b200_keygen(kosk_dropin_detail::state().ctx, keypair->pk, keypair->sk, raw_key)); }
+KOSK_DROPIN_API void prove(mpcith_proof *pi, const mlwe_inst *mlwe, const mpcith_randomness *rand, const mpcith_range_proof *eta_share)
 {
     kosk_dropin_detail::ok(kosk_b200_prove(kosk_dropin_detail::state().ctx, reinterpret_cast<uint8_t *>(pi), mlwe, rand, eta_share));
 }
-inline bool verify(const mpcith_proof *pi, const mlwe_inst *mlwe)
+KOSK_DROPIN_API bool verify(const mpcith_proof *pi, const mlwe_inst *mlwe)
 {
     const int r = kosk_b200_verify(kosk_dropin_detail::state().ctx, reinterpret_cast<const uint8_t *>(pi), mlwe);
     if (r < 0) kosk_dropin_detail::die();
     return r == 1;
 }
-inline void encode_mpcith_proof(uint8_t *buf, const mpcith_proof *pi) { memcpy(buf, pi, sizeof(mpcith_proof)); }     /* mlwe_prover.cpp:540-543 */
-inline void decode_mpcith_proof(mpcith_proof *pi, const uint8_t *buf) { memcpy(pi, buf, sizeof(mpcith_proof)); }     /* :545-630, field by field = the same bytes */
+KOSK_DROPIN_API void encode_mpcith_proof(uint8_t *buf, const mpcith_proof *pi) { memcpy(buf, pi, sizeof(mpcith_proof)); }     /* mlwe_prover.cpp:540-543 */
+KOSK_DROPIN_API void decode_mpcith_proof(mpcith_proof *pi, const uint8_t *buf) { memcpy(pi, buf, sizeof(mpcith_proof)); }     /* :545-630, field by field = the same bytes */
 
 /* ---- Kyber KEM on the generated keys (kyber/kem.h:29-33; main.cpp:98-113) ---- */
-inline int kosk_dropin_kem_keypair(uint8_t *pk, uint8_t *sk) { kosk_dropin_detail::ok(kosk_b200_kem_keypair(kosk_dropin_detail::state().ctx, pk, sk)); return 0; }
-inline int kosk_dropin_kem_enc(uint8_t *ct, uint8_t *ss, const uint8_t *pk) { kosk_dropin_detail::ok(kosk_b200_kem_enc(kosk_dropin_detail::state().ctx, ct, ss, pk)); return 0; }
-inline int kosk_dropin_kem_dec(uint8_t *ss, const uint8_t *ct, const uint8_t *sk) { kosk_dropin_detail::ok(kosk_b200_kem_dec(kosk_dropin_detail::state().ctx, ss, ct, sk)); return 0; }
+KOSK_DROPIN_API int kosk_dropin_kem_keypair(uint8_t *pk, uint8_t *sk) { kosk_dropin_detail::ok(kosk_b200_kem_keypair(kosk_dropin_detail::state().ctx, pk, sk)); return 0; }
+KOSK_DROPIN_API int kosk_dropin_kem_enc(uint8_t *ct, uint8_t *ss, const uint8_t *pk) { kosk_dropin_detail::ok(kosk_b200_kem_enc(kosk_dropin_detail::state().ctx, ct, ss, pk)); return 0; }
+KOSK_DROPIN_API int kosk_dropin_kem_dec(uint8_t *ss, const uint8_t *ct, const uint8_t *sk) { kosk_dropin_detail::ok(kosk_b200_kem_dec(kosk_dropin_detail::state().ctx, ss, ct, sk)); return 0; }
 #ifndef crypto_kem_enc      /* the reference namespaces these through macros as well (kyber/kem.h:26-33) */
 #define crypto_kem_keypair kosk_dropin_kem_keypair
 #define crypto_kem_enc kosk_dropin_kem_enc

@@ -27,6 +27,25 @@ def _nvcc():
     raise RuntimeError("nvcc not found: cannot build libkosk_b200.so")
 
 
+SHIMS = {2: "libkosk_kyber512.so", 3: "libkosk_kyber768.so", 4: "libkosk_kyber1024.so"}     # binary drop-in shims (csrc/dropin_shim.cpp)
+
+
+def build_shims(force=False):
+    """libkosk_kyber{512,768,1024}.so: the reference's own symbol names over libkosk_b200.so (g++ only, no device code)."""
+    src = os.path.join(CSRC, "dropin_shim.cpp")
+    deps = [src, os.path.join(HERE, "..", "include", "kosk_dropin.hpp"), os.path.join(HERE, "..", "include", "kosk_b200.h")]
+    out = []
+    for k, name in SHIMS.items():
+        lib = os.path.join(HERE, name)
+        if force or not os.path.exists(lib) or any(os.path.getmtime(d) > os.path.getmtime(lib) for d in deps):
+            r = subprocess.run(["g++", "-std=c++11", "-O2", "-fPIC", "-shared", "-fvisibility=hidden", f"-DKYBER_K={k}", src, "-L" + HERE, "-lkosk_b200",
+                                "-Wl,-rpath,$ORIGIN", "-o", lib], capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError("g++ failed for the drop-in shim:\n" + r.stdout + r.stderr)
+        out.append(lib)
+    return out
+
+
 def needs_build():
     if not os.path.exists(LIB):
         return True
@@ -37,6 +56,7 @@ def needs_build():
 
 def build(force=False, verbose=False):
     if not force and not needs_build():
+        build_shims()
         return LIB
     objs = []
     for src in HOST_SOURCES:
@@ -51,6 +71,7 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     if verbose:
         sys.stderr.write(res.stderr)
+    build_shims(force=True)
     return LIB
 
 

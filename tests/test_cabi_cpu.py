@@ -126,3 +126,34 @@ def test_reference_main_cpp_compiles_against_dropin_headers(built_lib):
     subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "dropin-main"], check=True, capture_output=True)
     for k in (2, 3, 4):
         assert os.path.exists(os.path.join(ROOT, "oracle", "_ref", f"main_dropin_k{k}"))
+
+
+@pytest.mark.parametrize("k", [2, 3, 4])
+def test_shim_exports_the_reference_symbols(built_lib, k):
+    """Binary drop-in: every symbol an object compiled against the reference's own headers imports from the reference (main.cpp ->
+    oracle/_ref/main_ref_k*.o; the reference's objects = oracle/_ref/libkosk_ref_k*.so) is defined, under the same (mangled) name, by
+    libkosk_kyber{512,768,1024}.so; plus the three names SURVEY 8(b) lists."""
+    import subprocess
+    from mpcith_kyber_kosk_b200 import build
+    shim = os.path.join(ROOT, "mpcith_kyber_kosk_b200", build.SHIMS[k])
+    assert os.path.exists(shim)
+
+    def syms(path, flag):
+        out = subprocess.run(["nm", flag, path], capture_output=True, text=True).stdout
+        return {l.split()[-1] for l in out.splitlines() if l.split()}
+    have = syms(shim, "-D")
+    for name in ("_Z23kyber_verifiable_keygenP13kyber_keypairPh", "_Z17kyber_kosk_verifyPKhS0_", "_Z12kyber_keygenP13kyber_keypairP9mlwe_inst",
+                 "_Z5proveP12mpcith_proofPK9mlwe_instPK17mpcith_randomnessPK18mpcith_range_proof", "_Z6verifyPK12mpcith_proofPK9mlwe_inst",
+                 "_Z18prepare_randomnessP17mpcith_randomness", "_Z19prepare_range_proofP18mpcith_range_proof",
+                 "_Z19encode_mpcith_proofPhPK12mpcith_proof", "_Z19decode_mpcith_proofP12mpcith_proofPKh",
+                 f"pqcrystals_kyber{256 * k}_ref_keypair", f"pqcrystals_kyber{256 * k}_ref_enc", f"pqcrystals_kyber{256 * k}_ref_dec"):
+        assert name in have, name
+    obj = os.path.join(ROOT, "oracle", "_ref", f"main_ref_k{k}.o")
+    ref = os.path.join(ROOT, "oracle", "_ref", f"libkosk_ref_k{k}.so")
+    if not (os.path.exists(obj) and os.path.exists(ref)):
+        pytest.skip("oracle/_ref not built in this checkout (no /root/reference)")
+    wanted = {l.split()[-1] for l in subprocess.run(["nm", "-u", obj], capture_output=True, text=True).stdout.splitlines() if l.split()}
+    ref_defined = {l.split()[-1] for l in subprocess.run(["nm", "-D", "--defined-only", ref], capture_output=True, text=True).stdout.splitlines() if l.split()}
+    from_reference = wanted & ref_defined
+    assert len(from_reference) >= 9
+    assert from_reference <= have, sorted(from_reference - have)

@@ -395,7 +395,7 @@ def test_struct_sequence_matches_reference_golden(ctxs, case):
 @pytest.mark.parametrize("k", [2, 3, 4])
 def test_struct_sequence_against_live_reference(ctxs, k):
     if O.ref(k) is None:
-        pytest.skip("oracle/_ref not built on this box")
+        pytest.fail("oracle/_ref missing: run __graft_entry__.build() where /root/reference exists (oracle/_ref travels with the repo)")
     seed = O.seed_of(77 + k)
     ctx = ctxs(k)
     got = _struct_sequence(ctx, seed)
@@ -502,12 +502,30 @@ def test_reference_main_cpp_runs_against_the_library(k):
     import subprocess
     exe = os.path.join(O.ORACLE_DIR, "_ref", f"main_dropin_k{k}")
     if not os.path.exists(exe):
-        pytest.skip("oracle/_ref/main_dropin_k* not built (no /root/reference in this checkout)")
+        pytest.fail("oracle/_ref/main_dropin_k* missing: run __graft_entry__.build() where /root/reference exists (the binary travels with the repo)")
     out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr
     for line in ("[result] mlwe verify success", "[result] kyber kosk verify success", "[result] decapsulated ss is the same as the encapsulated",
                  f"[proof size] {ctypes_proof_kib(k)} kilobytes"):
         assert line in out.stdout, out.stdout
+
+
+@pytest.mark.parametrize("k", [2, 3, 4])
+def test_reference_main_object_links_against_the_shim_only(k):
+    """BINARY drop-in: main.cpp compiled against the reference's OWN headers (oracle/_ref/main_ref_k*.o, `make -C oracle binlink-main`)
+    linked with nothing but libkosk_kyber{512,768,1024}.so, which exports the reference's C++-mangled symbols (kosk.hpp:17-23,
+    mlwe_prover.hpp:77-99, mlwe_verifier.hpp:14-15) and the pqcrystals_* KEM names (kyber/kem.h:20-33)."""
+    import subprocess
+    exe = os.path.join(O.ORACLE_DIR, "_ref", f"main_binlink_k{k}")
+    if not os.path.exists(exe):
+        pytest.fail("oracle/_ref/main_binlink_k* missing: run __graft_entry__.build() where /root/reference exists (the binary travels with the repo)")
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    for line in ("[result] mlwe verify success", "[result] kyber kosk verify success", "[result] decapsulated ss is the same as the encapsulated",
+                 f"[proof size] {ctypes_proof_kib(k)} kilobytes"):
+        assert line in out.stdout, out.stdout
+    maps = subprocess.run(["ldd", exe], capture_output=True, text=True).stdout
+    assert f"libkosk_kyber{256 * k}.so" in maps and "libkosk_ref" not in maps
 
 
 def ctypes_proof_kib(k):
@@ -520,7 +538,7 @@ def test_kem_arbitrary_bytes_match_live_reference(ctxs, k):
     """Inputs a well-formed key pair never produces: 12-bit coefficients >= q in pk / sk (the reference reduces them implicitly in
     its Montgomery arithmetic) and random ciphertext bytes (every bit pattern decompresses): same bytes out as the reference."""
     if O.ref(k) is None:
-        pytest.skip("oracle/_ref not built on this box")
+        pytest.fail("oracle/_ref missing: run __graft_entry__.build() where /root/reference exists (oracle/_ref travels with the repo)")
     ctx = ctxs(k)
     rng = np.random.default_rng(70 + k)
     n = 6
