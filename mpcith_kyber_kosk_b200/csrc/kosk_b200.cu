@@ -651,13 +651,15 @@ int kosk_b200_prove_batch(kosk_b200_ctx *c, size_t n, const uint8_t *seeds, uint
 // ---- compact wire format on the host-buffer paths (wire_kernels.cuh, wire_host.h) ----
 // the gate thread polls: a blocking-sync event makes the copy engine raise an interrupt per slice (measured: +1 ms per 64 slices of link
 // idle time), a spinning cudaEventSynchronize burns a core that the unpack workers need
+static int g_wire_poll_us = 20;      // KOSK_B200_WIRE_POLL_US: 0 = block in cudaEventSynchronize (events are then created with cudaEventBlockingSync)
 static int wire_wait_event(void *gate)
 {
+    if (g_wire_poll_us <= 0) return cudaEventSynchronize((cudaEvent_t)gate) == cudaSuccess ? 0 : 1;
     for (;;) {
         const cudaError_t e = cudaEventQuery((cudaEvent_t)gate);
         if (e == cudaSuccess) return 0;
         if (e != cudaErrorNotReady) return 1;
-        std::this_thread::sleep_for(std::chrono::microseconds(20));
+        std::this_thread::sleep_for(std::chrono::microseconds(g_wire_poll_us));
     }
 }
 static int wire_default_threads()
@@ -681,7 +683,8 @@ static int wire_ensure(kosk_b200_ctx *c, bool host_too)
             if (cudaHostAlloc((void **)&ln.h_wire, bytes, cudaHostAllocDefault) != cudaSuccess) { ln.h_wire = nullptr; return fail(KOSK_E_NOMEM, "cudaHostAlloc failed for the wire staging buffer"); }
             const int nsl = (c->chunk + c->wire_slice - 1) / c->wire_slice;
             ln.wev.resize(nsl);
-            for (cudaEvent_t &e : ln.wev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            if (const char *e = getenv("KOSK_B200_WIRE_POLL_US")) g_wire_poll_us = atoi(e);
+            for (cudaEvent_t &e : ln.wev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming | (g_wire_poll_us <= 0 ? cudaEventBlockingSync : 0)));
             ln.wctr.reset(new std::atomic<int>[nsl]);
             for (int i = 0; i < nsl; i++) ln.wctr[i].store(0);
             CU(cudaEventCreateWithFlags(&ln.h2d_done, cudaEventDisableTiming));
@@ -707,6 +710,8 @@ static int prove_async_impl(kosk_b200_ctx *c, size_t n, const uint8_t *seeds, ui
         Lane &ln = c->lanes[li];
         if (wire) {
             int rc = wire_ensure(c, !packed); if (rc) return rc;
+            static const int lanewait = getenv("KOSK_B200_WIRE_LANEWAIT") ? atoi(getenv("KOSK_B200_WIRE_LANEWAIT")) : 0;      // measurement switch
+            if (lanewait && !packed) for (size_t si = 0; si < ln.wev.size(); si++) wire_pool_wait_counter(c->wpool, &ln.wctr[si]);
         }
         wire_pool_trace(c->wpool, 10, li);
         CU(cudaMemcpyAsync(ln.d_seeds, seeds + 32 * o, 32 * (size_t)B, cudaMemcpyHostToDevice, ln.st));

@@ -40,6 +40,16 @@ void *run(void *p)
         memcpy(j->pk, kp->pk, KYBER_PUBLICKEYBYTES); memcpy(j->sk, kp->sk, KYBER_SECRETKEYBYTES);
         encode_mpcith_proof(j->pi, pi);
         delete rnd; delete eta; delete inst; delete kp; delete pi;
+    } else if (j->op == 4) {          /* prove() alone on caller-supplied structs, DRBG positioned at call number j->mode */
+        kosk_rng_reset(j->seed, KOSK_RNG_COUNTER);
+        uint8_t junk[1];
+        for (int i = 0; i < j->mode; i++) randombytes(junk, 1);
+        mpcith_randomness *rnd = new mpcith_randomness; mpcith_range_proof *eta = new mpcith_range_proof;
+        mlwe_inst *inst = new mlwe_inst; mpcith_proof *pi = new mpcith_proof;
+        memcpy(rnd, j->rand_img, sizeof *rnd); memcpy(eta, j->eta_img, sizeof *eta); memcpy(inst, j->cinst, sizeof *inst);
+        prove(pi, inst, rnd, eta);
+        encode_mpcith_proof(j->pi, pi);
+        delete rnd; delete eta; delete inst; delete pi;
     } else {                          /* verify() on a raw instance */
         mpcith_proof *pi = new mpcith_proof; mlwe_inst *inst = new mlwe_inst;
         decode_mpcith_proof(pi, j->cpi); memcpy(inst, j->cinst, sizeof *inst);
@@ -99,6 +109,11 @@ void ref_kem_enc_at(const uint8_t seed[32], uint32_t call, uint8_t *ct, uint8_t 
     uint8_t junk[1];
     for (uint32_t i = 0; i < call; i++) randombytes(junk, 1);
     crypto_kem_enc(ct, ss, pk);
+}
+/* prove() (mlwe_prover.cpp:81-538) on caller-supplied struct images with the counter DRBG positioned at call number `call` */
+void ref_prove_struct_at(const uint8_t seed[32], int call, const uint8_t *inst_img, uint8_t *rand_img, uint8_t *eta_img, uint8_t *pi)
+{
+    job j = {4, seed, call, 0, 0, pi, 0, 0, 0, rand_img, eta_img, 0, inst_img}; big_stack(&j);
 }
 int ref_verify_struct(const uint8_t *pi, const uint8_t *inst_img)
 {

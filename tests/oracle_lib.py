@@ -123,6 +123,9 @@ def ref(k):
                 getattr(lib, n).restype = ctypes.c_size_t
             lib.ref_struct_sequence.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, vp, vp]
             lib.ref_verify_struct.argtypes = [vp, vp]
+            if hasattr(lib, "ref_prove_struct_at"):
+                lib.ref_prove_struct_at.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp]
+                lib.ref_prove_struct_at.restype = None
             lib.ref_ct_bytes.restype = ctypes.c_size_t
             lib.ref_kem_enc_derand.argtypes = [vp, vp, vp, vp]
             lib.ref_kem_enc_derand.restype = None
@@ -182,6 +185,16 @@ def ref_struct_sequence(k, seed, rng_mode=0):
     ok = lib.ref_struct_sequence(_p(seed), rng_mode, _p(rnd), _p(eta), _p(inst), _p(pk), _p(sk), _p(pi))
     return {"rand": mask_share_vec_len(rnd, S["rand_shares_off"]), "eta": mask_share_vec_len(eta, 0), "inst": inst,
             "pk": pk, "sk": sk, "pi": pi, "ok": ok == 1}
+
+
+def ref_prove_struct_at(k, seed, call, inst, rand, eta):
+    """The reference's prove() on the given struct images, its randombytes() positioned at call number `call`."""
+    L = layout(k)
+    seed = np.frombuffer(bytes(seed), dtype=np.uint8).copy()
+    inst, rand, eta = (np.ascontiguousarray(x, dtype=np.uint8).copy() for x in (inst, rand, eta))
+    pi = np.zeros(L.proof_bytes, np.uint8)
+    ref(k).ref_prove_struct_at(_p(seed), int(call), _p(inst), _p(rand), _p(eta), _p(pi))
+    return pi
 
 
 def ref_verify_struct(k, pi, inst):

@@ -165,3 +165,36 @@ def test_interp_rows_match_oracle_lagrange_matrix(ctxs, degree2, pattern):
     want = (shares.astype(np.int64) @ Lm.astype(np.int64).T) % 3329
     got = ctxs(2).interp_rows(opened, shares, degree2)
     assert (got == want).all()
+
+
+# ---------------- struct-level prove() on inconsistent instances (the prover's algebraic shortcuts must not change the bytes) ----------------
+@pytest.mark.parametrize("k", [2, 3, 4])
+def test_struct_prove_on_inconsistent_instances_matches_live_reference(ctxs, k):
+    """DESIGN 3 removes the prover's reconstructions algebraically (the opened masked secret is s + r; the range-proof products come
+    straight from s / e).  Those identities hold for ANY instance, not only for t = As + e with s, e in [-eta, eta]: prove() on an instance
+    with a wrong t, an s coefficient outside the range and an e coefficient outside the range must give the reference's bytes, and both
+    verifiers must reject the result."""
+    if O.ref(k) is None or not hasattr(O.ref(k), "ref_prove_struct_at"):
+        pytest.fail("oracle/_ref (with ref_prove_struct_at) missing: run __graft_entry__.build() where /root/reference exists")
+    seed = O.seed_of(600 + k)
+    seq = O.ref_struct_sequence(k, seed)
+    S = O.struct_sizes(k)
+    call = 3 * S["F"] + 2 * k * S["E"] + 1                   # randombytes() calls made before prove() in main.cpp's order
+    oT = k * k * 256; oS = oT + k * 256; oE = oS + k * 256
+    ctx = ctxs(k)
+    cases = {"honest": lambda a: None,
+             "t+1": lambda a: a.__setitem__(oT, a[oT] + 1),
+             "s=7": lambda a: a.__setitem__(oS + 5, 7),
+             "e=-5": lambda a: a.__setitem__(oE + 200, -5),
+             "s=-1000,e=1200": lambda a: (a.__setitem__(oS + 255, -1000), a.__setitem__(oE, 1200))}
+    for name, edit in cases.items():
+        inst = seq["inst"].copy().view(np.int16)
+        edit(inst)
+        inst = inst.view(np.uint8)
+        want = O.ref_prove_struct_at(k, seed, call, inst, seq["rand"], seq["eta"])
+        ctx.rng_reset(seed)
+        ctx.prepare_randomness(); ctx.prepare_range_proof(); ctx.kyber_keygen()     # consume the calls that precede prove()
+        assert ctx.rng_calls() == call
+        got = np.frombuffer(ctx.prove(inst, seq["rand"], seq["eta"]), np.uint8)
+        assert (got == want).all(), (name, int((got != want).sum()))
+        assert ctx.verify(got, inst) == O.ref_verify_struct(k, want, inst) == (name == "honest"), name
