@@ -31,9 +31,10 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 MACS_PER_PROVE = {2: 135.14e6, 3: 142.69e6, 4: 160.41e6}
 KECCAK_PER_PROVE = {2: 11196, 3: 11220, 4: 11254}
 SHARE_MACS_PER_ROW = 1303 * 407          # ss.cpp:23-32: one sharing = 1303 x 407 MACs
-# share_ntt.cuh: FMA-pipe instructions per sharing (one warp): 2 forward passes x 328 + 6 inverse passes x 472 (DFT mat-vecs,
-# twiddles, pointwise products, two IMADs per Montgomery reduction), x 32 lanes
-NTT_IMAD_PER_SHARING = (2 * 328 + 6 * 472) * 32
+# share_ntt.cuh: FMA-heavy-pipe issue slots per sharing (one warp), counted in the SASS of k_conv_ntt<4,11>: a forward pass has 182 IMAD
+# + 40 IMAD.HI, an inverse pass 290 IMAD + 40 IMAD.HI (DFT mat-vecs with immediate operands, pointwise products, Barrett / Shoup
+# reductions); IMAD.HI issues at half the IMAD rate (kosk_b200_int_peak: 8.8 T vs 18.5 T thread-ops/s), so it counts twice; x 32 lanes
+NTT_IMAD_PER_SHARING = (2 * (182 + 2 * 40) + 6 * (290 + 2 * 40)) * 32
 INT_OPS_PER_KECCAK = 7440                # 24 rounds x 155 64-bit logic ops x 2 (32-bit lanes): algorithmic
 ALU_INSTR_PER_KECCAK = 24 * 180          # executed: 122 LOP3 + 58 SHF per round (keccak.cuh), thread-level
 SPONGE_FLOOR_US = 2.09                   # one warp-cooperative permutation alone on an SM (tools/exp/sponge_round_bench.cu)

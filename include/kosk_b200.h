@@ -133,6 +133,13 @@ typedef struct kosk_b200_pool kosk_b200_pool;
 int kosk_b200_pool_create(kosk_b200_ctx *ctx, size_t n, const uint8_t *seeds, kosk_b200_pool **pool);
 int kosk_b200_pool_prove(kosk_b200_pool *pool, uint8_t *pk, uint8_t *sk, uint8_t *pi);
 void kosk_b200_pool_destroy(kosk_b200_pool *pool);
+/* Serialiser of the preprocessed material (the working form of mlwe_prover.cpp:61-79): export writes kosk_b200_pool_bytes(pool)
+ * bytes (header | seeds | sharing inputs | evaluated f / NTT_f / eta sharings, about 0.7 MB per Kyber512 proof); import rebuilds a
+ * pool on any context of the same KYBER_K, and pool_prove on it gives the same bytes as on the exporting pool.  The image contains
+ * the seeds: it is as secret as the keys it will produce. */
+size_t kosk_b200_pool_bytes(const kosk_b200_pool *pool);
+int kosk_b200_pool_export(kosk_b200_pool *pool, void *image, size_t bytes);
+int kosk_b200_pool_import(kosk_b200_ctx *ctx, const void *image, size_t bytes, kosk_b200_pool **pool);
 
 /* Struct-level API: the reference's lower-level entry points, used directly by main.cpp:16-59, on byte
  * images of the reference's own structs (x86-64 layout, no padding):
@@ -208,8 +215,9 @@ int kosk_b200_debug_trace(kosk_b200_ctx *ctx, double *out, int max_triples);
 /* Measurement support.  With profiling on, every prove chunk records CUDA events on its launching stream at the
  * phase boundaries; kosk_b200_phase_times() synchronises and returns accumulated milliseconds and call counts for
  * the KOSK_PH_* phases (order: keygen, expand, share1, commit, fs1, eval, open, share2, view, fs2, assemble, verify).
- * kosk_b200_int_peak() runs issue-rate microbenchmarks and returns, in ops_per_s[4], thread-level ops/s for IMAD, LOP3
- * and SHF (the SM integer-pipe roofline denominators) and int8 MAC/s of warp-level mma.sync (for the opt-in tensor path). */
+ * kosk_b200_int_peak() runs issue-rate microbenchmarks and returns, in ops_per_s[5], thread-level ops/s for IMAD, LOP3
+ * and SHF (the SM integer-pipe roofline denominators), int8 MAC/s of warp-level mma.sync (for the opt-in tensor path) and
+ * thread-level ops/s of IMAD.HI (the high half of a 32 x 32 product, used by the Barrett / Shoup reductions). */
 #define KOSK_B200_NPHASE 12
 int kosk_b200_set_profiling(kosk_b200_ctx *ctx, int on);
 int kosk_b200_phase_times(kosk_b200_ctx *ctx, double *ms, uint64_t *calls, int n, int reset);

@@ -24,7 +24,7 @@ EXPORTS = [
     "kosk_b200_wire_bytes", "kosk_b200_set_wire", "kosk_b200_wire_info", "kosk_b200_wire_stats", "kosk_b200_prove_batch_packed", "kosk_b200_prove_batch_packed_async", "kosk_b200_verify_batch_packed",
     "kosk_b200_verify_batch_async", "kosk_b200_verify_batch_packed_async",
     "kosk_b200_wire_pack_device", "kosk_b200_wire_unpack_device", "kosk_b200_wire_pack", "kosk_b200_wire_unpack", "kosk_b200_wire_simd",
-    "kosk_b200_pool_create", "kosk_b200_pool_prove", "kosk_b200_pool_destroy", "kosk_b200_set_strict", "kosk_b200_set_profiling", "kosk_b200_phase_times", "kosk_b200_int_peak",
+    "kosk_b200_pool_bytes", "kosk_b200_pool_export", "kosk_b200_pool_import", "kosk_b200_pool_create", "kosk_b200_pool_prove", "kosk_b200_pool_destroy", "kosk_b200_set_strict", "kosk_b200_set_profiling", "kosk_b200_phase_times", "kosk_b200_int_peak",
 ]
 
 _lib = None
@@ -77,6 +77,10 @@ def load_library(path=None):
     lib.kosk_b200_set_strict.argtypes = [vp, i32]
     lib.kosk_b200_pool_create.argtypes = [vp, sz, u8p, ctypes.POINTER(vp)]
     lib.kosk_b200_pool_prove.argtypes = [vp, u8p, u8p, u8p]
+    lib.kosk_b200_pool_bytes.argtypes = [vp]
+    lib.kosk_b200_pool_bytes.restype = sz
+    lib.kosk_b200_pool_export.argtypes = [vp, u8p, sz]
+    lib.kosk_b200_pool_import.argtypes = [vp, u8p, sz, ctypes.POINTER(vp)]
     lib.kosk_b200_pool_destroy.argtypes = [vp]
     lib.kosk_b200_pool_destroy.restype = None
     lib.kosk_b200_rng_reset.argtypes = [vp, u8p]
@@ -442,6 +446,14 @@ class KoskContext:
         self._check(self.lib.kosk_b200_pool_create(self._h, seeds.shape[0], _ptr(seeds), ctypes.byref(h)), "pool_create")
         return KoskPool(self, h, seeds.shape[0])
 
+    def pool_import(self, image):
+        """Rebuild a preprocessing pool from an image written by KoskPool.export()."""
+        image = np.ascontiguousarray(image, dtype=np.uint8)
+        h = ctypes.c_void_p()
+        self._check(self.lib.kosk_b200_pool_import(self._h, _ptr(image), image.size, ctypes.byref(h)), "pool_import")
+        n = int(np.frombuffer(image[16:20].tobytes(), np.uint32)[0])
+        return KoskPool(self, h, n)
+
     def set_strict(self, on=True):
         """Hardened verifier; default off = the reference's accept set."""
         self._check(self.lib.kosk_b200_set_strict(self._h, 1 if on else 0), "set_strict")
@@ -456,9 +468,9 @@ class KoskContext:
         return {n: (float(m), int(c)) for n, m, c in zip(self.PHASES, ms, calls)}
 
     def int_peak(self):
-        out = np.zeros(4, np.float64)
+        out = np.zeros(8, np.float64)
         self._check(self.lib.kosk_b200_int_peak(self._h, _ptr(out)), "int_peak")
-        return {"imad": float(out[0]), "lop3": float(out[1]), "shf": float(out[2]), "imma_int8_mac": float(out[3])}
+        return {"imad": float(out[0]), "lop3": float(out[1]), "shf": float(out[2]), "imma_int8_mac": float(out[3]), "imad_hi": float(out[4])}
 
     def debug_trace(self, max_triples=4096):
         out = np.zeros(3 * max_triples, np.float64)
@@ -481,6 +493,13 @@ class KoskPool:
         pk, sk, pi = np.empty((self.n, c.pk_bytes), np.uint8), np.empty((self.n, c.sk_bytes), np.uint8), np.empty((self.n, c.proof_bytes), np.uint8)
         c._check(c.lib.kosk_b200_pool_prove(self._h, _ptr(pk), _ptr(sk), _ptr(pi)), "pool_prove")
         return pk, sk, pi
+
+    def export(self):
+        """Serialise the preprocessed material (contains the seeds: keep it secret)."""
+        c = self.ctx
+        out = np.empty(c.lib.kosk_b200_pool_bytes(self._h), np.uint8)
+        c._check(c.lib.kosk_b200_pool_export(self._h, _ptr(out), out.size), "pool_export")
+        return out
 
     def close(self):
         if self._h:

@@ -54,6 +54,17 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def build_variant(name, defines):
+    """Experiment helper: a second copy of the library with extra -D macros (mpcith_kyber_kosk_b200/libkosk_b200_<name>.so)."""
+    lib = os.path.join(HERE, f"libkosk_b200_{name}.so")
+    objs = [os.path.join(CSRC, src.rsplit(".", 1)[0] + ".o") for src in HOST_SOURCES]
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-o", lib] + [os.path.join(CSRC, s) for s in SOURCES] + objs + ["-lpthread"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    return lib
+
+
 def build(force=False, verbose=False):
     if not force and not needs_build():
         build_shims()

@@ -56,7 +56,7 @@ int kosk_b200_recon_rows(kosk_b200_ctx *c, int degree2, size_t n, const uint16_t
     if (c->use_ntt) {
         ConvArgs cv{}; cv.A = ba.as<u16>(); cv.C = bc.as<u16>(); cv.lda = ld; cv.ldc = 256; cv.mtotal = (int)n; cv.rpp = (int)n;
         cv.tw = c->sn.tw; cv.khat = sn_kh_m256(c->sn, degree2 ? 7 : 4); cv.pre = degree2 ? c->sn.wj2 : c->sn.wj;
-        cv.post = reinterpret_cast<const u16 *>(degree2 ? c->sn.pr2 : c->sn.pr1);
+        cv.post = degree2 ? c->sn.pr2 : c->sn.pr1;
         c->launches += degree2 ? conv_ntt_launch<7, 2, D2, 256, true, false>(cv, st) : conv_ntt_launch<4, 2, D1, 256, true, false>(cv, st);
     } else {
         GemmArgs g{}; g.ws = c->lanes[0].vb.WS; g.ws_elems = GE_WS_ELEMS; g.A = ba.as<u16>(); g.Bt = degree2 ? c->d_R2 : c->d_R1; g.C = bc.as<u16>();
@@ -94,7 +94,7 @@ int kosk_b200_interp_rows(kosk_b200_ctx *c, int degree2, const uint16_t *opened,
     c->launches += 3;
     if (c->use_ntt) {
         ConvArgs cv{}; cv.A = bA.as<u16>(); cv.C = bC.as<u16>(); cv.lda = kp; cv.ldc = ldo; cv.mtotal = (int)n; cv.rpp = (int)n; cv.a_slots = (int)n; cv.c_slots = (int)n;
-        cv.tw = c->sn.tw; cv.khat = sn_kh_m256(c->sn, degree2 ? 8 : 5); cv.post = degree2 ? vb.PT2 : vb.PT1; cv.post_group = degree2 ? 256 : LM1_ROWS;
+        cv.tw = c->sn.tw; cv.khat = sn_kh_m256(c->sn, degree2 ? 8 : 5); cv.post = reinterpret_cast<const int2 *>(degree2 ? vb.PT2 : vb.PT1); cv.post_group = degree2 ? 256 : LM1_ROWS;
         c->launches += degree2 ? conv_ntt_launch<8, 2, KP2, 256, false, true>(cv, st) : conv_ntt_launch<5, 4, KP1, D1, false, true>(cv, st);
     } else {
         GemmArgs g{}; g.ws = vb.WS; g.ws_elems = GE_WS_ELEMS; g.A = bA.as<u16>(); g.Bt = degree2 ? c->d_U2 : c->d_U1; g.C = bC.as<u16>(); g.lda = kp; g.ldb = kp; g.ldc = ldo;

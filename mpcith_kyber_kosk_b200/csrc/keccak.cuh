@@ -15,6 +15,17 @@ __constant__ uint64_t c_keccak_rc[24] = {
     0x8000000000008002ULL, 0x8000000000000080ULL, 0x000000000000800aULL, 0x800000008000000aULL,
     0x8000000080008081ULL, 0x8000000000008080ULL, 0x0000000080000001ULL, 0x8000000080008008ULL};
 
+// the same constants for fully unrolled permutations: folded into LOP3 immediates (a __constant__ array may be rewritten by the host, so
+// every use of it stays an LDC)
+struct KeccakRc { uint64_t v[24]; };
+__device__ constexpr KeccakRc c_keccak_rc_imm = {{
+    0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808aULL, 0x8000000080008000ULL,
+    0x000000000000808bULL, 0x0000000080000001ULL, 0x8000000080008081ULL, 0x8000000000008009ULL,
+    0x000000000000008aULL, 0x0000000000000088ULL, 0x0000000080008009ULL, 0x000000008000000aULL,
+    0x000000008000808bULL, 0x800000000000008bULL, 0x8000000000008089ULL, 0x8000000000008003ULL,
+    0x8000000000008002ULL, 0x8000000000000080ULL, 0x000000000000800aULL, 0x800000008000000aULL,
+    0x8000000080008081ULL, 0x8000000000008080ULL, 0x0000000080000001ULL, 0x8000000080008008ULL}};
+
 __device__ __forceinline__ uint64_t rol64(uint64_t x, int n)
 {
     // two funnel shifts on the 32-bit halves (SHF.L.W); n is a compile-time constant at every call site
@@ -160,7 +171,7 @@ struct WarpKeccak {
             const uint64_t ar = ((uint64_t)nh << 32) | nl;
             const uint64_t b = shfl(ar, src_pi), b1 = shfl(ar, src_c1), b2 = shfl(ar, src_c2);   // pi, fused with chi's two neighbour reads
             a = b ^ (~b1 & b2);                                            // chi
-            if (lane0) a ^= c_keccak_rc[r];                                // iota
+            if (lane0) a ^= c_keccak_rc_imm.v[r];                          // iota
         }
         return a;
     }

@@ -102,7 +102,7 @@ struct kosk_b200_ctx {
     int overlap_fs1 = 0;                   // KOSK_B200_OVERLAP_FS1=1: eta / z_j sharings on the lane's side stream next to commit hashes + FS-1 (measured: a loss, off)
     int overlap_tail = 1;                  // KOSK_B200_OVERLAP_TAIL: let a sub-batch start while the previous one runs FS-2 + assembly
     int use_ntt = 1;                       // KOSK_B200_SHARE_NTT: share evaluation as a blocked NTT convolution (share_ntt.cuh) instead of the dense table GEMM
-    int16_t *d_sn = nullptr;               // its tables (ShareNttTables), one allocation
+    uint8_t *d_sn = nullptr;               // its tables (ShareNttTables), one allocation
     ShareNttTables sn{};
     Slots sl; Layout L;
     uint64_t launches = 0;
@@ -312,14 +312,21 @@ int kosk_b200_create_ex(kosk_b200_ctx **out, int k, int device, int max_chunk, i
         }
         {   // tables of the NTT-convolution share evaluation (share_ntt.cuh)
             const ShareNttHost sh = share_ntt_tables();
-            CUC(cudaMemcpyToSymbol(c_sn_w16f, sh.w16f.data(), 256 * 4)); CUC(cudaMemcpyToSymbol(c_sn_w16i, sh.w16i.data(), 256 * 4));
-            std::vector<int16_t> all;
-            const std::vector<int16_t> *parts[] = {&sh.tw, &sh.kh_share, &sh.kh_m256, &sh.wj, &sh.wj2, &sh.px, &sh.pr1, &sh.pr2};
+            for (int i = 0; i < 256; i++)      // the kernel's compile-time DFT tables against the host construction
+                if (sh.w16f[i] != sn_make_w16(false).v[i] || sh.w16i[i] != sn_make_w16(true).v[i]) { ctx_free(c); return fail(KOSK_E_UNSUPPORTED, "share_ntt: DFT table mismatch (internal error)"); }
+            // one byte blob, every part 16-byte aligned
+            std::vector<uint8_t> all;
             size_t offs[8]; int np = 0;
-            for (const std::vector<int16_t> *v : parts) { offs[np++] = all.size(); all.insert(all.end(), v->begin(), v->end()); while (all.size() % 8) all.push_back(0); }
-            ALLOC(c->d_sn, all.size() * 2); CUC(cudaMemcpy(c->d_sn, all.data(), all.size() * 2, cudaMemcpyHostToDevice));
-            c->sn.tw = c->d_sn + offs[0]; c->sn.kh_share = c->d_sn + offs[1]; c->sn.kh_m256 = c->d_sn + offs[2]; c->sn.wj = c->d_sn + offs[3];
-            c->sn.wj2 = c->d_sn + offs[4]; c->sn.px = c->d_sn + offs[5]; c->sn.pr1 = c->d_sn + offs[6]; c->sn.pr2 = c->d_sn + offs[7];
+            auto put = [&](const void *p, size_t bytes) { offs[np++] = all.size(); const uint8_t *q = static_cast<const uint8_t *>(p); all.insert(all.end(), q, q + bytes); while (all.size() % 16) all.push_back(0); };
+            put(sh.tw.data(), sh.tw.size() * sizeof(int2)); put(sh.kh_share.data(), sh.kh_share.size() * 2); put(sh.kh_m256.data(), sh.kh_m256.size() * 2);
+            put(sh.wj.data(), sh.wj.size() * sizeof(int2)); put(sh.wj2.data(), sh.wj2.size() * sizeof(int2)); put(sh.px.data(), sh.px.size() * sizeof(int2));
+            put(sh.pr1.data(), sh.pr1.size() * sizeof(int2)); put(sh.pr2.data(), sh.pr2.size() * sizeof(int2));
+            ALLOC(c->d_sn, all.size()); CUC(cudaMemcpy(c->d_sn, all.data(), all.size(), cudaMemcpyHostToDevice));
+            const uint8_t *base = reinterpret_cast<const uint8_t *>(c->d_sn);
+            c->sn.tw = reinterpret_cast<const int2 *>(base + offs[0]); c->sn.kh_share = reinterpret_cast<const int16_t *>(base + offs[1]);
+            c->sn.kh_m256 = reinterpret_cast<const int16_t *>(base + offs[2]); c->sn.wj = reinterpret_cast<const int2 *>(base + offs[3]);
+            c->sn.wj2 = reinterpret_cast<const int2 *>(base + offs[4]); c->sn.px = reinterpret_cast<const int2 *>(base + offs[5]);
+            c->sn.pr1 = reinterpret_cast<const int2 *>(base + offs[6]); c->sn.pr2 = reinterpret_cast<const int2 *>(base + offs[7]);
         }
         std::vector<uint16_t> fc(2 * FACT_N);
         { uint32_t f = 1; for (int i = 0; i < FACT_N; i++) { if (i) f = f * i % Q; fc[i] = (uint16_t)f; fc[FACT_N + i] = inv[f]; } }
@@ -522,7 +529,7 @@ static int prove_chunk(kosk_b200_ctx *c, Lane &ln, const ProveBufs &bufs, int B,
         k_fs2<<<(B + 3) / 4, 128, 0, st>>>(pb.VWR, pb.I, pb.REST, B);
     }
     prof_mark(c, ln, KOSK_PH_ASSEMBLE);
-    k_assemble<K><<<dim3((NT + 31) / 32 + (NR + 31) / 32, B), 128, 0, st>>>(pb);
+    k_assemble<K><<<dim3(ASM_OPENED_CTAS + (NR + ASM_REST_ROWS - 1) / ASM_REST_ROWS, B), 256, 0, st>>>(pb);
     prof_mark(c, ln, -1);
     CU(cudaEventRecord(ln.computed, st)); c->last_computed = ln.computed;
     c->last_gate = tail_gate ? tail_gate : ln.computed;
@@ -994,6 +1001,61 @@ int kosk_b200_pool_prove(kosk_b200_pool *p, uint8_t *pk, uint8_t *sk, uint8_t *p
     return KOSK_OK;
 }
 
+// ---- pool serialiser: the working form of the reference's unused prepare_randomness (de)serialiser (mlwe_prover.cpp:61-79, which drops the
+// range-proof half).  Image = header | seeds[n][32] | Y[n][n2][YLD] u16 (every sharing's 256 secrets and 151 tail randoms, the prove-time
+// ones included: they are functions of the seed) | planes[n][s0][SLD] u16 (the evaluated f / NTT_f / eta sharings).  It holds the seeds:
+// treat it like a secret key.
+struct PoolHeader { char magic[8]; uint32_t version, k, n, n2, s0, yld, sld, reserved; };
+static const char POOL_MAGIC[8] = {'K', 'O', 'S', 'K', 'P', 'O', 'O', 'L'};
+static size_t pool_image_bytes(const kosk_b200_ctx *c, size_t n)
+{
+    return sizeof(PoolHeader) + n * (32 + (size_t)c->sl.n2 * YLD * 2 + (size_t)c->sl.s0 * SLD * 2);
+}
+size_t kosk_b200_pool_bytes(const kosk_b200_pool *p) { return p ? pool_image_bytes(p->ctx, p->n) : 0; }
+
+int kosk_b200_pool_export(kosk_b200_pool *p, void *image, size_t bytes)
+{
+    if (!p || !image) return fail(KOSK_E_ARG, "null argument");
+    kosk_b200_ctx *c = p->ctx;
+    LOCK(c);
+    if (bytes < pool_image_bytes(c, p->n)) return fail(KOSK_E_ARG, "image buffer too small (kosk_b200_pool_bytes)");
+    CU(cudaSetDevice(c->device));
+    const Slots &sl = c->sl; const size_t n = p->n;
+    PoolHeader h{}; memcpy(h.magic, POOL_MAGIC, 8); h.version = 1; h.k = (uint32_t)c->k; h.n = (uint32_t)n; h.n2 = (uint32_t)sl.n2; h.s0 = (uint32_t)sl.s0; h.yld = YLD; h.sld = SLD;
+    u8 *o = static_cast<u8 *>(image);
+    memcpy(o, &h, sizeof h); o += sizeof h;
+    CU(cudaStreamSynchronize(c->lanes[0].st));
+    CU(cudaMemcpy(o, p->d_seeds, 32 * n, cudaMemcpyDeviceToHost)); o += 32 * n;
+    CU(cudaMemcpy(o, p->pb.Y, n * sl.n2 * YLD * 2, cudaMemcpyDeviceToHost)); o += n * sl.n2 * YLD * 2;
+    CU(cudaMemcpy2D(o, (size_t)sl.s0 * SLD * 2, p->pb.SH, (size_t)sl.nslot * SLD * 2, (size_t)sl.s0 * SLD * 2, n, cudaMemcpyDeviceToHost));
+    return KOSK_OK;
+}
+
+int kosk_b200_pool_import(kosk_b200_ctx *c, const void *image, size_t bytes, kosk_b200_pool **out)
+{
+    if (!c || !image || !out || bytes < sizeof(PoolHeader)) return fail(KOSK_E_ARG, "bad argument");
+    PoolHeader h; memcpy(&h, image, sizeof h);
+    const Slots &sl = c->sl;
+    if (memcmp(h.magic, POOL_MAGIC, 8) || h.version != 1) return fail(KOSK_E_ARG, "not a pool image");
+    if (h.k != (uint32_t)c->k || h.n2 != (uint32_t)sl.n2 || h.s0 != (uint32_t)sl.s0 || h.yld != YLD || h.sld != SLD) return fail(KOSK_E_ARG, "pool image of another KYBER_K / layout");
+    const size_t n = h.n;
+    if (n == 0 || n > 16384 || bytes < pool_image_bytes(c, n)) return fail(KOSK_E_ARG, "truncated pool image");
+    LOCK(c);
+    CU(cudaSetDevice(c->device));
+    kosk_b200_pool *p = new kosk_b200_pool; p->ctx = c; p->n = n; c->live_pools++;
+    if (alloc_prove_bufs(p->pb, sl, c->k, n, c->use_tensor != 0) != 0 || cudaMalloc((void **)&p->d_seeds, 32 * n) != cudaSuccess) {
+        kosk_b200_pool_destroy(p); return fail(KOSK_E_NOMEM, "cudaMalloc failed for the preprocessing pool");
+    }
+    const u8 *o = static_cast<const u8 *>(image) + sizeof h;
+    cudaError_t e = cudaMemcpy(p->d_seeds, o, 32 * n, cudaMemcpyHostToDevice); o += 32 * n;
+    if (e == cudaSuccess) e = cudaMemcpy(p->pb.Y, o, n * sl.n2 * YLD * 2, cudaMemcpyHostToDevice);
+    o += n * sl.n2 * YLD * 2;
+    if (e == cudaSuccess) e = cudaMemcpy2D(p->pb.SH, (size_t)sl.nslot * SLD * 2, o, (size_t)sl.s0 * SLD * 2, (size_t)sl.s0 * SLD * 2, n, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { kosk_b200_pool_destroy(p); return fail(KOSK_E_CUDA, cudaGetErrorString(e)); }
+    *out = p;
+    return KOSK_OK;
+}
+
 int kosk_b200_share_eval_device(kosk_b200_ctx *c, size_t n, const uint16_t *d_y, uint16_t *d_planes, void *stream)
 {
     if (!c || !d_y || !d_planes) return fail(KOSK_E_ARG, "null argument");
@@ -1159,7 +1221,8 @@ __global__ void __launch_bounds__(256) k_int_peak(uint32_t *out, int iters, uint
             for (int i = 0; i < 16; i++) {
                 if (MODE == 0) r[i] = r[i] * m + x;                                   // IMAD (fma pipe)
                 else if (MODE == 1) r[i] = r[i] ^ (~r[(i + 1) & 15] & m);                  // LOP3 (alu pipe)
-                else r[i] = __funnelshift_l(r[i], r[(i + 5) & 15], 7);                 // SHF (alu pipe)
+                else if (MODE == 2) r[i] = __funnelshift_l(r[i], r[(i + 5) & 15], 7);  // SHF (alu pipe)
+                else r[i] = (uint32_t)__mulhi((int)r[i], (int)m) + x;                  // IMAD.HI (fma pipe: is the high half full rate?)
             }
     }
     uint32_t acc = 0;
@@ -1185,7 +1248,7 @@ __global__ void __launch_bounds__(256) k_imma_peak(int32_t *out, int iters)
     if (acc == 0x12345678) out[blockIdx.x] = acc;
 }
 
-extern "C" int kosk_b200_int_peak(kosk_b200_ctx *c, double *ops_per_s /* [4]: IMAD, LOP3, SHF thread-ops/s, IMMA int8 MAC/s */)
+extern "C" int kosk_b200_int_peak(kosk_b200_ctx *c, double *ops_per_s /* [5]: IMAD, LOP3, SHF thread-ops/s, IMMA int8 MAC/s, IMAD.HI thread-ops/s */)
 {
     if (!c || !ops_per_s) return fail(KOSK_E_ARG, "null argument");
     CU(cudaSetDevice(c->device));
@@ -1193,19 +1256,20 @@ extern "C" int kosk_b200_int_peak(kosk_b200_ctx *c, double *ops_per_s /* [4]: IM
     const int blocks = prop.multiProcessorCount * 8, iters = 4096;
     uint32_t *d = nullptr; CU(cudaMalloc(&d, blocks * 4));
     cudaEvent_t e0, e1; CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
-    for (int mode = 0; mode < 3; mode++) {
+    for (int mode = 0; mode < 4; mode++) {
         float best = 1e30f;
         for (int rep = 0; rep < 4; rep++) {
             CU(cudaEventRecord(e0, c->lanes[0].st));
             if (mode == 0) k_int_peak<0><<<blocks, 256, 0, c->lanes[0].st>>>(d, iters, 12345u + rep);
             else if (mode == 1) k_int_peak<1><<<blocks, 256, 0, c->lanes[0].st>>>(d, iters, 12345u + rep);
-            else k_int_peak<2><<<blocks, 256, 0, c->lanes[0].st>>>(d, iters, 12345u + rep);
+            else if (mode == 2) k_int_peak<2><<<blocks, 256, 0, c->lanes[0].st>>>(d, iters, 12345u + rep);
+            else k_int_peak<3><<<blocks, 256, 0, c->lanes[0].st>>>(d, iters, 12345u + rep);
             CU(cudaEventRecord(e1, c->lanes[0].st));
             CU(cudaEventSynchronize(e1));
             float ms = 0; CU(cudaEventElapsedTime(&ms, e0, e1));
             if (rep > 0 && ms < best) best = ms;
         }
-        ops_per_s[mode] = (double)blocks * 256.0 * iters * 64.0 / (best * 1e-3);
+        ops_per_s[mode == 3 ? 4 : mode] = (double)blocks * 256.0 * iters * 64.0 / (best * 1e-3);
     }
     {
         float best = 1e30f; const int it2 = 8192;

@@ -813,88 +813,152 @@ __global__ void __launch_bounds__(128) k_derive(ProveBufs pb)
 }
 
 // ---------------------------------------------------------------------------------------------
-// Proof assembly (mlwe_prover.cpp:480-537): gather the opened-set and rest-set fields into the packed
-// byte layout of struct mpcith_proof.  grid = (row tiles, B); tile 0..T_TILES-1 = opened rows.
+// Proof assembly (mlwe_prover.cpp:480-537): gather the opened-set and rest-set fields into the packed byte layout of struct
+// mpcith_proof.  grid = (ASM_OPENED_CTAS + rest tiles, B), 256 threads.
+//   Opened set (150 parties in the order of I, ~220 planes each): an element-wise gather costs one 32-byte sector per 2 useful bytes and
+//   is bound by DRAM latency (round 1: 1.53 GB read for 0.68 GB of proof, DRAM at 43 %).  Instead a CTA streams whole plane rows (2.9 KB,
+//   coalesced 16-byte loads), picks the 150 opened parties of each row through shared memory into a compact [plane][opened] tile and
+//   emits its fields from that tile with coalesced stores.  Three CTAs per proof: the f planes, the NTT_f planes, everything else.
+//   Rest set (1304 parties in ascending order): tiles of 64 consecutive rest parties; their plane reads are near-contiguous.
+constexpr int ASM_OPENED_CTAS = 3, ASM_RB = 4, ASM_OS = 154, ASM_REST_ROWS = 64;
+template <int K> struct AsmPlanes {              // local plane numbering of the "everything else" CTA
+    static constexpr int ETA = (K == 2) ? 3 : 2, E = 2 * ETA + 1, M = 2 * ETA;
+    static constexpr int S = 0, Ee = K, TSR = 2 * K, TER = 3 * K, ASR = 4 * K, AS = 5 * K, TR = 6 * K, SETA = 8 * K, EETA = SETA + K * E, ZS = EETA + K * E, ZE = ZS + K * M,
+                         N = ZE + K * M;
+    __device__ static int slot(const Slots &sl, int l)
+    {
+        if (l < Ee) return sl.s0 + l;
+        if (l < TSR) return sl.e0 + (l - Ee);
+        if (l < TER) return sl.Tsr0 + (l - TSR);
+        if (l < ASR) return sl.Ter0 + (l - TER);
+        if (l < AS) return sl.Asr0 + (l - ASR);
+        if (l < TR) return sl.As0 + (l - AS);
+        if (l < SETA) return sl.TR0 + (l - TR);
+        if (l < EETA) return sl.seta0 + (l - SETA);
+        if (l < ZS) return sl.eeta0 + (l - EETA);
+        if (l < ZE) return sl.zs0 + (l - ZS);
+        return sl.ze0 + (l - ZE);
+    }
+};
+
 template <int K>
-__global__ void __launch_bounds__(128) k_assemble(ProveBufs pb)
+__global__ void __launch_bounds__(256) k_assemble(ProveBufs pb)
 {
     constexpr int ETA = (K == 2) ? 3 : 2, E = 2 * ETA + 1, M = 2 * ETA, F = MK + 2 * K + 1;
-    constexpr int ROWS = 32, T_TILES = (NT + ROWS - 1) / ROWS;
+    using AP = AsmPlanes<K>;
+    constexpr int NPLMAX = AP::N > F ? AP::N : F;
     const Slots sl = make_slots(K);
     const Layout L = make_layout(K);
     const int b = blockIdx.y, tid = threadIdx.x;
     u8 *pi = pb.pi + L.proof_bytes * (size_t)b;
-    const u16 *I = pb.I + (size_t)b * NT, *rest = pb.REST + (size_t)b * NR;
-    auto P = [&](int slot, int p) -> uint32_t { return plane(pb, sl, b, slot)[p]; };
     auto out16 = [&](size_t off, size_t idx) -> u16 * { return reinterpret_cast<u16 *>(pi + off) + idx; };
-    __shared__ u16 sp[ROWS];
-    if ((int)blockIdx.x < T_TILES) {
-        const int r0 = blockIdx.x * ROWS, nr = min(ROWS, NT - r0);
-        if (tid < nr) { sp[tid] = I[r0 + tid]; *out16(L.o_I, r0 + tid) = sp[tid]; }
-        __syncthreads();
-        // every element of an opened party sits in a different plane (one 32-byte sector per 2 useful bytes): keep eight gathers in
-        // flight per thread, the loop is bound by DRAM latency otherwise
-        for (int base = tid; base < nr * F; base += 128 * 4) {
-            uint32_t vf[4], vt[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int idx = base + u * 128;
-                if (idx < nr * F) { const int r = idx / F, j = idx % F, p = sp[r]; vf[u] = P(sl.f0 + j, p); vt[u] = P(sl.Tf0 + j, p); }
+    __shared__ u16 sI[NT + 2];
+    __shared__ __align__(16) u16 srow[ASM_RB][SLD];
+    __shared__ u16 sO[NPLMAX][ASM_OS];
+    if ((int)blockIdx.x < ASM_OPENED_CTAS) {
+        const int grp = blockIdx.x, npl = grp < 2 ? F : AP::N;
+        const u16 *I = pb.I + (size_t)b * NT;
+        for (int i = tid; i < NT; i += 256) sI[i] = I[i];
+        // ---- compact: O[l][r] = plane(l)[I[r]] ----
+        const u16 *planes = pb.SH + (size_t)b * sl.nslot * SLD;
+        for (int base = 0; base < npl; base += ASM_RB) {
+            const int nrow = min(ASM_RB, npl - base);
+            __syncthreads();                                  // previous rows consumed (and sI visible)
+            for (int idx = tid; idx < nrow * (SLD / 8); idx += 256) {
+                const int r = idx / (SLD / 8), c = idx % (SLD / 8), l = base + r;
+                const int slot = grp == 0 ? sl.f0 + l : grp == 1 ? sl.Tf0 + l : AP::slot(sl, l);
+                reinterpret_cast<uint4 *>(srow[r])[c] = __ldcs(reinterpret_cast<const uint4 *>(planes + (size_t)slot * SLD) + c);
             }
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int idx = base + u * 128;
-                if (idx < nr * F) { const int r = idx / F, j = idx % F; *out16(L.o_f, (size_t)(r0 + r) * F + j) = (u16)vf[u]; *out16(L.o_Tf, (size_t)(r0 + r) * F + j) = (u16)vt[u]; }
+            __syncthreads();
+            for (int idx = tid; idx < nrow * NT; idx += 256) {
+                const int r = idx / NT, i = idx % NT;
+                sO[base + r][i] = srow[r][SOFF + sI[i]];
             }
         }
-        for (int idx = tid; idx < nr * K; idx += 128) {
-            const int r = idx / K, j = idx % K, p = sp[r];
-            const size_t o = (size_t)(r0 + r) * K + j;
-            const uint32_t s = P(sl.s0 + j, p), e = P(sl.e0 + j, p), As = P(sl.As0 + j, p);
-            const uint32_t Te = gf_sub(P(sl.Ter0 + j, p), P(sl.TR0 + K + j, p));
-            *out16(L.o_s, o) = (u16)s; *out16(L.o_e, o) = (u16)e;
-            *out16(L.o_NTTs, o) = (u16)gf_sub(P(sl.Tsr0 + j, p), P(sl.TR0 + j, p));
-            *out16(L.o_NTTe, o) = (u16)Te;
-            *out16(L.o_NTTAr, o) = (u16)gf_sub(P(sl.Asr0 + j, p), As);
-            *out16(L.o_NTTAs, o) = (u16)As;
-            for (int m = 0; m < E; m++) {
-                *out16(L.o_ssub, o * E + m) = (u16)gf_sub(s, P(sl.seta0 + j * E + m, p));
-                *out16(L.o_esub, o * E + m) = (u16)gf_sub(e, P(sl.eeta0 + j * E + m, p));
+        __syncthreads();
+        // ---- emit ----
+        if (grp < 2) {                                        // f_shares / NTT_f_shares [T][F]: two elements per 32-bit store
+            uint32_t *dst = reinterpret_cast<uint32_t *>(pi + (grp == 0 ? L.o_f : L.o_Tf));
+            for (int w = tid; w < NT * F / 2; w += 256) {
+                const int e0 = 2 * w, r0 = e0 / F, j0 = e0 % F, e1 = e0 + 1, r1 = e1 / F, j1 = e1 % F;
+                dst[w] = (uint32_t)sO[j0][r0] | ((uint32_t)sO[j1][r1] << 16);
             }
-            for (int m = 0; m < M; m++) {
-                *out16(L.o_zs, o * M + m) = (u16)P(sl.zs0 + j * M + m, p);
-                *out16(L.o_ze, o * M + m) = (u16)P(sl.ze0 + j * M + m, p);
+        } else {
+            for (int i = tid; i < NT; i += 256) *out16(L.o_I, i) = sI[i];
+            for (int idx = tid; idx < NT * K; idx += 256) {
+                const int r = idx / K, j = idx % K;
+                const uint32_t As = sO[AP::AS + j][r];
+                *out16(L.o_s, idx) = sO[AP::S + j][r];
+                *out16(L.o_e, idx) = sO[AP::Ee + j][r];
+                *out16(L.o_NTTs, idx) = (u16)gf_sub(sO[AP::TSR + j][r], sO[AP::TR + j][r]);
+                *out16(L.o_NTTe, idx) = (u16)gf_sub(sO[AP::TER + j][r], sO[AP::TR + K + j][r]);
+                *out16(L.o_NTTAr, idx) = (u16)gf_sub(sO[AP::ASR + j][r], As);
+                *out16(L.o_NTTAs, idx) = (u16)As;
+            }
+            for (int idx = tid; idx < NT * K * E; idx += 256) {
+                const int r = idx / (K * E), jm = idx % (K * E), j = jm / E;
+                *out16(L.o_ssub, idx) = (u16)gf_sub(sO[AP::S + j][r], sO[AP::SETA + jm][r]);
+                *out16(L.o_esub, idx) = (u16)gf_sub(sO[AP::Ee + j][r], sO[AP::EETA + jm][r]);
+            }
+            for (int idx = tid; idx < NT * K * M; idx += 256) {
+                const int r = idx / (K * M), jm = idx % (K * M);
+                *out16(L.o_zs, idx) = sO[AP::ZS + jm][r];
+                *out16(L.o_ze, idx) = sO[AP::ZE + jm][r];
             }
         }
     } else {
-        const int r0 = (blockIdx.x - T_TILES) * ROWS, nr = min(ROWS, NR - r0);
-        if (tid < nr) sp[tid] = rest[r0 + tid];
+        // The loops below are latency-bound unless several loads are in flight per thread: all sources are read through the non-coherent
+        // path (nothing this kernel writes is read back), so the compiler may hoist the loads of an unrolled body above its stores.
+        constexpr int ROWS = ASM_REST_ROWS;
+        const u16 *rest = pb.REST + (size_t)b * NR;
+        const u16 *__restrict__ planes = pb.SH + (size_t)b * sl.nslot * SLD + SOFF;
+        auto P = [&](int slot, int p) -> uint32_t { return __ldg(planes + (size_t)slot * SLD + p); };
+        const int r0 = (blockIdx.x - ASM_OPENED_CTAS) * ROWS, nr = min(ROWS, NR - r0);
+        if (tid < nr) sI[tid] = rest[r0 + tid];
         __syncthreads();
-        for (int idx = tid; idx < nr * MK; idx += 128) {
-            const int r = idx / MK, j = idx % MK, p = sp[r];
-            const u16 *bg = pb.BG + ((size_t)b * NP + p) * (2 * BGH);
-            *out16(L.o_beta, (size_t)(r0 + r) * MK + j) = bg[j];
-            *out16(L.o_gamma, (size_t)(r0 + r) * MK + j) = bg[BGH + j];
-        }
-        for (int idx = tid; idx < nr * 8; idx += 128) {         // 32-byte digests as 8 x u32 (proofs are only 4-byte aligned)
-            const int r = idx / 8, w = idx % 8, p = sp[r];
-            reinterpret_cast<uint32_t *>(pi + L.o_Tcomm)[(size_t)(r0 + r) * 8 + w] = reinterpret_cast<const uint32_t *>(pb.TCR + ((size_t)b * NP + p) * 32)[w];
-            reinterpret_cast<uint32_t *>(pi + L.o_comm)[(size_t)(r0 + r) * 8 + w] = reinterpret_cast<const uint32_t *>(pb.VWR + ((size_t)b * NP + p) * 32)[w];
-        }
-        for (int idx = tid; idx < nr * K; idx += 128) {
-            const int r = idx / K, j = idx % K, p = sp[r];
-            const size_t o = (size_t)(r0 + r) * K + j;
-            *out16(L.o_sr, o) = (u16)P(sl.SR0 + j, p);
-            *out16(L.o_er, o) = (u16)P(sl.ER0 + j, p);
-            *out16(L.o_t, o) = (u16)gf_add(P(sl.As0 + j, p), gf_sub(P(sl.Ter0 + j, p), P(sl.TR0 + K + j, p)));
-            for (int m = 0; m < E; m++) {
-                *out16(L.o_seta, o * E + m) = (u16)P(sl.seta0 + j * E + m, p);
-                *out16(L.o_eeta, o * E + m) = (u16)P(sl.eeta0 + j * E + m, p);
+        {   // beta / gamma [R][70]: rows of 70 u16 = 35 words, source rows 16-byte aligned, destination 4-byte aligned
+            uint32_t *__restrict__ db = reinterpret_cast<uint32_t *>(pi + L.o_beta) + (size_t)r0 * (MK / 2);
+            uint32_t *__restrict__ dg = reinterpret_cast<uint32_t *>(pi + L.o_gamma) + (size_t)r0 * (MK / 2);
+            const uint32_t *__restrict__ bgb = reinterpret_cast<const uint32_t *>(pb.BG + (size_t)b * NP * (2 * BGH));
+            constexpr int U = 5;
+            for (int base = tid; base < nr * (MK / 2); base += 256 * U) {
+                uint32_t vb[U], vg[U];
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    const int idx = base + 256 * u;
+                    if (idx < nr * (MK / 2)) { const int r = idx / (MK / 2), w = idx % (MK / 2); const uint32_t *bg = bgb + (size_t)sI[r] * BGH; vb[u] = __ldg(bg + w); vg[u] = __ldg(bg + BGH / 2 + w); }
+                }
+#pragma unroll
+                for (int u = 0; u < U; u++) { const int idx = base + 256 * u; if (idx < nr * (MK / 2)) { db[idx] = vb[u]; dg[idx] = vg[u]; } }
             }
-            for (int m = 0; m < M; m++) {
-                *out16(L.o_us, o * M + m) = (u16)P(sl.US0 + j * M + m, p);
-                *out16(L.o_ue, o * M + m) = (u16)P(sl.UE0 + j * M + m, p);
+        }
+        {   // 32-byte digests as 8 x u32 (proofs are only 4-byte aligned)
+            uint32_t *__restrict__ dt = reinterpret_cast<uint32_t *>(pi + L.o_Tcomm) + (size_t)r0 * 8, *__restrict__ dc = reinterpret_cast<uint32_t *>(pi + L.o_comm) + (size_t)r0 * 8;
+            const uint32_t *__restrict__ tcr = reinterpret_cast<const uint32_t *>(pb.TCR + (size_t)b * NP * 32), *__restrict__ vwr = reinterpret_cast<const uint32_t *>(pb.VWR + (size_t)b * NP * 32);
+            uint32_t vt[2], vc[2];
+#pragma unroll
+            for (int u = 0; u < 2; u++) { const int idx = tid + 256 * u; if (idx < nr * 8) { const int p = sI[idx / 8]; vt[u] = __ldg(tcr + (size_t)p * 8 + idx % 8); vc[u] = __ldg(vwr + (size_t)p * 8 + idx % 8); } }
+#pragma unroll
+            for (int u = 0; u < 2; u++) { const int idx = tid + 256 * u; if (idx < nr * 8) { dt[idx] = vt[u]; dc[idx] = vc[u]; } }
+        }
+        {   // sr, er, t [R][K]; s_eta, e_eta [R][K][E]; u_s, u_e [R][K][M]: all loads first, then the stores
+            constexpr int NKE = (ROWS * K * E + 255) / 256, NKM = (ROWS * K * M + 255) / 256;
+            uint32_t vk[5], ve[NKE][2], vm[NKM][2];
+            const bool hk = tid < nr * K;
+            if (hk) { const int r = tid / K, j = tid % K, p = sI[r]; vk[0] = P(sl.SR0 + j, p); vk[1] = P(sl.ER0 + j, p); vk[2] = P(sl.As0 + j, p); vk[3] = P(sl.Ter0 + j, p); vk[4] = P(sl.TR0 + K + j, p); }
+#pragma unroll
+            for (int u = 0; u < NKE; u++) { const int idx = tid + 256 * u; if (idx < nr * K * E) { const int p = sI[idx / (K * E)], jm = idx % (K * E); ve[u][0] = P(sl.seta0 + jm, p); ve[u][1] = P(sl.eeta0 + jm, p); } }
+#pragma unroll
+            for (int u = 0; u < NKM; u++) { const int idx = tid + 256 * u; if (idx < nr * K * M) { const int p = sI[idx / (K * M)], jm = idx % (K * M); vm[u][0] = P(sl.US0 + jm, p); vm[u][1] = P(sl.UE0 + jm, p); } }
+            if (hk) {
+                const size_t o = (size_t)r0 * K + tid;
+                *out16(L.o_sr, o) = (u16)vk[0]; *out16(L.o_er, o) = (u16)vk[1];
+                *out16(L.o_t, o) = (u16)gf_add(vk[2], gf_sub(vk[3], vk[4]));
             }
+#pragma unroll
+            for (int u = 0; u < NKE; u++) { const int idx = tid + 256 * u; if (idx < nr * K * E) { const size_t o = (size_t)r0 * K * E + idx; *out16(L.o_seta, o) = (u16)ve[u][0]; *out16(L.o_eeta, o) = (u16)ve[u][1]; } }
+#pragma unroll
+            for (int u = 0; u < NKM; u++) { const int idx = tid + 256 * u; if (idx < nr * K * M) { const size_t o = (size_t)r0 * K * M + idx; *out16(L.o_us, o) = (u16)vm[u][0]; *out16(L.o_ue, o) = (u16)vm[u][1]; } }
         }
     }
 }

@@ -22,10 +22,49 @@
 namespace kosk {
 
 constexpr int SN_NIN = 4, SN_NOUT = 11;                                  // the sharing: 407 inputs in 4 blocks, 1303 outputs in 11
-constexpr int SN_WARPS = 4;                                              // rows in flight per CTA
+#ifndef KOSK_SN_WARPS
+#define KOSK_SN_WARPS 4
+#endif
+#ifndef KOSK_SN_MINB
+#define KOSK_SN_MINB 4
+#endif
+constexpr int SN_WARPS = KOSK_SN_WARPS;                                  // rows in flight per CTA
 constexpr int SN_LD = 24;               // int16 per k1 row of a spectrum in shared memory: 16 values (k2) + pad, so that the 128-bit row reads of a quarter-warp hit distinct banks
 
-__constant__ int32_t c_sn_w16f[256], c_sn_w16i[256];   // w16^(+-a k) * R, centered; w16 = 17^16
+// w16^(+-a k), centered; w16 = 17^16.  Compile-time tables: on sm_100a an IMAD takes no constant-bank operand (every c[] use became
+// a separate LDC into a register: 159 of the 1158 instructions of an inverse pass), but with the loops unrolled a value folded from a
+// constant initialiser is a 32-bit immediate of the IMAD itself.
+struct SnW16 { int32_t v[256]; };
+constexpr uint32_t sn_cpow(uint32_t b, uint32_t e) { uint32_t r = 1; b %= Q; while (e) { if (e & 1) r = r * b % Q; b = b * b % Q; e >>= 1; } return r; }
+constexpr int32_t sn_ccenter(uint32_t v) { return (int32_t)(v % Q) > Q / 2 ? (int32_t)(v % Q) - Q : (int32_t)(v % Q); }
+constexpr SnW16 sn_make_w16(bool inv)
+{
+    SnW16 t{};
+    const uint32_t om16 = sn_cpow(17, 16), w = inv ? sn_cpow(om16, Q - 2) : om16;
+    for (int a = 0; a < 16; a++) for (int k = 0; k < 16; k++) t.v[a * 16 + k] = sn_ccenter(sn_cpow(w, (uint32_t)(a * k)));
+    return t;
+}
+__device__ constexpr SnW16 c_sn_w16f_tab = sn_make_w16(false), c_sn_w16i_tab = sn_make_w16(true);
+#define c_sn_w16f c_sn_w16f_tab.v
+#define c_sn_w16i c_sn_w16i_tab.v
+
+// Modular arithmetic of the kernel (all on the FMA pipe, no shifts or sign extensions on the ALU pipe):
+//   sn_barrett(a)      a mod q          in (-105, 2q)   for |a| < 2^28:  a - mulhi(a, floor(2^32 / q)) q
+//   sn_shoup(s, w, w') s w mod q        in (-105, q + 105) for |s| < 2^28, a constant w in [-1664, 1664] and its companion
+//                                       w' = round(w 2^32 / q):  s w - mulhi(s, w') q  (32-bit wrapping; the true value is small)
+// Lazy sums of at most 16 products of such values with centered constants stay below 2^28 (16 x 6658 x 1664 = 1.8e8).
+constexpr int32_t SN_BARRETT_M = (int32_t)((1ull << 32) / Q);
+__device__ __forceinline__ int32_t sn_barrett(int32_t a) { return a - __mulhi(a, SN_BARRETT_M) * Q; }
+__device__ __forceinline__ int32_t sn_shoup(int32_t s, int32_t w, int32_t wp)
+{
+    return (int32_t)((uint32_t)s * (uint32_t)w - (uint32_t)__mulhi(s, wp) * (uint32_t)Q);
+}
+__host__ __device__ inline int2 sn_pair(uint32_t v)                  // residue -> (centered w, w' = round(w 2^32 / q))
+{
+    const int32_t w = (int32_t)(v % Q) > Q / 2 ? (int32_t)(v % Q) - Q : (int32_t)(v % Q);
+    const long long num = (long long)w * 4294967296LL;
+    return make_int2(w, (int32_t)((num >= 0 ? num + Q / 2 : num - Q / 2) / Q));
+}
 
 // One Toeplitz product per row:  C[row][c_off + x] = post[x] * sum_j c[x - j + OFF] * (pre[j] * A[row][j]),  c[m] = 1/m (0 for m = 0),
 // x < nout <= 128 NOUT, j < nin <= 128 NIN.  OFF lives in the kernel-segment table `khat` ([NIN + NOUT - 1] segments for o - i).
@@ -37,41 +76,36 @@ struct ConvArgs {
     const u16 *A; u16 *C; long long lda, ldc;
     int mtotal, rpp, slot_lo, a_slots, c_slots, c_off;   // row m -> storage row (m / rpp) * slots + slot_lo + m % rpp
     int tail, tail_off;                                  // sharing: copy the 151 tail values to parties 0..150
-    const int16_t *tw;       // [2][16][16]  17^(+-b k1) * R (symmetric in b, k1)
-    const int16_t *khat;     // [NIN + NOUT - 1][16 k1][SN_LD]  NTT(K_delta)[k1 + 16 k2] / 256 * R at [k1][k2], delta = o - i
-    const int16_t *pre;      // [128 NIN] input factors * R, or nullptr
-    const u16 *post;         // output factors * R mod q as 16-bit patterns (int16 centered or u16 canonical: both are residues)
-    long long post_group;    // 0: one table; else the table of row m starts at post + (m / rpp) * post_group, entries are u16
+    const int2 *tw;          // [2][16][16]  (w, w') of 17^(+-b k1) (symmetric in b, k1)
+    const int16_t *khat;     // [NIN + NOUT - 1][16 k1][SN_LD]  NTT(K_delta)[k1 + 16 k2] / 256, centered, at [k1][k2], delta = o - i
+    const int2 *pre;         // [128 NIN] (w, w') of the input factors, or nullptr
+    const int2 *post;        // (w, w') of the output factors
+    long long post_group;    // 0: one table; else the table of row m starts at post + (m / rpp) * post_group
 };
-
-__device__ __forceinline__ int32_t sn_montred(int32_t a)            // a * 2^-16 mod q in (-q, q) for |a| < q * 2^15
-{
-    const int32_t t = (int32_t)(int16_t)(a * -3327);               // q^-1 mod 2^16 = -3327 (kyber/reduce.h)
-    return (a - t * Q) >> 16;
-}
 
 // NINV / NOUTV = valid inputs / outputs, PRE = input factors present, PGROUP = per-row-group output factors: compile-time, so that
 // the sharing's kernel carries none of the other products' branches
 template <int NIN, int NOUT, int NINV, int NOUTV, bool PRE, bool PGROUP>
-__global__ void __launch_bounds__(32 * SN_WARPS, (NIN <= 5 ? 4 : 3)) k_conv_ntt(const ConvArgs g)
+__global__ void __launch_bounds__(32 * SN_WARPS, (NIN <= 5 ? KOSK_SN_MINB : KOSK_SN_MINB - 1)) k_conv_ntt(const ConvArgs g)
 {
     constexpr int NK = NIN + NOUT - 1, NINP = (NIN + 1) & ~1;
     __shared__ __align__(16) int16_t s_kh[NK * 16 * SN_LD];
-    __shared__ int16_t s_tw[2 * 256];
+    __shared__ __align__(8) int2 s_tw[2 * 256];
     __shared__ __align__(16) int16_t s_uh[SN_WARPS][NINP][16 * SN_LD];
-    __shared__ int32_t s_t[SN_WARPS][2][16 * 17];
+    // transpose buffers, one per half-warp: rows of 17 int16; 288 = 32 (mod 64) int16 puts the second half-warp's 16 banks between the first's
+    __shared__ int16_t s_t[SN_WARPS][2][288];
     for (int i = threadIdx.x; i < NK * 16 * SN_LD; i += blockDim.x) s_kh[i] = g.khat[i];
     for (int i = threadIdx.x; i < 512; i += blockDim.x) s_tw[i] = g.tw[i];
     __syncthreads();
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, hw = lane >> 4, c = lane & 15;
     int16_t (*uh)[16 * SN_LD] = s_uh[wid];
-    int32_t *T = s_t[wid][hw];
+    int16_t *T = s_t[wid][hw];
     auto lo16 = [](uint32_t w) -> int32_t { return (int32_t)(int16_t)(w & 0xFFFFu); };
     auto hi16 = [](uint32_t w) -> int32_t { return (int32_t)w >> 16; };
     for (int m = blockIdx.x * SN_WARPS + wid; m < g.mtotal; m += gridDim.x * SN_WARPS) {
         const u16 *yrow = g.A + ((size_t)(m / g.rpp) * g.a_slots + g.slot_lo + m % g.rpp) * g.lda;
         u16 *dst = g.C + ((size_t)(m / g.rpp) * g.c_slots + g.slot_lo + m % g.rpp) * g.ldc + g.c_off;
-        const u16 *post = g.post + (PGROUP ? (size_t)(m / g.rpp) * g.post_group : 0);
+        const int2 *post = g.post + (PGROUP ? (size_t)(m / g.rpp) * g.post_group : 0);
         if (g.tail) for (int t = lane; t <= NT; t += 32) dst[t - (NT + 1)] = yrow[g.tail_off + t];
         // ---- forward: u_j = pre_j A_j, NTT of the zero-padded 128-wide input blocks (two per pass) ----
 #pragma unroll 1
@@ -82,7 +116,10 @@ __global__ void __launch_bounds__(32 * SN_WARPS, (NIN <= 5 ? 4 : 3)) k_conv_ntt(
             for (int a = 0; a < 8; a++) {
                 const int j = 128 * blk + 16 * a + c;
                 int32_t v = 0;
-                if (j < NINV) v = PRE ? sn_montred((int32_t)yrow[j] * (int32_t)__ldg(g.pre + j)) : (int32_t)yrow[j];
+                if (j < NINV) {
+                    v = (int32_t)yrow[j];
+                    if (PRE) { const int2 p = __ldg(g.pre + j); v = sn_shoup(v, p.x, p.y); }
+                }
                 x[a] = v;
             }
             int32_t y[16];
@@ -92,11 +129,12 @@ __global__ void __launch_bounds__(32 * SN_WARPS, (NIN <= 5 ? 4 : 3)) k_conv_ntt(
                 int32_t ev = 0, od = 0;
 #pragma unroll
                 for (int a = 0; a < 8; a += 2) { ev += x[a] * c_sn_w16f[a * 16 + k]; od += x[a + 1] * c_sn_w16f[(a + 1) * 16 + k]; }
-                y[k] = sn_montred(sn_montred(ev + od) * (int32_t)s_tw[k * 16 + c]);
-                y[k + 8] = sn_montred(sn_montred(ev - od) * (int32_t)s_tw[(k + 8) * 16 + c]);
+                const int2 t0 = s_tw[k * 16 + c], t1 = s_tw[(k + 8) * 16 + c];
+                y[k] = sn_shoup(ev + od, t0.x, t0.y);
+                y[k + 8] = sn_shoup(ev - od, t1.x, t1.y);
             }
 #pragma unroll
-            for (int k = 0; k < 16; k++) T[k * 17 + c] = y[k];
+            for (int k = 0; k < 16; k++) T[k * 17 + c] = (int16_t)y[k];
             __syncwarp();
             int32_t in[16];
 #pragma unroll
@@ -107,7 +145,7 @@ __global__ void __launch_bounds__(32 * SN_WARPS, (NIN <= 5 ? 4 : 3)) k_conv_ntt(
                 int32_t ev = 0, od = 0;
 #pragma unroll
                 for (int b = 0; b < 16; b += 2) { ev += in[b] * c_sn_w16f[b * 16 + k]; od += in[b + 1] * c_sn_w16f[(b + 1) * 16 + k]; }
-                X[k] = sn_montred(ev + od); X[k + 8] = sn_montred(ev - od);
+                X[k] = sn_barrett(ev + od); X[k + 8] = sn_barrett(ev - od);
             }
             {   // row k1 = c of the spectrum: 16 values (k2) as two 128-bit stores
                 uint32_t w[8];
@@ -146,7 +184,7 @@ __global__ void __launch_bounds__(32 * SN_WARPS, (NIN <= 5 ? 4 : 3)) k_conv_ntt(
                     }
                 }
 #pragma unroll
-                for (int k = 0; k < 16; k++) O[k] = sn_montred(acc[k]);
+                for (int k = 0; k < 16; k++) O[k] = sn_barrett(acc[k]);
             }
             int32_t v[16];
 #pragma unroll
@@ -154,11 +192,12 @@ __global__ void __launch_bounds__(32 * SN_WARPS, (NIN <= 5 ? 4 : 3)) k_conv_ntt(
                 int32_t ev = 0, od = 0;
 #pragma unroll
                 for (int k = 0; k < 16; k += 2) { ev += O[k] * c_sn_w16i[k * 16 + b]; od += O[k + 1] * c_sn_w16i[(k + 1) * 16 + b]; }
-                v[b] = sn_montred(sn_montred(ev + od) * (int32_t)s_tw[256 + b * 16 + c]);
-                v[b + 8] = sn_montred(sn_montred(ev - od) * (int32_t)s_tw[256 + (b + 8) * 16 + c]);
+                const int2 t0 = s_tw[256 + b * 16 + c], t1 = s_tw[256 + (b + 8) * 16 + c];
+                v[b] = sn_shoup(ev + od, t0.x, t0.y);
+                v[b + 8] = sn_shoup(ev - od, t1.x, t1.y);
             }
 #pragma unroll
-            for (int b = 0; b < 16; b++) T[b * 17 + c] = v[b];
+            for (int b = 0; b < 16; b++) T[b * 17 + c] = (int16_t)v[b];
             __syncwarp();
             int32_t in[16];
 #pragma unroll
@@ -170,9 +209,11 @@ __global__ void __launch_bounds__(32 * SN_WARPS, (NIN <= 5 ? 4 : 3)) k_conv_ntt(
                 for (int k = 0; k < 16; k++) acc += in[k] * c_sn_w16i[k * 16 + a];
                 const int xo = 128 * o + 16 * a + c;
                 if (live && xo < NOUTV) {
-                    const int32_t pf = PGROUP ? (int32_t)post[xo] : (int32_t)(int16_t)__ldg(post + xo);
-                    int32_t r = sn_montred(sn_montred(acc) * pf);
-                    dst[xo] = (u16)(r < 0 ? r + Q : r);
+                    const int2 pf = PGROUP ? post[xo] : __ldg(post + xo);
+                    int32_t r = sn_shoup(acc, pf.x, pf.y);
+                    if (r < 0) r += Q;
+                    if (r >= Q) r -= Q;
+                    dst[xo] = (u16)r;
                 }
             }
             __syncwarp();
@@ -191,13 +232,13 @@ static inline int share_ntt_launch(const ConvArgs &g, cudaStream_t st) { return 
 
 // device tables of all Toeplitz products of the KOSK path (one allocation per context)
 struct ShareNttTables {
-    const int16_t *tw;
+    const int2 *tw;
     const int16_t *kh_share;      // OFF = 407, (4, 11)
     const int16_t *kh_m256;       // OFF = -256: segments delta in [-7, 3]; a product with (NIN, NOUT) starts at delta = -(NIN - 1)
-    const int16_t *wj;            // [512]   w_j * R over 407 consecutive nodes (0 beyond)
-    const int16_t *wj2;           // [896]   the same over 813 consecutive nodes
-    const int16_t *px;            // [1408]  P(x) * R of the sharing
-    const int16_t *pr1, *pr2;     // [256]   prod_m (i - 256 - m) * R for m < 407 / m < 813 (recon_secrets_ddeg / _2ddeg)
+    const int2 *wj;               // [512]   (w, w') of w_j over 407 consecutive nodes (0 beyond)
+    const int2 *wj2;              // [896]   the same over 813 consecutive nodes
+    const int2 *px;               // [1408]  P(x) of the sharing
+    const int2 *pr1, *pr2;        // [256]   prod_m (i - 256 - m) for m < 407 / m < 813 (recon_secrets_ddeg / _2ddeg)
 };
 constexpr int SN_M256_DMIN = -7, SN_M256_DMAX = 3;
 __host__ __device__ inline const int16_t *sn_kh_m256(const ShareNttTables &t, int nin) { return t.kh_m256 + (size_t)(-(nin - 1) - SN_M256_DMIN) * 16 * SN_LD; }
@@ -207,50 +248,50 @@ static inline ConvArgs share_conv_args(const GemmArgs &g, const ShareNttTables &
     ConvArgs a{};
     a.A = g.A; a.C = g.C; a.lda = g.lda; a.ldc = g.ldc; a.mtotal = g.mtotal; a.rpp = g.rpp; a.slot_lo = g.slot_lo; a.a_slots = g.a_slots; a.c_slots = g.c_slots;
     a.c_off = g.c_off; a.tail = g.tail; a.tail_off = g.tail_off;
-    a.tw = t.tw; a.khat = t.kh_share; a.pre = t.wj; a.post = reinterpret_cast<const u16 *>(t.px); a.post_group = 0;
+    a.tw = t.tw; a.khat = t.kh_share; a.pre = t.wj; a.post = t.px; a.post_group = 0;
     return a;
 }
 
 // ---- host: table construction (plain modular arithmetic, once per context) ----
 struct ShareNttHost {
     std::vector<int32_t> w16f, w16i;
-    std::vector<int16_t> tw, kh_share, kh_m256, wj, wj2, px, pr1, pr2;
+    std::vector<int2> tw, wj, wj2, px, pr1, pr2;
+    std::vector<int16_t> kh_share, kh_m256;
 };
 static inline ShareNttHost share_ntt_tables()
 {
     auto pw = [](uint32_t b, uint32_t e) { uint32_t r = 1; b %= Q; while (e) { if (e & 1) r = r * b % Q; b = b * b % Q; e >>= 1; } return r; };
     auto inv = [&](uint32_t a) { return pw(a % Q, Q - 2); };
-    const uint32_t R = (1u << 16) % Q, om = 17, iom = inv(17), om16 = pw(om, 16), iom16 = inv(om16);
-    auto mont = [&](uint32_t v) { return (int32_t)gf_center(v % Q * R % Q); };
+    const uint32_t om = 17, iom = inv(17), om16 = pw(om, 16), iom16 = inv(om16);
     ShareNttHost h;
     h.w16f.resize(256); h.w16i.resize(256); h.tw.resize(512);
     for (int a = 0; a < 16; a++)
         for (int k = 0; k < 16; k++) {
-            h.w16f[a * 16 + k] = mont(pw(om16, a * k)); h.w16i[a * 16 + k] = mont(pw(iom16, a * k));
-            h.tw[a * 16 + k] = (int16_t)mont(pw(om, a * k)); h.tw[256 + a * 16 + k] = (int16_t)mont(pw(iom, a * k));
+            h.w16f[a * 16 + k] = gf_center(pw(om16, a * k)); h.w16i[a * 16 + k] = gf_center(pw(iom16, a * k));
+            h.tw[a * 16 + k] = sn_pair(pw(om, a * k)); h.tw[256 + a * 16 + k] = sn_pair(pw(iom, a * k));
         }
     // barycentric weights over n consecutive nodes: w_j = 1 / prod_{m != j} (j - m)
     auto weights = [&](int n, int padded) {
-        std::vector<int16_t> w(padded, 0);
+        std::vector<int2> w(padded, make_int2(0, 0));
         for (int j = 0; j < n; j++) {
             uint32_t d = 1;
             for (int m = 0; m < n; m++) if (m != j) d = d * (uint32_t)(((j - m) % Q + Q) % Q) % Q;
-            w[j] = (int16_t)mont(inv(d));
+            w[j] = sn_pair(inv(d));
         }
         return w;
     };
     h.wj = weights(D1, 512); h.wj2 = weights(D2, 896);
     // P at the targets: the sharing evaluates at x + 407 over the nodes 0..406; the reconstructions at i over the nodes 256..256+n-1
-    h.px.assign(1408, 0); h.pr1.assign(256, 0); h.pr2.assign(256, 0);
+    h.px.assign(1408, make_int2(0, 0)); h.pr1.assign(256, make_int2(0, 0)); h.pr2.assign(256, make_int2(0, 0));
     for (int x = 0; x < NX; x++) {
         uint32_t p = 1;
         for (int m = 0; m < D1; m++) p = p * (uint32_t)((x + D1 - m) % Q) % Q;
-        h.px[x] = (int16_t)mont(p);
+        h.px[x] = sn_pair(p);
     }
     for (int i = 0; i < NL; i++) {
         uint32_t p1 = 1, p2 = 1;
         for (int m = 0; m < D2; m++) { const uint32_t f = (uint32_t)(((i - 256 - m) % Q + Q) % Q); p2 = p2 * f % Q; if (m < D1) p1 = p1 * f % Q; }
-        h.pr1[i] = (int16_t)mont(p1); h.pr2[i] = (int16_t)mont(p2);
+        h.pr1[i] = sn_pair(p1); h.pr2[i] = sn_pair(p2);
     }
     // kernel segments K_delta[d] = c[128 delta + OFF + d], d in [-127, 127], c[m] = 1/m (0 when m = 0 mod q), and their 256-point
     // NTTs, index k = k1 + 16 k2 stored at [k1][k2], scaled by 1/256
@@ -269,7 +310,7 @@ static inline ShareNttHost share_ntt_tables()
             for (int k = 0; k < 256; k++) {
                 uint32_t s = 0;
                 for (int t = 0; t < 256; t++) s = (s + K[t] * opw[(t * k) & 255]) % Q;
-                out[((size_t)(dl - dmin) * 16 + (k & 15)) * SN_LD + (k >> 4)] = (int16_t)mont(s * i256 % Q);
+                out[((size_t)(dl - dmin) * 16 + (k & 15)) * SN_LD + (k >> 4)] = (int16_t)gf_center(s * i256 % Q);
             }
         }
         return out;

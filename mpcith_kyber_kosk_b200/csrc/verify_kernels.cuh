@@ -38,7 +38,7 @@ struct VerifyBufs {
     int k = 0, chunk = 0;
     int strict = 0;   // hardened decoding: off by default = the reference's accept set
     int raw_inst = 0; // verify() on a caller-supplied mlwe_inst (raw_api.cuh): AH / TPK are preloaded, pk is not parsed
-    int pt_mont = 0;  // P(t) tables carry the Montgomery factor 2^16 (the NTT-convolution path consumes them; the dense GEMM path does not)
+    int pt_mont = 0;  // P(t) tables hold (w, w') int2 pairs for the NTT-convolution path (share_ntt.cuh, sn_shoup); plain u16 residues for the dense GEMM path
 };
 
 struct VDims {
@@ -74,7 +74,7 @@ static inline int verify_alloc(VerifyBufs &v, int k, int chunk)
     VA(v.A2, B * d.n2rows * KP2 * 2, 1); VA(v.UZ, B * d.n2rows * 256 * 2, 0);
     VA(v.VSH, B * d.nyrows * SLD * 2, 1); VA(v.U2, B * d.n2rows * VR2LD * 2, 1); VA(v.UR, B * d.n2rows * 256 * 2, 0);
     VA(v.WS, (size_t)GE_WS_ELEMS * 4, 0);
-    VA(v.W1, B * YLD * 2, 1); VA(v.W2, B * VR2LD * 2, 1); VA(v.PT1, B * LM1_ROWS * 2, 1); VA(v.PT2, B * 256 * 2, 1);
+    VA(v.W1, B * YLD * 2, 1); VA(v.W2, B * VR2LD * 2, 1); VA(v.PT1, B * LM1_ROWS * 8, 1); VA(v.PT2, B * 256 * 8, 1);      // sized for int2 entries
 #undef VA
     return 0;
 }
@@ -323,8 +323,8 @@ __global__ void __launch_bounds__(256) kv_lagrange(VerifyBufs vb, const u16 *__r
                 else { v = gf_mul(fact[t - 256], fact[hi - t]); if ((hi - t) & 1) v = gf_sub(0, v); }
                 v = gf_mul(v, inv[den]);
             }
-            if (vb.pt_mont) v = gf_mul(v, (1u << 16) % Q);
-            (pass ? vb.PT2 + (size_t)b * 256 : vb.PT1 + (size_t)b * LM1_ROWS)[t] = (u16)v;
+            if (vb.pt_mont) (pass ? reinterpret_cast<int2 *>(vb.PT2) + (size_t)b * 256 : reinterpret_cast<int2 *>(vb.PT1) + (size_t)b * LM1_ROWS)[t] = sn_pair(v);
+            else (pass ? vb.PT2 + (size_t)b * 256 : vb.PT1 + (size_t)b * LM1_ROWS)[t] = (u16)v;
         }
         __syncthreads();
     }
@@ -554,11 +554,11 @@ static int verify_chunk_t(VerifyBufs &vb, const VerifyTables &vt, int B, const u
     // interpolation-apply: rows of all proofs against the fixed Cauchy operand 1 / (t - (p + 256)), columns scaled by each proof's P(t)
     if (vt.sn) {
         cv = ConvArgs{}; cv.A = vb.A1; cv.C = vb.YV; cv.lda = KP1; cv.ldc = YLD; cv.mtotal = B * d.n1rows; cv.rpp = d.n1rows; cv.a_slots = d.n1rows; cv.c_slots = d.nyrows;
-        cv.tw = vt.sn->tw; cv.khat = sn_kh_m256(*vt.sn, 5); cv.post = vb.PT1; cv.post_group = LM1_ROWS;
+        cv.tw = vt.sn->tw; cv.khat = sn_kh_m256(*vt.sn, 5); cv.post = reinterpret_cast<const int2 *>(vb.PT1); cv.post_group = LM1_ROWS;
         nl += conv_ntt_launch<5, 4, KP1, D1, false, true>(cv, s2);
         kv_node_targets<K><<<dim3(d.n1rows, B), 160, 0, s2>>>(vb, d_pi); nl++;
         cv = ConvArgs{}; cv.A = vb.A2; cv.C = vb.UZ; cv.lda = KP2; cv.ldc = 256; cv.mtotal = B * d.n2rows; cv.rpp = d.n2rows; cv.a_slots = d.n2rows; cv.c_slots = d.n2rows;
-        cv.tw = vt.sn->tw; cv.khat = sn_kh_m256(*vt.sn, 8); cv.post = vb.PT2; cv.post_group = 256;
+        cv.tw = vt.sn->tw; cv.khat = sn_kh_m256(*vt.sn, 8); cv.post = reinterpret_cast<const int2 *>(vb.PT2); cv.post_group = 256;
         nl += conv_ntt_launch<8, 2, KP2, 256, false, true>(cv, s2);
     } else {
         g = GemmArgs{}; g.ws = vb.WS; g.ws_elems = GE_WS_ELEMS; g.A = vb.A1; g.Bt = vt.U1; g.C = vb.YV; g.lda = KP1; g.ldb = KP1; g.ldc = YLD;
@@ -595,7 +595,7 @@ static int verify_chunk_t(VerifyBufs &vb, const VerifyTables &vt, int B, const u
     // beta/gamma reconstruction: ABG x R1 (recon_secrets_ddeg, ss.cpp:37-54)
     if (vt.sn) {
         cv = ConvArgs{}; cv.A = vb.ABG; cv.C = vb.BS; cv.lda = YLD; cv.ldc = 256; cv.mtotal = B * 2 * MK; cv.rpp = cv.mtotal;
-        cv.tw = vt.sn->tw; cv.khat = sn_kh_m256(*vt.sn, 4); cv.pre = vt.sn->wj; cv.post = reinterpret_cast<const u16 *>(vt.sn->pr1);
+        cv.tw = vt.sn->tw; cv.khat = sn_kh_m256(*vt.sn, 4); cv.pre = vt.sn->wj; cv.post = vt.sn->pr1;
         nl += conv_ntt_launch<4, 2, D1, 256, true, false>(cv, st);
     } else {
         g = GemmArgs{}; g.ws = vb.WS; g.ws_elems = GE_WS_ELEMS; g.A = vb.ABG; g.Bt = vt.R1; g.C = vb.BS; g.lda = YLD; g.ldb = YLD; g.ldc = 256;
@@ -607,7 +607,7 @@ static int verify_chunk_t(VerifyBufs &vb, const VerifyTables &vt, int B, const u
     kv_check_parties<K><<<dim3(ptiles, B), 128, 0, st>>>(vb, d_pi); nl++;
     if (vt.sn) {      // recon_secrets_2ddeg over parties 0..812 (ss.cpp:56-73)
         cv = ConvArgs{}; cv.A = vb.U2; cv.C = vb.UR; cv.lda = VR2LD; cv.ldc = 256; cv.mtotal = B * d.n2rows; cv.rpp = cv.mtotal;
-        cv.tw = vt.sn->tw; cv.khat = sn_kh_m256(*vt.sn, 7); cv.pre = vt.sn->wj2; cv.post = reinterpret_cast<const u16 *>(vt.sn->pr2);
+        cv.tw = vt.sn->tw; cv.khat = sn_kh_m256(*vt.sn, 7); cv.pre = vt.sn->wj2; cv.post = vt.sn->pr2;
         nl += conv_ntt_launch<7, 2, D2, 256, true, false>(cv, st);
     } else {
         g = GemmArgs{}; g.ws = vb.WS; g.ws_elems = GE_WS_ELEMS; g.A = vb.U2; g.Bt = vt.R2; g.C = vb.UR; g.lda = VR2LD; g.ldb = VR2LD; g.ldc = 256;

@@ -271,6 +271,35 @@ def test_offline_online_split_matches_one_shot(ctxs, k):
     assert ctx.verify_batch(pi, pk).all()
 
 
+@pytest.mark.parametrize("k", [2, 4])
+def test_pool_export_import_round_trip(ctxs, k):
+    """The working (de)serialiser of the preprocessing (reference: mlwe_prover.cpp:61-79, unused and lossy): a pool exported from one
+    context and imported into another proves the same bytes as the one-shot call; truncated / foreign images are refused."""
+    from mpcith_kyber_kosk_b200 import KoskContext, KoskError
+    seeds = seeds_for_range(4242, 0, 6)
+    ctx = ctxs(k, 16, 1)
+    pool = ctx.pool_create(seeds)
+    img = pool.export()
+    pool.close()
+    other = KoskContext(k, 0, 8, 2)
+    p2 = other.pool_import(img)
+    pk, sk, pi = p2.prove()
+    want = ctx.prove_batch(seeds)
+    for x, y in zip(want, (pk, sk, pi)):
+        assert (x == y).all()
+    opk, osk, opi = O.oracle_prove(k, seeds[5])
+    assert (pi[5] == opi).all() and (pk[5] == opk).all()
+    with pytest.raises(KoskError):
+        other.pool_import(img[:len(img) // 2])
+    bad = img.copy(); bad[0] ^= 1
+    with pytest.raises(KoskError):
+        other.pool_import(bad)
+    with pytest.raises(KoskError):
+        ctxs(3 if k == 2 else 2, 16, 1).pool_import(img)      # another KYBER_K
+    p2.close()
+    other.close()
+
+
 @pytest.mark.parametrize("k", [2, 3, 4])
 def test_experimental_tensor_path_is_bit_identical(ctxs, k):
     """Opt-in KOSK_F_TENSOR: share evaluation on int8 tensor cores (limb-split residues); same bytes as the INT32 pipe."""
