@@ -302,7 +302,19 @@ def run_b200(args):
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         if "KOSK_NCCL_DEBUG" in os.environ:
             os.environ["NCCL_DEBUG"] = os.environ["KOSK_NCCL_DEBUG"]
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner with a bare printf to stdout at communicator creation: keep stdout to the one JSON line by pointing
+        # fd 1 at stderr until the first collective has run
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.all_reduce(torch.zeros(1, device=dev))
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     k, B = args.kyber_k, args.batch
     chunk = args.chunk or -(-B // args.lanes)
     ctx = KoskContext(k, local, chunk, args.lanes)
