@@ -254,6 +254,39 @@ __global__ void __launch_bounds__(128) kv_gather(VerifyBufs vb, const u8 *__rest
     }
 }
 
+// ABG rows (beta / gamma shares of parties 0..406, one row per challenge column) through a shared-memory transpose: the proof holds
+// beta / gamma party-major ([rest party][70], 140-byte rows), the reconstruction wants them column-major.  A per-element gather costs
+// one 32-byte sector per value (kv_gather's first branch: 0.25 ms per 1024 proofs); here a CTA reads the rows of 64 consecutive
+// parties as words and writes 128-byte segments of the 140 output rows.  grid (ceil(407 / 64), B).
+constexpr int VG_TP = 64;
+template <int K>
+__global__ void __launch_bounds__(256) kv_gather_bg(VerifyBufs vb, const u8 *__restrict__ pis)
+{
+    const Layout L = make_layout(K);
+    const int b = blockIdx.y, p0 = blockIdx.x * VG_TP, tid = threadIdx.x, np = min(VG_TP, D1 - p0);
+    const u8 *pi = pis + L.proof_bytes * (size_t)b;
+    __shared__ uint32_t st[VG_TP][MK + 1];           // [party][35 words of beta | 35 words of gamma], odd stride
+    const uint32_t *__restrict__ beta = reinterpret_cast<const uint32_t *>(pi + L.o_beta), *__restrict__ gamma = reinterpret_cast<const uint32_t *>(pi + L.o_gamma);
+    for (int idx = tid; idx < np * MK; idx += 256) {
+        const int r = idx / MK, w = idx % MK, h = w >= MK / 2, ww = h ? w - MK / 2 : w;
+        const int pos = vb.POS[(size_t)b * NP + p0 + r];
+        uint32_t v;
+        if (pos >= 0) v = __ldg((h ? gamma : beta) + (size_t)pos * (MK / 2) + ww);
+        else v = __ldg(reinterpret_cast<const uint32_t *>(vb.OPV + ((size_t)b * NT + (-1 - pos)) * OPLD + h * MK) + ww);
+        st[r][w] = v;
+    }
+    __syncthreads();
+    u16 *dst = vb.ABG + (size_t)b * 2 * MK * YLD + p0;
+    for (int idx = tid; idx < 2 * MK * VG_TP; idx += 256) {
+        const int row = idx / VG_TP, r = idx % VG_TP;      // row = j * 2 + w
+        if (r >= np) continue;
+        const int j = row >> 1, h = row & 1;
+        const uint32_t wv = st[r][h * (MK / 2) + (j >> 1)];
+        const uint32_t v = (j & 1) ? wv >> 16 : wv & 0xFFFFu;
+        dst[(size_t)row * YLD + r] = (u16)(v % (uint32_t)Q);
+    }
+}
+
 // Targets 256..406 of the d-degree interpolation are themselves nodes when party t - 256 is a rest party: the interpolant passes
 // through the share, so the value is the share itself (the Cauchy operand has a zero there and P(t) = 0).  grid (n1rows, B).
 template <int K>
@@ -591,7 +624,7 @@ static int verify_chunk_t(VerifyBufs &vb, const VerifyTables &vt, int B, const u
     }
     if (fork) cudaEventRecord(sd.join, s2);
     // ---- main chain, continued: beta/gamma of parties 0..406 (rest: from the proof, opened: just evaluated), reconstruction, NTT check ----
-    kv_gather<K><<<dim3(2 * MK, B), 128, 0, st>>>(vb, d_pi, 0); nl++;
+    kv_gather_bg<K><<<dim3((D1 + VG_TP - 1) / VG_TP, B), 256, 0, st>>>(vb, d_pi); nl++;
     // beta/gamma reconstruction: ABG x R1 (recon_secrets_ddeg, ss.cpp:37-54)
     if (vt.sn) {
         cv = ConvArgs{}; cv.A = vb.ABG; cv.C = vb.BS; cv.lda = YLD; cv.ldc = 256; cv.mtotal = B * 2 * MK; cv.rpp = cv.mtotal;

@@ -95,3 +95,38 @@ def test_wire_mode_async_pipeline_many_steps(ctxs):
             opk, osk, opi = O.oracle_prove(k, seeds[s][i])
             assert (pi[i] == opi).all() and (pk[i] == opk).all()
     ctx.close()
+
+
+def test_context_serialises_concurrent_callers():
+    """Every entry point takes the context's lock: two host threads proving on ONE context get correct, complete results (the
+    reference's functions are re-entrant; a context is merely thread-safe)."""
+    import threading
+    k = 2
+    ctx = pkg.KoskContext(k, 0, 8, 2)
+    seeds = [seeds_for_range(900 + t, 0, 12) for t in range(2)]
+    outs = [None, None]
+
+    def work(t):
+        outs[t] = ctx.prove_batch(seeds[t])
+    ths = [threading.Thread(target=work, args=(t,)) for t in range(2)]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    for t in range(2):
+        pk, sk, pi = outs[t]
+        for i in (0, 11):
+            opk, osk, opi = O.oracle_prove(k, seeds[t][i])
+            assert (pi[i] == opi).all() and (pk[i] == opk).all() and (sk[i] == osk).all(), (t, i)
+        assert ctx.verify_batch(pi, pk).all()
+    ctx.close()
+
+
+def test_destroy_refuses_while_a_pool_is_alive():
+    ctx = pkg.KoskContext(2, 0, 8, 1)
+    pool = ctx.pool_create(seeds_for_range(1, 0, 2))
+    h = ctx._h
+    ctx.lib.kosk_b200_destroy(h)                       # refused: the pool still references the context's streams and tables
+    assert b"pools" in ctx.lib.kosk_b200_last_error()
+    pk, sk, pi = pool.prove()                          # ... and the context is still usable
+    assert ctx.verify_batch(pi, pk).all()
+    pool.close()
+    ctx.close()
