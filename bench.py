@@ -394,7 +394,9 @@ def run_b200(args):
               torch.empty(B * npi, dtype=torch.uint8).pin_memory()) for _ in range(2)]
     ctx_e = KoskContext(k, local, B, args.e2e_lanes)
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
-    wire_threads = args.wire_threads or max(2, min(16, len(os.sched_getaffinity(0)) // max(1, local_world)))
+    # worker threads expanding wire images: half of this rank's share of the CPUs (the other half is left to the driver threads, the gate
+    # thread and the DMA's memory traffic: measured best on the pool's 16-vCPU boxes was 8 of 16)
+    wire_threads = args.wire_threads or max(2, min(12, len(os.sched_getaffinity(0)) // max(1, local_world) // 2))
 
     # platform ceiling of the link, measured here and now: every rank copies one step's proofs D2H into its pinned buffer with no
     # kernel running (all ranks at once; tools/d2h_ceiling.py is the long form)
@@ -430,7 +432,7 @@ def run_b200(args):
         ctx_e.sync()
         torch.cuda.synchronize()
         return allmax((time.perf_counter() - t0) / steps)   # seconds per step, max over ranks
-    cal_steps = max(3, args.steps // 4)
+    cal_steps = max(5, args.steps // 2)
     e2e_cal = {}
     for pct in ([int(x) for x in args.wire_percent.split(",")] if args.wire_percent else [0, 50, 75, 100]):
         ctx_e.set_wire(pct, wire_threads)

@@ -198,3 +198,32 @@ def test_struct_prove_on_inconsistent_instances_matches_live_reference(ctxs, k):
         got = np.frombuffer(ctx.prove(inst, seq["rand"], seq["eta"]), np.uint8)
         assert (got == want).all(), (name, int((got != want).sum()))
         assert ctx.verify(got, inst) == O.ref_verify_struct(k, want, inst) == (name == "honest"), name
+
+
+@pytest.mark.parametrize("k", [2, 3])
+def test_struct_verify_rejects_non_canonical_t_like_the_reference(ctxs, k):
+    """encode_to_gf3329 (gf3329.c:308-310) only adds q to negative coefficients, so an instance whose t carries t_i + q (same residue, not
+    canonical) does not match the recomputed shares and the reference rejects it (mlwe_verifier.cpp:358-376); so must verify() here."""
+    if O.ref(k) is None:
+        pytest.fail("oracle/_ref missing: run __graft_entry__.build() where /root/reference exists")
+    seq = O.ref_struct_sequence(k, O.seed_of(650 + k))
+    oT = k * k * 256
+    ctx = ctxs(k)
+    assert ctx.verify(seq["pi"], seq["inst"]) is True
+    t = seq["inst"].view(np.int16)[oT:oT + k * 256]
+    neg, nonneg = int(np.nonzero(t < 0)[0][0]), int(np.nonzero(t >= 0)[0][0])
+    verdicts = {}
+    for name, pos, delta in (("nonneg+q", nonneg, 3329), ("neg+q", neg, 3329), ("neg-q", neg, -3329), ("last+q", k * 256 - 1, 3329)):
+        inst = seq["inst"].copy().view(np.int16)
+        inst[oT + pos] = int(inst[oT + pos]) + delta
+        inst = inst.view(np.uint8)
+        want = O.ref_verify_struct(k, seq["pi"], inst)
+        assert ctx.verify(seq["pi"], inst) is want, name
+        verdicts[name] = want
+    # t_i >= 0 shifted up by q stays non-canonical and is rejected; t_i < 0 shifted up by q is encoded to the canonical residue and accepted
+    assert verdicts["nonneg+q"] is False and verdicts["neg+q"] is True and verdicts["neg-q"] is False
+    # A is used arithmetically only: a coefficient shifted by q is the same matrix entry for both verifiers
+    inst = seq["inst"].copy().view(np.int16)
+    inst[3] = int(inst[3]) + 3329 if int(inst[3]) < 0 else int(inst[3]) - 3329
+    inst = inst.view(np.uint8)
+    assert ctx.verify(seq["pi"], inst) is O.ref_verify_struct(k, seq["pi"], inst)
