@@ -101,7 +101,7 @@ struct kosk_b200_ctx {
     cudaEvent_t last_gate = nullptr;       // event the next prove sub-batch waits for: last_computed, or the previous sub-batch's pre_tail
     int overlap_fs1 = 0;                   // KOSK_B200_OVERLAP_FS1=1: eta / z_j sharings on the lane's side stream next to commit hashes + FS-1 (measured: a loss, off)
     int overlap_tail = 1;                  // KOSK_B200_OVERLAP_TAIL: let a sub-batch start while the previous one runs FS-2 + assembly
-    int use_ntt = 1;                       // KOSK_B200_SHARE_NTT: share evaluation as a blocked NTT convolution (share_ntt.cuh) instead of the dense table GEMM
+    int use_ntt = 2;                       // KOSK_B200_SHARE_NTT: share evaluation as a blocked NTT convolution (share_ntt.cuh; 2 = k_share_ntt2, 1 = the generic equal-block kernel) instead of the dense table GEMM (0)
     uint8_t *d_sn = nullptr;               // its tables (ShareNttTables), one allocation
     ShareNttTables sn{};
     Slots sl; Layout L;
@@ -316,17 +316,18 @@ int kosk_b200_create_ex(kosk_b200_ctx **out, int k, int device, int max_chunk, i
                 if (sh.w16f[i] != sn_make_w16(false).v[i] || sh.w16i[i] != sn_make_w16(true).v[i]) { ctx_free(c); return fail(KOSK_E_UNSUPPORTED, "share_ntt: DFT table mismatch (internal error)"); }
             // one byte blob, every part 16-byte aligned
             std::vector<uint8_t> all;
-            size_t offs[8]; int np = 0;
+            size_t offs[9]; int np = 0;
             auto put = [&](const void *p, size_t bytes) { offs[np++] = all.size(); const uint8_t *q = static_cast<const uint8_t *>(p); all.insert(all.end(), q, q + bytes); while (all.size() % 16) all.push_back(0); };
             put(sh.tw.data(), sh.tw.size() * sizeof(int2)); put(sh.kh_share.data(), sh.kh_share.size() * 2); put(sh.kh_m256.data(), sh.kh_m256.size() * 2);
             put(sh.wj.data(), sh.wj.size() * sizeof(int2)); put(sh.wj2.data(), sh.wj2.size() * sizeof(int2)); put(sh.px.data(), sh.px.size() * sizeof(int2));
-            put(sh.pr1.data(), sh.pr1.size() * sizeof(int2)); put(sh.pr2.data(), sh.pr2.size() * sizeof(int2));
+            put(sh.pr1.data(), sh.pr1.size() * sizeof(int2)); put(sh.pr2.data(), sh.pr2.size() * sizeof(int2)); put(sh.kp_share.data(), sh.kp_share.size() * 4);
             ALLOC(c->d_sn, all.size()); CUC(cudaMemcpy(c->d_sn, all.data(), all.size(), cudaMemcpyHostToDevice));
             const uint8_t *base = reinterpret_cast<const uint8_t *>(c->d_sn);
             c->sn.tw = reinterpret_cast<const int2 *>(base + offs[0]); c->sn.kh_share = reinterpret_cast<const int16_t *>(base + offs[1]);
             c->sn.kh_m256 = reinterpret_cast<const int16_t *>(base + offs[2]); c->sn.wj = reinterpret_cast<const int2 *>(base + offs[3]);
             c->sn.wj2 = reinterpret_cast<const int2 *>(base + offs[4]); c->sn.px = reinterpret_cast<const int2 *>(base + offs[5]);
             c->sn.pr1 = reinterpret_cast<const int2 *>(base + offs[6]); c->sn.pr2 = reinterpret_cast<const int2 *>(base + offs[7]);
+            c->sn.kp_share = reinterpret_cast<const uint32_t *>(base + offs[8]);
         }
         std::vector<uint16_t> fc(2 * FACT_N);
         { uint32_t f = 1; for (int i = 0; i < FACT_N; i++) { if (i) f = f * i % Q; fc[i] = (uint16_t)f; fc[FACT_N + i] = inv[f]; } }
@@ -407,7 +408,7 @@ static void launch_share_eval(kosk_b200_ctx *c, const u16 *Y, u16 *SH, int slot_
     g.mtotal = B * rows; g.ksteps = YLD / GE_BK; g.nvalid = NX; g.c_off = SOFF + NT + 1;
     g.rpp = rows; g.slot_lo = slot_lo; g.a_slots = y_slots; g.c_slots = sh_slots; g.tail = 1; g.tail_off = NL;
     if (c->use_ntt && !(c->use_tensor && YL0)) {      // one warp per sharing; constant-secret rows need no special case here
-        c->launches += share_ntt_launch(share_conv_args(g, c->sn), st);
+        c->launches += share_ntt_launch(share_conv_args(g, c->sn), st, c->use_ntt);
         return;
     }
     const int koff = const_secret ? NL : 0;
@@ -549,7 +550,7 @@ static int prove_chunk_k(kosk_b200_ctx *c, Lane &ln, const ProveBufs &bufs, int 
 
 static int verify_chunk_lane(kosk_b200_ctx *c, Lane &ln, int B, const u8 *d_pi, const u8 *d_pk, u8 *d_ok)
 {
-    VerifyTables vt{c->d_St, c->d_R1, c->d_R2, c->d_inv, c->d_SU, c->d_fact, c->d_U1, c->d_U2, c->use_ntt ? &c->sn : nullptr};
+    VerifyTables vt{c->d_St, c->d_R1, c->d_R2, c->d_inv, c->d_SU, c->d_fact, c->d_U1, c->d_U2, c->use_ntt ? &c->sn : nullptr, c->use_ntt};
     if (c->last_computed && c->last_computed != ln.computed) CU(cudaStreamWaitEvent(ln.st, c->last_computed, 0));
     prof_mark(c, ln, KOSK_PH_VERIFY);
     int nl = verify_chunk(c->k, ln.vb, vt, B, d_pi, d_pk, d_ok, ln.st, ln.vside);

@@ -78,6 +78,7 @@ struct ConvArgs {
     int tail, tail_off;                                  // sharing: copy the 151 tail values to parties 0..150
     const int2 *tw;          // [2][16][16]  (w, w') of 17^(+-b k1) (symmetric in b, k1)
     const int16_t *khat;     // [NIN + NOUT - 1][16 k1][SN_LD]  NTT(K_delta)[k1 + 16 k2] / 256, centered, at [k1][k2], delta = o - i
+    const uint32_t *kpk;     // k_share_ntt2 only: [S2_NOUT][2][256] packed limb words of the (o, i) segment spectra
     const int2 *pre;         // [128 NIN] (w, w') of the input factors, or nullptr
     const int2 *post;        // (w, w') of the output factors
     long long post_group;    // 0: one table; else the table of row m starts at post + (m / rpp) * post_group
@@ -228,12 +229,165 @@ static inline int conv_ntt_launch(const ConvArgs &g, cudaStream_t st)
     if (ctas > 0) k_conv_ntt<NIN, NOUT, NINV, NOUTV, PRE, PGROUP><<<ctas, 32 * SN_WARPS, 0, st>>>(g);
     return 1;
 }
-static inline int share_ntt_launch(const ConvArgs &g, cudaStream_t st) { return conv_ntt_launch<SN_NIN, SN_NOUT, D1, NX, true, false>(g, st); }
+
+// ---------------------------------------------------------------------------------------------
+// The sharing itself (the (4, 11) product above, 96 % of all rows) with unequal blocks and a packed pointwise stage.
+//   * Blocks: 126 inputs x 131 outputs per length-256 cyclic convolution (126 + 131 - 1 = 256) instead of 128 x 128: 4 input blocks
+//     (504 >= 407) and TEN output blocks (1310 >= 1303) instead of eleven, i.e. five two-block passes instead of six.  The ninth output row
+//     (x' = 128..130) of a block is free: w16^(8 k) = (-1)^k, so rows 0 and 8 share one even / odd sum.  The kernel segment of block (o, i)
+//     is K[d] = c[131 o - 126 i + 407 + d], d in [-125, 130]: it depends on o and i separately, 40 spectra instead of 14.
+//   * Pointwise stage: the spectra of input blocks 2p and 2p + 1 sit in one 32-bit word (two int16), and the segment spectra of (o, 2p),
+//     (o, 2p + 1) are split into signed limbs k = 64 k1 + k0 (k0 in [-32, 32), |k1| <= 26) and packed as the four bytes (k0, k0', k1, k1') of
+//     one word, so that   acc0 += u . (k0, k0')  and  acc1 += u . (k1, k1')   are one IDP.2A.LO and one IDP.2A.HI on the FMA-heavy pipe (full
+//     rate, tools/exp/idp_bench.cu) with both operands used exactly as loaded: 64 IDP per pass replace 64 IMAD + 128 ALU-pipe unpacks
+//     (PRMT / SHF) of the int16 spectra; the limbs are recombined inside the Barrett step's input (acc0 + 64 acc1 < 2^26).
+// Shared-memory rows are 16 words without padding; the 16-byte chunk index is XOR-swizzled with bits 1..2 of the row so that the 128-bit
+// row reads of a quarter-warp hit distinct banks.
+constexpr int S2_BI = 126, S2_BO = 131, S2_NIN = 4, S2_NOUT = 10;
+#ifndef KOSK_S2_WARPS
+#define KOSK_S2_WARPS 7
+#endif
+#ifndef KOSK_S2_MINB
+#define KOSK_S2_MINB 4
+#endif
+constexpr int S2_WARPS = KOSK_S2_WARPS;
+static_assert(S2_BI + S2_BO - 1 == 256 && S2_NIN * S2_BI >= D1 && S2_NOUT * S2_BO >= NX && S2_NIN == 4 && S2_NOUT % 2 == 0, "share_ntt2 blocking");
+__host__ __device__ constexpr int s2_word(int k1, int k2) { return k1 * 16 + ((((k2 >> 2) ^ (k1 >> 1)) & 3) << 2) + (k2 & 3); }   // word of bin (k1, k2) in a swizzled [16][16] tile
+
+template <int NINV, int NOUTV>
+__global__ void __launch_bounds__(32 * S2_WARPS, KOSK_S2_MINB) k_share_ntt2(const ConvArgs g)
+{
+    __shared__ __align__(16) uint32_t s_kp[S2_NOUT * 2 * 256];             // [o][pair][k1][k2 swizzled]: bytes (k0, k0', k1, k1') of segments (o, 2 pair), (o, 2 pair + 1)
+    __shared__ __align__(8) int2 s_tw[2 * 256];
+    __shared__ __align__(16) uint32_t s_up[S2_WARPS][2 * 256];             // [pair][k1][k2 swizzled]: spectra of input blocks 2 pair (low half) and 2 pair + 1
+    __shared__ int16_t s_t[S2_WARPS][2][288];
+    for (int i = threadIdx.x; i < S2_NOUT * 2 * 256; i += blockDim.x) s_kp[i] = g.kpk[i];
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) s_tw[i] = g.tw[i];
+    __syncthreads();
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, hw = lane >> 4, c = lane & 15;
+    uint32_t *up = s_up[wid];
+    int16_t *T = s_t[wid][hw];
+    const int sw = (c >> 1) & 3;                                            // chunk ch of row c lives at chunk ch ^ sw
+    for (int m = blockIdx.x * S2_WARPS + wid; m < g.mtotal; m += gridDim.x * S2_WARPS) {
+        const u16 *yrow = g.A + ((size_t)(m / g.rpp) * g.a_slots + g.slot_lo + m % g.rpp) * g.lda;
+        u16 *dst = g.C + ((size_t)(m / g.rpp) * g.c_slots + g.slot_lo + m % g.rpp) * g.ldc + g.c_off;
+        if (g.tail) for (int t = lane; t <= NT; t += 32) dst[t - (NT + 1)] = yrow[g.tail_off + t];
+        // ---- forward: u_j = w_j y_j, NTT of the zero-padded 126-wide input blocks (two per pass) ----
+#pragma unroll 1
+        for (int it = 0; it < S2_NIN / 2; it++) {
+            const int blk = 2 * it + hw;
+            int32_t x[8];
+#pragma unroll
+            for (int a = 0; a < 8; a++) {
+                const int jl = 16 * a + c, j = S2_BI * blk + jl;
+                int32_t v = 0;
+                if ((a < 7 || jl < S2_BI) && j < NINV) { const int2 p = __ldg(g.pre + j); v = sn_shoup((int32_t)yrow[j], p.x, p.y); }
+                x[a] = v;
+            }
+            int32_t y[16];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                int32_t ev = 0, od = 0;
+#pragma unroll
+                for (int a = 0; a < 8; a += 2) { ev += x[a] * c_sn_w16f[a * 16 + k]; od += x[a + 1] * c_sn_w16f[(a + 1) * 16 + k]; }
+                const int2 t0 = s_tw[k * 16 + c], t1 = s_tw[(k + 8) * 16 + c];
+                y[k] = sn_shoup(ev + od, t0.x, t0.y);
+                y[k + 8] = sn_shoup(ev - od, t1.x, t1.y);
+            }
+#pragma unroll
+            for (int k = 0; k < 16; k++) T[k * 17 + c] = (int16_t)y[k];
+            __syncwarp();
+            int32_t in[16];
+#pragma unroll
+            for (int b = 0; b < 16; b++) in[b] = T[c * 17 + b];
+            int16_t *urow = reinterpret_cast<int16_t *>(up + it * 256 + c * 16) + hw;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                int32_t ev = 0, od = 0;
+#pragma unroll
+                for (int b = 0; b < 16; b += 2) { ev += in[b] * c_sn_w16f[b * 16 + k]; od += in[b + 1] * c_sn_w16f[(b + 1) * 16 + k]; }
+                urow[2 * ((((k >> 2) ^ sw) << 2) + (k & 3))] = (int16_t)sn_barrett(ev + od);
+                urow[2 * (((((k + 8) >> 2) ^ sw) << 2) + (k & 3))] = (int16_t)sn_barrett(ev - od);
+            }
+            __syncwarp();
+        }
+        // ---- inverse: output blocks two per pass ----
+#pragma unroll 1
+        for (int it = 0; it < S2_NOUT / 2; it++) {
+            const int o = 2 * it + hw;
+            int32_t O[16];
+            {
+                const uint4 *pu = reinterpret_cast<const uint4 *>(up + c * 16);
+                const uint4 *pk = reinterpret_cast<const uint4 *>(s_kp + o * 512 + c * 16);
+#pragma unroll
+                for (int ch = 0; ch < 4; ch++) {
+                    const uint4 u0 = pu[ch ^ sw], u1 = pu[64 + (ch ^ sw)], k0 = pk[ch ^ sw], k1 = pk[64 + (ch ^ sw)];
+                    const uint32_t uw0[4] = {u0.x, u0.y, u0.z, u0.w}, uw1[4] = {u1.x, u1.y, u1.z, u1.w}, kw0[4] = {k0.x, k0.y, k0.z, k0.w}, kw1[4] = {k1.x, k1.y, k1.z, k1.w};
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        const int32_t lo = __dp2a_lo((int)uw1[e], (int)kw1[e], __dp2a_lo((int)uw0[e], (int)kw0[e], 0));
+                        const int32_t hi = __dp2a_hi((int)uw1[e], (int)kw1[e], __dp2a_hi((int)uw0[e], (int)kw0[e], 0));
+                        O[4 * ch + e] = sn_barrett(hi * 64 + lo);
+                    }
+                }
+            }
+            int32_t v[16];
+#pragma unroll
+            for (int b = 0; b < 8; b++) {
+                int32_t ev = 0, od = 0;
+#pragma unroll
+                for (int k = 0; k < 16; k += 2) { ev += O[k] * c_sn_w16i[k * 16 + b]; od += O[k + 1] * c_sn_w16i[(k + 1) * 16 + b]; }
+                const int2 t0 = s_tw[256 + b * 16 + c], t1 = s_tw[256 + (b + 8) * 16 + c];
+                v[b] = sn_shoup(ev + od, t0.x, t0.y);
+                v[b + 8] = sn_shoup(ev - od, t1.x, t1.y);
+            }
+#pragma unroll
+            for (int b = 0; b < 16; b++) T[b * 17 + c] = (int16_t)v[b];
+            __syncwarp();
+            int32_t in[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) in[k] = T[c * 17 + k];
+            const int xb = S2_BO * o + c;                                   // first output of this lane; row a adds 16 a
+            const int2 *postp = g.post + xb;
+            u16 *dstp = dst + xb;
+            auto emit = [&](int a, int32_t acc) {
+                if ((a < 8 || c < S2_BO - 128) && xb + 16 * a < NOUTV) {
+                    const int2 pf = __ldg(postp + 16 * a);
+                    int32_t r = sn_shoup(acc, pf.x, pf.y);
+                    if (r < 0) r += Q;
+                    if (r >= Q) r -= Q;
+                    dstp[16 * a] = (u16)r;
+                }
+            };
+            {   // rows 0 and 8: w16^(-0 k) = 1, w16^(-8 k) = (-1)^k
+                int32_t ev = 0, od = 0;
+#pragma unroll
+                for (int k = 0; k < 16; k += 2) { ev += in[k]; od += in[k + 1]; }
+                emit(0, ev + od); emit(8, ev - od);
+            }
+#pragma unroll
+            for (int a = 1; a < 8; a++) {
+                int32_t acc = 0;
+#pragma unroll
+                for (int k = 0; k < 16; k++) acc += in[k] * c_sn_w16i[k * 16 + a];
+                emit(a, acc);
+            }
+            __syncwarp();
+        }
+    }
+}
+static inline int share_ntt2_launch(const ConvArgs &g, cudaStream_t st)
+{
+    const int ctas = std::min((g.mtotal + S2_WARPS - 1) / S2_WARPS, 148 * KOSK_S2_MINB);
+    if (ctas > 0) k_share_ntt2<D1, NX><<<ctas, 32 * S2_WARPS, 0, st>>>(g);
+    return 1;
+}
 
 // device tables of all Toeplitz products of the KOSK path (one allocation per context)
 struct ShareNttTables {
     const int2 *tw;
     const int16_t *kh_share;      // OFF = 407, (4, 11)
+    const uint32_t *kp_share;     // OFF = 407, 126 x 131 blocks, packed limbs (k_share_ntt2)
     const int16_t *kh_m256;       // OFF = -256: segments delta in [-7, 3]; a product with (NIN, NOUT) starts at delta = -(NIN - 1)
     const int2 *wj;               // [512]   (w, w') of w_j over 407 consecutive nodes (0 beyond)
     const int2 *wj2;              // [896]   the same over 813 consecutive nodes
@@ -248,8 +402,13 @@ static inline ConvArgs share_conv_args(const GemmArgs &g, const ShareNttTables &
     ConvArgs a{};
     a.A = g.A; a.C = g.C; a.lda = g.lda; a.ldc = g.ldc; a.mtotal = g.mtotal; a.rpp = g.rpp; a.slot_lo = g.slot_lo; a.a_slots = g.a_slots; a.c_slots = g.c_slots;
     a.c_off = g.c_off; a.tail = g.tail; a.tail_off = g.tail_off;
-    a.tw = t.tw; a.khat = t.kh_share; a.pre = t.wj; a.post = t.px; a.post_group = 0;
+    a.tw = t.tw; a.khat = t.kh_share; a.kpk = t.kp_share; a.pre = t.wj; a.post = t.px; a.post_group = 0;
     return a;
+}
+// variant 2 (default) = k_share_ntt2, variant 1 = the generic equal-block kernel
+static inline int share_ntt_launch(const ConvArgs &g, cudaStream_t st, int variant = 2)
+{
+    return variant >= 2 ? share_ntt2_launch(g, st) : conv_ntt_launch<SN_NIN, SN_NOUT, D1, NX, true, false>(g, st);
 }
 
 // ---- host: table construction (plain modular arithmetic, once per context) ----
@@ -257,6 +416,7 @@ struct ShareNttHost {
     std::vector<int32_t> w16f, w16i;
     std::vector<int2> tw, wj, wj2, px, pr1, pr2;
     std::vector<int16_t> kh_share, kh_m256;
+    std::vector<uint32_t> kp_share;
 };
 static inline ShareNttHost share_ntt_tables()
 {
@@ -317,6 +477,24 @@ static inline ShareNttHost share_ntt_tables()
     };
     h.kh_share = segments(D1, -(SN_NIN - 1), SN_NOUT - 1);
     h.kh_m256 = segments(-256, SN_M256_DMIN, SN_M256_DMAX);
+    // k_share_ntt2: segment (o, i) K[d] = c[131 o - 126 i + 407 + d], d in [-125, 130] at t = d mod 256; spectrum / 256, centered, as limbs k = 64 k1 + k0
+    h.kp_share.assign((size_t)S2_NOUT * 2 * 256, 0);
+    for (int o = 0; o < S2_NOUT; o++)
+        for (int i = 0; i < S2_NIN; i++) {
+            uint32_t K[256];
+            for (int t = 0; t < 256; t++) {
+                const int d = t < S2_BO ? t : t - 256;
+                const int mm = ((S2_BO * o - S2_BI * i + D1 + d) % Q + Q) % Q;
+                K[t] = mm == 0 ? 0 : inv((uint32_t)mm);
+            }
+            for (int k = 0; k < 256; k++) {
+                uint32_t s = 0;
+                for (int t = 0; t < 256; t++) s = (s + K[t] * opw[(t * k) & 255]) % Q;
+                const int v = gf_center(s * i256 % Q), k0 = ((v + 32) & 63) - 32, k1 = (v - k0) / 64;
+                uint32_t &w = h.kp_share[((size_t)o * 2 + i / 2) * 256 + s2_word(k & 15, k >> 4)];
+                w |= ((uint32_t)(uint8_t)(int8_t)k0) << (8 * (i & 1)) | ((uint32_t)(uint8_t)(int8_t)k1) << (16 + 8 * (i & 1));
+            }
+        }
     return h;
 }
 

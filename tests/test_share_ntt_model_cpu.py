@@ -57,3 +57,50 @@ def test_blocked_ntt_convolution_equals_the_share_table():
             if x < NX:
                 got[x] = blk[t] * i256 % Q * P[x] % Q
                 assert got[x] == want[151 + x], (o, t)
+
+
+def test_unequal_blocks_and_limb_split_equal_the_share_table():
+    """k_share_ntt2's form of the same identity: 126-wide input blocks x 131-wide output blocks (126 + 131 - 1 = 256, so ten output blocks
+    cover the 1303 shares), segment (o, i) K[d] = c[131 o - 126 i + 407 + d] for d in [-125, 130], and the pointwise stage on signed limbs
+    k = 64 k1 + k0 of the centered segment spectra (the IDP.2A operands): sum_i u_i (k0_i + 64 k1_i) = the product over GF(3329)."""
+    BI, BO, NIN, NOUT = 126, 131, 4, 10
+    assert BI + BO - 1 == 256 and NIN * BI >= D1 and NOUT * BO >= NX
+    w, P = [], []
+    for j in range(D1):
+        d = 1
+        for m in range(D1):
+            if m != j:
+                d = d * ((j - m) % Q) % Q
+        w.append(_inv(d))
+    for x in range(NX):
+        p = 1
+        for m in range(D1):
+            p = p * ((x + D1 - m) % Q) % Q
+        P.append(p)
+    rng = np.random.default_rng(5)
+    y = rng.integers(0, Q, size=D1, dtype=np.uint16)
+    want = O.oracle_share(y)
+    u = [w[j] * int(y[j]) % Q for j in range(D1)] + [0] * (NIN * BI - D1)
+    U = [_ntt(u[BI * i:BI * (i + 1)] + [0] * (256 - BI), 17) for i in range(NIN)]
+    i256, iom = _inv(256), _inv(17)
+    for o in (0, 4, 9):
+        acc0, acc1 = [0] * 256, [0] * 256
+        for i in range(NIN):
+            K = [0] * 256
+            for t in range(256):
+                d = t if t < BO else t - 256
+                mm = (BO * o - BI * i + D1 + d) % Q
+                K[t] = _inv(mm) if mm else 0
+            spec = [v * i256 % Q for v in _ntt(K, 17)]
+            for n in range(256):
+                v = spec[n] - Q if spec[n] > Q // 2 else spec[n]      # centered, then limbs as in share_ntt_tables()
+                k0 = ((v + 32) & 63) - 32
+                k1 = (v - k0) // 64
+                assert -32 <= k0 < 32 and -27 <= k1 <= 26 and 64 * k1 + k0 == v
+                acc0[n] += U[i][n] * k0
+                acc1[n] += U[i][n] * k1
+        blk = _ntt([(a0 + 64 * a1) % Q for a0, a1 in zip(acc0, acc1)], iom)
+        for t in range(BO):
+            x = BO * o + t
+            if x < NX:
+                assert blk[t] * P[x] % Q == want[151 + x], (o, t)
