@@ -254,6 +254,54 @@ constexpr int S2_WARPS = KOSK_S2_WARPS;
 static_assert(S2_BI + S2_BO - 1 == 256 && S2_NIN * S2_BI >= D1 && S2_NOUT * S2_BO >= NX && S2_NIN == 4 && S2_NOUT % 2 == 0, "share_ntt2 blocking");
 __host__ __device__ constexpr int s2_word(int k1, int k2) { return k1 * 16 + ((((k2 >> 2) ^ (k1 >> 1)) & 3) << 2) + (k2 & 3); }   // word of bin (k1, k2) in a swizzled [16][16] tile
 
+// 16-point DFTs of k_share_ntt2 as radix-2 decimation-in-time networks in registers (natural order in and out) instead of 16 x 16 mat-vecs:
+// 17 twiddle multiplications per transform.  A multiplication is either LAZY (one IMAD, the product of a small value with a centered constant
+// stays an unreduced int32) or a SHOUP multiplication (IMAD.HI + 2 IMAD = 4 issue slots, result in (-q/4, 5q/4) for any |s| < 2^31); which one
+// is a 17-bit compile-time mask, chosen by exhaustive search over interval bounds (tools/exp/fft16_plan.py) so that no intermediate exceeds
+// 2^31.  Multiplication ids: size-4 transform at offset o (x I): o (0..3); size-8 transform at offset o, k = 1..3: 4 + 3 o + k - 1; size 16,
+// k = 1..7: 9 + k.  SN_FFT_SMALL (inputs below 1.25 q: 32 slots) keeps only the operands of later lazy multiplications small; SN_FFT_BIG
+// (inputs up to 2^25.5, the unreduced pointwise sums: 68 slots) reduces in every multiplication, which replaces 16 Barrett reductions.
+constexpr uint32_t SN_FFT_SMALL = 0x386u, SN_FFT_BIG = 0x1ffffu;
+struct SnTw16 { int32_t w[16], wp[16]; };
+constexpr SnTw16 sn_make_tw16(bool inv)
+{
+    SnTw16 t{};
+    const uint32_t om16 = sn_cpow(17, 16), w = inv ? sn_cpow(om16, Q - 2) : om16;
+    for (int j = 0; j < 16; j++) {
+        t.w[j] = sn_ccenter(sn_cpow(w, (uint32_t)j));
+        const long long num = (long long)t.w[j] * 4294967296LL;
+        t.wp[j] = (int32_t)((num >= 0 ? num + Q / 2 : num - Q / 2) / Q);
+    }
+    return t;
+}
+__device__ constexpr SnTw16 c_sn_tw16f = sn_make_tw16(false), c_sn_tw16i = sn_make_tw16(true);
+
+template <int N, int OFF, int STRIDE, bool INV, uint32_t MASK>
+struct SnDft {
+    static __device__ __forceinline__ void run(const int32_t (&x)[16], int32_t (&out)[N])
+    {
+        int32_t E[N / 2], O[N / 2];
+        SnDft<N / 2, OFF, 2 * STRIDE, INV, MASK>::run(x, E);
+        SnDft<N / 2, OFF + STRIDE, 2 * STRIDE, INV, MASK>::run(x, O);
+#pragma unroll
+        for (int k = 0; k < N / 2; k++) {
+            int32_t t = O[k];
+            if (k > 0) {
+                const int id = N == 4 ? OFF : N == 8 ? 4 + 3 * OFF + k - 1 : 9 + k, j = k * (16 / N);
+                const int32_t w = INV ? c_sn_tw16i.w[j] : c_sn_tw16f.w[j], wp = INV ? c_sn_tw16i.wp[j] : c_sn_tw16f.wp[j];
+                t = ((MASK >> id) & 1u) ? sn_shoup(O[k], w, wp) : O[k] * w;
+            }
+            out[k] = E[k] + t; out[k + N / 2] = E[k] - t;
+        }
+    }
+};
+template <int OFF, int STRIDE, bool INV, uint32_t MASK>
+struct SnDft<1, OFF, STRIDE, INV, MASK> {
+    static __device__ __forceinline__ void run(const int32_t (&x)[16], int32_t (&out)[1]) { out[0] = x[OFF]; }
+};
+template <bool INV, uint32_t MASK>
+__device__ __forceinline__ void sn_dft16(const int32_t (&x)[16], int32_t (&out)[16]) { SnDft<16, 0, 1, INV, MASK>::run(x, out); }
+
 template <int NINV, int NOUTV>
 __global__ void __launch_bounds__(32 * S2_WARPS, KOSK_S2_MINB) k_share_ntt2(const ConvArgs g)
 {
@@ -276,39 +324,26 @@ __global__ void __launch_bounds__(32 * S2_WARPS, KOSK_S2_MINB) k_share_ntt2(cons
 #pragma unroll 1
         for (int it = 0; it < S2_NIN / 2; it++) {
             const int blk = 2 * it + hw;
-            int32_t x[8];
+            int32_t x[16];
 #pragma unroll
-            for (int a = 0; a < 8; a++) {
+            for (int a = 0; a < 16; a++) {
                 const int jl = 16 * a + c, j = S2_BI * blk + jl;
                 int32_t v = 0;
-                if ((a < 7 || jl < S2_BI) && j < NINV) { const int2 p = __ldg(g.pre + j); v = sn_shoup((int32_t)yrow[j], p.x, p.y); }
+                if (a < 8 && (a < 7 || jl < S2_BI) && j < NINV) { const int2 p = __ldg(g.pre + j); v = sn_shoup((int32_t)yrow[j], p.x, p.y); }
                 x[a] = v;
             }
             int32_t y[16];
+            sn_dft16<false, SN_FFT_SMALL>(x, y);                           // rows 8..15 of the block are zero padding: x[8..15] = 0 folds away
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                int32_t ev = 0, od = 0;
-#pragma unroll
-                for (int a = 0; a < 8; a += 2) { ev += x[a] * c_sn_w16f[a * 16 + k]; od += x[a + 1] * c_sn_w16f[(a + 1) * 16 + k]; }
-                const int2 t0 = s_tw[k * 16 + c], t1 = s_tw[(k + 8) * 16 + c];
-                y[k] = sn_shoup(ev + od, t0.x, t0.y);
-                y[k + 8] = sn_shoup(ev - od, t1.x, t1.y);
-            }
-#pragma unroll
-            for (int k = 0; k < 16; k++) T[k * 17 + c] = (int16_t)y[k];
+            for (int k = 0; k < 16; k++) { const int2 t = s_tw[k * 16 + c]; T[k * 17 + c] = (int16_t)sn_shoup(y[k], t.x, t.y); }
             __syncwarp();
-            int32_t in[16];
+            int32_t in[16], X[16];
 #pragma unroll
             for (int b = 0; b < 16; b++) in[b] = T[c * 17 + b];
+            sn_dft16<false, SN_FFT_SMALL>(in, X);
             int16_t *urow = reinterpret_cast<int16_t *>(up + it * 256 + c * 16) + hw;
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                int32_t ev = 0, od = 0;
-#pragma unroll
-                for (int b = 0; b < 16; b += 2) { ev += in[b] * c_sn_w16f[b * 16 + k]; od += in[b + 1] * c_sn_w16f[(b + 1) * 16 + k]; }
-                urow[2 * ((((k >> 2) ^ sw) << 2) + (k & 3))] = (int16_t)sn_barrett(ev + od);
-                urow[2 * (((((k + 8) >> 2) ^ sw) << 2) + (k & 3))] = (int16_t)sn_barrett(ev - od);
-            }
+            for (int k = 0; k < 16; k++) urow[2 * ((((k >> 2) ^ sw) << 2) + (k & 3))] = (int16_t)sn_barrett(X[k]);
             __syncwarp();
         }
         // ---- inverse: output blocks two per pass ----
@@ -327,51 +362,35 @@ __global__ void __launch_bounds__(32 * S2_WARPS, KOSK_S2_MINB) k_share_ntt2(cons
                     for (int e = 0; e < 4; e++) {
                         const int32_t lo = __dp2a_lo((int)uw1[e], (int)kw1[e], __dp2a_lo((int)uw0[e], (int)kw0[e], 0));
                         const int32_t hi = __dp2a_hi((int)uw1[e], (int)kw1[e], __dp2a_hi((int)uw0[e], (int)kw0[e], 0));
-                        O[4 * ch + e] = sn_barrett(hi * 64 + lo);
+                        O[4 * ch + e] = hi * 64 + lo;                       // < 2^25.5, reduced inside the transform (SN_FFT_BIG)
                     }
                 }
             }
             int32_t v[16];
+            sn_dft16<true, SN_FFT_BIG>(O, v);
 #pragma unroll
-            for (int b = 0; b < 8; b++) {
-                int32_t ev = 0, od = 0;
-#pragma unroll
-                for (int k = 0; k < 16; k += 2) { ev += O[k] * c_sn_w16i[k * 16 + b]; od += O[k + 1] * c_sn_w16i[(k + 1) * 16 + b]; }
-                const int2 t0 = s_tw[256 + b * 16 + c], t1 = s_tw[256 + (b + 8) * 16 + c];
-                v[b] = sn_shoup(ev + od, t0.x, t0.y);
-                v[b + 8] = sn_shoup(ev - od, t1.x, t1.y);
-            }
-#pragma unroll
-            for (int b = 0; b < 16; b++) T[b * 17 + c] = (int16_t)v[b];
+            for (int b = 0; b < 16; b++) { const int2 t = s_tw[256 + b * 16 + c]; T[b * 17 + c] = (int16_t)sn_shoup(v[b], t.x, t.y); }
             __syncwarp();
-            int32_t in[16];
+            int32_t in[16], out[16];
 #pragma unroll
             for (int k = 0; k < 16; k++) in[k] = T[c * 17 + k];
+            sn_dft16<true, SN_FFT_SMALL>(in, out);                          // only out[0..8] are used: the rest of the last level is dead code
             const int xb = S2_BO * o + c;                                   // first output of this lane; row a adds 16 a
             const int2 *postp = g.post + xb;
             u16 *dstp = dst + xb;
+            // rows a < na are valid: row 8 only holds x' = 128..130, and the last block ends at NOUTV
+            const int na = min(c < S2_BO - 128 ? 9 : 8, (NOUTV - xb + 15) >> 4);
             auto emit = [&](int a, int32_t acc) {
-                if ((a < 8 || c < S2_BO - 128) && xb + 16 * a < NOUTV) {
+                if (a < na) {
                     const int2 pf = __ldg(postp + 16 * a);
-                    int32_t r = sn_shoup(acc, pf.x, pf.y);
-                    if (r < 0) r += Q;
-                    if (r >= Q) r -= Q;
+                    uint32_t r = (uint32_t)sn_shoup(acc, pf.x, pf.y);       // in (-q/4, 5q/4): canonical with two unsigned minima, no predicates
+                    r = min(r, r + Q);
+                    r = min(r, r - Q);
                     dstp[16 * a] = (u16)r;
                 }
             };
-            {   // rows 0 and 8: w16^(-0 k) = 1, w16^(-8 k) = (-1)^k
-                int32_t ev = 0, od = 0;
 #pragma unroll
-                for (int k = 0; k < 16; k += 2) { ev += in[k]; od += in[k + 1]; }
-                emit(0, ev + od); emit(8, ev - od);
-            }
-#pragma unroll
-            for (int a = 1; a < 8; a++) {
-                int32_t acc = 0;
-#pragma unroll
-                for (int k = 0; k < 16; k++) acc += in[k] * c_sn_w16i[k * 16 + a];
-                emit(a, acc);
-            }
+            for (int a = 0; a < 9; a++) emit(a, out[a]);
             __syncwarp();
         }
     }
