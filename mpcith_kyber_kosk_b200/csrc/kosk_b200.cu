@@ -21,6 +21,7 @@
 #include <thread>
 #include <algorithm>
 #include <utility>
+#include <map>
 
 using namespace kosk;
 
@@ -104,6 +105,7 @@ struct kosk_b200_ctx {
     int use_ntt = 2;                       // KOSK_B200_SHARE_NTT: share evaluation as a blocked NTT convolution (share_ntt.cuh; 2 = k_share_ntt2, 1 = the generic equal-block kernel) instead of the dense table GEMM (0)
     uint8_t *d_sn = nullptr;               // its tables (ShareNttTables), one allocation
     ShareNttTables sn{};
+    std::map<cudaStream_t, SnTicket> sn_tickets;   // work tickets of k_share_ntt2, one device counter per stream that launches it (created on first use)
     Slots sl; Layout L;
     uint64_t launches = 0;
     // constant tables
@@ -191,6 +193,8 @@ static void ctx_free(kosk_b200_ctx *c)
     wire_pool_destroy(c->wpool); c->wpool = nullptr;
     void *ptrs[] = {c->d_sn, c->d_U1, c->d_U2, c->d_status, c->d_fact, c->tmpL0, c->tmpL1, c->d_St, c->d_St0, c->d_St1, c->d_SU, c->d_R1, c->d_R2, c->d_inv, c->d_tab_commit, c->d_tab_view};
     for (void *p : ptrs) if (p) cudaFree(p);
+    for (auto &kv : c->sn_tickets) if (kv.second.ctr) cudaFree(kv.second.ctr);
+    c->sn_tickets.clear();
     const size_t Bc = (size_t)c->chunk;
     for (Lane &ln : c->lanes) {
         // scratch that held seeds, s, e and secret keys is cleared before it goes back to the allocator
@@ -397,6 +401,17 @@ int kosk_b200_lanes(const kosk_b200_ctx *c) { return c ? (int)c->lanes.size() : 
 
 }  // extern "C"
 
+// work ticket of the share evaluation for launches on `st` (nullptr if the counter cannot be allocated: static striding)
+static SnTicket *sn_ticket(kosk_b200_ctx *c, cudaStream_t st)
+{
+    auto it = c->sn_tickets.find(st);
+    if (it != c->sn_tickets.end()) return &it->second;
+    SnTicket tk;
+    if (cudaMalloc(&tk.ctr, sizeof(unsigned)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (cudaMemset(tk.ctr, 0, sizeof(unsigned)) != cudaSuccess) { cudaGetLastError(); cudaFree(tk.ctr); return nullptr; }
+    return &(c->sn_tickets[st] = tk);
+}
+
 // ---- launch sequence for one chunk of B proofs on one lane ----
 static void launch_share_eval(kosk_b200_ctx *c, const u16 *Y, u16 *SH, int slot_lo, int rows, int y_slots, int sh_slots, int B, cudaStream_t st,
                               bool const_secret = false, int8_t *YL0 = nullptr, int8_t *YL1 = nullptr, int32_t *ws = nullptr)
@@ -408,7 +423,7 @@ static void launch_share_eval(kosk_b200_ctx *c, const u16 *Y, u16 *SH, int slot_
     g.mtotal = B * rows; g.ksteps = YLD / GE_BK; g.nvalid = NX; g.c_off = SOFF + NT + 1;
     g.rpp = rows; g.slot_lo = slot_lo; g.a_slots = y_slots; g.c_slots = sh_slots; g.tail = 1; g.tail_off = NL;
     if (c->use_ntt && !(c->use_tensor && YL0)) {      // one warp per sharing; constant-secret rows need no special case here
-        c->launches += share_ntt_launch(share_conv_args(g, c->sn), st, c->use_ntt);
+        c->launches += share_ntt_launch(share_conv_args(g, c->sn), st, c->use_ntt, sn_ticket(c, st));
         return;
     }
     const int koff = const_secret ? NL : 0;
@@ -550,7 +565,7 @@ static int prove_chunk_k(kosk_b200_ctx *c, Lane &ln, const ProveBufs &bufs, int 
 
 static int verify_chunk_lane(kosk_b200_ctx *c, Lane &ln, int B, const u8 *d_pi, const u8 *d_pk, u8 *d_ok)
 {
-    VerifyTables vt{c->d_St, c->d_R1, c->d_R2, c->d_inv, c->d_SU, c->d_fact, c->d_U1, c->d_U2, c->use_ntt ? &c->sn : nullptr, c->use_ntt};
+    VerifyTables vt{c->d_St, c->d_R1, c->d_R2, c->d_inv, c->d_SU, c->d_fact, c->d_U1, c->d_U2, c->use_ntt ? &c->sn : nullptr, c->use_ntt, sn_ticket(c, ln.st), ln.vside.st ? sn_ticket(c, ln.vside.st) : nullptr};
     if (c->last_computed && c->last_computed != ln.computed) CU(cudaStreamWaitEvent(ln.st, c->last_computed, 0));
     prof_mark(c, ln, KOSK_PH_VERIFY);
     int nl = verify_chunk(c->k, ln.vb, vt, B, d_pi, d_pk, d_ok, ln.st, ln.vside);

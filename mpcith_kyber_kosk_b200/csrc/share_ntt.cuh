@@ -29,6 +29,9 @@ constexpr int SN_NIN = 4, SN_NOUT = 11;                                  // the 
 #define KOSK_SN_MINB 4
 #endif
 constexpr int SN_WARPS = KOSK_SN_WARPS;                                  // rows in flight per CTA
+// transpose buffers: 16 rows of SN_TS int16 per half-warp.  An even stride of 18 (9 words) puts the 16 rows a half-warp reads at 16 distinct banks (9 c mod 32)
+// for every column, and the second half-warp's buffer (288 int16 = 16 banks further) on the other 16; with 17 rows 0 and 15 collided for odd columns.
+constexpr int SN_TS = 18;
 constexpr int SN_LD = 24;               // int16 per k1 row of a spectrum in shared memory: 16 values (k2) + pad, so that the 128-bit row reads of a quarter-warp hit distinct banks
 
 // w16^(+-a k), centered; w16 = 17^16.  Compile-time tables: on sm_100a an IMAD takes no constant-bank operand (every c[] use became
@@ -72,6 +75,9 @@ __host__ __device__ inline int2 sn_pair(uint32_t v)                  // residue 
 //   recon_secrets_ddeg / _2ddeg (ss.cpp:37-73)      OFF = -256, pre = w_j,      post = P'(i)       (4, 2) / (7, 2)
 //   verifier interpolation (mlwe_verifier.cpp:188-224 etc.), rows already scaled by the per-proof weights, columns = parties
 //                                                   OFF = -256, pre = none,     post = per-proof P(t) (5, 4) / (8, 2)
+// Work ticket of k_share_ntt2: a device counter private to one stream.  Every processed row draws exactly one ticket, so a launch over
+// mtotal rows advances the counter by mtotal and the host knows its value at the start of the next launch without resetting it.
+struct SnTicket { unsigned *ctr = nullptr; unsigned base = 0; };
 struct ConvArgs {
     const u16 *A; u16 *C; long long lda, ldc;
     int mtotal, rpp, slot_lo, a_slots, c_slots, c_off;   // row m -> storage row (m / rpp) * slots + slot_lo + m % rpp
@@ -79,6 +85,7 @@ struct ConvArgs {
     const int2 *tw;          // [2][16][16]  (w, w') of 17^(+-b k1) (symmetric in b, k1)
     const int16_t *khat;     // [NIN + NOUT - 1][16 k1][SN_LD]  NTT(K_delta)[k1 + 16 k2] / 256, centered, at [k1][k2], delta = o - i
     const uint32_t *kpk;     // k_share_ntt2 only: [S2_NOUT][2][256] packed limb words of the (o, i) segment spectra
+    unsigned *ctr; unsigned ctr_base;   // k_share_ntt2 only: work ticket (SnTicket); nullptr = rows strided statically over the warps
     const int2 *pre;         // [128 NIN] (w, w') of the input factors, or nullptr
     const int2 *post;        // (w, w') of the output factors
     long long post_group;    // 0: one table; else the table of row m starts at post + (m / rpp) * post_group
@@ -93,7 +100,7 @@ __global__ void __launch_bounds__(32 * SN_WARPS, (NIN <= 5 ? KOSK_SN_MINB : KOSK
     __shared__ __align__(16) int16_t s_kh[NK * 16 * SN_LD];
     __shared__ __align__(8) int2 s_tw[2 * 256];
     __shared__ __align__(16) int16_t s_uh[SN_WARPS][NINP][16 * SN_LD];
-    // transpose buffers, one per half-warp: rows of 17 int16; 288 = 32 (mod 64) int16 puts the second half-warp's 16 banks between the first's
+    // transpose buffers, one per half-warp (SN_TS)
     __shared__ int16_t s_t[SN_WARPS][2][288];
     for (int i = threadIdx.x; i < NK * 16 * SN_LD; i += blockDim.x) s_kh[i] = g.khat[i];
     for (int i = threadIdx.x; i < 512; i += blockDim.x) s_tw[i] = g.tw[i];
@@ -135,11 +142,11 @@ __global__ void __launch_bounds__(32 * SN_WARPS, (NIN <= 5 ? KOSK_SN_MINB : KOSK
                 y[k + 8] = sn_shoup(ev - od, t1.x, t1.y);
             }
 #pragma unroll
-            for (int k = 0; k < 16; k++) T[k * 17 + c] = (int16_t)y[k];
+            for (int k = 0; k < 16; k++) T[k * SN_TS + c] = (int16_t)y[k];
             __syncwarp();
             int32_t in[16];
 #pragma unroll
-            for (int b = 0; b < 16; b++) in[b] = T[c * 17 + b];
+            for (int b = 0; b < 16; b++) in[b] = T[c * SN_TS + b];
             int32_t X[16];
 #pragma unroll
             for (int k = 0; k < 8; k++) {
@@ -198,11 +205,11 @@ __global__ void __launch_bounds__(32 * SN_WARPS, (NIN <= 5 ? KOSK_SN_MINB : KOSK
                 v[b + 8] = sn_shoup(ev - od, t1.x, t1.y);
             }
 #pragma unroll
-            for (int b = 0; b < 16; b++) T[b * 17 + c] = (int16_t)v[b];
+            for (int b = 0; b < 16; b++) T[b * SN_TS + c] = (int16_t)v[b];
             __syncwarp();
             int32_t in[16];
 #pragma unroll
-            for (int k = 0; k < 16; k++) in[k] = T[c * 17 + k];
+            for (int k = 0; k < 16; k++) in[k] = T[c * SN_TS + k];
 #pragma unroll
             for (int a = 0; a < 8; a++) {
                 int32_t acc = 0;
@@ -316,10 +323,30 @@ __global__ void __launch_bounds__(32 * S2_WARPS, KOSK_S2_MINB) k_share_ntt2(cons
     uint32_t *up = s_up[wid];
     int16_t *T = s_t[wid][hw];
     const int sw = (c >> 1) & 3;                                            // chunk ch of row c lives at chunk ch ^ sw
-    for (int m = blockIdx.x * S2_WARPS + wid; m < g.mtotal; m += gridDim.x * S2_WARPS) {
+    // Rows are handed out dynamically (one ticket per row): with a static stride the warps of the single wave drifted apart and the SMs
+    // idled 18 % of the warp slots at the tail (ncu: 23.1 of 28 warps active on average).
+    const int nw = gridDim.x * S2_WARPS;
+    int m = blockIdx.x * S2_WARPS + wid;
+    while (m < g.mtotal) {
+        int mn = m + nw;
+        if (g.ctr) {
+            unsigned t = 0;
+            if (lane == 0) t = atomicAdd(g.ctr, 1u) - g.ctr_base;
+            mn = nw + (int)__shfl_sync(0xffffffffu, t, 0);
+        }
         const u16 *yrow = g.A + ((size_t)(m / g.rpp) * g.a_slots + g.slot_lo + m % g.rpp) * g.lda;
         u16 *dst = g.C + ((size_t)(m / g.rpp) * g.c_slots + g.slot_lo + m % g.rpp) * g.ldc + g.c_off;
-        if (g.tail) for (int t = lane; t <= NT; t += 32) dst[t - (NT + 1)] = yrow[g.tail_off + t];
+        {   // the first touch of an input row is a DRAM miss that nothing hides (ncu: 16 % of the stall samples sat on the first uses of
+            // yrow): ask for this warp's NEXT row now, a whole sharing ahead
+            if (mn < g.mtotal && lane * 64 < (int)g.lda) {
+                const u16 *nrow = g.A + ((size_t)(mn / g.rpp) * g.a_slots + g.slot_lo + mn % g.rpp) * g.lda + lane * 64;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nrow));
+            }
+        }
+        u16 tl[(NT + 32) / 32];                                             // tail values: loaded here, stored after the forward passes
+        if (g.tail)
+#pragma unroll
+            for (int i = 0; i < (NT + 32) / 32; i++) { const int t = lane + 32 * i; tl[i] = t <= NT ? yrow[g.tail_off + t] : (u16)0; }
         // ---- forward: u_j = w_j y_j, NTT of the zero-padded 126-wide input blocks (two per pass) ----
 #pragma unroll 1
         for (int it = 0; it < S2_NIN / 2; it++) {
@@ -335,17 +362,20 @@ __global__ void __launch_bounds__(32 * S2_WARPS, KOSK_S2_MINB) k_share_ntt2(cons
             int32_t y[16];
             sn_dft16<false, SN_FFT_SMALL>(x, y);                           // rows 8..15 of the block are zero padding: x[8..15] = 0 folds away
 #pragma unroll
-            for (int k = 0; k < 16; k++) { const int2 t = s_tw[k * 16 + c]; T[k * 17 + c] = (int16_t)sn_shoup(y[k], t.x, t.y); }
+            for (int k = 0; k < 16; k++) { const int2 t = s_tw[k * 16 + c]; T[k * SN_TS + c] = (int16_t)sn_shoup(y[k], t.x, t.y); }
             __syncwarp();
             int32_t in[16], X[16];
 #pragma unroll
-            for (int b = 0; b < 16; b++) in[b] = T[c * 17 + b];
+            for (int b = 0; b < 16; b++) in[b] = T[c * SN_TS + b];
             sn_dft16<false, SN_FFT_SMALL>(in, X);
             int16_t *urow = reinterpret_cast<int16_t *>(up + it * 256 + c * 16) + hw;
 #pragma unroll
             for (int k = 0; k < 16; k++) urow[2 * ((((k >> 2) ^ sw) << 2) + (k & 3))] = (int16_t)sn_barrett(X[k]);
             __syncwarp();
         }
+        if (g.tail)
+#pragma unroll
+            for (int i = 0; i < (NT + 32) / 32; i++) { const int t = lane + 32 * i; if (t <= NT) dst[t - (NT + 1)] = tl[i]; }
         // ---- inverse: output blocks two per pass ----
 #pragma unroll 1
         for (int it = 0; it < S2_NOUT / 2; it++) {
@@ -369,11 +399,11 @@ __global__ void __launch_bounds__(32 * S2_WARPS, KOSK_S2_MINB) k_share_ntt2(cons
             int32_t v[16];
             sn_dft16<true, SN_FFT_BIG>(O, v);
 #pragma unroll
-            for (int b = 0; b < 16; b++) { const int2 t = s_tw[256 + b * 16 + c]; T[b * 17 + c] = (int16_t)sn_shoup(v[b], t.x, t.y); }
+            for (int b = 0; b < 16; b++) { const int2 t = s_tw[256 + b * 16 + c]; T[b * SN_TS + c] = (int16_t)sn_shoup(v[b], t.x, t.y); }
             __syncwarp();
             int32_t in[16], out[16];
 #pragma unroll
-            for (int k = 0; k < 16; k++) in[k] = T[c * 17 + k];
+            for (int k = 0; k < 16; k++) in[k] = T[c * SN_TS + k];
             sn_dft16<true, SN_FFT_SMALL>(in, out);                          // only out[0..8] are used: the rest of the last level is dead code
             const int xb = S2_BO * o + c;                                   // first output of this lane; row a adds 16 a
             const int2 *postp = g.post + xb;
@@ -393,11 +423,15 @@ __global__ void __launch_bounds__(32 * S2_WARPS, KOSK_S2_MINB) k_share_ntt2(cons
             for (int a = 0; a < 9; a++) emit(a, out[a]);
             __syncwarp();
         }
+        m = mn;
     }
 }
-static inline int share_ntt2_launch(const ConvArgs &g, cudaStream_t st)
+static inline int share_ntt2_launch(const ConvArgs &g0, cudaStream_t st, SnTicket *tk = nullptr)
 {
+    ConvArgs g = g0;
     const int ctas = std::min((g.mtotal + S2_WARPS - 1) / S2_WARPS, 148 * KOSK_S2_MINB);
+    g.ctr = nullptr; g.ctr_base = 0;
+    if (tk && tk->ctr && ctas > 0) { g.ctr = tk->ctr; g.ctr_base = tk->base; tk->base += (unsigned)g.mtotal; }
     if (ctas > 0) k_share_ntt2<D1, NX><<<ctas, 32 * S2_WARPS, 0, st>>>(g);
     return 1;
 }
@@ -425,9 +459,9 @@ static inline ConvArgs share_conv_args(const GemmArgs &g, const ShareNttTables &
     return a;
 }
 // variant 2 (default) = k_share_ntt2, variant 1 = the generic equal-block kernel
-static inline int share_ntt_launch(const ConvArgs &g, cudaStream_t st, int variant = 2)
+static inline int share_ntt_launch(const ConvArgs &g, cudaStream_t st, int variant = 2, SnTicket *tk = nullptr)
 {
-    return variant >= 2 ? share_ntt2_launch(g, st) : conv_ntt_launch<SN_NIN, SN_NOUT, D1, NX, true, false>(g, st);
+    return variant >= 2 ? share_ntt2_launch(g, st, tk) : conv_ntt_launch<SN_NIN, SN_NOUT, D1, NX, true, false>(g, st);
 }
 
 // ---- host: table construction (plain modular arithmetic, once per context) ----

@@ -25,7 +25,8 @@ enum VFlag { VF_I = 1, VF_BG = 2, VF_SR = 4, VF_NTT = 8, VF_ASR = 16, VF_T = 32,
 struct VerifyTables { const int16_t *St, *R1, *R2; const u16 *inv; const int16_t *SU; const u16 *fact; /* [2][FACT_N]: i!, 1/i! */
                       const int16_t *U1, *U2; /* Cauchy operands [U1_ROWS][KP1], [256][KP2], centered */
                       const ShareNttTables *sn; /* share evaluation as an NTT convolution (share_ntt.cuh); nullptr = dense table GEMM */
-                      int sn_variant = 2; /* share_ntt_launch variant */ };
+                      int sn_variant = 2; /* share_ntt_launch variant */
+                      SnTicket *tk_main = nullptr, *tk_side = nullptr; /* work tickets of the main / side stream (share_ntt.cuh) */ };
 
 struct VerifyBufs {
     int *flags = nullptr;
@@ -611,7 +612,7 @@ static int verify_chunk_t(VerifyBufs &vb, const VerifyTables &vt, int B, const u
     if (vt.sn) {
         g = GemmArgs{}; g.A = vb.YV; g.C = vb.VSH; g.lda = YLD; g.ldc = SLD; g.rpp = d.nyrows; g.slot_lo = 0; g.a_slots = d.nyrows; g.c_slots = d.nyrows;
         g.mtotal = B * d.nyrows; g.c_off = SOFF + NT + 1; g.tail = 1; g.tail_off = NL;
-        nl += share_ntt_launch(share_conv_args(g, *vt.sn), s2, vt.sn_variant);
+        nl += share_ntt_launch(share_conv_args(g, *vt.sn), s2, vt.sn_variant, fork ? vt.tk_side : vt.tk_main);
     } else {
         const int grp_lo[3] = {0, 3 * K, d.n1rows}, grp_hi[3] = {3 * K, d.n1rows, d.nyrows};
         for (int gi = 0; gi < 3; gi++) {
