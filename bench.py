@@ -31,10 +31,15 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 MACS_PER_PROVE = {2: 135.14e6, 3: 142.69e6, 4: 160.41e6}
 KECCAK_PER_PROVE = {2: 11196, 3: 11220, 4: 11254}
 SHARE_MACS_PER_ROW = 1303 * 407          # ss.cpp:23-32: one sharing = 1303 x 407 MACs
-# share_ntt.cuh: FMA-heavy-pipe issue slots per sharing (one warp), counted in the SASS of k_conv_ntt<4,11>: a forward pass has 182 IMAD
-# + 40 IMAD.HI, an inverse pass 290 IMAD + 40 IMAD.HI (DFT mat-vecs with immediate operands, pointwise products, Barrett / Shoup
-# reductions); IMAD.HI issues at half the IMAD rate (kosk_b200_int_peak: 8.8 T vs 18.5 T thread-ops/s), so it counts twice; x 32 lanes
-NTT_IMAD_PER_SHARING = (2 * (182 + 2 * 40) + 6 * (290 + 2 * 40)) * 32
+# share_ntt.cuh: FMA-heavy-pipe issue slots per sharing (one warp), counted in the SASS of the kernel (`python tools/sass_loops.py k_share_ntt2`):
+# IMAD.HI / IMAD.WIDE issue at half the IMAD rate (kosk_b200_int_peak: 8.8 T vs 18.5 T thread-ops/s) and count twice; IDP.2A is full rate
+# (tools/exp/idp_bench.cu); x 32 lanes.
+#   variant 2 (default, k_share_ntt2: 126 x 131 blocks, IDP.2A pointwise stage, radix-2 DFT networks): a forward pass has 135 IMAD + 50 IMAD.HI
+#     + 2 IMAD.WIDE, an inverse pass 113 IMAD + 64 IDP.2A + 47 IMAD.HI; 2 forward + 5 inverse passes
+#   variant 1 (k_conv_ntt<4,11>, KOSK_B200_SHARE_NTT=1): forward 182 IMAD + 40 IMAD.HI, inverse 290 IMAD + 40 IMAD.HI; 2 + 6 passes
+NTT_SLOTS_PER_SHARING = {2: (2 * (135 + 2 * 50 + 2 * 2) + 5 * (113 + 64 + 2 * 47)) * 32, 1: (2 * (182 + 2 * 40) + 6 * (290 + 2 * 40)) * 32}
+NTT_VARIANT = int(os.environ.get("KOSK_B200_SHARE_NTT", "2") or 2)
+NTT_IMAD_PER_SHARING = NTT_SLOTS_PER_SHARING[2 if NTT_VARIANT >= 2 else 1]
 INT_OPS_PER_KECCAK = 7440                # 24 rounds x 155 64-bit logic ops x 2 (32-bit lanes): algorithmic
 ALU_INSTR_PER_KECCAK = 24 * 180          # executed: 122 LOP3 + 58 SHF per round (keccak.cuh), thread-level
 SPONGE_FLOOR_US = 2.09                   # one warp-cooperative permutation alone on an SM (tools/exp/sponge_round_bench.cu)
@@ -245,7 +250,7 @@ def kernel_table(k, B, phases, steps, peaks, hbm_peak, proof_bytes, use_ntt):
             e["note"] = note
         out.append(e)
     per_share = NTT_IMAD_PER_SHARING if use_ntt else SHARE_MACS_PER_ROW
-    share_kernel = "k_conv_ntt<4,11> (share_ntt.cuh)" if use_ntt else "k_gf_gemm (gf_gemm.cuh)"
+    share_kernel = ("k_share_ntt2 (share_ntt.cuh)" if NTT_VARIANT >= 2 else "k_conv_ntt<4,11> (share_ntt.cuh)") if use_ntt else "k_gf_gemm (gf_gemm.cuh)"
     add("keygen", "k_keygen", "latency (one CTA per proof)", None, None, None)
     add("expand", "k_expand_f + k_ntt_f + k_tails", "ALU pipe (LOP3/SHF: Keccak)", B * (5 * s["F"] + 3 * (s["n1"] + k)) * ALU_INSTR_PER_KECCAK, alu, "ALU thread-instr")
     add("share1", share_kernel, "FMA-heavy pipe (IMAD)", B * s["n1"] * per_share, imad, "IMAD thread-instr")
@@ -319,7 +324,7 @@ def run_b200(args):
     chunk = args.chunk or -(-B // args.lanes)
     ctx = KoskContext(k, local, chunk, args.lanes)
     npk, nsk, npi = ctx.pk_bytes, ctx.sk_bytes, ctx.proof_bytes
-    use_ntt = os.environ.get("KOSK_B200_SHARE_NTT", "1") != "0"
+    use_ntt = os.environ.get("KOSK_B200_SHARE_NTT", "2") != "0"
 
     def barrier():
         if world > 1:
@@ -647,7 +652,7 @@ def run_b200(args):
         step_ms = ms_max / args.steps
         # Dominant kernel by its distance from its roofline = the share evaluation.  `achieved` / `frac` are what the FMA-heavy pipe EXECUTES
         # (IMAD thread-instructions per second against the IMAD issue peak measured in this process); the reference's table mat-vec would
-        # need 530 321 MACs per sharing, the NTT convolution executes 111 616: that ratio is `algorithmic_speedup`, not a pipe fraction.
+        # need 530 321 MACs per sharing, the NTT convolution executes 58 656 FMA-heavy issue slots: that ratio is `algorithmic_speedup`, not a pipe fraction.
         roofline = {"bound": "int32-pipe (FMA-heavy: IMAD)", "kernel": sh["kernel"] + ": share evaluation, ss.cpp:23-32; first share-eval phase, all sharings of the step",
                     "achieved": sh["achieved_per_s"] / 1e12, "peak": peaks["imad"] / 1e12, "unit": "T IMAD/s (executed thread-instructions)", "frac": sh["frac"],
                     "executed_imad_per_sharing": NTT_IMAD_PER_SHARING if use_ntt else SHARE_MACS_PER_ROW,
