@@ -69,199 +69,7 @@ __host__ __device__ inline int2 sn_pair(uint32_t v)                  // residue 
     return make_int2(w, (int32_t)((num >= 0 ? num + Q / 2 : num - Q / 2) / Q));
 }
 
-// One Toeplitz product per row:  C[row][c_off + x] = post[x] * sum_j c[x - j + OFF] * (pre[j] * A[row][j]),  c[m] = 1/m (0 for m = 0),
-// x < nout <= 128 NOUT, j < nin <= 128 NIN.  OFF lives in the kernel-segment table `khat` ([NIN + NOUT - 1] segments for o - i).
-//   sharing (ss.cpp:23-32, :88-97)                 OFF = 407,  pre = w_j,      post = P(x)        (4, 11)
-//   recon_secrets_ddeg / _2ddeg (ss.cpp:37-73)      OFF = -256, pre = w_j,      post = P'(i)       (4, 2) / (7, 2)
-//   verifier interpolation (mlwe_verifier.cpp:188-224 etc.), rows already scaled by the per-proof weights, columns = parties
-//                                                   OFF = -256, pre = none,     post = per-proof P(t) (5, 4) / (8, 2)
-// Work ticket of k_share_ntt2: a device counter private to one stream.  Every processed row draws exactly one ticket, so a launch over
-// mtotal rows advances the counter by mtotal and the host knows its value at the start of the next launch without resetting it.
-struct SnTicket { unsigned *ctr = nullptr; unsigned base = 0; };
-struct ConvArgs {
-    const u16 *A; u16 *C; long long lda, ldc;
-    int mtotal, rpp, slot_lo, a_slots, c_slots, c_off;   // row m -> storage row (m / rpp) * slots + slot_lo + m % rpp
-    int tail, tail_off;                                  // sharing: copy the 151 tail values to parties 0..150
-    const int2 *tw;          // [2][16][16]  (w, w') of 17^(+-b k1) (symmetric in b, k1)
-    const int16_t *khat;     // [NIN + NOUT - 1][16 k1][SN_LD]  NTT(K_delta)[k1 + 16 k2] / 256, centered, at [k1][k2], delta = o - i
-    const uint32_t *kpk;     // k_share_ntt2 only: [S2_NOUT][2][256] packed limb words of the (o, i) segment spectra
-    unsigned *ctr; unsigned ctr_base;   // k_share_ntt2 only: work ticket (SnTicket); nullptr = rows strided statically over the warps
-    const int2 *pre;         // [128 NIN] (w, w') of the input factors, or nullptr
-    const int2 *post;        // (w, w') of the output factors
-    long long post_group;    // 0: one table; else the table of row m starts at post + (m / rpp) * post_group
-};
-
-// NINV / NOUTV = valid inputs / outputs, PRE = input factors present, PGROUP = per-row-group output factors: compile-time, so that
-// the sharing's kernel carries none of the other products' branches
-template <int NIN, int NOUT, int NINV, int NOUTV, bool PRE, bool PGROUP>
-__global__ void __launch_bounds__(32 * SN_WARPS, (NIN <= 5 ? KOSK_SN_MINB : KOSK_SN_MINB - 1)) k_conv_ntt(const ConvArgs g)
-{
-    constexpr int NK = NIN + NOUT - 1, NINP = (NIN + 1) & ~1;
-    __shared__ __align__(16) int16_t s_kh[NK * 16 * SN_LD];
-    __shared__ __align__(8) int2 s_tw[2 * 256];
-    __shared__ __align__(16) int16_t s_uh[SN_WARPS][NINP][16 * SN_LD];
-    // transpose buffers, one per half-warp (SN_TS)
-    __shared__ int16_t s_t[SN_WARPS][2][288];
-    for (int i = threadIdx.x; i < NK * 16 * SN_LD; i += blockDim.x) s_kh[i] = g.khat[i];
-    for (int i = threadIdx.x; i < 512; i += blockDim.x) s_tw[i] = g.tw[i];
-    __syncthreads();
-    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, hw = lane >> 4, c = lane & 15;
-    int16_t (*uh)[16 * SN_LD] = s_uh[wid];
-    int16_t *T = s_t[wid][hw];
-    auto lo16 = [](uint32_t w) -> int32_t { return (int32_t)(int16_t)(w & 0xFFFFu); };
-    auto hi16 = [](uint32_t w) -> int32_t { return (int32_t)w >> 16; };
-    for (int m = blockIdx.x * SN_WARPS + wid; m < g.mtotal; m += gridDim.x * SN_WARPS) {
-        const u16 *yrow = g.A + ((size_t)(m / g.rpp) * g.a_slots + g.slot_lo + m % g.rpp) * g.lda;
-        u16 *dst = g.C + ((size_t)(m / g.rpp) * g.c_slots + g.slot_lo + m % g.rpp) * g.ldc + g.c_off;
-        const int2 *post = g.post + (PGROUP ? (size_t)(m / g.rpp) * g.post_group : 0);
-        if (g.tail) for (int t = lane; t <= NT; t += 32) dst[t - (NT + 1)] = yrow[g.tail_off + t];
-        // ---- forward: u_j = pre_j A_j, NTT of the zero-padded 128-wide input blocks (two per pass) ----
-#pragma unroll 1
-        for (int it = 0; it < NINP / 2; it++) {
-            const int blk = 2 * it + hw;
-            int32_t x[8];
-#pragma unroll
-            for (int a = 0; a < 8; a++) {
-                const int j = 128 * blk + 16 * a + c;
-                int32_t v = 0;
-                if (j < NINV) {
-                    v = (int32_t)yrow[j];
-                    if (PRE) { const int2 p = __ldg(g.pre + j); v = sn_shoup(v, p.x, p.y); }
-                }
-                x[a] = v;
-            }
-            int32_t y[16];
-            // w16^(a (k + 8)) = (-1)^a w16^(a k): even and odd inputs are summed once for the output pair (k, k + 8)
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-                int32_t ev = 0, od = 0;
-#pragma unroll
-                for (int a = 0; a < 8; a += 2) { ev += x[a] * c_sn_w16f[a * 16 + k]; od += x[a + 1] * c_sn_w16f[(a + 1) * 16 + k]; }
-                const int2 t0 = s_tw[k * 16 + c], t1 = s_tw[(k + 8) * 16 + c];
-                y[k] = sn_shoup(ev + od, t0.x, t0.y);
-                y[k + 8] = sn_shoup(ev - od, t1.x, t1.y);
-            }
-#pragma unroll
-            for (int k = 0; k < 16; k++) T[k * SN_TS + c] = (int16_t)y[k];
-            __syncwarp();
-            int32_t in[16];
-#pragma unroll
-            for (int b = 0; b < 16; b++) in[b] = T[c * SN_TS + b];
-            int32_t X[16];
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-                int32_t ev = 0, od = 0;
-#pragma unroll
-                for (int b = 0; b < 16; b += 2) { ev += in[b] * c_sn_w16f[b * 16 + k]; od += in[b + 1] * c_sn_w16f[(b + 1) * 16 + k]; }
-                X[k] = sn_barrett(ev + od); X[k + 8] = sn_barrett(ev - od);
-            }
-            {   // row k1 = c of the spectrum: 16 values (k2) as two 128-bit stores
-                uint32_t w[8];
-#pragma unroll
-                for (int k = 0; k < 8; k++) w[k] = ((uint32_t)X[2 * k] & 0xFFFFu) | ((uint32_t)X[2 * k + 1] << 16);
-                uint4 *p = reinterpret_cast<uint4 *>(&uh[blk][c * SN_LD]);
-                p[0] = make_uint4(w[0], w[1], w[2], w[3]); p[1] = make_uint4(w[4], w[5], w[6], w[7]);
-            }
-            __syncwarp();
-        }
-        // ---- inverse: output blocks two per pass ----
-#pragma unroll 1
-        for (int it = 0; it < (NOUT + 1) / 2; it++) {
-            const int o = 2 * it + hw;
-            const bool live = o < NOUT;
-            int32_t O[16];
-            {
-                int32_t acc[16];
-#pragma unroll
-                for (int k = 0; k < 16; k++) acc[k] = 0;
-                if (live) {
-#pragma unroll
-                    for (int i = 0; i < NIN; i++) {
-                        const uint4 *pu = reinterpret_cast<const uint4 *>(&uh[i][c * SN_LD]);
-                        const uint4 *pk = reinterpret_cast<const uint4 *>(&s_kh[((o - i + NIN - 1) * 16 + c) * SN_LD]);
-#pragma unroll
-                        for (int h2 = 0; h2 < 2; h2++) {
-                            const uint4 u4 = pu[h2], k4 = pk[h2];
-                            const uint32_t uw[4] = {u4.x, u4.y, u4.z, u4.w}, kw[4] = {k4.x, k4.y, k4.z, k4.w};
-#pragma unroll
-                            for (int e = 0; e < 4; e++) {
-                                acc[8 * h2 + 2 * e] += lo16(uw[e]) * lo16(kw[e]);
-                                acc[8 * h2 + 2 * e + 1] += hi16(uw[e]) * hi16(kw[e]);
-                            }
-                        }
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < 16; k++) O[k] = sn_barrett(acc[k]);
-            }
-            int32_t v[16];
-#pragma unroll
-            for (int b = 0; b < 8; b++) {
-                int32_t ev = 0, od = 0;
-#pragma unroll
-                for (int k = 0; k < 16; k += 2) { ev += O[k] * c_sn_w16i[k * 16 + b]; od += O[k + 1] * c_sn_w16i[(k + 1) * 16 + b]; }
-                const int2 t0 = s_tw[256 + b * 16 + c], t1 = s_tw[256 + (b + 8) * 16 + c];
-                v[b] = sn_shoup(ev + od, t0.x, t0.y);
-                v[b + 8] = sn_shoup(ev - od, t1.x, t1.y);
-            }
-#pragma unroll
-            for (int b = 0; b < 16; b++) T[b * SN_TS + c] = (int16_t)v[b];
-            __syncwarp();
-            int32_t in[16];
-#pragma unroll
-            for (int k = 0; k < 16; k++) in[k] = T[c * SN_TS + k];
-#pragma unroll
-            for (int a = 0; a < 8; a++) {
-                int32_t acc = 0;
-#pragma unroll
-                for (int k = 0; k < 16; k++) acc += in[k] * c_sn_w16i[k * 16 + a];
-                const int xo = 128 * o + 16 * a + c;
-                if (live && xo < NOUTV) {
-                    const int2 pf = PGROUP ? post[xo] : __ldg(post + xo);
-                    int32_t r = sn_shoup(acc, pf.x, pf.y);
-                    if (r < 0) r += Q;
-                    if (r >= Q) r -= Q;
-                    dst[xo] = (u16)r;
-                }
-            }
-            __syncwarp();
-        }
-    }
-}
-
-template <int NIN, int NOUT, int NINV, int NOUTV, bool PRE, bool PGROUP>
-static inline int conv_ntt_launch(const ConvArgs &g, cudaStream_t st)
-{
-    const int ctas = std::min((g.mtotal + SN_WARPS - 1) / SN_WARPS, 148 * 8);
-    if (ctas > 0) k_conv_ntt<NIN, NOUT, NINV, NOUTV, PRE, PGROUP><<<ctas, 32 * SN_WARPS, 0, st>>>(g);
-    return 1;
-}
-
-// ---------------------------------------------------------------------------------------------
-// The sharing itself (the (4, 11) product above, 96 % of all rows) with unequal blocks and a packed pointwise stage.
-//   * Blocks: 126 inputs x 131 outputs per length-256 cyclic convolution (126 + 131 - 1 = 256) instead of 128 x 128: 4 input blocks
-//     (504 >= 407) and TEN output blocks (1310 >= 1303) instead of eleven, i.e. five two-block passes instead of six.  The ninth output row
-//     (x' = 128..130) of a block is free: w16^(8 k) = (-1)^k, so rows 0 and 8 share one even / odd sum.  The kernel segment of block (o, i)
-//     is K[d] = c[131 o - 126 i + 407 + d], d in [-125, 130]: it depends on o and i separately, 40 spectra instead of 14.
-//   * Pointwise stage: the spectra of input blocks 2p and 2p + 1 sit in one 32-bit word (two int16), and the segment spectra of (o, 2p),
-//     (o, 2p + 1) are split into signed limbs k = 64 k1 + k0 (k0 in [-32, 32), |k1| <= 26) and packed as the four bytes (k0, k0', k1, k1') of
-//     one word, so that   acc0 += u . (k0, k0')  and  acc1 += u . (k1, k1')   are one IDP.2A.LO and one IDP.2A.HI on the FMA-heavy pipe (full
-//     rate, tools/exp/idp_bench.cu) with both operands used exactly as loaded: 64 IDP per pass replace 64 IMAD + 128 ALU-pipe unpacks
-//     (PRMT / SHF) of the int16 spectra; the limbs are recombined inside the Barrett step's input (acc0 + 64 acc1 < 2^26).
-// Shared-memory rows are 16 words without padding; the 16-byte chunk index is XOR-swizzled with bits 1..2 of the row so that the 128-bit
-// row reads of a quarter-warp hit distinct banks.
-constexpr int S2_BI = 126, S2_BO = 131, S2_NIN = 4, S2_NOUT = 10;
-#ifndef KOSK_S2_WARPS
-#define KOSK_S2_WARPS 7
-#endif
-#ifndef KOSK_S2_MINB
-#define KOSK_S2_MINB 4
-#endif
-constexpr int S2_WARPS = KOSK_S2_WARPS;
-static_assert(S2_BI + S2_BO - 1 == 256 && S2_NIN * S2_BI >= D1 && S2_NOUT * S2_BO >= NX && S2_NIN == 4 && S2_NOUT % 2 == 0, "share_ntt2 blocking");
-__host__ __device__ constexpr int s2_word(int k1, int k2) { return k1 * 16 + ((((k2 >> 2) ^ (k1 >> 1)) & 3) << 2) + (k2 & 3); }   // word of bin (k1, k2) in a swizzled [16][16] tile
-
-// 16-point DFTs of k_share_ntt2 as radix-2 decimation-in-time networks in registers (natural order in and out) instead of 16 x 16 mat-vecs:
+// 16-point DFTs as radix-2 decimation-in-time networks in registers (natural order in and out) instead of 16 x 16 mat-vecs:
 // 17 twiddle multiplications per transform.  A multiplication is either LAZY (one IMAD, the product of a small value with a centered constant
 // stays an unreduced int32) or a SHOUP multiplication (IMAD.HI + 2 IMAD = 4 issue slots, result in (-q/4, 5q/4) for any |s| < 2^31); which one
 // is a 17-bit compile-time mask, chosen by exhaustive search over interval bounds (tools/exp/fft16_plan.py) so that no intermediate exceeds
@@ -308,6 +116,193 @@ struct SnDft<1, OFF, STRIDE, INV, MASK> {
 };
 template <bool INV, uint32_t MASK>
 __device__ __forceinline__ void sn_dft16(const int32_t (&x)[16], int32_t (&out)[16]) { SnDft<16, 0, 1, INV, MASK>::run(x, out); }
+
+// One Toeplitz product per row:  C[row][c_off + x] = post[x] * sum_j c[x - j + OFF] * (pre[j] * A[row][j]),  c[m] = 1/m (0 for m = 0),
+// x < nout <= 128 NOUT, j < nin <= 128 NIN.  OFF lives in the kernel-segment table `khat` ([NIN + NOUT - 1] segments for o - i).
+//   sharing (ss.cpp:23-32, :88-97)                 OFF = 407,  pre = w_j,      post = P(x)        (4, 11)
+//   recon_secrets_ddeg / _2ddeg (ss.cpp:37-73)      OFF = -256, pre = w_j,      post = P'(i)       (4, 2) / (7, 2)
+//   verifier interpolation (mlwe_verifier.cpp:188-224 etc.), rows already scaled by the per-proof weights, columns = parties
+//                                                   OFF = -256, pre = none,     post = per-proof P(t) (5, 4) / (8, 2)
+// Work ticket of k_share_ntt2: a device counter private to one stream.  Every processed row draws exactly one ticket, so a launch over
+// mtotal rows advances the counter by mtotal and the host knows its value at the start of the next launch without resetting it.
+struct SnTicket { unsigned *ctr = nullptr; unsigned base = 0; };
+struct ConvArgs {
+    const u16 *A; u16 *C; long long lda, ldc;
+    int mtotal, rpp, slot_lo, a_slots, c_slots, c_off;   // row m -> storage row (m / rpp) * slots + slot_lo + m % rpp
+    int tail, tail_off;                                  // sharing: copy the 151 tail values to parties 0..150
+    const int2 *tw;          // [2][16][16]  (w, w') of 17^(+-b k1) (symmetric in b, k1)
+    const int16_t *khat;     // [NIN + NOUT - 1][16 k1][SN_LD]  NTT(K_delta)[k1 + 16 k2] / 256, centered, at [k1][k2], delta = o - i
+    const uint32_t *kpk;     // k_share_ntt2 only: [S2_NOUT][2][256] packed limb words of the (o, i) segment spectra
+    unsigned *ctr; unsigned ctr_base;   // k_share_ntt2 only: work ticket (SnTicket); nullptr = rows strided statically over the warps
+    const int2 *pre;         // [128 NIN] (w, w') of the input factors, or nullptr
+    const int2 *post;        // (w, w') of the output factors
+    long long post_group;    // 0: one table; else the table of row m starts at post + (m / rpp) * post_group
+};
+
+// NINV / NOUTV = valid inputs / outputs, PRE = input factors present, PGROUP = per-row-group output factors: compile-time, so that
+// the sharing's kernel carries none of the other products' branches
+template <int NIN, int NOUT, int NINV, int NOUTV, bool PRE, bool PGROUP>
+__global__ void __launch_bounds__(32 * SN_WARPS, (NIN <= 5 ? KOSK_SN_MINB : KOSK_SN_MINB - 1)) k_conv_ntt(const ConvArgs g)
+{
+    constexpr int NK = NIN + NOUT - 1, NINP = (NIN + 1) & ~1;
+    __shared__ __align__(16) int16_t s_kh[NK * 16 * SN_LD];
+    __shared__ __align__(8) int2 s_tw[2 * 256];
+    __shared__ __align__(16) int16_t s_uh[SN_WARPS][NINP][16 * SN_LD];
+    // transpose buffers, one per half-warp (SN_TS)
+    __shared__ int16_t s_t[SN_WARPS][2][288];
+    for (int i = threadIdx.x; i < NK * 16 * SN_LD; i += blockDim.x) s_kh[i] = g.khat[i];
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) s_tw[i] = g.tw[i];
+    __syncthreads();
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, hw = lane >> 4, c = lane & 15;
+    int16_t (*uh)[16 * SN_LD] = s_uh[wid];
+    int16_t *T = s_t[wid][hw];
+    auto lo16 = [](uint32_t w) -> int32_t { return (int32_t)(int16_t)(w & 0xFFFFu); };
+    auto hi16 = [](uint32_t w) -> int32_t { return (int32_t)w >> 16; };
+    // rows are drawn from a work ticket and the next row is prefetched, as in k_share_ntt2 below
+    const int nw = gridDim.x * SN_WARPS;
+    int m = blockIdx.x * SN_WARPS + wid;
+    while (m < g.mtotal) {
+        int mn = m + nw;
+        if (g.ctr) {
+            unsigned t = 0;
+            if (lane == 0) t = atomicAdd(g.ctr, 1u) - g.ctr_base;
+            mn = nw + (int)__shfl_sync(0xffffffffu, t, 0);
+        }
+        const u16 *yrow = g.A + ((size_t)(m / g.rpp) * g.a_slots + g.slot_lo + m % g.rpp) * g.lda;
+        u16 *dst = g.C + ((size_t)(m / g.rpp) * g.c_slots + g.slot_lo + m % g.rpp) * g.ldc + g.c_off;
+        const int2 *post = g.post + (PGROUP ? (size_t)(m / g.rpp) * g.post_group : 0);
+        if (mn < g.mtotal && lane * 64 < NINV) {
+            const u16 *nrow = g.A + ((size_t)(mn / g.rpp) * g.a_slots + g.slot_lo + mn % g.rpp) * g.lda + lane * 64;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nrow));
+        }
+        if (g.tail) for (int t = lane; t <= NT; t += 32) dst[t - (NT + 1)] = yrow[g.tail_off + t];
+        // ---- forward: u_j = pre_j A_j, NTT of the zero-padded 128-wide input blocks (two per pass) ----
+#pragma unroll 1
+        for (int it = 0; it < NINP / 2; it++) {
+            const int blk = 2 * it + hw;
+            int32_t x[16];                                                 // rows 8..15 of a block are zero padding: they fold away in the transform
+#pragma unroll
+            for (int a = 0; a < 16; a++) {
+                const int j = 128 * blk + 16 * a + c;
+                int32_t v = 0;
+                if (a < 8 && j < NINV) {
+                    v = (int32_t)yrow[j];
+                    if (PRE) { const int2 p = __ldg(g.pre + j); v = sn_shoup(v, p.x, p.y); }   // without a factor: any u16, the transform's bounds hold up to 65535
+                }
+                x[a] = v;
+            }
+            int32_t y[16];
+            sn_dft16<false, SN_FFT_SMALL>(x, y);
+#pragma unroll
+            for (int k = 0; k < 16; k++) { const int2 t = s_tw[k * 16 + c]; T[k * SN_TS + c] = (int16_t)sn_shoup(y[k], t.x, t.y); }
+            __syncwarp();
+            int32_t in[16];
+#pragma unroll
+            for (int b = 0; b < 16; b++) in[b] = T[c * SN_TS + b];
+            int32_t X[16];
+            sn_dft16<false, SN_FFT_SMALL>(in, X);
+#pragma unroll
+            for (int k = 0; k < 16; k++) X[k] = sn_barrett(X[k]);
+            {   // row k1 = c of the spectrum: 16 values (k2) as two 128-bit stores
+                uint32_t w[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) w[k] = ((uint32_t)X[2 * k] & 0xFFFFu) | ((uint32_t)X[2 * k + 1] << 16);
+                uint4 *p = reinterpret_cast<uint4 *>(&uh[blk][c * SN_LD]);
+                p[0] = make_uint4(w[0], w[1], w[2], w[3]); p[1] = make_uint4(w[4], w[5], w[6], w[7]);
+            }
+            __syncwarp();
+        }
+        // ---- inverse: output blocks two per pass ----
+#pragma unroll 1
+        for (int it = 0; it < (NOUT + 1) / 2; it++) {
+            const int o = 2 * it + hw;
+            const bool live = o < NOUT;
+            int32_t O[16];
+            {
+                int32_t acc[16];
+#pragma unroll
+                for (int k = 0; k < 16; k++) acc[k] = 0;
+                if (live) {
+#pragma unroll
+                    for (int i = 0; i < NIN; i++) {
+                        const uint4 *pu = reinterpret_cast<const uint4 *>(&uh[i][c * SN_LD]);
+                        const uint4 *pk = reinterpret_cast<const uint4 *>(&s_kh[((o - i + NIN - 1) * 16 + c) * SN_LD]);
+#pragma unroll
+                        for (int h2 = 0; h2 < 2; h2++) {
+                            const uint4 u4 = pu[h2], k4 = pk[h2];
+                            const uint32_t uw[4] = {u4.x, u4.y, u4.z, u4.w}, kw[4] = {k4.x, k4.y, k4.z, k4.w};
+#pragma unroll
+                            for (int e = 0; e < 4; e++) {
+                                acc[8 * h2 + 2 * e] += lo16(uw[e]) * lo16(kw[e]);
+                                acc[8 * h2 + 2 * e + 1] += hi16(uw[e]) * hi16(kw[e]);
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 16; k++) O[k] = acc[k];                 // at most 8 x 6700 x 1664 < 2^26.5: reduced inside the transform (SN_FFT_BIG)
+            }
+            int32_t v[16];
+            sn_dft16<true, SN_FFT_BIG>(O, v);
+#pragma unroll
+            for (int b = 0; b < 16; b++) { const int2 t = s_tw[256 + b * 16 + c]; T[b * SN_TS + c] = (int16_t)sn_shoup(v[b], t.x, t.y); }
+            __syncwarp();
+            int32_t in[16], out[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) in[k] = T[c * SN_TS + k];
+            sn_dft16<true, SN_FFT_SMALL>(in, out);                          // only out[0..7] are used: the rest of the last level is dead code
+            const int na = !live ? 0 : min(8, (NOUTV - (128 * o + c) + 15) >> 4);
+#pragma unroll
+            for (int a = 0; a < 8; a++) {
+                const int xo = 128 * o + 16 * a + c;
+                if (a < na) {
+                    const int2 pf = PGROUP ? post[xo] : __ldg(post + xo);
+                    uint32_t r = (uint32_t)sn_shoup(out[a], pf.x, pf.y);     // in (-q/4, 5q/4): canonical with two unsigned minima
+                    r = min(r, r + Q);
+                    r = min(r, r - Q);
+                    dst[xo] = (u16)r;
+                }
+            }
+            __syncwarp();
+        }
+        m = mn;
+    }
+}
+
+template <int NIN, int NOUT, int NINV, int NOUTV, bool PRE, bool PGROUP>
+static inline int conv_ntt_launch(const ConvArgs &g0, cudaStream_t st, SnTicket *tk = nullptr)
+{
+    ConvArgs g = g0;
+    const int ctas = std::min((g.mtotal + SN_WARPS - 1) / SN_WARPS, 148 * 8);
+    g.ctr = nullptr; g.ctr_base = 0;
+    if (tk && tk->ctr && ctas > 0) { g.ctr = tk->ctr; g.ctr_base = tk->base; tk->base += (unsigned)g.mtotal; }
+    if (ctas > 0) k_conv_ntt<NIN, NOUT, NINV, NOUTV, PRE, PGROUP><<<ctas, 32 * SN_WARPS, 0, st>>>(g);
+    return 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The sharing itself (the (4, 11) product above, 96 % of all rows) with unequal blocks and a packed pointwise stage.
+//   * Blocks: 126 inputs x 131 outputs per length-256 cyclic convolution (126 + 131 - 1 = 256) instead of 128 x 128: 4 input blocks
+//     (504 >= 407) and TEN output blocks (1310 >= 1303) instead of eleven, i.e. five two-block passes instead of six.  The ninth output row
+//     (x' = 128..130) of a block is free: w16^(8 k) = (-1)^k, so rows 0 and 8 share one even / odd sum.  The kernel segment of block (o, i)
+//     is K[d] = c[131 o - 126 i + 407 + d], d in [-125, 130]: it depends on o and i separately, 40 spectra instead of 14.
+//   * Pointwise stage: the spectra of input blocks 2p and 2p + 1 sit in one 32-bit word (two int16), and the segment spectra of (o, 2p),
+//     (o, 2p + 1) are split into signed limbs k = 64 k1 + k0 (k0 in [-32, 32), |k1| <= 26) and packed as the four bytes (k0, k0', k1, k1') of
+//     one word, so that   acc0 += u . (k0, k0')  and  acc1 += u . (k1, k1')   are one IDP.2A.LO and one IDP.2A.HI on the FMA-heavy pipe (full
+//     rate, tools/exp/idp_bench.cu) with both operands used exactly as loaded: 64 IDP per pass replace 64 IMAD + 128 ALU-pipe unpacks
+//     (PRMT / SHF) of the int16 spectra; the limbs are recombined inside the Barrett step's input (acc0 + 64 acc1 < 2^26).
+// Shared-memory rows are 16 words without padding; the 16-byte chunk index is XOR-swizzled with bits 1..2 of the row so that the 128-bit
+// row reads of a quarter-warp hit distinct banks.
+constexpr int S2_BI = 126, S2_BO = 131, S2_NIN = 4, S2_NOUT = 10;
+#ifndef KOSK_S2_WARPS
+#define KOSK_S2_WARPS 7
+#endif
+#ifndef KOSK_S2_MINB
+#define KOSK_S2_MINB 4
+#endif
+constexpr int S2_WARPS = KOSK_S2_WARPS;
+static_assert(S2_BI + S2_BO - 1 == 256 && S2_NIN * S2_BI >= D1 && S2_NOUT * S2_BO >= NX && S2_NIN == 4 && S2_NOUT % 2 == 0, "share_ntt2 blocking");
+__host__ __device__ constexpr int s2_word(int k1, int k2) { return k1 * 16 + ((((k2 >> 2) ^ (k1 >> 1)) & 3) << 2) + (k2 & 3); }   // word of bin (k1, k2) in a swizzled [16][16] tile
 
 template <int NINV, int NOUTV>
 __global__ void __launch_bounds__(32 * S2_WARPS, KOSK_S2_MINB) k_share_ntt2(const ConvArgs g)
@@ -461,7 +456,7 @@ static inline ConvArgs share_conv_args(const GemmArgs &g, const ShareNttTables &
 // variant 2 (default) = k_share_ntt2, variant 1 = the generic equal-block kernel
 static inline int share_ntt_launch(const ConvArgs &g, cudaStream_t st, int variant = 2, SnTicket *tk = nullptr)
 {
-    return variant >= 2 ? share_ntt2_launch(g, st, tk) : conv_ntt_launch<SN_NIN, SN_NOUT, D1, NX, true, false>(g, st);
+    return variant >= 2 ? share_ntt2_launch(g, st, tk) : conv_ntt_launch<SN_NIN, SN_NOUT, D1, NX, true, false>(g, st, tk);
 }
 
 // ---- host: table construction (plain modular arithmetic, once per context) ----

@@ -590,11 +590,11 @@ static int verify_chunk_t(VerifyBufs &vb, const VerifyTables &vt, int B, const u
     if (vt.sn) {
         cv = ConvArgs{}; cv.A = vb.A1; cv.C = vb.YV; cv.lda = KP1; cv.ldc = YLD; cv.mtotal = B * d.n1rows; cv.rpp = d.n1rows; cv.a_slots = d.n1rows; cv.c_slots = d.nyrows;
         cv.tw = vt.sn->tw; cv.khat = sn_kh_m256(*vt.sn, 5); cv.post = reinterpret_cast<const int2 *>(vb.PT1); cv.post_group = LM1_ROWS;
-        nl += conv_ntt_launch<5, 4, KP1, D1, false, true>(cv, s2);
+        nl += conv_ntt_launch<5, 4, KP1, D1, false, true>(cv, s2, fork ? vt.tk_side : vt.tk_main);
         kv_node_targets<K><<<dim3(d.n1rows, B), 160, 0, s2>>>(vb, d_pi); nl++;
         cv = ConvArgs{}; cv.A = vb.A2; cv.C = vb.UZ; cv.lda = KP2; cv.ldc = 256; cv.mtotal = B * d.n2rows; cv.rpp = d.n2rows; cv.a_slots = d.n2rows; cv.c_slots = d.n2rows;
         cv.tw = vt.sn->tw; cv.khat = sn_kh_m256(*vt.sn, 8); cv.post = reinterpret_cast<const int2 *>(vb.PT2); cv.post_group = 256;
-        nl += conv_ntt_launch<8, 2, KP2, 256, false, true>(cv, s2);
+        nl += conv_ntt_launch<8, 2, KP2, 256, false, true>(cv, s2, fork ? vt.tk_side : vt.tk_main);
     } else {
         g = GemmArgs{}; g.ws = vb.WS; g.ws_elems = GE_WS_ELEMS; g.A = vb.A1; g.Bt = vt.U1; g.C = vb.YV; g.lda = KP1; g.ldb = KP1; g.ldc = YLD;
         g.mtotal = B * d.n1rows; g.ksteps = KP1 / GE_BK; g.nvalid = D1; g.rpp = d.n1rows; g.a_slots = d.n1rows; g.c_slots = d.nyrows;
@@ -631,7 +631,7 @@ static int verify_chunk_t(VerifyBufs &vb, const VerifyTables &vt, int B, const u
     if (vt.sn) {
         cv = ConvArgs{}; cv.A = vb.ABG; cv.C = vb.BS; cv.lda = YLD; cv.ldc = 256; cv.mtotal = B * 2 * MK; cv.rpp = cv.mtotal;
         cv.tw = vt.sn->tw; cv.khat = sn_kh_m256(*vt.sn, 4); cv.pre = vt.sn->wj; cv.post = vt.sn->pr1;
-        nl += conv_ntt_launch<4, 2, D1, 256, true, false>(cv, st);
+        nl += conv_ntt_launch<4, 2, D1, 256, true, false>(cv, st, vt.tk_main);
     } else {
         g = GemmArgs{}; g.ws = vb.WS; g.ws_elems = GE_WS_ELEMS; g.A = vb.ABG; g.Bt = vt.R1; g.C = vb.BS; g.lda = YLD; g.ldb = YLD; g.ldc = 256;
         g.mtotal = B * 2 * MK; g.ksteps = YLD / GE_BK; g.nvalid = 256; g.rpp = g.mtotal; g.c_off = 0; g.half_last = 1;
@@ -643,7 +643,7 @@ static int verify_chunk_t(VerifyBufs &vb, const VerifyTables &vt, int B, const u
     if (vt.sn) {      // recon_secrets_2ddeg over parties 0..812 (ss.cpp:56-73)
         cv = ConvArgs{}; cv.A = vb.U2; cv.C = vb.UR; cv.lda = VR2LD; cv.ldc = 256; cv.mtotal = B * d.n2rows; cv.rpp = cv.mtotal;
         cv.tw = vt.sn->tw; cv.khat = sn_kh_m256(*vt.sn, 7); cv.pre = vt.sn->wj2; cv.post = vt.sn->pr2;
-        nl += conv_ntt_launch<7, 2, D2, 256, true, false>(cv, st);
+        nl += conv_ntt_launch<7, 2, D2, 256, true, false>(cv, st, vt.tk_main);
     } else {
         g = GemmArgs{}; g.ws = vb.WS; g.ws_elems = GE_WS_ELEMS; g.A = vb.U2; g.Bt = vt.R2; g.C = vb.UR; g.lda = VR2LD; g.ldb = VR2LD; g.ldc = 256;
         g.mtotal = B * d.n2rows; g.ksteps = VR2LD / GE_BK; g.nvalid = 256; g.rpp = g.mtotal;
