@@ -185,25 +185,29 @@ __global__ void __launch_bounds__(320) kv_eval_opened(VerifyBufs vb)
     for (int kk = 0; kk < FP; kk++) fr[kk] = kk < F ? gf_center(f[kk] % (uint32_t)Q) : 0;
     const bool canon0 = f[0] < Q, canon71 = f[MK + 1] < Q;
     const int32_t c0 = fr[0], c71 = fr[MK + 1];
+    auto put = [&](int j, u16 res) { if (j < MK) out[half * MK + j] = res; else out[2 * MK + half * 2 * K + (j - MK)] = res; };
+    static_assert(NA % 2 == 0 && MK % 2 == 0, "challenge pairs must not straddle the beta / r boundary");
 #pragma unroll 1
-    for (int j = 0; j < NA; j++) {
+    for (int j = 0; j < NA; j += 2) {                           // two challenges per iteration: two independent IMAD chains per thread
         const bool fast = j < MK ? canon0 : canon71;
-        u16 res;
         if (fast) {
-            int32_t acc = 0;                                 // 78 * 1664^2 < 2^31; the k = 0 term is replaced by the c0 share below
+            int32_t acc0 = 0, acc1 = 0;                          // 78 * 1664^2 < 2^31; the k = 0 term is replaced by the c0 share below
 #pragma unroll
             for (int k4 = 0; k4 < FP / 4; k4++) {
-                const int4 w = *reinterpret_cast<const int4 *>(&spw[j][4 * k4]);
-                acc += fr[4 * k4] * w.x + fr[4 * k4 + 1] * w.y + fr[4 * k4 + 2] * w.z + fr[4 * k4 + 3] * w.w;
+                const int4 w0 = *reinterpret_cast<const int4 *>(&spw[j][4 * k4]), w1 = *reinterpret_cast<const int4 *>(&spw[j + 1][4 * k4]);
+                acc0 += fr[4 * k4] * w0.x + fr[4 * k4 + 1] * w0.y + fr[4 * k4 + 2] * w0.z + fr[4 * k4 + 3] * w0.w;
+                acc1 += fr[4 * k4] * w1.x + fr[4 * k4 + 1] * w1.y + fr[4 * k4 + 2] * w1.z + fr[4 * k4 + 3] * w1.w;
             }
-            acc += (j < MK ? c0 : c71) - fr[0] * spw[j][0];
-            res = (u16)gf_canon(acc);
-        } else {                                             // non-canonical first term: the reference's u16 chain, verbatim
-            u16 acc = f[j < MK ? 0 : MK + 1];
-            for (int kk = 1; kk < F; kk++) acc = ref_add(acc, (u16)(((uint32_t)gf_canon(spw[j][kk]) * f[kk]) % (uint32_t)Q));
-            res = acc;
+            const int32_t cc = j < MK ? c0 : c71;
+            put(j, (u16)gf_canon(acc0 + cc - fr[0] * spw[j][0]));
+            put(j + 1, (u16)gf_canon(acc1 + cc - fr[0] * spw[j + 1][0]));
+        } else {                                                 // non-canonical first term: the reference's u16 chain, verbatim
+            for (int jj = j; jj < j + 2; jj++) {
+                u16 acc = f[jj < MK ? 0 : MK + 1];
+                for (int kk = 1; kk < F; kk++) acc = ref_add(acc, (u16)(((uint32_t)gf_canon(spw[jj][kk]) * f[kk]) % (uint32_t)Q));
+                put(jj, acc);
+            }
         }
-        if (j < MK) out[half * MK + j] = res; else out[2 * MK + half * 2 * K + (j - MK)] = res;
     }
 }
 

@@ -585,15 +585,17 @@ def test_kem_arbitrary_bytes_match_live_reference(ctxs, k):
 
 @pytest.mark.parametrize("k", [2, 3, 4])
 def test_dense_table_share_eval_matches_ntt_convolution(k):
-    """The share evaluation runs as a blocked NTT convolution (share_ntt.cuh) by default and as the dense 1303 x 407 table GEMM
-    (gf_gemm.cuh) with KOSK_B200_SHARE_NTT=0: same shares, same proofs, same verify results, and both equal the oracle."""
+    """The share evaluation runs as a blocked NTT convolution by default (share_ntt.cuh: k_share_ntt2, unequal blocks + IDP.2A + radix-2 DFT
+    networks; KOSK_B200_SHARE_NTT=1 selects the generic equal-block kernel) and as the dense 1303 x 407 table GEMM (gf_gemm.cuh) with
+    KOSK_B200_SHARE_NTT=0: same shares, same proofs, same verify results, and all equal the oracle."""
     from mpcith_kyber_kosk_b200 import KoskContext
     rng = np.random.default_rng(90 + k)
     y = rng.integers(0, 3329, size=(37, 407), dtype=np.uint16)
     y[0] = 3328; y[1] = 0; y[2, :256] = 5
+    y[3, 0::2] = 3328; y[3, 1::2] = 1; y[4, 0::2] = 1664; y[4, 1::2] = 1665       # sign-alternating extremes for the lazy products of the DFT networks
     seeds = seeds_for_range(4000 + k, 0, 5)
     out = {}
-    for mode in ("1", "0"):
+    for mode in ("2", "1", "0"):
         old = os.environ.get("KOSK_B200_SHARE_NTT")
         os.environ["KOSK_B200_SHARE_NTT"] = mode
         try:
@@ -610,13 +612,14 @@ def test_dense_table_share_eval_matches_ntt_convolution(k):
         rej = ctx.verify_batch(bad, pk)
         out[mode] = (sh, pk.copy(), sk.copy(), pi.copy(), ok, rej)
         ctx.close()
-    for a, b in zip(out["1"], out["0"]):
-        assert (a == b).all()
-    assert out["1"][4].all() and not out["1"][5].any()
-    for i in (0, 1, 2, 36):
-        assert (out["1"][0][i] == O.oracle_share(y[i])).all()
+    for other in ("1", "0"):
+        for a, b in zip(out["2"], out[other]):
+            assert (a == b).all()
+    assert out["2"][4].all() and not out["2"][5].any()
+    for i in (0, 1, 2, 3, 4, 36):
+        assert (out["2"][0][i] == O.oracle_share(y[i])).all()
     opk, osk, opi = O.oracle_prove(k, bytes(seeds[0]))
-    assert (out["1"][3][0] == opi).all() and (out["1"][1][0] == opk).all()
+    assert (out["2"][3][0] == opi).all() and (out["2"][1][0] == opk).all()
 
 
 def test_share_eval_noncanonical_inputs(ctxs):
