@@ -731,7 +731,13 @@ def ncu_traffic(k, B):
     d = json.load(open(path))
     if d.get("kyber_k") != k or d.get("batch") != B:
         return None
-    return {"dram_bytes_per_step": d["dram_bytes_read"] + d["dram_bytes_write"], "unit": "B", "source": d.get("source")}
+    out = {"dram_bytes_per_step": d["dram_bytes_read"] + d["dram_bytes_write"], "unit": "B", "source": d.get("source")}
+    # what else the same capture says about the main launch: the pipe ncu calls fmaheavy, and the L1 / shared-memory data pipe that co-bounds the kernel
+    for key in ("fmaheavy_pct_main_launch", "l1_data_pipe_pct_main_launch", "issue_active_pct_main_launch", "alu_pct_main_launch", "shared_wavefronts_per_sharing",
+                "warp_instructions_per_sharing"):
+        if key in d:
+            out["ncu_" + key] = d[key]
+    return out
 
 
 if __name__ == "__main__":
