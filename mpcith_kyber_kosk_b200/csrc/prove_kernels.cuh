@@ -861,15 +861,33 @@ __global__ void __launch_bounds__(256) k_assemble(ProveBufs pb)
         for (int i = tid; i < NT; i += 256) sI[i] = I[i];
         // ---- compact: O[l][r] = plane(l)[I[r]] ----
         const u16 *planes = pb.SH + (size_t)b * sl.nslot * SLD;
+        // the rows of group g + 1 are loaded into registers while group g is picked: with load -> barrier -> pick -> barrier in sequence every
+        // group exposed a DRAM round trip (ncu: 49 % of the stall samples on long_scoreboard, 10 % on the barriers)
+        constexpr int NLD = (ASM_RB * (SLD / 8) + 255) / 256;
+        uint4 pre[NLD];
+        auto issue = [&](int base) {
+            const int nrow = min(ASM_RB, npl - base);
+#pragma unroll
+            for (int u = 0; u < NLD; u++) {
+                const int idx = tid + 256 * u;
+                if (idx < nrow * (SLD / 8)) {
+                    const int r = idx / (SLD / 8), c = idx % (SLD / 8), l = base + r;
+                    const int slot = grp == 0 ? sl.f0 + l : grp == 1 ? sl.Tf0 + l : AP::slot(sl, l);
+                    pre[u] = __ldcs(reinterpret_cast<const uint4 *>(planes + (size_t)slot * SLD) + c);
+                }
+            }
+        };
+        issue(0);
         for (int base = 0; base < npl; base += ASM_RB) {
             const int nrow = min(ASM_RB, npl - base);
             __syncthreads();                                  // previous rows consumed (and sI visible)
-            for (int idx = tid; idx < nrow * (SLD / 8); idx += 256) {
-                const int r = idx / (SLD / 8), c = idx % (SLD / 8), l = base + r;
-                const int slot = grp == 0 ? sl.f0 + l : grp == 1 ? sl.Tf0 + l : AP::slot(sl, l);
-                reinterpret_cast<uint4 *>(srow[r])[c] = __ldcs(reinterpret_cast<const uint4 *>(planes + (size_t)slot * SLD) + c);
+#pragma unroll
+            for (int u = 0; u < NLD; u++) {
+                const int idx = tid + 256 * u;
+                if (idx < nrow * (SLD / 8)) reinterpret_cast<uint4 *>(srow[idx / (SLD / 8)])[idx % (SLD / 8)] = pre[u];
             }
             __syncthreads();
+            if (base + ASM_RB < npl) issue(base + ASM_RB);
             for (int idx = tid; idx < nrow * NT; idx += 256) {
                 const int r = idx / NT, i = idx % NT;
                 sO[base + r][i] = srow[r][SOFF + sI[i]];
