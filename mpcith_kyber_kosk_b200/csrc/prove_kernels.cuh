@@ -820,7 +820,13 @@ __global__ void __launch_bounds__(128) k_derive(ProveBufs pb)
 //   coalesced 16-byte loads), picks the 150 opened parties of each row through shared memory into a compact [plane][opened] tile and
 //   emits its fields from that tile with coalesced stores.  Three CTAs per proof: the f planes, the NTT_f planes, everything else.
 //   Rest set (1304 parties in ascending order): tiles of 64 consecutive rest parties; their plane reads are near-contiguous.
-constexpr int ASM_OPENED_CTAS = 3, ASM_RB = 4, ASM_OS = 154, ASM_REST_ROWS = 64;
+#ifndef KOSK_ASM_RB
+#define KOSK_ASM_RB 4
+#endif
+#ifndef KOSK_ASM_MINB
+#define KOSK_ASM_MINB 1
+#endif
+constexpr int ASM_OPENED_CTAS = 3, ASM_RB = KOSK_ASM_RB, ASM_OS = 154, ASM_REST_ROWS = 64;
 template <int K> struct AsmPlanes {              // local plane numbering of the "everything else" CTA
     static constexpr int ETA = (K == 2) ? 3 : 2, E = 2 * ETA + 1, M = 2 * ETA;
     static constexpr int S = 0, Ee = K, TSR = 2 * K, TER = 3 * K, ASR = 4 * K, AS = 5 * K, TR = 6 * K, SETA = 8 * K, EETA = SETA + K * E, ZS = EETA + K * E, ZE = ZS + K * M,
@@ -842,7 +848,7 @@ template <int K> struct AsmPlanes {              // local plane numbering of the
 };
 
 template <int K>
-__global__ void __launch_bounds__(256) k_assemble(ProveBufs pb)
+__global__ void __launch_bounds__(256, KOSK_ASM_MINB) k_assemble(ProveBufs pb)
 {
     constexpr int ETA = (K == 2) ? 3 : 2, E = 2 * ETA + 1, M = 2 * ETA, F = MK + 2 * K + 1;
     using AP = AsmPlanes<K>;

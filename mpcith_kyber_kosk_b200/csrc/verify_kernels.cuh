@@ -447,7 +447,10 @@ __global__ void __launch_bounds__(128) kv_check_parties(VerifyBufs vb, const u8 
     if (p >= NP) return;
     const u8 *pi = pis + L.proof_bytes * (size_t)b;
     const u16 *vsh = vb.VSH + (size_t)b * d.nyrows * SLD + SOFF + p;
-    auto V = [&](int row) -> u16 { return vsh[(size_t)row * SLD]; };
+    // every source of this kernel is read-only here: loads through the non-coherent path may be hoisted above the stores of the long opened-party
+    // branch (vr, U2), which otherwise serialise into a chain of some 250 dependent L2 round trips per opened party
+    auto V = [&](int row) -> u16 { return __ldg(vsh + (size_t)row * SLD); };
+    auto pi16 = [](const u8 *q, size_t off, size_t idx) -> u16 { return __ldg(reinterpret_cast<const u16 *>(q + off) + idx); };
     const int pos = vb.POS[(size_t)b * NP + p];
     int f = 0;
     if (pos >= 0) {                                            // rest party, index pos in the proof's [R] arrays
@@ -473,19 +476,19 @@ __global__ void __launch_bounds__(128) kv_check_parties(VerifyBufs vb, const u8 
         u16 *vr = vb.VR + ((size_t)b * NT + o) * d.vrld;
         const u16 *tc = reinterpret_cast<const u16 *>(vb.TCR + ((size_t)b * NP + p) * 32);
         int vo = 0;
-        for (int i = 0; i < 16; i++) vr[vo++] = tc[i];
+        for (int i = 0; i < 16; i++) vr[vo++] = __ldg(tc + i);
         const u16 *cr = vb.CR + ((size_t)b * NT + o) * d.crld;
-        for (int i = 0; i < d.nc; i++) vr[vo++] = cr[i];
-        for (int i = 0; i < K; i++) vr[vo++] = opv[i];                                   // beta[0..K)
-        for (int i = 0; i < K; i++) vr[vo++] = opv[MK + i];                              // gamma[0..K)
+        for (int i = 0; i < d.nc; i++) vr[vo++] = __ldg(cr + i);
+        for (int i = 0; i < K; i++) vr[vo++] = __ldg(opv + i);                                   // beta[0..K)
+        for (int i = 0; i < K; i++) vr[vo++] = __ldg(opv + MK + i);                              // gamma[0..K)
         for (int i = 0; i < K; i++) vr[vo++] = V(i);                                     // regenerated [s+r] share (:249-255)
         for (int i = 0; i < K; i++) vr[vo++] = V(K + i);
         for (int i = 0; i < K; i++) {
             const size_t oi = (size_t)o * K + i;
             const u16 s = pi16(pi, L.o_s, oi), e = pi16(pi, L.o_e, oi);
             const u16 As = pi16(pi, L.o_NTTAs, oi), Ar = pi16(pi, L.o_NTTAr, oi), Te = pi16(pi, L.o_NTTe, oi);
-            if (pi16(pi, L.o_NTTs, oi) != ref_sub(V(d.n1rows + i), opv[2 * MK + 2 * K + i])) f |= VF_NTT;          // :273-284
-            if (Te != ref_sub(V(d.n1rows + K + i), opv[2 * MK + 2 * K + K + i])) f |= VF_NTT;
+            if (pi16(pi, L.o_NTTs, oi) != ref_sub(V(d.n1rows + i), __ldg(opv + 2 * MK + 2 * K + i))) f |= VF_NTT;          // :273-284
+            if (Te != ref_sub(V(d.n1rows + K + i), __ldg(opv + 2 * MK + 2 * K + K + i))) f |= VF_NTT;
             if (V(d.n1rows + 2 * K + i) != ref_add(As, Ar)) f |= VF_ASR;                                           // :304-312
             if (V(2 * K + i) != ref_add(As, Te)) f |= VF_TREL;                                                     // :365-376
             for (int m = 0; m < E; m++) {                                                                         // :447-466
