@@ -523,7 +523,7 @@ static int prove_chunk(kosk_b200_ctx *c, Lane &ln, const ProveBufs &bufs, int B,
     } else {
         k_hash_records<NCOMMIT><<<dim3(ptiles, B), 128, 0, st>>>(hc, pb.TCR, pb.SH, sl.nslot, sl.TC0);
         prof_mark(c, ln, KOSK_PH_FS1);
-        k_fs1<K><<<(B + 3) / 4, 128, 0, st>>>(pb.TCR, pb.PW, B);
+        { int fc, ft; fs_launch_dims(B, fc, ft); k_fs1<K><<<fc, ft, 0, st>>>(pb.TCR, pb.PW, B); }
     }
     prof_mark(c, ln, KOSK_PH_EVAL);
     k_eval<K><<<dim3(B < 16 ? (NP + 127) / 128 : 3, B), 256, 0, st>>>(pb);     // few proofs: one party tile per CTA (latency); many: 4 tiles per CTA amortise the table load
@@ -542,7 +542,7 @@ static int prove_chunk(kosk_b200_ctx *c, Lane &ln, const ProveBufs &bufs, int B,
         k_hash_records<NVIEW><<<dim3(ptiles, B), 128, 0, st>>>(hv, pb.VWR, nullptr, 0, 0);
         if (c->overlap_tail && c->lanes.size() > 1) { CU(cudaEventRecord(ln.pre_tail, st)); tail_gate = ln.pre_tail; }
         prof_mark(c, ln, KOSK_PH_FS2);
-        k_fs2<<<(B + 3) / 4, 128, 0, st>>>(pb.VWR, pb.I, pb.REST, B);
+        { int fc, ft; fs_launch_dims(B, fc, ft); k_fs2<<<fc, ft, 0, st>>>(pb.VWR, pb.I, pb.REST, B); }
     }
     prof_mark(c, ln, KOSK_PH_ASSEMBLE);
     k_assemble<K><<<dim3(ASM_OPENED_CTAS + (NR + ASM_REST_ROWS - 1) / ASM_REST_ROWS, B), 256, 0, st>>>(pb);

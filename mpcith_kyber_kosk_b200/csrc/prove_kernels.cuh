@@ -418,6 +418,13 @@ k_hash_records(const HashSrc hs, u8 *__restrict__ out_rows, u16 *__restrict__ ou
     }
 }
 
+// Sponge kernels: one warp per proof.  With four proofs per CTA a 1024-proof launch is 256 CTAs on 148 SMs: 108 SMs host eight sponge warps and
+// 40 host four, and the launch lasts as long as the crowded ones (shuffle-throughput contention).  One proof per CTA spreads them 7 / 6.
+#ifndef KOSK_FS_WPC
+#define KOSK_FS_WPC 1
+#endif
+static inline void fs_launch_dims(int B, int &ctas, int &threads) { const int wpc = B >= 256 ? KOSK_FS_WPC : 4; ctas = (B + wpc - 1) / wpc; threads = 32 * wpc; }
+
 // FS-1: alpha = BE16(SHAKE256(SHA3-256(Tcomm_0 || ... ) || 0x01)) mod q and the power table (mlwe_prover.cpp:130-153).
 // One warp per proof.
 // __launch_bounds__(128, 4): without a min-blocks hint ptxas squeezes these kernels into 32 registers (full occupancy), interleaves the
@@ -428,7 +435,7 @@ __global__ void __launch_bounds__(128, 4) k_fs1(const u8 *__restrict__ TCR, u16 
 {
     constexpr int F = MK + 2 * K + 1, NA = MK + 2 * K;
     __shared__ u16 salpha[4][80];
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, b = blockIdx.x * 4 + w;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, b = blockIdx.x * (blockDim.x >> 5) + w;      // 1 .. 4 proofs per CTA (fs_launch_dims)
     if (b >= B) return;
     WarpKeccak wk; wk.init();
     uint64_t a = wk.tree_hash(TCR + (size_t)b * TREE_BYTES);
@@ -479,7 +486,7 @@ __global__ void __launch_bounds__(128, 4) k_fs2(const u8 *__restrict__ VWR, u16 
 {
     __shared__ u16 sraw[4][NT + 2];
     __shared__ uint32_t sused[4][(NP + 31) / 32];
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, b = blockIdx.x * 4 + w;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, b = blockIdx.x * (blockDim.x >> 5) + w;      // 1 .. 4 proofs per CTA (fs_launch_dims)
     if (b >= B) return;
     WarpKeccak wk; wk.init();
     uint64_t a = wk.tree_hash(VWR + (size_t)b * TREE_BYTES);
@@ -491,7 +498,7 @@ __global__ void __launch_bounds__(128, 4) k_fs2(const u8 *__restrict__ VWR, u16 
             for (int i = 0; i < 4; i++) { const int j = blk * 68 + 4 * lane + i; if (j < NT) sraw[w][j] = (u16)(lane_be16(a, i) % (uint32_t)NP); }
         if (blk < 2) a = wk.permute(a);
     }
-    fs2_open_set(sraw[w], sused[w], Iout + (size_t)(blockIdx.x * 4 + (threadIdx.x >> 5)) * NT, REST + (size_t)(blockIdx.x * 4 + (threadIdx.x >> 5)) * NR);
+    fs2_open_set(sraw[w], sused[w], Iout + (size_t)b * NT, REST + (size_t)b * NR);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -588,7 +588,7 @@ static int verify_chunk_t(VerifyBufs &vb, const VerifyTables &vt, int B, const u
         HashSrc hs{vb.CR, (long long)NT * d.crld, d.crld, 1, 0, nullptr, vb.I, NT};
         k_hash_records<NC><<<dim3(2, B), 128, 0, st>>>(hs, vb.TCR, nullptr, 0, 0); nl++;
     }
-    k_fs1<K><<<(B + 3) / 4, 128, 0, st>>>(vb.TCR, vb.PW, B); nl++;
+    { int fc, ft; fs_launch_dims(B, fc, ft); k_fs1<K><<<fc, ft, 0, st>>>(vb.TCR, vb.PW, B); nl++; }
     kv_eval_opened<K><<<B, 320, 0, st>>>(vb); nl++;
     // ---- side chain (independent of the challenges) ----
     kv_lagrange<<<B, 256, 0, s2>>>(vb, vt.inv, vt.fact); nl++;
@@ -661,7 +661,7 @@ static int verify_chunk_t(VerifyBufs &vb, const VerifyTables &vt, int B, const u
         HashSrc hs{vb.VR, (long long)NT * d.vrld, d.vrld, 1, 0, nullptr, vb.I, NT};
         k_hash_records<NV><<<dim3(2, B), 128, 0, st>>>(hs, vb.VWR, nullptr, 0, 0); nl++;
     }
-    k_fs2<<<(B + 3) / 4, 128, 0, st>>>(vb.VWR, vb.I2, vb.REST2, B); nl++;
+    { int fc, ft; fs_launch_dims(B, fc, ft); k_fs2<<<fc, ft, 0, st>>>(vb.VWR, vb.I2, vb.REST2, B); nl++; }
     kv_final<K><<<B, 128, 0, st>>>(vb, d_ok); nl++;
     return cudaGetLastError() == cudaSuccess ? nl : -1;
 }

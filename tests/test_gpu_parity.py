@@ -36,6 +36,23 @@ def test_share_eval_sweep(ctxs, rows):
     assert (got[:, :151] == y[:, 256:]).all()
 
 
+def test_share_eval_work_tickets_across_launch_sizes(ctxs):
+    """k_share_ntt2 draws its rows from a per-stream device counter that is never reset (share_ntt.cuh, SnTicket): launches of very different
+    sizes back to back on one context, below, at and above the number of resident warps (148 SMs x 4 CTAs x 7 warps = 4144), must each
+    produce every row."""
+    ctx = ctxs(2)
+    rng = np.random.default_rng(77)
+    for rows in (5000, 3, 4144, 4145, 1, 9000, 4143):
+        y = rng.integers(0, 3329, size=(rows, 407), dtype=np.uint16)
+        got = ctx.share_eval(y)
+        assert (got[:, :151] == y[:, 256:]).all()
+        for i in sorted(set([0, rows - 1, rows // 2, rows // 3])):
+            assert (got[i] == O.oracle_share(y[i])).all(), (rows, i)
+        # every row was written: a row skipped by the scheduler would keep the previous launch's shares
+        z = ctx.share_eval(np.zeros((rows, 407), np.uint16))
+        assert not z.any()
+
+
 def test_share_eval_linearity_full_size(ctxs):
     """Size-independent property at a batch the oracle could not finish quickly: S is linear over GF(3329)."""
     rng = np.random.default_rng(5)

@@ -104,3 +104,32 @@ def test_unequal_blocks_and_limb_split_equal_the_share_table():
             x = BO * o + t
             if x < NX:
                 assert blk[t] * P[x] % Q == want[151 + x], (o, t)
+
+
+def test_dft_network_masks_keep_every_intermediate_below_2_31():
+    """The lazy / Shoup assignment hard-coded in share_ntt.cuh (SN_FFT_SMALL, SN_FFT_BIG) against the interval model of tools/exp/fft16_plan.py,
+    for every place the kernels use it and the largest inputs that can reach it."""
+    import importlib.util
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("fft16_plan", os.path.join(root, "tools", "exp", "fft16_plan.py"))
+    plan = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(plan)
+    src = open(os.path.join(root, "mpcith_kyber_kosk_b200", "csrc", "share_ntt.cuh")).read()
+    m = re.search(r"SN_FFT_SMALL = (0x[0-9a-f]+)u, SN_FFT_BIG = (0x[0-9a-f]+)u", src)
+    small, big = int(m.group(1), 16), int(m.group(2), 16)
+    every = set(range(16))
+    cases = [
+        ("forward stage 1, factor applied (Shoup output)", set(range(8)), 1.25 * Q, range(16), small),
+        ("forward stage 1, raw u16 rows of the verifier's products", set(range(8)), 65535, range(16), small),
+        ("forward stage 2 / inverse stage 2 (twiddle Shoup output)", every, 1.25 * Q, range(16), small),
+        ("inverse stage 1, k_share_ntt2 (4 blocks)", every, 4 * 6700 * 1664, range(16), big),
+        ("inverse stage 1, k_conv_ntt<8, 2> (8 blocks)", every, 8 * 6700 * 1664, range(16), big),
+    ]
+    for name, nz, bound, outs, mask in cases:
+        slots, ok, mx = plan.plan(nz, bound, outs, plan.LIM, mask)
+        assert ok and mx < 2 ** 31, name
+    # the cheapest valid assignment for reduced inputs costs 32 issue slots, and the hard-coded one is such an assignment
+    assert plan.plan(every, 1.25 * Q, range(16), plan.LIM, small)[0] == 32
+    assert plan.plan(every, 4 * 6700 * 1664, range(16), plan.LIM, big)[0] == 68
