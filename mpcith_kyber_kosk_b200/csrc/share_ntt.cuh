@@ -277,6 +277,7 @@ static inline int conv_ntt_launch(const ConvArgs &g0, cudaStream_t st, SnTicket 
     g.ctr = nullptr; g.ctr_base = 0;
     if (tk && tk->ctr && ctas > 0) { g.ctr = tk->ctr; g.ctr_base = tk->base; tk->base += (unsigned)g.mtotal; }
     if (ctas > 0) k_conv_ntt<NIN, NOUT, NINV, NOUTV, PRE, PGROUP><<<ctas, 32 * SN_WARPS, 0, st>>>(g);
+    if (g.ctr && cudaPeekAtLastError() != cudaSuccess) tk->base -= (unsigned)g.mtotal;      // the launch never ran: no ticket was drawn
     return 1;
 }
 
@@ -428,6 +429,7 @@ static inline int share_ntt2_launch(const ConvArgs &g0, cudaStream_t st, SnTicke
     g.ctr = nullptr; g.ctr_base = 0;
     if (tk && tk->ctr && ctas > 0) { g.ctr = tk->ctr; g.ctr_base = tk->base; tk->base += (unsigned)g.mtotal; }
     if (ctas > 0) k_share_ntt2<D1, NX><<<ctas, 32 * S2_WARPS, 0, st>>>(g);
+    if (g.ctr && cudaPeekAtLastError() != cudaSuccess) tk->base -= (unsigned)g.mtotal;      // the launch never ran: no ticket was drawn
     return 1;
 }
 
