@@ -35,7 +35,8 @@ SHARE_MACS_PER_ROW = 1303 * 407          # ss.cpp:23-32: one sharing = 1303 x 40
 # IMAD.HI / IMAD.WIDE issue at half the IMAD rate (kosk_b200_int_peak: 8.8 T vs 18.5 T thread-ops/s) and count twice; IDP.2A is full rate
 # (tools/exp/idp_bench.cu); x 32 lanes.
 #   variant 2 (default, k_share_ntt2: 126 x 131 blocks, IDP.2A pointwise stage, radix-2 DFT networks): a forward pass has 135 IMAD + 50 IMAD.HI
-#     + 2 IMAD.WIDE, an inverse pass 113 IMAD + 64 IDP.2A + 47 IMAD.HI; 2 forward + 5 inverse passes
+#     + 2 IMAD.WIDE, an inverse pass 113 IMAD + 64 IDP.2A + 47 IMAD.HI per output block pair (the two-pair iterations: 225 + 128 + 94); 2 forward
+#     passes + 5 block pairs
 #   variant 1 (k_conv_ntt<4,11>, KOSK_B200_SHARE_NTT=1): forward 182 IMAD + 40 IMAD.HI, inverse 290 IMAD + 40 IMAD.HI; 2 + 6 passes
 NTT_SLOTS_PER_SHARING = {2: (2 * (135 + 2 * 50 + 2 * 2) + 5 * (113 + 64 + 2 * 47)) * 32, 1: (2 * (182 + 2 * 40) + 6 * (290 + 2 * 40)) * 32}
 NTT_VARIANT = int(os.environ.get("KOSK_B200_SHARE_NTT", "2") or 2)

@@ -301,6 +301,9 @@ constexpr int S2_BI = 126, S2_BO = 131, S2_NIN = 4, S2_NOUT = 10;
 #ifndef KOSK_S2_MINB
 #define KOSK_S2_MINB 4
 #endif
+#ifndef KOSK_S2_DUAL
+#define KOSK_S2_DUAL 1     // two output blocks per half-warp and inverse iteration (0.92 -> 0.89 ms per 1024 proofs)
+#endif
 constexpr int S2_WARPS = KOSK_S2_WARPS;
 static_assert(S2_BI + S2_BO - 1 == 256 && S2_NIN * S2_BI >= D1 && S2_NOUT * S2_BO >= NX && S2_NIN == 4 && S2_NOUT % 2 == 0, "share_ntt2 blocking");
 __host__ __device__ constexpr int s2_word(int k1, int k2) { return k1 * 16 + ((((k2 >> 2) ^ (k1 >> 1)) & 3) << 2) + (k2 & 3); }   // word of bin (k1, k2) in a swizzled [16][16] tile
@@ -372,10 +375,83 @@ __global__ void __launch_bounds__(32 * S2_WARPS, KOSK_S2_MINB) k_share_ntt2(cons
         if (g.tail)
 #pragma unroll
             for (int i = 0; i < (NT + 32) / 32; i++) { const int t = lane + 32 * i; if (t <= NT) dst[t - (NT + 1)] = tl[i]; }
-        // ---- inverse: output blocks two per pass ----
+        // ---- inverse ----
+        // second DFT stage, output factors and stores of block o from the transposed values in T
+        auto stage2_emit = [&](int o) {
+            int32_t in[16], out[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) in[k] = T[c * SN_TS + k];
+            sn_dft16<true, SN_FFT_SMALL>(in, out);                          // only out[0..8] are used: the rest of the last level is dead code
+            const int xb = S2_BO * o + c;                                   // first output of this lane; row a adds 16 a
+            const int2 *postp = g.post + xb;
+            u16 *dstp = dst + xb;
+            // rows a < na are valid: row 8 only holds x' = 128..130, and the last block ends at NOUTV
+            const int na = min(c < S2_BO - 128 ? 9 : 8, (NOUTV - xb + 15) >> 4);
+#pragma unroll
+            for (int a = 0; a < 9; a++)
+                if (a < na) {
+                    const int2 pf = __ldg(postp + 16 * a);
+                    uint32_t r = (uint32_t)sn_shoup(out[a], pf.x, pf.y);    // in (-q/4, 5q/4): canonical with two unsigned minima, no predicates
+                    r = min(r, r + Q);
+                    r = min(r, r - Q);
+                    dstp[16 * a] = (u16)r;
+                }
+        };
+#if KOSK_S2_DUAL
+        // Two output blocks per half-warp and iteration (blocks o and o + 2) share the loads of the input spectra and of the twiddle pairs: the kernel
+        // is bound by the L1 / shared-memory data pipe (ncu: 92 %), and those two are 64 of the 128 shared-memory wavefronts of a single-block pass.
 #pragma unroll 1
-        for (int it = 0; it < S2_NOUT / 2; it++) {
-            const int o = 2 * it + hw;
+        for (int it = 0; it < S2_NOUT / 4; it++) {
+            const int oa = 4 * it + hw, ob = oa + 2;
+            int32_t Oa[16], Ob[16];
+            {
+                const uint4 *pu = reinterpret_cast<const uint4 *>(up + c * 16);
+                const uint4 *pka = reinterpret_cast<const uint4 *>(s_kp + oa * 512 + c * 16), *pkb = reinterpret_cast<const uint4 *>(s_kp + ob * 512 + c * 16);
+#pragma unroll
+                for (int ch = 0; ch < 4; ch++) {
+                    const uint4 u0 = pu[ch ^ sw], u1 = pu[64 + (ch ^ sw)];
+                    const uint32_t uw0[4] = {u0.x, u0.y, u0.z, u0.w}, uw1[4] = {u1.x, u1.y, u1.z, u1.w};
+                    {
+                        const uint4 k0 = pka[ch ^ sw], k1 = pka[64 + (ch ^ sw)];
+                        const uint32_t kw0[4] = {k0.x, k0.y, k0.z, k0.w}, kw1[4] = {k1.x, k1.y, k1.z, k1.w};
+#pragma unroll
+                        for (int e = 0; e < 4; e++)
+                            Oa[4 * ch + e] = __dp2a_hi((int)uw1[e], (int)kw1[e], __dp2a_hi((int)uw0[e], (int)kw0[e], 0)) * 64 + __dp2a_lo((int)uw1[e], (int)kw1[e], __dp2a_lo((int)uw0[e], (int)kw0[e], 0));
+                    }
+                    {
+                        const uint4 k0 = pkb[ch ^ sw], k1 = pkb[64 + (ch ^ sw)];
+                        const uint32_t kw0[4] = {k0.x, k0.y, k0.z, k0.w}, kw1[4] = {k1.x, k1.y, k1.z, k1.w};
+#pragma unroll
+                        for (int e = 0; e < 4; e++)
+                            Ob[4 * ch + e] = __dp2a_hi((int)uw1[e], (int)kw1[e], __dp2a_hi((int)uw0[e], (int)kw0[e], 0)) * 64 + __dp2a_lo((int)uw1[e], (int)kw1[e], __dp2a_lo((int)uw0[e], (int)kw0[e], 0));
+                    }
+                }
+            }
+            int32_t va[16], vb[16];
+            sn_dft16<true, SN_FFT_BIG>(Oa, va);
+            sn_dft16<true, SN_FFT_BIG>(Ob, vb);
+#pragma unroll
+            for (int b = 0; b < 16; b++) {
+                const int2 t = s_tw[256 + b * 16 + c];
+                T[b * SN_TS + c] = (int16_t)sn_shoup(va[b], t.x, t.y);
+                vb[b] = sn_shoup(vb[b], t.x, t.y);                          // waits in registers for the transposition buffer
+            }
+            __syncwarp();
+            stage2_emit(oa);
+            __syncwarp();
+#pragma unroll
+            for (int b = 0; b < 16; b++) T[b * SN_TS + c] = (int16_t)vb[b];
+            __syncwarp();
+            stage2_emit(ob);
+            __syncwarp();
+        }
+        constexpr int O_SINGLE = 4 * (S2_NOUT / 4);
+#else
+        constexpr int O_SINGLE = 0;
+#endif
+        // one output block per half-warp and pass
+#pragma unroll 1
+        for (int o = O_SINGLE + hw; o < S2_NOUT; o += 2) {
             int32_t O[16];
             {
                 const uint4 *pu = reinterpret_cast<const uint4 *>(up + c * 16);
@@ -397,26 +473,7 @@ __global__ void __launch_bounds__(32 * S2_WARPS, KOSK_S2_MINB) k_share_ntt2(cons
 #pragma unroll
             for (int b = 0; b < 16; b++) { const int2 t = s_tw[256 + b * 16 + c]; T[b * SN_TS + c] = (int16_t)sn_shoup(v[b], t.x, t.y); }
             __syncwarp();
-            int32_t in[16], out[16];
-#pragma unroll
-            for (int k = 0; k < 16; k++) in[k] = T[c * SN_TS + k];
-            sn_dft16<true, SN_FFT_SMALL>(in, out);                          // only out[0..8] are used: the rest of the last level is dead code
-            const int xb = S2_BO * o + c;                                   // first output of this lane; row a adds 16 a
-            const int2 *postp = g.post + xb;
-            u16 *dstp = dst + xb;
-            // rows a < na are valid: row 8 only holds x' = 128..130, and the last block ends at NOUTV
-            const int na = min(c < S2_BO - 128 ? 9 : 8, (NOUTV - xb + 15) >> 4);
-            auto emit = [&](int a, int32_t acc) {
-                if (a < na) {
-                    const int2 pf = __ldg(postp + 16 * a);
-                    uint32_t r = (uint32_t)sn_shoup(acc, pf.x, pf.y);       // in (-q/4, 5q/4): canonical with two unsigned minima, no predicates
-                    r = min(r, r + Q);
-                    r = min(r, r - Q);
-                    dstp[16 * a] = (u16)r;
-                }
-            };
-#pragma unroll
-            for (int a = 0; a < 9; a++) emit(a, out[a]);
+            stage2_emit(o);
             __syncwarp();
         }
         m = mn;
