@@ -831,7 +831,7 @@ __global__ void __launch_bounds__(128) k_derive(ProveBufs pb)
 #define KOSK_ASM_RB 4
 #endif
 #ifndef KOSK_ASM_MINB
-#define KOSK_ASM_MINB 1
+#define KOSK_ASM_MINB 5     // five CTAs per SM (48 registers): 0.40 -> 0.38 ms; six (40 registers) lose the register prefetch (0.55 ms)
 #endif
 constexpr int ASM_OPENED_CTAS = 3, ASM_RB = KOSK_ASM_RB, ASM_OS = 154, ASM_REST_ROWS = 64;
 template <int K> struct AsmPlanes {              // local plane numbering of the "everything else" CTA
