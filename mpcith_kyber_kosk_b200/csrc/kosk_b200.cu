@@ -833,6 +833,9 @@ static int verify_batch_impl(kosk_b200_ctx *c, size_t n, const uint8_t *in, cons
         // first, so it is on the link while the workers pack)
         int np = !wire ? 0 : packed ? B : (int)((size_t)B * c->wire_mode / 100);
         if (wire) { rc = wire_ensure(c, !packed); if (rc) break; }
+        // the public keys first: a small H2D queued behind the device unpack kernel would hold the copy engine's queue (and the next call's big copy
+        // behind it) until that kernel gets SMs next to the other lane's verify kernels (packed end to end: 12.1 ms per 1024 proofs for a 9.6 ms copy)
+        CU(cudaMemcpyAsync(ln.d_pk, pk + L.pk_bytes * o, L.pk_bytes * (size_t)B, cudaMemcpyHostToDevice, ln.st));
         if (!packed && np < B)
             CU(cudaMemcpyAsync(ln.d_pi + L.proof_bytes * (size_t)np, in + L.proof_bytes * (o + np), L.proof_bytes * (size_t)(B - np), cudaMemcpyHostToDevice, ln.st));
         if (np > 0 && !packed) {
@@ -848,7 +851,6 @@ static int verify_batch_impl(kosk_b200_ctx *c, size_t n, const uint8_t *in, cons
             if (!packed) { CU(cudaEventRecord(ln.h2d_done, ln.st)); ln.h2d_pending = true; }
             c->launches += wire_launch(false, ln.d_wire, ln.d_pi, c->k, np, ln.st);
         }
-        CU(cudaMemcpyAsync(ln.d_pk, pk + L.pk_bytes * o, L.pk_bytes * (size_t)B, cudaMemcpyHostToDevice, ln.st));
         rc = verify_chunk_lane(c, ln, B, ln.d_pi, ln.d_pk, ln.d_ok);
         if (rc) break;
         CU(cudaMemcpyAsync(ok + o, ln.d_ok, (size_t)B, cudaMemcpyDeviceToHost, ln.st));
