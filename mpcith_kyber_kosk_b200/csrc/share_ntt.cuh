@@ -314,13 +314,22 @@ __global__ void __launch_bounds__(32 * S2_WARPS, KOSK_S2_MINB) k_share_ntt2(cons
     __shared__ __align__(16) uint32_t s_kp[S2_NOUT * 2 * 256];             // [o][pair][k1][k2 swizzled]: bytes (k0, k0', k1, k1') of segments (o, 2 pair), (o, 2 pair + 1)
     __shared__ __align__(8) int2 s_tw[2 * 256];
     __shared__ __align__(16) uint32_t s_up[S2_WARPS][2 * 256];             // [pair][k1][k2 swizzled]: spectra of input blocks 2 pair (low half) and 2 pair + 1
-    __shared__ int16_t s_t[S2_WARPS][2][288];
+    __shared__ __align__(4) int16_t s_t[S2_WARPS][2][288];
     for (int i = threadIdx.x; i < S2_NOUT * 2 * 256; i += blockDim.x) s_kp[i] = g.kpk[i];
     for (int i = threadIdx.x; i < 512; i += blockDim.x) s_tw[i] = g.tw[i];
     __syncthreads();
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, hw = lane >> 4, c = lane & 15;
     uint32_t *up = s_up[wid];
     int16_t *T = s_t[wid][hw];
+    // the buffer is 4-byte aligned and a row starts at 36 c bytes, so the 16 halfword loads of a row pair up into 8 LDS.32
+    auto t_store = [&](const int32_t (&v)[16]) {
+#pragma unroll
+        for (int j = 0; j < 16; j++) T[j * SN_TS + c] = (int16_t)v[j];
+    };
+    auto t_load = [&](int32_t (&in)[16]) {
+#pragma unroll
+        for (int b2 = 0; b2 < 16; b2++) in[b2] = T[c * SN_TS + b2];
+    };
     const int sw = (c >> 1) & 3;                                            // chunk ch of row c lives at chunk ch ^ sw
     // Rows are handed out dynamically (one ticket per row): with a static stride the warps of the single wave drifted apart and the SMs
     // idled 18 % of the warp slots at the tail (ncu: 23.1 of 28 warps active on average).
@@ -361,11 +370,11 @@ __global__ void __launch_bounds__(32 * S2_WARPS, KOSK_S2_MINB) k_share_ntt2(cons
             int32_t y[16];
             sn_dft16<false, SN_FFT_SMALL>(x, y);                           // rows 8..15 of the block are zero padding: x[8..15] = 0 folds away
 #pragma unroll
-            for (int k = 0; k < 16; k++) { const int2 t = s_tw[k * 16 + c]; T[k * SN_TS + c] = (int16_t)sn_shoup(y[k], t.x, t.y); }
+            for (int k = 0; k < 16; k++) { const int2 t = s_tw[k * 16 + c]; y[k] = sn_shoup(y[k], t.x, t.y); }
+            t_store(y);
             __syncwarp();
             int32_t in[16], X[16];
-#pragma unroll
-            for (int b = 0; b < 16; b++) in[b] = T[c * SN_TS + b];
+            t_load(in);
             sn_dft16<false, SN_FFT_SMALL>(in, X);
             int16_t *urow = reinterpret_cast<int16_t *>(up + it * 256 + c * 16) + hw;
 #pragma unroll
@@ -379,8 +388,7 @@ __global__ void __launch_bounds__(32 * S2_WARPS, KOSK_S2_MINB) k_share_ntt2(cons
         // second DFT stage, output factors and stores of block o from the transposed values in T
         auto stage2_emit = [&](int o) {
             int32_t in[16], out[16];
-#pragma unroll
-            for (int k = 0; k < 16; k++) in[k] = T[c * SN_TS + k];
+            t_load(in);
             sn_dft16<true, SN_FFT_SMALL>(in, out);                          // only out[0..8] are used: the rest of the last level is dead code
             const int xb = S2_BO * o + c;                                   // first output of this lane; row a adds 16 a
             const int2 *postp = g.post + xb;
@@ -433,14 +441,14 @@ __global__ void __launch_bounds__(32 * S2_WARPS, KOSK_S2_MINB) k_share_ntt2(cons
 #pragma unroll
             for (int b = 0; b < 16; b++) {
                 const int2 t = s_tw[256 + b * 16 + c];
-                T[b * SN_TS + c] = (int16_t)sn_shoup(va[b], t.x, t.y);
+                va[b] = sn_shoup(va[b], t.x, t.y);
                 vb[b] = sn_shoup(vb[b], t.x, t.y);                          // waits in registers for the transposition buffer
             }
+            t_store(va);
             __syncwarp();
             stage2_emit(oa);
             __syncwarp();
-#pragma unroll
-            for (int b = 0; b < 16; b++) T[b * SN_TS + c] = (int16_t)vb[b];
+            t_store(vb);
             __syncwarp();
             stage2_emit(ob);
             __syncwarp();
@@ -471,7 +479,8 @@ __global__ void __launch_bounds__(32 * S2_WARPS, KOSK_S2_MINB) k_share_ntt2(cons
             int32_t v[16];
             sn_dft16<true, SN_FFT_BIG>(O, v);
 #pragma unroll
-            for (int b = 0; b < 16; b++) { const int2 t = s_tw[256 + b * 16 + c]; T[b * SN_TS + c] = (int16_t)sn_shoup(v[b], t.x, t.y); }
+            for (int b = 0; b < 16; b++) { const int2 t = s_tw[256 + b * 16 + c]; v[b] = sn_shoup(v[b], t.x, t.y); }
+            t_store(v);
             __syncwarp();
             stage2_emit(o);
             __syncwarp();
