@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(32 * SN_WARPS, (NIN <= 5 ? KOSK_SN_MINB : KOSK
     __shared__ __align__(8) int2 s_tw[2 * 256];
     __shared__ __align__(16) int16_t s_uh[SN_WARPS][NINP][16 * SN_LD];
     // transpose buffers, one per half-warp (SN_TS)
-    __shared__ int16_t s_t[SN_WARPS][2][288];
+    __shared__ __align__(4) int16_t s_t[SN_WARPS][2][288];      // 4-byte aligned: the halfword loads of a row (36 c bytes in) pair up into LDS.32
     for (int i = threadIdx.x; i < NK * 16 * SN_LD; i += blockDim.x) s_kh[i] = g.khat[i];
     for (int i = threadIdx.x; i < 512; i += blockDim.x) s_tw[i] = g.tw[i];
     __syncthreads();
