@@ -36,8 +36,8 @@ SHARE_MACS_PER_ROW = 1303 * 407          # ss.cpp:23-32: one sharing = 1303 x 40
 # (tools/exp/idp_bench.cu); x 32 lanes.
 #   variant 2 (default, k_share_ntt2: 126 x 131 blocks, IDP.2A pointwise stage, radix-2 DFT networks): a forward pass has 138 IMAD + 50 IMAD.HI
 #     + 2 IMAD.WIDE, an inverse iteration over two block pairs 236 IMAD + 128 IDP.2A + 94 IMAD.HI; 2 forward passes + 5 block pairs (2.5 iterations)
-#   variant 1 (k_conv_ntt<4,11>, KOSK_B200_SHARE_NTT=1): forward 182 IMAD + 40 IMAD.HI, inverse 290 IMAD + 40 IMAD.HI; 2 + 6 passes
-NTT_SLOTS_PER_SHARING = {2: (2 * (138 + 2 * 50 + 2 * 2) + 5 * (236 + 128 + 2 * 94) // 2) * 32, 1: (2 * (182 + 2 * 40) + 6 * (290 + 2 * 40)) * 32}
+#   variant 1 (k_conv_ntt<4,11>, KOSK_B200_SHARE_NTT=1, equal 128-wide blocks): forward 155 IMAD + 50 IMAD.HI + 2 IMAD.WIDE, inverse 196 IMAD + 46 IMAD.HI; 2 + 6 passes
+NTT_SLOTS_PER_SHARING = {2: (2 * (138 + 2 * 50 + 2 * 2) + 5 * (236 + 128 + 2 * 94) // 2) * 32, 1: (2 * (155 + 2 * 50 + 2 * 2) + 6 * (196 + 2 * 46)) * 32}
 NTT_VARIANT = int(os.environ.get("KOSK_B200_SHARE_NTT", "2") or 2)
 NTT_IMAD_PER_SHARING = NTT_SLOTS_PER_SHARING[2 if NTT_VARIANT >= 2 else 1]
 INT_OPS_PER_KECCAK = 7440                # 24 rounds x 155 64-bit logic ops x 2 (32-bit lanes): algorithmic
