@@ -3,6 +3,8 @@
 //   V1 V0 with iota taken off the critical path (rc folded into the theta inputs of the next round)
 //   V2 theta in one exchange stage: every lane fetches the ten words of its two neighbour columns (20 | 6 shuffles)
 //   V3 V1 + V2
+//   V4 column parity with three dependent shuffles (a ^ a[y+1], then ^ the same two rows further, then ^ a[y+4]): 6 | 4 | 6 shuffles in five stages
+//   V5 column parity with two stages (p = a ^ a[y+1]; c = p ^ a[y+2] ^ p[y+3]): 6 | 4 | 6 shuffles in four stages
 // Measures ns per permutation for a chain of dependent permutations, with 1 warp per SM and with ~7 warps per SM (the 1024-proof load).
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o sponge_round_bench sponge_round_bench.cu
 #include <cstdint>
@@ -50,11 +52,17 @@ struct WK {
     __device__ __forceinline__ uint64_t permute(uint64_t a) const
     {
         const bool lane0 = (threadIdx.x & 31) == 0;
-        if (V == 0 || V == 2) {
+        if (V == 0 || V == 2 || V == 4 || V == 5) {
 #pragma unroll UNROLL
             for (int r = 0; r < 24; r++) {
                 if (V == 0) {
                     const uint64_t c = a ^ shfl(a, l5) ^ shfl(a, l10) ^ shfl(a, l15) ^ shfl(a, l20);
+                    a ^= shfl(c, lm1) ^ rol64(shfl(c, lp1), 1);
+                } else if (V == 4) {
+                    const uint64_t s1 = a ^ shfl(a, l5), s2 = s1 ^ shfl(s1, l10), c = s2 ^ shfl(a, l20);
+                    a ^= shfl(c, lm1) ^ rol64(shfl(c, lp1), 1);
+                } else if (V == 5) {
+                    const uint64_t p = a ^ shfl(a, l5), q = shfl(a, l10), c = p ^ q ^ shfl(p, l15);
                     a ^= shfl(c, lm1) ^ rol64(shfl(c, lp1), 1);
                 } else {
                     const uint64_t m = shfl(a, cm[0]) ^ shfl(a, cm[1]) ^ shfl(a, cm[2]) ^ shfl(a, cm[3]) ^ shfl(a, cm[4]);
@@ -125,9 +133,12 @@ int main()
     const int perms = 344;
     {   std::vector<uint64_t> ref;
         run<0, 1>(d, 148, 32, perms, ref, "1 warp/SM"); run<0, 2>(d, 148, 32, perms, ref, "1 warp/SM"); run<0, 3>(d, 148, 32, perms, ref, "1 warp/SM"); run<0, 4>(d, 148, 32, perms, ref, "1 warp/SM");
-        run<0, 6>(d, 148, 32, perms, ref, "1 warp/SM"); run<0, 8>(d, 148, 32, perms, ref, "1 warp/SM"); run<0, 24>(d, 148, 32, perms, ref, "1 warp/SM"); run<1, 4>(d, 148, 32, perms, ref, "1 warp/SM"); run<1, 24>(d, 148, 32, perms, ref, "1 warp/SM"); }
+        run<0, 6>(d, 148, 32, perms, ref, "1 warp/SM"); run<0, 8>(d, 148, 32, perms, ref, "1 warp/SM"); run<0, 24>(d, 148, 32, perms, ref, "1 warp/SM"); run<1, 4>(d, 148, 32, perms, ref, "1 warp/SM"); run<1, 24>(d, 148, 32, perms, ref, "1 warp/SM"); run<4, 24>(d, 148, 32, perms, ref, "1 warp/SM"); run<5, 24>(d, 148, 32, perms, ref, "1 warp/SM"); }
     {   std::vector<uint64_t> ref;
         run<0, 1>(d, 256, 128, perms, ref, "1024 warps"); run<0, 2>(d, 256, 128, perms, ref, "1024 warps"); run<0, 3>(d, 256, 128, perms, ref, "1024 warps"); run<0, 4>(d, 256, 128, perms, ref, "1024 warps");
-        run<0, 6>(d, 256, 128, perms, ref, "1024 warps"); run<0, 8>(d, 256, 128, perms, ref, "1024 warps"); run<0, 24>(d, 256, 128, perms, ref, "1024 warps"); run<1, 4>(d, 256, 128, perms, ref, "1024 warps"); run<1, 24>(d, 256, 128, perms, ref, "1024 warps"); }
+        run<0, 6>(d, 256, 128, perms, ref, "1024 warps"); run<0, 8>(d, 256, 128, perms, ref, "1024 warps"); run<0, 24>(d, 256, 128, perms, ref, "1024 warps"); run<1, 4>(d, 256, 128, perms, ref, "1024 warps"); run<1, 24>(d, 256, 128, perms, ref, "1024 warps"); run<4, 24>(d, 256, 128, perms, ref, "1024 warps"); run<5, 24>(d, 256, 128, perms, ref, "1024 warps"); }
+    {   std::vector<uint64_t> ref;      // one warp per CTA, as the product launches batches of 256 proofs and more
+        run<0, 24>(d, 1024, 32, perms, ref, "1024 CTAs x 1 warp"); run<4, 24>(d, 1024, 32, perms, ref, "1024 CTAs x 1 warp"); run<5, 24>(d, 1024, 32, perms, ref, "1024 CTAs x 1 warp");
+        run<0, 24>(d, 2048, 32, perms, ref, "2048 CTAs x 1 warp"); run<5, 24>(d, 2048, 32, perms, ref, "2048 CTAs x 1 warp"); run<0, 24>(d, 4096, 32, perms, ref, "4096 CTAs x 1 warp"); run<5, 24>(d, 4096, 32, perms, ref, "4096 CTAs x 1 warp"); }
     return 0;
 }
