@@ -90,7 +90,9 @@ __global__ void __maxnreg__(NREG) k_gf_gemm(const GemmArgs g)
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             if (a_thr) {
-                const int32_t a0 = (int32_t)(wa[i] & 0xFFFF), a1 = (int32_t)(wa[i] >> 16);
+                int32_t a0 = (int32_t)(wa[i] & 0xFFFF), a1 = (int32_t)(wa[i] >> 16);
+                if (a0 >= Q) a0 %= Q;                       // rows need not be canonical (any u16 acts as its residue, utils/gf3329.c:282-284)
+                if (a1 >= Q) a1 %= Q;
                 As[buf][lha * 8 + 2 * i][lra] = a0 > Q / 2 ? a0 - Q : a0;
                 As[buf][lha * 8 + 2 * i + 1][lra] = a1 > Q / 2 ? a1 - Q : a1;
             }
@@ -162,7 +164,7 @@ __global__ void __maxnreg__(NREG) k_gf_gemm(const GemmArgs g)
         if (m >= g.mtotal) continue;
         u16 *dst = Cb + ((size_t)(m / g.rpp) * g.c_slots + g.slot_lo + m % g.rpp) * g.ldc + g.c_off;
         if (g.addvec) {
-            const int32_t cst = gf_center(g.scale_src[((size_t)(m / g.rpp) * g.a_slots + g.slot_lo + m % g.rpp) * g.lda]);
+            const int32_t cst = gf_center(g.scale_src[((size_t)(m / g.rpp) * g.a_slots + g.slot_lo + m % g.rpp) * g.lda] % (uint32_t)Q);
 #pragma unroll
             for (int j = 0; j < TN; j++) acc[i][j] += cst * (int32_t)g.addvec[n0 + col_of(j)];
         }
@@ -205,7 +207,7 @@ __global__ void __launch_bounds__(256) k_gf_gemm_finish(const GemmArgs g, int ns
     if (n < g.nvalid) {
         long long sum = 0;
         for (int z = 0; z < nslices; z++) sum += g.ws[((size_t)z * g.mtotal + m) * g.ws_ld + n];
-        if (g.addvec) sum += (long long)gf_center(g.scale_src[ar * g.lda]) * (long long)g.addvec[n];
+        if (g.addvec) sum += (long long)gf_center(g.scale_src[ar * g.lda] % (uint32_t)Q) * (long long)g.addvec[n];
         long long r = sum % Q; if (r < 0) r += Q;
         uint32_t v = (uint32_t)r;
         if (g.colscale) v = gf_mul(v, g.colscale[(size_t)(g.colscale_by_group ? m / g.rpp : 0) * g.colscale_batch + n]);

@@ -37,6 +37,7 @@ __global__ void __launch_bounds__(256) k_limb_split(const u16 *__restrict__ Y, i
 #pragma unroll
     for (int e = 0; e < 8; e++) {
         int32_t a = (int32_t)((e & 1) ? w[e >> 1] >> 16 : w[e >> 1] & 0xFFFF);
+        if (a >= Q) a %= Q;                                     // rows need not be canonical
         a = a > Q / 2 ? a - Q : a;
         const int32_t a0 = ((a + 64) & 127) - 64, a1 = (a - a0) >> 7;
         lo[e >> 2] |= (uint32_t)(a0 & 0xFF) << (8 * (e & 3));

@@ -639,12 +639,25 @@ def test_dense_table_share_eval_matches_ntt_convolution(k):
     assert (out["2"][3][0] == opi).all() and (out["2"][1][0] == opk).all()
 
 
-def test_share_eval_noncanonical_inputs(ctxs):
-    """u16 inputs >= q act as their residue, as in the reference's gf3329_mul ((uint32_t)a * b % 3329, utils/gf3329.c:282-284)."""
+@pytest.mark.parametrize("mode", ["2", "1", "0"])
+def test_share_eval_noncanonical_inputs(mode):
+    """u16 inputs >= q act as their residue, as in the reference's gf3329_mul ((uint32_t)a * b % 3329, utils/gf3329.c:282-284), on every
+    share-evaluation variant (KOSK_B200_SHARE_NTT = 2: k_share_ntt2, 1: generic convolution kernel, 0: dense table GEMM)."""
+    from mpcith_kyber_kosk_b200 import KoskContext
     rng = np.random.default_rng(11)
     y = rng.integers(0, 65536, size=(9, 407), dtype=np.uint16)
     y[0] = 65535
-    got = ctxs(2).share_eval(y)
+    old = os.environ.get("KOSK_B200_SHARE_NTT")
+    os.environ["KOSK_B200_SHARE_NTT"] = mode
+    try:
+        ctx = KoskContext(2, 0, 8)
+    finally:
+        if old is None:
+            os.environ.pop("KOSK_B200_SHARE_NTT", None)
+        else:
+            os.environ["KOSK_B200_SHARE_NTT"] = old
+    got = ctx.share_eval(y)
+    ctx.close()
     for i in range(9):
         want = O.oracle_share(y[i])
         assert (got[i, 151:] == want[151:]).all()
