@@ -410,13 +410,16 @@ def run_b200(args):
         with torch.cuda.stream(st):
             h_out[0][2][:nbytes].copy_(d_pi[:nbytes], non_blocking=True)
         st.synchronize()
-        barrier()
-        t0 = time.perf_counter()
-        with torch.cuda.stream(st):
-            for _ in range(reps):
-                h_out[0][2][:nbytes].copy_(d_pi[:nbytes], non_blocking=True)
-        st.synchronize()
-        return world * nbytes * reps / allmax(time.perf_counter() - t0) / 1e9
+        best = 0.0
+        for _trial in range(3):                              # a ceiling is the best the platform was seen to do: the shared host ingest path of a
+            barrier()                                        # multi-GPU box fluctuates (a single trial once read 20 % below the e2e run that followed it)
+            t0 = time.perf_counter()
+            with torch.cuda.stream(st):
+                for _ in range(reps):
+                    h_out[0][2][:nbytes].copy_(d_pi[:nbytes], non_blocking=True)
+            st.synchronize()
+            best = max(best, world * nbytes * reps / allmax(time.perf_counter() - t0) / 1e9)
+        return best
     ceil_raw_gbs = link_ceiling(B * npi)
     ceil_wire_gbs = link_ceiling(B * ctx_e.wire_bytes)
 
