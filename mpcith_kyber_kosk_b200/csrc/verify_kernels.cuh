@@ -452,8 +452,9 @@ __global__ void __launch_bounds__(128) kv_check_parties(VerifyBufs vb, const u8 
     auto V = [&](int row) -> u16 { return __ldg(vsh + (size_t)row * SLD); };
     auto pi16 = [](const u8 *q, size_t off, size_t idx) -> u16 { return __ldg(reinterpret_cast<const u16 *>(q + off) + idx); };
     const int pos = vb.POS[(size_t)b * NP + p];
+    if (pos < 0) return;                                       // opened party: kv_check_opened
     int f = 0;
-    if (pos >= 0) {                                            // rest party, index pos in the proof's [R] arrays
+    {                                                          // rest party, index pos in the proof's [R] arrays
         for (int i = 0; i < K; i++) {
             if (V(i) != pi16(pi, L.o_sr, (size_t)pos * K + i)) f |= VF_SR;              // :232-246
             if (V(K + i) != pi16(pi, L.o_er, (size_t)pos * K + i)) f |= VF_SR;
@@ -470,49 +471,67 @@ __global__ void __launch_bounds__(128) kv_check_parties(VerifyBufs vb, const u8 
                 const int w = r / (K * M), im = r % (K * M);
                 vb.U2[((size_t)b * d.n2rows + r) * VR2LD + p] = (u16)(pi16(pi, w ? L.o_ue : L.o_us, (size_t)pos * K * M + im) % (uint32_t)Q);
             }
-    } else {
-        const int o = -1 - pos;                                // opened party, index o in the proof's [T] arrays
-        const u16 *opv = vb.OPV + ((size_t)b * NT + o) * OPLD;
-        u16 *vr = vb.VR + ((size_t)b * NT + o) * d.vrld;
-        const u16 *tc = reinterpret_cast<const u16 *>(vb.TCR + ((size_t)b * NP + p) * 32);
-        int vo = 0;
-        for (int i = 0; i < 16; i++) vr[vo++] = __ldg(tc + i);
-        const u16 *cr = vb.CR + ((size_t)b * NT + o) * d.crld;
-        for (int i = 0; i < d.nc; i++) vr[vo++] = __ldg(cr + i);
-        for (int i = 0; i < K; i++) vr[vo++] = __ldg(opv + i);                                   // beta[0..K)
-        for (int i = 0; i < K; i++) vr[vo++] = __ldg(opv + MK + i);                              // gamma[0..K)
-        for (int i = 0; i < K; i++) vr[vo++] = V(i);                                     // regenerated [s+r] share (:249-255)
-        for (int i = 0; i < K; i++) vr[vo++] = V(K + i);
-        for (int i = 0; i < K; i++) {
-            const size_t oi = (size_t)o * K + i;
-            const u16 s = pi16(pi, L.o_s, oi), e = pi16(pi, L.o_e, oi);
-            const u16 As = pi16(pi, L.o_NTTAs, oi), Ar = pi16(pi, L.o_NTTAr, oi), Te = pi16(pi, L.o_NTTe, oi);
-            if (pi16(pi, L.o_NTTs, oi) != ref_sub(V(d.n1rows + i), __ldg(opv + 2 * MK + 2 * K + i))) f |= VF_NTT;          // :273-284
-            if (Te != ref_sub(V(d.n1rows + K + i), __ldg(opv + 2 * MK + 2 * K + K + i))) f |= VF_NTT;
-            if (V(d.n1rows + 2 * K + i) != ref_add(As, Ar)) f |= VF_ASR;                                           // :304-312
-            if (V(2 * K + i) != ref_add(As, Te)) f |= VF_TREL;                                                     // :365-376
-            for (int m = 0; m < E; m++) {                                                                         // :447-466
-                if (pi16(pi, L.o_ssub, oi * E + m) != ref_sub(s, V(3 * K + i * E + m))) f |= VF_SUBETA;
-                if (pi16(pi, L.o_esub, oi * E + m) != ref_sub(e, V(3 * K + K * E + i * E + m))) f |= VF_SUBETA;
-            }
-            u16 us[M], ue[M];
-            for (int m = 0; m < M; m++) {                                                                         // :471-493
-                const u16 as_ = m == 0 ? pi16(pi, L.o_ssub, oi * E) : pi16(pi, L.o_zs, oi * M + m - 1);
-                const u16 ae_ = m == 0 ? pi16(pi, L.o_esub, oi * E) : pi16(pi, L.o_ze, oi * M + m - 1);
-                const u16 z2s = (u16)(((uint32_t)as_ * pi16(pi, L.o_ssub, oi * E + m + 1)) % (uint32_t)Q);
-                const u16 z2e = (u16)(((uint32_t)ae_ * pi16(pi, L.o_esub, oi * E + m + 1)) % (uint32_t)Q);
-                us[m] = ref_sub(z2s, pi16(pi, L.o_zs, oi * M + m));
-                ue[m] = ref_sub(z2e, pi16(pi, L.o_ze, oi * M + m));
-                if (p < D2) {
-                    vb.U2[((size_t)b * d.n2rows + i * M + m) * VR2LD + p] = (u16)(us[m] % (uint32_t)Q);
-                    vb.U2[((size_t)b * d.n2rows + K * M + i * M + m) * VR2LD + p] = (u16)(ue[m] % (uint32_t)Q);
-                }
-            }
-            for (int m = 0; m < M; m++) vr[vo++] = pi16(pi, L.o_zs, oi * M + m);
-            for (int m = 0; m < M; m++) vr[vo++] = pi16(pi, L.o_ze, oi * M + m);
-            for (int m = 0; m < M; m++) vr[vo++] = us[m];
-            for (int m = 0; m < M; m++) vr[vo++] = ue[m];
+    }
+    if (f) atomicOr(&vb.flags[b], f);
+}
+
+// The opened parties' share of V9-V15 (mlwe_verifier.cpp:249-312, :365-376, :447-493) and their view records (:584-632): one CTA per opened party,
+// one thread per record element / check.  As a branch of the thread-per-party kernel above this was a chain of some 250 dependent loads in one lane
+// of nearly every warp (0.30 ms per 1024 proofs for very little work).
+template <int K>
+__global__ void __launch_bounds__(256) kv_check_opened(VerifyBufs vb, const u8 *__restrict__ pis)
+{
+    const Layout L = make_layout(K);
+    const VDims d = make_vdims(K);
+    constexpr int ETA = (K == 2) ? 3 : 2, E = 2 * ETA + 1, M = 2 * ETA;
+    const int o = blockIdx.x * 4 + (threadIdx.x >> 6), b = blockIdx.y, tid = threadIdx.x & 63;      // four opened parties per CTA, 64 threads each
+    if (o >= NT) return;
+    const int p = vb.I[(size_t)b * NT + o];                    // kv_setup left a valid, duplicate-free set here even for a malformed proof
+    const u8 *pi = pis + L.proof_bytes * (size_t)b;
+    const u16 *vsh = vb.VSH + (size_t)b * d.nyrows * SLD + SOFF + p;
+    auto V = [&](int row) -> u16 { return __ldg(vsh + (size_t)row * SLD); };
+    auto pi16 = [](const u8 *q, size_t off, size_t idx) -> u16 { return __ldg(reinterpret_cast<const u16 *>(q + off) + idx); };
+    const u16 *opv = vb.OPV + ((size_t)b * NT + o) * OPLD;
+    u16 *vr = vb.VR + ((size_t)b * NT + o) * d.vrld;
+    const u16 *tc = reinterpret_cast<const u16 *>(vb.TCR + ((size_t)b * NP + p) * 32);
+    const u16 *cr = vb.CR + ((size_t)b * NT + o) * d.crld;
+    int f = 0;
+    // view record: commitment digest | s e f NTT_f record | beta[0..K) gamma[0..K) [s+r] [e+r] | per i: z_s z_e u_s u_e
+    for (int idx = tid; idx < 16 + d.nc; idx += 64) vr[idx] = idx < 16 ? __ldg(tc + idx) : __ldg(cr + idx - 16);
+    if (tid < 4 * K) {
+        const int kind = tid / K, i = tid % K;
+        vr[16 + d.nc + tid] = kind == 0 ? __ldg(opv + i) : kind == 1 ? __ldg(opv + MK + i) : kind == 2 ? V(i) : V(K + i);
+    }
+    if (tid < K) {
+        const int i = tid;
+        const size_t oi = (size_t)o * K + i;
+        const u16 As = pi16(pi, L.o_NTTAs, oi), Ar = pi16(pi, L.o_NTTAr, oi), Te = pi16(pi, L.o_NTTe, oi);
+        if (pi16(pi, L.o_NTTs, oi) != ref_sub(V(d.n1rows + i), __ldg(opv + 2 * MK + 2 * K + i))) f |= VF_NTT;          // :273-284
+        if (Te != ref_sub(V(d.n1rows + K + i), __ldg(opv + 2 * MK + 2 * K + K + i))) f |= VF_NTT;
+        if (V(d.n1rows + 2 * K + i) != ref_add(As, Ar)) f |= VF_ASR;                                           // :304-312
+        if (V(2 * K + i) != ref_add(As, Te)) f |= VF_TREL;                                                     // :365-376
+    }
+    if (tid < K * E) {                                                                                        // :447-466
+        const int i = tid / E, m = tid % E;
+        const size_t oi = (size_t)o * K + i;
+        if (pi16(pi, L.o_ssub, oi * E + m) != ref_sub(pi16(pi, L.o_s, oi), V(3 * K + i * E + m))) f |= VF_SUBETA;
+        if (pi16(pi, L.o_esub, oi * E + m) != ref_sub(pi16(pi, L.o_e, oi), V(3 * K + K * E + i * E + m))) f |= VF_SUBETA;
+    }
+    if (tid < K * M) {                                                                                        // :471-493
+        const int i = tid / M, m = tid % M;
+        const size_t oi = (size_t)o * K + i;
+        const u16 as_ = m == 0 ? pi16(pi, L.o_ssub, oi * E) : pi16(pi, L.o_zs, oi * M + m - 1);
+        const u16 ae_ = m == 0 ? pi16(pi, L.o_esub, oi * E) : pi16(pi, L.o_ze, oi * M + m - 1);
+        const u16 z2s = (u16)(((uint32_t)as_ * pi16(pi, L.o_ssub, oi * E + m + 1)) % (uint32_t)Q);
+        const u16 z2e = (u16)(((uint32_t)ae_ * pi16(pi, L.o_esub, oi * E + m + 1)) % (uint32_t)Q);
+        const u16 zs = pi16(pi, L.o_zs, oi * M + m), ze = pi16(pi, L.o_ze, oi * M + m);
+        const u16 us = ref_sub(z2s, zs), ue = ref_sub(z2e, ze);
+        if (p < D2) {
+            vb.U2[((size_t)b * d.n2rows + i * M + m) * VR2LD + p] = (u16)(us % (uint32_t)Q);
+            vb.U2[((size_t)b * d.n2rows + K * M + i * M + m) * VR2LD + p] = (u16)(ue % (uint32_t)Q);
         }
+        u16 *vz = vr + 16 + d.nc + 4 * K + i * 4 * M;
+        vz[m] = zs; vz[M + m] = ze; vz[2 * M + m] = us; vz[3 * M + m] = ue;
     }
     if (f) atomicOr(&vb.flags[b], f);
 }
@@ -647,6 +666,7 @@ static int verify_chunk_t(VerifyBufs &vb, const VerifyTables &vt, int B, const u
     kv_check_bg<<<dim3(MK, B), 128, 0, st>>>(vb); nl++;
     if (fork) cudaStreamWaitEvent(st, sd.join, 0);
     kv_check_parties<K><<<dim3(ptiles, B), 128, 0, st>>>(vb, d_pi); nl++;
+    kv_check_opened<K><<<dim3((NT + 3) / 4, B), 256, 0, st>>>(vb, d_pi); nl++;
     if (vt.sn) {      // recon_secrets_2ddeg over parties 0..812 (ss.cpp:56-73)
         cv = ConvArgs{}; cv.A = vb.U2; cv.C = vb.UR; cv.lda = VR2LD; cv.ldc = 256; cv.mtotal = B * d.n2rows; cv.rpp = cv.mtotal;
         cv.tw = vt.sn->tw; cv.khat = sn_kh_m256(*vt.sn, 7); cv.pre = vt.sn->wj2; cv.post = vt.sn->pr2;
