@@ -316,8 +316,8 @@ int kosk_b200_create_ex(kosk_b200_ctx **out, int k, int device, int max_chunk, i
         }
         {   // tables of the NTT-convolution share evaluation (share_ntt.cuh)
             const ShareNttHost sh = share_ntt_tables();
-            for (int i = 0; i < 256; i++)      // the kernel's compile-time DFT tables against the host construction
-                if (sh.w16f[i] != sn_make_w16(false).v[i] || sh.w16i[i] != sn_make_w16(true).v[i]) { ctx_free(c); return fail(KOSK_E_UNSUPPORTED, "share_ntt: DFT table mismatch (internal error)"); }
+            for (int j = 0; j < 16; j++)       // the kernels' compile-time twiddles w16^(+-j) against the host construction
+                if (sh.w16f[16 + j] != sn_make_tw16(false).w[j] || sh.w16i[16 + j] != sn_make_tw16(true).w[j]) { ctx_free(c); return fail(KOSK_E_UNSUPPORTED, "share_ntt: DFT table mismatch (internal error)"); }
             // one byte blob, every part 16-byte aligned
             std::vector<uint8_t> all;
             size_t offs[9]; int np = 0;

@@ -10,11 +10,14 @@
 // Per sharing: 4 forward and 11 inverse 256-point NTTs plus 11 x 4 x 256 pointwise MACs, about 115 k IMADs instead of the
 // 530 k MACs of the dense table (every value is a field element, so the result is the same canonical residue).
 // A 256-point NTT is done as 16 x 16 (n = 16 a + b, k = k1 + 16 k2): a 16-point DFT down the columns, the twiddle
-// w^(b k1), a 16-point DFT along the rows; the 16-point DFTs are plain 16 x 16 mat-vecs whose coefficients are IMAD
-// constant-bank operands.  One warp per sharing; its two half-warps run two NTTs at a time (two input blocks, then two output
-// blocks), lane = column (then row) of the 16 x 16 matrix, transposed once per NTT through shared memory.
-// Arithmetic: int32 lazy sums of at most 16 products of a residue in (-q, q) with a centered constant (|.| <= 1664), then
-// Kyber's Montgomery reduction (kyber/reduce.c:16-23, R = 2^16); all tables carry the factor R.
+// w^(b k1), a 16-point DFT along the rows; the 16-point DFTs are radix-2 networks in registers whose twiddles are compile-time
+// constants, i.e. IMAD immediates (SnDft below).  One warp per sharing; its two half-warps run two NTTs at a time (two input
+// blocks, then two output blocks), lane = column (then row) of the 16 x 16 matrix, transposed once per NTT through shared memory.
+// Arithmetic: int32 values kept unreduced wherever the interval bounds allow it (tools/exp/fft16_plan.py); reductions are Barrett
+// (a - mulhi(a, floor(2^32 / q)) q) and multiplications by constants Shoup's (s w - mulhi(s, w') q with w' = round(w 2^32 / q)), both
+// on the FMA pipe; no Montgomery factors in any table.
+// Two kernels: k_conv_ntt<NIN, NOUT, ...>, generic over the block counts (the verifier's other Toeplitz products, and the sharing with
+// KOSK_B200_SHARE_NTT=1), and k_share_ntt2, the sharing's own kernel (unequal blocks, IDP.2A pointwise stage; the default).
 #pragma once
 #include "gf_gemm.cuh"
 #include <vector>
@@ -34,28 +37,16 @@ constexpr int SN_WARPS = KOSK_SN_WARPS;                                  // rows
 constexpr int SN_TS = 18;
 constexpr int SN_LD = 24;               // int16 per k1 row of a spectrum in shared memory: 16 values (k2) + pad, so that the 128-bit row reads of a quarter-warp hit distinct banks
 
-// w16^(+-a k), centered; w16 = 17^16.  Compile-time tables: on sm_100a an IMAD takes no constant-bank operand (every c[] use became
-// a separate LDC into a register: 159 of the 1158 instructions of an inverse pass), but with the loops unrolled a value folded from a
-// constant initialiser is a 32-bit immediate of the IMAD itself.
-struct SnW16 { int32_t v[256]; };
+// compile-time helpers for the constant tables (on sm_100a an IMAD takes no constant-bank operand: a value folded from a constexpr table in an
+// unrolled loop is a 32-bit immediate of the IMAD itself, a __constant__ array element a separate LDC)
 constexpr uint32_t sn_cpow(uint32_t b, uint32_t e) { uint32_t r = 1; b %= Q; while (e) { if (e & 1) r = r * b % Q; b = b * b % Q; e >>= 1; } return r; }
 constexpr int32_t sn_ccenter(uint32_t v) { return (int32_t)(v % Q) > Q / 2 ? (int32_t)(v % Q) - Q : (int32_t)(v % Q); }
-constexpr SnW16 sn_make_w16(bool inv)
-{
-    SnW16 t{};
-    const uint32_t om16 = sn_cpow(17, 16), w = inv ? sn_cpow(om16, Q - 2) : om16;
-    for (int a = 0; a < 16; a++) for (int k = 0; k < 16; k++) t.v[a * 16 + k] = sn_ccenter(sn_cpow(w, (uint32_t)(a * k)));
-    return t;
-}
-__device__ constexpr SnW16 c_sn_w16f_tab = sn_make_w16(false), c_sn_w16i_tab = sn_make_w16(true);
-#define c_sn_w16f c_sn_w16f_tab.v
-#define c_sn_w16i c_sn_w16i_tab.v
 
 // Modular arithmetic of the kernel (all on the FMA pipe, no shifts or sign extensions on the ALU pipe):
 //   sn_barrett(a)      a mod q          in (-105, 2q)   for |a| < 2^28:  a - mulhi(a, floor(2^32 / q)) q
 //   sn_shoup(s, w, w') s w mod q        in (-105, q + 105) for |s| < 2^28, a constant w in [-1664, 1664] and its companion
 //                                       w' = round(w 2^32 / q):  s w - mulhi(s, w') q  (32-bit wrapping; the true value is small)
-// Lazy sums of at most 16 products of such values with centered constants stay below 2^28 (16 x 6658 x 1664 = 1.8e8).
+// (for |a|, |s| up to 2^31 the results stay within (-q/4, 2q + q/2) and (-q/4, 5q/4): what the DFT networks below rely on)
 constexpr int32_t SN_BARRETT_M = (int32_t)((1ull << 32) / Q);
 __device__ __forceinline__ int32_t sn_barrett(int32_t a) { return a - __mulhi(a, SN_BARRETT_M) * Q; }
 __device__ __forceinline__ int32_t sn_shoup(int32_t s, int32_t w, int32_t wp)
