@@ -436,7 +436,8 @@ __global__ void __launch_bounds__(128) kv_open(VerifyBufs vb)
 
 // Per-party checks against the regenerated sharings (planes VSH, same row order as YV) and construction of the
 // inputs of the last two steps: the u^(2d) rows for recon_secrets_2ddeg (mlwe_verifier.cpp:469-556) and the view
-// records of the opened parties (:584-630).  One thread per (proof, party).
+// records of the opened parties (:584-630).  kv_check_parties: the rest set, one thread per (proof, party);
+// kv_check_opened (below): the opened set, one thread per record element / check.
 template <int K>
 __global__ void __launch_bounds__(128) kv_check_parties(VerifyBufs vb, const u8 *__restrict__ pis)
 {
@@ -447,8 +448,7 @@ __global__ void __launch_bounds__(128) kv_check_parties(VerifyBufs vb, const u8 
     if (p >= NP) return;
     const u8 *pi = pis + L.proof_bytes * (size_t)b;
     const u16 *vsh = vb.VSH + (size_t)b * d.nyrows * SLD + SOFF + p;
-    // every source of this kernel is read-only here: loads through the non-coherent path may be hoisted above the stores of the long opened-party
-    // branch (vr, U2), which otherwise serialise into a chain of some 250 dependent L2 round trips per opened party
+    // every source of this kernel is read-only here: loads through the non-coherent path may be hoisted above the U2 stores
     auto V = [&](int row) -> u16 { return __ldg(vsh + (size_t)row * SLD); };
     auto pi16 = [](const u8 *q, size_t off, size_t idx) -> u16 { return __ldg(reinterpret_cast<const u16 *>(q + off) + idx); };
     const int pos = vb.POS[(size_t)b * NP + p];
@@ -475,8 +475,8 @@ __global__ void __launch_bounds__(128) kv_check_parties(VerifyBufs vb, const u8 
     if (f) atomicOr(&vb.flags[b], f);
 }
 
-// The opened parties' share of V9-V15 (mlwe_verifier.cpp:249-312, :365-376, :447-493) and their view records (:584-632): one CTA per opened party,
-// one thread per record element / check.  As a branch of the thread-per-party kernel above this was a chain of some 250 dependent loads in one lane
+// The opened parties' share of V9-V15 (mlwe_verifier.cpp:249-312, :365-376, :447-493) and their view records (:584-632): 64 threads per opened party
+// (four parties per CTA), one thread per record element / check.  As a branch of the thread-per-party kernel above this was a chain of some 250 dependent loads in one lane
 // of nearly every warp (0.30 ms per 1024 proofs for very little work).
 template <int K>
 __global__ void __launch_bounds__(256) kv_check_opened(VerifyBufs vb, const u8 *__restrict__ pis)
