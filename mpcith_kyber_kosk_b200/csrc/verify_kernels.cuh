@@ -211,6 +211,82 @@ __global__ void __launch_bounds__(320) kv_eval_opened(VerifyBufs vb)
     }
 }
 
+// Batch form of kv_eval_opened on the dot-product instruction: thread = two records (one opened party: f and NTT_f), held as packed int16 pairs
+// (f[k], f[k+1]); the power table as signed limbs w = 64 w1 + w0 packed (w0[k], w0[k+1], w1[k], w1[k+1]) per word, so that one broadcast LDS.128
+// (eight powers of one challenge) feeds sixteen IDP.2A -- four times less shared-memory traffic per multiply-add than kv_eval_opened, which reads one
+// LDS.128 per four IMADs and is bound by the shared-memory pipe (32 % of the IMAD peak).  The k = 0 entries of the table are zero: the constant term
+// is added explicitly (f[0] for beta / gamma, f[71] for the r columns: the c0 quirk).
+template <int K>
+__global__ void __launch_bounds__(160, 4) kv_eval_opened_idp(VerifyBufs vb)
+{
+    constexpr int F = MK + 2 * K + 1, NA = MK + 2 * K, FW = (F + 1) / 2, FWP = (FW + 3) & ~3;      // words per challenge row, padded to LDS.128
+    const VDims d = make_vdims(K);
+    const int b = blockIdx.x, tid = threadIdx.x;
+    __shared__ __align__(16) uint32_t spk[NA][FWP];
+    for (int i = tid; i < NA * FWP; i += 160) {
+        const int j = i / FWP, wd = i % FWP;
+        uint32_t word = 0;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int kk = 2 * wd + h;
+            if (kk >= 1 && kk < F) {
+                const int v = gf_center(vb.PW[(size_t)b * NA * F + j * F + kk]), w0 = ((v + 32) & 63) - 32, w1 = (v - w0) / 64;
+                word |= ((uint32_t)(uint8_t)(int8_t)w0) << (8 * h) | ((uint32_t)(uint8_t)(int8_t)w1) << (16 + 8 * h);
+            }
+        }
+        spk[j][wd] = word;
+    }
+    __syncthreads();
+    if (tid >= NT) return;
+    const int i = tid;                                          // opened party: rows f (half 0) and NTT_f (half 1)
+    const u16 *f0 = vb.CR + ((size_t)b * NT + i) * d.crld + 2 * K, *f1 = f0 + F;
+    u16 *out = vb.OPV + ((size_t)b * NT + i) * OPLD;
+    uint32_t p0[FWP], p1[FWP];                                  // packed centered pairs (f[2w], f[2w+1])
+#pragma unroll
+    for (int wd = 0; wd < FWP; wd++) {
+        uint32_t a = 0, c = 0;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int kk = 2 * wd + h;
+            if (kk < F) {
+                a |= ((uint32_t)gf_center(f0[kk] % (uint32_t)Q) & 0xFFFFu) << (16 * h);
+                c |= ((uint32_t)gf_center(f1[kk] % (uint32_t)Q) & 0xFFFFu) << (16 * h);
+            }
+        }
+        p0[wd] = a; p1[wd] = c;
+    }
+    const u16 r00 = f0[0], r071 = f0[MK + 1], r10 = f1[0], r171 = f1[MK + 1];
+    const bool can00 = r00 < Q, can071 = r071 < Q, can10 = r10 < Q, can171 = r171 < Q;
+    const int32_t c00 = gf_center(r00 % (uint32_t)Q), c071 = gf_center(r071 % (uint32_t)Q), c10 = gf_center(r10 % (uint32_t)Q), c171 = gf_center(r171 % (uint32_t)Q);
+    auto put = [&](int half, int j, u16 res) { if (j < MK) out[half * MK + j] = res; else out[2 * MK + half * 2 * K + (j - MK)] = res; };
+    auto slow = [&](const u16 *f, int j) -> u16 {              // non-canonical first term: the reference's u16 chain, verbatim
+        u16 acc = f[j < MK ? 0 : MK + 1];
+        for (int kk = 1; kk < F; kk++) {
+            const uint32_t word = spk[j][kk >> 1];
+            const int w = 64 * (int)(int8_t)(word >> (16 + 8 * (kk & 1))) + (int)(int8_t)(word >> (8 * (kk & 1)));
+            acc = ref_add(acc, (u16)(((uint32_t)gf_canon(w) * f[kk]) % (uint32_t)Q));
+        }
+        return acc;
+    };
+#pragma unroll 1
+    for (int j = 0; j < NA; j++) {
+        int32_t lo0 = 0, hi0 = 0, lo1 = 0, hi1 = 0;
+#pragma unroll
+        for (int w4 = 0; w4 < FWP / 4; w4++) {
+            const uint4 w = *reinterpret_cast<const uint4 *>(&spk[j][4 * w4]);
+            const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                lo0 = __dp2a_lo((int)p0[4 * w4 + e], (int)ww[e], lo0); hi0 = __dp2a_hi((int)p0[4 * w4 + e], (int)ww[e], hi0);
+                lo1 = __dp2a_lo((int)p1[4 * w4 + e], (int)ww[e], lo1); hi1 = __dp2a_hi((int)p1[4 * w4 + e], (int)ww[e], hi1);
+            }
+        }
+        const bool beta = j < MK;
+        put(0, j, (beta ? can00 : can071) ? (u16)gf_canon(lo0 + 64 * hi0 + (beta ? c00 : c071)) : slow(f0, j));
+        put(1, j, (beta ? can10 : can171) ? (u16)gf_canon(lo1 + 64 * hi1 + (beta ? c10 : c171)) : slow(f1, j));
+    }
+}
+
 // Row gathers for the table / interpolation contractions (values reduced mod q exactly where the reference
 // reduces them: gf3329_mul in recon_* and the NTL ZZ_p assignment in the interpolation inputs).
 //   ABG[j*2+w][p]  p<407: beta/gamma share of party p      (mlwe_verifier.cpp:97-108)
@@ -608,7 +684,8 @@ static int verify_chunk_t(VerifyBufs &vb, const VerifyTables &vt, int B, const u
         k_hash_records<NC><<<dim3(2, B), 128, 0, st>>>(hs, vb.TCR, nullptr, 0, 0); nl++;
     }
     { int fc, ft; fs_launch_dims(B, fc, ft); k_fs1<K><<<fc, ft, 0, st>>>(vb.TCR, vb.PW, B); nl++; }
-    kv_eval_opened<K><<<B, 320, 0, st>>>(vb); nl++;
+    if (B >= 64) { kv_eval_opened_idp<K><<<B, 160, 0, st>>>(vb); nl++; }      // batches: two records per thread on IDP.2A; few proofs: one record per thread (latency)
+    else { kv_eval_opened<K><<<B, 320, 0, st>>>(vb); nl++; }
     // ---- side chain (independent of the challenges) ----
     kv_lagrange<<<B, 256, 0, s2>>>(vb, vt.inv, vt.fact); nl++;
     kv_gather<K><<<dim3(d.n1rows + d.n2rows, B), 128, 0, s2>>>(vb, d_pi, 2 * MK); nl++;
